@@ -1,0 +1,148 @@
+"""ctypes front-end of the CPU oracle (oracle/ggb_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, bench.py's cpu_baseline and
+``--impl reference`` legs, and __graft_entry__.smoke().  Nothing under
+ggmlsharp_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libggb_oracle.so")
+
+F32, F16, Q4_0, Q4_1, Q8_0, Q8_1 = 0, 1, 2, 3, 8, 9
+TYPE_SIZE = {F32: 4, F16: 2, Q4_0: 20, Q4_1: 24, Q8_0: 36, Q8_1: 44}
+BLCK_SIZE = {F32: 1, F16: 1, Q4_0: 32, Q4_1: 32, Q8_0: 32, Q8_1: 32}
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "ggb_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return _SO
+
+
+class _MM(C.Structure):
+    _fields_ = [("type", C.c_int),
+                ("ne0", C.c_int64 * 4), ("nb0", C.c_uint64 * 4), ("src0", C.c_void_p),
+                ("ne1", C.c_int64 * 4), ("nb1", C.c_uint64 * 4), ("src1", C.c_void_p),
+                ("ned", C.c_int64 * 4), ("nbd", C.c_uint64 * 4), ("dst", C.c_void_p),
+                ("wdata", C.c_void_p), ("wsize", C.c_size_t), ("nth", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_mul_mat_2d.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+        _lib.orc_mul_mat.argtypes = [C.POINTER(_MM)]
+        _lib.orc_mul_mat_work_size.argtypes = [C.c_int, C.c_int64]
+        _lib.orc_mul_mat_work_size.restype = C.c_size_t
+        _lib.orc_quantize_rows.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        _lib.orc_dequantize_rows.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        _lib.orc_f32_to_f16_row.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        _lib.orc_f16_to_f32_row.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        for n in ("orc_vec_dot_f32", "orc_vec_dot_f16", "orc_vec_dot_q4_0_q8_0", "orc_vec_dot_q4_1_q8_1"):
+            getattr(_lib, n).argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def row_bytes(t, k):
+    assert k % BLCK_SIZE[t] == 0
+    return TYPE_SIZE[t] * (k // BLCK_SIZE[t])
+
+
+def quantize_rows(t, x):
+    """x: float32 [nrows, k] -> uint8 [nrows, row_bytes] in the reference's block layout."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[None, :]
+    nrows, k = x.shape
+    out = np.zeros((nrows, row_bytes(t, k)), dtype=np.uint8)
+    rc = lib().orc_quantize_rows(t, _p(x), _p(out), nrows, k)
+    assert rc == 0, rc
+    return out
+
+
+def dequantize_rows(t, q, k):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    if q.ndim == 1:
+        q = q[None, :]
+    nrows = q.shape[0]
+    out = np.zeros((nrows, k), dtype=np.float32)
+    rc = lib().orc_dequantize_rows(t, _p(q), _p(out), nrows, k)
+    assert rc == 0, rc
+    return out
+
+
+def f32_to_f16(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros(x.shape, dtype=np.uint16)
+    lib().orc_f32_to_f16_row(_p(x), _p(out), x.size)
+    return out
+
+
+def f16_to_f32(h):
+    h = np.ascontiguousarray(h, dtype=np.uint16)
+    out = np.zeros(h.shape, dtype=np.float32)
+    lib().orc_f16_to_f32_row(_p(h), _p(out), h.size)
+    return out
+
+
+def encode_weights(t, w):
+    """float32 [M, K] -> bytes of a src0 tensor of type t as uint8 [M, row_bytes]."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    if t == F32:
+        return w.view(np.uint8).reshape(w.shape[0], -1).copy()
+    if t == F16:
+        return f32_to_f16(w).view(np.uint8).reshape(w.shape[0], -1).copy()
+    return quantize_rows(t, w)
+
+
+def mul_mat_2d(t, wbytes, M, K, x, nth=1):
+    """dst[N][M] of ggml_mul_mat(W, X) for contiguous W (M rows of K, type t) and X float32 [N, K]."""
+    wbytes = np.ascontiguousarray(wbytes)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[None, :]
+    N = x.shape[0]
+    assert x.shape[1] == K and wbytes.nbytes == M * row_bytes(t, K)
+    y = np.zeros((N, M), dtype=np.float32)
+    rc = lib().orc_mul_mat_2d(t, _p(wbytes), M, K, _p(x), N, _p(y), nth)
+    assert rc == 0, rc
+    return y
+
+
+def mul_mat_strided(t, src0, ne0, nb0, src1, ne1, nb1, dst, ned, nbd, nth=1):
+    """Full ggml_compute_forward_mul_mat with explicit ne/nb (numpy buffers as backing store)."""
+    p = _MM()
+    p.type = t
+    p.nth = nth
+    for i in range(4):
+        p.ne0[i], p.nb0[i] = ne0[i], nb0[i]
+        p.ne1[i], p.nb1[i] = ne1[i], nb1[i]
+        p.ned[i], p.nbd[i] = ned[i], nbd[i]
+    p.src0, p.src1, p.dst = src0.ctypes.data, src1.ctypes.data, dst.ctypes.data
+    nel1 = int(np.prod(ne1))
+    ws = lib().orc_mul_mat_work_size(t, nel1)
+    wbuf = np.zeros(max(ws, 1), dtype=np.uint8)
+    p.wdata, p.wsize = wbuf.ctypes.data, ws
+    rc = lib().orc_mul_mat(C.byref(p))
+    assert rc == 0, rc
+    return dst
+
+
+def vec_dot(name, n, x, y):
+    s = np.zeros(1, dtype=np.float32)
+    getattr(lib(), "orc_vec_dot_" + name)(n, _p(s), _p(np.ascontiguousarray(x)), _p(np.ascontiguousarray(y)))
+    return float(s[0])

@@ -1,0 +1,88 @@
+"""The C oracle against the committed golden vectors (tests/golden/make_golden.py,
+an independent pure-Python restatement of Ggml.cs) and SURVEY.md Appendix B KATs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as orc
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _f32(h):
+    return np.frombuffer(bytes.fromhex(h), dtype=np.float32)
+
+
+@pytest.fixture(scope="module")
+def kats():
+    with open(os.path.join(G, "quant_kat.json")) as f:
+        return json.load(f)["blocks"]
+
+
+@pytest.mark.parametrize("t,key", [(orc.Q4_0, "q4_0"), (orc.Q4_1, "q4_1"), (orc.Q8_0, "q8_0"), (orc.Q8_1, "q8_1")])
+def test_quantize_kats_bit_exact(kats, t, key):
+    for b in kats:
+        got = orc.quantize_rows(t, _f32(b["x"])).tobytes().hex()
+        assert got == b[key], (b["name"], key)
+
+
+def test_appendix_b_literals(kats):
+    # SURVEY.md Appendix B (derived by hand from Ggml.cs:334-377, 487-528)
+    x = np.arange(32, dtype=np.float32) - 16
+    assert orc.quantize_rows(orc.Q4_0, x).tobytes().hex() == "000000400021224344656687" + "88a9aacbccedeeff"
+    # ties-to-even, not C roundf: with roundf the bytes would be 00 11 22 33 ...
+    assert orc.quantize_rows(orc.Q4_0, x).tobytes().hex() != "00000040" + "0011223344556677" + "98a9bacbdcedfeff"
+    z = np.zeros(32, dtype=np.float32)
+    assert orc.quantize_rows(orc.Q4_0, z).tobytes().hex() == "00000080" + "88" * 16      # d = -0.0f
+
+
+@pytest.mark.parametrize("t,key", [(orc.Q4_0, "deq4_0"), (orc.Q4_1, "deq4_1")])
+def test_dequantize_kats_bit_exact(kats, t, key):
+    src = {"deq4_0": "q4_0", "deq4_1": "q4_1"}[key]
+    for b in kats:
+        q = np.frombuffer(bytes.fromhex(b[src]), dtype=np.uint8)
+        got = orc.dequantize_rows(t, q, 32)
+        assert got.tobytes().hex() == b[key], b["name"]
+
+
+def test_f16_conversions_match_numpy():
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.standard_normal(20000).astype(np.float32) * s for s in (1e-8, 1e-5, 1e-3, 1, 100, 7e4)]
+                       + [np.array([0, -0.0, 65504, 65519.99, 65520, 2.0**-24, 2.0**-25, 2.0**-25 * 1.0001,
+                                    6.1e-5, np.inf, -np.inf], dtype=np.float32)])
+    with np.errstate(over="ignore"):
+        want = x.astype(np.float16).view(np.uint16)
+    np.testing.assert_array_equal(orc.f32_to_f16(x), want)
+    h = np.arange(65536, dtype=np.uint16)
+    got = orc.f16_to_f32(h)
+    ref = h.view(np.float16).astype(np.float32)
+    np.testing.assert_array_equal(got.view(np.uint32)[~np.isnan(ref)], ref.view(np.uint32)[~np.isnan(ref)])
+
+
+@pytest.mark.parametrize("t,key,wkey", [(orc.F32, "f32", "W"), (orc.F16, "f16", "W_f16"),
+                                        (orc.Q4_0, "q4_0", "W_q4_0"), (orc.Q4_1, "q4_1", "W_q4_1")])
+@pytest.mark.parametrize("nth", [1, 4])
+def test_mul_mat_small_golden_bit_exact(t, key, wkey, nth):
+    with open(os.path.join(G, "mul_mat_small.json")) as f:
+        g = json.load(f)
+    M, K, N = g["M"], g["K"], g["N"]
+    wb = np.frombuffer(bytes.fromhex(g[wkey]), dtype=np.uint8)
+    X = _f32(g["X"]).reshape(N, K)
+    # the weight bytes themselves: oracle encode == golden encode
+    np.testing.assert_array_equal(orc.encode_weights(t, _f32(g["W"]).reshape(M, K)).ravel(), wb)
+    got = orc.mul_mat_2d(t, wb, M, K, X, nth=nth)
+    assert got.tobytes().hex() == g[key]
+
+
+def test_quantize_roundtrip_properties():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((64, 256)).astype(np.float32)
+    for t, tol in ((orc.Q4_0, 1 / 8), (orc.Q4_1, 0.5 / 15)):  # Q4_0: clamp at +8 -> 15 costs up to |d|
+        q = orc.quantize_rows(t, x)
+        y = orc.dequantize_rows(t, q, 256)
+        xb = x.reshape(64, 8, 32)
+        rngs = np.abs(xb).max(-1) if t == orc.Q4_0 else (xb.max(-1) - xb.min(-1))
+        err = np.abs(y.reshape(64, 8, 32) - xb).max(-1)
+        assert (err <= rngs * tol * 1.01 + 1e-12).all()
