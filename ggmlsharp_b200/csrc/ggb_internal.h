@@ -1,0 +1,74 @@
+// Internal declarations shared by the CUDA translation units of libggb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/ggb200.h"
+
+#define GGB_QK 32
+
+namespace ggb {
+
+// ---- error plumbing (ggb_shim.cu) ----
+int set_error(int code, const char *fmt, ...);
+void count_launch(int n = 1);
+#define GGB_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return ggb::set_error(GGB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+static inline size_t type_size(int t) {
+    switch (t) { case GGML_TYPE_F32: return 4; case GGML_TYPE_F16: return 2; case GGML_TYPE_Q4_0: return 20;
+                 case GGML_TYPE_Q4_1: return 24; case GGML_TYPE_Q8_0: return 36; case GGML_TYPE_Q8_1: return 44;
+                 case GGML_TYPE_I8: return 1; case GGML_TYPE_I16: return 2; case GGML_TYPE_I32: return 4; default: return 0; }
+}
+static inline int blck_size(int t) {
+    switch (t) { case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_1: case GGML_TYPE_Q8_0: case GGML_TYPE_Q8_1: return GGB_QK; default: return 1; }
+}
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- codecs (ggb_codecs.cu) ----
+// reference-layout row codecs; rows of k elements, src row stride ldx elements, dst rows packed
+int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int64_t nrows, int64_t k, cudaStream_t s);
+int launch_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k, cudaStream_t s);
+
+// Activation staging for mul_mat (the reference's INIT phase, Ggml.cs:6362-6379 / 6641-6655), device-private layouts:
+//   Q4_0/Q4_1 weights: "Q8P" rows  [kb x 16 B even quants][kb x 16 B odd quants][kb x {float d; int sum}]
+//   F16 weights:       K halfs (RNE), F32 weights: K floats (copied so every row is 16-byte aligned and dense)
+size_t act_row_bytes(int wtype, int64_t K);
+struct ActNode { const float *x; long long ldx_bytes; uint8_t *out; int N; int blk0; };
+struct ActBatch { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; ActNode node[64]; };
+int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl);
+// batched path: activations as dense fp16 [Npad][K] holding d * q (the value the reference's dot multiplies by)
+int launch_act_f16_dequant(int wtype, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s);
+
+// ---- GEMV (ggb_gemv.cu) ----
+struct GemvNode { const uint8_t *W; const uint8_t *xq; float *y; int M; int ldy; int g0; int ngroups; };
+struct GemvBatch {
+    int n_nodes, total_groups;
+    int type, ncols;
+    int K, row_bytes;          // row_bytes = bytes of K elements
+    long long nb01;
+    int rs, nchunk, chunk_bytes;
+    int stage_bytes, depth;
+    int xcol_bytes;
+    int async;                 // 1: cp.async.bulk staging (16-byte aligned rows), 0: plain-load staging
+    int n_peers;
+    long long peer_delta[7];   // byte offset from a node's y to the same element of peer p's copy
+    GemvNode node[64];
+};
+int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl);
+int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase_probe);
+int gemv_num_ctas();
+
+// ---- GEMM (ggb_gemm.cu): tcgen05 batched path ----
+struct GemmArgs {
+    int type; int64_t M, K, N; const void *W; int64_t nb01; const __half *Xh; int64_t Npad;
+    float *Y; int64_t ldy; int n_peers; float *ypeer[7];
+};
+bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W);
+size_t gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
+int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s);
+
+int device_sm_count();
+
+} // namespace ggb

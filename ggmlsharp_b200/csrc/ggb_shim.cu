@@ -1,0 +1,733 @@
+// libggb200.so -- the C ABI of include/ggb200.h: device state, the pool behind a ggml_context,
+// weight residency, and the CUDA-stream executor that replaces the reference's CPU thread pool for
+// MUL_MAT graph nodes (ggml_graph_compute, Ggml.cs:3209-3736).
+//
+// There is no CPU fallback anywhere in this file: every compute entry point needs an sm_100 device.
+#include "ggb_internal.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+namespace ggb {
+
+static thread_local char g_err[512] = "";
+static std::mutex g_mu;
+static bool g_inited = false;
+static int g_device = 0, g_sms = 148;
+static cudaStream_t g_stream = nullptr;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static ggb_stats g_stats = {};
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+void count_launch(int n) { g_stats.kernel_launches += (uint64_t)n; }
+int device_sm_count() { return g_sms; }
+
+static int ensure_init()
+{
+    if (g_inited) return GGB_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return set_error(GGB_E_NODEVICE, "no CUDA device (%s); libggb200 has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    }
+    int dev = 0;
+    if (const char *s = getenv("GGB200_DEVICE")) dev = atoi(s);
+    else if (const char *lr = getenv("LOCAL_RANK")) dev = atoi(lr) % n;      // one process per GPU under torchrun
+    if (dev < 0 || dev >= n) return set_error(GGB_E_NODEVICE, "GGB200_DEVICE=%d but %d device(s) present", dev, n);
+    GGB_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp p;
+    GGB_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (p.major != 10) return set_error(GGB_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, p.major, p.minor);
+    g_device = dev; g_sms = p.multiProcessorCount;
+    GGB_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    GGB_CUDA(cudaEventCreate(&g_ev0));
+    GGB_CUDA(cudaEventCreate(&g_ev1));
+    g_inited = true;
+    return GGB_OK;
+}
+
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-level batch: plan + launch
+// ------------------------------------------------------------------------------------------------
+
+static inline bool use_gemm(const ggb_dev_mm &m)
+{
+    return m.N >= 16 && gemm_supported(m.type, m.M, m.K, m.N, m.nb01, m.W);
+}
+static size_t mm_ws_bytes(const ggb_dev_mm &m)
+{
+    if (use_gemm(m)) return align_up(gemm_workspace_bytes(m.type, m.M, m.K, m.N), 256);
+    return align_up((size_t)m.N * act_row_bytes(m.type, m.K), 256);
+}
+// upper bound that does not depend on operand addresses (for sizing before buffers exist)
+static size_t mm_ws_bytes_bound(int type, int64_t M, int64_t K, int64_t N)
+{
+    return std::max(align_up(gemm_workspace_bytes(type, M, K, N), 256), align_up((size_t)N * act_row_bytes(type, K), 256));
+}
+
+static int check_mm(const ggb_dev_mm &m)
+{
+    if (m.type != GGML_TYPE_F32 && m.type != GGML_TYPE_F16 && m.type != GGML_TYPE_Q4_0 && m.type != GGML_TYPE_Q4_1)
+        return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (F32, F16, Q4_0, Q4_1)", m.type);
+    if (m.M < 0 || m.N < 0 || m.K <= 0) return set_error(GGB_E_INVALID, "mul_mat: bad shape M=%lld N=%lld K=%lld", (long long)m.M, (long long)m.N, (long long)m.K);
+    if (m.K % blck_size(m.type)) return set_error(GGB_E_INVALID, "mul_mat: ne00=%lld %% 32 != 0 (Ggml.cs:6694)", (long long)m.K);
+    const int64_t rb = m.K / blck_size(m.type) * (int64_t)type_size(m.type);
+    if (m.nb01 < rb) return set_error(GGB_E_INVALID, "mul_mat: nb01=%lld < row bytes %lld", (long long)m.nb01, (long long)rb);
+    if ((m.ldx_bytes & 3) || (m.ldy_bytes & 3) || m.ldx_bytes < 4 * m.K || (m.N > 1 && m.ldy_bytes < 4 * m.M))
+        return set_error(GGB_E_INVALID, "mul_mat: bad activation/output row stride");
+    if (m.n_peers < 0 || m.n_peers > 7) return set_error(GGB_E_INVALID, "mul_mat: n_peers=%d", m.n_peers);
+    if (m.M > 0 && m.N > 0 && (!m.W || !m.X || !m.Y)) return set_error(GGB_E_INVALID, "mul_mat: null operand");
+    return GGB_OK;
+}
+
+static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    if (count <= 0) return GGB_OK;
+    std::vector<size_t> off(count + 1, 0);
+    for (int i = 0; i < count; i++) {
+        int rc = check_mm(mm[i]);
+        if (rc) return rc;
+        off[i + 1] = off[i] + mm_ws_bytes(mm[i]);
+    }
+    if (off[count] > ws_bytes) return set_error(GGB_E_INVALID, "mul_mat: workspace %zu B < required %zu B", ws_bytes, off[count]);
+    if (off[count] && (reinterpret_cast<uintptr_t>(ws) & 255)) return set_error(GGB_E_INVALID, "mul_mat: workspace must be 256-byte aligned");
+    uint8_t *wsb = static_cast<uint8_t *>(ws);
+
+    // ---- batched (tensor-core) nodes: one launch pair each ----
+    std::vector<int> gemv_idx;
+    for (int i = 0; i < count; i++) {
+        const ggb_dev_mm &m = mm[i];
+        if (m.M == 0 || m.N == 0) continue;
+        if (!use_gemm(m)) { gemv_idx.push_back(i); continue; }
+        const int64_t Npad = (m.N + 15) / 16 * 16;
+        __half *xh = reinterpret_cast<__half *>(wsb + off[i]);
+        int rc = launch_act_f16_dequant(m.type, m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s);
+        if (rc) return rc;
+        GemmArgs a = {};
+        a.type = m.type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
+        a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
+        for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
+        rc = launch_gemm(a, wsb + off[i] + align_up((size_t)Npad * m.K * 2, 256), s);
+        if (rc) return rc;
+    }
+
+    // ---- single-token nodes: group by (type, K), fuse each group into one act launch + GEMV launches ----
+    std::vector<char> done(count, 0);
+    for (size_t a0 = 0; a0 < gemv_idx.size(); a0++) {
+        const int i0 = gemv_idx[a0];
+        if (done[i0]) continue;
+        std::vector<int> grp;
+        for (size_t a1 = a0; a1 < gemv_idx.size(); a1++) {
+            const int i = gemv_idx[a1];
+            if (!done[i] && mm[i].type == mm[i0].type && mm[i].K == mm[i0].K) { grp.push_back(i); done[i] = 1; }
+        }
+        const int type = mm[i0].type; const int64_t K = mm[i0].K;
+        const size_t arow = act_row_bytes(type, K);
+        const bool quant = type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1;
+        // activation staging (INIT phase)
+        for (size_t c0 = 0; c0 < grp.size(); c0 += 64) {
+            ActBatch ab = {};
+            ab.K = (int)K; ab.kb = (int)(K / GGB_QK); ab.row_bytes = (int)arow; ab.wtype = type; ab.vec16 = 1;
+            int tot = 0;
+            for (size_t c = c0; c < std::min(grp.size(), c0 + 64); c++) {
+                const ggb_dev_mm &m = mm[grp[c]];
+                ActNode &an = ab.node[ab.n_nodes++];
+                an.x = m.X; an.ldx_bytes = m.ldx_bytes; an.out = wsb + off[grp[c]]; an.N = (int)m.N; an.blk0 = tot;
+                tot += quant ? (int)(m.N * ab.kb) : (int)m.N;
+                if ((reinterpret_cast<uintptr_t>(m.X) & 15) || (m.ldx_bytes & 15)) ab.vec16 = 0;
+            }
+            ab.total_blk = tot;
+            int rc = launch_act_batch(ab, s, true);
+            if (rc) return rc;
+        }
+        // column passes of 8/4/2/1, grouped by what must be uniform inside one launch
+        struct Pass { int i, col0, nc; };
+        std::vector<Pass> passes;
+        for (int i : grp) {
+            int64_t c = 0;
+            while (c < mm[i].N) { int nc = mm[i].N - c >= 8 ? 8 : mm[i].N - c >= 4 ? 4 : mm[i].N - c >= 2 ? 2 : 1; passes.push_back({i, (int)c, nc}); c += nc; }
+        }
+        std::vector<char> pdone(passes.size(), 0);
+        bool first_launch = true;
+        for (size_t p0 = 0; p0 < passes.size(); p0++) {
+            if (pdone[p0]) continue;
+            const ggb_dev_mm &m0 = mm[passes[p0].i];
+            GemvBatch gb = {};
+            int rc = gemv_plan(gb, type, K, m0.nb01, passes[p0].nc, m0.W);
+            if (rc) return rc;
+            gb.n_peers = m0.n_peers;
+            for (int p = 0; p < m0.n_peers; p++) gb.peer_delta[p] = (long long)(reinterpret_cast<char *>(m0.Y_peer[p]) - reinterpret_cast<char *>(m0.Y));
+            auto compatible = [&](const Pass &ps) {
+                const ggb_dev_mm &m = mm[ps.i];
+                if (ps.nc != passes[p0].nc || m.nb01 != m0.nb01 || m.n_peers != m0.n_peers) return false;
+                if (((reinterpret_cast<uintptr_t>(m.W) & 15) == 0) != ((reinterpret_cast<uintptr_t>(m0.W) & 15) == 0)) return false;
+                for (int p = 0; p < m.n_peers; p++)
+                    if ((long long)(reinterpret_cast<char *>(m.Y_peer[p]) - reinterpret_cast<char *>(m.Y)) != gb.peer_delta[p]) return false;
+                return true;
+            };
+            auto flush = [&]() -> int {
+                if (!gb.n_nodes) return GGB_OK;
+                int r = launch_gemv_batch(gb, s, first_launch);
+                first_launch = false;
+                gb.n_nodes = 0; gb.total_groups = 0;
+                return r;
+            };
+            for (size_t p1 = p0; p1 < passes.size(); p1++) {
+                if (pdone[p1] || !compatible(passes[p1])) continue;
+                pdone[p1] = 1;
+                const ggb_dev_mm &m = mm[passes[p1].i];
+                GemvNode &nd = gb.node[gb.n_nodes++];
+                nd.W = static_cast<const uint8_t *>(m.W);
+                nd.xq = wsb + off[passes[p1].i] + (size_t)passes[p1].col0 * arow;
+                nd.y = m.Y + (size_t)passes[p1].col0 * (m.ldy_bytes / 4);
+                nd.M = (int)m.M; nd.ldy = (int)(m.ldy_bytes / 4);
+                nd.g0 = gb.total_groups; nd.ngroups = (int)((m.M + gb.rs - 1) / gb.rs);
+                gb.total_groups += nd.ngroups;
+                if (gb.n_nodes == 64) { rc = flush(); if (rc) return rc; }
+            }
+            rc = flush();
+            if (rc) return rc;
+        }
+    }
+    return GGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pool + executor
+// ------------------------------------------------------------------------------------------------
+
+struct Mirror { void *dptr; size_t bytes; };
+
+struct DevArena {           // grow-only device scratch, reset per compute
+    uint8_t *base = nullptr; size_t cap = 0, used = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return GGB_OK;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        const size_t want = align_up(bytes + bytes / 4, 1 << 20);
+        GGB_CUDA(cudaMalloc(reinterpret_cast<void **>(&base), want));
+        cap = want;
+        return GGB_OK;
+    }
+    void *take(size_t bytes) { void *p = base + used; used += align_up(bytes, 256); return p; }
+};
+
+} // namespace ggb
+
+struct ggb_pool {
+    void *host_base = nullptr;
+    size_t bytes = 0;
+    bool owned = false, registered = false, register_tried = false;
+    std::map<const void *, ggb::Mirror> mirrors;    // keyed by host data pointer of a leaf src0
+    ggb::DevArena arena;
+};
+
+namespace ggb {
+
+static size_t tensor_span(const ggml_tensor *t)
+{
+    // bytes from data to the end of the last element, honouring strides (views / padded rows)
+    const size_t rb = (size_t)(t->ne[0] / blck_size(t->type)) * type_size(t->type);
+    size_t span = rb;
+    for (int i = 1; i < GGML_MAX_DIMS; i++) span += (size_t)(t->ne[i] - 1) * t->nb[i];
+    return span;
+}
+static bool dst_contiguous(const ggml_tensor *t)
+{
+    return t->nb[0] == 4 && t->nb[1] == (uint64_t)t->ne[0] * 4 && t->nb[2] == t->nb[1] * (uint64_t)t->ne[1] && t->nb[3] == t->nb[2] * (uint64_t)t->ne[2];
+}
+
+// What ggml_compute_forward_mul_mat_* assert (Ggml.cs:6016-6034, 6221-6238, 6388, 6481-6504, 6694) and
+// ggml_can_mul_mat (Ggml.cs:8345-8353), returned as a status instead of Debug.Assert.
+static int validate_mul_mat(const ggml_tensor *dst)
+{
+    const ggml_tensor *a = dst->src0, *b = dst->src1;
+    if (!a || !b) return set_error(GGB_E_INVALID, "MUL_MAT node without src0/src1");
+    if (dst->op != GGML_OP_MUL_MAT) return set_error(GGB_E_INVALID, "node op %d is not GGML_OP_MUL_MAT", dst->op);
+    if (b->type != GGML_TYPE_F32 || dst->type != GGML_TYPE_F32) return set_error(GGB_E_INVALID, "mul_mat: src1 and dst must be F32 (Ggml.cs:3379-3382)");
+    if (a->type != GGML_TYPE_F32 && a->type != GGML_TYPE_F16 && a->type != GGML_TYPE_Q4_0 && a->type != GGML_TYPE_Q4_1)
+        return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is outside this backend's path (F32, F16, Q4_0, Q4_1)", a->type);
+    if (a->ne[0] != b->ne[0] || a->ne[2] != b->ne[2] || a->ne[3] != b->ne[3]) return set_error(GGB_E_INVALID, "mul_mat: ggml_can_mul_mat fails (Ggml.cs:8345-8353)");
+    if (dst->ne[0] != a->ne[1] || dst->ne[1] != b->ne[1] || dst->ne[2] != a->ne[2] || dst->ne[3] != a->ne[3])
+        return set_error(GGB_E_INVALID, "mul_mat: dst shape does not match (Ggml.cs:6031-6034)");
+    if (a->nb[0] != type_size(a->type)) return set_error(GGB_E_INVALID, "mul_mat: permuted src0 (nb00 != type size, Ggml.cs:6022/6227/6492)");
+    if (b->nb[0] != 4) return set_error(GGB_E_INVALID, "mul_mat: permuted src1 (nb10 != 4, Ggml.cs:6023/6388/6493)");
+    if (dst->nb[0] != 4 || dst->nb[0] > dst->nb[1] || dst->nb[1] > dst->nb[2] || dst->nb[2] > dst->nb[3])
+        return set_error(GGB_E_INVALID, "mul_mat: transposed or permuted dst (Ggml.cs:6026-6029)");
+    if (a->ne[0] % blck_size(a->type)) return set_error(GGB_E_INVALID, "mul_mat: ne00 %% 32 != 0 (Ggml.cs:6694)");
+    if (!dst_contiguous(dst)) return set_error(GGB_E_UNSUPPORTED, "mul_mat: dst must be contiguous (as ggml_mul_mat always creates it, Ggml.cs:8237-8238)");
+    if (!a->data || !b->data || !dst->data) return set_error(GGB_E_INVALID, "mul_mat: tensor without data (no_alloc context?)");
+    return GGB_OK;
+}
+
+static int validate_cpy(const ggml_tensor *node)
+{
+    const ggml_tensor *a = node->src0, *b = node->src1;
+    if (!a || !b || !a->data || !b->data) return set_error(GGB_E_INVALID, "CPY node without operands/data");
+    if (a->type != GGML_TYPE_F32) return set_error(GGB_E_UNSUPPORTED, "cpy: only F32 sources are on this path");
+    if (b->type != GGML_TYPE_Q4_0 && b->type != GGML_TYPE_Q4_1 && b->type != GGML_TYPE_F16)
+        return set_error(GGB_E_UNSUPPORTED, "cpy: destination type %d is not on this path (F16, Q4_0, Q4_1)", b->type);
+    int64_t na = a->ne[0] * a->ne[1] * a->ne[2] * a->ne[3], nb = b->ne[0] * b->ne[1] * b->ne[2] * b->ne[3];
+    if (na != nb) return set_error(GGB_E_INVALID, "cpy: element counts differ (Ggml.cs:8281)");
+    if (a->nb[0] != 4 || a->nb[1] != 4 * (uint64_t)a->ne[0] || a->nb[2] != a->nb[1] * (uint64_t)a->ne[1] || a->nb[3] != a->nb[2] * (uint64_t)a->ne[2])
+        return set_error(GGB_E_UNSUPPORTED, "cpy: non-contiguous source");
+    const uint64_t rb = (uint64_t)(b->ne[0] / blck_size(b->type)) * type_size(b->type);
+    if (b->nb[0] != type_size(b->type) || b->nb[1] != rb || b->nb[2] != rb * (uint64_t)b->ne[1] || b->nb[3] != b->nb[2] * (uint64_t)b->ne[2])
+        return set_error(GGB_E_UNSUPPORTED, "cpy: non-contiguous destination");
+    if (a->ne[0] % blck_size(b->type) || a->ne[0] != b->ne[0]) return set_error(GGB_E_UNSUPPORTED, "cpy: rows must map one to one (ne00 == ne0, %% 32)");
+    return GGB_OK;
+}
+
+struct Produced { const uint8_t *host; size_t bytes; uint8_t *dev; int level; };
+
+static const Produced *find_produced(const std::vector<Produced> &v, const void *p)
+{
+    const uint8_t *q = static_cast<const uint8_t *>(p);
+    for (const Produced &pr : v) if (q >= pr.host && q < pr.host + pr.bytes) return &pr;
+    return nullptr;
+}
+
+// Runs `nodes` (MUL_MAT / CPY, already validated to be runnable, in graph order).
+static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    cudaStream_t s = g_stream;
+    const size_t n = nodes.size();
+    if (!n) return GGB_OK;
+    if (!pool->owned && !pool->register_tried) {
+        // pinning the caller's memory is an optimisation only; pageable memory still works
+        pool->register_tried = true;
+        if (cudaHostRegister(pool->host_base, pool->bytes, cudaHostRegisterDefault) == cudaSuccess) pool->registered = true; else cudaGetLastError();
+    }
+
+    // ---- pass 1: sizes, so the scratch arena is allocated once before anything is enqueued ----
+    size_t need = 0;
+    std::vector<Produced> produced_plan;
+    for (size_t i = 0; i < n; i++) {
+        ggml_tensor *t = nodes[i];
+        const ggml_tensor *a = t->src0, *b = t->src1;
+        if (t->op == GGML_OP_MUL_MAT) {
+            const bool a_dev = find_produced(produced_plan, a->data) != nullptr;
+            const bool a_cached = !a_dev && a->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE);
+            if (!a_dev && !a_cached) need += align_up(tensor_span(a), 256);
+            if (!find_produced(produced_plan, b->data)) need += align_up(tensor_span(b), 256);
+            need += align_up(tensor_span(t), 256);
+            need += (size_t)(a->ne[2] * a->ne[3]) * mm_ws_bytes_bound(a->type, a->ne[1], a->ne[0], b->ne[1]);
+            produced_plan.push_back({static_cast<const uint8_t *>(t->data), tensor_span(t), nullptr, 0});
+        } else {
+            if (!find_produced(produced_plan, a->data)) need += align_up(tensor_span(a), 256);
+            need += align_up(tensor_span(b), 256);
+            produced_plan.push_back({static_cast<const uint8_t *>(b->data), tensor_span(b), nullptr, 0});
+        }
+    }
+    rc = pool->arena.reserve(need + 4096);
+    if (rc) return rc;
+    pool->arena.used = 0;
+
+    GGB_CUDA(cudaEventRecord(g_ev0, s));
+
+    // ---- pass 2: stage inputs, group nodes into dependency levels, launch ----
+    std::vector<Produced> produced;
+    struct Item { ggml_tensor *t; int level; uint8_t *da, *db, *dd; };
+    std::vector<Item> items(n);
+    int max_level = 0;
+    for (size_t i = 0; i < n; i++) {
+        ggml_tensor *t = nodes[i];
+        ggml_tensor *a = t->src0, *b = t->src1;
+        Item &it = items[i];
+        it.t = t; it.level = 0;
+        // src0
+        if (const Produced *pr = find_produced(produced, a->data)) {
+            it.da = pr->dev + (static_cast<const uint8_t *>(a->data) - pr->host);
+            it.level = std::max(it.level, pr->level + 1);
+        } else if (t->op == GGML_OP_MUL_MAT && a->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE)) {
+            const size_t span = tensor_span(a);
+            auto f = pool->mirrors.find(a->data);
+            if (f != pool->mirrors.end() && f->second.bytes < span) { cudaFree(f->second.dptr); pool->mirrors.erase(f); f = pool->mirrors.end(); }
+            if (f == pool->mirrors.end()) {
+                void *d = nullptr;
+                GGB_CUDA(cudaMalloc(&d, align_up(span, 256)));
+                GGB_CUDA(cudaMemcpyAsync(d, a->data, span, cudaMemcpyHostToDevice, s));
+                g_stats.h2d_bytes += span; g_stats.weight_uploads++;
+                f = pool->mirrors.emplace(a->data, Mirror{d, span}).first;
+            } else g_stats.weight_cache_hits++;
+            it.da = static_cast<uint8_t *>(f->second.dptr);
+        } else {
+            const size_t span = tensor_span(a);
+            it.da = static_cast<uint8_t *>(pool->arena.take(span));
+            GGB_CUDA(cudaMemcpyAsync(it.da, a->data, span, cudaMemcpyHostToDevice, s));
+            g_stats.h2d_bytes += span;
+        }
+        if (t->op == GGML_OP_MUL_MAT) {
+            if (const Produced *pr = find_produced(produced, b->data)) {
+                it.db = pr->dev + (static_cast<const uint8_t *>(b->data) - pr->host);
+                it.level = std::max(it.level, pr->level + 1);
+            } else {
+                const size_t span = tensor_span(b);
+                it.db = static_cast<uint8_t *>(pool->arena.take(span));
+                GGB_CUDA(cudaMemcpyAsync(it.db, b->data, span, cudaMemcpyHostToDevice, s));
+                g_stats.h2d_bytes += span;
+            }
+            it.dd = static_cast<uint8_t *>(pool->arena.take(tensor_span(t)));
+            produced.push_back({static_cast<const uint8_t *>(t->data), tensor_span(t), it.dd, it.level});
+        } else {
+            it.db = nullptr;
+            it.dd = static_cast<uint8_t *>(pool->arena.take(tensor_span(b)));
+            // a CPY rewrites b->data: a cached mirror of it is stale from here on
+            auto f = pool->mirrors.find(b->data);
+            if (f != pool->mirrors.end()) { cudaFree(f->second.dptr); pool->mirrors.erase(f); }
+            produced.push_back({static_cast<const uint8_t *>(b->data), tensor_span(b), it.dd, it.level});
+        }
+        max_level = std::max(max_level, it.level);
+    }
+
+    for (int lv = 0; lv <= max_level; lv++) {
+        std::vector<ggb_dev_mm> mms;
+        for (Item &it : items) {
+            if (it.level != lv) continue;
+            ggml_tensor *t = it.t; const ggml_tensor *a = t->src0, *b = t->src1;
+            if (t->op == GGML_OP_MUL_MAT) {
+                for (int64_t i3 = 0; i3 < a->ne[3]; i3++) for (int64_t i2 = 0; i2 < a->ne[2]; i2++) {
+                    ggb_dev_mm m = {};
+                    m.type = a->type; m.M = a->ne[1]; m.K = a->ne[0]; m.N = b->ne[1];
+                    m.W = it.da + i2 * a->nb[2] + i3 * a->nb[3]; m.nb01 = (int64_t)a->nb[1];
+                    m.X = reinterpret_cast<const float *>(it.db + i2 * b->nb[2] + i3 * b->nb[3]); m.ldx_bytes = (int64_t)b->nb[1];
+                    m.Y = reinterpret_cast<float *>(it.dd + i2 * t->nb[2] + i3 * t->nb[3]);
+                    // the F16 and quantized drivers index dst as dst_col[ic*ne0] (Ggml.cs:6423, 6697); F32 uses nb1 (6160)
+                    m.ldy_bytes = a->type == GGML_TYPE_F32 ? (int64_t)t->nb[1] : (int64_t)t->ne[0] * 4;
+                    mms.push_back(m);
+                }
+            } else {
+                const int64_t rows = b->ne[1] * b->ne[2] * b->ne[3];
+                rc = launch_quantize_rows(b->type, reinterpret_cast<const float *>(it.da), a->ne[0], it.dd, rows, b->ne[0], s);
+                if (rc) return rc;
+            }
+        }
+        if (!mms.empty()) {
+            size_t wsb = 0;
+            for (const ggb_dev_mm &m : mms) wsb += mm_ws_bytes(m);
+            void *ws = pool->arena.take(wsb);
+            rc = dev_batch(mms.data(), (int)mms.size(), ws, wsb, s);
+            if (rc) return rc;
+        }
+    }
+
+    // ---- results back into the host arena ----
+    for (size_t i = 0; i < n; i++) {
+        const Item &it = items[i];
+        ggml_tensor *t = it.t;
+        if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i] && t->op == GGML_OP_MUL_MAT) continue;   // a CPY target is user-visible
+        void *hdst = t->op == GGML_OP_MUL_MAT ? t->data : t->src1->data;
+        const size_t span = t->op == GGML_OP_MUL_MAT ? tensor_span(t) : tensor_span(t->src1);
+        GGB_CUDA(cudaMemcpyAsync(hdst, it.dd, span, cudaMemcpyDeviceToHost, s));
+        g_stats.d2h_bytes += span;
+    }
+    GGB_CUDA(cudaEventRecord(g_ev1, s));
+    GGB_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    GGB_CUDA(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
+    g_stats.last_graph_device_ms = ms;
+    g_stats.nodes_executed += n;
+    const int64_t us_each = (int64_t)(ms * 1000.0 / (double)n);
+    for (size_t i = 0; i < n; i++) { nodes[i]->perf_runs++; nodes[i]->perf_time_us += us_each; }   // Ggml.cs:3700-3702
+    return GGB_OK;
+}
+
+} // namespace ggb
+
+using namespace ggb;
+
+extern "C" {
+
+const char *ggb_last_error(void) { return g_err; }
+int ggb_abi_version(void) { return GGB_ABI_VERSION; }
+
+int ggb_abi_check(int sizeof_tensor, int offsetof_data, int sizeof_cgraph, int offsetof_nodes, int sizeof_block_q4_0, int sizeof_block_q4_1)
+{
+    static_assert(sizeof(ggml_tensor) == 176 && offsetof(ggml_tensor, data) == 160, "ggml_tensor layout (TypeDefinitions.cs:65-99)");
+    static_assert(offsetof(ggml_tensor, op) == 72 && offsetof(ggml_tensor, grad) == 80 && offsetof(ggml_tensor, src0) == 88 && offsetof(ggml_tensor, n_tasks) == 136, "ggml_tensor offsets");
+    static_assert(sizeof(ggml_cgraph) == 98360 && offsetof(ggml_cgraph, nodes) == 32 && offsetof(ggml_cgraph, leafs) == 65568, "ggml_cgraph layout (TypeDefinitions.cs:102-152)");
+    static_assert(sizeof(block_q4_0) == 20 && sizeof(block_q4_1) == 24 && sizeof(block_q8_0) == 36 && sizeof(block_q8_1) == 44, "block layouts");
+    if (sizeof_tensor != (int)sizeof(ggml_tensor) || offsetof_data != (int)offsetof(ggml_tensor, data) ||
+        sizeof_cgraph != (int)sizeof(ggml_cgraph) || offsetof_nodes != (int)offsetof(ggml_cgraph, nodes) ||
+        sizeof_block_q4_0 != 20 || sizeof_block_q4_1 != 24)
+        return set_error(GGB_E_ABI, "ABI mismatch: host says tensor %d/%d cgraph %d/%d q4_0 %d q4_1 %d; library has %zu/%zu %zu/%zu 20 24",
+                         sizeof_tensor, offsetof_data, sizeof_cgraph, offsetof_nodes, sizeof_block_q4_0, sizeof_block_q4_1,
+                         sizeof(ggml_tensor), offsetof(ggml_tensor, data), sizeof(ggml_cgraph), offsetof(ggml_cgraph, nodes));
+    return GGB_OK;
+}
+
+int ggb_init(void) { std::lock_guard<std::mutex> lk(g_mu); return ensure_init(); }
+
+int ggb_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_inited) return GGB_OK;
+    cudaStreamSynchronize(g_stream);
+    cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1);
+    cudaStreamDestroy(g_stream);
+    g_stream = nullptr; g_inited = false;
+    return GGB_OK;
+}
+
+int ggb_device_count(int *count)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (count) *count = n;
+    return GGB_OK;
+}
+
+int ggb_pool_alloc(size_t bytes, void **host_base, ggb_pool **out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!host_base || !out) return set_error(GGB_E_INVALID, "ggb_pool_alloc: null out pointer");
+    int rc = ensure_init();
+    if (rc) return rc;
+    void *p = nullptr;
+    GGB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault));   // page-aligned >= GGML_MEM_ALIGN
+    ggb_pool *pool = new ggb_pool();
+    pool->host_base = p; pool->bytes = bytes; pool->owned = true;
+    *host_base = p; *out = pool;
+    return GGB_OK;
+}
+
+int ggb_pool_adopt(void *host_base, size_t bytes, ggb_pool **out)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!host_base || !out) return set_error(GGB_E_INVALID, "ggb_pool_adopt: null pointer");
+    if (reinterpret_cast<uintptr_t>(host_base) % GGML_MEM_ALIGN) return set_error(GGB_E_INVALID, "ggb_pool_adopt: buffer not %d-byte aligned (Ggml.cs:1557)", GGML_MEM_ALIGN);
+    // No device work yet: the caller owns the memory; it is pinned lazily at the first compute.
+    ggb_pool *pool = new ggb_pool();
+    pool->host_base = host_base; pool->bytes = bytes; pool->owned = false;
+    *out = pool;
+    return GGB_OK;
+}
+
+int ggb_pool_free(ggb_pool *pool)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pool) return GGB_OK;
+    if (g_inited) cudaStreamSynchronize(g_stream);
+    for (auto &kv : pool->mirrors) cudaFree(kv.second.dptr);
+    if (pool->arena.base) cudaFree(pool->arena.base);
+    if (pool->registered) cudaHostUnregister(pool->host_base);
+    if (pool->owned && pool->host_base) cudaFreeHost(pool->host_base);
+    cudaGetLastError();
+    delete pool;
+    return GGB_OK;
+}
+
+int ggb_tensor_invalidate(ggb_pool *pool, const ggml_tensor *t)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pool) return set_error(GGB_E_INVALID, "ggb_tensor_invalidate: null pool");
+    if (g_inited) cudaStreamSynchronize(g_stream);
+    if (!t) { for (auto &kv : pool->mirrors) cudaFree(kv.second.dptr); pool->mirrors.clear(); return GGB_OK; }
+    auto f = pool->mirrors.find(t->data);
+    if (f != pool->mirrors.end()) { cudaFree(f->second.dptr); pool->mirrors.erase(f); }
+    return GGB_OK;
+}
+
+int ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pool || !dst) return set_error(GGB_E_INVALID, "ggb_mul_mat_node: null argument");
+    int rc = validate_mul_mat(dst);
+    if (rc) return rc;
+    std::vector<ggml_tensor *> nodes{dst};
+    return run_nodes(pool, nodes, 0, std::vector<char>{1});
+}
+
+int ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *g, int flags, uint8_t *done)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pool || !g) return set_error(GGB_E_INVALID, "ggb_graph_compute_mul_mats: null argument");
+    if (g->n_nodes < 0 || g->n_nodes > GGML_MAX_NODES) return set_error(GGB_E_INVALID, "graph with %d nodes", g->n_nodes);
+    // A node is runnable here if it is a MUL_MAT / supported CPY whose operands are leafs (op NONE) or runnable nodes.
+    std::vector<ggml_tensor *> run;
+    std::vector<int> run_idx;
+    std::map<const ggml_tensor *, bool> runnable;
+    for (int i = 0; i < g->n_nodes; i++) {
+        ggml_tensor *t = g->nodes[i];
+        if (done) done[i] = 0;
+        if (!t) return set_error(GGB_E_INVALID, "graph node %d is null", i);
+        bool ok = false;
+        if (t->op == GGML_OP_MUL_MAT || t->op == GGML_OP_CPY) {
+            auto operand_ok = [&](const ggml_tensor *o) { return o && (o->op == GGML_OP_NONE || runnable.count(o)); };
+            if (operand_ok(t->src0) && operand_ok(t->src1)) {
+                int rc = t->op == GGML_OP_MUL_MAT ? validate_mul_mat(t) : validate_cpy(t);
+                if (rc == GGB_E_INVALID) return rc;        // the reference would assert: report it
+                ok = rc == GGB_OK;                         // unsupported: leave the node to the caller's loop
+            }
+        }
+        if (ok) { runnable[t] = true; run.push_back(t); run_idx.push_back(i); }
+    }
+    // graph outputs = executed nodes nobody else in the executed set consumes
+    std::vector<char> is_output(run.size(), 1);
+    for (size_t i = 0; i < run.size(); i++)
+        for (size_t j = i + 1; j < run.size(); j++)
+            if (run[j]->src0 == run[i] || run[j]->src1 == run[i]) is_output[i] = 0;
+    // a consumer outside the executed set (a CPU op of the caller) needs the data on the host
+    for (int i = 0; i < g->n_nodes; i++) {
+        ggml_tensor *t = g->nodes[i];
+        if (runnable.count(t)) continue;
+        for (size_t j = 0; j < run.size(); j++) if (t->src0 == run[j] || t->src1 == run[j]) is_output[j] = 1;
+    }
+    int rc = run_nodes(pool, run, flags, is_output);
+    if (rc) return rc;
+    if (done) for (int i : run_idx) done[i] = 1;
+    g->perf_runs++;
+    g->perf_time_us += (int64_t)(g_stats.last_graph_device_ms * 1000.0);
+    return (int)run.size();
+}
+
+// ---- codecs on host or device pointers ----
+
+static int codec_rows(bool quantize, int type, const void *src, void *dst, int64_t nrows, int64_t k)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (nrows < 0 || k < 0) return set_error(GGB_E_INVALID, "negative size");
+    if (nrows == 0 || k == 0) return GGB_OK;
+    const int blck = blck_size(type);
+    if (!type_size(type) || (quantize && type == GGML_TYPE_F32)) return set_error(GGB_E_UNSUPPORTED, "codec: type %d", type);
+    if (k % blck) return set_error(GGB_E_INVALID, "codec: k=%lld not a multiple of %d", (long long)k, blck);
+    const size_t fbytes = (size_t)nrows * k * 4, qbytes = (size_t)nrows * (k / blck) * type_size(type);
+    const size_t sbytes = quantize ? fbytes : qbytes, dbytes = quantize ? qbytes : fbytes;
+    const bool sdev = is_device_ptr(src), ddev = is_device_ptr(dst);
+    void *ds = const_cast<void *>(src), *dd = dst;
+    if (!sdev) { GGB_CUDA(cudaMalloc(&ds, sbytes)); GGB_CUDA(cudaMemcpyAsync(ds, src, sbytes, cudaMemcpyHostToDevice, g_stream)); g_stats.h2d_bytes += sbytes; }
+    if (!ddev) { GGB_CUDA(cudaMalloc(&dd, dbytes)); }
+    rc = quantize ? launch_quantize_rows(type, (const float *)ds, k, dd, nrows, k, g_stream)
+                  : launch_dequantize_rows(type, ds, (float *)dd, nrows, k, g_stream);
+    if (!rc && !ddev) { cudaError_t e = cudaMemcpyAsync(dst, dd, dbytes, cudaMemcpyDeviceToHost, g_stream); g_stats.d2h_bytes += dbytes;
+                        if (e != cudaSuccess) rc = set_error(GGB_E_CUDA, "D2H failed: %s", cudaGetErrorString(e)); }
+    cudaError_t e = cudaStreamSynchronize(g_stream);
+    if (!rc && e != cudaSuccess) rc = set_error(GGB_E_CUDA, "codec kernel failed: %s", cudaGetErrorString(e));
+    if (!sdev) cudaFree(ds);
+    if (!ddev) cudaFree(dd);
+    return rc;
+}
+
+int ggb_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return codec_rows(true, type, src, dst, nrows, k);
+}
+int ggb_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    return codec_rows(false, type, src, dst, nrows, k);
+}
+
+// ---- device-resident entry points ----
+
+size_t ggb_dev_workspace_bytes(const ggb_dev_mm *mm, int count)
+{
+    size_t t = 0;
+    for (int i = 0; i < count; i++) t += mm_ws_bytes(mm[i]);
+    return t;
+}
+
+int ggb_dev_mul_mat_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, void *stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (count < 0 || (count && !mm)) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch: bad arguments");
+    return dev_batch(mm, count, ws, ws_bytes, stream ? static_cast<cudaStream_t>(stream) : g_stream);
+}
+
+int ggb_dev_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k, void *stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    return launch_quantize_rows(type, src, k, dst, nrows, k, stream ? static_cast<cudaStream_t>(stream) : g_stream);
+}
+int ggb_dev_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k, void *stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    return launch_dequantize_rows(type, src, dst, nrows, k, stream ? static_cast<cudaStream_t>(stream) : g_stream);
+}
+
+int ggb_dev_alloc(size_t bytes, void **dptr)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!dptr) return set_error(GGB_E_INVALID, "null out pointer");
+    GGB_CUDA(cudaMalloc(dptr, bytes ? bytes : 256));
+    return GGB_OK;
+}
+int ggb_dev_free(void *dptr) { if (dptr) { GGB_CUDA(cudaFree(dptr)); } return GGB_OK; }
+int ggb_dev_upload(void *dptr, const void *host, size_t bytes)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    GGB_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, g_stream));
+    GGB_CUDA(cudaStreamSynchronize(g_stream));
+    g_stats.h2d_bytes += bytes;
+    return GGB_OK;
+}
+int ggb_dev_download(void *host, const void *dptr, size_t bytes)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    GGB_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, g_stream));
+    GGB_CUDA(cudaStreamSynchronize(g_stream));
+    g_stats.d2h_bytes += bytes;
+    return GGB_OK;
+}
+int ggb_stream_sync(void *stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    GGB_CUDA(cudaStreamSynchronize(stream ? static_cast<cudaStream_t>(stream) : g_stream));
+    return GGB_OK;
+}
+
+int ggb_ipc_export(void *dptr, uint8_t handle[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    GGB_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, 64);
+    return GGB_OK;
+}
+int ggb_ipc_open(const uint8_t handle[64], void **peer)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    GGB_CUDA(cudaIpcOpenMemHandle(peer, h, cudaIpcMemLazyEnablePeerAccess));
+    return GGB_OK;
+}
+int ggb_ipc_close(void *peer) { GGB_CUDA(cudaIpcCloseMemHandle(peer)); return GGB_OK; }
+
+int ggb_get_stats(ggb_stats *out) { if (!out) return set_error(GGB_E_INVALID, "null"); *out = g_stats; return GGB_OK; }
+int ggb_reset_stats(void) { g_stats = ggb_stats{}; return GGB_OK; }
+
+} // extern "C"

@@ -1,0 +1,217 @@
+/*
+ * ggb200.h -- C ABI of libggb200.so, the B200 (sm_100a) backend for GGMLSharp's
+ * matrix-multiply path.
+ *
+ * The reference (kant2002/GGMLSharp, C#) has no FFI of its own: it is one static class
+ * with no DllImport.  This header is therefore the boundary a maintainer would bind
+ * with P/Invoke at the three seams upstream ggml used for its cuBLAS hook, which the
+ * reference still carries as dead `#if GGML_USE_CUBLAS` text:
+ *     seam A  pool allocation in ggml_init / ggml_free        Ggml.cs:1543-1545, 1584-1588
+ *     seam B  ggml_graph_compute's per-node loop              Ggml.cs:3539-3704
+ *     seam C  the MUL_MAT arm of ggml_compute_forward         Ggml.cs:8649-8653 -> 6714-6744
+ *     (one-time init where ggml_init_cublas() sat             Ggml.cs:1499-1504)
+ * INTEGRATION.md shows the C# stubs.  Every struct below is laid out exactly as the C#
+ * struct it mirrors (TypeDefinitions.cs), so the C# side passes its own pointers.
+ *
+ * Conventions: every function returns 0 (GGB_OK) or a negative ggb_status and never
+ * throws or aborts; ggb_last_error() returns a thread-local message.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with GGB_E_NODEVICE.
+ */
+#ifndef GGB200_H
+#define GGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGB_ABI_VERSION 1
+
+/* ---- mirrors of TypeDefinitions.cs ------------------------------------------------ */
+
+#define GGML_MAX_DIMS   4
+#define GGML_MAX_NODES  4096
+#define GGML_MAX_OPT    4
+#define GGML_MEM_ALIGN  16      /* Ggml.cs:16 */
+#define GGML_OBJECT_SIZE 32     /* sizeof(ggml_object) */
+
+/* TypeDefinitions.cs:153-169 */
+typedef enum ggml_type {
+    GGML_TYPE_F32 = 0, GGML_TYPE_F16 = 1, GGML_TYPE_Q4_0 = 2, GGML_TYPE_Q4_1 = 3,
+    GGML_TYPE_Q4_2 = 4, GGML_TYPE_Q4_3 = 5, GGML_TYPE_Q5_0 = 6, GGML_TYPE_Q5_1 = 7,
+    GGML_TYPE_Q8_0 = 8, GGML_TYPE_Q8_1 = 9, GGML_TYPE_I8 = 10, GGML_TYPE_I16 = 11,
+    GGML_TYPE_I32 = 12, GGML_TYPE_COUNT = 13
+} ggml_type;
+
+/* TypeDefinitions.cs:172-220 (only the values this path dispatches on) */
+enum { GGML_OP_NONE = 0, GGML_OP_DUP = 1, GGML_OP_MUL_MAT = 20, GGML_OP_SCALE = 21, GGML_OP_CPY = 22, GGML_OP_CONT = 23 };
+
+/* TypeDefinitions.cs:65-99 -- 176 bytes, data at 160 */
+typedef struct ggml_tensor {
+    int32_t  type;
+    int32_t  n_dims;
+    int64_t  ne[GGML_MAX_DIMS];
+    uint64_t nb[GGML_MAX_DIMS];
+    int32_t  op;
+    uint8_t  is_param;          /* C# bool, 1 byte */
+    uint8_t  _pad0[3];
+    struct ggml_tensor *grad;
+    struct ggml_tensor *src0;
+    struct ggml_tensor *src1;
+    int64_t  opt[GGML_MAX_OPT];
+    int32_t  n_tasks;
+    int32_t  perf_runs;
+    int64_t  perf_cycles;
+    int64_t  perf_time_us;
+    void    *data;
+    uint8_t  padding[8];
+} ggml_tensor;
+
+/* TypeDefinitions.cs:102-152 -- 98 360 bytes, passed by pointer */
+typedef struct ggml_cgraph {
+    int32_t  n_nodes;
+    int32_t  n_leafs;
+    int32_t  n_threads;
+    int32_t  _pad0;
+    uint64_t work_size;
+    ggml_tensor *work;
+    ggml_tensor *nodes[GGML_MAX_NODES];
+    ggml_tensor *grads[GGML_MAX_NODES];
+    ggml_tensor *leafs[GGML_MAX_NODES];
+    int32_t  perf_runs;
+    int32_t  _pad1;
+    int64_t  perf_cycles;
+    int64_t  perf_time_us;
+} ggml_cgraph;
+
+/* TypeDefinitions.cs:236-248 -- weight blocks: float32 scale(s) + 16 bytes; byte j holds
+ * element 2j in its low nibble and element 2j+1 in its high nibble (Ggml.cs:361-373). */
+typedef struct { float d; uint8_t qs[16]; } block_q4_0;                    /* 20 B */
+typedef struct { float d; float m; uint8_t qs[16]; } block_q4_1;           /* 24 B */
+/* TypeDefinitions.cs:277-290 -- activation blocks (quants are int8: SURVEY.md defect D4) */
+typedef struct { float d; int8_t qs[32]; } block_q8_0;                     /* 36 B */
+typedef struct { float d; float s0; float s1; int8_t qs[32]; } block_q8_1; /* 44 B */
+
+/* ---- status ------------------------------------------------------------------------ */
+
+typedef enum ggb_status {
+    GGB_OK            =  0,
+    GGB_E_INVALID     = -1,   /* an assert of the reference path would have fired (shape/stride/type) */
+    GGB_E_UNSUPPORTED = -2,   /* valid ggml, but not a type/op this backend implements */
+    GGB_E_CUDA        = -3,   /* a CUDA call failed; message in ggb_last_error() */
+    GGB_E_NOMEM       = -4,
+    GGB_E_ABI         = -5,   /* struct layout mismatch between host language and this library */
+    GGB_E_NODEVICE    = -6    /* no usable sm_100 device: there is deliberately no CPU fallback */
+} ggb_status;
+
+const char *ggb_last_error(void);
+int  ggb_abi_version(void);
+
+/* Called once from ggml_init's first-call block (where ggml_init_cublas() was, Ggml.cs:1499-1504)
+ * with the host language's own sizeof/offsetof so a layout drift is refused, not corrupted. */
+int  ggb_abi_check(int sizeof_tensor, int offsetof_data, int sizeof_cgraph, int offsetof_nodes,
+                   int sizeof_block_q4_0, int sizeof_block_q4_1);
+
+/* Idempotent.  Selects the device (env GGB200_DEVICE, default 0), creates the stream. */
+int  ggb_init(void);
+int  ggb_shutdown(void);
+int  ggb_device_count(int *count);
+
+/* ---- seam A: the memory pool behind a ggml_context --------------------------------- */
+
+typedef struct ggb_pool ggb_pool;
+
+/* Replaces NativeMemory.AlignedAlloc(mem_size, 16) (Ggml.cs:1545).  *host_base is pinned host
+ * memory, >= 16-byte aligned; tensor->data pointers keep pointing into it, so user code that
+ * reads and writes tensor->data directly (Test3/Program.cs:37-40) is unchanged. */
+int  ggb_pool_alloc(size_t bytes, void **host_base, ggb_pool **pool);
+/* For a caller-supplied ggml_init_params.mem_buffer (Ggml.cs:1543-1544): the memory stays the
+ * caller's; the pool only tracks device mirrors of tensors inside it. */
+int  ggb_pool_adopt(void *host_base, size_t bytes, ggb_pool **pool);
+/* Replaces NativeMemory.AlignedFree (Ggml.cs:1587); frees device mirrors, and the host memory
+ * only if ggb_pool_alloc made it (mirrors mem_buffer_owned, Ggml.cs:1546). */
+int  ggb_pool_free(ggb_pool *pool);
+/* Weight (leaf src0) bytes are uploaded on first use and cached by (data, nbytes).  Call this
+ * after rewriting a cached weight tensor in place; pass NULL to drop every mirror. */
+int  ggb_tensor_invalidate(ggb_pool *pool, const ggml_tensor *t);
+
+/* ---- seam C / seam B: execute MUL_MAT nodes ------------------------------------------ */
+
+/* Drop-in for ggml_compute_forward_mul_mat (Ggml.cs:6714-6744) on one node, synchronous:
+ * validates what the reference asserts (Ggml.cs:6016-6034, 6221-6238, 6481-6504, 6694), uploads
+ * src1 (and src0 unless cached), runs the kernels, copies dst->data back, fills perf_*. */
+int  ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst);
+
+#define GGB_GRAPH_KEEP_ON_DEVICE 1   /* do not copy intermediate MUL_MAT results back (only graph outputs) */
+#define GGB_GRAPH_NO_WEIGHT_CACHE 2  /* re-upload every src0 (what the CPU path observes if weights change) */
+
+/* Called from ggml_graph_compute (Ggml.cs:3539) instead of walking MUL_MAT nodes one by one:
+ * runs, in node order and on one stream with one final sync, every MUL_MAT node (and F32->
+ * {F16,Q4_0,Q4_1} CPY node, the public route to quantize_row_q, Ggml.cs:4339-4363) whose inputs
+ * are leafs or nodes it runs itself.  done[i] (n_nodes bytes, may be NULL) is set to 1 for each
+ * node it executed; the caller's loop runs the rest.  Returns the number executed or < 0. */
+int  ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *graph, int flags, uint8_t *done);
+
+/* ---- the codec column of quantize_fns[] (Ggml.cs:219-290) ----------------------------- */
+
+/* quantize_row_q / dequantize_row_q over nrows rows of k elements; src and dst may each be a
+ * host or a device pointer.  Bit-exact with quantize_row_q4_0_reference_impl (Ggml.cs:334-377),
+ * quantize_row_q4_1_reference_impl (487-528), quantize_row_q8_0/q8_1 (733-823, defects D2-D4
+ * repaired) and the scalar dequantize_row_q4_0/q4_1 (884-911, 961-987).  F16 = (Half) cast. */
+int  ggb_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k);
+int  ggb_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k);
+
+/* ---- device-resident entry points (what the executor itself calls) --------------------- */
+
+/* One mul_mat on device pointers: dst[n][m] = sum_k W[m][k] * X[n][k]  (m < M, n < N).
+ * W: M rows of K elements of `type`, row stride nb01 bytes.  X, Y: float32, row strides in
+ * bytes.  A rank of a row-split passes its slice of W with Y offset to its column block. */
+typedef struct ggb_dev_mm {
+    int32_t  type;
+    int32_t  n_peers;              /* 0, or number of extra destinations in Y_peer (fused row-split epilogue) */
+    int64_t  M, K, N;
+    const void  *W;  int64_t nb01;
+    const float *X;  int64_t ldx_bytes;
+    float       *Y;  int64_t ldy_bytes;
+    float       *Y_peer[7];        /* peer-mapped copies of Y on other GPUs, written by the same kernel */
+} ggb_dev_mm;
+
+/* Scratch the batch needs (quantized / converted activations, the reference's `wdata`). */
+size_t ggb_dev_workspace_bytes(const ggb_dev_mm *mm, int count);
+/* Enqueue `count` independent mul_mats on `stream` (a cudaStream_t; NULL = the library's own).
+ * Single-token nodes that share (type, K) are fused into one persistent GEMV launch. */
+int  ggb_dev_mul_mat_batch(const ggb_dev_mm *mm, int count, void *workspace, size_t workspace_bytes, void *stream);
+/* Device-pointer codecs on a stream (no sync). */
+int  ggb_dev_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k, void *stream);
+int  ggb_dev_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k, void *stream);
+
+/* Plain device-memory helpers so a host language without a CUDA binding can stage data. */
+int  ggb_dev_alloc(size_t bytes, void **dptr);
+int  ggb_dev_free(void *dptr);
+int  ggb_dev_upload(void *dptr, const void *host, size_t bytes);
+int  ggb_dev_download(void *host, const void *dptr, size_t bytes);
+int  ggb_stream_sync(void *stream);
+
+/* Same-node multi-process row-split: export a device allocation / map a peer's (CUDA IPC). */
+int  ggb_ipc_export(void *dptr, uint8_t handle[64]);
+int  ggb_ipc_open(const uint8_t handle[64], void **peer_dptr);
+int  ggb_ipc_close(void *peer_dptr);
+
+/* ---- counters -------------------------------------------------------------------------- */
+
+typedef struct ggb_stats {
+    uint64_t kernel_launches;      /* kernels of this library launched since init / last reset */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t weight_uploads, weight_cache_hits;
+    uint64_t nodes_executed;
+    double   last_graph_device_ms; /* CUDA-event time of the last ggb_graph_compute_mul_mats / ggb_mul_mat_node */
+} ggb_stats;
+int  ggb_get_stats(ggb_stats *out);
+int  ggb_reset_stats(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGB200_H */

@@ -12,12 +12,8 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def has_gpu():
-    try:
-        import torch
-        return torch.cuda.is_available()
-    except Exception:
-        return False
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from gpu_util import has_gpu  # noqa: E402
 
 
 def pytest_collection_modifyitems(config, items):

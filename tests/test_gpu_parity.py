@@ -1,0 +1,416 @@
+"""GPU parity: the CUDA path, called through the C ABI (libggb200.so) and the host mirror of the reference API,
+against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): quantized blocks bit-exact; mul_mat rel-L2 <= 1e-3 for Q4_0/Q4_1/F16
+weights and <= 1e-5 for F32 weights.  The kernels are in fact much closer (only the summation order
+differs), so each test also asserts a tighter regression bound.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from gpu_util import rel_l2
+from ggmlsharp_b200 import ggml, native as N
+from oracle import pyoracle as orc
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+TOL = {N.F32: 1e-5, N.F16: 1e-3, N.Q4_0: 1e-3, N.Q4_1: 1e-3}          # the contract
+TIGHT = {N.F32: 2e-6, N.F16: 2e-6, N.Q4_0: 2e-6, N.Q4_1: 5e-6}        # what the GEMV path actually achieves
+NAMES = {N.F32: "f32", N.F16: "f16", N.Q4_0: "q4_0", N.Q4_1: "q4_1"}
+
+
+def _f32(h):
+    return np.frombuffer(bytes.fromhex(h), dtype=np.float32)
+
+
+def weights(rng, M, K, kind="weights"):
+    if kind == "weights":
+        return (rng.standard_normal((M, K)) * 0.02).astype(np.float32)
+    return rng.uniform(-1, 1, (M, K)).astype(np.float32)
+
+
+# ---------------------------------------------------------------- codecs: bit-exact
+
+@pytest.mark.parametrize("t,key", [(N.Q4_0, "q4_0"), (N.Q4_1, "q4_1"), (N.Q8_0, "q8_0"), (N.Q8_1, "q8_1")])
+def test_quantize_golden_kats(t, key):
+    with open(os.path.join(G, "quant_kat.json")) as f:
+        for b in json.load(f)["blocks"]:
+            got = ggml.quantize_rows(t, _f32(b["x"])).tobytes().hex()
+            assert got == b[key], (b["name"], key)
+
+
+@pytest.mark.parametrize("t,key,src", [(N.Q4_0, "deq4_0", "q4_0"), (N.Q4_1, "deq4_1", "q4_1")])
+def test_dequantize_golden_kats(t, key, src):
+    with open(os.path.join(G, "quant_kat.json")) as f:
+        for b in json.load(f)["blocks"]:
+            q = np.frombuffer(bytes.fromhex(b[src]), dtype=np.uint8)
+            assert ggml.dequantize_rows(t, q, 32).tobytes().hex() == b[key], b["name"]
+
+
+def _nasty(rng, nrows, k):
+    """Inputs that exercise every branch that decides a bit: ties, zero blocks, +-0, equal magnitudes, tiny/huge."""
+    x = rng.standard_normal((nrows, k)).astype(np.float32)
+    x[0, :32] = 0.0                                        # all-zero block -> d = -0.0f
+    x[1, :32] = -0.0
+    x[2, :32] = np.where(np.arange(32) % 2 == 0, 1.5, -1.5)            # |max| tie: first element wins
+    x[3, :32] = np.where(np.arange(32) % 2 == 0, -1.5, 1.5)
+    x[4, :32] = np.arange(32) - 16                                       # ties-to-even on .5
+    x[5, :32] = (np.arange(32) - 16) * 0.5
+    x[6, :32] = 1e-38 * rng.standard_normal(32)                          # subnormal scales
+    x[7, :32] = 1e30 * rng.standard_normal(32)
+    x[8, :32] = 3.25
+    x[9, :32] = np.array([0.0, -0.0] * 16)                               # min is +0 or -0 by order
+    x[10, :32] = np.array([-0.0, 0.0] * 16)
+    return x
+
+
+@pytest.mark.parametrize("t", [N.Q4_0, N.Q4_1, N.Q8_0, N.Q8_1])
+def test_quantize_bit_exact_random_and_edge_blocks(t):
+    rng = np.random.default_rng(11)
+    for nrows, k in ((16, 32), (12, 96), (33, 4096), (7, 11008)):
+        x = _nasty(rng, nrows, k) if nrows >= 11 else rng.standard_normal((nrows, k)).astype(np.float32)
+        for scale in (1.0, 0.02):
+            xs = (x * np.float32(scale)).astype(np.float32)
+            got, want = ggml.quantize_rows(t, xs), orc.quantize_rows(t, xs)
+            assert np.array_equal(got, want), (t, nrows, k, scale, int(np.argmax((got != want).any(1))))
+
+
+@pytest.mark.parametrize("t", [N.Q4_0, N.Q4_1])
+def test_quantize_bit_exact_cfg1_full_matrix(t):
+    # BASELINE.json configs[1]: quantize_row_q4_0 over the 4096x4096 F32 source, bit-exact
+    rng = np.random.default_rng(1001)
+    W = weights(rng, 4096, 4096)
+    got, want = ggml.quantize_rows(t, W), orc.quantize_rows(t, W)
+    assert np.array_equal(got, want)
+    # size-independent property: dequantize(quantize(W)) stays within half a step of W (one step at the Q4_0 clamp)
+    back = ggml.dequantize_rows(t, got, 4096)
+    assert np.array_equal(back, orc.dequantize_rows(t, want, 4096))
+    blk = W.reshape(-1, 32)
+    step = np.abs(blk).max(1) / 8 if t == N.Q4_0 else (blk.max(1) - blk.min(1)) / 30
+    assert (np.abs(back.reshape(-1, 32) - blk).max(1) <= step * 1.001 + 1e-12).all()
+
+
+def test_f16_cast_matches_half_rne():
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.standard_normal(4096).astype(np.float32) * s for s in (1e-7, 1e-4, 1, 3e4, 1e5)]).reshape(5, 4096)
+    got = ggml.quantize_rows(N.F16, x).view(np.uint16)
+    np.testing.assert_array_equal(got, orc.f32_to_f16(x))
+
+
+def test_codec_edge_cases():
+    assert ggml.quantize_rows(N.Q4_0, np.zeros((0, 32), np.float32)).shape == (0, 20)        # empty input
+    L = N.lib()
+    x = np.zeros((1, 48), np.float32)
+    out = np.zeros(64, np.uint8)
+    assert L.ggb_quantize_rows(N.Q4_0, x.ctypes.data, out.ctypes.data, 1, 48) == N.E_INVALID  # k % 32 (Ggml.cs:336)
+    assert L.ggb_quantize_rows(N.Q4_2 if hasattr(N, "Q4_2") else 4, x.ctypes.data, out.ctypes.data, 1, 32) == N.E_UNSUPPORTED
+
+
+# ---------------------------------------------------------------- mul_mat through the device-level C ABI
+
+class Dev:
+    """Tiny RAII helper over ggb_dev_alloc/upload/download."""
+
+    def __init__(self):
+        self.ptrs = []
+
+    def put(self, arr):
+        arr = np.ascontiguousarray(arr)
+        p = C.c_void_p()
+        N.check(N.lib().ggb_dev_alloc(max(arr.nbytes, 1), C.byref(p)))
+        self.ptrs.append(p)
+        if arr.nbytes:
+            N.check(N.lib().ggb_dev_upload(p, arr.ctypes.data, arr.nbytes))
+        return p.value
+
+    def empty(self, nbytes):
+        p = C.c_void_p()
+        N.check(N.lib().ggb_dev_alloc(max(nbytes, 1), C.byref(p)))
+        self.ptrs.append(p)
+        return p.value
+
+    def get(self, ptr, shape, dtype=np.float32):
+        out = np.zeros(shape, dtype=dtype)
+        if out.nbytes:
+            N.check(N.lib().ggb_dev_download(out.ctypes.data, ptr, out.nbytes))
+        return out
+
+    def close(self):
+        for p in self.ptrs:
+            N.lib().ggb_dev_free(p)
+        self.ptrs = []
+
+
+def dev_mul_mat(t, wbytes, M, K, X, nb01=None):
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    Nn = X.shape[0]
+    d = Dev()
+    try:
+        mm = N.ggb_dev_mm()
+        mm.type, mm.M, mm.K, mm.N = t, M, K, Nn
+        mm.W, mm.nb01 = d.put(wbytes), nb01 or (N.TYPE_SIZE[t] * (K // N.BLCK_SIZE[t]))
+        mm.X, mm.ldx_bytes = d.put(X), 4 * K
+        mm.Y, mm.ldy_bytes = d.empty(4 * M * Nn), 4 * M
+        wsb = N.lib().ggb_dev_workspace_bytes(C.byref(mm), 1)
+        ws = d.empty(wsb)
+        N.check(N.lib().ggb_dev_mul_mat_batch(C.byref(mm), 1, ws, wsb, None))
+        N.check(N.lib().ggb_stream_sync(None))
+        return d.get(mm.Y, (Nn, M))
+    finally:
+        d.close()
+
+
+@pytest.mark.parametrize("t,key,wkey", [(N.F32, "f32", "W"), (N.F16, "f16", "W_f16"), (N.Q4_0, "q4_0", "W_q4_0"), (N.Q4_1, "q4_1", "W_q4_1")])
+def test_mul_mat_small_golden(t, key, wkey):
+    with open(os.path.join(G, "mul_mat_small.json")) as f:
+        g = json.load(f)
+    M, K, Nn = g["M"], g["K"], g["N"]
+    wb = np.frombuffer(bytes.fromhex(g[wkey]), dtype=np.uint8)
+    got = dev_mul_mat(t, wb, M, K, _f32(g["X"]).reshape(Nn, K))
+    want = _f32(g[key]).reshape(Nn, M)
+    assert rel_l2(got, want) <= TIGHT[t]
+
+
+SHAPES = [
+    (4096, 4096, 1),      # cfg 1 / cfg 0
+    (11008, 4096, 1),     # cfg 2: w1/w3
+    (4096, 11008, 1),     # cfg 2: w2 (K = 11008, rows chunked)
+    (1, 32, 1), (3, 64, 1), (130, 96, 1),          # tiny / ragged: rows shorter than one copy
+    (257, 4128, 1),       # 129 blocks per row: Q4_0 rows are not 16-byte multiples -> plain-load staging
+    (512, 2048, 2), (300, 1024, 3), (64, 4096, 7), (96, 512, 8), (40, 256, 13), (128, 1024, 15),
+]
+
+
+@pytest.mark.parametrize("t", [N.F32, N.F16, N.Q4_0, N.Q4_1])
+@pytest.mark.parametrize("M,K,Nn", SHAPES)
+def test_mul_mat_vs_oracle(t, M, K, Nn):
+    rng = np.random.default_rng(1000 + M + K + Nn)
+    for kind, xs in (("weights", "normal"), ("uniform", "uniform")):
+        W = weights(rng, M, K, kind)
+        X = rng.standard_normal((Nn, K)).astype(np.float32) if xs == "normal" else rng.uniform(-1, 1, (Nn, K)).astype(np.float32)
+        wb = orc.encode_weights(t, W)
+        got = dev_mul_mat(t, wb, M, K, X)
+        want = orc.mul_mat_2d(t, wb, M, K, X, nth=8)
+        err = rel_l2(got, want)
+        assert err <= TOL[t], (NAMES[t], M, K, Nn, err)
+        assert err <= TIGHT[t], (NAMES[t], M, K, Nn, err)
+
+
+@pytest.mark.parametrize("t", [N.F32, N.F16, N.Q4_0, N.Q4_1])
+def test_mul_mat_padded_rows_and_zero_sizes(t):
+    rng = np.random.default_rng(77)
+    M, K = 50, 256
+    W = weights(rng, M, K)
+    wb = orc.encode_weights(t, W)                       # [M, rb]
+    rb = wb.shape[1]
+    padded = np.zeros((M, rb + 48), dtype=np.uint8)     # a view with nb01 > row bytes
+    padded[:, :rb] = wb
+    X = rng.standard_normal((2, K)).astype(np.float32)
+    got = dev_mul_mat(t, padded, M, K, X, nb01=rb + 48)
+    assert rel_l2(got, orc.mul_mat_2d(t, wb, M, K, X)) <= TIGHT[t]
+    assert dev_mul_mat(t, wb[:0], 0, K, X).shape == (2, 0)          # empty weight
+    assert dev_mul_mat(t, wb, M, K, X[:0]).shape == (0, M)          # no activations
+
+
+def test_linearity_property_full_size_q4_0():
+    # size-independent property at BASELINE's full size: W.(a*x) == a*(W.x) exactly for a power of two
+    # (quantize_row_q8_0 scales d by a and keeps the same quants), and y(x1)+y(x2) ~ y(x1+x2) within Q8 noise
+    rng = np.random.default_rng(3)
+    M = K = 4096
+    wb = orc.quantize_rows(orc.Q4_0, weights(rng, M, K))
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    y1 = dev_mul_mat(N.Q4_0, wb, M, K, x)
+    y4 = dev_mul_mat(N.Q4_0, wb, M, K, x * np.float32(4))
+    np.testing.assert_array_equal(y4, y1 * np.float32(4))
+    assert np.array_equal(dev_mul_mat(N.Q4_0, wb, M, K, x), y1)     # deterministic run to run
+
+
+# ---------------------------------------------------------------- through the reference-shaped host API
+
+def host_mul_mat(t, W, X, n_dims_x=None):
+    M, K = W.shape
+    X = np.atleast_2d(X)
+    wb = orc.encode_weights(t, W)
+    with ggml.Context(64 << 20 if wb.nbytes < (16 << 20) else wb.nbytes * 2 + (64 << 20)) as c:
+        a = c.tensor_from(t, K, M, data=wb)
+        b = c.tensor_from(N.F32, K, data=X) if (X.shape[0] == 1 and n_dims_x == 1) else c.tensor_from(N.F32, K, X.shape[0], data=X)
+        y = c.mul_mat(a, b)
+        g = c.build_forward(y)
+        c.graph_compute(g)
+        out = ggml.tensor_f32(y).reshape(X.shape[0], M).copy()
+        assert y.contents.perf_runs == 1 and g.perf_runs == 1
+    return out, wb
+
+
+@pytest.mark.parametrize("t", [N.F32, N.F16, N.Q4_0, N.Q4_1])
+def test_graph_compute_single_node(t):
+    rng = np.random.default_rng(21)
+    W, X = weights(rng, 320, 1024), rng.standard_normal((1, 1024)).astype(np.float32)
+    got, wb = host_mul_mat(t, W, X, n_dims_x=1)
+    assert rel_l2(got, orc.mul_mat_2d(t, wb, 320, 1024, X)) <= TIGHT[t]
+    got5, wb = host_mul_mat(t, W, rng.standard_normal((5, 1024)).astype(np.float32))
+    assert got5.shape == (5, 320)
+
+
+def test_test3_style_f32_mul_mat():
+    # Test3/Program.cs:22-57: F[NP=4096 rows][NF=256] from the LCG, x* = (+1 x128, -1 x128) is what L-BFGS must
+    # converge to, so F.x* ~ l = (+1 x2048, -1 x2048).  Pins orientation, strides and the F32 dot through the API.
+    NP, NF = 1 << 12, 1 << 8
+    nxt, r = 0, np.zeros(NP * NF, dtype=np.float32)
+    for n in range(NP * NF):                                        # xrand(), Test3/Program.cs:98-102, xsrand(0)
+        nxt = (nxt * 214013 + 2531011) & 0xFFFFFFFFFFFFFFFF
+        r[n] = (nxt >> 16) & 0x7FFF
+    l = np.where(np.arange(NP) < NP // 2, 1.0, -1.0).astype(np.float32)
+    i = np.arange(NF)[None, :]
+    ind = np.where(((l[:, None] > 0) & (i < NF // 2)) | ((l[:, None] < 0) & (i >= NF // 2)), 1.0, 0.0).astype(np.float32)
+    noise = (r.reshape(NP, NF) / np.float32(32767) - np.float32(0.5)) * np.float32(0.1)
+    F = ((ind + noise) / np.float32(0.5 * NF)).astype(np.float32)
+    xstar = np.where(np.arange(NF) < NF // 2, 1.0, -1.0).astype(np.float32)[None, :]
+    got, wb = host_mul_mat(N.F32, F, xstar, n_dims_x=1)
+    want = orc.mul_mat_2d(orc.F32, wb, NP, NF, xstar, nth=8)
+    assert rel_l2(got, want) <= 1e-6
+    assert np.abs(got[0] - l).max() < 2e-2            # Test3/Program.cs:82-88 tolerance 1e-2 on x, same order on F.x
+
+
+def test_graph_levels_chain_and_fanout():
+    # y1 = W1.x ; y2 = W2.y1 ; y3 = W3.y1  -> two dependency levels, y1 stays on the device
+    rng = np.random.default_rng(31)
+    K, M1, M2 = 512, 256, 96
+    W1, W2, W3 = weights(rng, M1, K), weights(rng, M2, M1, "uniform"), weights(rng, M2, M1, "uniform")
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    w1b, w2b, w3b = orc.encode_weights(N.Q4_0, W1), orc.encode_weights(N.F16, W2), orc.encode_weights(N.Q4_1, W3)
+    with ggml.Context(32 << 20) as c:
+        a1, a2, a3 = c.tensor_from(N.Q4_0, K, M1, data=w1b), c.tensor_from(N.F16, M1, M2, data=w2b), c.tensor_from(N.Q4_1, M1, M2, data=w3b)
+        b = c.tensor_from(N.F32, K, data=x)
+        y1 = c.mul_mat(a1, b)
+        y2, y3 = c.mul_mat(a2, y1), c.mul_mat(a3, y1)
+        g = c.build_forward(y2)
+        N.host().ggml_build_forward_expand(C.byref(g), y3)
+        assert g.n_nodes == 3
+        c.graph_compute(g)
+        g1, g2, g3 = (ggml.tensor_f32(t).reshape(1, -1).copy() for t in (y1, y2, y3))
+    r1 = orc.mul_mat_2d(orc.Q4_0, w1b, M1, K, x)
+    assert rel_l2(g1, r1) <= TIGHT[N.Q4_0]
+    # feed the ORACLE's y1 to the oracle, the DEVICE's y1 to the device: compare like with like
+    assert rel_l2(g2, orc.mul_mat_2d(orc.F16, w2b, M2, M1, g1)) <= 1e-5
+    assert rel_l2(g3, orc.mul_mat_2d(orc.Q4_1, w3b, M2, M1, g1)) <= 1e-5
+
+
+def test_batched_dims_ne02_ne03():
+    # src0 [K, M, 2, 3] x src1 [K, N, 2, 3]: every (i02, i03) slice is an independent mul_mat (Ggml.cs:6142-6162)
+    rng = np.random.default_rng(41)
+    K, M, Nn = 128, 24, 2
+    W = weights(rng, 6 * M, K).reshape(3, 2, M, K)
+    X = rng.standard_normal((3, 2, Nn, K)).astype(np.float32)
+    for t in (N.F32, N.Q4_0):
+        wb = orc.encode_weights(t, W.reshape(-1, K))
+        with ggml.Context(16 << 20) as c:
+            a = c.tensor_from(t, K, M, 2, 3, data=wb)
+            b = c.tensor_from(N.F32, K, Nn, 2, 3, data=X)
+            y = c.mul_mat(a, b)
+            g = c.build_forward(y)
+            c.graph_compute(g)
+            got = ggml.tensor_f32(y).copy()                     # [3, 2, Nn, M]
+        rb = wb.shape[1]
+        for i3 in range(3):
+            for i2 in range(2):
+                ws = wb.reshape(3, 2, M, rb)[i3, i2]
+                assert rel_l2(got[i3, i2], orc.mul_mat_2d(t, ws, M, K, X[i3, i2])) <= TIGHT[t]
+
+
+def test_weight_cache_and_invalidate():
+    rng = np.random.default_rng(51)
+    M, K = 64, 256
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    W1, W2 = weights(rng, M, K), weights(rng, M, K)
+    with ggml.Context(8 << 20) as c:
+        a = c.tensor_from(N.F32, K, M, data=W1)
+        b = c.tensor_from(N.F32, K, data=x)
+        y = c.mul_mat(a, b)
+        g = c.build_forward(y)
+        N.lib().ggb_reset_stats()
+        c.graph_compute(g)
+        c.graph_compute(g)
+        s = N.stats()
+        assert s.weight_uploads == 1 and s.weight_cache_hits == 1
+        first = ggml.tensor_f32(y).reshape(1, M).copy()
+        ggml.tensor_bytes(a)[:] = W2.view(np.uint8).ravel()     # user rewrites the weight through tensor->data
+        c.graph_compute(g)
+        stale = ggml.tensor_f32(y).reshape(1, M).copy()
+        np.testing.assert_array_equal(stale, first)             # documented: cached weights are not re-read
+    # explicit pool: ggb_tensor_invalidate makes the rewrite visible
+    lib = N.lib
+    buf = np.zeros(8 << 20, dtype=np.uint8)
+    with ggml.Context(buf.nbytes, mem_buffer=buf) as c:
+        a = c.tensor_from(N.F32, K, M, data=W1)
+        b = c.tensor_from(N.F32, K, data=x)
+        y = c.mul_mat(a, b)
+        pool = C.c_void_p()
+        N.check(lib().ggb_pool_adopt(buf.ctypes.data, buf.nbytes, C.byref(pool)))
+        N.check(lib().ggb_mul_mat_node(pool, y))
+        r1 = ggml.tensor_f32(y).reshape(1, M).copy()
+        ggml.tensor_bytes(a)[:] = W2.view(np.uint8).ravel()
+        N.check(lib().ggb_tensor_invalidate(pool, a))
+        N.check(lib().ggb_mul_mat_node(pool, y))
+        r2 = ggml.tensor_f32(y).reshape(1, M).copy()
+        N.check(lib().ggb_pool_free(pool))
+    assert rel_l2(r1, orc.mul_mat_2d(orc.F32, W1.view(np.uint8).reshape(M, -1), M, K, x)) <= TIGHT[N.F32]
+    assert rel_l2(r2, orc.mul_mat_2d(orc.F32, W2.view(np.uint8).reshape(M, -1), M, K, x)) <= TIGHT[N.F32]
+
+
+def test_cpy_quantizes_through_the_public_route():
+    # ggml_cpy(f32 -> q4_0) is the only public route to quantize_row_q (Ggml.cs:4339-4363); then use the result as src0
+    rng = np.random.default_rng(61)
+    M, K = 48, 512
+    W, x = weights(rng, M, K), rng.standard_normal((1, K)).astype(np.float32)
+    for t in (N.Q4_0, N.Q4_1, N.F16):
+        with ggml.Context(8 << 20) as c:
+            src = c.tensor_from(N.F32, K, M, data=W)
+            dstq = c.new_tensor(t, K, M)
+            cp = c.cpy(src, dstq)
+            b = c.tensor_from(N.F32, K, data=x)
+            y = c.mul_mat(cp, b)
+            g = c.build_forward(y)
+            assert g.n_nodes == 2
+            c.graph_compute(g)
+            qbytes = ggml.tensor_bytes(dstq).copy()
+            got = ggml.tensor_f32(y).reshape(1, M).copy()
+        want_q = orc.encode_weights(t, W)
+        assert np.array_equal(qbytes, want_q.ravel())           # bit-exact blocks in the user's tensor
+        assert rel_l2(got, orc.mul_mat_2d(t, want_q, M, K, x)) <= TIGHT[t]
+
+
+def test_error_behaviour_matches_reference_asserts():
+    L = N.lib()
+    buf = np.zeros(4 << 20, dtype=np.uint8)
+    with ggml.Context(buf.nbytes, mem_buffer=buf) as c:
+        pool = C.c_void_p()
+        N.check(L.ggb_pool_adopt(buf.ctypes.data, buf.nbytes, C.byref(pool)))
+        w = c.new_tensor(N.Q8_0, 64, 4)                          # a type outside the path (Ggml.cs:6726 handles it, we do not)
+        x = c.new_tensor(N.F32, 64)
+        y = c.mul_mat(w, x)
+        assert L.ggb_mul_mat_node(pool, y) == N.E_UNSUPPORTED
+        w2 = c.new_tensor(N.F32, 64, 4)
+        y2 = c.mul_mat(w2, x)
+        y2.contents.ne[0] = 5                                    # dst shape no longer matches (Ggml.cs:6031)
+        assert L.ggb_mul_mat_node(pool, y2) == N.E_INVALID
+        y2.contents.ne[0] = 4
+        x.contents.nb[0] = 8                                     # permuted src1 (Ggml.cs:6023)
+        assert L.ggb_mul_mat_node(pool, y2) == N.E_INVALID
+        x.contents.nb[0] = 4
+        assert L.ggb_mul_mat_node(pool, y2) == 0
+        N.check(L.ggb_pool_free(pool))
+
+
+def test_stats_count_launches():
+    N.lib().ggb_reset_stats()
+    rng = np.random.default_rng(71)
+    W = weights(rng, 64, 128)
+    dev_mul_mat(N.Q4_0, orc.encode_weights(N.Q4_0, W), 64, 128, rng.standard_normal((1, 128)).astype(np.float32))
+    s = N.stats()
+    assert s.kernel_launches == 2            # activation quantize + fused GEMV
