@@ -1,0 +1,345 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline benchmark of BASELINE.json on B200.
+
+Metric: "Q4_0 mul_mat HBM GB/s (% roofline)".  Workload at N=1 = BASELINE.json configs[1]: Q4_0 weight
+4096x4096 GEMV, single token.  One matrix is 10.5 MB -- smaller than the 126 MB L2 and shorter than a kernel
+launch -- so a "step" is one pass of the mul_mat path over a RING of 32 distinct 4096x4096 Q4_0 matrices
+(335.5 MB > 2x L2), each with its own activation vector: 32 independent MUL_MAT graph nodes, which the executor
+fuses into one activation-quantize launch + one persistent GEMV launch.  Inputs are larger than L2, so no flush.
+
+  value     whole-job GB/s = algorithmic bytes (W + x + y per node) / device time, weights, activations
+            and outputs resident in HBM, timed with CUDA events on the launching stream.
+  e2e       the same bytes / wall time through the reference-shaped API (ggml_graph_compute of a 32-node graph over a
+            host arena): per step the activations go host->device and the results device->host inside the timing.
+  roofline  the GEMV kernel alone: algorithmic bytes per launch / its event-timed duration vs MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference: the C oracle's restatement of the reference's CPU mul_mat on the box's host cores
+            (the reference is C#; no .NET toolchain exists here, so kind = "port").
+
+N > 1 (torchrun, one rank per GPU): weak scaling of the row split.  Every node's weight matrix grows to
+(4096*N) x 4096; rank r owns rows [4096 r, 4096 (r+1)) -- the reference's thread row split (Ggml.cs:6665-6672) with
+nth = N -- and the outputs are all-gathered so every rank ends the step with the full result.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_LOCAL, K, RING = 4096, 4096, 32
+Q4_0 = 2
+
+
+def alg_bytes_per_node(m, k, n=1, row_bytes=None):
+    rb = row_bytes if row_bytes is not None else k // 32 * 20
+    return m * rb + 4 * k * n + 4 * m * n
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_mul_mat_ring(nodes, nth, seconds_budget=None, repeats=1):
+    """The oracle's CPU mul_mat (reference algorithm: serial INIT quantization + row-split scalar dots) over `nodes`
+    = [(wbytes, x)], `repeats` times.  Returns seconds per pass (best)."""
+    from oracle import pyoracle as orc
+    best = None
+    t_start = time.perf_counter()
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for wb, x in nodes:
+            orc.mul_mat_2d(orc.Q4_0, wb, wb.shape[0], K, x, nth=nth)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        if seconds_budget and time.perf_counter() - t_start > seconds_budget:
+            break
+    return best
+
+
+def host_ring(n_nodes, m, seed=1001):
+    """Synthetic weights N(0, 0.02^2) -> oracle quantize_row_q4_0, activations N(0,1) (SURVEY 8d generators)."""
+    import numpy as np
+    from oracle import pyoracle as orc
+    rng = np.random.default_rng(seed)
+    nodes = []
+    base = (rng.standard_normal((m, K)) * 0.02).astype(np.float32)
+    for i in range(n_nodes):
+        w = np.roll(base, i * 17 + 1, axis=0) if i else base      # distinct bytes per node without 32 full RNG passes
+        nodes.append((orc.quantize_rows(orc.Q4_0, w), rng.standard_normal((1, K)).astype(np.float32)))
+    return nodes
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (C restatement; see module docstring) on the host cores."""
+    if rank != 0:
+        return
+    nth = os.cpu_count() or 1
+    sample_nodes = RING                                         # one step = the whole ring: ~0.5 s single-threaded
+    nodes = host_ring(sample_nodes, M_LOCAL * world)
+    for _ in range(args.warmup):
+        cpu_mul_mat_ring(nodes[:4], nth)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_mul_mat_ring(nodes, nth)
+    dt = (time.perf_counter() - t0) / args.steps
+    nbytes = sum(alg_bytes_per_node(M_LOCAL * world, K) for _ in nodes)
+    val = nbytes / dt / 1e9
+    line = {"impl": "reference", "metric": "Q4_0 mul_mat HBM GB/s (% roofline)", "value": val, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8 dot (Q4_0 x Q8_0), f32 scales", "data": "synthetic",
+            "config": {"workload": "configs[1]: Q4_0 4096x4096 GEMV, single token; ring of %d distinct matrices (%d rows each)" % (RING, M_LOCAL * world)},
+            "cpu_baseline": {"value": val, "unit": "GB/s", "cores": nth, "kind": "port",
+                             "sample": "full ring of %d GEMVs per step; C restatement of ggml_compute_forward_mul_mat_q_f32 (not .NET RyuJIT)" % RING},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "fused"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ggmlsharp_b200 import ggml, native as N
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the mul_mat path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = N.lib()
+    os.environ.setdefault("GGB200_DEVICE", str(local_rank))
+    N.check(L.ggb_init())
+    # a real (non-default) stream: a NULL stream handle means "the library's own stream" in the C ABI, and CUDA
+    # events only see work on the stream they are recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = C.c_void_p(stream.cuda_stream)
+    assert sptr.value, "expected a non-default stream"
+
+    # ---- device-resident workload: RING nodes, this rank's 4096-row slice of each ----
+    rb = K // 32 * 20
+    M_total = M_LOCAL * world
+    gen = torch.Generator(device=dev); gen.manual_seed(1001 + rank)
+    Wq = torch.empty((RING, M_LOCAL, rb), dtype=torch.uint8, device=dev)
+    for i in range(RING):
+        wf = torch.randn((M_LOCAL, K), generator=gen, device=dev, dtype=torch.float32) * 0.02
+        N.check(L.ggb_dev_quantize_rows(Q4_0, wf.data_ptr(), Wq[i].data_ptr(), M_LOCAL, K, sptr))
+    xgen = torch.Generator(device=dev); xgen.manual_seed(2001)     # same activations on every rank (replicated)
+    X = torch.randn((RING, K), generator=xgen, device=dev, dtype=torch.float32)
+    Y = torch.zeros((world, RING, M_LOCAL), dtype=torch.float32, device=dev)     # all-gather layout [rank][node][rows]
+    Yloc = Y[rank]
+    mms = (N.ggb_dev_mm * RING)()
+    for i in range(RING):
+        m = mms[i]
+        m.type, m.M, m.K, m.N = Q4_0, M_LOCAL, K, 1
+        m.W, m.nb01 = Wq[i].data_ptr(), rb
+        m.X, m.ldx_bytes = X[i].data_ptr(), 4 * K
+        m.Y, m.ldy_bytes = Yloc[i].data_ptr(), 4 * M_LOCAL
+    wsb = L.ggb_dev_workspace_bytes(mms, RING)
+    ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+    wsp = (ws.data_ptr() + 255) // 256 * 256
+    torch.cuda.synchronize()
+
+    def step():
+        N.check(L.ggb_dev_mul_mat_batch(mms, RING, wsp, wsb, sptr))
+        if world > 1:
+            dist.all_gather_into_tensor(Y.view(-1), Yloc.reshape(-1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    L.ggb_reset_stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # keep the timed region long enough for nvidia-smi to sample it (>= ~0.5 s), but time EXACTLY --steps steps
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(N.stats().kernel_launches)
+    # extra untimed steps under the sampler so short runs still see clocks under load
+    t_end = time.perf_counter() + 0.6
+    while time.perf_counter() < t_end:
+        step()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    step_bytes_rank = RING * alg_bytes_per_node(M_LOCAL, K)
+    value = world * step_bytes_rank / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (the persistent GEMV), timed alone with events around each launch ----
+    # activations are already staged in the workspace by the previous step; relaunching the batch re-runs both
+    # kernels, so the act kernel (4.7 KB out per node) is timed separately and subtracted.
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
+    one = (N.ggb_dev_mm * 1)()
+    torch.cuda.synchronize()
+    for a, b in ev:
+        a.record(stream)
+        N.check(L.ggb_dev_mul_mat_batch(mms, RING, wsp, wsb, sptr))
+        b.record(stream)
+    torch.cuda.synchronize()
+    batch_ms = sorted(a.elapsed_time(b) for a, b in ev)
+    batch_ms = sum(batch_ms) / len(batch_ms)
+    # activation kernel alone: quantize RING rows of K floats with the reference-layout Q8_0 kernel (same work shape)
+    q8 = torch.empty((RING, K // 32 * 36), dtype=torch.uint8, device=dev)
+    for a, b in ev:
+        a.record(stream)
+        N.check(L.ggb_dev_quantize_rows(8, X.data_ptr(), q8.data_ptr(), RING, K, sptr))
+        b.record(stream)
+    torch.cuda.synchronize()
+    act_ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
+    gemv_ms = max(batch_ms - act_ms, 1e-6)
+    peak, peak_src = load_peaks()
+    achieved = step_bytes_rank / (gemv_ms * 1e-3) / 1e9
+
+    line = {"metric": "Q4_0 mul_mat HBM GB/s (% roofline)", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 dot (Q4_0 x Q8_0), f32 scales", "data": "synthetic",
+            "config": {"workload": "configs[1]: Q4_0 4096x4096 GEMV, single token", "ring": RING,
+                       "step": "%d independent MUL_MAT nodes (distinct weights, %.1f MB > 2x L2, no flush needed), 1 act + 1 GEMV launch" % (RING, RING * M_LOCAL * rb / 1e6),
+                       "rows_per_rank": M_LOCAL, "rows_total": M_total, "k": K,
+                       "parallelism": "row-split x%d + all-gather (%s)" % (world, args.gather) if world > 1 else "1 GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_gemv<Q4_0,1>", "launch_ms": gemv_ms, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0, "batch_ms": batch_ms, "act_ms": act_ms},
+            "gpu_launches": launches, "clocks": clocks}
+
+    if rank == 0:
+        # ---- e2e: reference-shaped API over a host arena (weights cached on device after the first compute) ----
+        e2e = None
+        if world == 1:
+            arena = RING * (M_LOCAL * rb + 4 * K + 4 * M_LOCAL + 3 * 256) + (8 << 20)
+            wq_host = Wq.cpu().numpy()
+            x_host = X.cpu().numpy()
+            with ggml.Context(arena) as c:
+                ys = []
+                g = None
+                for i in range(RING):
+                    a = c.tensor_from(N.Q4_0, K, M_LOCAL, data=wq_host[i])
+                    b = c.tensor_from(N.F32, K, data=x_host[i])
+                    y = c.mul_mat(a, b)
+                    ys.append(y)
+                    if g is None:
+                        g = c.build_forward(y)
+                    else:
+                        N.host().ggml_build_forward_expand(C.byref(g), y)
+                for _ in range(3):
+                    c.graph_compute(g)
+                L.ggb_reset_stats()
+                n_e2e = max(10, min(args.steps, 100))
+                t0 = time.perf_counter()
+                for _ in range(n_e2e):
+                    c.graph_compute(g)
+                dt = (time.perf_counter() - t0) / n_e2e
+                s = N.stats()
+                # check the API path against the device-resident path on node 0
+                y0 = ggml.tensor_f32(ys[0]).reshape(-1)
+                ref0 = Y[0, 0].cpu().numpy()
+                assert np.array_equal(y0, ref0), "e2e result differs from the device-resident result"
+                e2e = {"value": step_bytes_rank / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
+                       "h2d_bytes_per_step": int(s.h2d_bytes // n_e2e), "d2h_bytes_per_step": int(s.d2h_bytes // n_e2e),
+                       "api": "ggml_graph_compute over a %d-node graph (host arena; weights device-cached)" % RING}
+        line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            nth = os.cpu_count() or 1
+            nodes = host_ring(8, M_LOCAL)
+            sec = cpu_mul_mat_ring(nodes, nth, seconds_budget=15, repeats=5)
+            line["cpu_baseline"] = {"value": 8 * alg_bytes_per_node(M_LOCAL, K) / sec / 1e9, "unit": "GB/s", "cores": nth, "kind": "port",
+                                    "sample": "8 of the %d ring GEMVs, best of <=5 passes; C restatement of the reference algorithm (not .NET RyuJIT)" % RING}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

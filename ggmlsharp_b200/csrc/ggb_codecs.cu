@@ -13,7 +13,12 @@ namespace ggb {
 
 namespace {
 
-__device__ __forceinline__ int rne_i(float v) { return __float2int_rn(v); }   // cvt.rni.s32.f32: ties-to-even
+// (byte)Math.Round(v) as .NET 8 / x64 evaluates it: ties-to-even, then cvttsd2si + truncation to 8 bits; NaN and
+// values outside int32 (only reachable when 1/d overflowed to infinity on a subnormal scale) give byte 0.
+__device__ __forceinline__ int cs_byte(float r) { return (r != r || fabsf(r) >= 2147483648.0f) ? 0 : (__float2int_rz(r) & 0xFF); }
+__device__ __forceinline__ int rne_byte(float v) { return cs_byte(rintf(v)); }
+// (byte)Math.Min(15, Math.Round(v) + 8): Math.Min propagates NaN
+__device__ __forceinline__ int rne_q4_0(float v) { const float r = rintf(v) + 8.0f; return (r != r) ? 0 : (r >= 15.0f ? 15 : cs_byte(r)); }
 
 // (amax, signed value) of the FIRST element with the largest magnitude: `if (amax < |v|)` (Ggml.cs:349)
 struct FirstAbsMax { float amax, val; };
@@ -53,7 +58,7 @@ __global__ void __launch_bounds__(256) k_quantize_rows(const float *__restrict__
         const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
         int q[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) q[i] = min(15, rne_i(__fmul_rn(e[i], id)) + 8) & 0xFF;
+        for (int i = 0; i < 4; i++) q[i] = rne_q4_0(__fmul_rn(e[i], id));
         uint32_t h = (uint32_t)(q[0] | (q[1] << 4)) & 0xFF;
         h |= ((uint32_t)(q[2] | (q[3] << 4)) & 0xFF) << 8;
         const uint32_t hn = __shfl_down_sync(0xffffffffu, h, 1);
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(256) k_quantize_rows(const float *__restrict__
         const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
         int q[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) q[i] = rne_i(__fmul_rn(__fsub_rn(e[i], mn), id)) & 0xFF;   // (byte), no clamp
+        for (int i = 0; i < 4; i++) q[i] = rne_byte(__fmul_rn(__fsub_rn(e[i], mn), id));   // (byte), no clamp
         uint32_t h = (uint32_t)(q[0] | (q[1] << 4)) & 0xFF;
         h |= ((uint32_t)(q[2] | (q[3] << 4)) & 0xFF) << 8;
         const uint32_t hn = __shfl_down_sync(0xffffffffu, h, 1);
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(256) k_quantize_rows(const float *__restrict__
         const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
         int q[4], s = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { q[i] = rne_i(__fmul_rn(e[i], id)); s += q[i]; }
+        for (int i = 0; i < 4; i++) { q[i] = (int)(int8_t)rne_byte(__fmul_rn(e[i], id)); s += q[i]; }
         const uint32_t w = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
         if (TYPE == GGML_TYPE_Q8_0) {
             if (live) {
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
         const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
         int q[4], s = 0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) { q[i] = rne_i(__fmul_rn(e[i], id)); s += q[i]; }
+        for (int i = 0; i < 4; i++) { q[i] = (int)(int8_t)rne_byte(__fmul_rn(e[i], id)); s += q[i]; }
 #pragma unroll
         for (int off = 1; off < 8; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         uint32_t ev = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[2] & 0xFF) << 8);
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(256) k_act_f16_dequant(int wtype, const float 
         const float d = __fdiv_rn(amax, 127.0f);
         const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
 #pragma unroll
-        for (int i = 0; i < 4; i++) e[i] = __fmul_rn(d, (float)rne_i(__fmul_rn(e[i], id)));
+        for (int i = 0; i < 4; i++) e[i] = __fmul_rn(d, (float)(int)(int8_t)rne_byte(__fmul_rn(e[i], id)));
     }
     const __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
     uint2 pk; pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);

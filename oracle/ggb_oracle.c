@@ -96,6 +96,17 @@ float orc_f16_to_f32(uint16_t h)
 
 /* ---- row quantizers ---- */
 
+/* C# `(byte)someDouble` on .NET 8 / x64 is cvttsd2si + truncation: NaN and values outside int32 give the
+ * "integer indefinite" 0x80000000, whose low byte is 0.  Only reachable when a block's scale is so small
+ * (subnormal) that 1/d overflows to infinity; kept so that even those blocks are bit-defined. */
+static inline uint8_t cs_byte(double t)
+{
+    if (t != t || t >= 2147483648.0 || t < -2147483648.0) return 0;
+    return (uint8_t)(int32_t)t;
+}
+/* Math.Min(double, double) propagates NaN (C fmin does not). */
+static inline double cs_min(double a, double b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
+
 /* Ggml.cs:334-377 quantize_row_q4_0_reference_impl (the bit-exactness target). */
 void orc_quantize_row_q4_0(const float *x, void *vy, int k)
 {
@@ -113,10 +124,8 @@ void orc_quantize_row_q4_0(const float *x, void *vy, int k)
         for (int l = 0; l < QK; l += 2) {
             const float v0 = x[i * QK + l + 0] * id;
             const float v1 = x[i * QK + l + 1] * id;
-            const double r0 = fmin(15.0, nearbyint((double)v0) + 8.0);
-            const double r1 = fmin(15.0, nearbyint((double)v1) + 8.0);
-            const uint8_t vi0 = (uint8_t)(int)r0;
-            const uint8_t vi1 = (uint8_t)(int)r1;
+            const uint8_t vi0 = cs_byte(cs_min(15.0, nearbyint((double)v0) + 8.0));
+            const uint8_t vi1 = cs_byte(cs_min(15.0, nearbyint((double)v1) + 8.0));
             y[i].qs[l / 2] = (uint8_t)(vi0 | (vi1 << 4));
         }
     }
@@ -141,8 +150,8 @@ void orc_quantize_row_q4_1(const float *x, void *vy, int k)
         for (int l = 0; l < QK; l += 2) {
             const float v0 = (x[i * QK + l + 0] - min) * id;
             const float v1 = (x[i * QK + l + 1] - min) * id;
-            const uint8_t vi0 = (uint8_t)(int)nearbyint((double)v0);   /* no clamp */
-            const uint8_t vi1 = (uint8_t)(int)nearbyint((double)v1);
+            const uint8_t vi0 = cs_byte(nearbyint((double)v0));   /* no clamp */
+            const uint8_t vi1 = cs_byte(nearbyint((double)v1));
             y[i].qs[l / 2] = (uint8_t)(vi0 | (vi1 << 4));
         }
     }
@@ -164,7 +173,7 @@ void orc_quantize_row_q8_0(const float *x, void *vy, int k)
         y[i].d = d;
         for (int l = 0; l < QK; l++) {
             const float v0 = x[i * QK + l] * id;
-            y[i].qs[l] = (int8_t)(int)nearbyint((double)v0);
+            y[i].qs[l] = (int8_t)cs_byte(nearbyint((double)v0));
         }
     }
 }
@@ -187,8 +196,8 @@ void orc_quantize_row_q8_1(const float *x, void *vy, int k)
         for (int l = 0; l < QK / 2; l++) {
             const float v0 = x[i * QK + l] * id;
             const float v1 = x[i * QK + QK / 2 + l] * id;
-            y[i].qs[l] = (int8_t)(int)nearbyint((double)v0);
-            y[i].qs[QK / 2 + l] = (int8_t)(int)nearbyint((double)v1);
+            y[i].qs[l] = (int8_t)cs_byte(nearbyint((double)v0));
+            y[i].qs[QK / 2 + l] = (int8_t)cs_byte(nearbyint((double)v1));
             sum0 += y[i].qs[l];
             sum1 += y[i].qs[QK / 2 + l];
         }
