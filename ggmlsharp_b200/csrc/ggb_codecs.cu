@@ -200,11 +200,12 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
         od |= __shfl_down_sync(0xffffffffu, od, 1) << 16;
         if (live) {
             uint8_t *o = nd.out + (long long)row * b.row_bytes;
+            const int idx = b.bps > 1 ? (col % b.bps) * (b.kb / b.bps) + col / b.bps : col;
             if ((sub & 1) == 0) {
-                reinterpret_cast<uint32_t *>(o + (long long)col * 16)[sub >> 1] = ev;
-                reinterpret_cast<uint32_t *>(o + (long long)b.kb * 16 + (long long)col * 16)[sub >> 1] = od;
+                reinterpret_cast<uint32_t *>(o + (long long)idx * 16)[sub >> 1] = ev;
+                reinterpret_cast<uint32_t *>(o + (long long)b.kb * 16 + (long long)idx * 16)[sub >> 1] = od;
             }
-            if (sub == 1) *reinterpret_cast<int2 *>(o + (long long)b.kb * 32 + (long long)col * 8) = make_int2(__float_as_int(d), s);
+            if (sub == 1) *reinterpret_cast<int2 *>(o + (long long)b.kb * 32 + (long long)idx * 8) = make_int2(__float_as_int(d), s);
         }
     } else {
         // F16 weights: src1 -> Half (Ggml.cs:6362-6379); F32 weights: dense copy.  One thread per 4 elements.

@@ -332,6 +332,253 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_gemv(const __grid_constant__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: rows are whole 16-byte-aligned "units" (Q4_0: 4 blocks = 80 B, Q4_1: 2 blocks = 48 B,
+// F16/F32: 16 B), so a lane reads a unit with LDS.128 (lane strides of 20 / 12 / 4 words are
+// bank-conflict free) and every bulk copy is legal.  16 warps per CTA, stage/phase counters instead
+// of div/mod, and -- for single-token Q4 nodes with K <= 4096 -- the lane's slice of the quantized
+// activation vector lives in registers for the whole node.
+// Activation layout for Q4 types here is "unit-major": block b = bps*u + j is stored at plane index
+// j*S + u (S = units per row), so lanes reading consecutive units hit consecutive 16-byte slots.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int NWF = 16;
+
+struct XBlk { int4 ev, od; int2 ds; };
+
+__device__ __forceinline__ int q4_isum(const uint32_t q0, const uint32_t q1, const uint32_t q2, const uint32_t q3, const XBlk &x, int s)
+{
+    s = __dp4a((int)(q0 & 0x0F0F0F0Fu), x.ev.x, s); s = __dp4a((int)((q0 >> 4) & 0x0F0F0F0Fu), x.od.x, s);
+    s = __dp4a((int)(q1 & 0x0F0F0F0Fu), x.ev.y, s); s = __dp4a((int)((q1 >> 4) & 0x0F0F0F0Fu), x.od.y, s);
+    s = __dp4a((int)(q2 & 0x0F0F0F0Fu), x.ev.z, s); s = __dp4a((int)((q2 >> 4) & 0x0F0F0F0Fu), x.od.z, s);
+    s = __dp4a((int)(q3 & 0x0F0F0F0Fu), x.ev.w, s); s = __dp4a((int)((q3 >> 4) & 0x0F0F0F0Fu), x.od.w, s);
+    return s;
+}
+
+__device__ __forceinline__ XBlk load_xblk(const uint8_t *xc, int kb, int idx)
+{
+    XBlk x;
+    x.ev = *reinterpret_cast<const int4 *>(xc + idx * 16);
+    x.od = *reinterpret_cast<const int4 *>(xc + kb * 16 + idx * 16);
+    x.ds = *reinterpret_cast<const int2 *>(xc + kb * 32 + idx * 8);
+    return x;
+}
+
+// one Q4_0 unit (4 blocks, 80 bytes at w) against 4 activation blocks
+__device__ __forceinline__ float q4_0_unit(const uint8_t *w, const XBlk (&x)[4], float acc)
+{
+    const uint4 *wp = reinterpret_cast<const uint4 *>(w);
+    const uint4 a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
+    // words: d0 q q q q | d1 q q q q | d2 q q q q | d3 q q q q
+    int s;
+    s = q4_isum(a0.y, a0.z, a0.w, a1.x, x[0], x[0].ds.y * -8);
+    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(__uint_as_float(a0.x), __int_as_float(x[0].ds.x)), (float)s));
+    s = q4_isum(a1.z, a1.w, a2.x, a2.y, x[1], x[1].ds.y * -8);
+    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(__uint_as_float(a1.y), __int_as_float(x[1].ds.x)), (float)s));
+    s = q4_isum(a2.w, a3.x, a3.y, a3.z, x[2], x[2].ds.y * -8);
+    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(__uint_as_float(a2.z), __int_as_float(x[2].ds.x)), (float)s));
+    s = q4_isum(a4.x, a4.y, a4.z, a4.w, x[3], x[3].ds.y * -8);
+    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(__uint_as_float(a3.w), __int_as_float(x[3].ds.x)), (float)s));
+    return acc;
+}
+
+// one Q4_1 unit (2 blocks, 48 bytes at w) against 2 activation blocks
+__device__ __forceinline__ float q4_1_unit(const uint8_t *w, const XBlk (&x)[4], float acc)
+{
+    const uint4 *wp = reinterpret_cast<const uint4 *>(w);
+    const uint4 a0 = wp[0], a1 = wp[1], a2 = wp[2];
+    // words: d0 m0 q q | q q d1 m1 | q q q q
+    int s = q4_isum(a0.z, a0.w, a1.x, a1.y, x[0], 0);
+    float d1 = __int_as_float(x[0].ds.x);
+    acc += (__uint_as_float(a0.x) * d1) * (float)s + (__uint_as_float(a0.y) * d1) * (float)x[0].ds.y;
+    s = q4_isum(a2.x, a2.y, a2.z, a2.w, x[1], 0);
+    d1 = __int_as_float(x[1].ds.x);
+    acc += (__uint_as_float(a1.z) * d1) * (float)s + (__uint_as_float(a1.w) * d1) * (float)x[1].ds.y;
+    return acc;
+}
+
+template <int TYPE> struct UnitTraits { static constexpr int BYTES = 16, BPS = 0; };
+template <> struct UnitTraits<GGML_TYPE_Q4_0> { static constexpr int BYTES = 80, BPS = 4; };
+template <> struct UnitTraits<GGML_TYPE_Q4_1> { static constexpr int BYTES = 48, BPS = 2; };
+
+// partial dot of `nunits` staged units starting at unit u0 of the row
+template <int TYPE, int NC, bool XREG>
+__device__ __forceinline__ void dot_units(const uint8_t *w, int u0, int nunits, int S, int kb, const uint8_t *xs, int xcol_bytes,
+                                          const XBlk (&xr)[4], int lane, float (&acc)[NC])
+{
+    constexpr int UB = UnitTraits<TYPE>::BYTES, BPS = UnitTraits<TYPE>::BPS;
+    if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_1) {
+        if (XREG) {                                               // NC == 1, S <= 32: this lane owns unit `lane`
+            if (lane < nunits) acc[0] = TYPE == GGML_TYPE_Q4_0 ? q4_0_unit(w + lane * UB, xr, acc[0]) : q4_1_unit(w + lane * UB, xr, acc[0]);
+        } else {
+            for (int u = lane; u < nunits; u += 32) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    XBlk x[4];
+#pragma unroll
+                    for (int j = 0; j < BPS; j++) x[j] = load_xblk(xs + c * xcol_bytes, kb, j * S + u0 + u);
+                    acc[c] = TYPE == GGML_TYPE_Q4_0 ? q4_0_unit(w + u * UB, x, acc[c]) : q4_1_unit(w + u * UB, x, acc[c]);
+                }
+            }
+        }
+    } else if (TYPE == GGML_TYPE_F16) {
+        dot_f16<NC>(w, u0 * 16, nunits * 16, xs, xcol_bytes, lane, acc);
+    } else {
+        dot_f32<NC>(w, u0 * 16, nunits * 16, xs, xcol_bytes, lane, acc);
+    }
+}
+
+template <int TYPE, int NC, bool XREG>
+__global__ void __launch_bounds__(NWF * 32, 1) k_gemv_fast(const __grid_constant__ GemvBatch b)
+{
+    constexpr int UB = UnitTraits<TYPE>::BYTES, BPS = UnitTraits<TYPE>::BPS;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int depth = b.depth, stage_bytes = b.stage_bytes, rs = b.rs, nchunk = b.nchunk, row_bytes = b.row_bytes, chunk_bytes = b.chunk_bytes;
+    const int xcol_bytes = b.xcol_bytes, kb = b.K / GGB_QK;
+    const int S = row_bytes / UB;                                 // units per row
+    const int chunk_units = chunk_bytes / UB;
+    const long long nb01 = b.nb01;
+    const int xbytes = (NC * xcol_bytes + 127) & ~127;
+    uint8_t *xs = smem;
+    uint8_t *stages = smem + xbytes + (size_t)warp * depth * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + xbytes + (size_t)NWF * depth * stage_bytes) + warp * MAX_DEPTH;
+    const uint32_t bar0 = smem_u32(bars), stage0 = smem_u32(stages);
+
+    const int g_begin = (int)((long long)b.total_groups * blockIdx.x / gridDim.x);
+    const int g_end = (int)((long long)b.total_groups * (blockIdx.x + 1) / gridDim.x);
+
+    if (lane == 0) {
+        for (int s = 0; s < depth; s++) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    // producer cursor: groups g_begin+warp, +NWF, ...; each group is nchunk copies
+    int pg = g_begin + warp, pc = 0, pn = 0, pst = 0;
+    auto issue = [&]() {
+        while (pg >= b.node[pn].g0 + b.node[pn].ngroups) pn++;
+        const int row0 = (pg - b.node[pn].g0) * rs;
+        if (lane == 0) {
+            const int rows = min(rs, b.node[pn].M - row0);
+            const uint32_t bytes = nchunk == 1 ? (uint32_t)(rows * row_bytes) : (uint32_t)min(chunk_bytes, row_bytes - pc * chunk_bytes);
+            const uint32_t bar = bar0 + 8 * pst;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(stage0 + pst * stage_bytes, b.node[pn].W + (long long)row0 * nb01 + (long long)pc * chunk_bytes, bytes, bar);
+        }
+        if (++pst == depth) pst = 0;
+        if (++pc == nchunk) { pc = 0; pg += NWF; }
+    };
+    for (int i = 0; i < depth && pg < g_end; i++) issue();
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (g_begin >= g_end) return;
+
+    int st = 0; uint32_t ph = 0;
+    int n = 0;
+    while (g_begin >= b.node[n].g0 + b.node[n].ngroups) n++;
+    for (; n < b.n_nodes && b.node[n].g0 < g_end; n++) {
+        const int ng0 = b.node[n].g0, nM = b.node[n].M, nldy = b.node[n].ldy;
+        float *const ny = b.node[n].y;
+        XBlk xr[4];
+        if (XREG) {
+            // lane u keeps activation blocks BPS*u .. BPS*u+BPS-1 of this node (read straight from the act workspace)
+            const uint8_t *xq = b.node[n].xq;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (j < BPS) xr[j] = lane < S ? load_xblk(xq, kb, j * S + lane) : XBlk{make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int2(0, 0)};
+        } else {
+            __syncthreads();
+            const uint4 *src = reinterpret_cast<const uint4 *>(b.node[n].xq);
+            uint4 *dst = reinterpret_cast<uint4 *>(xs);
+            for (int i = threadIdx.x; i < (NC * xcol_bytes) >> 4; i += NWF * 32) dst[i] = src[i];
+            __syncthreads();
+        }
+        const int seg_lo = max(g_begin, ng0), seg_hi = min(g_end, ng0 + b.node[n].ngroups);
+        int g = seg_lo + ((warp - (seg_lo - g_begin)) & (NWF - 1));
+        for (; g < seg_hi; g += NWF) {
+            const int row0 = (g - ng0) * rs;
+            const int rows = min(rs, nM - row0);
+            float acc[NC];
+#pragma unroll
+            for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
+            for (int c = 0; c < nchunk; c++) {
+                mbar_wait(bar0 + 8 * st, ph);
+                const uint8_t *stage = stages + (size_t)st * stage_bytes;
+                if (nchunk == 1) {
+                    for (int r = 0; r < rows; r++) {
+                        if (r) {
+#pragma unroll
+                            for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
+                        }
+                        dot_units<TYPE, NC, XREG>(stage + r * row_bytes, 0, S, S, kb, xs, xcol_bytes, xr, lane, acc);
+#pragma unroll
+                        for (int cc = 0; cc < NC; cc++) {
+                            const float v = warp_sum(acc[cc]);
+                            if (lane == 0) {
+                                float *yp = ny + (long long)cc * nldy + row0 + r;
+                                *yp = v;
+                                for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
+                            }
+                        }
+                    }
+                } else {
+                    const int nunits = min(chunk_units, S - c * chunk_units);
+                    dot_units<TYPE, NC, false>(stage, c * chunk_units, nunits, S, kb, xs, xcol_bytes, xr, lane, acc);
+                    if (c == nchunk - 1) {
+#pragma unroll
+                        for (int cc = 0; cc < NC; cc++) {
+                            const float v = warp_sum(acc[cc]);
+                            if (lane == 0) {
+                                float *yp = ny + (long long)cc * nldy + row0;
+                                *yp = v;
+                                for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                                    // every lane has finished reading this stage
+                if (pg < g_end) issue();
+                if (++st == depth) { st = 0; ph ^= 1; }
+            }
+        }
+    }
+}
+
+template <int TYPE>
+int launch_fast_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s, bool pdl)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NWF * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    constexpr bool Q = TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_1;
+    const bool xreg = Q && b.ncols == 1 && b.nchunk == 1 && b.row_bytes / UnitTraits<TYPE>::BYTES <= 32;
+#define GGB_FAST_CASE(NCV, XR) { \
+        static bool attr_set = false; \
+        if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemv_fast<TYPE, NCV, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; } \
+        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemv_fast<TYPE, NCV, XR>, b)); }
+    if (xreg) { if constexpr (Q) GGB_FAST_CASE(1, true) }
+    else switch (b.ncols) {
+        case 1: GGB_FAST_CASE(1, false) break;
+        case 2: GGB_FAST_CASE(2, false) break;
+        case 4: GGB_FAST_CASE(4, false) break;
+        case 8: GGB_FAST_CASE(8, false) break;
+        default: return set_error(GGB_E_INVALID, "gemv: ncols=%d", b.ncols);
+    }
+#undef GGB_FAST_CASE
+    count_launch();
+    return GGB_OK;
+}
+
 template <int TYPE>
 int launch_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s, bool pdl)
 {
@@ -364,6 +611,7 @@ constexpr int STAGE_MAX = 4096;            // bytes of one bulk copy (one row, s
 } // namespace
 
 int gemv_num_ctas() { return device_sm_count(); }
+int gemv_act_bps(const GemvBatch &b) { return !b.async ? 1 : b.type == GGML_TYPE_Q4_0 ? 4 : b.type == GGML_TYPE_Q4_1 ? 2 : 1; }
 
 // Fills the shape-dependent fields of b (everything but the node list).  ncols in {1,2,4,8}.
 int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase)
@@ -377,8 +625,8 @@ int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const 
     b.type = type; b.ncols = ncols; b.K = (int)K; b.row_bytes = (int)row_bytes; b.nb01 = nb01; b.xcol_bytes = (int)xcol;
     const int unit_async = type == GGML_TYPE_Q4_0 ? 80 : type == GGML_TYPE_Q4_1 ? 48 : 16;
     const int unit_sync = type == GGML_TYPE_Q4_0 ? 20 : type == GGML_TYPE_Q4_1 ? 24 : 16;
-    b.async = ((reinterpret_cast<uintptr_t>(Wbase) & 15) == 0 && (nb01 & 15) == 0 && (row_bytes & 15) == 0 &&
-               (row_bytes <= STAGE_MAX || row_bytes % unit_async == 0)) ? 1 : 0;
+    // 16-byte aligned rows made of whole units -> TMA bulk staging + the fast kernel; anything else -> plain-load staging
+    b.async = ((reinterpret_cast<uintptr_t>(Wbase) & 15) == 0 && (nb01 & 15) == 0 && (row_bytes & 15) == 0 && row_bytes % unit_async == 0) ? 1 : 0;
     const int unit = b.async ? unit_async : unit_sync;
     if (row_bytes <= STAGE_MAX) {
         b.nchunk = 1;
@@ -397,9 +645,10 @@ int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const 
         b.stage_bytes = (int)align_up((size_t)b.chunk_bytes, 16);
     }
     const long long xbytes = (xcol * ncols + 127) & ~127ll;
-    long long wbudget = 227 * 1024 - xbytes - NWARPS * MAX_DEPTH * 8 - 1024;
+    const int nw = b.async ? NWF : NWARPS;
+    long long wbudget = 227 * 1024 - xbytes - nw * MAX_DEPTH * 8 - 1024;
     if (wbudget > W_BUDGET) wbudget = W_BUDGET;
-    int depth = b.async ? (int)(wbudget / ((long long)NWARPS * b.stage_bytes)) : 1;
+    int depth = b.async ? (int)(wbudget / ((long long)nw * b.stage_bytes)) : 1;
     if (depth > MAX_DEPTH) depth = MAX_DEPTH;
     if (depth < 1) return set_error(GGB_E_UNSUPPORTED, "mul_mat: shape needs more shared memory than one SM has");
     b.depth = depth;
@@ -410,10 +659,18 @@ int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl)
 {
     if (b.n_nodes <= 0 || b.total_groups <= 0) return GGB_OK;
     const size_t xbytes = ((size_t)b.ncols * b.xcol_bytes + 127) & ~(size_t)127;
-    const size_t smem = xbytes + (size_t)NWARPS * b.depth * b.stage_bytes + NWARPS * MAX_DEPTH * 8;
+    const int nw = b.async ? NWF : NWARPS;
+    const size_t smem = xbytes + (size_t)nw * b.depth * b.stage_bytes + nw * MAX_DEPTH * 8;
     int grid = gemv_num_ctas();
-    const int want = (b.total_groups + NWARPS - 1) / NWARPS;
+    const int want = (b.total_groups + nw - 1) / nw;
     if (grid > want) grid = want;
+    if (b.async) switch (b.type) {
+    case GGML_TYPE_Q4_0: return launch_fast_typed<GGML_TYPE_Q4_0>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q4_1: return launch_fast_typed<GGML_TYPE_Q4_1>(b, smem, grid, s, pdl);
+    case GGML_TYPE_F16: return launch_fast_typed<GGML_TYPE_F16>(b, smem, grid, s, pdl);
+    case GGML_TYPE_F32: return launch_fast_typed<GGML_TYPE_F32>(b, smem, grid, s, pdl);
+    default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6739-6742)", b.type);
+    }
     switch (b.type) {
     case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0>(b, smem, grid, s, pdl);
     case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1>(b, smem, grid, s, pdl);

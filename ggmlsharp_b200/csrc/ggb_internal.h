@@ -36,7 +36,8 @@ int launch_dequantize_rows(int type, const void *src, float *dst, int64_t nrows,
 //   F16 weights:       K halfs (RNE), F32 weights: K floats (copied so every row is 16-byte aligned and dense)
 size_t act_row_bytes(int wtype, int64_t K);
 struct ActNode { const float *x; long long ldx_bytes; uint8_t *out; int N; int blk0; };
-struct ActBatch { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; ActNode node[64]; };
+// bps > 1: unit-major Q8P planes for the fast GEMV (block b = bps*u + j stored at plane index j*(kb/bps) + u); else linear
+struct ActBatch { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; ActNode node[64]; };
 int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl);
 // batched path: activations as dense fp16 [Npad][K] holding d * q (the value the reference's dot multiplies by)
 int launch_act_f16_dequant(int wtype, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s);
@@ -58,6 +59,7 @@ struct GemvBatch {
 };
 int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl);
 int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase_probe);
+int gemv_act_bps(const GemvBatch &b);   // the ActBatch::bps the planned kernel expects
 int gemv_num_ctas();
 
 // ---- GEMM (ggb_gemm.cu): tcgen05 batched path ----

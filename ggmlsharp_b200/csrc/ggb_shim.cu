@@ -136,10 +136,22 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     for (size_t a0 = 0; a0 < gemv_idx.size(); a0++) {
         const int i0 = gemv_idx[a0];
         if (done[i0]) continue;
+        // the activation layout depends on which GEMV kernel will read it, so that is part of the key
+        auto act_bps = [&](const ggb_dev_mm &m, int &bps) -> int {
+            GemvBatch probe = {};
+            int r = gemv_plan(probe, m.type, m.K, m.nb01, 1, m.W);
+            bps = r ? 0 : gemv_act_bps(probe);
+            return r;
+        };
+        int bps0 = 1;
+        { int r = act_bps(mm[i0], bps0); if (r) return r; }
         std::vector<int> grp;
         for (size_t a1 = a0; a1 < gemv_idx.size(); a1++) {
             const int i = gemv_idx[a1];
-            if (!done[i] && mm[i].type == mm[i0].type && mm[i].K == mm[i0].K) { grp.push_back(i); done[i] = 1; }
+            if (done[i] || mm[i].type != mm[i0].type || mm[i].K != mm[i0].K) continue;
+            int bps = 1;
+            { int r = act_bps(mm[i], bps); if (r) return r; }
+            if (bps == bps0) { grp.push_back(i); done[i] = 1; }
         }
         const int type = mm[i0].type; const int64_t K = mm[i0].K;
         const size_t arow = act_row_bytes(type, K);
@@ -147,7 +159,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         // activation staging (INIT phase)
         for (size_t c0 = 0; c0 < grp.size(); c0 += 64) {
             ActBatch ab = {};
-            ab.K = (int)K; ab.kb = (int)(K / GGB_QK); ab.row_bytes = (int)arow; ab.wtype = type; ab.vec16 = 1;
+            ab.K = (int)K; ab.kb = (int)(K / GGB_QK); ab.row_bytes = (int)arow; ab.wtype = type; ab.vec16 = 1; ab.bps = bps0;
             int tot = 0;
             for (size_t c = c0; c < std::min(grp.size(), c0 + 64); c++) {
                 const ggb_dev_mm &m = mm[grp[c]];
@@ -180,7 +192,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
             auto compatible = [&](const Pass &ps) {
                 const ggb_dev_mm &m = mm[ps.i];
                 if (ps.nc != passes[p0].nc || m.nb01 != m0.nb01 || m.n_peers != m0.n_peers) return false;
-                if (((reinterpret_cast<uintptr_t>(m.W) & 15) == 0) != ((reinterpret_cast<uintptr_t>(m0.W) & 15) == 0)) return false;
+                if (((reinterpret_cast<uintptr_t>(m.W) & 15) == 0) != ((reinterpret_cast<uintptr_t>(m0.W) & 15) == 0)) return false;   // same staging mode
                 for (int p = 0; p < m.n_peers; p++)
                     if ((long long)(reinterpret_cast<char *>(m.Y_peer[p]) - reinterpret_cast<char *>(m.Y)) != gb.peer_delta[p]) return false;
                 return true;
