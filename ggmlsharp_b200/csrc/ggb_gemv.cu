@@ -21,6 +21,8 @@
 // Roofline: HBM.  Algorithmic bytes per node = M*row_bytes (weights) + 4*K*N (x) + 4*M*N (y).
 #include "ggb_internal.h"
 
+#include <algorithm>
+
 namespace ggb {
 
 namespace {
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_gemv(const __grid_constant__
 // j*S + u (S = units per row), so lanes reading consecutive units hit consecutive 16-byte slots.
 // ------------------------------------------------------------------------------------------------
 
-constexpr int NWF = 16;
+constexpr int NWF = 15;      // consumer warps; +1 producer warp = 16 warps = 512 threads -> 128 registers per thread
 
 struct XBlk { int4 ev, od; int2 ds; };
 
@@ -429,121 +431,134 @@ __device__ __forceinline__ void dot_units(const uint8_t *w, int u0, int nunits, 
     }
 }
 
+// CTA = NWF consumer warps + 1 producer warp.  A stage holds one "tile": TR = NWF*rpw consecutive rows
+// (or, for rows longer than one copy, one K-chunk of NWF rows); the producer warp's lanes issue one
+// bulk copy per row onto the stage's full-barrier and run `depth` stages ahead; consumer warp w owns
+// rows w*rpw .. w*rpw+rpw-1 of every tile and releases the stage through its empty-barrier.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 template <int TYPE, int NC, bool XREG>
-__global__ void __launch_bounds__(NWF * 32, 1) k_gemv_fast(const __grid_constant__ GemvBatch b)
+__global__ void __launch_bounds__((NWF + 1) * 32, 1) k_gemv_fast(const __grid_constant__ GemvBatch b)
 {
     constexpr int UB = UnitTraits<TYPE>::BYTES, BPS = UnitTraits<TYPE>::BPS;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int depth = b.depth, stage_bytes = b.stage_bytes, rs = b.rs, nchunk = b.nchunk, row_bytes = b.row_bytes, chunk_bytes = b.chunk_bytes;
-    const int xcol_bytes = b.xcol_bytes, kb = b.K / GGB_QK;
-    const int S = row_bytes / UB;                                 // units per row
-    const int chunk_units = chunk_bytes / UB;
-    const long long nb01 = b.nb01;
-    const int xbytes = (NC * xcol_bytes + 127) & ~127;
+    const int depth = b.depth, stage_bytes = b.stage_bytes, rpw = b.rs, nchunk = b.nchunk, row_bytes = b.row_bytes, chunk_bytes = b.chunk_bytes;
+    const int TR = NWF * rpw;
+    const int xbytes = (NC * b.xcol_bytes + 127) & ~127;
     uint8_t *xs = smem;
-    uint8_t *stages = smem + xbytes + (size_t)warp * depth * stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + xbytes + (size_t)NWF * depth * stage_bytes) + warp * MAX_DEPTH;
-    const uint32_t bar0 = smem_u32(bars), stage0 = smem_u32(stages);
+    uint8_t *stages = smem + xbytes;
+    const uint32_t stage0 = smem_u32(stages);
+    const uint32_t full0 = smem_u32(smem + xbytes + (size_t)depth * stage_bytes), empty0 = full0 + 8 * MAX_DEPTH;
 
-    const int g_begin = (int)((long long)b.total_groups * blockIdx.x / gridDim.x);
-    const int g_end = (int)((long long)b.total_groups * (blockIdx.x + 1) / gridDim.x);
+    const int t_begin = (int)((long long)b.total_groups * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)b.total_groups * (blockIdx.x + 1) / gridDim.x);
 
-    if (lane == 0) {
-        for (int s = 0; s < depth; s++) mbar_init(bar0 + 8 * s, 1);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < depth; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NWF); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncwarp();
+    __syncthreads();
 
-    // producer cursor: groups g_begin+warp, +NWF, ...; each group is nchunk copies
-    int pg = g_begin + warp, pc = 0, pn = 0, pst = 0;
-    auto issue = [&]() {
-        while (pg >= b.node[pn].g0 + b.node[pn].ngroups) pn++;
-        const int row0 = (pg - b.node[pn].g0) * rs;
-        if (lane == 0) {
-            const int rows = min(rs, b.node[pn].M - row0);
-            const uint32_t bytes = nchunk == 1 ? (uint32_t)(rows * row_bytes) : (uint32_t)min(chunk_bytes, row_bytes - pc * chunk_bytes);
-            const uint32_t bar = bar0 + 8 * pst;
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(stage0 + pst * stage_bytes, b.node[pn].W + (long long)row0 * nb01 + (long long)pc * chunk_bytes, bytes, bar);
-        }
-        if (++pst == depth) pst = 0;
-        if (++pc == nchunk) { pc = 0; pg += NWF; }
-    };
-    for (int i = 0; i < depth && pg < g_end; i++) issue();
-
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (g_begin >= g_end) return;
-
-    int st = 0; uint32_t ph = 0;
-    int n = 0;
-    while (g_begin >= b.node[n].g0 + b.node[n].ngroups) n++;
-    for (; n < b.n_nodes && b.node[n].g0 < g_end; n++) {
-        const int ng0 = b.node[n].g0, nM = b.node[n].M, nldy = b.node[n].ldy;
-        float *const ny = b.node[n].y;
-        XBlk xr[4];
-        if (XREG) {
-            // lane u keeps activation blocks BPS*u .. BPS*u+BPS-1 of this node (read straight from the act workspace)
-            const uint8_t *xq = b.node[n].xq;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (j < BPS) xr[j] = lane < S ? load_xblk(xq, kb, j * S + lane) : XBlk{make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int2(0, 0)};
-        } else {
-            __syncthreads();
-            const uint4 *src = reinterpret_cast<const uint4 *>(b.node[n].xq);
-            uint4 *dst = reinterpret_cast<uint4 *>(xs);
-            for (int i = threadIdx.x; i < (NC * xcol_bytes) >> 4; i += NWF * 32) dst[i] = src[i];
-            __syncthreads();
-        }
-        const int seg_lo = max(g_begin, ng0), seg_hi = min(g_end, ng0 + b.node[n].ngroups);
-        int g = seg_lo + ((warp - (seg_lo - g_begin)) & (NWF - 1));
-        for (; g < seg_hi; g += NWF) {
-            const int row0 = (g - ng0) * rs;
-            const int rows = min(rs, nM - row0);
-            float acc[NC];
-#pragma unroll
-            for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
+    if (warp == NWF) {
+        // ===== producer warp: weights do not depend on the preceding kernel, so no PDL wait here =====
+        const long long nb01 = b.nb01;
+        int n = 0, st = 0; uint32_t ph = 0;
+        for (int t = t_begin; t < t_end; t++) {
+            while (t >= b.node[n].g0 + b.node[n].ngroups) n++;
+            const int row0 = (t - b.node[n].g0) * TR;
+            const int rows = min(TR, b.node[n].M - row0);
+            const uint8_t *src = b.node[n].W + (long long)row0 * nb01;
             for (int c = 0; c < nchunk; c++) {
-                mbar_wait(bar0 + 8 * st, ph);
-                const uint8_t *stage = stages + (size_t)st * stage_bytes;
-                if (nchunk == 1) {
-                    for (int r = 0; r < rows; r++) {
-                        if (r) {
+                const int cb = nchunk == 1 ? row_bytes : min(chunk_bytes, row_bytes - c * chunk_bytes);
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                if (lane == 0) mbar_expect_tx(full0 + 8 * st, (uint32_t)(rows * cb));
+                __syncwarp();
+                const uint32_t dst = stage0 + st * stage_bytes;
+                for (int r = lane; r < rows; r += 32)
+                    bulk_g2s(dst + r * cb, src + (long long)r * nb01 + (long long)c * chunk_bytes, (uint32_t)cb, full0 + 8 * st);
+                if (++st == depth) { st = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // activations come from k_act_batch
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int xcol_bytes = b.xcol_bytes, kb = b.K / GGB_QK;
+    const int S = row_bytes / UB, chunk_units = chunk_bytes / UB;
+    int n = -1, st = 0; uint32_t ph = 0;
+    int nt_end = 0, nM = 0, nldy = 0, nt0 = 0;
+    float *ny = nullptr;
+    XBlk xr[4];
+    for (int t = t_begin; t < t_end; t++) {
+        if (t >= nt_end) {
+            // next node: (re)load this node's activations
+            do { n++; } while (t >= b.node[n].g0 + b.node[n].ngroups);
+            nt0 = b.node[n].g0; nt_end = nt0 + b.node[n].ngroups; nM = b.node[n].M; nldy = b.node[n].ldy; ny = b.node[n].y;
+            if (XREG) {
+                const uint8_t *xq = b.node[n].xq;
 #pragma unroll
-                            for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
-                        }
-                        dot_units<TYPE, NC, XREG>(stage + r * row_bytes, 0, S, S, kb, xs, xcol_bytes, xr, lane, acc);
-#pragma unroll
-                        for (int cc = 0; cc < NC; cc++) {
-                            const float v = warp_sum(acc[cc]);
-                            if (lane == 0) {
-                                float *yp = ny + (long long)cc * nldy + row0 + r;
-                                *yp = v;
-                                for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
-                            }
-                        }
+                for (int j = 0; j < 4; j++)
+                    if (j < BPS) {
+                        xr[j] = lane < S ? load_xblk(xq, kb, j * S + lane) : XBlk{make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int2(0, 0)};
                     }
-                } else {
-                    const int nunits = min(chunk_units, S - c * chunk_units);
-                    dot_units<TYPE, NC, false>(stage, c * chunk_units, nunits, S, kb, xs, xcol_bytes, xr, lane, acc);
-                    if (c == nchunk - 1) {
+            } else {
+                asm volatile("bar.sync 1, %0;" ::"n"(NWF * 32) : "memory");      // all consumers are done with the previous x
+                const uint4 *src = reinterpret_cast<const uint4 *>(b.node[n].xq);
+                uint4 *dst = reinterpret_cast<uint4 *>(xs);
+                for (int i = threadIdx.x; i < (NC * xcol_bytes) >> 4; i += NWF * 32) dst[i] = src[i];
+                asm volatile("bar.sync 1, %0;" ::"n"(NWF * 32) : "memory");
+            }
+        }
+        const int row_base = (t - nt0) * TR + warp * rpw;
+        const int nrows = min(rpw, nM - row_base);               // <= 0: this warp has no row in a ragged last tile
+        float acc[NC];
+        for (int c = 0; c < nchunk; c++) {
+            mbar_wait(full0 + 8 * st, ph);
+            const uint8_t *stage = stages + (size_t)st * stage_bytes;
+            if (nchunk == 1) {
+                for (int r = 0; r < nrows; r++) {
 #pragma unroll
-                        for (int cc = 0; cc < NC; cc++) {
-                            const float v = warp_sum(acc[cc]);
-                            if (lane == 0) {
-                                float *yp = ny + (long long)cc * nldy + row0;
-                                *yp = v;
-                                for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
-                            }
+                    for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
+                    dot_units<TYPE, NC, XREG>(stage + (warp * rpw + r) * row_bytes, 0, S, S, kb, xs, xcol_bytes, xr, lane, acc);
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc++) {
+                        const float v = warp_sum(acc[cc]);
+                        if (lane == 0) {
+                            float *yp = ny + (long long)cc * nldy + row_base + r;
+                            *yp = v;
+                            for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
                         }
                     }
                 }
-                __syncwarp();                                    // every lane has finished reading this stage
-                if (pg < g_end) issue();
-                if (++st == depth) { st = 0; ph ^= 1; }
+            } else if (nrows > 0) {
+                if (c == 0) {
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
+                }
+                const int cbytes = min(chunk_bytes, row_bytes - c * chunk_bytes);
+                dot_units<TYPE, NC, false>(stage + warp * cbytes, c * chunk_units, cbytes / UB, S, kb, xs, xcol_bytes, xr, lane, acc);
+                if (c == nchunk - 1) {
+#pragma unroll
+                    for (int cc = 0; cc < NC; cc++) {
+                        const float v = warp_sum(acc[cc]);
+                        if (lane == 0) {
+                            float *yp = ny + (long long)cc * nldy + row_base;
+                            *yp = v;
+                            for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
+                        }
+                    }
+                }
             }
+            __syncwarp();                                        // every lane has finished reading this stage
+            if (lane == 0) mbar_arrive(empty0 + 8 * st);
+            if (++st == depth) { st = 0; ph ^= 1; }
         }
     }
 }
@@ -553,7 +568,7 @@ int launch_fast_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s,
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NWF * 32);
+    cfg.blockDim = dim3((NWF + 1) * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -605,12 +620,13 @@ int launch_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s, bool
 }
 
 constexpr int X_BUDGET = 64 * 1024;        // activation columns resident in shared memory
-constexpr int W_BUDGET = 144 * 1024;       // weight stages of all warps
+constexpr int W_BUDGET = 160 * 1024;       // weight stages of all warps
 constexpr int STAGE_MAX = 4096;            // bytes of one bulk copy (one row, several short rows, or a K-chunk of a long row)
 
 } // namespace
 
 int gemv_num_ctas() { return device_sm_count(); }
+int gemv_group_rows(const GemvBatch &b) { return b.async ? NWF * b.rs : b.rs; }
 int gemv_act_bps(const GemvBatch &b) { return !b.async ? 1 : b.type == GGML_TYPE_Q4_0 ? 4 : b.type == GGML_TYPE_Q4_1 ? 2 : 1; }
 
 // Fills the shape-dependent fields of b (everything but the node list).  ncols in {1,2,4,8}.
@@ -628,13 +644,35 @@ int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const 
     // 16-byte aligned rows made of whole units -> TMA bulk staging + the fast kernel; anything else -> plain-load staging
     b.async = ((reinterpret_cast<uintptr_t>(Wbase) & 15) == 0 && (nb01 & 15) == 0 && (row_bytes & 15) == 0 && row_bytes % unit_async == 0) ? 1 : 0;
     const int unit = b.async ? unit_async : unit_sync;
+    if (b.async) {
+        // fast kernel: stage = 16*rpw whole rows, or one K-chunk of 16 rows
+        if (row_bytes <= STAGE_MAX) {
+            b.nchunk = 1; b.chunk_bytes = (int)row_bytes;
+            b.rs = (int)std::max<long long>(1, std::min<long long>(8, 2048 / row_bytes));     // rows per consumer warp per stage
+            b.stage_bytes = (int)(NWF * b.rs * row_bytes);
+        } else {
+            const long long units = row_bytes / unit;
+            long long nchunk = (row_bytes + STAGE_MAX - 1) / STAGE_MAX;
+            const long long cu = (units + nchunk - 1) / nchunk;
+            b.chunk_bytes = (int)(cu * unit);
+            b.nchunk = (int)((row_bytes + b.chunk_bytes - 1) / b.chunk_bytes);
+            b.rs = 1;
+            b.stage_bytes = NWF * b.chunk_bytes;
+        }
+        const long long xb = (xcol * ncols + 127) & ~127ll;
+        long long budget = 227 * 1024 - xb - 2 * MAX_DEPTH * 8 - 1024;
+        if (budget > W_BUDGET) budget = W_BUDGET;
+        int d = (int)(budget / b.stage_bytes);
+        if (d > MAX_DEPTH) d = MAX_DEPTH;
+        if (d < 2) return set_error(GGB_E_UNSUPPORTED, "mul_mat: shape needs more shared memory than one SM has");
+        b.depth = d;
+        return GGB_OK;
+    }
     if (row_bytes <= STAGE_MAX) {
         b.nchunk = 1;
         b.chunk_bytes = (int)row_bytes;
-        // several short rows per copy only when rows are densely packed
-        b.rs = (nb01 == row_bytes && b.async) ? (int)(STAGE_MAX / row_bytes) : 1;
-        if (b.rs > 64) b.rs = 64;
-        b.stage_bytes = (int)align_up((size_t)b.rs * row_bytes, 16);
+        b.rs = 1;
+        b.stage_bytes = (int)align_up((size_t)row_bytes, 16);
     } else {
         const long long units = (row_bytes + unit - 1) / unit;
         long long nchunk = (row_bytes + STAGE_MAX - 1) / STAGE_MAX;
@@ -645,12 +683,10 @@ int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const 
         b.stage_bytes = (int)align_up((size_t)b.chunk_bytes, 16);
     }
     const long long xbytes = (xcol * ncols + 127) & ~127ll;
-    const int nw = b.async ? NWF : NWARPS;
-    long long wbudget = 227 * 1024 - xbytes - nw * MAX_DEPTH * 8 - 1024;
+    long long wbudget = 227 * 1024 - xbytes - NWARPS * MAX_DEPTH * 8 - 1024;
     if (wbudget > W_BUDGET) wbudget = W_BUDGET;
-    int depth = b.async ? (int)(wbudget / ((long long)nw * b.stage_bytes)) : 1;
-    if (depth > MAX_DEPTH) depth = MAX_DEPTH;
-    if (depth < 1) return set_error(GGB_E_UNSUPPORTED, "mul_mat: shape needs more shared memory than one SM has");
+    int depth = 1;
+    if ((long long)NWARPS * b.stage_bytes > wbudget) return set_error(GGB_E_UNSUPPORTED, "mul_mat: shape needs more shared memory than one SM has");
     b.depth = depth;
     return GGB_OK;
 }
@@ -659,10 +695,11 @@ int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl)
 {
     if (b.n_nodes <= 0 || b.total_groups <= 0) return GGB_OK;
     const size_t xbytes = ((size_t)b.ncols * b.xcol_bytes + 127) & ~(size_t)127;
-    const int nw = b.async ? NWF : NWARPS;
-    const size_t smem = xbytes + (size_t)nw * b.depth * b.stage_bytes + nw * MAX_DEPTH * 8;
     int grid = gemv_num_ctas();
-    const int want = (b.total_groups + nw - 1) / nw;
+    // async: groups are tiles and every CTA takes whole tiles; sync: groups are rows, one per warp
+    const size_t smem = b.async ? xbytes + (size_t)b.depth * b.stage_bytes + 2 * MAX_DEPTH * 8
+                                : xbytes + (size_t)NWARPS * b.depth * b.stage_bytes + NWARPS * MAX_DEPTH * 8;
+    const int want = b.async ? b.total_groups : (b.total_groups + NWARPS - 1) / NWARPS;
     if (grid > want) grid = want;
     if (b.async) switch (b.type) {
     case GGML_TYPE_Q4_0: return launch_fast_typed<GGML_TYPE_Q4_0>(b, smem, grid, s, pdl);

@@ -59,7 +59,8 @@ struct GemvBatch {
 };
 int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl);
 int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase_probe);
-int gemv_act_bps(const GemvBatch &b);   // the ActBatch::bps the planned kernel expects
+int gemv_act_bps(const GemvBatch &b);
+int gemv_group_rows(const GemvBatch &b);  // weight rows per work group (tile) of the planned kernel   // the ActBatch::bps the planned kernel expects
 int gemv_num_ctas();
 
 // ---- GEMM (ggb_gemm.cu): tcgen05 batched path ----

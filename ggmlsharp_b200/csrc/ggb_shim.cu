@@ -213,7 +213,8 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
                 nd.xq = wsb + off[passes[p1].i] + (size_t)passes[p1].col0 * arow;
                 nd.y = m.Y + (size_t)passes[p1].col0 * (m.ldy_bytes / 4);
                 nd.M = (int)m.M; nd.ldy = (int)(m.ldy_bytes / 4);
-                nd.g0 = gb.total_groups; nd.ngroups = (int)((m.M + gb.rs - 1) / gb.rs);
+                const int64_t rows_per_group = gemv_group_rows(gb);
+                nd.g0 = gb.total_groups; nd.ngroups = (int)((m.M + rows_per_group - 1) / rows_per_group);
                 gb.total_groups += nd.ngroups;
                 if (gb.n_nodes == 64) { rc = flush(); if (rc) return rc; }
             }
