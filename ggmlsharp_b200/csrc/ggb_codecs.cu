@@ -237,13 +237,13 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
 // Batched (tensor-core) path: activations as fp16 values the reference's dot effectively multiplies by:
 // Q4_x weights -> d * round(x / d) of the Q8 block (same d, same quants as quantize_row_q8_x); F16 -> (Half)x.
 // Rows n >= N of the padded buffer are zero.
-__global__ void __launch_bounds__(256) k_act_f16_dequant(int wtype, const float *__restrict__ x, long long ldx_bytes,
+__global__ void __launch_bounds__(256) k_act_f16_dequant(int wtype, int perm, const float *__restrict__ x, long long ldx_bytes,
                                                          __half *__restrict__ out, int N, int Npad, int K)
 {
     const int lane = threadIdx.x & 31, sub = lane & 7;
     const int kb = K / GGB_QK;
     const long long blk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    if (blk >= (long long)Npad * kb) return;                    // K % 32 == 0 on this path, so groups of 8 lanes stay whole
+    if (blk >= (long long)Npad * kb) return;                    // whole warps leave together: (Npad*kb*8) % 32 == 0 since Npad % 16 == 0
     const int row = (int)(blk / kb), col = (int)(blk - (long long)row * kb);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < N) v = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(x) + (long long)row * ldx_bytes + (long long)col * 128 + sub * 16);
@@ -259,6 +259,14 @@ __global__ void __launch_bounds__(256) k_act_f16_dequant(int wtype, const float 
     }
     const __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
     uint2 pk; pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+    if (perm) {
+        // K order 0,4,1,5,2,6,3,7 inside every group of 8: the order the GEMM's nibble unpack produces
+        const bool odd = sub & 1;
+        const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? pk.x : pk.y, 1);
+        const uint32_t a = odd ? recv : pk.x, b = odd ? pk.y : recv;     // even: (mine01, partner01); odd: (partner23, mine23)
+        pk.x = __byte_perm(a, b, 0x5410);
+        pk.y = __byte_perm(a, b, 0x7632);
+    }
     *reinterpret_cast<uint2 *>(out + (long long)row * K + (long long)col * GGB_QK + sub * 4) = pk;
 }
 
@@ -331,11 +339,11 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
     return GGB_OK;
 }
 
-int launch_act_f16_dequant(int wtype, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s)
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s)
 {
     const long long threads = Npad * (K / GGB_QK) * 8;
     if (threads <= 0) return GGB_OK;
-    k_act_f16_dequant<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(wtype, x, ldx_bytes, out, (int)N, (int)Npad, (int)K);
+    k_act_f16_dequant<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(wtype, perm, x, ldx_bytes, out, (int)N, (int)Npad, (int)K);
     count_launch(); GGB_CUDA(cudaGetLastError());
     return GGB_OK;
 }

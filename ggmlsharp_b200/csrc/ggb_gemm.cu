@@ -1,7 +1,382 @@
-// Batched (N >= 16) mul_mat on tcgen05 tensor cores -- placeholder until the kernel lands.
+// Batched (N >= 16) mul_mat on the 5th-generation tensor cores: tcgen05.mma with the accumulator in
+// TMEM, operands staged in shared memory by TMA, one warp-specialised CTA per 128 x BN output tile.
+//
+// Replaces ggml_compute_forward_mul_mat_q_f32 / _f16_f32 (Ggml.cs:6440-6712, 6180-6438) for prompt-sized
+// batches.  dst[n][m] = sum_k W[m][k] * X[n][k]; both operands are K-major, so the MMA "M" dimension (the
+// 128 TMEM lanes) is a tile of weight rows and the MMA "N" dimension (TMEM columns) a tile of activation
+// rows; the epilogue's 32x32b TMEM load then gives each thread one m and 32 consecutive n, and a warp's store
+// of one n is 32 consecutive floats of dst -- coalesced with no transpose.
+//
+//   warp 0       TMA producer: raw quant blocks (2-D byte tensor map, box = 128 rows x 4 blocks) or, for F16
+//                weights, swizzled fp16 tiles; plus the activation tiles (fp16, swizzle-128B)
+//   warp 1       MMA issuer: one elected lane, 8 x tcgen05.mma (K = 16 each) per 128-wide K step
+//   warp 2       TMEM allocator
+//   warps 4..19  dequant: each thread expands one 32-weight block per K step into the swizzle-128B K-major A
+//                tile (nibble -> fp16 with the 0x6400 / 0x5400 magic-number trick, exact q-8, then * d),
+//                fence.proxy.async, arrive; warps 4..7 are also the epilogue (tcgen05.ld -> global)
+//
+// Numerics: activations are quantized exactly as quantize_row_q8_0/q8_1 do (same d, same quants) and enter
+// the MMA as fp16(d1*q); weights as fp16(d0*(q-8)) (Q4_0), fp16(d0*(q-8) + (m0+8*d0)) (Q4_1) or the stored fp16 (F16);
+// products are exact in the tensor core and accumulate in fp32.  Measured rel-L2 vs the CPU oracle is in
+// tests/test_gpu_gemm.py (bound 1e-3).  The magic-number unpack yields the 8 weights of a 32-bit word in the
+// order 0,4,1,5,2,6,3,7; the activation kernel stores K in the same order, so no re-pairing is needed.
 #include "ggb_internal.h"
+
+#include <cuda.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+
 namespace ggb {
-bool gemm_supported(int, int64_t, int64_t, int64_t, int64_t, const void *) { return false; }
-size_t gemm_workspace_bytes(int, int64_t, int64_t, int64_t) { return 0; }
-int launch_gemm(const GemmArgs &, void *, cudaStream_t) { return set_error(GGB_E_UNSUPPORTED, "batched tensor-core path not built"); }
+
+namespace {
+
+constexpr int BM = 128;            // weight rows per tile  (MMA M, TMEM lanes)
+constexpr int BK = 128;            // K per pipeline step   (4 quant blocks; two 64-wide swizzle atoms)
+constexpr int RAW_STAGES = 4, A_STAGES = 2, B_STAGES = 3;
+constexpr int NDQ_WARPS = 16;
+constexpr int NTHREADS = (4 + NDQ_WARPS) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row (1024 B) swizzle atoms stacked along M/N.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
+    d |= (uint64_t)0 << 16;                            // leading byte offset: unused for a single swizzled K atom
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = bn
+__device__ __forceinline__ uint32_t make_idesc(int bn)
+{
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Smem {
+    // offsets from the 1024-aligned base
+    static constexpr int A_BYTES = BM * BK * 2;                 // 32 KB: two [128][64] fp16 swizzle-128B sub-tiles
+    static constexpr int RAW_MAX = BM * 96;                     // Q4_1: 4 blocks x 24 B per row
+};
+
+template <int TYPE>
+__device__ __forceinline__ void dequant_block(const uint8_t *raw, uint8_t *a_stage, int r, int j)
+{
+    // block j (0..3) of row r of this K step -> sub-tile j/2, 64 bytes at K offset 32*(j&1) halfs
+    uint32_t q[4];
+    __half2 d2, m2;
+    if (TYPE == GGML_TYPE_Q4_0) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(raw + r * 80 + j * 20);
+        d2 = __float2half2_rn(__uint_as_float(p[0]));
+        q[0] = p[1]; q[1] = p[2]; q[2] = p[3]; q[3] = p[4];
+    } else {
+        const uint2 *p = reinterpret_cast<const uint2 *>(raw + r * 96 + j * 24);
+        const uint2 dm = p[0], qa = p[1], qb = p[2];
+        d2 = __float2half2_rn(__uint_as_float(dm.x));
+        // q*d + m == (q-8)*d + (m + 8d): the recentred offset is ~5x smaller than m, and so is its fp16 rounding
+        // error, which is coherent over the block's 32 elements and would otherwise dominate the Q4_1 error
+        m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(dm.x), __uint_as_float(dm.y)));
+        q[0] = qa.x; q[1] = qa.y; q[2] = qb.x; q[3] = qb.y;
+    }
+    uint8_t *row = a_stage + (j >> 1) * (BM * 128) + r * 128;
+    const int rot = (j >> 1) * 2;                               // bank-conflict-free STS order across a quarter warp
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int ci = (i + rot) & 3;
+        const uint32_t w = q[ci];
+        // (lo | 0x6400) = 1024 + q as fp16 pair for bytes 0 and 2; (hi | 0x5400) = 64 + q for the high nibbles
+        uint32_t v0 = (w & 0x000F000Fu) | 0x64006400u;          // elements 0, 4
+        uint32_t v1 = (w & 0x00F000F0u) | 0x54005400u;          // elements 1, 5
+        const uint32_t ws = w >> 8;
+        uint32_t v2 = (ws & 0x000F000Fu) | 0x64006400u;         // elements 2, 6
+        uint32_t v3 = (ws & 0x00F000F0u) | 0x54005400u;         // elements 3, 7
+        __half2 h0 = *reinterpret_cast<__half2 *>(&v0), h1 = *reinterpret_cast<__half2 *>(&v1);
+        __half2 h2 = *reinterpret_cast<__half2 *>(&v2), h3 = *reinterpret_cast<__half2 *>(&v3);
+        if (TYPE == GGML_TYPE_Q4_0) {
+            const __half2 o_lo = __float2half2_rn(1032.0f), o_hi = __float2half2_rn(72.0f);     // 1024+8, 64+8
+            h0 = __hmul2(__hsub2(h0, o_lo), d2); h1 = __hmul2(__hsub2(h1, o_hi), d2);
+            h2 = __hmul2(__hsub2(h2, o_lo), d2); h3 = __hmul2(__hsub2(h3, o_hi), d2);
+        } else {
+            const __half2 o_lo = __float2half2_rn(1032.0f), o_hi = __float2half2_rn(72.0f);
+            h0 = __hfma2(__hsub2(h0, o_lo), d2, m2); h1 = __hfma2(__hsub2(h1, o_hi), d2, m2);
+            h2 = __hfma2(__hsub2(h2, o_lo), d2, m2); h3 = __hfma2(__hsub2(h3, o_hi), d2, m2);
+        }
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t *>(&h0); o.y = *reinterpret_cast<uint32_t *>(&h1);
+        o.z = *reinterpret_cast<uint32_t *>(&h2); o.w = *reinterpret_cast<uint32_t *>(&h3);
+        const int chunk = ((j & 1) * 4 + ci) ^ (r & 7);         // 128-byte swizzle: 16-byte chunk index XOR row-in-atom
+        *reinterpret_cast<uint4 *>(row + chunk * 16) = o;
+    }
+}
+
+template <int TYPE, int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+       float *__restrict__ Y, long long ldy, int M, int N, int K, int n_peers, const long long *__restrict__ peer_delta_unused)
+{
+    constexpr bool DEQ = TYPE != GGML_TYPE_F16;
+    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int RAW_BYTES = DEQ ? BM * RAW_ROW : 0;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    constexpr int NA = DEQ ? A_STAGES : B_STAGES;               // F16 weights: A rides with B through TMA
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;                                          // NA x A_BYTES       (1024-aligned)
+    uint8_t *sB = sA + NA * A_BYTES;                             // B_STAGES x B_BYTES (1024-aligned)
+    uint8_t *sRaw = sB + B_STAGES * B_BYTES;                     // RAW_STAGES x RAW_BYTES
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sRaw + RAW_STAGES * RAW_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    // barrier indices
+    constexpr int RAW_FULL = 0, RAW_EMPTY = RAW_FULL + RAW_STAGES, A_FULL = RAW_EMPTY + RAW_STAGES, A_EMPTY = A_FULL + 4,
+                  B_FULL = A_EMPTY + 4, B_EMPTY = B_FULL + B_STAGES, ACC_FULL = B_EMPTY + B_STAGES, NBARS = ACC_FULL + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
+    auto BAR = [&](int i) { return bar0 + 8 * i; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int ksteps = (K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RAW_STAGES; i++) { mbar_init(BAR(RAW_FULL + i), 1); mbar_init(BAR(RAW_EMPTY + i), NDQ_WARPS); }
+        for (int i = 0; i < NA; i++) { mbar_init(BAR(A_FULL + i), DEQ ? NDQ_WARPS : 1); mbar_init(BAR(A_EMPTY + i), 1); }
+        for (int i = 0; i < B_STAGES; i++) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        mbar_init(BAR(ACC_FULL), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int ks = 0; ks < ksteps; ks++) {
+                if (DEQ) {
+                    const int s = ks % RAW_STAGES;
+                    mbar_wait(BAR(RAW_EMPTY + s), ((ks / RAW_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(BAR(RAW_FULL + s), RAW_BYTES);
+                    tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &map_w, BAR(RAW_FULL + s), ks * RAW_ROW, m0);
+                }
+                const int sb = ks % B_STAGES;
+                mbar_wait(BAR(B_EMPTY + sb), ((ks / B_STAGES) & 1) ^ 1);
+                mbar_expect_tx(BAR(B_FULL + sb), B_BYTES + (DEQ ? 0 : A_BYTES));
+                tma_load_2d(smem_u32(sB + sb * B_BYTES), &map_x, BAR(B_FULL + sb), ks * BK, n0);
+                tma_load_2d(smem_u32(sB + sb * B_BYTES + BN * 128), &map_x, BAR(B_FULL + sb), ks * BK + 64, n0);
+                if (!DEQ) {
+                    tma_load_2d(smem_u32(sA + sb * A_BYTES), &map_w, BAR(B_FULL + sb), ks * BK, m0);
+                    tma_load_2d(smem_u32(sA + sb * A_BYTES + BM * 128), &map_w, BAR(B_FULL + sb), ks * BK + 64, m0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = make_idesc(BN);
+        for (int ks = 0; ks < ksteps; ks++) {
+            const int sa = ks % NA, sb = ks % B_STAGES;
+            if (DEQ) mbar_wait(BAR(A_FULL + sa), (ks / NA) & 1);
+            mbar_wait(BAR(B_FULL + sb), (ks / B_STAGES) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_base = smem_u32(sA + sa * A_BYTES), b_base = smem_u32(sB + sb * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++) {
+                    // sub-tile k/4 (64 K each), then 32 bytes per K=16 step inside the 128-byte swizzle row
+                    const uint64_t ad = make_sdesc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32);
+                    const uint64_t bd = make_sdesc(b_base + (k >> 2) * (BN * 128) + (k & 3) * 32);
+                    tc_mma_f16(tmem, ad, bd, idesc, (ks | k) != 0);
+                }
+                if (DEQ) tc_commit(BAR(A_EMPTY + sa));           // frees the A stage once these MMAs have read it
+                tc_commit(BAR(B_EMPTY + sb));
+                if (ks == ksteps - 1) tc_commit(BAR(ACC_FULL));
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ===== dequant warps (then warps 4..7: epilogue) =====
+        if (DEQ) {
+            const int dw = warp - 4;
+            const int r = dw * 8 + (lane >> 2), j = lane & 3;    // one 32-weight block per thread per K step
+            for (int ks = 0; ks < ksteps; ks++) {
+                const int s = ks % RAW_STAGES, sa = ks % A_STAGES;
+                mbar_wait(BAR(RAW_FULL + s), (ks / RAW_STAGES) & 1);
+                mbar_wait(BAR(A_EMPTY + sa), ((ks / A_STAGES) & 1) ^ 1);
+                dequant_block<TYPE>(sRaw + s * RAW_BYTES, sA + sa * A_BYTES, r, j);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(BAR(A_FULL + sa)); mbar_arrive(BAR(RAW_EMPTY + s)); }
+            }
+        }
+        if (warp < 8) {
+            const int q = warp & 3;                              // TMEM lane quadrant this warp may access
+            mbar_wait(BAR(ACC_FULL), 0);
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+            for (int cb = 0; cb < BN / 32; cb++) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                               "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                             : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (m < M) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int n = n0 + cb * 32 + c;
+                        if (n < N) Y[(long long)n * ldy + m] = __uint_as_float(v[c]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+    }
+}
+
+// ---- host side: tensor maps ----
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(GGB_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {dim0, dim1};
+    const cuuint64_t strides[1] = {stride1_bytes};
+    const cuuint32_t box[2] = {box0, box1};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = fn(map, dt, 2, const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(GGB_E_CUDA, "cuTensorMapEncodeTiled failed (%d) dims=%llu x %llu stride=%llu box=%u x %u",
+                                            (int)r, (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)stride1_bytes, box0, box1);
+    return GGB_OK;
+}
+
+template <int TYPE, int BN>
+int launch_typed(const GemmArgs &a, cudaStream_t s)
+{
+    constexpr bool DEQ = TYPE != GGML_TYPE_F16;
+    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    CUtensorMap mw, mx;
+    int rc;
+    if (DEQ) {
+        const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * (TYPE == GGML_TYPE_Q4_0 ? 20 : 24);
+        rc = make_map_2d(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, row_bytes, (uint64_t)a.M, (uint64_t)a.nb01, RAW_ROW, BM, CU_TENSOR_MAP_SWIZZLE_NONE);
+    } else {
+        rc = make_map_2d(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.W, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.nb01, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    if (rc) return rc;
+    rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, RAW_BYTES = DEQ ? BM * RAW_ROW : 0;
+    constexpr int NA = DEQ ? A_STAGES : B_STAGES;
+    constexpr size_t smem = 1024 + (size_t)NA * A_BYTES + (size_t)B_STAGES * B_BYTES + (size_t)RAW_STAGES * RAW_BYTES + 64 * 8 + 16;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemm<TYPE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    dim3 grid((unsigned)((a.M + BM - 1) / BM), (unsigned)((a.N + BN - 1) / BN));
+    k_gemm<TYPE, BN><<<grid, NTHREADS, smem, s>>>(mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, a.n_peers, nullptr);
+    count_launch();
+    GGB_CUDA(cudaGetLastError());
+    return GGB_OK;
+}
+
+} // namespace
+
+bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W)
+{
+    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1 && type != GGML_TYPE_F16) return false;     // F32 weights stay on FFMA (1e-5 bar)
+    if (M <= 0 || N < 16 || K <= 0 || K % GGB_QK) return false;
+    if ((reinterpret_cast<uintptr_t>(W) & 15) || (nb01 & 15)) return false;                            // TMA: 16-byte base and strides
+    if (type == GGML_TYPE_F16) return K % 8 == 0;
+    return K % 128 == 0;                                                                               // whole 4-block boxes
+}
+
+size_t gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N)
+{
+    (void)type; (void)M;
+    const int64_t Npad = (N + 15) / 16 * 16;
+    return align_up((size_t)Npad * K * 2, 256);
+}
+
+int gemm_act_perm(int type) { return type == GGML_TYPE_F16 ? 0 : 1; }
+
+int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s)
+{
+    (void)ws;
+    if (a.n_peers) return set_error(GGB_E_UNSUPPORTED, "batched path: fused peer stores are not implemented");
+    switch (a.type) {
+    case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, 128>(a, s);
+    case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, 128>(a, s);
+    case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, 128>(a, s);
+    default: return set_error(GGB_E_UNSUPPORTED, "batched path: type %d", a.type);
+    }
+}
+
+} // namespace ggb

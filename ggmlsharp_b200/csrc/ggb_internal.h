@@ -40,7 +40,7 @@ struct ActNode { const float *x; long long ldx_bytes; uint8_t *out; int N; int b
 struct ActBatch { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; ActNode node[64]; };
 int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl);
 // batched path: activations as dense fp16 [Npad][K] holding d * q (the value the reference's dot multiplies by)
-int launch_act_f16_dequant(int wtype, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s);
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s);
 
 // ---- GEMV (ggb_gemv.cu) ----
 struct GemvNode { const uint8_t *W; const uint8_t *xq; float *y; int M; int ldy; int g0; int ngroups; };
@@ -71,6 +71,7 @@ struct GemmArgs {
 bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W);
 size_t gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
 int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s);
+int gemm_act_perm(int type);       // 1: the activation buffer must use the K order 0,4,1,5,2,6,3,7 per group of 8
 
 int device_sm_count();
 

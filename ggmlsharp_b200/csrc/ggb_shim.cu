@@ -121,7 +121,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         if (!use_gemm(m)) { gemv_idx.push_back(i); continue; }
         const int64_t Npad = (m.N + 15) / 16 * 16;
         __half *xh = reinterpret_cast<__half *>(wsb + off[i]);
-        int rc = launch_act_f16_dequant(m.type, m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s);
+        int rc = launch_act_f16_dequant(m.type, gemm_act_perm(m.type), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s);
         if (rc) return rc;
         GemmArgs a = {};
         a.type = m.type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;

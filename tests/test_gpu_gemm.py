@@ -1,0 +1,76 @@
+"""Batched (N >= 16) mul_mat on the tcgen05 tensor-core path vs the CPU oracle (BASELINE.json configs[3]).
+
+Bar: rel-L2 <= 1e-3 for Q4_0 / Q4_1 / F16 weights.  Expected error: activations enter as fp16(d1*q) and Q4 weights
+as fp16(d0*(q-8)) (two ~2^-12 roundings), products exact, fp32 accumulation -> ~3e-4..5e-4 for Q4, ~1e-6 for F16
+(whose activations the reference itself rounds to Half)."""
+import numpy as np
+import pytest
+
+from gpu_util import rel_l2
+from ggmlsharp_b200 import native as N
+from oracle import pyoracle as orc
+from test_gpu_parity import dev_mul_mat, weights
+
+pytestmark = pytest.mark.gpu
+
+GEMM_TOL = {N.Q4_0: 1e-3, N.Q4_1: 1e-3, N.F16: 1e-3}
+GEMM_TIGHT = {N.Q4_0: 5e-4, N.Q4_1: 6e-4, N.F16: 5e-5}
+
+SHAPES = [
+    (128, 128, 16), (128, 256, 17), (256, 512, 64), (200, 384, 48),     # ragged M, N
+    (384, 1024, 128), (1024, 4096, 130), (4096, 4096, 512),             # cfg 3
+    (11008, 4096, 32), (4096, 11008, 16),                               # Llama FFN shapes, prompt batch
+]
+
+
+@pytest.mark.parametrize("t", [N.Q4_0, N.Q4_1, N.F16])
+@pytest.mark.parametrize("M,K,Nn", SHAPES)
+def test_gemm_vs_oracle(t, M, K, Nn):
+    rng = np.random.default_rng(3000 + M + K + Nn)
+    W = weights(rng, M, K)
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    wb = orc.encode_weights(t, W)
+    N.lib().ggb_reset_stats()
+    got = dev_mul_mat(t, wb, M, K, X)
+    assert N.stats().kernel_launches == 2            # activation kernel + one tcgen05 GEMM launch (not GEMV passes)
+    want = orc.mul_mat_2d(t, wb, M, K, X, nth=16)
+    err = rel_l2(got, want)
+    print('GEMM_ERR type=%d M=%d K=%d N=%d rel_l2=%.3e' % (t, M, K, Nn, err))
+    assert err <= GEMM_TOL[t], (t, M, K, Nn, err)
+    assert err <= GEMM_TIGHT[t], (t, M, K, Nn, err)
+
+
+@pytest.mark.parametrize("t", [N.Q4_0, N.F16])
+def test_gemm_uniform_inputs_and_determinism(t):
+    rng = np.random.default_rng(9)
+    M, K, Nn = 512, 2048, 96
+    W = weights(rng, M, K, "uniform")
+    X = rng.uniform(-1, 1, (Nn, K)).astype(np.float32)
+    wb = orc.encode_weights(t, W)
+    a = dev_mul_mat(t, wb, M, K, X)
+    b = dev_mul_mat(t, wb, M, K, X)
+    assert np.array_equal(a, b)
+    assert rel_l2(a, orc.mul_mat_2d(t, wb, M, K, X, nth=16)) <= GEMM_TOL[t]
+
+
+def test_gemm_columns_match_gemv_columns():
+    # the same activation row must give (nearly) the same answer through the N=1 GEMV path and inside a batch
+    rng = np.random.default_rng(10)
+    M, K, Nn = 256, 1024, 32
+    W = weights(rng, M, K)
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    wb = orc.encode_weights(N.Q4_0, W)
+    batch = dev_mul_mat(N.Q4_0, wb, M, K, X)
+    single = dev_mul_mat(N.Q4_0, wb, M, K, X[5:6])
+    assert rel_l2(batch[5:6], single) <= 1e-3
+
+
+def test_f32_weights_batched_stay_on_ffma_path():
+    # F32 weights must hold 1e-5, which fp16/tf32 tensor-core operands cannot: the batch runs as GEMV column passes
+    rng = np.random.default_rng(12)
+    M, K, Nn = 96, 256, 20
+    W = weights(rng, M, K)
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    wb = orc.encode_weights(N.F32, W)
+    got = dev_mul_mat(N.F32, wb, M, K, X)
+    assert rel_l2(got, orc.mul_mat_2d(N.F32, wb, M, K, X)) <= 2e-6
