@@ -1,0 +1,35 @@
+// P/Invoke surface of libggb200.so for GGMLSharp (include/ggb200.h).  Drop this file into the GGMLSharp
+// project; it adds no public API.  NOT compiled in this repository: no .NET toolchain exists in the build
+// image.  The layouts it relies on are verified at run time by ggb_abi_check().
+using System;
+using System.Runtime.InteropServices;
+
+namespace GGMLSharp;
+
+internal static unsafe partial class GgbNative
+{
+    const string Lib = "ggb200";   // libggb200.so next to the application
+
+    public const int GGB_GRAPH_KEEP_ON_DEVICE = 1, GGB_GRAPH_NO_WEIGHT_CACHE = 2;
+
+    [DllImport(Lib)] public static extern IntPtr ggb_last_error();
+    [DllImport(Lib)] public static extern int ggb_abi_check(int sizeofTensor, int offsetofData, int sizeofCgraph, int offsetofNodes, int sizeofQ4_0, int sizeofQ4_1);
+    [DllImport(Lib)] public static extern int ggb_init();
+    [DllImport(Lib)] public static extern int ggb_shutdown();
+    [DllImport(Lib)] public static extern int ggb_pool_alloc(nuint bytes, void** hostBase, IntPtr* pool);
+    [DllImport(Lib)] public static extern int ggb_pool_adopt(void* hostBase, nuint bytes, IntPtr* pool);
+    [DllImport(Lib)] public static extern int ggb_pool_free(IntPtr pool);
+    [DllImport(Lib)] public static extern int ggb_tensor_invalidate(IntPtr pool, ggml_tensor* t);
+    [DllImport(Lib)] public static extern int ggb_mul_mat_node(IntPtr pool, ggml_tensor* dst);
+    [DllImport(Lib)] public static extern int ggb_graph_compute_mul_mats(IntPtr pool, ggml_cgraph* graph, int flags, byte* done);
+    [DllImport(Lib)] public static extern int ggb_quantize_rows(int type, float* src, void* dst, long nrows, long k);
+    [DllImport(Lib)] public static extern int ggb_dequantize_rows(int type, void* src, float* dst, long nrows, long k);
+
+    public static string LastError() => Marshal.PtrToStringUTF8(ggb_last_error()) ?? "";
+
+    // ggml_context* -> ggb_pool*.  ggml_context itself (TypeDefinitions.cs:32-46) is left untouched.
+    static readonly System.Collections.Generic.Dictionary<IntPtr, IntPtr> Pools = new();
+    public static void Bind(ggml_context* ctx, IntPtr pool) { lock (Pools) Pools[(IntPtr)ctx] = pool; }
+    public static IntPtr PoolOf(ggml_context* ctx) { lock (Pools) return Pools.TryGetValue((IntPtr)ctx, out var p) ? p : IntPtr.Zero; }
+    public static IntPtr Unbind(ggml_context* ctx) { lock (Pools) { Pools.Remove((IntPtr)ctx, out var p); return p; } }
+}
