@@ -23,6 +23,7 @@
 #include "ggb_internal.h"
 
 #include <cuda.h>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -33,7 +34,15 @@ namespace {
 
 constexpr int BM = 128;            // weight rows per tile  (MMA M, TMEM lanes)
 constexpr int BK = 128;            // K per pipeline step   (4 quant blocks; two 64-wide swizzle atoms)
-constexpr int RAW_STAGES = 4, A_STAGES = 2, B_STAGES = 3;
+// Pipeline depth is what hides the ~1.3 us TMA latency: bytes in flight per SM must cover latency x fill rate, so the
+// shared memory budget is spent on as many activation / raw stages as fit (profiles/r01_gemm_*: v1 with 3 stages was
+// latency-bound at ~1100 cycles per K step against a 512-cycle MMA floor).
+template <int TYPE, int CG> struct Stages {
+    static constexpr bool DEQ = TYPE != GGML_TYPE_F16;
+    static constexpr int RAW = DEQ ? 4 : 1;                                  // (F16: unused, RAW_BYTES == 0)
+    static constexpr int A = DEQ ? (CG == 2 ? 3 : 2) : (CG == 2 ? 4 : 3);     // F16: A rides with B
+    static constexpr int B = DEQ ? (CG == 2 ? 5 : 3) : A;
+};
 constexpr int NDQ_WARPS = 16;
 constexpr int NTHREADS = (4 + NDQ_WARPS) * 32;
 
@@ -54,6 +63,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -83,72 +95,112 @@ __device__ __forceinline__ uint32_t make_idesc(int bn)
     return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-struct Smem {
-    // offsets from the 1024-aligned base
-    static constexpr int A_BYTES = BM * BK * 2;                 // 32 KB: two [128][64] fp16 swizzle-128B sub-tiles
-    static constexpr int RAW_MAX = BM * 96;                     // Q4_1: 4 blocks x 24 B per row
-};
-
-template <int TYPE>
-__device__ __forceinline__ void dequant_block(const uint8_t *raw, uint8_t *a_stage, int r, int j)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
 {
-    // block j (0..3) of row r of this K step -> sub-tile j/2, 64 bytes at K offset 32*(j&1) halfs
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on a barrier that may live in the peer CTA (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 2-CTA TMA load: bytes land in this CTA's shared memory, completion is signalled on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2(uint32_t bar)      // arrives on the barrier at this offset in BOTH CTAs of the pair
+{
+    asm volatile("{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\ttcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+                 ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// One 32-weight block -> 64 bytes of the swizzle-128B K-major A tile.  `row` points at this thread's 128-byte row of its
+// sub-tile, `cx` is the row's swizzle XOR (r & 7), `half` selects the 32-K half of the 64-wide sub-tile, `rot` the STS order.
+// (w & mask) | magic in ONE LOP3 (immLut 0xEA = (a & b) | c); the constants are passed in registers so ptxas cannot split it
+__device__ __forceinline__ uint32_t and_or(uint32_t w, uint32_t mask, uint32_t magic)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "r"(mask), "r"(magic));
+    return d;
+}
+
+// One 32-weight block -> 64 bytes of the swizzle-128B K-major A tile.  `row` is the shared-space address of this thread's
+// 128-byte row in its sub-tile, `cx` the row's swizzle XOR (r & 7), `half` selects the 32-K half of the 64-wide sub-tile.
+template <int TYPE>
+__device__ __forceinline__ void dequant_block(uint32_t blk, uint32_t row, int cx, int half)
+{
     uint32_t q[4];
-    __half2 d2, m2;
+    __half2 d2, m2 = __float2half2_rn(0.0f);
     if (TYPE == GGML_TYPE_Q4_0) {
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(raw + r * 80 + j * 20);
-        d2 = __float2half2_rn(__uint_as_float(p[0]));
-        q[0] = p[1]; q[1] = p[2]; q[2] = p[3]; q[3] = p[4];
+        d2 = __float2half2_rn(__uint_as_float(lds32(blk)));
+        q[0] = lds32(blk + 4); q[1] = lds32(blk + 8); q[2] = lds32(blk + 12); q[3] = lds32(blk + 16);
     } else {
-        const uint2 *p = reinterpret_cast<const uint2 *>(raw + r * 96 + j * 24);
-        const uint2 dm = p[0], qa = p[1], qb = p[2];
+        const uint2 dm = lds64(blk), qa = lds64(blk + 8), qb = lds64(blk + 16);
         d2 = __float2half2_rn(__uint_as_float(dm.x));
         // q*d + m == (q-8)*d + (m + 8d): the recentred offset is ~5x smaller than m, and so is its fp16 rounding
         // error, which is coherent over the block's 32 elements and would otherwise dominate the Q4_1 error
         m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(dm.x), __uint_as_float(dm.y)));
         q[0] = qa.x; q[1] = qa.y; q[2] = qb.x; q[3] = qb.y;
     }
-    uint8_t *row = a_stage + (j >> 1) * (BM * 128) + r * 128;
-    const int rot = (j >> 1) * 2;                               // bank-conflict-free STS order across a quarter warp
+    const __half2 o_lo = __float2half2_rn(1032.0f), o_hi = __float2half2_rn(72.0f);     // 1024+8, 64+8
+    uint32_t mk_lo = 0x000F000Fu, mk_hi = 0x00F000F0u, mg_lo = 0x64006400u, mg_hi = 0x54005400u;
+    asm volatile("" : "+r"(mk_lo), "+r"(mk_hi), "+r"(mg_lo), "+r"(mg_hi));              // keep the four constants in registers
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int ci = (i + rot) & 3;
-        const uint32_t w = q[ci];
-        // (lo | 0x6400) = 1024 + q as fp16 pair for bytes 0 and 2; (hi | 0x5400) = 64 + q for the high nibbles
-        uint32_t v0 = (w & 0x000F000Fu) | 0x64006400u;          // elements 0, 4
-        uint32_t v1 = (w & 0x00F000F0u) | 0x54005400u;          // elements 1, 5
-        const uint32_t ws = w >> 8;
-        uint32_t v2 = (ws & 0x000F000Fu) | 0x64006400u;         // elements 2, 6
-        uint32_t v3 = (ws & 0x00F000F0u) | 0x54005400u;         // elements 3, 7
+        const uint32_t w = q[i], ws = w >> 8;
+        // (lo | 0x6400) = 1024 + q as an fp16 pair for bytes 0 and 2; (hi | 0x5400) = 64 + q for the high nibbles
+        uint32_t v0 = and_or(w, mk_lo, mg_lo);                  // elements 0, 4
+        uint32_t v1 = and_or(w, mk_hi, mg_hi);                  // elements 1, 5
+        uint32_t v2 = and_or(ws, mk_lo, mg_lo);                 // elements 2, 6
+        uint32_t v3 = and_or(ws, mk_hi, mg_hi);                 // elements 3, 7
         __half2 h0 = *reinterpret_cast<__half2 *>(&v0), h1 = *reinterpret_cast<__half2 *>(&v1);
         __half2 h2 = *reinterpret_cast<__half2 *>(&v2), h3 = *reinterpret_cast<__half2 *>(&v3);
         if (TYPE == GGML_TYPE_Q4_0) {
-            const __half2 o_lo = __float2half2_rn(1032.0f), o_hi = __float2half2_rn(72.0f);     // 1024+8, 64+8
             h0 = __hmul2(__hsub2(h0, o_lo), d2); h1 = __hmul2(__hsub2(h1, o_hi), d2);
             h2 = __hmul2(__hsub2(h2, o_lo), d2); h3 = __hmul2(__hsub2(h3, o_hi), d2);
         } else {
-            const __half2 o_lo = __float2half2_rn(1032.0f), o_hi = __float2half2_rn(72.0f);
             h0 = __hfma2(__hsub2(h0, o_lo), d2, m2); h1 = __hfma2(__hsub2(h1, o_hi), d2, m2);
             h2 = __hfma2(__hsub2(h2, o_lo), d2, m2); h3 = __hfma2(__hsub2(h3, o_hi), d2, m2);
         }
         uint4 o;
         o.x = *reinterpret_cast<uint32_t *>(&h0); o.y = *reinterpret_cast<uint32_t *>(&h1);
         o.z = *reinterpret_cast<uint32_t *>(&h2); o.w = *reinterpret_cast<uint32_t *>(&h3);
-        const int chunk = ((j & 1) * 4 + ci) ^ (r & 7);         // 128-byte swizzle: 16-byte chunk index XOR row-in-atom
-        *reinterpret_cast<uint4 *>(row + chunk * 16) = o;
+        sts128(row + (uint32_t)(((half * 4 + i) ^ cx) << 4), o);                  // 128-byte swizzle: chunk index XOR row-in-atom
     }
 }
 
-template <int TYPE, int BN>
+// CG = CTAs per tile: 2 -> tcgen05 cta_group::2, the pair computes 256 weight rows x BN; each CTA stages (and, for Q4,
+// dequantizes) its own 128 rows of A and only HALF of the activation tile, which halves the dominant shared-memory fill.
+template <int TYPE, int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-       float *__restrict__ Y, long long ldy, int M, int N, int K, int n_peers, const long long *__restrict__ peer_delta_unused)
+       float *__restrict__ Y, long long ldy, int M, int N, int K, long long *__restrict__ dbg)
 {
     constexpr bool DEQ = TYPE != GGML_TYPE_F16;
-    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96, BLK = TYPE == GGML_TYPE_Q4_0 ? 20 : 24;
     constexpr int RAW_BYTES = DEQ ? BM * RAW_ROW : 0;
-    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-    constexpr int NA = DEQ ? A_STAGES : B_STAGES;               // F16 weights: A rides with B through TMA
+    constexpr int BNL = BN / CG;                                 // activation rows staged by this CTA
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2;
+    constexpr int RAW_STAGES = Stages<TYPE, CG>::RAW, A_STAGES = Stages<TYPE, CG>::A, B_STAGES = Stages<TYPE, CG>::B;
+    constexpr int NA = A_STAGES;                                 // F16 weights: A rides with B through TMA (NA == B_STAGES)
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -157,20 +209,25 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
     uint8_t *sRaw = sB + B_STAGES * B_BYTES;                     // RAW_STAGES x RAW_BYTES
     uint64_t *bars = reinterpret_cast<uint64_t *>(sRaw + RAW_STAGES * RAW_BYTES);
     const uint32_t bar0 = smem_u32(bars);
-    // barrier indices
-    constexpr int RAW_FULL = 0, RAW_EMPTY = RAW_FULL + RAW_STAGES, A_FULL = RAW_EMPTY + RAW_STAGES, A_EMPTY = A_FULL + 4,
+    constexpr int RAW_FULL = 0, RAW_EMPTY = RAW_FULL + 4, A_FULL = RAW_EMPTY + 4, A_EMPTY = A_FULL + 4,
                   B_FULL = A_EMPTY + 4, B_EMPTY = B_FULL + B_STAGES, ACC_FULL = B_EMPTY + B_STAGES, NBARS = ACC_FULL + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
     auto BAR = [&](int i) { return bar0 + 8 * i; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    long long *const tdbg = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 : nullptr;   // GGB200_GEMM_TRACE: clock64 timeline
+    if (tdbg && threadIdx.x == 0) tdbg[0] = clock64();
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN + (int)rank * BNL;
     const int ksteps = (K + BK - 1) / BK;
+    // barriers the MMA issuer waits on live in the leader CTA
+    auto LBAR = [&](int i) { return CG == 2 ? mapa_u32(BAR(i), 0) : BAR(i); };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < RAW_STAGES; i++) { mbar_init(BAR(RAW_FULL + i), 1); mbar_init(BAR(RAW_EMPTY + i), NDQ_WARPS); }
-        for (int i = 0; i < NA; i++) { mbar_init(BAR(A_FULL + i), DEQ ? NDQ_WARPS : 1); mbar_init(BAR(A_EMPTY + i), 1); }
-        for (int i = 0; i < B_STAGES; i++) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
+        for (int i = 0; i < NA; i++) { mbar_init(BAR(A_FULL + i), DEQ ? CG * NDQ_WARPS : 1); mbar_init(BAR(A_EMPTY + i), 1); }
+        for (int i = 0; i < B_STAGES; i++) { mbar_init(BAR(B_FULL + i), CG); mbar_init(BAR(B_EMPTY + i), 1); }
         mbar_init(BAR(ACC_FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -180,16 +237,22 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // peer barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (tdbg && threadIdx.x == 0) tdbg[1] = clock64();                                 // setup done
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (one per CTA) =====
         if (lane == 0) {
             for (int ks = 0; ks < ksteps; ks++) {
                 if (DEQ) {
@@ -200,60 +263,102 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
                 }
                 const int sb = ks % B_STAGES;
                 mbar_wait(BAR(B_EMPTY + sb), ((ks / B_STAGES) & 1) ^ 1);
-                mbar_expect_tx(BAR(B_FULL + sb), B_BYTES + (DEQ ? 0 : A_BYTES));
-                tma_load_2d(smem_u32(sB + sb * B_BYTES), &map_x, BAR(B_FULL + sb), ks * BK, n0);
-                tma_load_2d(smem_u32(sB + sb * B_BYTES + BN * 128), &map_x, BAR(B_FULL + sb), ks * BK + 64, n0);
-                if (!DEQ) {
-                    tma_load_2d(smem_u32(sA + sb * A_BYTES), &map_w, BAR(B_FULL + sb), ks * BK, m0);
-                    tma_load_2d(smem_u32(sA + sb * A_BYTES + BM * 128), &map_w, BAR(B_FULL + sb), ks * BK + 64, m0);
+                const uint32_t full = LBAR(B_FULL + sb);
+                constexpr uint32_t per_cta = B_BYTES + (DEQ ? 0 : A_BYTES);
+                if (CG == 2) {
+                    if (leader) mbar_expect_tx(BAR(B_FULL + sb), CG * per_cta);   // counts both CTAs' bytes
+                    else mbar_arrive_cluster(full);
+                    tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES), &map_x, full, ks * BK, n0);
+                    tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, full, ks * BK + 64, n0);
+                    if (!DEQ) {
+                        tma_load_2d_cg2(smem_u32(sA + sb * A_BYTES), &map_w, full, ks * BK, m0);
+                        tma_load_2d_cg2(smem_u32(sA + sb * A_BYTES + BM * 128), &map_w, full, ks * BK + 64, m0);
+                    }
+                } else {
+                    mbar_expect_tx(BAR(B_FULL + sb), per_cta);
+                    tma_load_2d(smem_u32(sB + sb * B_BYTES), &map_x, full, ks * BK, n0);
+                    tma_load_2d(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, full, ks * BK + 64, n0);
+                    if (!DEQ) {
+                        tma_load_2d(smem_u32(sA + sb * A_BYTES), &map_w, full, ks * BK, m0);
+                        tma_load_2d(smem_u32(sA + sb * A_BYTES + BM * 128), &map_w, full, ks * BK + 64, m0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        const uint32_t idesc = make_idesc(BN);
-        for (int ks = 0; ks < ksteps; ks++) {
-            const int sa = ks % NA, sb = ks % B_STAGES;
-            if (DEQ) mbar_wait(BAR(A_FULL + sa), (ks / NA) & 1);
-            mbar_wait(BAR(B_FULL + sb), (ks / B_STAGES) & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_base = smem_u32(sA + sa * A_BYTES), b_base = smem_u32(sB + sb * B_BYTES);
+        // ===== MMA issuer: the leader CTA only =====
+        if (leader) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+            for (int ks = 0; ks < ksteps; ks++) {
+                const int sa = ks % NA, sb = ks % B_STAGES;
+                if (DEQ) mbar_wait_cluster(BAR(A_FULL + sa), (ks / NA) & 1);
+                if (tdbg && lane == 0 && ks < 20) tdbg[8 + 2 * ks] = clock64();        // A ready
+                mbar_wait_cluster(BAR(B_FULL + sb), (ks / B_STAGES) & 1);
+                if (tdbg && lane == 0 && ks < 20) tdbg[9 + 2 * ks] = clock64();        // B ready
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_base = smem_u32(sA + sa * A_BYTES), b_base = smem_u32(sB + sb * B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; k++) {
-                    // sub-tile k/4 (64 K each), then 32 bytes per K=16 step inside the 128-byte swizzle row
-                    const uint64_t ad = make_sdesc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32);
-                    const uint64_t bd = make_sdesc(b_base + (k >> 2) * (BN * 128) + (k & 3) * 32);
-                    tc_mma_f16(tmem, ad, bd, idesc, (ks | k) != 0);
+                    for (int k = 0; k < BK / 16; k++) {
+                        // sub-tile k/4 (64 K each), then 32 bytes per K=16 step inside the 128-byte swizzle row
+                        const uint64_t ad = make_sdesc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32);
+                        const uint64_t bd = make_sdesc(b_base + (k >> 2) * (BNL * 128) + (k & 3) * 32);
+                        if (CG == 2) tc_mma_f16_cg2(tmem, ad, bd, idesc, (ks | k) != 0);
+                        else tc_mma_f16(tmem, ad, bd, idesc, (ks | k) != 0);
+                    }
+                    if (CG == 2) {
+                        if (DEQ) tc_commit_cg2(BAR(A_EMPTY + sa));
+                        tc_commit_cg2(BAR(B_EMPTY + sb));
+                        if (ks == ksteps - 1) tc_commit_cg2(BAR(ACC_FULL));
+                    } else {
+                        if (DEQ) tc_commit(BAR(A_EMPTY + sa));   // frees the A stage once these MMAs have read it
+                        tc_commit(BAR(B_EMPTY + sb));
+                        if (ks == ksteps - 1) tc_commit(BAR(ACC_FULL));
+                    }
                 }
-                if (DEQ) tc_commit(BAR(A_EMPTY + sa));           // frees the A stage once these MMAs have read it
-                tc_commit(BAR(B_EMPTY + sb));
-                if (ks == ksteps - 1) tc_commit(BAR(ACC_FULL));
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== dequant warps (then warps 4..7: epilogue) =====
         if (DEQ) {
             const int dw = warp - 4;
-            const int r = dw * 8 + (lane >> 2), j = lane & 3;    // one 32-weight block per thread per K step
+            // one 32-weight block per thread per K step.  Lane bits: [0] K-half of the sub-tile, [1:2] row, [3] sub-tile,
+            // [4] row: 8 consecutive lanes = 4 rows x 2 halves of ONE sub-tile -> their STS.128 hit 8 distinct swizzled
+            // chunk slots (no bank conflict), and a warp's 32 raw blocks (rows x 20/24-byte blocks) read conflict-free too.
+            const int r = dw * 8 + (((lane >> 1) & 3) | ((lane >> 4) << 2)), j = (lane & 1) | (((lane >> 3) & 1) << 1);
+            const int raw_off = r * RAW_ROW + j * BLK;
+            const int a_off = (j >> 1) * (BM * 128) + r * 128;
+            const int cx = r & 7, half = j & 1;
+            int s = 0, sa = 0; uint32_t ph_raw = 0, ph_a = 1;
+            const uint32_t a_full0 = LBAR(A_FULL);
+            const uint32_t sraw0 = smem_u32(sRaw), sa0 = smem_u32(sA);
             for (int ks = 0; ks < ksteps; ks++) {
-                const int s = ks % RAW_STAGES, sa = ks % A_STAGES;
-                mbar_wait(BAR(RAW_FULL + s), (ks / RAW_STAGES) & 1);
-                mbar_wait(BAR(A_EMPTY + sa), ((ks / A_STAGES) & 1) ^ 1);
-                dequant_block<TYPE>(sRaw + s * RAW_BYTES, sA + sa * A_BYTES, r, j);
+                mbar_wait(BAR(RAW_FULL + s), ph_raw);
+                if (tdbg && threadIdx.x == 128 && ks < 40) { tdbg[48 + ks] = clock64(); }      // raw ready
+                mbar_wait(BAR(A_EMPTY + sa), ph_a);
+                if (tdbg && threadIdx.x == 128 && ks < 40) tdbg[88 + ks] = clock64();      // both waits done
+                dequant_block<TYPE>(sraw0 + s * RAW_BYTES + raw_off, sa0 + sa * A_BYTES + a_off, cx, half);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(BAR(A_FULL + sa)); mbar_arrive(BAR(RAW_EMPTY + s)); }
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cluster(a_full0 + 8 * sa); else mbar_arrive(BAR(A_FULL + sa));
+                    mbar_arrive(BAR(RAW_EMPTY + s));
+                }
+                if (++s == RAW_STAGES) { s = 0; ph_raw ^= 1; }
+                if (++sa == A_STAGES) { sa = 0; ph_a ^= 1; }
             }
         }
-        if (warp < 8) {
+        {
+            // epilogue on all 16 warps: warp -> (TMEM lane quadrant warp%4, 32-column group)
             const int q = warp & 3;                              // TMEM lane quadrant this warp may access
             mbar_wait(BAR(ACC_FULL), 0);
+            if (tdbg && threadIdx.x == 128) tdbg[2] = clock64();                       // accumulator complete
             tc_fence_after();
             const int m = m0 + q * 32 + lane;
+            const int nbase = blockIdx.y * BN;
 #pragma unroll 1
-            for (int cb = 0; cb < BN / 32; cb++) {
+            for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -268,18 +373,20 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
                 if (m < M) {
 #pragma unroll
                     for (int c = 0; c < 32; c++) {
-                        const int n = n0 + cb * 32 + c;
+                        const int n = nbase + cb * 32 + c;
                         if (n < N) Y[(long long)n * ldy + m] = __uint_as_float(v[c]);
                     }
                 }
             }
         }
     }
+    if (tdbg && threadIdx.x == 128) tdbg[3] = clock64();                               // epilogue stores issued
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // the peer's shared memory / TMEM stay valid until both are done
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
     }
 }
 
@@ -318,11 +425,12 @@ int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint
     return GGB_OK;
 }
 
-template <int TYPE, int BN>
+template <int TYPE, int BN, int CG>
 int launch_typed(const GemmArgs &a, cudaStream_t s)
 {
     constexpr bool DEQ = TYPE != GGML_TYPE_F16;
     constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int BNL = BN / CG;
     CUtensorMap mw, mx;
     int rc;
     if (DEQ) {
@@ -332,18 +440,26 @@ int launch_typed(const GemmArgs &a, cudaStream_t s)
         rc = make_map_2d(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.W, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.nb01, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     }
     if (rc) return rc;
-    rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, BNL, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, RAW_BYTES = DEQ ? BM * RAW_ROW : 0;
-    constexpr int NA = DEQ ? A_STAGES : B_STAGES;
-    constexpr size_t smem = 1024 + (size_t)NA * A_BYTES + (size_t)B_STAGES * B_BYTES + (size_t)RAW_STAGES * RAW_BYTES + 64 * 8 + 16;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2, RAW_BYTES = DEQ ? BM * RAW_ROW : 0;
+    constexpr size_t smem = 1024 + (size_t)Stages<TYPE, CG>::A * A_BYTES + (size_t)Stages<TYPE, CG>::B * B_BYTES +
+                            (size_t)Stages<TYPE, CG>::RAW * RAW_BYTES + 64 * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool attr_set = false;
-    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemm<TYPE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-    dim3 grid((unsigned)((a.M + BM - 1) / BM), (unsigned)((a.N + BN - 1) / BN));
-    k_gemm<TYPE, BN><<<grid, NTHREADS, smem, s>>>(mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, a.n_peers, nullptr);
+    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemm<TYPE, BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    const unsigned mt = (unsigned)((a.M + BM - 1) / BM);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((mt + CG - 1) / CG * CG, (unsigned)((a.N + BN - 1) / BN));    // whole CTA pairs; a padding CTA sees only out-of-bounds (zero) rows
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm<TYPE, BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, static_cast<long long *>(a.trace)));
     count_launch();
-    GGB_CUDA(cudaGetLastError());
     return GGB_OK;
 }
 
@@ -371,10 +487,17 @@ int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s)
 {
     (void)ws;
     if (a.n_peers) return set_error(GGB_E_UNSUPPORTED, "batched path: fused peer stores are not implemented");
+    static const int cg = [] { const char *e = getenv("GGB200_GEMM_CG"); return e ? atoi(e) : 2; }();
+    if (cg == 1) switch (a.type) {
+    case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, 128, 1>(a, s);
+    case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, 128, 1>(a, s);
+    case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, 128, 1>(a, s);
+    default: break;
+    }
     switch (a.type) {
-    case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, 128>(a, s);
-    case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, 128>(a, s);
-    case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, 128>(a, s);
+    case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, 128, 2>(a, s);
+    case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, 128, 2>(a, s);
+    case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, 128, 2>(a, s);
     default: return set_error(GGB_E_UNSUPPORTED, "batched path: type %d", a.type);
     }
 }

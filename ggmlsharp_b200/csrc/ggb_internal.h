@@ -67,6 +67,7 @@ int gemv_num_ctas();
 struct GemmArgs {
     int type; int64_t M, K, N; const void *W; int64_t nb01; const __half *Xh; int64_t Npad;
     float *Y; int64_t ldy; int n_peers; float *ypeer[7];
+    void *trace;              // optional clock64 timeline buffer (128 x int64 per CTA), debugging only
 };
 bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W);
 size_t gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);

@@ -127,6 +127,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         a.type = m.type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
         a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
         for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
+        if (const char *tr = getenv("GGB200_GEMM_TRACE")) a.trace = reinterpret_cast<void *>(strtoull(tr, nullptr, 0));   // debugging: device pointer
         rc = launch_gemm(a, wsb + off[i] + align_up((size_t)Npad * m.K * 2, 256), s);
         if (rc) return rc;
     }
