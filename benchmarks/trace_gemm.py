@@ -27,6 +27,11 @@ for cta in (0, 1, 64, 127):
     per = [ready[k + 1][1] - ready[k][1] for k in range(19)]
     print("cta %3d: setup %d  first-ready %d  acc_full %d  epilogue_end %d  | B-ready deltas: %s" % (cta, r[1] - t0, ready[0][1], r[2] - t0, r[3] - t0, per))
     print("         A-ready vs B-ready (A-B): %s" % [a - b for a, b in ready])
-    print("         dq warp: raw-ready %s" % [int(r[48 + k] - t0) for k in range(0, 32, 3)])
-    print("         dq warp: waits-done %s" % [int(r[88 + k] - t0) for k in range(0, 32, 3)])
+    for base, nm, nit in ((48, "w4(q0)", 8),):
+        for it in range(nit):
+            st = [int(r[base + it * 6 + i] - t0) for i in range(6)]
+            print("         dq %s ks=%2d: top %6d | raw-wait +%5d | lds+A_EMPTY +%5d | dequant+st +%4d | wait::st +%3d | arrive +%3d -> %6d" % (nm, it * 4, st[0], st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[5]))
+    for k in range(8):
+        st = [int(r[96 + 4 * k + i] - t0) for i in range(4)]
+        print("         mma ks=%2d: issue-start %6d | 8 MMAs + commits + probes +%4d | residual waits +%4d" % (k + 8, st[0], st[1] - st[0], st[2] - st[1]))
     print("         mma    : A-ready   %s" % [a for a, b in ready[0:20:3]])

@@ -58,6 +58,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)      // non-blocking probe
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -286,37 +293,42 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the leader CTA only =====
-        if (leader) {
+        // ===== MMA issuer: the leader CTA only; one lane, commits and next-step barrier probes hidden between MMAs =====
+        if (leader && lane == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+            if (DEQ) mbar_wait(BAR(A_FULL + 0), 0);
+            mbar_wait(BAR(B_FULL + 0), 0);
+            tc_fence_after();
             for (int ks = 0; ks < ksteps; ks++) {
                 const int sa = ks % NA, sb = ks % B_STAGES;
-                if (DEQ) mbar_wait_cluster(BAR(A_FULL + sa), (ks / NA) & 1);
-                if (tdbg && lane == 0 && ks < 20) tdbg[8 + 2 * ks] = clock64();        // A ready
-                mbar_wait_cluster(BAR(B_FULL + sb), (ks / B_STAGES) & 1);
-                if (tdbg && lane == 0 && ks < 20) tdbg[9 + 2 * ks] = clock64();        // B ready
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t a_base = smem_u32(sA + sa * A_BYTES), b_base = smem_u32(sB + sb * B_BYTES);
+                const int san = (ks + 1) % NA, sbn = (ks + 1) % B_STAGES;
+                const uint32_t par_an = (uint32_t)(((ks + 1) / NA) & 1), par_bn = (uint32_t)(((ks + 1) / B_STAGES) & 1);
+                const bool more = ks + 1 < ksteps;
+                bool a_ok = !more || !DEQ, b_ok = !more;
+                const uint32_t a_base = smem_u32(sA + sa * A_BYTES), b_base = smem_u32(sB + sb * B_BYTES);
+                if (tdbg && ks < 20) tdbg[9 + 2 * ks] = clock64();
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++) {
-                        // sub-tile k/4 (64 K each), then 32 bytes per K=16 step inside the 128-byte swizzle row
-                        const uint64_t ad = make_sdesc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32);
-                        const uint64_t bd = make_sdesc(b_base + (k >> 2) * (BNL * 128) + (k & 3) * 32);
-                        if (CG == 2) tc_mma_f16_cg2(tmem, ad, bd, idesc, (ks | k) != 0);
-                        else tc_mma_f16(tmem, ad, bd, idesc, (ks | k) != 0);
+                for (int k = 0; k < BK / 16; k++) {
+                    // sub-tile k/4 (64 K each), then 32 bytes per K=16 step inside the 128-byte swizzle row
+                    const uint64_t ad = make_sdesc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32);
+                    const uint64_t bd = make_sdesc(b_base + (k >> 2) * (BNL * 128) + (k & 3) * 32);
+                    if (CG == 2) tc_mma_f16_cg2(tmem, ad, bd, idesc, (ks | k) != 0);
+                    else tc_mma_f16(tmem, ad, bd, idesc, (ks | k) != 0);
+                    if (ks > 0) {
+                        const int sap = (ks - 1) % NA, sbp = (ks - 1) % B_STAGES;
+                        if (k == 0 && DEQ) { if (CG == 2) tc_commit_cg2(BAR(A_EMPTY + sap)); else tc_commit(BAR(A_EMPTY + sap)); }
+                        if (k == 1) { if (CG == 2) tc_commit_cg2(BAR(B_EMPTY + sbp)); else tc_commit(BAR(B_EMPTY + sbp)); }
                     }
-                    if (CG == 2) {
-                        if (DEQ) tc_commit_cg2(BAR(A_EMPTY + sa));
-                        tc_commit_cg2(BAR(B_EMPTY + sb));
-                        if (ks == ksteps - 1) tc_commit_cg2(BAR(ACC_FULL));
-                    } else {
-                        if (DEQ) tc_commit(BAR(A_EMPTY + sa));   // frees the A stage once these MMAs have read it
-                        tc_commit(BAR(B_EMPTY + sb));
-                        if (ks == ksteps - 1) tc_commit(BAR(ACC_FULL));
-                    }
+                    if (k >= 2) { if (!a_ok) a_ok = mbar_test(BAR(A_FULL + san), par_an); else if (!b_ok) b_ok = mbar_test(BAR(B_FULL + sbn), par_bn); }
                 }
-                __syncwarp();
+                if (!a_ok) mbar_wait(BAR(A_FULL + san), par_an);
+                if (!b_ok) mbar_wait(BAR(B_FULL + sbn), par_bn);
+                tc_fence_after();
+            }
+            {
+                const int sal = (ksteps - 1) % NA, sbl = (ksteps - 1) % B_STAGES;
+                if (CG == 2) { if (DEQ) tc_commit_cg2(BAR(A_EMPTY + sal)); tc_commit_cg2(BAR(B_EMPTY + sbl)); tc_commit_cg2(BAR(ACC_FULL)); }
+                else { if (DEQ) tc_commit(BAR(A_EMPTY + sal)); tc_commit(BAR(B_EMPTY + sbl)); tc_commit(BAR(ACC_FULL)); }
             }
         }
     } else if (warp >= 4) {
@@ -387,6 +399,283 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
         tc_fence_after();
         if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q4_0 / Q4_1 weights: the dequantized A operand lives in TENSOR MEMORY, not shared memory.
+//
+// profiles/r01_gemm_trace.txt: with A staged in shared memory the K step took ~1150 cycles against a 512-cycle MMA floor,
+// and the clock64 trace showed neither TMA latency nor instruction issue but shared-memory BANDWIDTH as the limit:
+// per K step a CTA moved raw 10 KB in + 10 KB out, A 32 KB in (STS) + 32 KB out (tensor core), B 16 KB in + 16 KB out
+// = 116 KB at 128 B/clk.  tcgen05.mma can take A from TMEM, and the dequant warps already own one weight row per lane --
+// exactly TMEM's lane = row layout -- so they write fp16 pairs with tcgen05.st and 64 KB of shared traffic per step
+// disappears (52 KB left = ~400 cycles, below the MMA floor).
+//
+// TMEM columns: [0, BN) fp32 accumulator; [BN + 64*g, +64) A stage g (128 K halfs = 64 x 32-bit), g = K step mod 4.
+// Dequant warp (4 + 4*g + q): TMEM lane quadrant q = warp % 4 (hardware rule), K steps ks == g (mod 4).  Each thread reads its
+// row's 80 / 96 raw bytes of the step with LDS.128 (lane stride 20 / 24 words), expands 4 blocks to 64 half2 registers
+// in the K order 0,4,1,5,2,6,3,7 per 8 (the activation buffer uses the same order) and stores them to its lane.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool cg2)
+{
+    if (cg2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// 8 weights of one 32-bit nibble word -> 4 half2 in K order (0,4) (1,5) (2,6) (3,7), scaled: (q-8)*d [+ m']
+template <int TYPE>
+__device__ __forceinline__ void dequant_word(uint32_t w, __half2 d2, __half2 m2, uint32_t mk_lo, uint32_t mk_hi, uint32_t mg_lo, uint32_t mg_hi, uint32_t *out)
+{
+    const __half2 o_lo = __float2half2_rn(1032.0f), o_hi = __float2half2_rn(72.0f);     // 1024+8, 64+8
+    const uint32_t ws = w >> 8;
+    uint32_t v0 = and_or(w, mk_lo, mg_lo), v1 = and_or(w, mk_hi, mg_hi), v2 = and_or(ws, mk_lo, mg_lo), v3 = and_or(ws, mk_hi, mg_hi);
+    __half2 h0 = *reinterpret_cast<__half2 *>(&v0), h1 = *reinterpret_cast<__half2 *>(&v1);
+    __half2 h2 = *reinterpret_cast<__half2 *>(&v2), h3 = *reinterpret_cast<__half2 *>(&v3);
+    if (TYPE == GGML_TYPE_Q4_0) {
+        h0 = __hmul2(__hsub2(h0, o_lo), d2); h1 = __hmul2(__hsub2(h1, o_hi), d2);
+        h2 = __hmul2(__hsub2(h2, o_lo), d2); h3 = __hmul2(__hsub2(h3, o_hi), d2);
+    } else {
+        h0 = __hfma2(__hsub2(h0, o_lo), d2, m2); h1 = __hfma2(__hsub2(h1, o_hi), d2, m2);
+        h2 = __hfma2(__hsub2(h2, o_lo), d2, m2); h3 = __hfma2(__hsub2(h3, o_hi), d2, m2);
+    }
+    out[0] = *reinterpret_cast<uint32_t *>(&h0); out[1] = *reinterpret_cast<uint32_t *>(&h1);
+    out[2] = *reinterpret_cast<uint32_t *>(&h2); out[3] = *reinterpret_cast<uint32_t *>(&h3);
+}
+
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t *v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+                   "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+
+template <int TYPE, int CG> struct QStages {
+    static constexpr int RAW = TYPE == GGML_TYPE_Q4_0 ? 8 : 6;
+    static constexpr int B = CG == 2 ? 8 : 4;
+};
+
+template <int TYPE, int BN, int CG>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+         float *__restrict__ Y, long long ldy, int M, int N, int K, long long *__restrict__ dbg, int dbg_flags)
+{
+    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int RAW_BYTES = BM * RAW_ROW;
+    constexpr int BNL = BN / CG;
+    constexpr int B_BYTES = BNL * BK * 2;
+    constexpr int RAW_STAGES = QStages<TYPE, CG>::RAW, B_STAGES = QStages<TYPE, CG>::B, A_STAGES = 4;
+    // two MMA issuer warps (even / odd K steps) accumulate into separate TMEM regions that the epilogue adds
+    constexpr int TMEM_COLS = 512, NISSUE = 2, A_COL0 = NISSUE * BN;
+    static_assert(NISSUE * BN + A_STAGES * 64 <= TMEM_COLS, "TMEM budget");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem;
+    uint8_t *sRaw = sB + B_STAGES * B_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sRaw + RAW_STAGES * RAW_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    constexpr int RAW_FULL = 0, RAW_EMPTY = 8, A_FULL = 16, A_EMPTY = 20, B_FULL = 24, B_EMPTY = 32, ACC_FULL = 40, NBARS = 41;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
+    auto BAR = [&](int i) { return bar0 + 8 * i; };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long *const tdbg = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 : nullptr;
+    if (tdbg && threadIdx.x == 0) tdbg[0] = clock64();
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN + (int)rank * BNL;
+    const int ksteps = (K + BK - 1) / BK;
+    auto LBAR = [&](int i) { return CG == 2 ? mapa_u32(BAR(i), 0) : BAR(i); };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RAW_STAGES; i++) { mbar_init(BAR(RAW_FULL + i), 1); mbar_init(BAR(RAW_EMPTY + i), 4); }
+        for (int i = 0; i < A_STAGES; i++) { mbar_init(BAR(A_FULL + i), 4 * CG); mbar_init(BAR(A_EMPTY + i), 1); }
+        for (int i = 0; i < B_STAGES; i++) { mbar_init(BAR(B_FULL + i), CG); mbar_init(BAR(B_EMPTY + i), 1); }
+        mbar_init(BAR(ACC_FULL), NISSUE);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    }
+    if (warp == 2) {
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (tdbg && threadIdx.x == 0) tdbg[1] = clock64();
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int s = 0, sb = 0; uint32_t ph_s = 1, ph_b = 1;
+            for (int ks = 0; ks < ksteps; ks++) {
+                mbar_wait(BAR(RAW_EMPTY + s), ph_s);
+                mbar_expect_tx(BAR(RAW_FULL + s), RAW_BYTES);
+                tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &map_w, BAR(RAW_FULL + s), ks * RAW_ROW, m0);
+                mbar_wait(BAR(B_EMPTY + sb), ph_b);
+                if (CG == 2) {
+                    const uint32_t full = LBAR(B_FULL + sb);
+                    if (leader) mbar_expect_tx(BAR(B_FULL + sb), CG * B_BYTES); else mbar_arrive_cluster(full);
+                    tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES), &map_x, full, ks * BK, n0);
+                    tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, full, ks * BK + 64, n0);
+                } else {
+                    mbar_expect_tx(BAR(B_FULL + sb), B_BYTES);
+                    tma_load_2d(smem_u32(sB + sb * B_BYTES), &map_x, BAR(B_FULL + sb), ks * BK, n0);
+                    tma_load_2d(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, BAR(B_FULL + sb), ks * BK + 64, n0);
+                }
+                if (++s == RAW_STAGES) { s = 0; ph_s ^= 1; }
+                if (++sb == B_STAGES) { sb = 0; ph_b ^= 1; }
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers (leader CTA): A from TMEM, B from shared memory =====
+        // benchmarks/micro/mma_rate.cu: tcgen05.mma issue is effectively synchronous for the issuing thread -- a lone
+        // issuer that also waits on barriers and commits ran at ~125 cycles per 128x128x16 MMA against the 64-cycle
+        // floor, two issuers with the same overhead at ~78.  So warps 1 and 3 take the even / odd K steps, each with its
+        // own accumulator (columns [0,BN) and [BN,2BN)); descriptors are one 64-bit add off a per-stage base.
+        if (leader && lane == 0) {
+            const int me = warp >> 1;                                  // 0 or 1
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+            const uint32_t acc = tmem + (uint32_t)(me * BN);
+            const uint64_t bdesc0 = make_sdesc(smem_u32(sB));
+            for (int ks = me; ks < ksteps; ks += NISSUE) {
+                const int g = ks & 3, sb = ks % B_STAGES;
+                mbar_wait(BAR(A_FULL + g), (uint32_t)((ks >> 2) & 1));
+                mbar_wait(BAR(B_FULL + sb), (uint32_t)((ks / B_STAGES) & 1));
+                tc_fence_after();
+                const uint64_t bd0 = bdesc0 + (uint64_t)((sb * B_BYTES) >> 4);
+                const uint32_t a_base = tmem + A_COL0 + g * 64;
+#pragma unroll
+                for (int k = 0; k < BK / 16; k++)
+                    tc_mma_f16_ts(acc, a_base + k * 8, bd0 + (uint64_t)(((k >> 2) * (BNL * 128) + (k & 3) * 32) >> 4), idesc, (ks >= NISSUE) || k != 0, CG == 2);
+                if (CG == 2) { tc_commit_cg2(BAR(A_EMPTY + g)); tc_commit_cg2(BAR(B_EMPTY + sb)); }
+                else { tc_commit(BAR(A_EMPTY + g)); tc_commit(BAR(B_EMPTY + sb)); }
+            }
+            if (CG == 2) tc_commit_cg2(BAR(ACC_FULL)); else tc_commit(BAR(ACC_FULL));
+        }
+    } else if (warp >= 4) {
+        // ===== dequant warps: raw blocks (shared) -> fp16 A rows (tensor memory) =====
+        {
+            const int q = warp & 3, g = (warp - 4) >> 2;
+            const int r = q * 32 + lane;
+            const uint32_t raw_row = smem_u32(sRaw) + (uint32_t)(r * RAW_ROW);
+            const uint32_t a_full = LBAR(A_FULL + g);
+            const uint32_t a_tmem = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_COL0 + g * 64);
+            uint32_t mk_lo = 0x000F000Fu, mk_hi = 0x00F000F0u, mg_lo = 0x64006400u, mg_hi = 0x54005400u;
+            asm volatile("" : "+r"(mk_lo), "+r"(mk_hi), "+r"(mg_lo), "+r"(mg_hi));
+            uint32_t ph_a = 1;
+            for (int ks = g; ks < ksteps; ks += 4) {
+                const int s = ks % RAW_STAGES;
+                if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 0] = clock64();
+                mbar_wait(BAR(RAW_FULL + s), (uint32_t)((ks / RAW_STAGES) & 1));
+                if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 1] = clock64();
+                uint32_t w[RAW_ROW / 4] = {};
+                if (!(dbg_flags & 2))
+#pragma unroll
+                for (int i = 0; i < RAW_ROW / 16; i++) {
+                    const uint4 t = lds128(raw_row + (uint32_t)(s * RAW_BYTES + i * 16));
+                    w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(RAW_EMPTY + s));          // raw bytes are in registers: release the stage early
+                mbar_wait(BAR(A_EMPTY + g), ph_a);
+                if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 2] = clock64();
+                tc_fence_after();
+                if (!(dbg_flags & 1))
+#pragma unroll
+                for (int hb = 0; hb < 2; hb++) {                         // two blocks (64 K = 32 columns) per TMEM store
+                    uint32_t v[32];
+#pragma unroll
+                    for (int jb = 0; jb < 2; jb++) {
+                        const int j = hb * 2 + jb;
+                        __half2 d2, m2 = __float2half2_rn(0.0f);
+                        const uint32_t *wb = TYPE == GGML_TYPE_Q4_0 ? &w[5 * j] : &w[6 * j];
+                        d2 = __float2half2_rn(__uint_as_float(wb[0]));
+                        if (TYPE == GGML_TYPE_Q4_1) m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(wb[0]), __uint_as_float(wb[1])));   // m + 8d, see dequant_block
+                        const uint32_t *qw = TYPE == GGML_TYPE_Q4_0 ? wb + 1 : wb + 2;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) dequant_word<TYPE>(qw[i], d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16 + i * 4]);
+                    }
+                    tmem_st_x32(a_tmem + (uint32_t)(hb * 32), v);
+                }
+                if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 3] = clock64();
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 4] = clock64();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (CG == 2) mbar_arrive_cluster(a_full); else mbar_arrive(BAR(A_FULL + g)); }
+                if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 5] = clock64();
+                ph_a ^= 1;
+            }
+        }
+        {
+            // epilogue on all 16 warps: warp -> (TMEM lane quadrant warp%4, 32-column group)
+            const int q = warp & 3;
+            mbar_wait(BAR(ACC_FULL), 0);
+            if (tdbg && threadIdx.x == 128) tdbg[2] = clock64();
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+            const int nbase = blockIdx.y * BN;
+#pragma unroll 1
+            for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
+                uint32_t v[32], u[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
+#define GGB_TMEM_LD32(ARR, ADDR) \
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
+                             : "=r"(ARR[0]), "=r"(ARR[1]), "=r"(ARR[2]), "=r"(ARR[3]), "=r"(ARR[4]), "=r"(ARR[5]), "=r"(ARR[6]), "=r"(ARR[7]), \
+                               "=r"(ARR[8]), "=r"(ARR[9]), "=r"(ARR[10]), "=r"(ARR[11]), "=r"(ARR[12]), "=r"(ARR[13]), "=r"(ARR[14]), "=r"(ARR[15]), \
+                               "=r"(ARR[16]), "=r"(ARR[17]), "=r"(ARR[18]), "=r"(ARR[19]), "=r"(ARR[20]), "=r"(ARR[21]), "=r"(ARR[22]), "=r"(ARR[23]), \
+                               "=r"(ARR[24]), "=r"(ARR[25]), "=r"(ARR[26]), "=r"(ARR[27]), "=r"(ARR[28]), "=r"(ARR[29]), "=r"(ARR[30]), "=r"(ARR[31]) \
+                             : "r"(ADDR) : "memory")
+                GGB_TMEM_LD32(v, taddr);
+                GGB_TMEM_LD32(u, taddr + (uint32_t)BN);
+#undef GGB_TMEM_LD32
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ksteps > 1) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(u[c]));     // even-K + odd-K partial sums
+                }
+                if (m < M) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        const int n = nbase + cb * 32 + c;
+                        if (n < N) Y[(long long)n * ldy + m] = __uint_as_float(v[c]);
+                    }
+                }
+            }
+        }
+    }
+    if (tdbg && threadIdx.x == 128) tdbg[3] = clock64();
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -463,6 +752,37 @@ int launch_typed(const GemmArgs &a, cudaStream_t s)
     return GGB_OK;
 }
 
+template <int TYPE, int BN, int CG>
+int launch_q(const GemmArgs &a, cudaStream_t s)
+{
+    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int BNL = BN / CG;
+    CUtensorMap mw, mx;
+    const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * (TYPE == GGML_TYPE_Q4_0 ? 20 : 24);
+    int rc = make_map_2d(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, row_bytes, (uint64_t)a.M, (uint64_t)a.nb01, RAW_ROW, BM, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, BNL, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    constexpr size_t smem = 1024 + (size_t)QStages<TYPE, CG>::B * (BNL * BK * 2) + (size_t)QStages<TYPE, CG>::RAW * (BM * RAW_ROW) + 64 * 8 + 16;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemm_q<TYPE, BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    const unsigned mt = (unsigned)((a.M + BM - 1) / BM);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((mt + CG - 1) / CG * CG, (unsigned)((a.N + BN - 1) / BN));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    static const int dbg_flags = [] { const char *e = getenv("GGB200_GEMM_DBG"); return e ? atoi(e) : 0; }();   // perf experiments only (wrong results)
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_q<TYPE, BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, static_cast<long long *>(a.trace), dbg_flags));
+    count_launch();
+    return GGB_OK;
+}
+
 } // namespace
 
 bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W)
@@ -488,6 +808,11 @@ int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s)
     (void)ws;
     if (a.n_peers) return set_error(GGB_E_UNSUPPORTED, "batched path: fused peer stores are not implemented");
     static const int cg = [] { const char *e = getenv("GGB200_GEMM_CG"); return e ? atoi(e) : 2; }();
+    static const bool a_smem = [] { const char *e = getenv("GGB200_GEMM_A"); return e && e[0] == 's'; }();   // debugging: A staged in shared memory
+    if (!a_smem) {
+        if (a.type == GGML_TYPE_Q4_0) return cg == 1 ? launch_q<GGML_TYPE_Q4_0, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_0, 128, 2>(a, s);
+        if (a.type == GGML_TYPE_Q4_1) return cg == 1 ? launch_q<GGML_TYPE_Q4_1, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_1, 128, 2>(a, s);
+    }
     if (cg == 1) switch (a.type) {
     case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, 128, 1>(a, s);
     case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, 128, 1>(a, s);
