@@ -21,6 +21,10 @@ for _ in range(3):
     N.check(L.ggb_dev_mul_mat_batch(C.byref(mm), 1, wsp, wsb, sp))
 torch.cuda.synchronize()
 tr = trace.cpu().numpy()
+import numpy as np
+st, en = tr[:128, 4], tr[:128, 5]
+print('globaltimer (ns): CTA start spread %d, first start -> last end %d, per-CTA duration min/med/max %d/%d/%d' % (st.max() - st.min(), en.max() - st.min(), (en - st).min(), np.median(en - st), (en - st).max()))
+print('per-CTA cycles (clock64) min/med/max: %d/%d/%d' % ((tr[:128,3]-tr[:128,0]).min(), np.median(tr[:128,3]-tr[:128,0]), (tr[:128,3]-tr[:128,0]).max()))
 for cta in (0, 1, 64, 127):
     r = tr[cta]; t0 = r[0]
     ready = [(int(r[8 + 2 * k] - t0), int(r[9 + 2 * k] - t0)) for k in range(20)]

@@ -236,38 +236,62 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
 
 // Batched (tensor-core) path: activations as fp16 values the reference's dot effectively multiplies by:
 // Q4_x weights -> d * round(x / d) of the Q8 block (same d, same quants as quantize_row_q8_x); F16 -> (Half)x.
-// Rows n >= N of the padded buffer are zero.
+// Rows n >= N of the padded buffer are zero.  One thread per block of 32 elements (128 B in, 64 B out): the kernel is
+// a pure stream (12 B per element), so everything is kept in registers and the K permutation 0,4,1,5,2,6,3,7 that the
+// GEMM's nibble unpack produces costs nothing.
 __global__ void __launch_bounds__(256) k_act_f16_dequant(int wtype, int perm, const float *__restrict__ x, long long ldx_bytes,
-                                                         __half *__restrict__ out, int N, int Npad, int K)
+                                                         __half *__restrict__ out, int N, int Npad, int K, int vec16)
 {
-    const int lane = threadIdx.x & 31, sub = lane & 7;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the GEMM's prologue and weight streaming may start now
+    asm volatile("griddepcontrol.wait;" ::: "memory");                // x may be the previous kernel's output
     const int kb = K / GGB_QK;
-    const long long blk = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    if (blk >= (long long)Npad * kb) return;                    // whole warps leave together: (Npad*kb*8) % 32 == 0 since Npad % 16 == 0
-    const int row = (int)(blk / kb), col = (int)(blk - (long long)row * kb);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < N) v = *reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(x) + (long long)row * ldx_bytes + (long long)col * 128 + sub * 16);
-    float e[4] = {v.x, v.y, v.z, v.w};
-    if (wtype != GGML_TYPE_F16) {
-        float amax = fmaxf(fmaxf(fabsf(e[0]), fabsf(e[1])), fmaxf(fabsf(e[2]), fabsf(e[3])));
+    const long long nblk = (long long)Npad * kb;
+    for (long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(blk / kb), col = (int)(blk - (long long)row * kb);
+        float e[32];
+        if (row < N) {
+            const char *p = reinterpret_cast<const char *>(x) + (long long)row * ldx_bytes + (long long)col * 128;
+            if (vec16) {
 #pragma unroll
-        for (int off = 1; off < 8; off <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
-        const float d = __fdiv_rn(amax, 127.0f);
-        const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+                for (int i = 0; i < 8; i++) { const float4 v = __ldg(reinterpret_cast<const float4 *>(p) + i); e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w; }
+            } else {
 #pragma unroll
-        for (int i = 0; i < 4; i++) e[i] = __fmul_rn(d, (float)(int)(int8_t)rne_byte(__fmul_rn(e[i], id)));
+                for (int i = 0; i < 32; i++) e[i] = reinterpret_cast<const float *>(p)[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) e[i] = 0.0f;
+        }
+        if (wtype != GGML_TYPE_F16) {
+            float amax = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(e[i]));
+            const float d = __fdiv_rn(amax, 127.0f);
+            const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+            if (id < 3.0e38f) {                                    // every sane block: |x*id| <= 127.0000x, plain ties-to-even
+#pragma unroll
+                for (int i = 0; i < 32; i++) e[i] = __fmul_rn(d, (float)__float2int_rn(__fmul_rn(e[i], id)));
+            } else {                                               // 1/d overflowed (subnormal scale): .NET cast semantics
+#pragma unroll
+                for (int i = 0; i < 32; i++) e[i] = __fmul_rn(d, (float)(int)(int8_t)rne_byte(__fmul_rn(e[i], id)));
+            }
+        }
+        uint32_t o[16];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            // group of 8 elements -> 4 half2; natural order (0,1)(2,3)(4,5)(6,7) or permuted (0,4)(1,5)(2,6)(3,7)
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float a = perm ? e[8 * g + t] : e[8 * g + 2 * t];
+                const float b = perm ? e[8 * g + 4 + t] : e[8 * g + 2 * t + 1];
+                const __half2 h = __floats2half2_rn(a, b);
+                o[4 * g + t] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(out + (long long)row * K + (long long)col * GGB_QK);
+#pragma unroll
+        for (int i = 0; i < 4; i++) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
     }
-    const __half2 h0 = __floats2half2_rn(e[0], e[1]), h1 = __floats2half2_rn(e[2], e[3]);
-    uint2 pk; pk.x = *reinterpret_cast<const uint32_t *>(&h0); pk.y = *reinterpret_cast<const uint32_t *>(&h1);
-    if (perm) {
-        // K order 0,4,1,5,2,6,3,7 inside every group of 8: the order the GEMM's nibble unpack produces
-        const bool odd = sub & 1;
-        const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? pk.x : pk.y, 1);
-        const uint32_t a = odd ? recv : pk.x, b = odd ? pk.y : recv;     // even: (mine01, partner01); odd: (partner23, mine23)
-        pk.x = __byte_perm(a, b, 0x5410);
-        pk.y = __byte_perm(a, b, 0x7632);
-    }
-    *reinterpret_cast<uint2 *>(out + (long long)row * K + (long long)col * GGB_QK + sub * 4) = pk;
 }
 
 } // namespace
@@ -341,10 +365,22 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
 
 int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s)
 {
-    const long long threads = Npad * (K / GGB_QK) * 8;
-    if (threads <= 0) return GGB_OK;
-    k_act_f16_dequant<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(wtype, perm, x, ldx_bytes, out, (int)N, (int)Npad, (int)K);
-    count_launch(); GGB_CUDA(cudaGetLastError());
+    const long long nblk = Npad * (K / GGB_QK);
+    if (nblk <= 0) return GGB_OK;
+    const int vec16 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx_bytes & 15) == 0) ? 1 : 0;
+    long long grid = (nblk + 255) / 256;
+    const long long cap = (long long)device_sm_count() * 8;
+    if (grid > cap) grid = cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant, wtype, perm, x, (long long)ldx_bytes, out, (int)N, (int)Npad, (int)K, vec16));
+    count_launch();
     return GGB_OK;
 }
 

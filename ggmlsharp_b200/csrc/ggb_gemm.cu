@@ -261,6 +261,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
     if (warp == 0) {
         // ===== TMA producer (one per CTA) =====
         if (lane == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");       // PDL: activations come from the preceding kernel
             for (int ks = 0; ks < ksteps; ks++) {
                 if (DEQ) {
                     const int s = ks % RAW_STAGES;
@@ -461,10 +462,14 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t *v)
                    "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
 }
 
+// RAW must be a multiple of the 4 dequant groups: then raw stage s is always consumed by group s % 4, which also consumed
+// its previous phase, so a parity wait can never alias a stale phase (with RAW = 6 a group running ahead of the TMA read
+// a stage one revolution early -- rel-L2 1.5e-2 on large Q4_1 shapes, caught by tests/test_gpu_gemm.py).
 template <int TYPE, int CG> struct QStages {
-    static constexpr int RAW = TYPE == GGML_TYPE_Q4_0 ? 8 : 6;
-    static constexpr int B = CG == 2 ? 8 : 4;
+    static constexpr int RAW = 8;
+    static constexpr int B = 4;
 };
+static_assert(QStages<GGML_TYPE_Q4_1, 2>::RAW % 4 == 0, "raw ring must be a multiple of the dequant groups");
 
 template <int TYPE, int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -475,7 +480,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
     constexpr int RAW_BYTES = BM * RAW_ROW;
     constexpr int BNL = BN / CG;
     constexpr int B_BYTES = BNL * BK * 2;
-    constexpr int RAW_STAGES = QStages<TYPE, CG>::RAW, B_STAGES = QStages<TYPE, CG>::B, A_STAGES = 4;
+    constexpr int RAW_STAGES = QStages<TYPE, CG>::RAW, A_STAGES = 4, B_STAGES = A_STAGES;   // A (TMEM) and B (smem) stages share one barrier ring
     // two MMA issuer warps (even / odd K steps) accumulate into separate TMEM regions that the epilogue adds
     constexpr int TMEM_COLS = 512, NISSUE = 2, A_COL0 = NISSUE * BN;
     static_assert(NISSUE * BN + A_STAGES * 64 <= TMEM_COLS, "TMEM budget");
@@ -486,13 +491,14 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
     uint8_t *sRaw = sB + B_STAGES * B_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sRaw + RAW_STAGES * RAW_BYTES);
     const uint32_t bar0 = smem_u32(bars);
-    constexpr int RAW_FULL = 0, RAW_EMPTY = 8, A_FULL = 16, A_EMPTY = 20, B_FULL = 24, B_EMPTY = 32, ACC_FULL = 40, NBARS = 41;
+    // FULL[g]: 4*CG dequant-warp arrivals + CG activation-producer arrivals (+ the TMA bytes); EMPTY[g]: one commit per K step
+    constexpr int RAW_FULL = 0, RAW_EMPTY = 8, A_FULL = 16, A_EMPTY = 20, ACC_FULL = 24, NBARS = 25;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
     auto BAR = [&](int i) { return bar0 + 8 * i; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long *const tdbg = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 : nullptr;
-    if (tdbg && threadIdx.x == 0) tdbg[0] = clock64();
+    if (tdbg && threadIdx.x == 0) { tdbg[0] = clock64(); unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); tdbg[4] = (long long)gt; }
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
     const bool leader = rank == 0;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN + (int)rank * BNL;
@@ -501,8 +507,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < RAW_STAGES; i++) { mbar_init(BAR(RAW_FULL + i), 1); mbar_init(BAR(RAW_EMPTY + i), 4); }
-        for (int i = 0; i < A_STAGES; i++) { mbar_init(BAR(A_FULL + i), 4 * CG); mbar_init(BAR(A_EMPTY + i), 1); }
-        for (int i = 0; i < B_STAGES; i++) { mbar_init(BAR(B_FULL + i), CG); mbar_init(BAR(B_EMPTY + i), 1); }
+        for (int i = 0; i < A_STAGES; i++) { mbar_init(BAR(A_FULL + i), 4 * CG + CG); mbar_init(BAR(A_EMPTY + i), 1); }
         mbar_init(BAR(ACC_FULL), NISSUE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -527,25 +532,33 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
     if (tdbg && threadIdx.x == 0) tdbg[1] = clock64();
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer 1: raw quant blocks (own barrier ring, never blocked by the activation ring) =====
         if (lane == 0) {
-            int s = 0, sb = 0; uint32_t ph_s = 1, ph_b = 1;
+            int s = 0; uint32_t ph_s = 1;
             for (int ks = 0; ks < ksteps; ks++) {
                 mbar_wait(BAR(RAW_EMPTY + s), ph_s);
                 mbar_expect_tx(BAR(RAW_FULL + s), RAW_BYTES);
                 tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &map_w, BAR(RAW_FULL + s), ks * RAW_ROW, m0);
-                mbar_wait(BAR(B_EMPTY + sb), ph_b);
+                if (++s == RAW_STAGES) { s = 0; ph_s ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== TMA producer 2: activation tiles (this CTA's half of the BN rows) =====
+        if (lane == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");       // PDL: the activation kernel must have finished; weights never wait
+            int sb = 0; uint32_t ph_b = 1;
+            for (int ks = 0; ks < ksteps; ks++) {
+                mbar_wait(BAR(A_EMPTY + sb), ph_b);
                 if (CG == 2) {
-                    const uint32_t full = LBAR(B_FULL + sb);
-                    if (leader) mbar_expect_tx(BAR(B_FULL + sb), CG * B_BYTES); else mbar_arrive_cluster(full);
+                    const uint32_t full = LBAR(A_FULL + sb);
+                    if (leader) mbar_expect_tx(BAR(A_FULL + sb), CG * B_BYTES); else mbar_arrive_cluster(full);
                     tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES), &map_x, full, ks * BK, n0);
                     tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, full, ks * BK + 64, n0);
                 } else {
-                    mbar_expect_tx(BAR(B_FULL + sb), B_BYTES);
-                    tma_load_2d(smem_u32(sB + sb * B_BYTES), &map_x, BAR(B_FULL + sb), ks * BK, n0);
-                    tma_load_2d(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, BAR(B_FULL + sb), ks * BK + 64, n0);
+                    mbar_expect_tx(BAR(A_FULL + sb), B_BYTES);
+                    tma_load_2d(smem_u32(sB + sb * B_BYTES), &map_x, BAR(A_FULL + sb), ks * BK, n0);
+                    tma_load_2d(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, BAR(A_FULL + sb), ks * BK + 64, n0);
                 }
-                if (++s == RAW_STAGES) { s = 0; ph_s ^= 1; }
                 if (++sb == B_STAGES) { sb = 0; ph_b ^= 1; }
             }
         }
@@ -561,17 +574,15 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
             const uint32_t acc = tmem + (uint32_t)(me * BN);
             const uint64_t bdesc0 = make_sdesc(smem_u32(sB));
             for (int ks = me; ks < ksteps; ks += NISSUE) {
-                const int g = ks & 3, sb = ks % B_STAGES;
-                mbar_wait(BAR(A_FULL + g), (uint32_t)((ks >> 2) & 1));
-                mbar_wait(BAR(B_FULL + sb), (uint32_t)((ks / B_STAGES) & 1));
+                const int g = ks & 3;
+                mbar_wait(BAR(A_FULL + g), (uint32_t)((ks >> 2) & 1));       // A rows in TMEM (both CTAs) + both halves of the B tile
                 tc_fence_after();
-                const uint64_t bd0 = bdesc0 + (uint64_t)((sb * B_BYTES) >> 4);
+                const uint64_t bd0 = bdesc0 + (uint64_t)((g * B_BYTES) >> 4);
                 const uint32_t a_base = tmem + A_COL0 + g * 64;
 #pragma unroll
                 for (int k = 0; k < BK / 16; k++)
                     tc_mma_f16_ts(acc, a_base + k * 8, bd0 + (uint64_t)(((k >> 2) * (BNL * 128) + (k & 3) * 32) >> 4), idesc, (ks >= NISSUE) || k != 0, CG == 2);
-                if (CG == 2) { tc_commit_cg2(BAR(A_EMPTY + g)); tc_commit_cg2(BAR(B_EMPTY + sb)); }
-                else { tc_commit(BAR(A_EMPTY + g)); tc_commit(BAR(B_EMPTY + sb)); }
+                if (CG == 2) tc_commit_cg2(BAR(A_EMPTY + g)); else tc_commit(BAR(A_EMPTY + g));     // frees TMEM stage g and B stage g
             }
             if (CG == 2) tc_commit_cg2(BAR(ACC_FULL)); else tc_commit(BAR(ACC_FULL));
         }
@@ -598,8 +609,9 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                     const uint4 t = lds128(raw_row + (uint32_t)(s * RAW_BYTES + i * 16));
                     w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(RAW_EMPTY + s));          // raw bytes are in registers: release the stage early
+                // NOTE: the raw stage is released only after the dequant below has CONSUMED these registers.  Arriving right after
+                // issuing the LDS (data still in flight) let the next TMA overwrite the stage under the loads: intermittent
+                // rel-L2 ~5e-3 on large Q4_1 shapes (benchmarks/q41_bisect.sh).
                 mbar_wait(BAR(A_EMPTY + g), ph_a);
                 if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 2] = clock64();
                 tc_fence_after();
@@ -625,7 +637,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                 if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 4] = clock64();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { if (CG == 2) mbar_arrive_cluster(a_full); else mbar_arrive(BAR(A_FULL + g)); }
+                if (lane == 0) { if (CG == 2) mbar_arrive_cluster(a_full); else mbar_arrive(BAR(A_FULL + g)); mbar_arrive(BAR(RAW_EMPTY + s)); }
                 if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 5] = clock64();
                 ph_a ^= 1;
             }
@@ -669,7 +681,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
             }
         }
     }
-    if (tdbg && threadIdx.x == 128) tdbg[3] = clock64();
+    if (tdbg && threadIdx.x == 128) { tdbg[3] = clock64(); unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); tdbg[5] = (long long)gt; }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
@@ -743,10 +755,13 @@ int launch_typed(const GemmArgs &a, cudaStream_t s)
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // prologue + weight streaming overlap the activation kernel
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("GGB200_NO_PDL") != nullptr;
+    cfg.attrs = at; cfg.numAttrs = no_pdl ? 1 : 2;
     GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm<TYPE, BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, static_cast<long long *>(a.trace)));
     count_launch();
     return GGB_OK;
@@ -773,10 +788,13 @@ int launch_q(const GemmArgs &a, cudaStream_t s)
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // prologue + weight streaming overlap the activation kernel
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("GGB200_NO_PDL") != nullptr;
+    cfg.attrs = at; cfg.numAttrs = no_pdl ? 1 : 2;
     static const int dbg_flags = [] { const char *e = getenv("GGB200_GEMM_DBG"); return e ? atoi(e) : 0; }();   // perf experiments only (wrong results)
     GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_q<TYPE, BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, static_cast<long long *>(a.trace), dbg_flags));
     count_launch();
