@@ -130,7 +130,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     nth = os.cpu_count() or 1
-    sample_nodes = RING                                         # one step = the whole ring: ~0.5 s single-threaded
+    sample_nodes = int(os.environ.get("GGB_BENCH_REF_RING", RING))        # one step = the whole ring: ~0.5 s single-threaded (tests shrink it)
     nodes = host_ring(sample_nodes, M_LOCAL * world)
     for _ in range(args.warmup):
         cpu_mul_mat_ring(nodes[:4], nth)
@@ -143,9 +143,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "Q4_0 mul_mat HBM GB/s (% roofline)", "value": val, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8 dot (Q4_0 x Q8_0), f32 scales", "data": "synthetic",
-            "config": {"workload": "configs[1]: Q4_0 4096x4096 GEMV, single token; ring of %d distinct matrices (%d rows each)" % (RING, M_LOCAL * world)},
+            "config": {"workload": "configs[1]: Q4_0 4096x4096 GEMV, single token; ring of %d distinct matrices (%d rows each)" % (len(nodes), M_LOCAL * world)},
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": nth, "kind": "port",
-                             "sample": "full ring of %d GEMVs per step; C restatement of ggml_compute_forward_mul_mat_q_f32 (not .NET RyuJIT)" % RING},
+                             "sample": "full ring of %d GEMVs per step; C restatement of ggml_compute_forward_mul_mat_q_f32 (not .NET RyuJIT)" % len(nodes)},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -158,7 +158,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "fused"])
+    ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
+    ap.add_argument("--epilogue-stores", action="store_true", help="fused gather through per-row peer stores in the GEMV epilogue instead of the push kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -201,15 +202,38 @@ def main():
         N.check(L.ggb_dev_quantize_rows(Q4_0, wf.data_ptr(), Wq[i].data_ptr(), M_LOCAL, K, sptr))
     xgen = torch.Generator(device=dev); xgen.manual_seed(2001)     # same activations on every rank (replicated)
     X = torch.randn((RING, K), generator=xgen, device=dev, dtype=torch.float32)
-    Y = torch.zeros((world, RING, M_LOCAL), dtype=torch.float32, device=dev)     # all-gather layout [rank][node][rows]
-    Yloc = Y[rank]
+    gather = args.gather if world > 1 else "none"
+    sym = None
     mms = (N.ggb_dev_mm * RING)()
+    if gather == "fused":
+        # every rank holds the FULL dst of every node, [node][rows_total]; the GEMV epilogue stores this rank's rows into all
+        # copies through CUDA-IPC mapped peer pointers, then one flag barrier over NVLink closes the step
+        from ggmlsharp_b200 import rowsplit
+
+        def ago(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        sym = rowsplit.SymmetricBuffer(RING * M_total * 4, rank, world, ago)
+        Y = None
+    else:
+        Y = torch.zeros((world, RING, M_LOCAL), dtype=torch.float32, device=dev)     # all-gather layout [rank][node][rows]
+        Yloc = Y[rank]
     for i in range(RING):
         m = mms[i]
         m.type, m.M, m.K, m.N = Q4_0, M_LOCAL, K, 1
         m.W, m.nb01 = Wq[i].data_ptr(), rb
         m.X, m.ldx_bytes = X[i].data_ptr(), 4 * K
-        m.Y, m.ldy_bytes = Yloc[i].data_ptr(), 4 * M_LOCAL
+        if sym is not None:
+            off = (i * M_total + rank * M_LOCAL) * 4
+            m.Y, m.ldy_bytes = sym.payload() + off, 4 * M_total
+            if args.epilogue_stores:                      # variant: the GEMV epilogue itself stores into every peer (4-byte NVLink writes)
+                peers = [r for r in range(world) if r != rank]
+                m.n_peers = len(peers)
+                for j, r in enumerate(peers):
+                    m.Y_peer[j] = sym.payload(r) + off
+        else:
+            m.Y, m.ldy_bytes = Yloc[i].data_ptr(), 4 * M_LOCAL
     wsb = L.ggb_dev_workspace_bytes(mms, RING)
     ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
     wsp = (ws.data_ptr() + 255) // 256 * 256
@@ -217,7 +241,12 @@ def main():
 
     def step():
         N.check(L.ggb_dev_mul_mat_batch(mms, RING, wsp, wsb, sptr))
-        if world > 1:
+        if gather == "fused":
+            if args.epilogue_stores:
+                sym.barrier(sptr)
+            else:                                          # one kernel: coalesced push of this rank's blocks to all peers + flag barrier
+                sym.push_barrier(sptr, rank * M_LOCAL * 4, M_LOCAL * 4, M_total * 4, RING)
+        elif gather == "nccl":
             dist.all_gather_into_tensor(Y.view(-1), Yloc.reshape(-1))
 
     def barrier():
@@ -242,9 +271,14 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(N.stats().kernel_launches)
-    # extra untimed steps under the sampler so short runs still see clocks under load
-    t_end = time.perf_counter() + 0.6
-    while time.perf_counter() < t_end:
+    # extra untimed steps under the sampler so short runs still see clocks under load; the SAME count on every rank
+    # (each step ends in a collective / flag barrier)
+    n_extra = int(min(20000, max(10, 0.6 / max(ms / args.steps * 1e-3, 1e-6))))
+    if world > 1:
+        t = torch.tensor([n_extra], device=dev, dtype=torch.int64)
+        dist.broadcast(t, 0)
+        n_extra = int(t.item())
+    for _ in range(n_extra):
         step()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
@@ -256,31 +290,31 @@ def main():
     step_bytes_rank = RING * alg_bytes_per_node(M_LOCAL, K)
     value = world * step_bytes_rank / (ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (the persistent GEMV), timed alone with events around each launch ----
-    # activations are already staged in the workspace by the previous step; relaunching the batch re-runs both
-    # kernels, so the act kernel (4.7 KB out per node) is timed separately and subtracted.
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
-    one = (N.ggb_dev_mm * 1)()
-    torch.cuda.synchronize()
-    for a, b in ev:
-        a.record(stream)
+    # ---- the fused exchange must leave the same bytes everywhere as a plain all-gather of the per-rank blocks ----
+    if gather == "fused":
+        mine = np.zeros((RING, M_total), dtype=np.float32)
+        N.check(L.ggb_stream_sync(sptr))
+        N.check(L.ggb_dev_download(mine.ctypes.data, sym.payload(), mine.nbytes))
+        loc = torch.from_numpy(mine[:, rank * M_LOCAL:(rank + 1) * M_LOCAL].copy()).to(dev)
+        allb = torch.zeros((world, RING, M_LOCAL), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allb.view(-1), loc.reshape(-1))
+        want = allb.permute(1, 0, 2).reshape(RING, M_total).cpu().numpy()
+        assert np.array_equal(mine, want), "fused row-split exchange differs from the all-gather of the per-rank blocks"
+
+    # ---- roofline of the dominant kernel (the persistent GEMV): CUDA events around each GEMV launch, inside the library,
+    #      on the launching stream (ggb_set_kernel_timing).  The brackets disable the PDL overlap, so this is a separate pass.
+    L.ggb_reset_stats()
+    N.check(L.ggb_set_kernel_timing(1))
+    n_prof = min(args.steps, 50)
+    for _ in range(n_prof):
         N.check(L.ggb_dev_mul_mat_batch(mms, RING, wsp, wsb, sptr))
-        b.record(stream)
     torch.cuda.synchronize()
-    batch_ms = sorted(a.elapsed_time(b) for a, b in ev)
-    batch_ms = sum(batch_ms) / len(batch_ms)
-    # activation kernel alone: quantize RING rows of K floats with the reference-layout Q8_0 kernel (same work shape)
-    q8 = torch.empty((RING, K // 32 * 36), dtype=torch.uint8, device=dev)
-    for a, b in ev:
-        a.record(stream)
-        N.check(L.ggb_dev_quantize_rows(8, X.data_ptr(), q8.data_ptr(), RING, K, sptr))
-        b.record(stream)
-    torch.cuda.synchronize()
-    act_ms = sum(a.elapsed_time(b) for a, b in ev) / len(ev)
-    gemv_ms = max(batch_ms - act_ms, 1e-6)
+    st = N.stats()
+    N.check(L.ggb_set_kernel_timing(0))
+    gemv_ms = st.timed_kernel_ms / max(st.timed_kernel_launches, 1)
     peak, peak_src = load_peaks()
     achieved = step_bytes_rank / (gemv_ms * 1e-3) / 1e9
-
+    batch_ms, act_ms = None, None
     line = {"metric": "Q4_0 mul_mat HBM GB/s (% roofline)", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 dot (Q4_0 x Q8_0), f32 scales", "data": "synthetic",
@@ -289,45 +323,46 @@ def main():
                        "rows_per_rank": M_LOCAL, "rows_total": M_total, "k": K,
                        "parallelism": "row-split x%d + all-gather (%s)" % (world, args.gather) if world > 1 else "1 GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "k_gemv<Q4_0,1>", "launch_ms": gemv_ms, "peak_source": peak_src,
-                         "frac_of_nominal_8TBs": achieved / 8000.0, "batch_ms": batch_ms, "act_ms": act_ms},
+                         "kernel": "k_gemv_fast<Q4_0,1,xreg>", "launch_ms": gemv_ms, "launches_timed": int(st.timed_kernel_launches), "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": step_bytes_rank},
             "gpu_launches": launches, "clocks": clocks}
 
+    # ---- e2e: reference-shaped API over a host arena (weights cached on device after the first compute).  Every rank runs
+    #      ggml_graph_compute over its own row slice (activations host->device, this rank's dst block device->host each step);
+    #      the time is the max over ranks, the bytes are all ranks'. ----
+    arena = RING * (M_LOCAL * rb + 4 * K + 4 * M_LOCAL + 3 * 256) + (8 << 20)
+    wq_host = Wq.cpu().numpy()
+    x_host = X.cpu().numpy()
+    with ggml.Context(arena) as c:
+        ys, g = [], None
+        for i in range(RING):
+            a = c.tensor_from(N.Q4_0, K, M_LOCAL, data=wq_host[i])
+            b = c.tensor_from(N.F32, K, data=x_host[i])
+            y = c.mul_mat(a, b)
+            ys.append(y)
+            if g is None:
+                g = c.build_forward(y)
+            else:
+                N.host().ggml_build_forward_expand(C.byref(g), y)
+        for _ in range(3):
+            c.graph_compute(g)
+        L.ggb_reset_stats()
+        n_e2e = max(10, min(args.steps, 100))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            c.graph_compute(g)
+        dt = (time.perf_counter() - t0) / n_e2e
+        s_e2e = N.stats()
+        y0 = ggml.tensor_f32(ys[0]).reshape(-1).copy()
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": world * step_bytes_rank / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
+           "h2d_bytes_per_step": int(s_e2e.h2d_bytes // n_e2e) * world, "d2h_bytes_per_step": int(s_e2e.d2h_bytes // n_e2e) * world,
+           "api": "ggml_graph_compute over a %d-node graph per rank (host arena, weights device-cached)%s" % (RING, "; each rank reads back its own dst block" if world > 1 else "")}
     if rank == 0:
-        # ---- e2e: reference-shaped API over a host arena (weights cached on device after the first compute) ----
-        e2e = None
-        if world == 1:
-            arena = RING * (M_LOCAL * rb + 4 * K + 4 * M_LOCAL + 3 * 256) + (8 << 20)
-            wq_host = Wq.cpu().numpy()
-            x_host = X.cpu().numpy()
-            with ggml.Context(arena) as c:
-                ys = []
-                g = None
-                for i in range(RING):
-                    a = c.tensor_from(N.Q4_0, K, M_LOCAL, data=wq_host[i])
-                    b = c.tensor_from(N.F32, K, data=x_host[i])
-                    y = c.mul_mat(a, b)
-                    ys.append(y)
-                    if g is None:
-                        g = c.build_forward(y)
-                    else:
-                        N.host().ggml_build_forward_expand(C.byref(g), y)
-                for _ in range(3):
-                    c.graph_compute(g)
-                L.ggb_reset_stats()
-                n_e2e = max(10, min(args.steps, 100))
-                t0 = time.perf_counter()
-                for _ in range(n_e2e):
-                    c.graph_compute(g)
-                dt = (time.perf_counter() - t0) / n_e2e
-                s = N.stats()
-                # check the API path against the device-resident path on node 0
-                y0 = ggml.tensor_f32(ys[0]).reshape(-1)
-                ref0 = Y[0, 0].cpu().numpy()
-                assert np.array_equal(y0, ref0), "e2e result differs from the device-resident result"
-                e2e = {"value": step_bytes_rank / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
-                       "h2d_bytes_per_step": int(s.h2d_bytes // n_e2e), "d2h_bytes_per_step": int(s.d2h_bytes // n_e2e),
-                       "api": "ggml_graph_compute over a %d-node graph (host arena; weights device-cached)" % RING}
         line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
             nth = os.cpu_count() or 1
@@ -336,6 +371,9 @@ def main():
             line["cpu_baseline"] = {"value": 8 * alg_bytes_per_node(M_LOCAL, K) / sec / 1e9, "unit": "GB/s", "cores": nth, "kind": "port",
                                     "sample": "8 of the %d ring GEMVs, best of <=5 passes; C restatement of the reference algorithm (not .NET RyuJIT)" % RING}
         print(json.dumps(line), flush=True)
+    if sym is not None:
+        barrier()
+        sym.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -23,6 +23,8 @@ static int g_device = 0, g_sms = 148;
 static cudaStream_t g_stream = nullptr;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static ggb_stats g_stats = {};
+static bool g_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timed;   // pending event pairs, resolved in ggb_get_stats
 
 int set_error(int code, const char *fmt, ...)
 {
@@ -32,6 +34,15 @@ int set_error(int code, const char *fmt, ...)
     return code;
 }
 void count_launch(int n) { g_stats.kernel_launches += (uint64_t)n; }
+struct KernelTimer {            // RAII bracket around one mul_mat kernel launch
+    cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
+    explicit KernelTimer(cudaStream_t st) : s(st) {
+        if (!g_timing || g_timed.size() >= 4096) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+        cudaEventRecord(a, s);
+    }
+    ~KernelTimer() { if (a) { cudaEventRecord(b, s); g_timed.emplace_back(a, b); } }
+};
 int device_sm_count() { return g_sms; }
 
 static int ensure_init()
@@ -128,7 +139,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
         for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
         if (const char *tr = getenv("GGB200_GEMM_TRACE")) a.trace = reinterpret_cast<void *>(strtoull(tr, nullptr, 0));   // debugging: device pointer
-        rc = launch_gemm(a, wsb + off[i] + align_up((size_t)Npad * m.K * 2, 256), s);
+        { KernelTimer kt(s); rc = launch_gemm(a, wsb + off[i] + align_up((size_t)Npad * m.K * 2, 256), s); }
         if (rc) return rc;
     }
 
@@ -200,7 +211,8 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
             };
             auto flush = [&]() -> int {
                 if (!gb.n_nodes) return GGB_OK;
-                int r = launch_gemv_batch(gb, s, first_launch);
+                int r;
+                { KernelTimer kt(s); r = launch_gemv_batch(gb, s, first_launch); }
                 first_launch = false;
                 gb.n_nodes = 0; gb.total_groups = 0;
                 return r;
@@ -741,7 +753,124 @@ int ggb_ipc_open(const uint8_t handle[64], void **peer)
 }
 int ggb_ipc_close(void *peer) { GGB_CUDA(cudaIpcCloseMemHandle(peer)); return GGB_OK; }
 
-int ggb_get_stats(ggb_stats *out) { if (!out) return set_error(GGB_E_INVALID, "null"); *out = g_stats; return GGB_OK; }
-int ggb_reset_stats(void) { g_stats = ggb_stats{}; return GGB_OK; }
+namespace ggb {
+struct PeerFlags { uint64_t *p[8]; };
+__global__ void k_peer_barrier(PeerFlags f, int rank, int world, unsigned long long epoch)
+{
+    const int t = threadIdx.x;
+    if (t < world) {
+        __threadfence_system();                                   // this rank's earlier peer stores (previous kernels) are ordered before the flag
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.p[t] + rank), "l"(epoch) : "memory");
+        unsigned long long v;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f.p[rank] + t) : "memory");
+            if (v < epoch && clock64() - t0 > 20000000000ll) __trap();      // ~10 s: a peer died; fail the launch instead of hanging the GPU
+        } while (v < epoch);
+    }
+}
+} // namespace ggb
+
+namespace ggb {
+struct PeerBases { uint8_t *p[8]; };
+__global__ void __launch_bounds__(256) k_peer_push_barrier(PeerBases b, PeerFlags f, uint32_t *counter, int rank, int world,
+                                                           unsigned long long seg_offset, unsigned long long seg_bytes, unsigned long long seg_stride,
+                                                           int n_seg, unsigned long long epoch)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // the producing kernel's stores to the local segments are complete
+    const unsigned long long vec_per_seg = seg_bytes >> 4, total = vec_per_seg * (unsigned long long)n_seg;
+    const uint8_t *src = b.p[rank];
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long sgi = i / vec_per_seg, v = i - sgi * vec_per_seg;
+        const unsigned long long off = seg_offset + sgi * seg_stride + (v << 4);
+        const uint4 val = *reinterpret_cast<const uint4 *>(src + off);
+        for (int p = 0; p < world; p++)
+            if (p != rank) *reinterpret_cast<uint4 *>(b.p[p] + off) = val;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *counter = 0;
+    const int t = threadIdx.x;
+    if (t < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.p[t] + rank), "l"(epoch) : "memory");
+        unsigned long long v;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f.p[rank] + t) : "memory");
+            if (v < epoch && clock64() - t0 > 20000000000ll) __trap();
+        } while (v < epoch);
+    }
+}
+} // namespace ggb
+
+int ggb_peer_push_barrier(void *const *peer_bases, uint64_t *const *peer_flags, uint32_t *counter, int rank, int world,
+                          size_t seg_offset, size_t seg_bytes, size_t seg_stride, int n_seg, uint64_t epoch, void *stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!peer_bases || !peer_flags || !counter || world < 1 || world > 8 || rank < 0 || rank >= world || n_seg < 0)
+        return set_error(GGB_E_INVALID, "ggb_peer_push_barrier: bad arguments");
+    if ((seg_offset | seg_bytes | seg_stride) & 15) return set_error(GGB_E_INVALID, "ggb_peer_push_barrier: segments must be 16-byte multiples");
+    PeerBases b = {}; PeerFlags f = {};
+    for (int i = 0; i < world; i++) {
+        if (!peer_bases[i] || !peer_flags[i]) return set_error(GGB_E_INVALID, "ggb_peer_push_barrier: null pointer for rank %d", i);
+        b.p[i] = static_cast<uint8_t *>(peer_bases[i]); f.p[i] = peer_flags[i];
+    }
+    const unsigned long long total = (unsigned long long)(seg_bytes >> 4) * (unsigned long long)n_seg;
+    unsigned grid = (unsigned)std::min<unsigned long long>(64, std::max<unsigned long long>(1, (total + 1023) / 1024));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256);
+    cfg.stream = stream ? static_cast<cudaStream_t>(stream) : g_stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_peer_push_barrier, b, f, counter, rank, world, (unsigned long long)seg_offset, (unsigned long long)seg_bytes,
+                                (unsigned long long)seg_stride, n_seg, (unsigned long long)epoch));
+    count_launch();
+    return GGB_OK;
+}
+
+int ggb_peer_barrier(uint64_t *const *peer_flags, int rank, int world, uint64_t epoch, void *stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!peer_flags || world < 1 || world > 8 || rank < 0 || rank >= world) return set_error(GGB_E_INVALID, "ggb_peer_barrier: bad arguments");
+    PeerFlags f = {};
+    for (int i = 0; i < world; i++) { if (!peer_flags[i]) return set_error(GGB_E_INVALID, "ggb_peer_barrier: null flags pointer for rank %d", i); f.p[i] = peer_flags[i]; }
+    k_peer_barrier<<<1, 32, 0, stream ? static_cast<cudaStream_t>(stream) : g_stream>>>(f, rank, world, (unsigned long long)epoch);
+    count_launch();
+    GGB_CUDA(cudaGetLastError());
+    return GGB_OK;
+}
+
+int ggb_set_kernel_timing(int on) { g_timing = on != 0; return GGB_OK; }
+int ggb_get_stats(ggb_stats *out)
+{
+    if (!out) return set_error(GGB_E_INVALID, "null");
+    for (auto &pr : g_timed) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            g_stats.timed_kernel_ms += ms; g_stats.timed_kernel_launches++;
+        }
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    g_timed.clear();
+    cudaGetLastError();
+    *out = g_stats;
+    return GGB_OK;
+}
+int ggb_reset_stats(void)
+{
+    for (auto &pr : g_timed) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    g_timed.clear();
+    g_stats = ggb_stats{};
+    return GGB_OK;
+}
 
 } // extern "C"

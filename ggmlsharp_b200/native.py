@@ -70,7 +70,7 @@ class ggb_dev_mm(C.Structure):
 class ggb_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("weight_uploads", C.c_uint64), ("weight_cache_hits", C.c_uint64), ("nodes_executed", C.c_uint64),
-                ("last_graph_device_ms", C.c_double)]
+                ("last_graph_device_ms", C.c_double), ("timed_kernel_ms", C.c_double), ("timed_kernel_launches", C.c_uint64)]
 
 
 assert C.sizeof(ggml_tensor) == 176 and ggml_tensor.data.offset == 160
@@ -107,8 +107,11 @@ GGB_SYMBOLS = {
     "ggb_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ggb_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "ggb_ipc_close": (C.c_int, [C.c_void_p]),
+    "ggb_peer_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint64, C.c_void_p]),
+    "ggb_peer_push_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_uint64, C.c_void_p]),
     "ggb_get_stats": (C.c_int, [C.POINTER(ggb_stats)]),
     "ggb_reset_stats": (C.c_int, []),
+    "ggb_set_kernel_timing": (C.c_int, [C.c_int]),
 }
 
 HOST_SYMBOLS = {

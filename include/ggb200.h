@@ -198,6 +198,20 @@ int  ggb_stream_sync(void *stream);
 int  ggb_ipc_export(void *dptr, uint8_t handle[64]);
 int  ggb_ipc_open(const uint8_t handle[64], void **peer_dptr);
 int  ggb_ipc_close(void *peer_dptr);
+/* The exchange step of the fused row split.  Every rank owns `flags` (world x uint64, zero-initialised, inside an
+ * IPC-exported allocation); peer_flags[r] is rank r's array mapped here (peer_flags[rank] = own).  Enqueues one tiny
+ * kernel that publishes `epoch` into slot `rank` of every rank's array with system-scope release stores over NVLink
+ * and then waits until all `world` local slots hold >= epoch: when it completes, every peer's Y_peer stores that were
+ * enqueued before its own barrier call are visible in this rank's buffer.  epoch must increase by 1 per call. */
+int  ggb_peer_barrier(uint64_t *const *peer_flags, int rank, int world, uint64_t epoch, void *stream);
+/* The row-split exchange as ONE kernel over peer memory (no NCCL): copies this rank's n_seg segments
+ * [seg_offset + s*seg_stride, +seg_bytes) of its symmetric buffer into the same place of every peer's buffer with
+ * coalesced 16-byte stores over NVLink, then -- last CTA -- runs the flag barrier above.  peer_bases[r] is rank r's buffer
+ * mapped here (own for r == rank), `counter` a zero-initialised uint32 in local device memory.  seg_offset, seg_bytes and
+ * seg_stride must be multiples of 16.  Launched with programmatic dependent launch: it waits for the preceding kernel
+ * (the GEMV that produced the segments) on the device, not on the host. */
+int  ggb_peer_push_barrier(void *const *peer_bases, uint64_t *const *peer_flags, uint32_t *counter, int rank, int world,
+                           size_t seg_offset, size_t seg_bytes, size_t seg_stride, int n_seg, uint64_t epoch, void *stream);
 
 /* ---- counters -------------------------------------------------------------------------- */
 
@@ -207,7 +221,12 @@ typedef struct ggb_stats {
     uint64_t weight_uploads, weight_cache_hits;
     uint64_t nodes_executed;
     double   last_graph_device_ms; /* CUDA-event time of the last ggb_graph_compute_mul_mats / ggb_mul_mat_node */
+    double   timed_kernel_ms;      /* with ggb_set_kernel_timing(1): summed CUDA-event time of the GEMV / GEMM launches only */
+    uint64_t timed_kernel_launches;
 } ggb_stats;
+/* Measurement aid for the roofline: bracket every mul_mat kernel launch (not the activation staging) with CUDA events on
+ * the launching stream.  The brackets defeat the programmatic-dependent-launch overlap, so leave it off when timing steps. */
+int  ggb_set_kernel_timing(int on);
 int  ggb_get_stats(ggb_stats *out);
 int  ggb_reset_stats(void);
 
