@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a captured CUDA graph")
     ap.add_argument("--epilogue-stores", action="store_true", help="fused gather through per-row peer stores in the GEMV epilogue instead of the push kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -204,50 +205,99 @@ def main():
     X = torch.randn((RING, K), generator=xgen, device=dev, dtype=torch.float32)
     gather = args.gather if world > 1 else "none"
     sym = None
-    mms = (N.ggb_dev_mm * RING)()
+    NBUF = 2 if gather == "fused" and not args.epilogue_stores else 1
+    mm_bufs = [(N.ggb_dev_mm * RING)() for _ in range(NBUF)]
     if gather == "fused":
-        # every rank holds the FULL dst of every node, [node][rows_total]; the GEMV epilogue stores this rank's rows into all
-        # copies through CUDA-IPC mapped peer pointers, then one flag barrier over NVLink closes the step
+        # every rank holds the FULL dst of every node, [node][rows_total] (x2: double buffered).  The exchange is one kernel
+        # over CUDA-IPC mapped peer memory: coalesced push of this rank's blocks into every peer's copy + a flag barrier.
+        # It runs on a second stream, so the exchange of step i overlaps the GEMVs of step i+1 (the nodes of consecutive
+        # steps are independent); the timed region ends only when every step's exchange has completed.
         from ggmlsharp_b200 import rowsplit
 
         def ago(obj):
             out = [None] * world
             dist.all_gather_object(out, obj)
             return out
-        sym = rowsplit.SymmetricBuffer(RING * M_total * 4, rank, world, ago)
+        sym = rowsplit.SymmetricBuffer(NBUF * RING * M_total * 4, rank, world, ago)
         Y = None
     else:
         Y = torch.zeros((world, RING, M_LOCAL), dtype=torch.float32, device=dev)     # all-gather layout [rank][node][rows]
         Yloc = Y[rank]
-    for i in range(RING):
-        m = mms[i]
-        m.type, m.M, m.K, m.N = Q4_0, M_LOCAL, K, 1
-        m.W, m.nb01 = Wq[i].data_ptr(), rb
-        m.X, m.ldx_bytes = X[i].data_ptr(), 4 * K
-        if sym is not None:
-            off = (i * M_total + rank * M_LOCAL) * 4
-            m.Y, m.ldy_bytes = sym.payload() + off, 4 * M_total
-            if args.epilogue_stores:                      # variant: the GEMV epilogue itself stores into every peer (4-byte NVLink writes)
-                peers = [r for r in range(world) if r != rank]
-                m.n_peers = len(peers)
-                for j, r in enumerate(peers):
-                    m.Y_peer[j] = sym.payload(r) + off
-        else:
-            m.Y, m.ldy_bytes = Yloc[i].data_ptr(), 4 * M_LOCAL
+    for bsel in range(NBUF):
+        for i in range(RING):
+            m = mm_bufs[bsel][i]
+            m.type, m.M, m.K, m.N = Q4_0, M_LOCAL, K, 1
+            m.W, m.nb01 = Wq[i].data_ptr(), rb
+            m.X, m.ldx_bytes = X[i].data_ptr(), 4 * K
+            if sym is not None:
+                off = ((bsel * RING + i) * M_total + rank * M_LOCAL) * 4
+                m.Y, m.ldy_bytes = sym.payload() + off, 4 * M_total
+                if args.epilogue_stores:                      # variant: the GEMV epilogue itself stores into every peer (4-byte NVLink writes)
+                    peers = [r for r in range(world) if r != rank]
+                    m.n_peers = len(peers)
+                    for j, r in enumerate(peers):
+                        m.Y_peer[j] = sym.payload(r) + off
+            else:
+                m.Y, m.ldy_bytes = Yloc[i].data_ptr(), 4 * M_LOCAL
+    mms = mm_bufs[0]
     wsb = L.ggb_dev_workspace_bytes(mms, RING)
-    ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+    ws = torch.empty(NBUF * wsb + 256, dtype=torch.uint8, device=dev)
     wsp = (ws.data_ptr() + 255) // 256 * 256
+    comm = torch.cuda.Stream(device=dev) if NBUF == 2 else None
+    cptr = C.c_void_p(comm.cuda_stream) if comm is not None else None
+    ev_compute = [torch.cuda.Event() for _ in range(NBUF)]
+    ev_comm = [torch.cuda.Event() for _ in range(NBUF)]
+    step_no = [0]
     torch.cuda.synchronize()
 
+    def step_body(b, evc=None, evm=None, wait=True):
+        # one step on buffer b: GEMVs on the compute stream, exchange on the comm stream (overlaps the next step's GEMVs)
+        evc = evc or ev_compute
+        evm = evm or ev_comm
+        if wait:
+            stream.wait_event(evm[b])                       # the exchange that last read / filled buffer b is done
+        N.check(L.ggb_dev_mul_mat_batch(mm_bufs[b], RING, wsp + b * wsb, wsb, sptr))
+        evc[b].record(stream)
+        comm.wait_event(evc[b])
+        sym.push_barrier(cptr, (b * RING * M_total + rank * M_LOCAL) * 4, M_LOCAL * 4, M_total * 4, RING)
+        evm[b].record(comm)
+
     def step():
+        if gather == "fused" and NBUF == 2:
+            b = step_no[0] & 1
+            step_no[0] += 1
+            step_body(b)
+            return
         N.check(L.ggb_dev_mul_mat_batch(mms, RING, wsp, wsb, sptr))
         if gather == "fused":
-            if args.epilogue_stores:
-                sym.barrier(sptr)
-            else:                                          # one kernel: coalesced push of this rank's blocks to all peers + flag barrier
-                sym.push_barrier(sptr, rank * M_LOCAL * 4, M_LOCAL * 4, M_total * 4, RING)
+            sym.barrier(sptr)
         elif gather == "nccl":
             dist.all_gather_into_tensor(Y.view(-1), Yloc.reshape(-1))
+
+    # Host launch cost (2 kernels + exchange + 4 event ops per step from Python) is comparable to the 57 us of GPU work, so
+    # GSTEPS steps are captured once into a CUDA graph (both streams) and replayed; the flag-barrier epoch lives in device memory.
+    GSTEPS = 8
+    graph = None
+
+    def build_graph():
+        g = torch.cuda.CUDAGraph()
+        gc, gm = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]      # events that live inside the capture
+        with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
+            for j in range(GSTEPS):
+                # replays serialise on the stream, so the first use of each buffer in a replay has nothing to wait for
+                step_body(j & 1, gc, gm, wait=j >= 2)
+            for e in gm:
+                stream.wait_event(e)                        # join the comm stream back before the capture ends
+        return g
+
+    def run_steps(n):
+        """exactly n steps"""
+        if graph is not None:
+            for _ in range(n // GSTEPS):
+                graph.replay()
+            n = n % GSTEPS
+        for _ in range(n):
+            step()
 
     def barrier():
         if world > 1:
@@ -257,6 +307,13 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    if gather == "fused" and NBUF == 2 and not args.no_graph:
+        if step_no[0] & 1:
+            step()                                          # graphs start on buffer 0
+        torch.cuda.synchronize()
+        graph = build_graph()
+        graph.replay()
+        barrier()
     L.ggb_reset_stats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -265,12 +322,16 @@ def main():
     # keep the timed region long enough for nvidia-smi to sample it (>= ~0.5 s), but time EXACTLY --steps steps
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
-        step()
+    run_steps(args.steps)
+    if comm is not None:
+        for e in ev_comm:
+            stream.wait_event(e)                            # every step's exchange is inside the timed region
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(N.stats().kernel_launches)
+    if graph is not None:
+        launches += (args.steps // GSTEPS) * GSTEPS * 3      # replayed steps: act + GEMV + exchange kernels each
     # extra untimed steps under the sampler so short runs still see clocks under load; the SAME count on every rank
     # (each step ends in a collective / flag barrier)
     n_extra = int(min(20000, max(10, 0.6 / max(ms / args.steps * 1e-3, 1e-6))))
@@ -278,8 +339,7 @@ def main():
         t = torch.tensor([n_extra], device=dev, dtype=torch.int64)
         dist.broadcast(t, 0)
         n_extra = int(t.item())
-    for _ in range(n_extra):
-        step()
+    run_steps(n_extra)
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -294,7 +354,8 @@ def main():
     if gather == "fused":
         mine = np.zeros((RING, M_total), dtype=np.float32)
         N.check(L.ggb_stream_sync(sptr))
-        N.check(L.ggb_dev_download(mine.ctypes.data, sym.payload(), mine.nbytes))
+        lastb = (step_no[0] - 1) & 1 if NBUF == 2 else 0
+        N.check(L.ggb_dev_download(mine.ctypes.data, sym.payload() + lastb * RING * M_total * 4, mine.nbytes))
         loc = torch.from_numpy(mine[:, rank * M_LOCAL:(rank + 1) * M_LOCAL].copy()).to(dev)
         allb = torch.zeros((world, RING, M_LOCAL), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(allb.view(-1), loc.reshape(-1))

@@ -787,13 +787,20 @@ __global__ void __launch_bounds__(256) k_peer_push_barrier(PeerBases b, PeerFlag
         for (int p = 0; p < world; p++)
             if (p != rank) *reinterpret_cast<uint4 *>(b.p[p] + off) = val;
     }
-    __threadfence_system();
     __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) { __threadfence_system(); last = atomicAdd(counter, 1u) == gridDim.x - 1; }   // cumulative fence after the CTA barrier
     __syncthreads();
     if (!last) return;
-    if (threadIdx.x == 0) *counter = 0;
+    __shared__ unsigned long long ep;
+    if (threadIdx.x == 0) {
+        *counter = 0;
+        // epoch == 0: take the next epoch from device memory (counter + 8 bytes), so a captured CUDA graph can be replayed
+        unsigned long long *dev_epoch = reinterpret_cast<unsigned long long *>(counter + 2);
+        ep = epoch ? epoch : ++(*dev_epoch);
+    }
+    __syncthreads();
+    epoch = ep;
     const int t = threadIdx.x;
     if (t < world) {
         __threadfence_system();

@@ -59,6 +59,7 @@ class SymmetricBuffer:
             self.peer_base.append(q.value)
         self._flags = (C.c_void_p * world)(*[C.c_void_p(b) for b in self.peer_base])
         self.epoch = 0
+        self._payloads = None
 
     def payload(self, r=None):
         return (self.base if r is None else self.peer_base[r]) + self.FLAG_BYTES
@@ -68,11 +69,13 @@ class SymmetricBuffer:
         self.N.check(self.N.lib().ggb_peer_barrier(self._flags, self.rank, self.world, self.epoch, stream))
 
     def push_barrier(self, stream, seg_offset, seg_bytes, seg_stride, n_seg):
-        """Copy this rank's segments of the payload into every peer's payload and close the step with the flag barrier."""
-        self.epoch += 1
-        payloads = (C.c_void_p * self.world)(*[C.c_void_p(b + self.FLAG_BYTES) for b in self.peer_base])
-        self.N.check(self.N.lib().ggb_peer_push_barrier(payloads, self._flags, self.base + 128, self.rank, self.world,
-                                                        seg_offset, seg_bytes, seg_stride, n_seg, self.epoch, stream))
+        """Copy this rank's segments of the payload into every peer's payload and close the step with the flag barrier.
+        The epoch lives in device memory (epoch argument 0), so the call can sit inside a replayed CUDA graph; do not mix
+        with barrier() on the same buffer."""
+        if self._payloads is None:
+            self._payloads = (C.c_void_p * self.world)(*[C.c_void_p(b + self.FLAG_BYTES) for b in self.peer_base])
+        self.N.check(self.N.lib().ggb_peer_push_barrier(self._payloads, self._flags, self.base + 128, self.rank, self.world,
+                                                        seg_offset, seg_bytes, seg_stride, n_seg, 0, stream))
 
     def close(self):
         L = self.N.lib()

@@ -207,7 +207,8 @@ int  ggb_peer_barrier(uint64_t *const *peer_flags, int rank, int world, uint64_t
 /* The row-split exchange as ONE kernel over peer memory (no NCCL): copies this rank's n_seg segments
  * [seg_offset + s*seg_stride, +seg_bytes) of its symmetric buffer into the same place of every peer's buffer with
  * coalesced 16-byte stores over NVLink, then -- last CTA -- runs the flag barrier above.  peer_bases[r] is rank r's buffer
- * mapped here (own for r == rank), `counter` a zero-initialised uint32 in local device memory.  seg_offset, seg_bytes and
+ * mapped here (own for r == rank), `counter` 16 zero-initialised bytes of local device memory (CTA counter; a uint64
+ * running epoch at +8 that is used when `epoch` is passed as 0, which makes the call CUDA-graph replayable).  seg_offset, seg_bytes and
  * seg_stride must be multiples of 16.  Launched with programmatic dependent launch: it waits for the preceding kernel
  * (the GEMV that produced the segments) on the device, not on the host. */
 int  ggb_peer_push_barrier(void *const *peer_bases, uint64_t *const *peer_flags, uint32_t *counter, int rank, int world,
