@@ -375,7 +375,12 @@ def main():
     gemv_ms = st.timed_kernel_ms / max(st.timed_kernel_launches, 1)
     peak, peak_src = load_peaks()
     achieved = step_bytes_rank / (gemv_ms * 1e-3) / 1e9
-    batch_ms, act_ms = None, None
+    traffic = None                                          # DRAM bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)["k_gemv_fast"]
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     line = {"metric": "Q4_0 mul_mat HBM GB/s (% roofline)", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 dot (Q4_0 x Q8_0), f32 scales", "data": "synthetic",
@@ -383,7 +388,7 @@ def main():
                        "step": "%d independent MUL_MAT nodes (distinct weights, %.1f MB > 2x L2, no flush needed), 1 act + 1 GEMV launch" % (RING, RING * M_LOCAL * rb / 1e6),
                        "rows_per_rank": M_LOCAL, "rows_total": M_total, "k": K,
                        "parallelism": "row-split x%d + all-gather (%s)" % (world, args.gather) if world > 1 else "1 GPU"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_gemv_fast<Q4_0,1,xreg>", "launch_ms": gemv_ms, "launches_timed": int(st.timed_kernel_launches), "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0, "bytes_per_launch": step_bytes_rank},
             "gpu_launches": launches, "clocks": clocks}
