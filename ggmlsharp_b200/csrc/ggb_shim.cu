@@ -242,6 +242,33 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
 // pool + executor
 // ------------------------------------------------------------------------------------------------
 
+// Small results go back to the pinned host arena through ONE kernel (coalesced 16-byte stores over PCIe to
+// UVA-mapped memory) instead of one cudaMemcpyAsync per node; small activations are read by the activation
+// kernel straight from the arena the same way.  Large tensors still use the copy engine.
+constexpr size_t ZC_MAX = 64 * 1024;
+struct CopySeg { const uint8_t *src; uint8_t *dst; unsigned bytes; unsigned vec0; };     // vec0: first 16-byte vector index of this segment
+struct CopyBatch { int n; unsigned total_vec; CopySeg seg[96]; };
+__global__ void __launch_bounds__(256) k_copy_batch(const __grid_constant__ CopyBatch b)
+{
+    for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < b.total_vec; v += gridDim.x * blockDim.x) {
+        int sgi = 0;
+        while (sgi + 1 < b.n && v >= b.seg[sgi + 1].vec0) sgi++;
+        const CopySeg &sg = b.seg[sgi];
+        const unsigned off = (v - sg.vec0) * 16;
+        if (off + 16 <= sg.bytes) *reinterpret_cast<uint4 *>(sg.dst + off) = *reinterpret_cast<const uint4 *>(sg.src + off);
+        else for (unsigned i = off; i < sg.bytes; i += 4) *reinterpret_cast<uint32_t *>(sg.dst + i) = *reinterpret_cast<const uint32_t *>(sg.src + i);
+    }
+}
+static int flush_copy_batch(CopyBatch &cb, cudaStream_t s)
+{
+    if (!cb.n) return GGB_OK;
+    k_copy_batch<<<std::min(64u, (cb.total_vec + 255) / 256), 256, 0, s>>>(cb);
+    count_launch();
+    GGB_CUDA(cudaGetLastError());
+    cb.n = 0; cb.total_vec = 0;
+    return GGB_OK;
+}
+
 struct Mirror { void *dptr; size_t bytes; };
 
 struct DevArena {           // grow-only device scratch, reset per compute
@@ -412,8 +439,12 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                 it.level = std::max(it.level, pr->level + 1);
             } else {
                 const size_t span = tensor_span(b);
-                it.db = static_cast<uint8_t *>(pool->arena.take(span));
-                GGB_CUDA(cudaMemcpyAsync(it.db, b->data, span, cudaMemcpyHostToDevice, s));
+                if (pool->owned && span <= ZC_MAX && (reinterpret_cast<uintptr_t>(b->data) & 3) == 0) {
+                    it.db = static_cast<uint8_t *>(b->data);            // UVA: the activation kernel reads the pinned arena directly
+                } else {
+                    it.db = static_cast<uint8_t *>(pool->arena.take(span));
+                    GGB_CUDA(cudaMemcpyAsync(it.db, b->data, span, cudaMemcpyHostToDevice, s));
+                }
                 g_stats.h2d_bytes += span;
             }
             it.dd = static_cast<uint8_t *>(pool->arena.take(tensor_span(t)));
@@ -461,15 +492,25 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     }
 
     // ---- results back into the host arena ----
+    CopyBatch cb = {};
     for (size_t i = 0; i < n; i++) {
         const Item &it = items[i];
         ggml_tensor *t = it.t;
         if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i] && t->op == GGML_OP_MUL_MAT) continue;   // a CPY target is user-visible
         void *hdst = t->op == GGML_OP_MUL_MAT ? t->data : t->src1->data;
         const size_t span = t->op == GGML_OP_MUL_MAT ? tensor_span(t) : tensor_span(t->src1);
-        GGB_CUDA(cudaMemcpyAsync(hdst, it.dd, span, cudaMemcpyDeviceToHost, s));
+        if (pool->owned && span <= ZC_MAX && (span & 3) == 0 && (reinterpret_cast<uintptr_t>(hdst) & 15) == 0) {
+            CopySeg &sg = cb.seg[cb.n++];
+            sg.src = it.dd; sg.dst = static_cast<uint8_t *>(hdst); sg.bytes = (unsigned)span; sg.vec0 = cb.total_vec;
+            cb.total_vec += (unsigned)((span + 15) / 16);
+            if (cb.n == 96) { rc = flush_copy_batch(cb, s); if (rc) return rc; }
+        } else {
+            GGB_CUDA(cudaMemcpyAsync(hdst, it.dd, span, cudaMemcpyDeviceToHost, s));
+        }
         g_stats.d2h_bytes += span;
     }
+    rc = flush_copy_batch(cb, s);
+    if (rc) return rc;
     GGB_CUDA(cudaEventRecord(g_ev1, s));
     GGB_CUDA(cudaStreamSynchronize(s));
     float ms = 0.f;
