@@ -240,10 +240,10 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
 // a pure stream (12 B per element), so everything is kept in registers and the K permutation 0,4,1,5,2,6,3,7 that the
 // GEMM's nibble unpack produces costs nothing.
 __global__ void __launch_bounds__(256) k_act_f16_dequant(int wtype, int perm, const float *__restrict__ x, long long ldx_bytes,
-                                                         __half *__restrict__ out, int N, int Npad, int K, int vec16)
+                                                         __half *__restrict__ out, int N, int Npad, int K, int vec16, int wait_prior)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the GEMM's prologue and weight streaming may start now
-    asm volatile("griddepcontrol.wait;" ::: "memory");                // x may be the previous kernel's output
+    if (wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory"); // x may be the previous kernel's output (first node of a batch only)
     const int kb = K / GGB_QK;
     const long long nblk = (long long)Npad * kb;
     for (long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
@@ -363,7 +363,7 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
     return GGB_OK;
 }
 
-int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s)
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior)
 {
     const long long nblk = Npad * (K / GGB_QK);
     if (nblk <= 0) return GGB_OK;
@@ -379,7 +379,7 @@ int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_byte
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant, wtype, perm, x, (long long)ldx_bytes, out, (int)N, (int)Npad, (int)K, vec16));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant, wtype, perm, x, (long long)ldx_bytes, out, (int)N, (int)Npad, (int)K, vec16, wait_prior ? 1 : 0));
     count_launch();
     return GGB_OK;
 }

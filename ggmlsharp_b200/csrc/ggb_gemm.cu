@@ -256,6 +256,7 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
     if (CG == 2) cluster_sync_all(); else __syncthreads();       // peer barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next node's activation kernel may run beside this GEMM
     if (tdbg && threadIdx.x == 0) tdbg[1] = clock64();                                 // setup done
 
     if (warp == 0) {
@@ -529,6 +530,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next node's activation kernel may run beside this GEMM
     if (tdbg && threadIdx.x == 0) tdbg[1] = clock64();
 
     if (warp == 0) {

@@ -40,7 +40,7 @@ struct ActNode { const float *x; long long ldx_bytes; uint8_t *out; int N; int b
 struct ActBatch { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; ActNode node[64]; };
 int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl);
 // batched path: activations as dense fp16 [Npad][K] holding d * q (the value the reference's dot multiplies by)
-int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s);
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior);
 
 // ---- GEMV (ggb_gemv.cu) ----
 struct GemvNode { const uint8_t *W; const uint8_t *xq; float *y; int M; int ldy; int g0; int ngroups; };

@@ -124,16 +124,21 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     if (off[count] && (reinterpret_cast<uintptr_t>(ws) & 255)) return set_error(GGB_E_INVALID, "mul_mat: workspace must be 256-byte aligned");
     uint8_t *wsb = static_cast<uint8_t *>(ws);
 
-    // ---- batched (tensor-core) nodes: one launch pair each ----
+    // ---- batched (tensor-core) nodes: act(i), gemm(i) interleaved.  Every kernel is launched programmatically dependent on
+    //      its predecessor and the GEMM triggers its dependents as soon as it is set up, so the activation staging of node
+    //      i+1 runs on the SMs WHILE node i's GEMM streams -- nodes of one batch are independent by contract and write
+    //      disjoint workspace regions, so only the first activation kernel has to wait for earlier work in the stream ----
     std::vector<int> gemv_idx;
+    bool first_gemm = true;
     for (int i = 0; i < count; i++) {
         const ggb_dev_mm &m = mm[i];
         if (m.M == 0 || m.N == 0) continue;
         if (!use_gemm(m)) { gemv_idx.push_back(i); continue; }
         const int64_t Npad = (m.N + 15) / 16 * 16;
         __half *xh = reinterpret_cast<__half *>(wsb + off[i]);
-        int rc = launch_act_f16_dequant(m.type, gemm_act_perm(m.type), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s);
+        int rc = launch_act_f16_dequant(m.type, gemm_act_perm(m.type), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s, first_gemm);
         if (rc) return rc;
+        first_gemm = false;
         GemmArgs a = {};
         a.type = m.type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
         a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
