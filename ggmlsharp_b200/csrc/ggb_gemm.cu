@@ -34,15 +34,6 @@ namespace {
 
 constexpr int BM = 128;            // weight rows per tile  (MMA M, TMEM lanes)
 constexpr int BK = 128;            // K per pipeline step   (4 quant blocks; two 64-wide swizzle atoms)
-// Pipeline depth is what hides the ~1.3 us TMA latency: bytes in flight per SM must cover latency x fill rate, so the
-// shared memory budget is spent on as many activation / raw stages as fit (profiles/r01_gemm_*: v1 with 3 stages was
-// latency-bound at ~1100 cycles per K step against a 512-cycle MMA floor).
-template <int TYPE, int CG> struct Stages {
-    static constexpr bool DEQ = TYPE != GGML_TYPE_F16;
-    static constexpr int RAW = DEQ ? 4 : 1;                                  // (F16: unused, RAW_BYTES == 0)
-    static constexpr int A = DEQ ? (CG == 2 ? 3 : 2) : (CG == 2 ? 4 : 3);     // F16: A rides with B
-    static constexpr int B = DEQ ? (CG == 2 ? 5 : 3) : A;
-};
 constexpr int NDQ_WARPS = 16;
 constexpr int NTHREADS = (4 + NDQ_WARPS) * 32;
 
@@ -149,93 +140,39 @@ __device__ __forceinline__ uint32_t and_or(uint32_t w, uint32_t mask, uint32_t m
     return d;
 }
 
-// One 32-weight block -> 64 bytes of the swizzle-128B K-major A tile.  `row` is the shared-space address of this thread's
-// 128-byte row in its sub-tile, `cx` the row's swizzle XOR (r & 7), `half` selects the 32-K half of the 64-wide sub-tile.
-template <int TYPE>
-__device__ __forceinline__ void dequant_block(uint32_t blk, uint32_t row, int cx, int half)
-{
-    uint32_t q[4];
-    __half2 d2, m2 = __float2half2_rn(0.0f);
-    if (TYPE == GGML_TYPE_Q4_0) {
-        d2 = __float2half2_rn(__uint_as_float(lds32(blk)));
-        q[0] = lds32(blk + 4); q[1] = lds32(blk + 8); q[2] = lds32(blk + 12); q[3] = lds32(blk + 16);
-    } else {
-        const uint2 dm = lds64(blk), qa = lds64(blk + 8), qb = lds64(blk + 16);
-        d2 = __float2half2_rn(__uint_as_float(dm.x));
-        // q*d + m == (q-8)*d + (m + 8d): the recentred offset is ~5x smaller than m, and so is its fp16 rounding
-        // error, which is coherent over the block's 32 elements and would otherwise dominate the Q4_1 error
-        m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(dm.x), __uint_as_float(dm.y)));
-        q[0] = qa.x; q[1] = qa.y; q[2] = qb.x; q[3] = qb.y;
-    }
-    const __half2 o_lo = __float2half2_rn(1032.0f), o_hi = __float2half2_rn(72.0f);     // 1024+8, 64+8
-    uint32_t mk_lo = 0x000F000Fu, mk_hi = 0x00F000F0u, mg_lo = 0x64006400u, mg_hi = 0x54005400u;
-    asm volatile("" : "+r"(mk_lo), "+r"(mk_hi), "+r"(mg_lo), "+r"(mg_hi));              // keep the four constants in registers
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t w = q[i], ws = w >> 8;
-        // (lo | 0x6400) = 1024 + q as an fp16 pair for bytes 0 and 2; (hi | 0x5400) = 64 + q for the high nibbles
-        uint32_t v0 = and_or(w, mk_lo, mg_lo);                  // elements 0, 4
-        uint32_t v1 = and_or(w, mk_hi, mg_hi);                  // elements 1, 5
-        uint32_t v2 = and_or(ws, mk_lo, mg_lo);                 // elements 2, 6
-        uint32_t v3 = and_or(ws, mk_hi, mg_hi);                 // elements 3, 7
-        __half2 h0 = *reinterpret_cast<__half2 *>(&v0), h1 = *reinterpret_cast<__half2 *>(&v1);
-        __half2 h2 = *reinterpret_cast<__half2 *>(&v2), h3 = *reinterpret_cast<__half2 *>(&v3);
-        if (TYPE == GGML_TYPE_Q4_0) {
-            h0 = __hmul2(__hsub2(h0, o_lo), d2); h1 = __hmul2(__hsub2(h1, o_hi), d2);
-            h2 = __hmul2(__hsub2(h2, o_lo), d2); h3 = __hmul2(__hsub2(h3, o_hi), d2);
-        } else {
-            h0 = __hfma2(__hsub2(h0, o_lo), d2, m2); h1 = __hfma2(__hsub2(h1, o_hi), d2, m2);
-            h2 = __hfma2(__hsub2(h2, o_lo), d2, m2); h3 = __hfma2(__hsub2(h3, o_hi), d2, m2);
-        }
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t *>(&h0); o.y = *reinterpret_cast<uint32_t *>(&h1);
-        o.z = *reinterpret_cast<uint32_t *>(&h2); o.w = *reinterpret_cast<uint32_t *>(&h3);
-        sts128(row + (uint32_t)(((half * 4 + i) ^ cx) << 4), o);                  // 128-byte swizzle: chunk index XOR row-in-atom
-    }
-}
-
-// CG = CTAs per tile: 2 -> tcgen05 cta_group::2, the pair computes 256 weight rows x BN; each CTA stages (and, for Q4,
-// dequantizes) its own 128 rows of A and only HALF of the activation tile, which halves the dominant shared-memory fill.
-template <int TYPE, int BN, int CG>
+// F16 weights: both operands are fp16 tiles fetched by TMA (swizzle-128B), A from shared memory.
+// CG = CTAs per tile: 2 -> tcgen05 cta_group::2, the pair computes 256 weight rows x BN; each CTA stages its own 128 rows of A
+// and only HALF of the activation tile.  Two issuer warps (even / odd K steps, separate accumulators) as in k_gemm_q.
+template <int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-       float *__restrict__ Y, long long ldy, int M, int N, int K, long long *__restrict__ dbg)
+k_gemm_f16(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+           float *__restrict__ Y, long long ldy, int M, int N, int K)
 {
-    constexpr bool DEQ = TYPE != GGML_TYPE_F16;
-    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96, BLK = TYPE == GGML_TYPE_Q4_0 ? 20 : 24;
-    constexpr int RAW_BYTES = DEQ ? BM * RAW_ROW : 0;
-    constexpr int BNL = BN / CG;                                 // activation rows staged by this CTA
+    constexpr int BNL = BN / CG;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2;
-    constexpr int RAW_STAGES = Stages<TYPE, CG>::RAW, A_STAGES = Stages<TYPE, CG>::A, B_STAGES = Stages<TYPE, CG>::B;
-    constexpr int NA = A_STAGES;                                 // F16 weights: A rides with B through TMA (NA == B_STAGES)
+    constexpr int STAGES = CG == 2 ? 4 : 3, NISSUE = 2;
+    constexpr int TMEM_COLS = NISSUE * BN;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *sA = smem;                                          // NA x A_BYTES       (1024-aligned)
-    uint8_t *sB = sA + NA * A_BYTES;                             // B_STAGES x B_BYTES (1024-aligned)
-    uint8_t *sRaw = sB + B_STAGES * B_BYTES;                     // RAW_STAGES x RAW_BYTES
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sRaw + RAW_STAGES * RAW_BYTES);
+    uint8_t *sA = smem;                                          // STAGES x A_BYTES (1024-aligned)
+    uint8_t *sB = sA + STAGES * A_BYTES;                         // STAGES x B_BYTES
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BYTES);
     const uint32_t bar0 = smem_u32(bars);
-    constexpr int RAW_FULL = 0, RAW_EMPTY = RAW_FULL + 4, A_FULL = RAW_EMPTY + 4, A_EMPTY = A_FULL + 4,
-                  B_FULL = A_EMPTY + 4, B_EMPTY = B_FULL + B_STAGES, ACC_FULL = B_EMPTY + B_STAGES, NBARS = ACC_FULL + 1;
+    constexpr int FULL = 0, EMPTY = 4, ACC_FULL = 8, NBARS = 9;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
     auto BAR = [&](int i) { return bar0 + 8 * i; };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    long long *const tdbg = dbg ? dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 : nullptr;   // GGB200_GEMM_TRACE: clock64 timeline
-    if (tdbg && threadIdx.x == 0) tdbg[0] = clock64();
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
     const bool leader = rank == 0;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN + (int)rank * BNL;
     const int ksteps = (K + BK - 1) / BK;
-    // barriers the MMA issuer waits on live in the leader CTA
     auto LBAR = [&](int i) { return CG == 2 ? mapa_u32(BAR(i), 0) : BAR(i); };
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RAW_STAGES; i++) { mbar_init(BAR(RAW_FULL + i), 1); mbar_init(BAR(RAW_EMPTY + i), NDQ_WARPS); }
-        for (int i = 0; i < NA; i++) { mbar_init(BAR(A_FULL + i), DEQ ? CG * NDQ_WARPS : 1); mbar_init(BAR(A_EMPTY + i), 1); }
-        for (int i = 0; i < B_STAGES; i++) { mbar_init(BAR(B_FULL + i), CG); mbar_init(BAR(B_EMPTY + i), 1); }
-        mbar_init(BAR(ACC_FULL), 1);
+        for (int i = 0; i < STAGES; i++) { mbar_init(BAR(FULL + i), CG); mbar_init(BAR(EMPTY + i), 1); }
+        mbar_init(BAR(ACC_FULL), NISSUE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -245,162 +182,107 @@ k_gemm(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtens
     }
     if (warp == 2) {
         if (CG == 2) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
         } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
     }
     tc_fence_before();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();       // peer barriers are initialised before anyone signals them
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next node's activation kernel may run beside this GEMM
-    if (tdbg && threadIdx.x == 0) tdbg[1] = clock64();                                 // setup done
 
     if (warp == 0) {
-        // ===== TMA producer (one per CTA) =====
+        // ===== TMA producer: this CTA's 128 weight rows and its half of the activation rows, per K step =====
         if (lane == 0) {
-            asm volatile("griddepcontrol.wait;" ::: "memory");       // PDL: activations come from the preceding kernel
+            asm volatile("griddepcontrol.wait;" ::: "memory");       // activations come from the preceding kernel
+            int sb = 0; uint32_t ph = 1;
             for (int ks = 0; ks < ksteps; ks++) {
-                if (DEQ) {
-                    const int s = ks % RAW_STAGES;
-                    mbar_wait(BAR(RAW_EMPTY + s), ((ks / RAW_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(BAR(RAW_FULL + s), RAW_BYTES);
-                    tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &map_w, BAR(RAW_FULL + s), ks * RAW_ROW, m0);
-                }
-                const int sb = ks % B_STAGES;
-                mbar_wait(BAR(B_EMPTY + sb), ((ks / B_STAGES) & 1) ^ 1);
-                const uint32_t full = LBAR(B_FULL + sb);
-                constexpr uint32_t per_cta = B_BYTES + (DEQ ? 0 : A_BYTES);
+                mbar_wait(BAR(EMPTY + sb), ph);
+                const uint32_t full = LBAR(FULL + sb);
+                constexpr uint32_t per_cta = B_BYTES + A_BYTES;
                 if (CG == 2) {
-                    if (leader) mbar_expect_tx(BAR(B_FULL + sb), CG * per_cta);   // counts both CTAs' bytes
-                    else mbar_arrive_cluster(full);
+                    if (leader) mbar_expect_tx(BAR(FULL + sb), CG * per_cta); else mbar_arrive_cluster(full);
                     tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES), &map_x, full, ks * BK, n0);
                     tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, full, ks * BK + 64, n0);
-                    if (!DEQ) {
-                        tma_load_2d_cg2(smem_u32(sA + sb * A_BYTES), &map_w, full, ks * BK, m0);
-                        tma_load_2d_cg2(smem_u32(sA + sb * A_BYTES + BM * 128), &map_w, full, ks * BK + 64, m0);
-                    }
+                    tma_load_2d_cg2(smem_u32(sA + sb * A_BYTES), &map_w, full, ks * BK, m0);
+                    tma_load_2d_cg2(smem_u32(sA + sb * A_BYTES + BM * 128), &map_w, full, ks * BK + 64, m0);
                 } else {
-                    mbar_expect_tx(BAR(B_FULL + sb), per_cta);
+                    mbar_expect_tx(BAR(FULL + sb), per_cta);
                     tma_load_2d(smem_u32(sB + sb * B_BYTES), &map_x, full, ks * BK, n0);
                     tma_load_2d(smem_u32(sB + sb * B_BYTES + BNL * 128), &map_x, full, ks * BK + 64, n0);
-                    if (!DEQ) {
-                        tma_load_2d(smem_u32(sA + sb * A_BYTES), &map_w, full, ks * BK, m0);
-                        tma_load_2d(smem_u32(sA + sb * A_BYTES + BM * 128), &map_w, full, ks * BK + 64, m0);
-                    }
+                    tma_load_2d(smem_u32(sA + sb * A_BYTES), &map_w, full, ks * BK, m0);
+                    tma_load_2d(smem_u32(sA + sb * A_BYTES + BM * 128), &map_w, full, ks * BK + 64, m0);
                 }
+                if (++sb == STAGES) { sb = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer: the leader CTA only; one lane, commits and next-step barrier probes hidden between MMAs =====
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers (leader CTA): even / odd K steps, own accumulator each =====
         if (leader && lane == 0) {
+            const int me = warp >> 1;
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
-            if (DEQ) mbar_wait(BAR(A_FULL + 0), 0);
-            mbar_wait(BAR(B_FULL + 0), 0);
-            tc_fence_after();
-            for (int ks = 0; ks < ksteps; ks++) {
-                const int sa = ks % NA, sb = ks % B_STAGES;
-                const int san = (ks + 1) % NA, sbn = (ks + 1) % B_STAGES;
-                const uint32_t par_an = (uint32_t)(((ks + 1) / NA) & 1), par_bn = (uint32_t)(((ks + 1) / B_STAGES) & 1);
-                const bool more = ks + 1 < ksteps;
-                bool a_ok = !more || !DEQ, b_ok = !more;
-                const uint32_t a_base = smem_u32(sA + sa * A_BYTES), b_base = smem_u32(sB + sb * B_BYTES);
-                if (tdbg && ks < 20) tdbg[9 + 2 * ks] = clock64();
+            const uint32_t acc = tmem + (uint32_t)(me * BN);
+            const uint64_t adesc0 = make_sdesc(smem_u32(sA)), bdesc0 = make_sdesc(smem_u32(sB));
+            for (int ks = me; ks < ksteps; ks += NISSUE) {
+                const int sb = ks % STAGES;
+                mbar_wait(BAR(FULL + sb), (uint32_t)((ks / STAGES) & 1));
+                tc_fence_after();
+                const uint64_t ad0 = adesc0 + (uint64_t)((sb * A_BYTES) >> 4), bd0 = bdesc0 + (uint64_t)((sb * B_BYTES) >> 4);
 #pragma unroll
                 for (int k = 0; k < BK / 16; k++) {
                     // sub-tile k/4 (64 K each), then 32 bytes per K=16 step inside the 128-byte swizzle row
-                    const uint64_t ad = make_sdesc(a_base + (k >> 2) * (BM * 128) + (k & 3) * 32);
-                    const uint64_t bd = make_sdesc(b_base + (k >> 2) * (BNL * 128) + (k & 3) * 32);
-                    if (CG == 2) tc_mma_f16_cg2(tmem, ad, bd, idesc, (ks | k) != 0);
-                    else tc_mma_f16(tmem, ad, bd, idesc, (ks | k) != 0);
-                    if (ks > 0) {
-                        const int sap = (ks - 1) % NA, sbp = (ks - 1) % B_STAGES;
-                        if (k == 0 && DEQ) { if (CG == 2) tc_commit_cg2(BAR(A_EMPTY + sap)); else tc_commit(BAR(A_EMPTY + sap)); }
-                        if (k == 1) { if (CG == 2) tc_commit_cg2(BAR(B_EMPTY + sbp)); else tc_commit(BAR(B_EMPTY + sbp)); }
-                    }
-                    if (k >= 2) { if (!a_ok) a_ok = mbar_test(BAR(A_FULL + san), par_an); else if (!b_ok) b_ok = mbar_test(BAR(B_FULL + sbn), par_bn); }
+                    const uint64_t ad = ad0 + (uint64_t)(((k >> 2) * (BM * 128) + (k & 3) * 32) >> 4);
+                    const uint64_t bd = bd0 + (uint64_t)(((k >> 2) * (BNL * 128) + (k & 3) * 32) >> 4);
+                    if (CG == 2) tc_mma_f16_cg2(acc, ad, bd, idesc, (ks >= NISSUE) || k != 0);
+                    else tc_mma_f16(acc, ad, bd, idesc, (ks >= NISSUE) || k != 0);
                 }
-                if (!a_ok) mbar_wait(BAR(A_FULL + san), par_an);
-                if (!b_ok) mbar_wait(BAR(B_FULL + sbn), par_bn);
-                tc_fence_after();
+                if (CG == 2) tc_commit_cg2(BAR(EMPTY + sb)); else tc_commit(BAR(EMPTY + sb));
             }
-            {
-                const int sal = (ksteps - 1) % NA, sbl = (ksteps - 1) % B_STAGES;
-                if (CG == 2) { if (DEQ) tc_commit_cg2(BAR(A_EMPTY + sal)); tc_commit_cg2(BAR(B_EMPTY + sbl)); tc_commit_cg2(BAR(ACC_FULL)); }
-                else { if (DEQ) tc_commit(BAR(A_EMPTY + sal)); tc_commit(BAR(B_EMPTY + sbl)); tc_commit(BAR(ACC_FULL)); }
-            }
+            if (CG == 2) tc_commit_cg2(BAR(ACC_FULL)); else tc_commit(BAR(ACC_FULL));
         }
     } else if (warp >= 4) {
-        // ===== dequant warps (then warps 4..7: epilogue) =====
-        if (DEQ) {
-            const int dw = warp - 4;
-            // one 32-weight block per thread per K step.  Lane bits: [0] K-half of the sub-tile, [1:2] row, [3] sub-tile,
-            // [4] row: 8 consecutive lanes = 4 rows x 2 halves of ONE sub-tile -> their STS.128 hit 8 distinct swizzled
-            // chunk slots (no bank conflict), and a warp's 32 raw blocks (rows x 20/24-byte blocks) read conflict-free too.
-            const int r = dw * 8 + (((lane >> 1) & 3) | ((lane >> 4) << 2)), j = (lane & 1) | (((lane >> 3) & 1) << 1);
-            const int raw_off = r * RAW_ROW + j * BLK;
-            const int a_off = (j >> 1) * (BM * 128) + r * 128;
-            const int cx = r & 7, half = j & 1;
-            int s = 0, sa = 0; uint32_t ph_raw = 0, ph_a = 1;
-            const uint32_t a_full0 = LBAR(A_FULL);
-            const uint32_t sraw0 = smem_u32(sRaw), sa0 = smem_u32(sA);
-            for (int ks = 0; ks < ksteps; ks++) {
-                mbar_wait(BAR(RAW_FULL + s), ph_raw);
-                if (tdbg && threadIdx.x == 128 && ks < 40) { tdbg[48 + ks] = clock64(); }      // raw ready
-                mbar_wait(BAR(A_EMPTY + sa), ph_a);
-                if (tdbg && threadIdx.x == 128 && ks < 40) tdbg[88 + ks] = clock64();      // both waits done
-                dequant_block<TYPE>(sraw0 + s * RAW_BYTES + raw_off, sa0 + sa * A_BYTES + a_off, cx, half);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) mbar_arrive_cluster(a_full0 + 8 * sa); else mbar_arrive(BAR(A_FULL + sa));
-                    mbar_arrive(BAR(RAW_EMPTY + s));
-                }
-                if (++s == RAW_STAGES) { s = 0; ph_raw ^= 1; }
-                if (++sa == A_STAGES) { sa = 0; ph_a ^= 1; }
-            }
-        }
-        {
-            // epilogue on all 16 warps: warp -> (TMEM lane quadrant warp%4, 32-column group)
-            const int q = warp & 3;                              // TMEM lane quadrant this warp may access
-            mbar_wait(BAR(ACC_FULL), 0);
-            if (tdbg && threadIdx.x == 128) tdbg[2] = clock64();                       // accumulator complete
-            tc_fence_after();
-            const int m = m0 + q * 32 + lane;
-            const int nbase = blockIdx.y * BN;
+        // ===== epilogue on all 16 warps: warp -> (TMEM lane quadrant warp%4, 32-column group) =====
+        const int q = warp & 3;
+        mbar_wait(BAR(ACC_FULL), 0);
+        tc_fence_after();
+        const int m = m0 + q * 32 + lane;
+        const int nbase = blockIdx.y * BN;
 #pragma unroll 1
-            for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                               "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                             : "r"(taddr) : "memory");
+        for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
+#pragma unroll 1
+            for (int hc = 0; hc < 2; hc++) {                      // 16 columns at a time keeps both accumulators in 32 registers
+                uint32_t v[16], u[16];
+#define GGB_TMEM_LD16(ARR, ADDR) \
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                             : "=r"(ARR[0]), "=r"(ARR[1]), "=r"(ARR[2]), "=r"(ARR[3]), "=r"(ARR[4]), "=r"(ARR[5]), "=r"(ARR[6]), "=r"(ARR[7]), \
+                               "=r"(ARR[8]), "=r"(ARR[9]), "=r"(ARR[10]), "=r"(ARR[11]), "=r"(ARR[12]), "=r"(ARR[13]), "=r"(ARR[14]), "=r"(ARR[15]) \
+                             : "r"(ADDR) : "memory")
+                GGB_TMEM_LD16(v, taddr + (uint32_t)(hc * 16));
+                GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
+#undef GGB_TMEM_LD16
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (m < M) {
 #pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const int n = nbase + cb * 32 + c;
-                        if (n < N) Y[(long long)n * ldy + m] = __uint_as_float(v[c]);
+                    for (int c = 0; c < 16; c++) {
+                        const int n = nbase + cb * 32 + hc * 16 + c;
+                        const float r = ksteps > 1 ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);
+                        if (n < N) Y[(long long)n * ldy + m] = r;
                     }
                 }
             }
         }
     }
-    if (tdbg && threadIdx.x == 128) tdbg[3] = clock64();                               // epilogue stores issued
     tc_fence_before();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();       // the peer's shared memory / TMEM stay valid until both are done
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
-        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(BN) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -654,30 +536,26 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
             const int nbase = blockIdx.y * BN;
 #pragma unroll 1
             for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
-                uint32_t v[32], u[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
-#define GGB_TMEM_LD32(ARR, ADDR) \
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " \
-                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
-                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" \
-                             : "=r"(ARR[0]), "=r"(ARR[1]), "=r"(ARR[2]), "=r"(ARR[3]), "=r"(ARR[4]), "=r"(ARR[5]), "=r"(ARR[6]), "=r"(ARR[7]), \
-                               "=r"(ARR[8]), "=r"(ARR[9]), "=r"(ARR[10]), "=r"(ARR[11]), "=r"(ARR[12]), "=r"(ARR[13]), "=r"(ARR[14]), "=r"(ARR[15]), \
-                               "=r"(ARR[16]), "=r"(ARR[17]), "=r"(ARR[18]), "=r"(ARR[19]), "=r"(ARR[20]), "=r"(ARR[21]), "=r"(ARR[22]), "=r"(ARR[23]), \
-                               "=r"(ARR[24]), "=r"(ARR[25]), "=r"(ARR[26]), "=r"(ARR[27]), "=r"(ARR[28]), "=r"(ARR[29]), "=r"(ARR[30]), "=r"(ARR[31]) \
-                             : "r"(ADDR) : "memory")
-                GGB_TMEM_LD32(v, taddr);
-                GGB_TMEM_LD32(u, taddr + (uint32_t)BN);
-#undef GGB_TMEM_LD32
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (ksteps > 1) {
+#pragma unroll 1
+                for (int hc = 0; hc < 2; hc++) {                      // 16 columns at a time keeps both accumulators in 32 registers
+                    uint32_t v[16], u[16];
+#define GGB_TMEM_LD16(ARR, ADDR) \
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                                 : "=r"(ARR[0]), "=r"(ARR[1]), "=r"(ARR[2]), "=r"(ARR[3]), "=r"(ARR[4]), "=r"(ARR[5]), "=r"(ARR[6]), "=r"(ARR[7]), \
+                                   "=r"(ARR[8]), "=r"(ARR[9]), "=r"(ARR[10]), "=r"(ARR[11]), "=r"(ARR[12]), "=r"(ARR[13]), "=r"(ARR[14]), "=r"(ARR[15]) \
+                                 : "r"(ADDR) : "memory")
+                    GGB_TMEM_LD16(v, taddr + (uint32_t)(hc * 16));
+                    GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
+#undef GGB_TMEM_LD16
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (m < M) {
 #pragma unroll
-                    for (int c = 0; c < 32; c++) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(u[c]));     // even-K + odd-K partial sums
-                }
-                if (m < M) {
-#pragma unroll
-                    for (int c = 0; c < 32; c++) {
-                        const int n = nbase + cb * 32 + c;
-                        if (n < N) Y[(long long)n * ldy + m] = __uint_as_float(v[c]);
+                        for (int c = 0; c < 16; c++) {
+                            const int n = nbase + cb * 32 + hc * 16 + c;
+                            const float r = ksteps > 1 ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);   // even-K + odd-K partial sums
+                            if (n < N) Y[(long long)n * ldy + m] = r;
+                        }
                     }
                 }
             }
@@ -728,29 +606,20 @@ int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint
     return GGB_OK;
 }
 
-template <int TYPE, int BN, int CG>
-int launch_typed(const GemmArgs &a, cudaStream_t s)
+template <int BN, int CG>
+int launch_f16(const GemmArgs &a, cudaStream_t s)
 {
-    constexpr bool DEQ = TYPE != GGML_TYPE_F16;
-    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
     constexpr int BNL = BN / CG;
     CUtensorMap mw, mx;
-    int rc;
-    if (DEQ) {
-        const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * (TYPE == GGML_TYPE_Q4_0 ? 20 : 24);
-        rc = make_map_2d(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, row_bytes, (uint64_t)a.M, (uint64_t)a.nb01, RAW_ROW, BM, CU_TENSOR_MAP_SWIZZLE_NONE);
-    } else {
-        rc = make_map_2d(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.W, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.nb01, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
-    }
+    int rc = make_map_2d(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.W, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.nb01, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, BNL, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
-    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2, RAW_BYTES = DEQ ? BM * RAW_ROW : 0;
-    constexpr size_t smem = 1024 + (size_t)Stages<TYPE, CG>::A * A_BYTES + (size_t)Stages<TYPE, CG>::B * B_BYTES +
-                            (size_t)Stages<TYPE, CG>::RAW * RAW_BYTES + 64 * 8 + 16;
+    constexpr int STAGES = CG == 2 ? 4 : 3;
+    constexpr size_t smem = 1024 + STAGES * (size_t)(BM * BK * 2) + STAGES * (size_t)(BNL * BK * 2) + 64 * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool attr_set = false;
-    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemm<TYPE, BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemm_f16<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     const unsigned mt = (unsigned)((a.M + BM - 1) / BM);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((mt + CG - 1) / CG * CG, (unsigned)((a.N + BN - 1) / BN));    // whole CTA pairs; a padding CTA sees only out-of-bounds (zero) rows
@@ -760,11 +629,11 @@ int launch_typed(const GemmArgs &a, cudaStream_t s)
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // prologue + weight streaming overlap the activation kernel
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // prologue overlaps the activation kernel
     at[1].val.programmaticStreamSerializationAllowed = 1;
     static const bool no_pdl = getenv("GGB200_NO_PDL") != nullptr;
     cfg.attrs = at; cfg.numAttrs = no_pdl ? 1 : 2;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm<TYPE, BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, static_cast<long long *>(a.trace)));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_f16<BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K));
     count_launch();
     return GGB_OK;
 }
@@ -827,22 +696,11 @@ int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s)
 {
     (void)ws;
     if (a.n_peers) return set_error(GGB_E_UNSUPPORTED, "batched path: fused peer stores are not implemented");
-    static const int cg = [] { const char *e = getenv("GGB200_GEMM_CG"); return e ? atoi(e) : 2; }();
-    static const bool a_smem = [] { const char *e = getenv("GGB200_GEMM_A"); return e && e[0] == 's'; }();   // debugging: A staged in shared memory
-    if (!a_smem) {
-        if (a.type == GGML_TYPE_Q4_0) return cg == 1 ? launch_q<GGML_TYPE_Q4_0, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_0, 128, 2>(a, s);
-        if (a.type == GGML_TYPE_Q4_1) return cg == 1 ? launch_q<GGML_TYPE_Q4_1, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_1, 128, 2>(a, s);
-    }
-    if (cg == 1) switch (a.type) {
-    case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, 128, 1>(a, s);
-    case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, 128, 1>(a, s);
-    case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, 128, 1>(a, s);
-    default: break;
-    }
+    static const int cg = [] { const char *e = getenv("GGB200_GEMM_CG"); return e ? atoi(e) : 2; }();     // debugging: 1 = no CTA pairs
     switch (a.type) {
-    case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, 128, 2>(a, s);
-    case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, 128, 2>(a, s);
-    case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, 128, 2>(a, s);
+    case GGML_TYPE_Q4_0: return cg == 1 ? launch_q<GGML_TYPE_Q4_0, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_0, 128, 2>(a, s);
+    case GGML_TYPE_Q4_1: return cg == 1 ? launch_q<GGML_TYPE_Q4_1, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_1, 128, 2>(a, s);
+    case GGML_TYPE_F16: return cg == 1 ? launch_f16<128, 1>(a, s) : launch_f16<128, 2>(a, s);
     default: return set_error(GGB_E_UNSUPPORTED, "batched path: type %d", a.type);
     }
 }
