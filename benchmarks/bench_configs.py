@@ -1,0 +1,132 @@
+#!/usr/bin/env python3
+"""Every configuration of BASELINE.json on one B200, device-resident, CUDA-event timed.
+
+  cfg0  F32  4096x4096 . 4096x1                      (GEMV, HBM)
+  cfg1  Q4_0 4096x4096 . 4096x1                      (GEMV, HBM)  + quantize_row_q4_0 over the 4096x4096 source
+  cfg2  Q4_1 / F16, 11008x4096 (w1/w3) and 4096x11008 (w2), N=1   (GEMV, HBM)
+  cfg3  Q4_0 / F16 4096x4096 . 4096x512              (tcgen05 GEMM)
+  cfg4  32 layers x {wq,wk,wv,wo 4096x4096; w1,w3 11008x4096; w2 4096x11008} Q4_0, N=1 decode and N=512 prompt, 1 GPU
+
+GEMV configs cycle a ring of distinct weight matrices larger than 2x L2 and submit the whole ring as ONE batch (a graph
+level of independent nodes), which is the steady state the bandwidth target applies to; "isolated" is one node per call.
+Prints one JSON object per line; fractions are of MEASURED_PEAKS.json ("of measured") and of nominal 8 TB/s / 2.25 PF.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from ggmlsharp_b200 import native as N
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=30)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    L = N.lib()
+    N.check(L.ggb_init())
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sp = C.c_void_p(stream.cuda_stream)
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm, tf = float(pk.get("hbm_gbs", 6650.0)), float(pk.get("bf16_tflops", 1590.0))
+    TN = {N.F32: "f32", N.F16: "f16", N.Q4_0: "q4_0", N.Q4_1: "q4_1"}
+
+    def make_w(t, M, K):
+        rb = N.TYPE_SIZE[t] * (K // N.BLCK_SIZE[t])
+        wf = torch.randn((M, K), device=dev) * 0.02
+        if t == N.F32:
+            return wf.view(torch.uint8).view(M, rb).clone(), rb
+        w = torch.empty((M, rb), dtype=torch.uint8, device=dev)
+        N.check(L.ggb_dev_quantize_rows(t, wf.data_ptr(), w.data_ptr(), M, K, sp))
+        return w, rb
+
+    def time_calls(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def run_nodes(shapes, Nn, label, iters):
+        """shapes: list of (type, M, K); all submitted as one batch per call."""
+        keep, mm = [], (N.ggb_dev_mm * len(shapes))()
+        wbytes = flop = abytes = 0
+        for i, (t, M, K) in enumerate(shapes):
+            w, rb = make_w(t, M, K)
+            x = torch.randn((Nn, K), device=dev)
+            y = torch.zeros((Nn, M), device=dev)
+            keep += [w, x, y]
+            m = mm[i]
+            m.type, m.M, m.K, m.N = t, M, K, Nn
+            m.W, m.nb01, m.X, m.ldx_bytes, m.Y, m.ldy_bytes = w.data_ptr(), rb, x.data_ptr(), 4 * K, y.data_ptr(), 4 * M
+            wbytes += M * rb
+            abytes += M * rb + 4 * K * Nn + 4 * M * Nn
+            flop += 2.0 * M * K * Nn
+        wsb = L.ggb_dev_workspace_bytes(mm, len(shapes))
+        ws = torch.empty(wsb + 256, dtype=torch.uint8, device=dev)
+        wsp = (ws.data_ptr() + 255) // 256 * 256
+        ms = time_calls(lambda: N.check(L.ggb_dev_mul_mat_batch(mm, len(shapes), wsp, wsb, sp)), iters)
+        out = {"config": label, "nodes": len(shapes), "N": Nn, "weight_MB": wbytes / 1e6, "ms": ms}
+        if Nn < 16:
+            gbs = abytes / (ms * 1e-3) / 1e9
+            out.update({"GB/s": gbs, "frac_of_measured_hbm": gbs / hbm, "frac_of_8TBs": gbs / 8000.0})
+        else:
+            tfl = flop / (ms * 1e-3) / 1e12
+            out.update({"TFLOP/s": tfl, "frac_of_measured_bf16": tfl / tf, "frac_of_2.25PF": tfl / 2250.0})
+        print(json.dumps(out), flush=True)
+        del keep
+        torch.cuda.empty_cache()
+
+    sel = set(a.only.split(",")) if a.only else None
+
+    def want(k):
+        return sel is None or k in sel
+
+    if want("cfg0"):
+        run_nodes([(N.F32, 4096, 4096)] * 5, 1, "cfg0 F32 4096x4096 GEMV, ring of 5 (336 MB)", a.iters)
+        run_nodes([(N.F32, 4096, 4096)], 1, "cfg0 F32 4096x4096 GEMV, isolated (L2-warm)", a.iters)
+    if want("cfg1"):
+        run_nodes([(N.Q4_0, 4096, 4096)] * 32, 1, "cfg1 Q4_0 4096x4096 GEMV, ring of 32 (336 MB)", a.iters)
+        run_nodes([(N.Q4_0, 4096, 4096)], 1, "cfg1 Q4_0 4096x4096 GEMV, isolated (L2-warm)", a.iters)
+        src = torch.randn((8, 4096, 4096), device=dev) * 0.02                      # 8 distinct 64 MiB sources (> L2)
+        dst = torch.empty((4096, 4096 // 32 * 20), dtype=torch.uint8, device=dev)
+        it = [0]
+
+        def q():
+            N.check(L.ggb_dev_quantize_rows(N.Q4_0, src[it[0] % 8].data_ptr(), dst.data_ptr(), 4096, 4096, sp))
+            it[0] += 1
+        ms = time_calls(q, a.iters)
+        by = 4096 * 4096 * 4 + 4096 * 4096 // 32 * 20
+        print(json.dumps({"config": "cfg1 quantize_row_q4_0 over 4096x4096 F32 (bit-exact kernel)", "ms": ms, "GB/s": by / ms / 1e6,
+                          "frac_of_measured_hbm": by / ms / 1e6 / hbm}), flush=True)
+        del src, dst
+    if want("cfg2"):
+        for t in (N.Q4_1, N.F16):
+            n_ring = 10 if t == N.Q4_1 else 4
+            run_nodes([(t, 11008, 4096)] * n_ring, 1, "cfg2 %s 11008x4096 (w1/w3) GEMV, ring of %d" % (TN[t], n_ring), a.iters)
+            run_nodes([(t, 4096, 11008)] * n_ring, 1, "cfg2 %s 4096x11008 (w2, K=11008) GEMV, ring of %d" % (TN[t], n_ring), a.iters)
+    if want("cfg3"):
+        for t in (N.Q4_0, N.F16):
+            run_nodes([(t, 4096, 4096)] * 8, 512, "cfg3 %s 4096x4096 . 4096x512, batch of 8 nodes" % TN[t], max(4, a.iters // 4))
+            run_nodes([(t, 4096, 4096)], 512, "cfg3 %s 4096x4096 . 4096x512, isolated" % TN[t], a.iters)
+    if want("cfg4"):
+        layer = [(N.Q4_0, 4096, 4096)] * 4 + [(N.Q4_0, 11008, 4096)] * 2 + [(N.Q4_0, 4096, 11008)]
+        run_nodes(layer * 32, 1, "cfg4 Llama-7B-shaped stack, 32 layers x 7 Q4_0 matrices (4.05 GB), N=1 decode step, 1 GPU", max(3, a.iters // 6))
+        run_nodes(layer * 4, 512, "cfg4 Llama-7B-shaped layers (4 of 32: 28 matrices), N=512 prompt step, 1 GPU", 3)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,6 +9,8 @@
 // + 0.625 / 0.75 B written per element).
 #include "ggb_internal.h"
 
+#include <algorithm>
+
 namespace ggb {
 
 namespace {
@@ -123,6 +125,68 @@ __global__ void __launch_bounds__(256) k_quantize_rows(const float *__restrict__
                 if (sub == 4) out[2] = __float_as_uint(__fmul_rn(d, (float)s));
             }
         }
+    }
+}
+
+// Weight quantizers, one thread per block of 32 (128 B in, 20 / 24 B out): the first-max and min/max scans run in the
+// reference's element order, entirely in registers; eight 128-bit loads per thread are in flight at once.
+template <int TYPE>
+__device__ __forceinline__ void quantize_block_q4(const float (&e)[32], uint32_t *out)
+{
+    uint32_t w[4];
+    if (TYPE == GGML_TYPE_Q4_0) {
+        float amax = 0.0f, mx = 0.0f;                          // Ggml.cs:343-354: strict <, the first maximum wins
+#pragma unroll
+        for (int i = 0; i < 32; i++) { const float av = fabsf(e[i]); if (amax < av) { amax = av; mx = e[i]; } }
+        const float d = __fdiv_rn(mx, -8.0f);
+        const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int q0 = rne_q4_0(__fmul_rn(e[8 * j + 2 * b], id)), q1 = rne_q4_0(__fmul_rn(e[8 * j + 2 * b + 1], id));
+                acc |= (uint32_t)((q0 | (q1 << 4)) & 0xFF) << (8 * b);
+            }
+            w[j] = acc;
+        }
+        out[0] = __float_as_uint(d);
+        out[1] = w[0]; out[2] = w[1]; out[3] = w[2]; out[4] = w[3];
+    } else {
+        float mn = e[0], mx = e[0];                            // Ggml.cs:496-504 (equal values keep the earlier element)
+#pragma unroll
+        for (int i = 1; i < 32; i++) { if (e[i] < mn) mn = e[i]; if (e[i] > mx) mx = e[i]; }
+        const float d = __fdiv_rn(__fsub_rn(mx, mn), 15.0f);
+        const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int q0 = rne_byte(__fmul_rn(__fsub_rn(e[8 * j + 2 * b], mn), id)), q1 = rne_byte(__fmul_rn(__fsub_rn(e[8 * j + 2 * b + 1], mn), id));
+                acc |= (uint32_t)((q0 | (q1 << 4)) & 0xFF) << (8 * b);
+            }
+            w[j] = acc;
+        }
+        out[0] = __float_as_uint(d); out[1] = __float_as_uint(mn);
+        out[2] = w[0]; out[3] = w[1]; out[4] = w[2]; out[5] = w[3];
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(256) k_quantize_q4_rows(const float *__restrict__ x, long long ldx, uint8_t *__restrict__ y,
+                                                          long long nblk, int kb)
+{
+    // (A variant that staged loads and stores through shared memory for fully coalesced 128-bit global accesses measured
+    //  slower -- 2.9 vs 3.4 TB/s on 4096x4096 -- the kernel is latency-, not transaction-bound; profiles/README.md.)
+    for (long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
+        const long long row = blk / kb;
+        const int col = (int)(blk - row * kb);
+        const float4 *p = reinterpret_cast<const float4 *>(x + row * ldx + (long long)col * GGB_QK);
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float4 v = __ldg(p + i); e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w; }
+        quantize_block_q4<TYPE>(e, reinterpret_cast<uint32_t *>(y + blk * (TYPE == GGML_TYPE_Q4_0 ? 20 : 24)));
     }
 }
 
@@ -320,9 +384,10 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
     const long long nblk = nrows * kb;
     const unsigned grid = (unsigned)((nblk * 8 + 255) / 256);
     uint8_t *y = (uint8_t *)dst;
+    const unsigned grid4 = (unsigned)std::min<long long>((nblk + 255) / 256, (long long)device_sm_count() * 16);
     switch (type) {
-    case GGML_TYPE_Q4_0: k_quantize_rows<GGML_TYPE_Q4_0><<<grid, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
-    case GGML_TYPE_Q4_1: k_quantize_rows<GGML_TYPE_Q4_1><<<grid, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
+    case GGML_TYPE_Q4_0: k_quantize_q4_rows<GGML_TYPE_Q4_0><<<grid4, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
+    case GGML_TYPE_Q4_1: k_quantize_q4_rows<GGML_TYPE_Q4_1><<<grid4, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
     case GGML_TYPE_Q8_0: k_quantize_rows<GGML_TYPE_Q8_0><<<grid, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
     case GGML_TYPE_Q8_1: k_quantize_rows<GGML_TYPE_Q8_1><<<grid, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
     default: return set_error(GGB_E_UNSUPPORTED, "quantize: type %d has no codec on this path", type);
