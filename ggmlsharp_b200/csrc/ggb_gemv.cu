@@ -5,12 +5,13 @@
 // 1124-1201).  The reference splits src0 rows over OS threads (dr = ceil(nr/nth)); here rows are split
 // over every warp of a one-CTA-per-SM grid, and one launch walks all nodes of a batch.
 //
-// Data movement: weight rows are contiguous byte ranges (nb01 bytes each), so every warp streams its
-// own rows HBM -> shared memory with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a private
-// ring of `depth` stages guarded by mbarriers -- no CTA-wide barrier in the steady state, ~10-20 KB in
-// flight per warp.  Lanes then read 20-byte Q4_0 / 24-byte Q4_1 blocks from shared memory with a lane
-// stride of 5 / 6 words (bank-conflict free), so the raw reference block layout is kept in HBM and the
-// unaligned-vector-load problem of 20-byte blocks never reaches the memory system.
+// Data movement: weight rows are contiguous byte ranges (nb01 bytes each), so a producer warp streams
+// tiles of rows HBM -> shared memory with 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a ring
+// of stages guarded by full/empty mbarriers (k_gemv_fast); rows that are not 16-byte multiples take
+// k_gemv, which stages with plain loads.  Lanes read 20-byte Q4_0 / 24-byte Q4_1 blocks from shared
+// memory (80 / 48-byte units with LDS.128, or single blocks with a lane stride of 5 / 6 words: both
+// bank-conflict free), so the raw reference block layout is kept in HBM and the unaligned-vector-load
+// problem of 20-byte blocks never reaches the memory system.
 // The activation vector(s) were quantized by k_act_batch exactly as quantize_row_q8_0/q8_1 do and sit
 // in shared memory for the whole node.
 //
@@ -191,14 +192,9 @@ __device__ __forceinline__ void dot_chunk(const GemvBatch &b, const uint8_t *w, 
     else dot_f32<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, lane, acc);
 }
 
-// The sequence of (group, chunk) items one warp streams: groups g_begin+warp, +NWARPS, ... below g_end.
-struct Cursor {
-    int g, c, n;
-    __device__ __forceinline__ bool valid(int g_end) const { return g < g_end; }
-    __device__ __forceinline__ void advance(const GemvBatch &b) { if (++c == b.nchunk) { c = 0; g += NWARPS; } }
-    __device__ __forceinline__ void locate(const GemvBatch &b) { while (g >= b.node[n].g0 + b.node[n].ngroups) n++; }
-};
-
+// Generic path for rows that are not 16-byte multiples / not 16-byte aligned (e.g. K = 4128, byte-offset views): the same
+// math, but every warp stages its own row (or K-chunk of a long row) into shared memory with plain loads.  One group = one
+// weight row; groups are dealt to warps round-robin inside a CTA's contiguous range.
 template <int TYPE, int NC>
 __global__ void __launch_bounds__(NWARPS * 32, 1) k_gemv(const __grid_constant__ GemvBatch b)
 {
@@ -206,47 +202,14 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_gemv(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int xbytes = (NC * b.xcol_bytes + 127) & ~127;
     uint8_t *xs = smem;
-    uint8_t *stages = smem + xbytes + (size_t)warp * b.depth * b.stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + xbytes + (size_t)NWARPS * b.depth * b.stage_bytes) + warp * MAX_DEPTH;
+    uint8_t *stage = smem + xbytes + (size_t)warp * b.stage_bytes;
 
     const int g_begin = (int)((long long)b.total_groups * blockIdx.x / gridDim.x);
     const int g_end = (int)((long long)b.total_groups * (blockIdx.x + 1) / gridDim.x);
 
-    if (b.async && lane == 0) {
-        for (int s = 0; s < b.depth; s++) mbar_init(smem_u32(&bars[s]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp();
-
-    Cursor prod{g_begin + warp, 0, 0};
-    int n_issued = 0;
-    auto issue = [&]() {
-        // all lanes keep the cursor; lane 0 arms the barrier and launches the copy
-        prod.locate(b);
-        const GemvNode &nd = b.node[prod.n];
-        const int row0 = (prod.g - nd.g0) * b.rs;
-        const int rows = min(b.rs, nd.M - row0);
-        const uint32_t bytes = b.nchunk == 1 ? (uint32_t)(rows * b.row_bytes)
-                                             : (uint32_t)min(b.chunk_bytes, b.row_bytes - prod.c * b.chunk_bytes);
-        if (lane == 0) {
-            const int st = n_issued % b.depth;
-            const uint32_t bar = smem_u32(&bars[st]);
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(smem_u32(stages + (size_t)st * b.stage_bytes), nd.W + (long long)row0 * b.nb01 + (long long)prod.c * b.chunk_bytes, bytes, bar);
-        }
-        n_issued++;
-        prod.advance(b);
-    };
-    // Weights do not depend on the preceding kernel: start streaming before the PDL wait.
-    if (b.async)
-        for (int i = 0; i < b.depth && prod.valid(g_end); i++) issue();
-
     asm volatile("griddepcontrol.wait;" ::: "memory");           // activations come from k_act_batch
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
     if (g_begin >= g_end) return;
-    int it = 0;
     int n = 0;
     while (g_begin >= b.node[n].g0 + b.node[n].ngroups) n++;
     for (; n < b.n_nodes && b.node[n].g0 < g_end; n++) {
@@ -261,79 +224,33 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_gemv(const __grid_constant__
         const int seg_lo = max(g_begin, nd.g0), seg_hi = min(g_end, nd.g0 + nd.ngroups);
         int g = seg_lo + ((warp - (seg_lo - g_begin) % NWARPS + NWARPS) % NWARPS);
         for (; g < seg_hi; g += NWARPS) {
-            const int row0 = (g - nd.g0) * b.rs;
-            const int rows = min(b.rs, nd.M - row0);
+            const int row = g - nd.g0;
             float acc[NC];
-            for (int c = 0; c < b.nchunk; c++, it++) {
-                const int st = b.async ? it % b.depth : 0;
-                const uint8_t *stage = stages + (size_t)st * b.stage_bytes;
-                const int nbytes = b.nchunk == 1 ? rows * b.row_bytes : min(b.chunk_bytes, b.row_bytes - c * b.chunk_bytes);
-                if (b.async) {
-                    mbar_wait(smem_u32(&bars[st]), (uint32_t)((it / b.depth) & 1));
-                } else {
-                    // unaligned rows: the warp stages its chunk itself with plain loads
-                    const uint8_t *src = nd.W + (long long)row0 * b.nb01 + (long long)c * b.chunk_bytes;
-                    __syncwarp();
-                    if (b.nchunk == 1) {
-                        for (int r = 0; r < rows; r++) {
-                            const uint8_t *sr = src + (long long)r * b.nb01;
-                            uint8_t *dr = const_cast<uint8_t *>(stage) + r * b.row_bytes;
-                            if (((reinterpret_cast<uintptr_t>(sr) | (uintptr_t)b.row_bytes) & 3) == 0)
-                                for (int i = lane; i < b.row_bytes >> 2; i += 32) reinterpret_cast<uint32_t *>(dr)[i] = reinterpret_cast<const uint32_t *>(sr)[i];
-                            else
-                                for (int i = lane; i < b.row_bytes >> 1; i += 32) reinterpret_cast<uint16_t *>(dr)[i] = reinterpret_cast<const uint16_t *>(sr)[i];
-                        }
-                    } else {
-                        uint8_t *dr = const_cast<uint8_t *>(stage);
-                        if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)nbytes) & 3) == 0)
-                            for (int i = lane; i < nbytes >> 2; i += 32) reinterpret_cast<uint32_t *>(dr)[i] = reinterpret_cast<const uint32_t *>(src)[i];
-                        else
-                            for (int i = lane; i < nbytes >> 1; i += 32) reinterpret_cast<uint16_t *>(dr)[i] = reinterpret_cast<const uint16_t *>(src)[i];
-                    }
-                    __syncwarp();
-                }
-                if (b.nchunk == 1) {
-                    for (int r = 0; r < rows; r++) {
 #pragma unroll
-                        for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
-                        dot_chunk<TYPE, NC>(b, stage + r * b.row_bytes, 0, b.row_bytes, xs, lane, acc);
+            for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
+            for (int c = 0; c < b.nchunk; c++) {
+                const int nbytes = min(b.chunk_bytes, b.row_bytes - c * b.chunk_bytes);
+                const uint8_t *src = nd.W + (long long)row * b.nb01 + (long long)c * b.chunk_bytes;
+                __syncwarp();                                    // previous chunk fully consumed
+                if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)nbytes) & 3) == 0)
+                    for (int i = lane; i < nbytes >> 2; i += 32) reinterpret_cast<uint32_t *>(stage)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+                else
+                    for (int i = lane; i < nbytes >> 1; i += 32) reinterpret_cast<uint16_t *>(stage)[i] = reinterpret_cast<const uint16_t *>(src)[i];
+                __syncwarp();
+                dot_chunk<TYPE, NC>(b, stage, c * b.chunk_bytes, nbytes, xs, lane, acc);
+            }
 #pragma unroll
-                        for (int cc = 0; cc < NC; cc++) {
-                            const float v = warp_sum(acc[cc]);
-                            if (lane == 0) {
-                                float *yp = nd.y + (long long)cc * nd.ldy + row0 + r;
-                                *yp = v;
-                                for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
-                            }
-                        }
-                    }
-                } else {
-                    if (c == 0) {
-#pragma unroll
-                        for (int cc = 0; cc < NC; cc++) acc[cc] = 0.0f;
-                    }
-                    dot_chunk<TYPE, NC>(b, stage, c * b.chunk_bytes, nbytes, xs, lane, acc);
-                    if (c == b.nchunk - 1) {
-#pragma unroll
-                        for (int cc = 0; cc < NC; cc++) {
-                            const float v = warp_sum(acc[cc]);
-                            if (lane == 0) {
-                                float *yp = nd.y + (long long)cc * nd.ldy + row0;
-                                *yp = v;
-                                for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
-                            }
-                        }
-                    }
-                }
-                if (b.async) {
-                    __syncwarp();                                // every lane has finished reading this stage
-                    if (prod.valid(g_end)) issue();
+            for (int cc = 0; cc < NC; cc++) {
+                const float v = warp_sum(acc[cc]);
+                if (lane == 0) {
+                    float *yp = nd.y + (long long)cc * nd.ldy + row;
+                    *yp = v;
+                    for (int p = 0; p < b.n_peers; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + b.peer_delta[p]) = v;
                 }
             }
         }
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // Fast path: rows are whole 16-byte-aligned "units" (Q4_0: 4 blocks = 80 B, Q4_1: 2 blocks = 48 B,
@@ -698,7 +615,7 @@ int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl)
     int grid = gemv_num_ctas();
     // async: groups are tiles and every CTA takes whole tiles; sync: groups are rows, one per warp
     const size_t smem = b.async ? xbytes + (size_t)b.depth * b.stage_bytes + 2 * MAX_DEPTH * 8
-                                : xbytes + (size_t)NWARPS * b.depth * b.stage_bytes + NWARPS * MAX_DEPTH * 8;
+                                : xbytes + (size_t)NWARPS * b.stage_bytes;
     const int want = b.async ? b.total_groups : (b.total_groups + NWARPS - 1) / NWARPS;
     if (grid > want) grid = want;
     if (b.async) switch (b.type) {

@@ -74,3 +74,42 @@ def test_f32_weights_batched_stay_on_ffma_path():
     wb = orc.encode_weights(N.F32, W)
     got = dev_mul_mat(N.F32, wb, M, K, X)
     assert rel_l2(got, orc.mul_mat_2d(N.F32, wb, M, K, X)) <= 2e-6
+
+
+def test_graph_compute_routes_prompt_batches_to_the_tensor_core_path():
+    # through the reference-shaped API: ggml_mul_mat with N = 48 columns, two dependent levels (y2 = W2 . y1)
+    import ctypes as C
+    from ggmlsharp_b200 import ggml
+    rng = np.random.default_rng(77)
+    K, M1, M2, Nn = 512, 384, 256, 48
+    W1, W2 = weights(rng, M1, K), weights(rng, M2, M1, "uniform")
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    w1b, w2b = orc.encode_weights(N.Q4_0, W1), orc.encode_weights(N.F16, W2)
+    with ggml.Context(32 << 20) as c:
+        a1, a2 = c.tensor_from(N.Q4_0, K, M1, data=w1b), c.tensor_from(N.F16, M1, M2, data=w2b)
+        b = c.tensor_from(N.F32, K, Nn, data=X)
+        y1 = c.mul_mat(a1, b)
+        y2 = c.mul_mat(a2, y1)
+        g = c.build_forward(y2)
+        N.lib().ggb_reset_stats()
+        c.graph_compute(g)
+        assert N.stats().kernel_launches == 5          # 2 x (activation + GEMM) + 1 result-copy kernel... or memcpy for large results
+        g1, g2 = ggml.tensor_f32(y1).reshape(Nn, M1).copy(), ggml.tensor_f32(y2).reshape(Nn, M2).copy()
+    assert rel_l2(g1, orc.mul_mat_2d(orc.Q4_0, w1b, M1, K, X, nth=8)) <= 1e-3
+    assert rel_l2(g2, orc.mul_mat_2d(orc.F16, w2b, M2, M1, g1, nth=8)) <= 1e-4
+
+
+def test_kernel_timing_brackets_only_the_mul_mat_kernels():
+    L = N.lib()
+    rng = np.random.default_rng(78)
+    W = weights(rng, 256, 512)
+    wb = orc.encode_weights(N.Q4_0, W)
+    L.ggb_reset_stats()
+    N.check(L.ggb_set_kernel_timing(1))
+    try:
+        dev_mul_mat(N.Q4_0, wb, 256, 512, rng.standard_normal((1, 512)).astype(np.float32))      # GEMV
+        dev_mul_mat(N.Q4_0, wb, 256, 512, rng.standard_normal((32, 512)).astype(np.float32))     # GEMM
+        s = N.stats()
+    finally:
+        N.check(L.ggb_set_kernel_timing(0))
+    assert s.kernel_launches == 4 and s.timed_kernel_launches == 2 and 0.0 < s.timed_kernel_ms < 5.0

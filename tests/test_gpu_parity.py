@@ -414,3 +414,19 @@ def test_stats_count_launches():
     dev_mul_mat(N.Q4_0, orc.encode_weights(N.Q4_0, W), 64, 128, rng.standard_normal((1, 128)).astype(np.float32))
     s = N.stats()
     assert s.kernel_launches == 2            # activation quantize + fused GEMV
+
+
+def test_peer_exchange_degenerates_cleanly_on_one_rank():
+    # world = 1: ggb_peer_push_barrier copies nothing and the flag barrier completes on its own flags (epoch from device memory)
+    from ggmlsharp_b200 import rowsplit
+    sym = rowsplit.SymmetricBuffer(4096, 0, 1, lambda h: [h])
+    try:
+        for _ in range(3):
+            sym.push_barrier(None, 0, 1024, 2048, 2)
+            sym.barrier(None)
+        N.check(N.lib().ggb_stream_sync(None))
+        flags = np.zeros(32, dtype=np.uint64)
+        N.check(N.lib().ggb_dev_download(flags.ctypes.data, sym.base, 256))
+        assert flags[0] == 3                     # the last writer was barrier() with host epoch 3; push_barrier used device epochs 1..3
+    finally:
+        sym.close()
