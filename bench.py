@@ -130,10 +130,15 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     nth = os.cpu_count() or 1
-    sample_nodes = int(os.environ.get("GGB_BENCH_REF_RING", RING))        # one step = the whole ring: ~0.5 s single-threaded (tests shrink it)
-    nodes = host_ring(sample_nodes, M_LOCAL * world)
+    ring = int(os.environ.get("GGB_BENCH_REF_RING", RING))        # tests shrink it
+    nodes = host_ring(ring, M_LOCAL * world)
+    # bounded sample: as many ring nodes per step as keep the whole --steps/--warmup run within ~2 minutes of CPU time
+    t_node = cpu_mul_mat_ring(nodes[:1], nth, repeats=2)
+    budget = 120.0 / max(args.steps + args.warmup, 1)
+    sample_nodes = int(max(1, min(ring, budget / max(t_node, 1e-6))))
+    nodes = nodes[:sample_nodes]
     for _ in range(args.warmup):
-        cpu_mul_mat_ring(nodes[:4], nth)
+        cpu_mul_mat_ring(nodes, nth)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_mul_mat_ring(nodes, nth)
@@ -145,7 +150,7 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "int8 dot (Q4_0 x Q8_0), f32 scales", "data": "synthetic",
             "config": {"workload": "configs[1]: Q4_0 4096x4096 GEMV, single token; ring of %d distinct matrices (%d rows each)" % (len(nodes), M_LOCAL * world)},
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": nth, "kind": "port",
-                             "sample": "full ring of %d GEMVs per step; C restatement of ggml_compute_forward_mul_mat_q_f32 (not .NET RyuJIT)" % len(nodes)},
+                             "sample": "%d of the %d ring GEMVs per step (bounded to ~2 min total); C restatement of ggml_compute_forward_mul_mat_q_f32 with %d threads (not .NET RyuJIT)" % (len(nodes), ring, nth)},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
