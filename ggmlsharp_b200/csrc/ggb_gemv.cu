@@ -473,6 +473,11 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_gemv_fast(const __grid_co
                     }
                 }
             }
+            // Release the stage only after its bytes have been CONSUMED: the accumulators are named as inputs of an (empty) asm
+            // so the compiler cannot sink the dot-product math below the arrive; in-order issue then guarantees every LDS of
+            // this stage has returned before the barrier is signalled (the same WAR hazard bit the GEMM, profiles/README.md).
+#pragma unroll
+            for (int cc = 0; cc < NC; cc++) asm volatile("" ::"f"(acc[cc]) : "memory");
             __syncwarp();                                        // every lane has finished reading this stage
             if (lane == 0) mbar_arrive(empty0 + 8 * st);
             if (++st == depth) { st = 0; ph ^= 1; }

@@ -225,8 +225,10 @@ typedef struct ggb_stats {
     double   timed_kernel_ms;      /* with ggb_set_kernel_timing(1): summed CUDA-event time of the GEMV / GEMM launches only */
     uint64_t timed_kernel_launches;
 } ggb_stats;
-/* Measurement aid for the roofline: bracket every mul_mat kernel launch (not the activation staging) with CUDA events on
- * the launching stream.  The brackets defeat the programmatic-dependent-launch overlap, so leave it off when timing steps. */
+/* Measurement aid for the roofline.  1: bracket every mul_mat kernel launch (not the activation staging) with CUDA events on
+ * the launching stream -- the brackets defeat the programmatic-dependent-launch overlap, so leave it off when timing steps.
+ * 2: additionally skip the activation staging of single-token nodes and reuse what the previous identical call left in the
+ * workspace, so that a stream of calls is a stream of the GEMV kernel alone (time it with your own events). 0: off. */
 int  ggb_set_kernel_timing(int on);
 int  ggb_get_stats(ggb_stats *out);
 int  ggb_reset_stats(void);
