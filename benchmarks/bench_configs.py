@@ -113,6 +113,37 @@ def main():
         print(json.dumps({"config": "cfg1 quantize_row_q4_0 over 4096x4096 F32 (bit-exact kernel)", "ms": ms, "GB/s": by / ms / 1e6,
                           "frac_of_measured_hbm": by / ms / 1e6 / hbm}), flush=True)
         del src, dst
+    if want("codecs"):
+        # the codec column on its own: 4 B read + 0.625 / 0.75 B written per element (quantize), the reverse (dequantize);
+        # sources cycle through > 2x L2 of distinct data
+        for rows in (4096, 11008):
+            nsrc = max(2, (300 << 20) // (rows * 4096 * 4) + 1)
+            src = torch.randn((nsrc, rows, 4096), device=dev) * 0.02
+            for t in (N.Q4_0, N.Q4_1):
+                rb = 4096 // 32 * N.TYPE_SIZE[t]
+                dst = torch.empty((nsrc, rows, rb), dtype=torch.uint8, device=dev)
+                it = [0]
+
+                def q():
+                    N.check(L.ggb_dev_quantize_rows(t, src[it[0] % nsrc].data_ptr(), dst[it[0] % nsrc].data_ptr(), rows, 4096, sp))
+                    it[0] += 1
+                ms = time_calls(q, a.iters)
+                by = rows * 4096 * 4 + rows * rb
+                print(json.dumps({"config": "quantize_row_%s over %dx4096 F32" % (TN[t], rows), "ms": ms, "GB/s": by / ms / 1e6,
+                                  "frac_of_measured_hbm": by / ms / 1e6 / hbm}), flush=True)
+                for _ in range(nsrc):
+                    q()                                                                # every dst slot holds valid blocks
+                back = torch.empty((nsrc, rows, 4096), device=dev)
+
+                def dq():
+                    N.check(L.ggb_dev_dequantize_rows(t, dst[it[0] % nsrc].data_ptr(), back[it[0] % nsrc].data_ptr(), rows, 4096, sp))
+                    it[0] += 1
+                ms = time_calls(dq, a.iters)
+                print(json.dumps({"config": "dequantize_row_%s over %dx4096" % (TN[t], rows), "ms": ms, "GB/s": by / ms / 1e6,
+                                  "frac_of_measured_hbm": by / ms / 1e6 / hbm}), flush=True)
+                del dst, back
+            del src
+            torch.cuda.empty_cache()
     if want("cfg2"):
         for t in (N.Q4_1, N.F16):
             n_ring = 10 if t == N.Q4_1 else 4

@@ -10,6 +10,7 @@
 #include "ggb_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ggb {
 
@@ -130,9 +131,14 @@ __global__ void __launch_bounds__(256) k_quantize_rows(const float *__restrict__
 
 // Weight quantizers, one thread per block of 32 (128 B in, 20 / 24 B out): the first-max and min/max scans run in the
 // reference's element order, entirely in registers; eight 128-bit loads per thread are in flight at once.
+// This is the EXACT path: every corner of the reference's evaluation order (NaN skipping, +-0 ties, .NET cast semantics
+// for overflowed 1/d).  The fast path below handles ordinary blocks and hands anything unusual to it.
 template <int TYPE>
-__device__ __forceinline__ void quantize_block_q4(const float (&e)[32], uint32_t *out)
+__device__ __noinline__ void quantize_block_q4(const float4 *__restrict__ p, uint32_t *out)
 {
+    float e[32];                                               // reloaded (L1-hot) so the caller keeps no stack frame
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const float4 v = __ldg(p + i); e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w; }
     uint32_t w[4];
     if (TYPE == GGML_TYPE_Q4_0) {
         float amax = 0.0f, mx = 0.0f;                          // Ggml.cs:343-354: strict <, the first maximum wins
@@ -153,9 +159,9 @@ __device__ __forceinline__ void quantize_block_q4(const float (&e)[32], uint32_t
         out[0] = __float_as_uint(d);
         out[1] = w[0]; out[2] = w[1]; out[3] = w[2]; out[4] = w[3];
     } else {
-        float mn = e[0], mx = e[0];                            // Ggml.cs:496-504 (equal values keep the earlier element)
+        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;  // Ggml.cs:494-504: FLT_MAX / -FLT_MAX, equal values keep the earlier element, NaN never wins
 #pragma unroll
-        for (int i = 1; i < 32; i++) { if (e[i] < mn) mn = e[i]; if (e[i] > mx) mx = e[i]; }
+        for (int i = 0; i < 32; i++) { if (e[i] < mn) mn = e[i]; if (e[i] > mx) mx = e[i]; }
         const float d = __fdiv_rn(__fsub_rn(mx, mn), 15.0f);
         const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
 #pragma unroll
@@ -173,21 +179,140 @@ __device__ __forceinline__ void quantize_block_q4(const float (&e)[32], uint32_t
     }
 }
 
+// Fast path for ordinary blocks.  rintf + float->int conversion run on the quarter-rate XU pipe (two per element made the
+// first version of this kernel conversion-bound at 3.4 TB/s), so rounding is done on the FP32 pipe instead: for |t| < 2^22,
+// t + 1.5*2^23 (round-to-nearest-even add) IS Math.Round(t), and the integer sits in the low mantissa bits.  Nibbles are
+// packed by shifted integer adds of the raw float bits; the eight 0x4B400000 biases of a word come off as one constant.
+// Everything the trick cannot represent -- NaN / infinite inputs, an overflowed 1/d, a |max| tie between a positive and a
+// negative element (the reference takes the first), all-zero blocks (d = -0.0f), a +-0 minimum or maximum (sign of m) -- is
+// detected from the OR of the biased bit patterns or two compares and handed to the exact path: returns false.
+constexpr float Q_MAGIC = 12582912.0f;                          // 1.5 * 2^23
+constexpr uint32_t Q_MAGIC_BITS = 0x4B400000u;
+constexpr uint32_t q_pack_bias(uint32_t per_nibble) { uint32_t s = 0; for (int i = 0; i < 8; i++) s += per_nibble << (4 * i); return s; }
+
 template <int TYPE>
-__global__ void __launch_bounds__(256) k_quantize_q4_rows(const float *__restrict__ x, long long ldx, uint8_t *__restrict__ y,
-                                                          long long nblk, int kb)
+__device__ __forceinline__ bool quantize_block_q4_fast(const float (&e)[32], uint32_t *out)
 {
-    // (A variant that staged loads and stores through shared memory for fully coalesced 128-bit global accesses measured
-    //  slower -- 2.9 vs 3.4 TB/s on 4096x4096 -- the kernel is latency-, not transaction-bound; profiles/README.md.)
-    for (long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
-        const long long row = blk / kb;
-        const int col = (int)(blk - row * kb);
-        const float4 *p = reinterpret_cast<const float4 *>(x + row * ldx + (long long)col * GGB_QK);
-        float e[32];
+    float smax = e[0], smin = e[0];                              // fmaxf / fminf skip NaN exactly like `amax < |v|` does
 #pragma unroll
-        for (int i = 0; i < 8; i++) { const float4 v = __ldg(p + i); e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w; }
-        quantize_block_q4<TYPE>(e, reinterpret_cast<uint32_t *>(y + blk * (TYPE == GGML_TYPE_Q4_0 ? 20 : 24)));
+    for (int i = 1; i < 32; i++) { smax = fmaxf(smax, e[i]); smin = fminf(smin, e[i]); }
+    uint32_t w[4], seen = 0;
+    if (TYPE == GGML_TYPE_Q4_0) {
+        const float amax = fmaxf(smax, -smin);
+        const bool pos = smax == amax, neg = -smin == amax;
+        if (pos == neg) return false;                            // +a and -a both present (order decides), all zero, or NaN block
+        const float d = __fdiv_rn(pos ? amax : -amax, -8.0f);
+        const float id = __fdiv_rn(1.0f, d);                     // d != 0 here
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const float u = __fadd_rn(__fmul_rn(e[8 * j + b], id), Q_MAGIC);        // Round(x*id) + bias
+                seen |= __float_as_uint(u);
+                acc += __float_as_uint(fminf(u, Q_MAGIC + 7.0f)) << (4 * b);            // Math.Min(15, . + 8)
+            }
+            w[j] = acc - q_pack_bias(Q_MAGIC_BITS - 8u);
+        }
+        if (seen & 0x30000000u) return false;                    // some |x*id| was not a small finite number
+        out[0] = __float_as_uint(d);
+        out[1] = w[0]; out[2] = w[1]; out[3] = w[2]; out[4] = w[3];
+    } else {
+        if (smin == 0.0f || smax == 0.0f || !(smin < smax)) return false;   // sign of a zero min/max depends on element order; d == 0; NaN
+        const float d = __fdiv_rn(__fsub_rn(smax, smin), 15.0f);
+        if (d == 0.0f) return false;
+        const float id = __fdiv_rn(1.0f, d);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const float u = __fadd_rn(__fmul_rn(__fsub_rn(e[8 * j + b], smin), id), Q_MAGIC);
+                seen |= __float_as_uint(u);
+                acc += __float_as_uint(u) << (4 * b);
+            }
+            w[j] = acc - q_pack_bias(Q_MAGIC_BITS);
+        }
+        if ((seen & 0xFFFFFFF0u) != Q_MAGIC_BITS) return false;  // a quant outside 0..15 (or NaN / inf): exact path, (byte) cast semantics
+        out[0] = __float_as_uint(d); out[1] = __float_as_uint(smin);
+        out[2] = w[0]; out[3] = w[1]; out[4] = w[2]; out[5] = w[3];
     }
+    return true;
+}
+
+// Data movement (profiles/README.md, round-1 codec captures): with one thread per block and direct 128-bit loads, a warp
+// load instruction touches 32 different 128-byte lines and the kernel stalled on memory at ~57-67 % of the copy peak.
+// So each WARP runs its own cp.async pipeline: a tile is 32 blocks = 4 KB of contiguous source, fetched by eight fully
+// coalesced 16-byte-per-lane async copies into shared rows padded to 144 B; lane l then reads block l with eight LDS.128
+// (row stride 36 words: conflict-free) while the next two tiles are already in flight.  No CTA-wide barrier anywhere.  The
+// 20 / 24-byte outputs go through a small shared staging row so the warp stores 640 / 768 contiguous bytes.
+constexpr int QT_WARPS = 4, QT_STAGES = 3, QT_ROW = 144;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(QT_WARPS * 32) k_quantize_q4_tiles(const float *__restrict__ x, long long ldx, uint8_t *__restrict__ y,
+                                                                     long long nblk, int kb, int exact_only)
+{
+    constexpr int BS = TYPE == GGML_TYPE_Q4_0 ? 20 : 24, OW = BS / 4;
+    extern __shared__ uint4 qt_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(qt_smem) + (size_t)warp * (QT_STAGES * 32 * QT_ROW + 32 * BS);
+    const uint32_t in0 = (uint32_t)__cvta_generic_to_shared(wbase);
+    uint32_t *ostage = reinterpret_cast<uint32_t *>(wbase + QT_STAGES * 32 * QT_ROW);
+    const long long ntiles = (nblk + 31) >> 5;
+    const long long gw = (long long)blockIdx.x * QT_WARPS + warp, nw = (long long)gridDim.x * QT_WARPS;
+    const bool dense = ldx == (long long)kb * GGB_QK;
+    const int sub = lane & 7, g = lane >> 3;
+
+    auto src_of = [&](long long blk) -> const float * {
+        if (dense) return x + blk * GGB_QK;
+        const long long row = blk / kb;
+        return x + row * ldx + (blk - row * kb) * GGB_QK;
+    };
+    auto issue = [&](long long tile, int stage) {
+        if (tile < ntiles) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const long long blk = tile * 32 + i * 4 + g;
+                if (blk < nblk) cp_async16(in0 + (uint32_t)(stage * 32 * QT_ROW + (i * 4 + g) * QT_ROW + sub * 16), src_of(blk) + sub * 4);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");     // always commit so the group count stays uniform
+    };
+
+    issue(gw, 0);
+    issue(gw + nw, 1);
+    int stage = 0;
+    for (long long tile = gw; tile < ntiles; tile += nw) {
+        issue(tile + 2 * nw, stage == 0 ? 2 : stage - 1);       // the stage consumed in the previous iteration
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
+        const long long blk = tile * 32 + lane;
+        float e[32];
+        const uint4 *row = reinterpret_cast<const uint4 *>(wbase + stage * 32 * QT_ROW + lane * QT_ROW);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint4 v = row[i];
+            e[4 * i] = __uint_as_float(v.x); e[4 * i + 1] = __uint_as_float(v.y); e[4 * i + 2] = __uint_as_float(v.z); e[4 * i + 3] = __uint_as_float(v.w);
+        }
+        uint32_t *o = ostage + lane * OW;
+        if (blk < nblk) {
+            if (exact_only || !quantize_block_q4_fast<TYPE>(e, o)) quantize_block_q4<TYPE>(reinterpret_cast<const float4 *>(src_of(blk)), o);
+        }
+        __syncwarp();
+        // 32 blocks x OW words, contiguous in y: lane-contiguous 4-byte stores
+        const long long nvalid = nblk - tile * 32 < 32 ? nblk - tile * 32 : 32;
+        uint32_t *yo = reinterpret_cast<uint32_t *>(y + tile * 32 * BS);
+#pragma unroll
+        for (int j = 0; j < OW; j++) { const int wi = j * 32 + lane; if (wi < nvalid * OW) yo[wi] = ostage[wi]; }
+        __syncwarp();                                            // ostage and this input stage are free again
+        stage = stage == QT_STAGES - 1 ? 0 : stage + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256) k_f32_to_f16_rows(const float *__restrict__ x, long long ldx, __half *__restrict__ y,
@@ -199,29 +324,44 @@ __global__ void __launch_bounds__(256) k_f32_to_f16_rows(const float *__restrict
     y[i] = __float2half_rn(x[r * ldx + c]);                     // (Half)float, Ggml.cs:6370
 }
 
-// Ggml.cs:886-910 (Q4_0) and 962-987 (Q4_1): one thread per nibble byte -> two floats
+// Ggml.cs:886-910 (Q4_0) and 962-987 (Q4_1).  One thread per 16 output bytes: lane sub = t & 7 of a block expands nibble
+// bytes 2*sub, 2*sub+1 into one float4, so a warp store is 512 contiguous bytes; the (tiny) scale and 2-byte nibble loads of
+// four independent slices are issued before any of them is used (the first version -- one dependent load pair per thread
+// and 32 768 small CTAs -- sat at 41 % of the copy peak, 76 % of its stall samples on memory).
 template <int TYPE>
 __global__ void __launch_bounds__(256) k_dequantize_rows(const uint8_t *__restrict__ x, float *__restrict__ y, long long nblk)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long blk = t >> 4;
-    const int j = (int)(t & 15);
-    if (blk >= nblk) return;
-    constexpr int BS = TYPE == GGML_TYPE_Q4_0 ? 20 : 24;
-    const uint8_t *b = x + blk * BS;
-    const float d = *reinterpret_cast<const float *>(b);
-    float2 o;
-    if (TYPE == GGML_TYPE_Q4_0) {
-        const uint8_t vi = b[4 + j];
-        o.x = __fmul_rn((float)((int)(vi & 0x0F) - 8), d);
-        o.y = __fmul_rn((float)((int)(vi >> 4) - 8), d);
-    } else {
-        const float m = *reinterpret_cast<const float *>(b + 4);
-        const uint8_t vi = b[8 + j];
-        o.x = __fadd_rn(__fmul_rn((float)(vi & 0x0F), d), m);   // product rounded, then sum rounded
-        o.y = __fadd_rn(__fmul_rn((float)(vi >> 4), d), m);
+    constexpr int BS = TYPE == GGML_TYPE_Q4_0 ? 20 : 24, QOFF = TYPE == GGML_TYPE_Q4_0 ? 4 : 8, U = 4;
+    const long long total = nblk * 8;
+    for (long long base = (long long)blockIdx.x * (256 * U) + threadIdx.x; base < total; base += (long long)gridDim.x * (256 * U)) {
+        float d[U], m[U]; uint32_t q[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long t = base + u * 256;
+            d[u] = 0.f; m[u] = 0.f; q[u] = 0;
+            if (t < total) {
+                const uint8_t *b = x + (t >> 3) * BS;
+                d[u] = __ldg(reinterpret_cast<const float *>(b));
+                if (TYPE == GGML_TYPE_Q4_1) m[u] = __ldg(reinterpret_cast<const float *>(b + 4));
+                q[u] = __ldg(reinterpret_cast<const unsigned short *>(b + QOFF + 2 * (int)(t & 7)));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long t = base + u * 256;
+            if (t >= total) continue;
+            const int n0 = q[u] & 15, n1 = (q[u] >> 4) & 15, n2 = (q[u] >> 8) & 15, n3 = q[u] >> 12;
+            float4 o;
+            if (TYPE == GGML_TYPE_Q4_0) {
+                o.x = __fmul_rn((float)(n0 - 8), d[u]); o.y = __fmul_rn((float)(n1 - 8), d[u]);
+                o.z = __fmul_rn((float)(n2 - 8), d[u]); o.w = __fmul_rn((float)(n3 - 8), d[u]);
+            } else {                                             // product rounded, then sum rounded (two roundings)
+                o.x = __fadd_rn(__fmul_rn((float)n0, d[u]), m[u]); o.y = __fadd_rn(__fmul_rn((float)n1, d[u]), m[u]);
+                o.z = __fadd_rn(__fmul_rn((float)n2, d[u]), m[u]); o.w = __fadd_rn(__fmul_rn((float)n3, d[u]), m[u]);
+            }
+            reinterpret_cast<float4 *>(y)[t] = o;
+        }
     }
-    reinterpret_cast<float2 *>(y)[t] = o;
 }
 
 // ---- activation staging for mul_mat (the reference's INIT phase) ----
@@ -384,10 +524,23 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
     const long long nblk = nrows * kb;
     const unsigned grid = (unsigned)((nblk * 8 + 255) / 256);
     uint8_t *y = (uint8_t *)dst;
-    const unsigned grid4 = (unsigned)std::min<long long>((nblk + 255) / 256, (long long)device_sm_count() * 16);
+    static const int exact_only = getenv("GGB200_QUANT_EXACT") ? 1 : 0;      // testing: force the exact path for every block
     switch (type) {
-    case GGML_TYPE_Q4_0: k_quantize_q4_rows<GGML_TYPE_Q4_0><<<grid4, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
-    case GGML_TYPE_Q4_1: k_quantize_q4_rows<GGML_TYPE_Q4_1><<<grid4, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
+    case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_1: {
+        const int bs = type == GGML_TYPE_Q4_0 ? 20 : 24;
+        const size_t smem = (size_t)QT_WARPS * (QT_STAGES * 32 * QT_ROW + 32 * bs);
+        static bool attr_set = false;
+        if (!attr_set) {
+            GGB_CUDA(cudaFuncSetAttribute(k_quantize_q4_tiles<GGML_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QT_WARPS * (QT_STAGES * 32 * QT_ROW + 32 * 20))));
+            GGB_CUDA(cudaFuncSetAttribute(k_quantize_q4_tiles<GGML_TYPE_Q4_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QT_WARPS * (QT_STAGES * 32 * QT_ROW + 32 * 24))));
+            attr_set = true;
+        }
+        const long long ntiles = (nblk + 31) / 32;
+        const unsigned gridt = (unsigned)std::min<long long>((ntiles + QT_WARPS - 1) / QT_WARPS, (long long)device_sm_count() * 3);
+        if (type == GGML_TYPE_Q4_0) k_quantize_q4_tiles<GGML_TYPE_Q4_0><<<gridt, QT_WARPS * 32, smem, s>>>(src, ldx, y, nblk, kb, exact_only);
+        else k_quantize_q4_tiles<GGML_TYPE_Q4_1><<<gridt, QT_WARPS * 32, smem, s>>>(src, ldx, y, nblk, kb, exact_only);
+        break;
+    }
     case GGML_TYPE_Q8_0: k_quantize_rows<GGML_TYPE_Q8_0><<<grid, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
     case GGML_TYPE_Q8_1: k_quantize_rows<GGML_TYPE_Q8_1><<<grid, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
     default: return set_error(GGB_E_UNSUPPORTED, "quantize: type %d has no codec on this path", type);
@@ -401,7 +554,7 @@ int launch_dequantize_rows(int type, const void *src, float *dst, int64_t nrows,
     if (nrows <= 0 || k <= 0) return GGB_OK;
     if (k % GGB_QK) return set_error(GGB_E_INVALID, "dequantize: k=%lld is not a multiple of %d (Ggml.cs:839)", (long long)k, GGB_QK);
     const long long nblk = nrows * (k / GGB_QK);
-    const unsigned grid = (unsigned)((nblk * 16 + 255) / 256);
+    const unsigned grid = (unsigned)std::min<long long>((nblk * 8 + 1023) / 1024, (long long)device_sm_count() * 8);
     if (type == GGML_TYPE_Q4_0) k_dequantize_rows<GGML_TYPE_Q4_0><<<grid, 256, 0, s>>>((const uint8_t *)src, dst, nblk);
     else if (type == GGML_TYPE_Q4_1) k_dequantize_rows<GGML_TYPE_Q4_1><<<grid, 256, 0, s>>>((const uint8_t *)src, dst, nblk);
     else return set_error(GGB_E_UNSUPPORTED, "dequantize: type %d has no codec on this path", type);
