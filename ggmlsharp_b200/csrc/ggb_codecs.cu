@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
         const int blk = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
         const bool live = blk < b.total_blk;
         int n = 0;
-        if (live) while (n + 1 < b.n_nodes && blk >= b.node[n + 1].blk0) n++;
+        if (live) { int hi = b.n_nodes - 1; while (n < hi) { const int mid = (n + hi + 1) >> 1; if (blk >= b.node[mid].blk0) n = mid; else hi = mid - 1; } }   // last node with blk0 <= blk
         const ActNode &nd = b.node[n];
         const int local = live ? blk - nd.blk0 : 0;
         const int row = local / b.kb, col = local - row * b.kb;
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
         if (t < total) {
             const int grow = (int)(t / q4), c4 = (int)(t - (long long)grow * q4);
             int n = 0;
-            while (n + 1 < b.n_nodes && grow >= b.node[n + 1].blk0) n++;
+            { int hi = b.n_nodes - 1; while (n < hi) { const int mid = (n + hi + 1) >> 1; if (grow >= b.node[mid].blk0) n = mid; else hi = mid - 1; } }
             const ActNode &nd = b.node[n];
             const int row = grow - nd.blk0;
             const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(nd.x) + (long long)row * nd.ldx_bytes) + c4 * 4;
@@ -443,11 +443,13 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
 // Rows n >= N of the padded buffer are zero.  One thread per block of 32 elements (128 B in, 64 B out): the kernel is
 // a pure stream (12 B per element), so everything is kept in registers and the K permutation 0,4,1,5,2,6,3,7 that the
 // GEMM's nibble unpack produces costs nothing.
-__global__ void __launch_bounds__(256) k_act_f16_dequant(int wtype, int perm, const float *__restrict__ x, long long ldx_bytes,
-                                                         __half *__restrict__ out, int N, int Npad, int K, int vec16, int wait_prior)
+__global__ void __launch_bounds__(256) k_act_f16_dequant(const __grid_constant__ ActGemmBatch b)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the GEMM's prologue and weight streaming may start now
-    if (wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory"); // x may be the previous kernel's output (first node of a batch only)
+    if (b.wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory"); // x may be the previous kernel's output (first launch of a batch only)
+    const ActGemmNode &nd = b.node[blockIdx.y];
+    const int wtype = b.wtype, perm = b.perm, N = nd.N, Npad = nd.Npad, K = nd.K, vec16 = nd.vec16;
+    const float *__restrict__ x = nd.x; const long long ldx_bytes = nd.ldx_bytes; __half *__restrict__ out = nd.out;
     const int kb = K / GGB_QK;
     const long long nblk = (long long)Npad * kb;
     for (long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
@@ -496,6 +498,10 @@ __global__ void __launch_bounds__(256) k_act_f16_dequant(int wtype, int perm, co
 #pragma unroll
         for (int i = 0; i < 4; i++) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
     }
+    // Completion must be transitive along the stream: kernels of one batch are launched programmatically dependent on their
+    // predecessor only, so this kernel does not COMPLETE before everything ahead of it in the stream has (a consumer that
+    // waits for the last kernel of the batch then sees every node's dst).  Costs nothing: the work above is already done.
+    if (!b.wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 } // namespace
@@ -581,25 +587,38 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
     return GGB_OK;
 }
 
-int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior)
+int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s)
 {
-    const long long nblk = Npad * (K / GGB_QK);
-    if (nblk <= 0) return GGB_OK;
-    const int vec16 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx_bytes & 15) == 0) ? 1 : 0;
-    long long grid = (nblk + 255) / 256;
-    const long long cap = (long long)device_sm_count() * 8;
+    if (b.n_nodes <= 0) return GGB_OK;
+    long long maxblk = 0;
+    for (int i = 0; i < b.n_nodes; i++) {
+        ActGemmNode &nd = b.node[i];
+        nd.vec16 = ((reinterpret_cast<uintptr_t>(nd.x) & 15) == 0 && (nd.ldx_bytes & 15) == 0) ? 1 : 0;
+        maxblk = std::max(maxblk, (long long)nd.Npad * (nd.K / GGB_QK));
+    }
+    if (maxblk <= 0) return GGB_OK;
+    long long grid = (maxblk + 255) / 256;
+    const long long cap = std::max<long long>(1, (long long)device_sm_count() * 8 / b.n_nodes);
     if (grid > cap) grid = cap;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
+    cfg.gridDim = dim3((unsigned)grid, (unsigned)b.n_nodes);
     cfg.blockDim = dim3(256);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant, wtype, perm, x, (long long)ldx_bytes, out, (int)N, (int)Npad, (int)K, vec16, wait_prior ? 1 : 0));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant, b));
     count_launch();
     return GGB_OK;
+}
+
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior)
+{
+    static thread_local ActGemmBatch b;
+    b.n_nodes = 1; b.wtype = wtype; b.perm = perm; b.wait_prior = wait_prior ? 1 : 0;
+    b.node[0] = ActGemmNode{x, (long long)ldx_bytes, out, (int)N, (int)Npad, (int)K, 0};
+    return launch_act_f16_dequant_batch(b, s);
 }
 
 } // namespace ggb

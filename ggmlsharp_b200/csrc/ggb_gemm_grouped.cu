@@ -1,0 +1,487 @@
+// Batched (N >= 16) mul_mat over a whole GROUP of independent nodes in one launch: persistent CTA pairs walk the 256 x 128
+// output tiles of up to GGB_GEMM_GROUP_NODES Q4_0 / Q4_1 / F16 nodes (ggml_compute_forward_mul_mat_q_f32 / _f16_f32,
+// Ggml.cs:6440-6712, 6180-6438).
+//
+// Why (profiles/README.md, round-1 GEMM notes): the per-node kernel k_gemm_q spends ~550 cycles per 128-wide K step against a
+// 512-cycle tensor-pipe floor, but around that mainloop every launch pays ~3 k cycles of prologue (barrier init, TMEM
+// allocation, descriptor fetch, first TMA round trip), a launch gap, and -- worst -- whatever part of the machine the node's
+// own tile count leaves idle: 4096 x 512 gives 64 pair-tiles for 74 SM pairs, a row-split shard of it on 8 GPUs gives 8.  A
+// graph level of MUL_MAT nodes is independent work, so here the tile list of ALL its nodes is dealt round-robin to the
+// resident pairs: the pipeline (TMA rings, TMEM A stages, barrier phases) keeps running across tile and node boundaries,
+// and the TMA producers prefetch the next tile's operands while the 16 dequant warps drain the accumulators of the
+// current one.
+//
+// Tile = one CTA pair (tcgen05 cta_group::2): 256 weight rows x 128 activation rows, K step 128.  Warp roles, TMEM layout,
+// the nibble -> fp16 -> tcgen05.st A path and the even/odd dual MMA issuers are those of k_gemm_q (ggb_gemm.cu); what is
+// new is the tile loop, the running K-step counter that indexes every ring, and the ACC_EMPTY barrier that lets the issuers
+// overwrite the accumulators only after both CTAs have read them.
+#include "ggb_tc.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+namespace ggb {
+
+namespace {
+
+using namespace tc;
+
+struct alignas(64) GroupNode {
+    CUtensorMap map_w, map_x;      // raw quant bytes [M][row_bytes] (box 128 rows x 4 blocks); fp16 activations [Npad][K] (box 64 x 64, swizzle-128B)
+    float *Y; long long ldy;       // dst, row stride in floats
+    int M, N, ksteps;
+    int tile0, tile_end, nt;       // this node's tiles in the launch are [tile0, tile_end); nt = tiles along the activation rows
+    int n_peers, pad_;
+    long long peer_delta[7];       // row split: byte offset from Y to the same element of peer p's dst (CUDA-IPC mapped)
+};
+struct alignas(64) GemmGroup { int n_nodes, total_tiles; int pad_[14]; GroupNode node[GGB_GEMM_GROUP_NODES]; };
+static_assert(sizeof(GemmGroup) <= 32000, "kernel parameter space");
+
+template <int TYPE>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_constant__ GemmGroup G)
+{
+    constexpr int BN = 128, BNL = 64;
+    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int RAW_BYTES = BM * RAW_ROW, B_BYTES = BNL * BK * 2;
+    constexpr int RAW_STAGES = 8, A_STAGES = 4;               // raw ring: a multiple of the 4 dequant groups (see ggb_gemm.cu)
+    constexpr int TMEM_COLS = 512, A_COL0 = 2 * BN;           // [0,128) even-K acc, [128,256) odd-K acc, then 4 x 64 columns of A stages
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem;
+    uint8_t *sRaw = sB + A_STAGES * B_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sRaw + RAW_STAGES * RAW_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    constexpr int RAW_FULL = 0, RAW_EMPTY = 8, A_FULL = 16, A_EMPTY = 20, ACC_FULL = 24, ACC_EMPTY = 25, NBARS = 26;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
+    auto BAR = [&](int i) { return bar0 + 8 * i; };
+    auto LBAR = [&](int i) { return mapa_u32(BAR(i), 0); };   // the same barrier in the leader CTA
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RAW_STAGES; i++) { mbar_init(BAR(RAW_FULL + i), 1); mbar_init(BAR(RAW_EMPTY + i), 4); }
+        for (int i = 0; i < A_STAGES; i++) { mbar_init(BAR(A_FULL + i), 4 * 2 + 2); mbar_init(BAR(A_EMPTY + i), 1); }
+        mbar_init(BAR(ACC_FULL), 2);
+        mbar_init(BAR(ACC_EMPTY), 2 * NDQ_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: the next group's activation kernel may start beside this GEMM
+
+    // Every role walks the same tile sequence: t = pair, pair + npairs, ...; tiles of a node are ordered n-tile fastest so
+    // that concurrently running pairs share weight rows in L2.
+    struct Tile { const GroupNode *nd; int m0, n0, ksteps; };
+    int scan_n = 0;
+    auto locate = [&](int t) -> Tile {
+        while (t >= G.node[scan_n].tile_end) scan_n++;
+        const GroupNode &nd = G.node[scan_n];
+        const int local = t - nd.tile0, mt = local / nd.nt, ntile = local - mt * nd.nt;
+        return Tile{&nd, (mt * 2 + (int)rank) * BM, ntile * BN, nd.ksteps};
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer 1: this CTA's 128 rows of raw quant blocks =====
+        if (lane == 0) {
+            uint32_t gk = 0;
+            for (int t = pair; t < G.total_tiles; t += npairs) {
+                const Tile tl = locate(t);
+                for (int ks = 0; ks < tl.ksteps; ks++, gk++) {
+                    const int s = gk & (RAW_STAGES - 1);
+                    mbar_wait(BAR(RAW_EMPTY + s), ((gk >> 3) & 1) ^ 1);
+                    mbar_expect_tx(BAR(RAW_FULL + s), RAW_BYTES);
+                    tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &tl.nd->map_w, BAR(RAW_FULL + s), ks * RAW_ROW, tl.m0);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== TMA producer 2: this CTA's half (64 rows) of the activation tile =====
+        if (lane == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");       // the activation kernel must have finished; weights never wait
+            uint32_t gk = 0;
+            for (int t = pair; t < G.total_tiles; t += npairs) {
+                const Tile tl = locate(t);
+                const int n0 = tl.n0 + (int)rank * BNL;
+                for (int ks = 0; ks < tl.ksteps; ks++, gk++) {
+                    const int sb = gk & (A_STAGES - 1);
+                    mbar_wait(BAR(A_EMPTY + sb), ((gk >> 2) & 1) ^ 1);
+                    const uint32_t full = LBAR(A_FULL + sb);
+                    if (leader) mbar_expect_tx(BAR(A_FULL + sb), 2 * B_BYTES); else mbar_arrive_cluster(full);
+                    tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES), &tl.nd->map_x, full, ks * BK, n0);
+                    tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES + BNL * 128), &tl.nd->map_x, full, ks * BK + 64, n0);
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers (leader CTA): even / odd K steps of every tile, own accumulator each =====
+        if (leader && lane == 0) {
+            const int me = warp >> 1;
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * 2) >> 4) << 24);
+            const uint32_t acc = tmem + (uint32_t)(me * BN);
+            const uint64_t bdesc0 = make_sdesc(smem_u32(sB));
+            uint32_t gk0 = 0, it = 0;
+            for (int t = pair; t < G.total_tiles; t += npairs, it++) {
+                const Tile tl = locate(t);
+                if (it) { mbar_wait(BAR(ACC_EMPTY), (it - 1) & 1); tc_fence_after(); }    // both CTAs have drained the previous tile's accumulators
+                for (int ks = me; ks < tl.ksteps; ks += 2) {
+                    const uint32_t gk = gk0 + (uint32_t)ks;
+                    const int g = gk & 3;
+                    mbar_wait(BAR(A_FULL + g), (gk >> 2) & 1);           // A rows in TMEM (both CTAs) + both halves of the B tile
+                    tc_fence_after();
+                    const uint64_t bd0 = bdesc0 + (uint64_t)((g * B_BYTES) >> 4);
+                    const uint32_t a_base = tmem + A_COL0 + g * 64;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                        tc_mma_f16_ts(acc, a_base + k * 8, bd0 + (uint64_t)(((k >> 2) * (BNL * 128) + (k & 3) * 32) >> 4), idesc, (ks >= 2) || k != 0, true);
+                    tc_commit_cg2(BAR(A_EMPTY + g));                      // frees TMEM stage g and B stage g in both CTAs
+                }
+                tc_commit_cg2(BAR(ACC_FULL));
+                gk0 += (uint32_t)tl.ksteps;
+            }
+        }
+    } else {
+        // ===== 16 dequant warps (TMEM lane quadrant q, K-step group g), which are also the epilogue =====
+        const int q = warp & 3, g = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t raw_row = smem_u32(sRaw) + (uint32_t)(r * RAW_ROW);
+        const uint32_t a_full = LBAR(A_FULL + g), acc_empty = LBAR(ACC_EMPTY);
+        const uint32_t a_tmem = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_COL0 + g * 64);
+        uint32_t mk_lo = 0x000F000Fu, mk_hi = 0x00F000F0u, mg_lo = 0x64006400u, mg_hi = 0x54005400u;
+        asm volatile("" : "+r"(mk_lo), "+r"(mk_hi), "+r"(mg_lo), "+r"(mg_hi));
+        uint32_t gk0 = 0, it = 0;
+        for (int t = pair; t < G.total_tiles; t += npairs, it++) {
+            const Tile tl = locate(t);
+            for (int ks = (int)((g - gk0) & 3); ks < tl.ksteps; ks += 4) {
+                const uint32_t gk = gk0 + (uint32_t)ks;
+                const int s = gk & (RAW_STAGES - 1);
+                mbar_wait(BAR(RAW_FULL + s), (gk >> 3) & 1);
+                uint32_t w[RAW_ROW / 4];
+#pragma unroll
+                for (int i = 0; i < RAW_ROW / 16; i++) {
+                    const uint4 v4 = lds128(raw_row + (uint32_t)(s * RAW_BYTES + i * 16));
+                    w[4 * i] = v4.x; w[4 * i + 1] = v4.y; w[4 * i + 2] = v4.z; w[4 * i + 3] = v4.w;
+                }
+                // the raw stage is released only after the dequant below has CONSUMED these registers (ggb_gemm.cu)
+                mbar_wait(BAR(A_EMPTY + g), ((gk >> 2) & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int hb = 0; hb < 2; hb++) {                         // two blocks (64 K = 32 columns) per TMEM store
+                    uint32_t v[32];
+#pragma unroll
+                    for (int jb = 0; jb < 2; jb++) {
+                        const int j = hb * 2 + jb;
+                        __half2 d2, m2 = __float2half2_rn(0.0f);
+                        const uint32_t *wb = TYPE == GGML_TYPE_Q4_0 ? &w[5 * j] : &w[6 * j];
+                        d2 = __float2half2_rn(__uint_as_float(wb[0]));
+                        if (TYPE == GGML_TYPE_Q4_1) m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(wb[0]), __uint_as_float(wb[1])));   // m + 8d
+                        const uint32_t *qw = TYPE == GGML_TYPE_Q4_0 ? wb + 1 : wb + 2;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) dequant_word<TYPE>(qw[i], d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16 + i * 4]);
+                    }
+                    tmem_st_x32(a_tmem + (uint32_t)(hb * 32), v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive_cluster(a_full); mbar_arrive(BAR(RAW_EMPTY + s)); }
+            }
+            gk0 += (uint32_t)tl.ksteps;
+
+            // ---- epilogue of this tile: warp -> (lane quadrant q, 32-column groups g, g+4, ...) ----
+            mbar_wait(BAR(ACC_FULL), it & 1);
+            tc_fence_after();
+            const GroupNode &nd = *tl.nd;
+            const int m = tl.m0 + q * 32 + lane;
+            const bool two = tl.ksteps > 1;
+#pragma unroll 1
+            for (int cb = g; cb < BN / 32; cb += NDQ_WARPS / 4) {
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
+#pragma unroll 1
+                for (int hc = 0; hc < 2; hc++) {                      // 16 columns at a time keeps both accumulators in 32 registers
+                    uint32_t v[16], u[16];
+#define GGB_TMEM_LD16(ARR, ADDR) \
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                                 : "=r"(ARR[0]), "=r"(ARR[1]), "=r"(ARR[2]), "=r"(ARR[3]), "=r"(ARR[4]), "=r"(ARR[5]), "=r"(ARR[6]), "=r"(ARR[7]), \
+                                   "=r"(ARR[8]), "=r"(ARR[9]), "=r"(ARR[10]), "=r"(ARR[11]), "=r"(ARR[12]), "=r"(ARR[13]), "=r"(ARR[14]), "=r"(ARR[15]) \
+                                 : "r"(ADDR) : "memory")
+                    GGB_TMEM_LD16(v, taddr + (uint32_t)(hc * 16));
+                    GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
+#undef GGB_TMEM_LD16
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (m < nd.M) {
+#pragma unroll
+                        for (int c = 0; c < 16; c++) {
+                            const int n = tl.n0 + cb * 32 + hc * 16 + c;
+                            const float res = two ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);   // even-K + odd-K partial sums
+                            if (n < nd.N) {
+                                float *yp = nd.Y + (long long)n * nd.ldy + m;
+                                *yp = res;
+                                for (int pp = 0; pp < nd.n_peers; pp++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + nd.peer_delta[pp]) = res;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty);            // this warp's TMEM reads of the tile are complete
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// F16 weights: both operands come from shared memory (TMA, swizzle-128B), so the 16 warps that dequantize in the Q4 kernel
+// have nothing to do during the main loop and TMEM has room for TWO accumulator sets (2 x (even-K + odd-K) x 128 columns):
+// the epilogue of tile i runs under the main loop of tile i + 1.
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_constant__ GemmGroup G)
+{
+    constexpr int BN = 128, BNL = 64;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2, STAGES = 4;
+    constexpr int TMEM_COLS = 512;                             // accumulator set b: columns [256 b, 256 b + 128) even-K, [+128, +256) odd-K
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + STAGES * A_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + STAGES * B_BYTES);
+    const uint32_t bar0 = smem_u32(bars);
+    constexpr int FULL = 0, EMPTY = 4, ACC_FULL = 8, ACC_EMPTY = 10, NBARS = 12;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
+    auto BAR = [&](int i) { return bar0 + 8 * i; };
+    auto LBAR = [&](int i) { return mapa_u32(BAR(i), 0); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; i++) { mbar_init(BAR(FULL + i), 2); mbar_init(BAR(EMPTY + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(ACC_FULL + i), 2); mbar_init(BAR(ACC_EMPTY + i), 2 * NDQ_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    struct Tile { const GroupNode *nd; int m0, n0, ksteps; };
+    int scan_n = 0;
+    auto locate = [&](int t) -> Tile {
+        while (t >= G.node[scan_n].tile_end) scan_n++;
+        const GroupNode &nd = G.node[scan_n];
+        const int local = t - nd.tile0, mt = local / nd.nt, ntile = local - mt * nd.nt;
+        return Tile{&nd, (mt * 2 + (int)rank) * BM, ntile * BN, nd.ksteps};
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer: this CTA's 128 weight rows and its half of the activation rows, per K step =====
+        if (lane == 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");       // activations come from the preceding kernel
+            uint32_t gk = 0;
+            for (int t = pair; t < G.total_tiles; t += npairs) {
+                const Tile tl = locate(t);
+                const int n0 = tl.n0 + (int)rank * BNL;
+                for (int ks = 0; ks < tl.ksteps; ks++, gk++) {
+                    const int sb = gk & (STAGES - 1);
+                    mbar_wait(BAR(EMPTY + sb), ((gk >> 2) & 1) ^ 1);
+                    const uint32_t full = LBAR(FULL + sb);
+                    if (leader) mbar_expect_tx(BAR(FULL + sb), 2 * (A_BYTES + B_BYTES)); else mbar_arrive_cluster(full);
+                    tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES), &tl.nd->map_x, full, ks * BK, n0);
+                    tma_load_2d_cg2(smem_u32(sB + sb * B_BYTES + BNL * 128), &tl.nd->map_x, full, ks * BK + 64, n0);
+                    tma_load_2d_cg2(smem_u32(sA + sb * A_BYTES), &tl.nd->map_w, full, ks * BK, tl.m0);
+                    tma_load_2d_cg2(smem_u32(sA + sb * A_BYTES + BM * 128), &tl.nd->map_w, full, ks * BK + 64, tl.m0);
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ===== MMA issuers (leader CTA): even / odd K steps, accumulator set it & 1 =====
+        if (leader && lane == 0) {
+            const int me = warp >> 1;
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * 2) >> 4) << 24);
+            const uint64_t adesc0 = make_sdesc(smem_u32(sA)), bdesc0 = make_sdesc(smem_u32(sB));
+            uint32_t gk0 = 0, it = 0;
+            for (int t = pair; t < G.total_tiles; t += npairs, it++) {
+                const Tile tl = locate(t);
+                const int ab = it & 1;
+                const uint32_t acc = tmem + (uint32_t)(ab * 2 * BN + me * BN);
+                if (it >= 2) { mbar_wait(BAR(ACC_EMPTY + ab), ((it >> 1) - 1) & 1); tc_fence_after(); }
+                for (int ks = me; ks < tl.ksteps; ks += 2) {
+                    const uint32_t gk = gk0 + (uint32_t)ks;
+                    const int sb = gk & (STAGES - 1);
+                    mbar_wait(BAR(FULL + sb), (gk >> 2) & 1);
+                    tc_fence_after();
+                    const uint64_t ad0 = adesc0 + (uint64_t)((sb * A_BYTES) >> 4), bd0 = bdesc0 + (uint64_t)((sb * B_BYTES) >> 4);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) {
+                        const uint64_t ad = ad0 + (uint64_t)(((k >> 2) * (BM * 128) + (k & 3) * 32) >> 4);
+                        const uint64_t bd = bd0 + (uint64_t)(((k >> 2) * (BNL * 128) + (k & 3) * 32) >> 4);
+                        tc_mma_f16_cg2(acc, ad, bd, idesc, (ks >= 2) || k != 0);
+                    }
+                    tc_commit_cg2(BAR(EMPTY + sb));
+                }
+                tc_commit_cg2(BAR(ACC_FULL + ab));
+                gk0 += (uint32_t)tl.ksteps;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue warps: tile it drains accumulator set it & 1 while the issuers fill the other =====
+        const int q = warp & 3, g = (warp - 4) >> 2;
+        uint32_t it = 0;
+        for (int t = pair; t < G.total_tiles; t += npairs, it++) {
+            const Tile tl = locate(t);
+            const int ab = it & 1;
+            const uint32_t acc_empty = LBAR(ACC_EMPTY + ab);
+            mbar_wait(BAR(ACC_FULL + ab), (it >> 1) & 1);
+            tc_fence_after();
+            const GroupNode &nd = *tl.nd;
+            const int m = tl.m0 + q * 32 + lane;
+            const bool two = tl.ksteps > 1;
+#pragma unroll 1
+            for (int cb = g; cb < BN / 32; cb += NDQ_WARPS / 4) {
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * BN + cb * 32);
+#pragma unroll 1
+                for (int hc = 0; hc < 2; hc++) {
+                    uint32_t v[16], u[16];
+#define GGB_TMEM_LD16(ARR, ADDR) \
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                                 : "=r"(ARR[0]), "=r"(ARR[1]), "=r"(ARR[2]), "=r"(ARR[3]), "=r"(ARR[4]), "=r"(ARR[5]), "=r"(ARR[6]), "=r"(ARR[7]), \
+                                   "=r"(ARR[8]), "=r"(ARR[9]), "=r"(ARR[10]), "=r"(ARR[11]), "=r"(ARR[12]), "=r"(ARR[13]), "=r"(ARR[14]), "=r"(ARR[15]) \
+                                 : "r"(ADDR) : "memory")
+                    GGB_TMEM_LD16(v, taddr + (uint32_t)(hc * 16));
+                    GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
+#undef GGB_TMEM_LD16
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (m < nd.M) {
+#pragma unroll
+                        for (int c = 0; c < 16; c++) {
+                            const int n = tl.n0 + cb * 32 + hc * 16 + c;
+                            const float res = two ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);
+                            if (n < nd.N) {
+                                float *yp = nd.Y + (long long)n * nd.ldy + m;
+                                *yp = res;
+                                for (int pp = 0; pp < nd.n_peers; pp++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + nd.peer_delta[pp]) = res;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+
+template <int TYPE>
+int launch_grouped(const GemmGroup &G, cudaStream_t s)
+{
+    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr size_t smem = TYPE == GGML_TYPE_F16 ? 1024 + (size_t)4 * (BM * BK * 2) + (size_t)4 * (64 * BK * 2) + 64 * 8 + 16
+                                                  : 1024 + (size_t)4 * (64 * BK * 2) + (size_t)8 * (BM * RAW_ROW) + 64 * 8 + 16;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    void (*kern)(const GemmGroup) = nullptr;
+    if constexpr (TYPE == GGML_TYPE_F16) kern = k_gemm_f16_grouped; else kern = k_gemm_q_grouped<TYPE>;
+    static bool attr_set = false;
+    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    // The tile lists are static, so every pair of the grid must be resident at once: ask how many 2-CTA clusters the device
+    // can actually co-schedule (a GPC with an odd number of usable SMs leaves one unpaired) instead of assuming SMs / 2.
+    static int max_pairs = 0;
+    if (!max_pairs) {
+        cfg.gridDim = dim3((unsigned)(device_sm_count() / 2 * 2));
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = device_sm_count() / 2; }
+        if (const char *e = getenv("GGB200_GEMM_PAIRS")) nc = std::max(1, std::min(nc, atoi(e)));
+        max_pairs = nc;
+        if (getenv("GGB200_VERBOSE")) fprintf(stderr, "[ggb200] grouped GEMM: %d resident CTA pairs\n", nc);
+    }
+    const int pairs = std::min(G.total_tiles, max_pairs);
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // prologue + weight streaming overlap the activation kernel
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("GGB200_NO_PDL") != nullptr;
+    cfg.attrs = at; cfg.numAttrs = no_pdl ? 1 : 2;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, kern, G));
+    count_launch();
+    return GGB_OK;
+}
+
+} // namespace
+
+bool gemm_grouped_supported(int type) { return type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1 || type == GGML_TYPE_F16; }
+
+int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
+{
+    if (count <= 0) return GGB_OK;
+    if (count > GGB_GEMM_GROUP_NODES) return set_error(GGB_E_INVALID, "grouped GEMM: %d nodes > %d", count, GGB_GEMM_GROUP_NODES);
+    static thread_local GemmGroup G;                                   // ~25 KB: kept off the stack
+    const int type = args[0].type;
+    G.n_nodes = count; G.total_tiles = 0;
+    for (int i = 0; i < count; i++) {
+        const GemmArgs &a = args[i];
+        if (a.type != type) return set_error(GGB_E_INVALID, "grouped GEMM: mixed weight types in one group");
+        if (a.n_peers < 0 || a.n_peers > 7) return set_error(GGB_E_INVALID, "grouped GEMM: n_peers=%d", a.n_peers);
+        GroupNode &nd = G.node[i];
+        int rc;
+        if (type == GGML_TYPE_F16) {
+            rc = make_map_2d(&nd.map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.W, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.nb01, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+        } else {
+            const int raw_row = type == GGML_TYPE_Q4_0 ? 80 : 96;
+            const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * (type == GGML_TYPE_Q4_0 ? 20 : 24);
+            rc = make_map_2d(&nd.map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, row_bytes, (uint64_t)a.M, (uint64_t)a.nb01, (uint32_t)raw_row, BM, CU_TENSOR_MAP_SWIZZLE_NONE);
+        }
+        if (rc) return rc;
+        rc = make_map_2d(&nd.map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        nd.Y = a.Y; nd.ldy = a.ldy; nd.M = (int)a.M; nd.N = (int)a.N; nd.ksteps = (int)((a.K + BK - 1) / BK);
+        nd.nt = (int)((a.N + 127) / 128);
+        const int mt = (int)((a.M + 2 * BM - 1) / (2 * BM));
+        nd.tile0 = G.total_tiles; nd.tile_end = nd.tile0 + mt * nd.nt;
+        G.total_tiles = nd.tile_end;
+        nd.n_peers = a.n_peers;
+        for (int p = 0; p < a.n_peers; p++) nd.peer_delta[p] = (long long)(reinterpret_cast<char *>(a.ypeer[p]) - reinterpret_cast<char *>(a.Y));
+    }
+    if (G.total_tiles == 0) return GGB_OK;
+    if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16>(G, s);
+    return type == GGML_TYPE_Q4_0 ? launch_grouped<GGML_TYPE_Q4_0>(G, s) : launch_grouped<GGML_TYPE_Q4_1>(G, s);
+}
+
+} // namespace ggb

@@ -7,6 +7,10 @@
 #include "../../include/ggb200.h"
 
 #define GGB_QK 32
+// nodes one activation / GEMV launch can carry (kernel-parameter descriptors: 256 x 40 B, inside the 32 KB parameter space)
+#define GGB_MAX_BATCH_NODES 256
+// nodes one grouped tensor-core launch can carry (two 128-byte tensor maps + 128 B of descriptor each)
+#define GGB_GEMM_GROUP_NODES 64
 
 namespace ggb {
 
@@ -37,10 +41,14 @@ int launch_dequantize_rows(int type, const void *src, float *dst, int64_t nrows,
 size_t act_row_bytes(int wtype, int64_t K);
 struct ActNode { const float *x; long long ldx_bytes; uint8_t *out; int N; int blk0; };
 // bps > 1: unit-major Q8P planes for the fast GEMV (block b = bps*u + j stored at plane index j*(kb/bps) + u); else linear
-struct ActBatch { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; ActNode node[64]; };
+struct ActBatch { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; ActNode node[GGB_MAX_BATCH_NODES]; };
 int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl);
 // batched path: activations as dense fp16 [Npad][K] holding d * q (the value the reference's dot multiplies by)
 int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior);
+// the same for every node of a grouped GEMM launch, one kernel (grid.y = node)
+struct ActGemmNode { const float *x; long long ldx_bytes; __half *out; int N, Npad, K, vec16; };
+struct ActGemmBatch { int n_nodes, wtype, perm, wait_prior; ActGemmNode node[GGB_GEMM_GROUP_NODES]; };
+int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s);
 
 // ---- GEMV (ggb_gemv.cu) ----
 struct GemvNode { const uint8_t *W; const uint8_t *xq; float *y; int M; int ldy; int g0; int ngroups; };
@@ -55,7 +63,7 @@ struct GemvBatch {
     int async;                 // 1: cp.async.bulk staging (16-byte aligned rows), 0: plain-load staging
     int n_peers;
     long long peer_delta[7];   // byte offset from a node's y to the same element of peer p's copy
-    GemvNode node[64];
+    GemvNode node[GGB_MAX_BATCH_NODES];
 };
 int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl);
 int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase_probe);
@@ -72,8 +80,19 @@ struct GemmArgs {
 bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W);
 size_t gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
 int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s);
+// ggb_gemm_grouped.cu: persistent CTA pairs over the tiles of up to GGB_GEMM_GROUP_NODES nodes of one weight type
+bool gemm_grouped_supported(int type);
+int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s);
 int gemm_act_perm(int type);       // 1: the activation buffer must use the K order 0,4,1,5,2,6,3,7 per group of 8
 
 int device_sm_count();
+
+} // namespace ggb
+
+// tensor-map encoding through the driver entry point (ggb_gemm.cu); CUtensorMap comes from <cuda.h>
+#include <cuda.h>
+namespace ggb {
+int make_map_2d(CUtensorMap *map, CUtensorMapDataType dt, const void *base, uint64_t dim0, uint64_t dim1, uint64_t stride1_bytes,
+                uint32_t box0, uint32_t box1, CUtensorMapSwizzle sw);
 
 } // namespace ggb

@@ -131,10 +131,17 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     //      disjoint workspace regions, so only the first activation kernel has to wait for earlier work in the stream ----
     std::vector<int> gemv_idx;
     bool first_gemm = true;
+    static const bool grouped = [] { const char *e = getenv("GGB200_GEMM_GROUPED"); return !e || atoi(e) != 0; }();
+    std::vector<int> q_nodes[3];                                  // Q4_0 / Q4_1 / F16 nodes of this batch, for the grouped kernels
+    auto qslot = [](int type) { return type == GGML_TYPE_Q4_0 ? 0 : type == GGML_TYPE_Q4_1 ? 1 : 2; };
+    int n_tc = 0;
+    for (int i = 0; i < count; i++) if (mm[i].M > 0 && mm[i].N > 0 && use_gemm(mm[i])) n_tc++;
     for (int i = 0; i < count; i++) {
         const ggb_dev_mm &m = mm[i];
         if (m.M == 0 || m.N == 0) continue;
         if (!use_gemm(m)) { gemv_idx.push_back(i); continue; }
+        // a lone node keeps the per-node kernel (smaller launch); two or more go through the persistent grouped kernels
+        if (grouped && n_tc > 1 && !getenv("GGB200_GEMM_TRACE") && gemm_grouped_supported(m.type)) { q_nodes[qslot(m.type)].push_back(i); continue; }
         const int64_t Npad = (m.N + 15) / 16 * 16;
         __half *xh = reinterpret_cast<__half *>(wsb + off[i]);
         int rc = launch_act_f16_dequant(m.type, gemm_act_perm(m.type), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s, first_gemm);
@@ -147,6 +154,35 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         if (const char *tr = getenv("GGB200_GEMM_TRACE")) a.trace = reinterpret_cast<void *>(strtoull(tr, nullptr, 0));   // debugging: device pointer
         { KernelTimer kt(s); rc = launch_gemm(a, wsb + off[i] + align_up((size_t)Npad * m.K * 2, 256), s); }
         if (rc) return rc;
+    }
+    // ---- Q4_0 / Q4_1 batched nodes: one activation launch + one persistent grouped GEMM launch per <= 64 nodes.  The GEMM
+    //      triggers its dependents at start-up, so the next group's activation staging overlaps it (ggb_gemm_grouped.cu) ----
+    for (int qi = 0; qi < 3; qi++) {
+        const std::vector<int> &qn = q_nodes[qi];
+        for (size_t c0 = 0; c0 < qn.size(); c0 += GGB_GEMM_GROUP_NODES) {
+            const int cnt = (int)std::min(qn.size() - c0, (size_t)GGB_GEMM_GROUP_NODES);
+            static thread_local ActGemmBatch ab;
+            static thread_local GemmArgs ga[GGB_GEMM_GROUP_NODES];
+            const int type = qi == 0 ? GGML_TYPE_Q4_0 : qi == 1 ? GGML_TYPE_Q4_1 : GGML_TYPE_F16;
+            ab.n_nodes = cnt; ab.wtype = type; ab.perm = gemm_act_perm(type); ab.wait_prior = first_gemm ? 1 : 0;
+            for (int c = 0; c < cnt; c++) {
+                const int i = qn[c0 + c];
+                const ggb_dev_mm &m = mm[i];
+                const int64_t Npad = (m.N + 15) / 16 * 16;
+                __half *xh = reinterpret_cast<__half *>(wsb + off[i]);
+                ab.node[c] = ActGemmNode{m.X, (long long)m.ldx_bytes, xh, (int)m.N, (int)Npad, (int)m.K, 0};
+                GemmArgs &a = ga[c];
+                a = GemmArgs{};
+                a.type = m.type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
+                a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
+                for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
+            }
+            int rc = launch_act_f16_dequant_batch(ab, s);
+            if (rc) return rc;
+            first_gemm = false;
+            { KernelTimer kt(s); rc = launch_gemm_grouped(ga, cnt, s); }
+            if (rc) return rc;
+        }
     }
 
     // ---- single-token nodes: group by (type, K), fuse each group into one act launch + GEMV launches ----
@@ -175,11 +211,11 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         const size_t arow = act_row_bytes(type, K);
         const bool quant = type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1;
         // activation staging (INIT phase)
-        for (size_t c0 = 0; c0 < grp.size(); c0 += 64) {
+        for (size_t c0 = 0; c0 < grp.size(); c0 += GGB_MAX_BATCH_NODES) {
             ActBatch ab = {};
             ab.K = (int)K; ab.kb = (int)(K / GGB_QK); ab.row_bytes = (int)arow; ab.wtype = type; ab.vec16 = 1; ab.bps = bps0;
             int tot = 0;
-            for (size_t c = c0; c < std::min(grp.size(), c0 + 64); c++) {
+            for (size_t c = c0; c < std::min(grp.size(), c0 + (size_t)GGB_MAX_BATCH_NODES); c++) {
                 const ggb_dev_mm &m = mm[grp[c]];
                 ActNode &an = ab.node[ab.n_nodes++];
                 an.x = m.X; an.ldx_bytes = m.ldx_bytes; an.out = wsb + off[grp[c]]; an.N = (int)m.N; an.blk0 = tot;
@@ -236,7 +272,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
                 const int64_t rows_per_group = gemv_group_rows(gb);
                 nd.g0 = gb.total_groups; nd.ngroups = (int)((m.M + rows_per_group - 1) / rows_per_group);
                 gb.total_groups += nd.ngroups;
-                if (gb.n_nodes == 64) { rc = flush(); if (rc) return rc; }
+                if (gb.n_nodes == GGB_MAX_BATCH_NODES) { rc = flush(); if (rc) return rc; }
             }
             rc = flush();
             if (rc) return rc;

@@ -113,3 +113,67 @@ def test_kernel_timing_brackets_only_the_mul_mat_kernels():
     finally:
         N.check(L.ggb_set_kernel_timing(0))
     assert s.kernel_launches == 4 and s.timed_kernel_launches == 2 and 0.0 < s.timed_kernel_ms < 5.0
+
+
+def dev_mul_mat_batch(nodes):
+    """nodes: [(type, wbytes, M, K, X)] submitted as ONE ggb_dev_mul_mat_batch call; returns the list of dst arrays."""
+    import ctypes as C
+    from test_gpu_parity import Dev
+    d = Dev()
+    try:
+        mms = (N.ggb_dev_mm * len(nodes))()
+        for i, (t, wb, M, K, X) in enumerate(nodes):
+            X = np.ascontiguousarray(X, dtype=np.float32)
+            m = mms[i]
+            m.type, m.M, m.K, m.N = t, M, K, X.shape[0]
+            m.W, m.nb01 = d.put(wb), N.TYPE_SIZE[t] * (K // N.BLCK_SIZE[t])
+            m.X, m.ldx_bytes = d.put(X), 4 * K
+            m.Y, m.ldy_bytes = d.empty(4 * M * X.shape[0]), 4 * M
+        wsb = N.lib().ggb_dev_workspace_bytes(mms, len(nodes))
+        ws = d.empty(wsb)
+        N.check(N.lib().ggb_dev_mul_mat_batch(mms, len(nodes), ws, wsb, None))
+        N.check(N.lib().ggb_stream_sync(None))
+        return [d.get(mms[i].Y, (nodes[i][4].shape[0], nodes[i][2])) for i in range(len(nodes))]
+    finally:
+        d.close()
+
+
+# (M, K, N): ragged M and N, a single K step (K = 128), odd K-step counts (384, 640), more tiles than CTA pairs, long K
+GROUP_SHAPES = [(300, 128, 17), (128, 384, 16), (520, 640, 130), (4096, 4096, 512), (1376, 4096, 40), (512, 11008, 24), (256, 256, 64)]
+
+
+@pytest.mark.parametrize("t", [N.Q4_0, N.Q4_1, N.F16])
+def test_grouped_gemm_batch_vs_oracle(t):
+    # one call with several batched nodes -> the persistent grouped kernel (one activation launch + one GEMM launch):
+    # every node must match the oracle, and match what the same node gives when submitted alone (per-node kernel)
+    rng = np.random.default_rng(4100 + t)
+    nodes = []
+    for (M, K, Nn) in GROUP_SHAPES:
+        wb = orc.encode_weights(t, weights(rng, M, K))
+        nodes.append((t, wb, M, K, rng.standard_normal((Nn, K)).astype(np.float32)))
+    N.lib().ggb_reset_stats()
+    got = dev_mul_mat_batch(nodes)
+    assert N.stats().kernel_launches == 2
+    for (tt, wb, M, K, X), y in zip(nodes, got):
+        want = orc.mul_mat_2d(tt, wb, M, K, X, nth=16)
+        err = rel_l2(y, want)
+        assert err <= GEMM_TIGHT[t], (t, M, K, X.shape[0], err)
+        alone = dev_mul_mat(tt, wb, M, K, X)
+        assert rel_l2(y, alone) <= 1e-6, (t, M, K, X.shape[0])
+
+
+def test_grouped_gemm_mixed_batch_and_rerun():
+    # Q4_0 + Q4_1 + F16 batched nodes and single-token nodes in one call; run twice into the same buffers (ring phases of a
+    # second launch start from scratch) and require identical bits
+    rng = np.random.default_rng(4200)
+    nodes = []
+    for t, (M, K, Nn) in [(N.Q4_0, (512, 1024, 32)), (N.F16, (384, 512, 48)), (N.Q4_1, (640, 768, 20)), (N.Q4_0, (256, 1024, 1)),
+                          (N.Q4_0, (768, 2048, 96)), (N.F16, (256, 2048, 16)), (N.Q4_1, (256, 128, 33)), (N.F32, (64, 256, 1))]:
+        wb = orc.encode_weights(t, weights(rng, M, K))
+        nodes.append((t, wb, M, K, rng.standard_normal((Nn, K)).astype(np.float32)))
+    a = dev_mul_mat_batch(nodes)
+    b = dev_mul_mat_batch(nodes)
+    for (t, wb, M, K, X), ya, yb in zip(nodes, a, b):
+        assert np.array_equal(ya, yb)
+        tol = GEMM_TOL[t] if X.shape[0] >= 16 else 5e-6
+        assert rel_l2(ya, orc.mul_mat_2d(t, wb, M, K, X, nth=8)) <= tol, (t, M, K, X.shape[0])

@@ -1,5 +1,5 @@
 """Row-split across 2 GPUs through the C ABI (needs >= 2 devices; skipped otherwise): both exchange variants -- peer stores
-from the GEMV epilogue (ggb_dev_mm.Y_peer) and the push+barrier kernel (ggb_peer_push_barrier) -- must leave, on EVERY
+from the GEMV / tcgen05 GEMM epilogue (ggb_dev_mm.Y_peer) and the push+barrier kernel (ggb_peer_push_barrier) -- must leave, on EVERY
 rank, the bytes the unsharded oracle computes (<= the GEMV tolerance) and the same bytes on both ranks."""
 import os
 import subprocess
@@ -30,9 +30,9 @@ WORKER = textwrap.dedent('''
     wbs = [orc.quantize_rows(orc.Q4_0, w) for w in Ws]
     want = np.stack([orc.mul_mat_2d(orc.Q4_0, wb, M, K, x)[0] for wb, x in zip(wbs, Xs)])          # [NODES][M]
     ok = True
-    for variant in ("epilogue", "push", "push_gemm"):
-        NB = 24 if variant == "push_gemm" else 1           # 24 activation rows -> the tcgen05 path; dst is [NB][M] per node
-        if variant == "push_gemm":
+    for variant in ("epilogue", "push", "push_gemm", "epilogue_gemm"):
+        NB = 24 if variant.endswith("_gemm") else 1           # 24 activation rows -> the tcgen05 path; dst is [NB][M] per node
+        if variant.endswith("_gemm"):
             Xg = [rng.standard_normal((NB, K)).astype(np.float32) for _ in range(NODES)]
             wantg = np.stack([orc.mul_mat_2d(orc.Q4_0, wb, M, K, x, nth=8) for wb, x in zip(wbs, Xg)])      # [NODES][NB][M]
         sym = rowsplit.SymmetricBuffer(NODES * NB * M * 4, rank, world, ago)
@@ -44,10 +44,10 @@ WORKER = textwrap.dedent('''
             m = mms[i]
             m.type, m.M, m.K, m.N = N.Q4_0, n, K, NB
             m.W, m.nb01 = put(np.ascontiguousarray(wbs[i][r0:r0 + n])), wbs[i].shape[1]
-            m.X, m.ldx_bytes = put(Xg[i] if variant == "push_gemm" else Xs[i]), 4 * K
+            m.X, m.ldx_bytes = put(Xg[i] if variant.endswith("_gemm") else Xs[i]), 4 * K
             off = (i * NB * M + r0) * 4
             m.Y, m.ldy_bytes = sym.payload() + off, 4 * M
-            if variant == "epilogue":
+            if variant.startswith("epilogue"):
                 peers = [r for r in range(world) if r != rank]
                 m.n_peers = len(peers)
                 for j, r in enumerate(peers): m.Y_peer[j] = sym.payload(r) + off
@@ -55,16 +55,16 @@ WORKER = textwrap.dedent('''
         ws = C.c_void_p(); N.check(L.ggb_dev_alloc(wsb + 256, C.byref(ws)))
         for rep in range(3):
             N.check(L.ggb_dev_mul_mat_batch(mms, NODES, ws, wsb, None))
-            if variant == "epilogue": sym.barrier(None)
+            if variant.startswith("epilogue"): sym.barrier(None)
             else: sym.push_barrier(None, r0 * 4, n * 4, M * 4, NODES * NB)      # every dst row of every node is one segment
         N.check(L.ggb_stream_sync(None))
         got = np.zeros((NODES, NB, M), np.float32)
         N.check(L.ggb_dev_download(got.ctypes.data, sym.payload(), got.nbytes))
-        ref_ = wantg if variant == "push_gemm" else want.reshape(NODES, 1, M)
+        ref_ = wantg if variant.endswith("_gemm") else want.reshape(NODES, 1, M)
         err = float(np.linalg.norm(got - ref_) / np.linalg.norm(ref_))
         t = torch.from_numpy(got).cuda(); ref = t.clone(); dist.broadcast(ref, 0)
         same = bool(torch.equal(t, ref))
-        ok = ok and err <= (1e-3 if variant == "push_gemm" else 2e-6) and same
+        ok = ok and err <= (1e-3 if variant.endswith("_gemm") else 2e-6) and same
         dist.barrier(); sym.close()
     flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0: print("ROWSPLIT_GPU_OK" if flag.item() == 1 else "ROWSPLIT_GPU_MISMATCH")
