@@ -315,6 +315,102 @@ __global__ void __launch_bounds__(QT_WARPS * 32) k_quantize_q4_tiles(const float
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ggml_compute_forward_add_q_f32 (Ggml.cs:4797-4906): dst_row = quantize_row_q(dequantize_row_q(src0_row) + src1_row).  Both
+// codecs work on 32-element blocks, so the whole op is block-local: one thread per block reads 20 / 24 B of src0 and 128 B of
+// src1, rebuilds the 32 floats in registers (dequantize exactly as k_dequantize_rows, then one float add: ggml_vec_acc_f32,
+// Ggml.cs:2591-2594) and requantizes them with the quantizer above.  dst may alias src0 (ggml_add_inplace).
+template <int TYPE>
+__device__ __forceinline__ void addq_block_values(const uint8_t *__restrict__ qb, const float4 *__restrict__ xp, float (&e)[32])
+{
+    constexpr int QOFF = TYPE == GGML_TYPE_Q4_0 ? 4 : 8;
+    const float d = *reinterpret_cast<const float *>(qb);
+    const float m = TYPE == GGML_TYPE_Q4_1 ? *reinterpret_cast<const float *>(qb + 4) : 0.0f;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = *reinterpret_cast<const uint32_t *>(qb + QOFF + 4 * i);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const float4 xv = __ldg(xp + i);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int l = 4 * i + j;                                   // element l: byte l/2, low nibble if l even
+            const int q = (int)((w[l >> 3] >> (4 * (l & 7))) & 15u);
+            const float v = TYPE == GGML_TYPE_Q4_0 ? __fmul_rn((float)(q - 8), d) : __fadd_rn(__fmul_rn((float)q, d), m);
+            e[l] = __fadd_rn(v, xs[j]);
+        }
+    }
+}
+
+template <int TYPE>
+__device__ __noinline__ void addq_block_exact(const uint8_t *__restrict__ qb, const float4 *__restrict__ xp, uint32_t *out)
+{
+    float e[32];
+    addq_block_values<TYPE>(qb, xp, e);
+    uint32_t tmp[6];
+    // the exact scan of quantize_block_q4 on register values (same code as its body, fed from e[])
+    if (TYPE == GGML_TYPE_Q4_0) {
+        float amax = 0.0f, mx = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) { const float av = fabsf(e[i]); if (amax < av) { amax = av; mx = e[i]; } }
+        const float d = __fdiv_rn(mx, -8.0f);
+        const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+        tmp[0] = __float_as_uint(d);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int q0 = rne_q4_0(__fmul_rn(e[8 * j + 2 * b], id)), q1 = rne_q4_0(__fmul_rn(e[8 * j + 2 * b + 1], id));
+                acc |= (uint32_t)((q0 | (q1 << 4)) & 0xFF) << (8 * b);
+            }
+            tmp[1 + j] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; i++) out[i] = tmp[i];
+    } else {
+        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) { if (e[i] < mn) mn = e[i]; if (e[i] > mx) mx = e[i]; }
+        const float d = __fdiv_rn(__fsub_rn(mx, mn), 15.0f);
+        const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+        tmp[0] = __float_as_uint(d); tmp[1] = __float_as_uint(mn);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int q0 = rne_byte(__fmul_rn(__fsub_rn(e[8 * j + 2 * b], mn), id)), q1 = rne_byte(__fmul_rn(__fsub_rn(e[8 * j + 2 * b + 1], mn), id));
+                acc |= (uint32_t)((q0 | (q1 << 4)) & 0xFF) << (8 * b);
+            }
+            tmp[2 + j] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) out[i] = tmp[i];
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(256) k_add_q_f32(const uint8_t *__restrict__ q, const float *__restrict__ x, uint8_t *__restrict__ y, long long nblk)
+{
+    constexpr int BS = TYPE == GGML_TYPE_Q4_0 ? 20 : 24, OW = BS / 4;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
+        const uint8_t *qb = q + blk * BS;
+        const float4 *xp = reinterpret_cast<const float4 *>(x + blk * GGB_QK);
+        float e[32];
+        addq_block_values<TYPE>(qb, xp, e);
+        uint32_t o[OW];
+        uint32_t *dst = reinterpret_cast<uint32_t *>(y + blk * BS);
+        if (quantize_block_q4_fast<TYPE>(e, o)) {
+#pragma unroll
+            for (int i = 0; i < OW; i++) dst[i] = o[i];
+        } else {
+            addq_block_exact<TYPE>(qb, xp, dst);                      // reads qb completely before it writes dst (same block when in place)
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_f32_to_f16_rows(const float *__restrict__ x, long long ldx, __half *__restrict__ y,
                                                          long long nrows, long long k)
 {
@@ -552,6 +648,26 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
     default: return set_error(GGB_E_UNSUPPORTED, "quantize: type %d has no codec on this path", type);
     }
     count_launch(); GGB_CUDA(cudaGetLastError());
+    return GGB_OK;
+}
+
+int launch_add_q_f32(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k, cudaStream_t s)
+{
+    if (nrows <= 0 || k <= 0) return GGB_OK;
+    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1) return set_error(GGB_E_UNSUPPORTED, "add_q_f32: type %d is not on this path (Q4_0, Q4_1)", type);
+    if (k % GGB_QK) return set_error(GGB_E_INVALID, "add_q_f32: ne00=%lld %% 32 != 0 (Ggml.cs:4891)", (long long)k);
+    if (reinterpret_cast<uintptr_t>(src1) & 15) return set_error(GGB_E_UNSUPPORTED, "add_q_f32: src1 must be 16-byte aligned");
+    const long long nblk = nrows * (k / GGB_QK);
+    const unsigned grid = (unsigned)std::min<long long>((nblk + 255) / 256, (long long)device_sm_count() * 8);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (type == GGML_TYPE_Q4_0) GGB_CUDA(cudaLaunchKernelEx(&cfg, k_add_q_f32<GGML_TYPE_Q4_0>, (const uint8_t *)src0, src1, (uint8_t *)dst, nblk));
+    else GGB_CUDA(cudaLaunchKernelEx(&cfg, k_add_q_f32<GGML_TYPE_Q4_1>, (const uint8_t *)src0, src1, (uint8_t *)dst, nblk));
+    count_launch();
     return GGB_OK;
 }
 

@@ -34,6 +34,16 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // reference-layout row codecs; rows of k elements, src row stride ldx elements, dst rows packed
 int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int64_t nrows, int64_t k, cudaStream_t s);
 int launch_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k, cudaStream_t s);
+// ggml_compute_forward_add_q_f32 on contiguous rows: dst = quantize(dequantize(src0) + src1); dst may alias src0
+int launch_add_q_f32(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k, cudaStream_t s);
+
+// ---- F32 neighbours of mul_mat (ggb_ops.cu) ----
+int launch_binary_f32(int op, const float *a, const float *b, float *dst, int64_t n, cudaStream_t s);       // GGML_OP_ADD / GGML_OP_MUL
+int launch_scale_f32(float *y, float v, int64_t n, cudaStream_t s);                                          // in place
+int launch_silu_f32(const float *x, float *y, int64_t n, cudaStream_t s);
+int launch_rms_norm_f32(const float *x, int64_t x_stride, float *y, int64_t y_stride, int64_t nrows, int64_t ne00, cudaStream_t s);   // strides in floats
+int launch_repeat_f32(const float *src, int64_t src_stride, int64_t nc0, int64_t nr0, float *dst, int64_t dst_stride, int64_t nc, int64_t nr, cudaStream_t s);   // strides in floats
+int launch_dup_f32_strided(const void *src, const int64_t ne[4], const uint64_t nb[4], float *dst, cudaStream_t s);                  // dst contiguous
 
 // Activation staging for mul_mat (the reference's INIT phase, Ggml.cs:6362-6379 / 6641-6655), device-private layouts:
 //   Q4_0/Q4_1 weights: "Q8P" rows  [kb x 16 B even quants][kb x 16 B odd quants][kb x {float d; int sum}]

@@ -343,16 +343,25 @@ namespace ggb {
 
 static size_t tensor_span(const ggml_tensor *t)
 {
-    // bytes from data to the end of the last element, honouring strides (views / padded rows)
-    const size_t rb = (size_t)(t->ne[0] / blck_size(t->type)) * type_size(t->type);
-    size_t span = rb;
+    // bytes from data to the end of the last element, honouring strides (views, padded rows, transposed / permuted tensors)
+    const int blck = blck_size(t->type);
+    size_t span = type_size(t->type);
+    span += (size_t)(t->ne[0] / blck - 1) * t->nb[0];
     for (int i = 1; i < GGML_MAX_DIMS; i++) span += (size_t)(t->ne[i] - 1) * t->nb[i];
     return span;
 }
-static bool dst_contiguous(const ggml_tensor *t)
+static bool is_contiguous(const ggml_tensor *t)                  // ggml_is_contiguous, Ggml.cs:3823-3832
 {
-    return t->nb[0] == 4 && t->nb[1] == (uint64_t)t->ne[0] * 4 && t->nb[2] == t->nb[1] * (uint64_t)t->ne[1] && t->nb[3] == t->nb[2] * (uint64_t)t->ne[2];
+    const uint64_t ts = type_size(t->type);
+    return t->nb[0] == ts && t->nb[1] == ts * (uint64_t)(t->ne[0] / blck_size(t->type)) && t->nb[2] == t->nb[1] * (uint64_t)t->ne[1] &&
+           t->nb[3] == t->nb[2] * (uint64_t)t->ne[2];
 }
+static bool dst_contiguous(const ggml_tensor *t) { return t->type == GGML_TYPE_F32 && is_contiguous(t); }
+static bool same_shape(const ggml_tensor *a, const ggml_tensor *b)
+{
+    return a->ne[0] == b->ne[0] && a->ne[1] == b->ne[1] && a->ne[2] == b->ne[2] && a->ne[3] == b->ne[3];
+}
+static int64_t nelements(const ggml_tensor *t) { return t->ne[0] * t->ne[1] * t->ne[2] * t->ne[3]; }
 
 // What ggml_compute_forward_mul_mat_* assert (Ggml.cs:6016-6034, 6221-6238, 6388, 6481-6504, 6694) and
 // ggml_can_mul_mat (Ggml.cs:8345-8353), returned as a status instead of Debug.Assert.
@@ -384,27 +393,82 @@ static int validate_cpy(const ggml_tensor *node)
     if (a->type != GGML_TYPE_F32) return set_error(GGB_E_UNSUPPORTED, "cpy: only F32 sources are on this path");
     if (b->type != GGML_TYPE_Q4_0 && b->type != GGML_TYPE_Q4_1 && b->type != GGML_TYPE_F16)
         return set_error(GGB_E_UNSUPPORTED, "cpy: destination type %d is not on this path (F16, Q4_0, Q4_1)", b->type);
-    int64_t na = a->ne[0] * a->ne[1] * a->ne[2] * a->ne[3], nb = b->ne[0] * b->ne[1] * b->ne[2] * b->ne[3];
-    if (na != nb) return set_error(GGB_E_INVALID, "cpy: element counts differ (Ggml.cs:8281)");
-    if (a->nb[0] != 4 || a->nb[1] != 4 * (uint64_t)a->ne[0] || a->nb[2] != a->nb[1] * (uint64_t)a->ne[1] || a->nb[3] != a->nb[2] * (uint64_t)a->ne[2])
-        return set_error(GGB_E_UNSUPPORTED, "cpy: non-contiguous source");
-    const uint64_t rb = (uint64_t)(b->ne[0] / blck_size(b->type)) * type_size(b->type);
-    if (b->nb[0] != type_size(b->type) || b->nb[1] != rb || b->nb[2] != rb * (uint64_t)b->ne[1] || b->nb[3] != b->nb[2] * (uint64_t)b->ne[2])
-        return set_error(GGB_E_UNSUPPORTED, "cpy: non-contiguous destination");
+    if (nelements(a) != nelements(b)) return set_error(GGB_E_INVALID, "cpy: element counts differ (Ggml.cs:8281)");
+    if (!is_contiguous(a)) return set_error(GGB_E_UNSUPPORTED, "cpy: non-contiguous source");
+    if (!is_contiguous(b)) return set_error(GGB_E_UNSUPPORTED, "cpy: non-contiguous destination");
     if (a->ne[0] % blck_size(b->type) || a->ne[0] != b->ne[0]) return set_error(GGB_E_UNSUPPORTED, "cpy: rows must map one to one (ne00 == ne0, %% 32)");
     return GGB_OK;
 }
 
+// The neighbours of mul_mat.  GGB_E_INVALID = the reference would assert; GGB_E_UNSUPPORTED = valid ggml that stays on the CPU loop.
+static int validate_neighbour(const ggml_tensor *t)
+{
+    const ggml_tensor *a = t->src0, *b = t->src1;
+    if (!a || !a->data || !t->data) return set_error(GGB_E_INVALID, "op %d: node without src0/data", t->op);
+    switch (t->op) {
+    case GGML_OP_ADD:
+        if (!b || !b->data) return set_error(GGB_E_INVALID, "add: no src1");
+        if (!same_shape(a, b) || !same_shape(a, t)) return set_error(GGB_E_INVALID, "add: shapes differ (Ggml.cs:4628, 4803)");
+        if (a->type == GGML_TYPE_Q4_0 || a->type == GGML_TYPE_Q4_1) {                  // add_q_f32
+            if (b->type != GGML_TYPE_F32 || t->type != a->type) return set_error(GGB_E_INVALID, "add_q_f32: src1 must be F32 and dst of src0's type (Ggml.cs:4862-4864)");
+            if (a->ne[0] % GGB_QK) return set_error(GGB_E_INVALID, "add_q_f32: ne00 %% 32 != 0 (Ggml.cs:4891)");
+            if (!is_contiguous(a) || !is_contiguous(b) || !is_contiguous(t)) return set_error(GGB_E_UNSUPPORTED, "add_q_f32: contiguous tensors only");
+            if (reinterpret_cast<uintptr_t>(b->data) & 15) return set_error(GGB_E_UNSUPPORTED, "add_q_f32: unaligned src1");
+            return GGB_OK;
+        }
+        // fallthrough: F32 + F32
+    case GGML_OP_MUL:
+        if (!b || !b->data) return set_error(GGB_E_INVALID, "op %d: no src1", t->op);
+        if (!same_shape(a, b) || !same_shape(a, t)) return set_error(GGB_E_INVALID, "op %d: shapes differ (Ggml.cs:4628, 5014)", t->op);
+        if (a->type != GGML_TYPE_F32 || b->type != GGML_TYPE_F32 || t->type != GGML_TYPE_F32) return set_error(GGB_E_UNSUPPORTED, "op %d: F32 operands only on this path", t->op);
+        if (!is_contiguous(a) || !is_contiguous(b) || !is_contiguous(t)) return set_error(GGB_E_UNSUPPORTED, "op %d: contiguous tensors only", t->op);
+        return GGB_OK;
+    case GGML_OP_SILU: case GGML_OP_RMS_NORM:
+        if (!same_shape(a, t)) return set_error(GGB_E_INVALID, "op %d: shapes differ (Ggml.cs:5712, 5863)", t->op);
+        if (a->type != GGML_TYPE_F32 || t->type != GGML_TYPE_F32) return set_error(GGB_E_UNSUPPORTED, "op %d: F32 only (Ggml.cs:5757, 5927)", t->op);
+        if (!is_contiguous(a) || !is_contiguous(t)) return set_error(GGB_E_UNSUPPORTED, "op %d: contiguous tensors only", t->op);
+        return GGB_OK;
+    case GGML_OP_SCALE:
+        if (!b || !b->data) return set_error(GGB_E_INVALID, "scale: no src1");
+        if (nelements(b) != 1) return set_error(GGB_E_INVALID, "scale: src1 is not a scalar (Ggml.cs:6755)");
+        if (!same_shape(a, t)) return set_error(GGB_E_INVALID, "scale: shapes differ (Ggml.cs:6754)");
+        if (a->type != GGML_TYPE_F32 || b->type != GGML_TYPE_F32 || t->type != GGML_TYPE_F32) return set_error(GGB_E_UNSUPPORTED, "scale: F32 only");
+        if (!is_contiguous(a) || !is_contiguous(t)) return set_error(GGB_E_INVALID, "scale: non-contiguous (Ggml.cs:6752-6753)");
+        if (b->op != GGML_OP_NONE) return set_error(GGB_E_UNSUPPORTED, "scale: the factor must be a leaf (it is read on the host when the node is enqueued)");
+        return GGB_OK;
+    case GGML_OP_REPEAT:
+        if (a->type != GGML_TYPE_F32 || t->type != GGML_TYPE_F32) return set_error(GGB_E_UNSUPPORTED, "repeat: F32 only (Ggml.cs:5392)");
+        if (a->ne[2] != 1 || a->ne[3] != 1 || t->ne[2] != 1 || t->ne[3] != 1) return set_error(GGB_E_INVALID, "repeat: rank > 2 (Ggml.cs:5354-5357)");
+        if (a->ne[0] <= 0 || a->ne[1] <= 0 || t->ne[0] % a->ne[0] || t->ne[1] % a->ne[1]) return set_error(GGB_E_INVALID, "repeat: ggml_can_repeat fails (Ggml.cs:8398-8407)");
+        if (a->nb[0] != 4 || t->nb[0] != 4 || (a->nb[1] & 3) || (t->nb[1] & 3)) return set_error(GGB_E_INVALID, "repeat: transposed operand (Ggml.cs:5367-5368)");
+        return GGB_OK;
+    case GGML_OP_CONT: case GGML_OP_DUP:
+        if (a->type != GGML_TYPE_F32 || t->type != GGML_TYPE_F32) return set_error(GGB_E_UNSUPPORTED, "cont/dup: F32 -> F32 only on this path");
+        if (nelements(a) != nelements(t)) return set_error(GGB_E_INVALID, "cont/dup: element counts differ (Ggml.cs:4206)");
+        if (!same_shape(a, t) || !is_contiguous(t)) return set_error(GGB_E_UNSUPPORTED, "cont/dup: destination must be the contiguous tensor of src0's shape");
+        for (int i = 0; i < GGML_MAX_DIMS; i++) if (a->nb[i] & 3) return set_error(GGB_E_UNSUPPORTED, "cont/dup: unaligned strides");
+        return GGB_OK;
+    default:
+        return set_error(GGB_E_UNSUPPORTED, "op %d is not on this path", t->op);
+    }
+}
+static bool is_view_op(int op) { return op == GGML_OP_RESHAPE || op == GGML_OP_VIEW || op == GGML_OP_PERMUTE || op == GGML_OP_TRANSPOSE; }
+static bool is_neighbour_op(int op)
+{
+    return op == GGML_OP_ADD || op == GGML_OP_MUL || op == GGML_OP_SILU || op == GGML_OP_RMS_NORM || op == GGML_OP_SCALE || op == GGML_OP_REPEAT ||
+           op == GGML_OP_CONT || op == GGML_OP_DUP;
+}
+
 struct Produced { const uint8_t *host; size_t bytes; uint8_t *dev; int level; };
 
-static const Produced *find_produced(const std::vector<Produced> &v, const void *p)
+static Produced *find_produced(std::vector<Produced> &v, const void *p)
 {
     const uint8_t *q = static_cast<const uint8_t *>(p);
-    for (const Produced &pr : v) if (q >= pr.host && q < pr.host + pr.bytes) return &pr;
+    for (size_t i = v.size(); i-- > 0;) if (q >= v[i].host && q < v[i].host + v[i].bytes) return &v[i];     // newest first
     return nullptr;
 }
 
-// Runs `nodes` (MUL_MAT / CPY, already validated to be runnable, in graph order).
+// Runs `nodes` (already validated to be runnable, in graph order; view ops are not in the list).
 static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output)
 {
     int rc = ensure_init();
@@ -417,25 +481,28 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         pool->register_tried = true;
         if (cudaHostRegister(pool->host_base, pool->bytes, cudaHostRegisterDefault) == cudaSuccess) pool->registered = true; else cudaGetLastError();
     }
+    auto out_tensor = [](ggml_tensor *t) -> ggml_tensor * { return t->op == GGML_OP_CPY ? t->src1 : t; };      // whose data the node writes
 
-    // ---- pass 1: sizes, so the scratch arena is allocated once before anything is enqueued ----
+    // ---- pass 1: an upper bound of the scratch needed, so the arena is allocated once before anything is enqueued ----
     size_t need = 0;
-    std::vector<Produced> produced_plan;
-    for (size_t i = 0; i < n; i++) {
-        ggml_tensor *t = nodes[i];
-        const ggml_tensor *a = t->src0, *b = t->src1;
-        if (t->op == GGML_OP_MUL_MAT) {
-            const bool a_dev = find_produced(produced_plan, a->data) != nullptr;
-            const bool a_cached = !a_dev && a->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE);
-            if (!a_dev && !a_cached) need += align_up(tensor_span(a), 256);
-            if (!find_produced(produced_plan, b->data)) need += align_up(tensor_span(b), 256);
-            need += align_up(tensor_span(t), 256);
-            need += (size_t)(a->ne[2] * a->ne[3]) * mm_ws_bytes_bound(a->type, a->ne[1], a->ne[0], b->ne[1]);
-            produced_plan.push_back({static_cast<const uint8_t *>(t->data), tensor_span(t), nullptr, 0});
-        } else {
-            if (!find_produced(produced_plan, a->data)) need += align_up(tensor_span(a), 256);
-            need += align_up(tensor_span(b), 256);
-            produced_plan.push_back({static_cast<const uint8_t *>(b->data), tensor_span(b), nullptr, 0});
+    {
+        std::vector<Produced> plan;
+        for (size_t i = 0; i < n; i++) {
+            ggml_tensor *t = nodes[i];
+            const ggml_tensor *a = t->src0, *b = t->src1;
+            if (t->op == GGML_OP_MUL_MAT) {
+                const bool a_dev = find_produced(plan, a->data) != nullptr;
+                const bool a_cached = !a_dev && a->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE);
+                if (!a_dev && !a_cached) need += align_up(tensor_span(a), 256);
+                if (!find_produced(plan, b->data)) need += align_up(tensor_span(b), 256);
+                need += (size_t)(a->ne[2] * a->ne[3]) * mm_ws_bytes_bound(a->type, a->ne[1], a->ne[0], b->ne[1]);
+            } else {
+                if (!find_produced(plan, a->data)) need += align_up(tensor_span(a), 256);
+                if (b && t->op != GGML_OP_CPY && t->op != GGML_OP_SCALE && !find_produced(plan, b->data)) need += align_up(tensor_span(b), 256);
+            }
+            ggml_tensor *o = out_tensor(t);
+            need += align_up(tensor_span(o), 256);
+            plan.push_back({static_cast<const uint8_t *>(o->data), tensor_span(o), nullptr, 0});
         }
     }
     rc = pool->arena.reserve(need + 4096);
@@ -449,56 +516,79 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     struct Item { ggml_tensor *t; int level; uint8_t *da, *db, *dd; };
     std::vector<Item> items(n);
     int max_level = 0;
-    for (size_t i = 0; i < n; i++) {
-        ggml_tensor *t = nodes[i];
-        ggml_tensor *a = t->src0, *b = t->src1;
-        Item &it = items[i];
-        it.t = t; it.level = 0;
-        // src0
-        if (const Produced *pr = find_produced(produced, a->data)) {
-            it.da = pr->dev + (static_cast<const uint8_t *>(a->data) - pr->host);
-            it.level = std::max(it.level, pr->level + 1);
-        } else if (t->op == GGML_OP_MUL_MAT && a->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE)) {
-            const size_t span = tensor_span(a);
-            auto f = pool->mirrors.find(a->data);
+    auto drop_mirror = [&](const void *hostp) {
+        auto f = pool->mirrors.find(hostp);
+        if (f != pool->mirrors.end()) { cudaFree(f->second.dptr); pool->mirrors.erase(f); }
+    };
+    // device address of an operand: produced earlier in this call, a cached weight mirror, read in place from the pinned
+    // arena (small tensors, UVA), or uploaded into the scratch arena
+    auto stage = [&](const ggml_tensor *x, int &level, bool weight, uint8_t *&out) -> int {
+        if (Produced *pr = find_produced(produced, x->data)) {
+            out = pr->dev + (static_cast<const uint8_t *>(x->data) - pr->host);
+            level = std::max(level, pr->level + 1);
+            return GGB_OK;
+        }
+        const size_t span = tensor_span(x);
+        if (weight && x->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE)) {
+            auto f = pool->mirrors.find(x->data);
             if (f != pool->mirrors.end() && f->second.bytes < span) { cudaFree(f->second.dptr); pool->mirrors.erase(f); f = pool->mirrors.end(); }
             if (f == pool->mirrors.end()) {
                 void *d = nullptr;
                 GGB_CUDA(cudaMalloc(&d, align_up(span, 256)));
-                GGB_CUDA(cudaMemcpyAsync(d, a->data, span, cudaMemcpyHostToDevice, s));
+                GGB_CUDA(cudaMemcpyAsync(d, x->data, span, cudaMemcpyHostToDevice, s));
                 g_stats.h2d_bytes += span; g_stats.weight_uploads++;
-                f = pool->mirrors.emplace(a->data, Mirror{d, span}).first;
+                f = pool->mirrors.emplace(x->data, Mirror{d, span}).first;
             } else g_stats.weight_cache_hits++;
-            it.da = static_cast<uint8_t *>(f->second.dptr);
+            out = static_cast<uint8_t *>(f->second.dptr);
+            return GGB_OK;
+        }
+        if (!weight && pool->owned && span <= ZC_MAX && (reinterpret_cast<uintptr_t>(x->data) & 3) == 0) {
+            out = static_cast<uint8_t *>(x->data);               // UVA: kernels read the pinned arena directly
         } else {
+            out = static_cast<uint8_t *>(pool->arena.take(span));
+            GGB_CUDA(cudaMemcpyAsync(out, x->data, span, cudaMemcpyHostToDevice, s));
+        }
+        g_stats.h2d_bytes += span;
+        return GGB_OK;
+    };
+    for (size_t i = 0; i < n; i++) {
+        ggml_tensor *t = nodes[i];
+        ggml_tensor *a = t->src0, *b = t->src1;
+        Item &it = items[i];
+        it.t = t; it.level = 0; it.da = it.db = it.dd = nullptr;
+        ggml_tensor *o = out_tensor(t);
+        const size_t ospan = tensor_span(o);
+        // does the node write over one of its inputs (ggml_scale, ggml_*_inplace: the result is a view of src0)?
+        const uint8_t *od = static_cast<const uint8_t *>(o->data), *ad = static_cast<const uint8_t *>(a->data);
+        const bool in_place = t->op != GGML_OP_CPY && od >= ad && od < ad + tensor_span(a);
+        if (in_place && t->op != GGML_OP_SCALE && t->op != GGML_OP_ADD && t->op != GGML_OP_MUL && t->op != GGML_OP_SILU && t->op != GGML_OP_RMS_NORM)
+            return set_error(GGB_E_UNSUPPORTED, "op %d writing over its own source is not supported", t->op);
+        if (in_place && od != ad) return set_error(GGB_E_UNSUPPORTED, "in-place op %d on a shifted view", t->op);
+        if (in_place && !find_produced(produced, a->data)) {
+            // in place on a leaf: work on an arena copy (never on the pinned host arena directly, never on a cached mirror)
             const size_t span = tensor_span(a);
             it.da = static_cast<uint8_t *>(pool->arena.take(span));
             GGB_CUDA(cudaMemcpyAsync(it.da, a->data, span, cudaMemcpyHostToDevice, s));
             g_stats.h2d_bytes += span;
-        }
-        if (t->op == GGML_OP_MUL_MAT) {
-            if (const Produced *pr = find_produced(produced, b->data)) {
-                it.db = pr->dev + (static_cast<const uint8_t *>(b->data) - pr->host);
-                it.level = std::max(it.level, pr->level + 1);
-            } else {
-                const size_t span = tensor_span(b);
-                if (pool->owned && span <= ZC_MAX && (reinterpret_cast<uintptr_t>(b->data) & 3) == 0) {
-                    it.db = static_cast<uint8_t *>(b->data);            // UVA: the activation kernel reads the pinned arena directly
-                } else {
-                    it.db = static_cast<uint8_t *>(pool->arena.take(span));
-                    GGB_CUDA(cudaMemcpyAsync(it.db, b->data, span, cudaMemcpyHostToDevice, s));
-                }
-                g_stats.h2d_bytes += span;
-            }
-            it.dd = static_cast<uint8_t *>(pool->arena.take(tensor_span(t)));
-            produced.push_back({static_cast<const uint8_t *>(t->data), tensor_span(t), it.dd, it.level});
+            drop_mirror(a->data);
         } else {
-            it.db = nullptr;
-            it.dd = static_cast<uint8_t *>(pool->arena.take(tensor_span(b)));
-            // a CPY rewrites b->data: a cached mirror of it is stale from here on
-            auto f = pool->mirrors.find(b->data);
-            if (f != pool->mirrors.end()) { cudaFree(f->second.dptr); pool->mirrors.erase(f); }
-            produced.push_back({static_cast<const uint8_t *>(b->data), tensor_span(b), it.dd, it.level});
+            rc = stage(a, it.level, t->op == GGML_OP_MUL_MAT, it.da);
+            if (rc) return rc;
+        }
+        if (b && t->op != GGML_OP_CPY && t->op != GGML_OP_SCALE && t->op != GGML_OP_REPEAT) {
+            rc = stage(b, it.level, false, it.db);
+            if (rc) return rc;
+        }
+        if (in_place) {
+            // runs after every earlier node (some of them may still read the old contents), and later readers wait for it
+            it.level = std::max(it.level, max_level + 1);
+            it.dd = it.da;
+            if (Produced *pr = find_produced(produced, a->data)) pr->level = it.level;
+            else produced.push_back({od, ospan, it.dd, it.level});
+        } else {
+            it.dd = static_cast<uint8_t *>(pool->arena.take(ospan));
+            if (t->op == GGML_OP_CPY) drop_mirror(o->data);      // a CPY rewrites b->data: a cached mirror of it is stale from here on
+            produced.push_back({od, ospan, it.dd, it.level});
         }
         max_level = std::max(max_level, it.level);
     }
@@ -508,7 +598,8 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         for (Item &it : items) {
             if (it.level != lv) continue;
             ggml_tensor *t = it.t; const ggml_tensor *a = t->src0, *b = t->src1;
-            if (t->op == GGML_OP_MUL_MAT) {
+            switch (t->op) {
+            case GGML_OP_MUL_MAT:
                 for (int64_t i3 = 0; i3 < a->ne[3]; i3++) for (int64_t i2 = 0; i2 < a->ne[2]; i2++) {
                     ggb_dev_mm m = {};
                     m.type = a->type; m.M = a->ne[1]; m.K = a->ne[0]; m.N = b->ne[1];
@@ -519,11 +610,35 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                     m.ldy_bytes = a->type == GGML_TYPE_F32 ? (int64_t)t->nb[1] : (int64_t)t->ne[0] * 4;
                     mms.push_back(m);
                 }
-            } else {
-                const int64_t rows = b->ne[1] * b->ne[2] * b->ne[3];
-                rc = launch_quantize_rows(b->type, reinterpret_cast<const float *>(it.da), a->ne[0], it.dd, rows, b->ne[0], s);
-                if (rc) return rc;
+                break;
+            case GGML_OP_CPY:
+                rc = launch_quantize_rows(b->type, reinterpret_cast<const float *>(it.da), a->ne[0], it.dd, b->ne[1] * b->ne[2] * b->ne[3], b->ne[0], s);
+                break;
+            case GGML_OP_ADD:
+                if (a->type != GGML_TYPE_F32) { rc = launch_add_q_f32(a->type, it.da, reinterpret_cast<const float *>(it.db), it.dd, a->ne[1] * a->ne[2] * a->ne[3], a->ne[0], s); break; }
+                // fallthrough
+            case GGML_OP_MUL:
+                rc = launch_binary_f32(t->op, reinterpret_cast<const float *>(it.da), reinterpret_cast<const float *>(it.db), reinterpret_cast<float *>(it.dd), nelements(t), s);
+                break;
+            case GGML_OP_SILU:
+                rc = launch_silu_f32(reinterpret_cast<const float *>(it.da), reinterpret_cast<float *>(it.dd), nelements(t), s);
+                break;
+            case GGML_OP_RMS_NORM:
+                rc = launch_rms_norm_f32(reinterpret_cast<const float *>(it.da), a->ne[0], reinterpret_cast<float *>(it.dd), t->ne[0], a->ne[1] * a->ne[2] * a->ne[3], a->ne[0], s);
+                break;
+            case GGML_OP_SCALE:
+                rc = launch_scale_f32(reinterpret_cast<float *>(it.dd), *static_cast<const float *>(b->data), nelements(t), s);   // float v = *(float*)src1->data (Ggml.cs:6763)
+                break;
+            case GGML_OP_REPEAT:
+                rc = launch_repeat_f32(reinterpret_cast<const float *>(it.da), (int64_t)(a->nb[1] / 4), a->ne[0], a->ne[1], reinterpret_cast<float *>(it.dd), (int64_t)(t->nb[1] / 4), t->ne[0], t->ne[1], s);
+                break;
+            case GGML_OP_CONT: case GGML_OP_DUP:
+                rc = launch_dup_f32_strided(it.da, a->ne, a->nb, reinterpret_cast<float *>(it.dd), s);
+                break;
+            default:
+                rc = set_error(GGB_E_UNSUPPORTED, "executor: op %d", t->op);
             }
+            if (rc) return rc;
         }
         if (!mms.empty()) {
             size_t wsb = 0;
@@ -539,9 +654,10 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     for (size_t i = 0; i < n; i++) {
         const Item &it = items[i];
         ggml_tensor *t = it.t;
-        if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i] && t->op == GGML_OP_MUL_MAT) continue;   // a CPY target is user-visible
-        void *hdst = t->op == GGML_OP_MUL_MAT ? t->data : t->src1->data;
-        const size_t span = t->op == GGML_OP_MUL_MAT ? tensor_span(t) : tensor_span(t->src1);
+        if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i] && t->op != GGML_OP_CPY) continue;   // a CPY target is user-visible
+        ggml_tensor *o = out_tensor(t);
+        void *hdst = o->data;
+        const size_t span = tensor_span(o);
         if (pool->owned && span <= ZC_MAX && (span & 3) == 0 && (reinterpret_cast<uintptr_t>(hdst) & 15) == 0) {
             CopySeg &sg = cb.seg[cb.n++];
             sg.src = it.dd; sg.dst = static_cast<uint8_t *>(hdst); sg.bytes = (unsigned)span; sg.vec0 = cb.total_vec;
@@ -676,39 +792,54 @@ int ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *g, int flags, uint8_
     std::lock_guard<std::mutex> lk(g_mu);
     if (!pool || !g) return set_error(GGB_E_INVALID, "ggb_graph_compute_mul_mats: null argument");
     if (g->n_nodes < 0 || g->n_nodes > GGML_MAX_NODES) return set_error(GGB_E_INVALID, "graph with %d nodes", g->n_nodes);
-    // A node is runnable here if it is a MUL_MAT / supported CPY whose operands are leafs (op NONE) or runnable nodes.
+    // A node is runnable here if it is on the path (MUL_MAT, the F32 -> {F16,Q4_0,Q4_1} CPY, and unless GGB_GRAPH_MUL_MAT_ONLY the
+    // neighbours of mul_mat) and its operands are leafs (op NONE) or runnable nodes.  RESHAPE / VIEW / PERMUTE / TRANSPOSE do
+    // nothing at compute time (Ggml.cs:8668-8687): they are "runnable" when their source is, marked done, and never enqueued.
     std::vector<ggml_tensor *> run;
-    std::vector<int> run_idx;
+    std::vector<int> run_idx, view_idx;
     std::map<const ggml_tensor *, bool> runnable;
+    const bool neighbours = !(flags & GGB_GRAPH_MUL_MAT_ONLY);
     for (int i = 0; i < g->n_nodes; i++) {
         ggml_tensor *t = g->nodes[i];
         if (done) done[i] = 0;
         if (!t) return set_error(GGB_E_INVALID, "graph node %d is null", i);
+        auto operand_ok = [&](const ggml_tensor *o) { return o && (o->op == GGML_OP_NONE || runnable.count(o)); };
         bool ok = false;
-        if (t->op == GGML_OP_MUL_MAT || t->op == GGML_OP_CPY) {
-            auto operand_ok = [&](const ggml_tensor *o) { return o && (o->op == GGML_OP_NONE || runnable.count(o)); };
-            if (operand_ok(t->src0) && operand_ok(t->src1)) {
-                int rc = t->op == GGML_OP_MUL_MAT ? validate_mul_mat(t) : validate_cpy(t);
+        if (neighbours && is_view_op(t->op)) {
+            if (operand_ok(t->src0)) { runnable[t] = true; view_idx.push_back(i); }
+            continue;
+        }
+        if (t->op == GGML_OP_MUL_MAT || t->op == GGML_OP_CPY || (neighbours && is_neighbour_op(t->op))) {
+            const bool unary = t->op == GGML_OP_SILU || t->op == GGML_OP_RMS_NORM || t->op == GGML_OP_CONT || t->op == GGML_OP_DUP;
+            // REPEAT's src1 only supplies the shape (Ggml.cs:8015-8034); it is never read
+            const bool need_b = !unary && t->op != GGML_OP_REPEAT;
+            if (operand_ok(t->src0) && (!need_b || operand_ok(t->src1))) {
+                int rc = t->op == GGML_OP_MUL_MAT ? validate_mul_mat(t) : t->op == GGML_OP_CPY ? validate_cpy(t) : validate_neighbour(t);
                 if (rc == GGB_E_INVALID) return rc;        // the reference would assert: report it
                 ok = rc == GGB_OK;                         // unsupported: leave the node to the caller's loop
             }
         }
         if (ok) { runnable[t] = true; run.push_back(t); run_idx.push_back(i); }
     }
-    // graph outputs = executed nodes nobody else in the executed set consumes
+    // graph outputs = executed nodes nobody else in the executed set consumes (views are looked through)
+    auto base_of = [](const ggml_tensor *o) { while (o && is_view_op(o->op) && o->src0) o = o->src0; return o; };
     std::vector<char> is_output(run.size(), 1);
     for (size_t i = 0; i < run.size(); i++)
         for (size_t j = i + 1; j < run.size(); j++)
-            if (run[j]->src0 == run[i] || run[j]->src1 == run[i]) is_output[i] = 0;
+            if (base_of(run[j]->src0) == run[i] || base_of(run[j]->src1) == run[i]) is_output[i] = 0;
     // a consumer outside the executed set (a CPU op of the caller) needs the data on the host
     for (int i = 0; i < g->n_nodes; i++) {
         ggml_tensor *t = g->nodes[i];
         if (runnable.count(t)) continue;
-        for (size_t j = 0; j < run.size(); j++) if (t->src0 == run[j] || t->src1 == run[j]) is_output[j] = 1;
+        for (size_t j = 0; j < run.size(); j++) if (base_of(t->src0) == run[j] || base_of(t->src1) == run[j]) is_output[j] = 1;
     }
+    // an in-place node (SCALE, *_inplace) shares its host bytes with its source: the LAST writer of a range carries the result
+    for (size_t i = 0; i < run.size(); i++)
+        for (size_t j = i + 1; j < run.size(); j++)
+            if (run[j]->op != GGML_OP_CPY && run[j]->data == run[i]->data && run[i]->op != GGML_OP_CPY) is_output[i] = 0;
     int rc = run_nodes(pool, run, flags, is_output);
     if (rc) return rc;
-    if (done) for (int i : run_idx) done[i] = 1;
+    if (done) { for (int i : run_idx) done[i] = 1; for (int i : view_idx) done[i] = 1; }
     g->perf_runs++;
     g->perf_time_us += (int64_t)(g_stats.last_graph_device_ms * 1000.0);
     return (int)run.size();
@@ -782,6 +913,19 @@ int ggb_dev_dequantize_rows(int type, const void *src, float *dst, int64_t nrows
     if (rc) return rc;
     return launch_dequantize_rows(type, src, dst, nrows, k, stream ? static_cast<cudaStream_t>(stream) : g_stream);
 }
+
+#define GGB_DEV_WRAP(call) do { int rc_ = ensure_init(); if (rc_) return rc_; cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_stream; return call; } while (0)
+int ggb_dev_binary(int op, const float *a, const float *b, float *dst, int64_t n, void *stream) { GGB_DEV_WRAP(launch_binary_f32(op, a, b, dst, n, st)); }
+int ggb_dev_scale(float *x, float v, int64_t n, void *stream) { GGB_DEV_WRAP(launch_scale_f32(x, v, n, st)); }
+int ggb_dev_silu(const float *x, float *dst, int64_t n, void *stream) { GGB_DEV_WRAP(launch_silu_f32(x, dst, n, st)); }
+int ggb_dev_rms_norm(const float *x, int64_t x_stride, float *dst, int64_t dst_stride, int64_t nrows, int64_t ne00, void *stream)
+{ GGB_DEV_WRAP(launch_rms_norm_f32(x, x_stride, dst, dst_stride, nrows, ne00, st)); }
+int ggb_dev_repeat(const float *src, int64_t src_stride, int64_t nc0, int64_t nr0, float *dst, int64_t dst_stride, int64_t nc, int64_t nr, void *stream)
+{ GGB_DEV_WRAP(launch_repeat_f32(src, src_stride, nc0, nr0, dst, dst_stride, nc, nr, st)); }
+int ggb_dev_cont(const void *src, const int64_t ne[4], const uint64_t nb[4], float *dst, void *stream) { GGB_DEV_WRAP(launch_dup_f32_strided(src, ne, nb, dst, st)); }
+int ggb_dev_add_q(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k, void *stream)
+{ GGB_DEV_WRAP(launch_add_q_f32(type, src0, src1, dst, nrows, k, st)); }
+#undef GGB_DEV_WRAP
 
 int ggb_dev_alloc(size_t bytes, void **dptr)
 {

@@ -70,6 +70,13 @@ class Context:
             raise N.GgbError(N.host().ggml_host_last_status(), "ggml_cpy rejected the operands")
         return r
 
+    def op(self, name, *operands):
+        """ggml_add / ggml_mul / ggml_scale / ggml_repeat / ggml_silu / ggml_rms_norm / ggml_cont / ggml_transpose / *_inplace."""
+        r = getattr(N.host(), "ggml_" + name)(self.ctx, *operands)
+        if not r:
+            raise N.GgbError(N.host().ggml_host_last_status(), "ggml_%s rejected the operands" % name)
+        return r
+
     def build_forward(self, t):
         g = N.ggml_cgraph()
         N.host().ggml_build_forward_into(C.byref(g), t)

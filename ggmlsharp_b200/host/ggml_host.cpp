@@ -13,7 +13,8 @@
 //   ggml_graph_compute                        Ggml.cs:3209-3736   (seam B: MUL_MAT/CPY nodes -> CUDA stream executor)
 //
 // Everything arithmetic happens in libggb200.so; this file only builds tensor headers and graphs.
-// Ops other than MUL_MAT / CPY are outside the path: ggml_graph_compute reports them and stops.
+//   ggml_add / mul / silu / rms_norm / scale / repeat / cont / transpose (builders)   Ggml.cs:6846-7225, 7868-8322
+// Ops outside the path: ggml_graph_compute reports them and stops.
 #include "../../include/ggb200.h"
 
 #include <cstdio>
@@ -77,6 +78,7 @@ ggb_pool *pool_of(const ggml_context *ctx)
 extern "C" {
 
 int ggml_host_last_status(void) { return g_last_status; }
+void *ggml_host_pool_of(const ggml_context *ctx) { return pool_of(ctx); }       // tests drive seam B directly with flags
 
 ggml_context *ggml_init(ggml_init_params params)
 {
@@ -213,6 +215,71 @@ ggml_tensor *ggml_cpy(ggml_context *ctx, ggml_tensor *a, ggml_tensor *b)
     r->op = GGML_OP_CPY;
     r->src0 = a;
     r->src1 = b;
+    return r;
+}
+
+// ---- the neighbours of mul_mat in a Llama layer: builders only, the arithmetic is in libggb200.so ----
+
+static bool ggml_are_same_shape(const ggml_tensor *a, const ggml_tensor *b) { return a->ne[0] == b->ne[0] && a->ne[1] == b->ne[1] && a->ne[2] == b->ne[2] && a->ne[3] == b->ne[3]; }
+// ggml_dup_tensor / ggml_view_tensor (Ggml.cs:2397-2406, 2850-2861)
+ggml_tensor *ggml_dup_tensor(ggml_context *ctx, const ggml_tensor *src) { return ggml_new_tensor_impl(ctx, src->type, src->n_dims, src->ne, nullptr); }
+ggml_tensor *ggml_view_tensor(ggml_context *ctx, const ggml_tensor *src)
+{
+    ggml_tensor *r = ggml_new_tensor_impl(ctx, src->type, src->n_dims, src->ne, src->data);
+    if (r) for (int i = 0; i < GGML_MAX_DIMS; i++) r->nb[i] = src->nb[i];
+    return r;
+}
+static ggml_tensor *unary_or_binary(ggml_context *ctx, int op, ggml_tensor *a, ggml_tensor *b, bool inplace)
+{
+    ggml_tensor *r = inplace ? ggml_view_tensor(ctx, a) : ggml_dup_tensor(ctx, a);
+    if (!r) return nullptr;
+    r->op = op; r->src0 = a; r->src1 = b;
+    return r;
+}
+// Ggml.cs:7868-7890, 7918-7945: Debug.Assert(ggml_are_same_shape(a, b))
+ggml_tensor *ggml_add(ggml_context *ctx, ggml_tensor *a, ggml_tensor *b)
+{
+    if (!ggml_are_same_shape(a, b)) { g_last_status = GGB_E_INVALID; return nullptr; }
+    return unary_or_binary(ctx, GGML_OP_ADD, a, b, false);
+}
+ggml_tensor *ggml_add_inplace(ggml_context *ctx, ggml_tensor *a, ggml_tensor *b)
+{
+    if (!ggml_are_same_shape(a, b)) { g_last_status = GGB_E_INVALID; return nullptr; }
+    return unary_or_binary(ctx, GGML_OP_ADD, a, b, true);
+}
+ggml_tensor *ggml_mul(ggml_context *ctx, ggml_tensor *a, ggml_tensor *b)
+{
+    if (!ggml_are_same_shape(a, b)) { g_last_status = GGB_E_INVALID; return nullptr; }
+    return unary_or_binary(ctx, GGML_OP_MUL, a, b, false);
+}
+ggml_tensor *ggml_silu(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_SILU, a, nullptr, false); }                 // Ggml.cs:8154-8174
+ggml_tensor *ggml_silu_inplace(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_SILU, a, nullptr, true); }
+ggml_tensor *ggml_rms_norm(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_RMS_NORM, a, nullptr, false); }         // Ggml.cs:8199-8220
+ggml_tensor *ggml_cont(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_CONT, a, nullptr, false); }                 // Ggml.cs:8301-8322
+// Ggml.cs:8248-8271: the result is ALWAYS a view of a (the reference's TODO), so the node scales a's data in place
+ggml_tensor *ggml_scale(ggml_context *ctx, ggml_tensor *a, ggml_tensor *b)
+{
+    if (ggml_nelements(b) != 1) { g_last_status = GGB_E_INVALID; return nullptr; }
+    return unary_or_binary(ctx, GGML_OP_SCALE, a, b, true);
+}
+// Ggml.cs:8015-8040: result has b's shape; ggml_can_repeat (8398-8407)
+ggml_tensor *ggml_repeat(ggml_context *ctx, ggml_tensor *a, ggml_tensor *b)
+{
+    for (int i = 0; i < GGML_MAX_DIMS; i++) if (a->ne[i] <= 0 || b->ne[i] % a->ne[i]) { g_last_status = GGB_E_INVALID; return nullptr; }
+    if (ggml_are_same_shape(a, b)) return a;
+    ggml_tensor *r = ggml_new_tensor(ctx, a->type, b->n_dims, b->ne);
+    if (!r) return nullptr;
+    r->op = GGML_OP_REPEAT; r->src0 = a; r->src1 = b;
+    return r;
+}
+// Ggml.cs:7199-7225: a view with ne0/ne1 and nb0/nb1 swapped
+ggml_tensor *ggml_transpose(ggml_context *ctx, ggml_tensor *a)
+{
+    ggml_tensor *r = ggml_view_tensor(ctx, a);
+    if (!r) return nullptr;
+    r->ne[0] = a->ne[1]; r->ne[1] = a->ne[0];
+    r->nb[0] = a->nb[1]; r->nb[1] = a->nb[0];
+    r->op = GGML_OP_TRANSPOSE; r->src0 = a; r->src1 = nullptr;
     return r;
 }
 

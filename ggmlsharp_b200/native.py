@@ -8,8 +8,9 @@ LIBDIR = os.path.join(HERE, "lib")
 GGML_MAX_DIMS, GGML_MAX_NODES, GGML_MAX_OPT = 4, 4096, 4
 F32, F16, Q4_0, Q4_1, Q8_0, Q8_1, I8, I16, I32 = 0, 1, 2, 3, 8, 9, 10, 11, 12
 OP_NONE, OP_MUL_MAT, OP_CPY = 0, 20, 22
+OP_DUP, OP_ADD, OP_MUL, OP_REPEAT, OP_SILU, OP_RMS_NORM, OP_SCALE, OP_CONT, OP_TRANSPOSE = 1, 2, 4, 10, 17, 19, 21, 23, 27
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_ABI, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
-GRAPH_KEEP_ON_DEVICE, GRAPH_NO_WEIGHT_CACHE = 1, 2
+GRAPH_KEEP_ON_DEVICE, GRAPH_NO_WEIGHT_CACHE, GRAPH_MUL_MAT_ONLY = 1, 2, 4
 
 TYPE_SIZE = {F32: 4, F16: 2, Q4_0: 20, Q4_1: 24, Q8_0: 36, Q8_1: 44, I8: 1, I16: 2, I32: 4}
 BLCK_SIZE = {F32: 1, F16: 1, Q4_0: 32, Q4_1: 32, Q8_0: 32, Q8_1: 32, I8: 1, I16: 1, I32: 1}
@@ -99,6 +100,13 @@ GGB_SYMBOLS = {
     "ggb_dev_mul_mat_batch": (C.c_int, [C.POINTER(ggb_dev_mm), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ggb_dev_quantize_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "ggb_dev_dequantize_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "ggb_dev_binary": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ggb_dev_scale": (C.c_int, [C.c_void_p, C.c_float, C.c_int64, C.c_void_p]),
+    "ggb_dev_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ggb_dev_rms_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "ggb_dev_repeat": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "ggb_dev_cont": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]),
+    "ggb_dev_add_q": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "ggb_dev_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "ggb_dev_free": (C.c_int, [C.c_void_p]),
     "ggb_dev_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -116,6 +124,7 @@ GGB_SYMBOLS = {
 
 HOST_SYMBOLS = {
     "ggml_host_last_status": (C.c_int, []),
+    "ggml_host_pool_of": (C.c_void_p, [C.POINTER(ggml_context)]),
     "ggml_init": (C.POINTER(ggml_context), [ggml_init_params]),
     "ggml_free": (None, [C.POINTER(ggml_context)]),
     "ggml_nelements": (C.c_int64, [TP]),
@@ -131,6 +140,18 @@ HOST_SYMBOLS = {
     "ggml_get_f32_1d": (C.c_float, [TP, C.c_int]),
     "ggml_mul_mat": (TP, [C.POINTER(ggml_context), TP, TP]),
     "ggml_cpy": (TP, [C.POINTER(ggml_context), TP, TP]),
+    "ggml_add": (TP, [C.POINTER(ggml_context), TP, TP]),
+    "ggml_add_inplace": (TP, [C.POINTER(ggml_context), TP, TP]),
+    "ggml_mul": (TP, [C.POINTER(ggml_context), TP, TP]),
+    "ggml_scale": (TP, [C.POINTER(ggml_context), TP, TP]),
+    "ggml_repeat": (TP, [C.POINTER(ggml_context), TP, TP]),
+    "ggml_silu": (TP, [C.POINTER(ggml_context), TP]),
+    "ggml_silu_inplace": (TP, [C.POINTER(ggml_context), TP]),
+    "ggml_rms_norm": (TP, [C.POINTER(ggml_context), TP]),
+    "ggml_cont": (TP, [C.POINTER(ggml_context), TP]),
+    "ggml_transpose": (TP, [C.POINTER(ggml_context), TP]),
+    "ggml_dup_tensor": (TP, [C.POINTER(ggml_context), TP]),
+    "ggml_view_tensor": (TP, [C.POINTER(ggml_context), TP]),
     "ggml_build_forward_expand": (None, [C.POINTER(ggml_cgraph), TP]),
     "ggml_build_forward_into": (None, [C.POINTER(ggml_cgraph), TP]),
     "ggml_graph_compute": (None, [C.POINTER(ggml_context), C.POINTER(ggml_cgraph)]),

@@ -46,7 +46,9 @@ typedef enum ggml_type {
 } ggml_type;
 
 /* TypeDefinitions.cs:172-220 (only the values this path dispatches on) */
-enum { GGML_OP_NONE = 0, GGML_OP_DUP = 1, GGML_OP_MUL_MAT = 20, GGML_OP_SCALE = 21, GGML_OP_CPY = 22, GGML_OP_CONT = 23 };
+enum { GGML_OP_NONE = 0, GGML_OP_DUP = 1, GGML_OP_ADD = 2, GGML_OP_MUL = 4, GGML_OP_REPEAT = 10, GGML_OP_SILU = 17, GGML_OP_RMS_NORM = 19,
+       GGML_OP_MUL_MAT = 20, GGML_OP_SCALE = 21, GGML_OP_CPY = 22, GGML_OP_CONT = 23, GGML_OP_RESHAPE = 24, GGML_OP_VIEW = 25,
+       GGML_OP_PERMUTE = 26, GGML_OP_TRANSPOSE = 27 };
 
 /* TypeDefinitions.cs:65-99 -- 176 bytes, data at 160 */
 typedef struct ggml_tensor {
@@ -144,8 +146,9 @@ int  ggb_tensor_invalidate(ggb_pool *pool, const ggml_tensor *t);
  * src1 (and src0 unless cached), runs the kernels, copies dst->data back, fills perf_*. */
 int  ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst);
 
-#define GGB_GRAPH_KEEP_ON_DEVICE 1   /* do not copy intermediate MUL_MAT results back (only graph outputs) */
+#define GGB_GRAPH_KEEP_ON_DEVICE 1   /* do not copy intermediate results back (only graph outputs) */
 #define GGB_GRAPH_NO_WEIGHT_CACHE 2  /* re-upload every src0 (what the CPU path observes if weights change) */
+#define GGB_GRAPH_MUL_MAT_ONLY 4     /* round-1 behaviour: run MUL_MAT and F32->{F16,Q4_0,Q4_1} CPY nodes only */
 
 /* Called from ggml_graph_compute (Ggml.cs:3539) instead of walking MUL_MAT nodes one by one:
  * runs, in node order and on one stream with one final sync, every MUL_MAT node (and F32->
@@ -153,6 +156,13 @@ int  ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst);
  * are leafs or nodes it runs itself.  done[i] (n_nodes bytes, may be NULL) is set to 1 for each
  * node it executed; the caller's loop runs the rest.  Returns the number executed or < 0. */
 int  ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *graph, int flags, uint8_t *done);
+/* Unless GGB_GRAPH_MUL_MAT_ONLY is set the same call also keeps the neighbours of mul_mat in a Llama layer on the device
+ * (SURVEY.md 8f), so consecutive MUL_MATs need no host round trip: F32 ADD / MUL (Ggml.cs:4622-4685, 5007-5034), SILU
+ * (5705-5747, fp16 table semantics of GGML_SILU_FP16), RMS_NORM (5858-5921), SCALE (6746-6780, in place on the view of src0),
+ * ADD with Q4_0 / Q4_1 src0 (add_q_f32, 4797-4906), 2-D REPEAT (5340-5383) and CONT / DUP of a transposed or permuted F32 tensor (4199-4398; what
+ * MUL_MAT's backward issues, 7453-7462).  RESHAPE / VIEW / PERMUTE / TRANSPOSE nodes are no-ops in the reference
+ * (8668-8687) and are marked done.  An element-wise node is taken only when at least one operand is produced on the device
+ * by this call (otherwise uploading it would cost more than the C# loop); contiguous tensors only. */
 
 /* ---- the codec column of quantize_fns[] (Ggml.cs:219-290) ----------------------------- */
 
@@ -186,6 +196,17 @@ int  ggb_dev_mul_mat_batch(const ggb_dev_mm *mm, int count, void *workspace, siz
 /* Device-pointer codecs on a stream (no sync). */
 int  ggb_dev_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k, void *stream);
 int  ggb_dev_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k, void *stream);
+
+/* The same neighbours on device pointers (no sync).  op is GGML_OP_ADD or GGML_OP_MUL; n counts floats; rms_norm / repeat row
+ * strides are in floats (repeat: dst[r][c] = src[r % nr0][c % nc0]); ggb_dev_cont copies the strided F32 view (ne, nb in bytes: the fields of a transposed / permuted ggml_tensor) into a
+ * contiguous dst; ggb_dev_add_q is add_q_f32 over nrows contiguous rows of k elements (type Q4_0 or Q4_1), dst may alias src0. */
+int  ggb_dev_binary(int op, const float *a, const float *b, float *dst, int64_t n, void *stream);
+int  ggb_dev_scale(float *x, float v, int64_t n, void *stream);
+int  ggb_dev_silu(const float *x, float *dst, int64_t n, void *stream);
+int  ggb_dev_rms_norm(const float *x, int64_t x_stride, float *dst, int64_t dst_stride, int64_t nrows, int64_t ne00, void *stream);
+int  ggb_dev_repeat(const float *src, int64_t src_stride, int64_t nc0, int64_t nr0, float *dst, int64_t dst_stride, int64_t nc, int64_t nr, void *stream);
+int  ggb_dev_cont(const void *src, const int64_t ne[4], const uint64_t nb[4], float *dst, void *stream);
+int  ggb_dev_add_q(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k, void *stream);
 
 /* Plain device-memory helpers so a host language without a CUDA binding can stage data. */
 int  ggb_dev_alloc(size_t bytes, void **dptr);

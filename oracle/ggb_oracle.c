@@ -478,3 +478,101 @@ int orc_dequantize_rows(int type, const void *x, float *y, int64_t nrows, int64_
 
 void orc_f32_to_f16_row(const float *x, uint16_t *y, int64_t n) { for (int64_t i = 0; i < n; i++) y[i] = orc_f32_to_f16(x[i]); }
 void orc_f16_to_f32_row(const uint16_t *x, float *y, int64_t n) { for (int64_t i = 0; i < n; i++) y[i] = orc_f16_to_f32(x[i]); }
+
+/* ==================================================================================================
+ * Neighbours of mul_mat in a Llama layer: F32 element-wise ops, the quantized
+ * accumulate add_q_f32, and the strided dup behind cont(transpose(x)).  Same rules as above: one C
+ * function per reference function, reference operation order and rounding.
+ * ================================================================================================== */
+
+/* ggml_vec_add_f32 / ggml_vec_mul_f32 (Ggml.cs:2586-2589, 2621-2624) over the rows that
+ * ggml_compute_forward_add_f32 / mul_f32 walk (Ggml.cs:4622-4685, 5007-5034): one float operation per element. */
+void orc_add_f32(int64_t n, const float *x, const float *y, float *z) { for (int64_t i = 0; i < n; i++) z[i] = x[i] + y[i]; }
+void orc_mul_f32(int64_t n, const float *x, const float *y, float *z) { for (int64_t i = 0; i < n; i++) z[i] = x[i] * y[i]; }
+
+/* ggml_compute_forward_scale_f32 (Ggml.cs:6746-6780) -> ggml_vec_scale_f32 (Ggml.cs:1416-1443, scalar branch): the
+ * result tensor is a view of src0 (ggml_scale_impl, Ggml.cs:8248-8271), so dst is scaled in place. */
+void orc_scale_f32(int64_t n, float *y, float v) { for (int64_t i = 0; i < n; i++) y[i] *= v; }
+
+/* ggml_vec_silu_f32 with GGML_SILU_FP16 defined (GGMLSharp.csproj:9; Ggml.cs:2736-2746): y = (float)table_silu_f16[(Half)x],
+ * table_silu_f16[i] = (Half)ggml_silu_f32(f16_to_f32(i)) built in ggml_init (Ggml.cs:1461-1471), ggml_silu_f32(x) =
+ * x / (1.0f + MathF.Exp(-x)) (Ggml.cs:2723-2726).  MathF.Exp is the platform C runtime's expf. */
+static uint16_t g_silu_table[1 << 16];
+static int g_silu_ready = 0;
+static void silu_table_init(void)
+{
+    if (g_silu_ready) return;
+    for (int i = 0; i < (1 << 16); i++) {
+        const float f = orc_f16_to_f32((uint16_t)i);
+        const float e = expf(-f);
+        const float den = 1.0f + e;
+        g_silu_table[i] = orc_f32_to_f16(f / den);
+    }
+    g_silu_ready = 1;
+}
+void orc_silu_table(uint16_t *out) { silu_table_init(); memcpy(out, g_silu_table, sizeof g_silu_table); }
+void orc_silu_f32(int64_t n, const float *x, float *y)
+{
+    silu_table_init();
+    for (int64_t i = 0; i < n; i++) y[i] = orc_f16_to_f32(g_silu_table[orc_f32_to_f16(x[i])]);
+}
+
+/* ggml_compute_forward_rms_norm_f32 (Ggml.cs:5858-5921): per row, sum of float products in a double, mean cast to
+ * float, scale = 1.0f / MathF.Sqrt(mean + eps) with eps = 1e-6f, then y = x * scale. */
+void orc_rms_norm_f32(int64_t nrows, int64_t ne00, const float *x, int64_t x_stride, float *y, int64_t y_stride)
+{
+    const float eps = 1e-6f;
+    for (int64_t r = 0; r < nrows; r++) {
+        const float *xr = x + r * x_stride;
+        float *yr = y + r * y_stride;
+        double sum = 0.0;
+        for (int64_t i = 0; i < ne00; i++) { const float p = xr[i] * xr[i]; sum += p; }
+        const float mean = (float)(sum / (double)(uint64_t)ne00);
+        const float scale = 1.0f / sqrtf(mean + eps);
+        for (int64_t i = 0; i < ne00; i++) yr[i] = xr[i] * scale;
+    }
+}
+
+/* ggml_compute_forward_add_q_f32 (Ggml.cs:4797-4906) for contiguous rows: dequantize_row_q -> ggml_vec_acc_f32
+ * (y[i] += x[i], Ggml.cs:2591-2594) -> quantize_row_q, with the codec table looked up by type (defect D1) and the scalar
+ * quantizers (defect D5). */
+int orc_add_q_f32(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k)
+{
+    if (type != 2 && type != 3) return -2;
+    if (k % 32) return -1;
+    const size_t rb = (size_t)(k / 32) * (type == 2 ? 20 : 24);
+    float *w = (float *)malloc((size_t)k * sizeof(float));
+    if (!w) return -4;
+    for (int64_t r = 0; r < nrows; r++) {
+        const uint8_t *s = (const uint8_t *)src0 + (size_t)r * rb;
+        uint8_t *d = (uint8_t *)dst + (size_t)r * rb;
+        if (type == 2) orc_dequantize_row_q4_0(s, w, (int)k); else orc_dequantize_row_q4_1(s, w, (int)k);
+        for (int64_t i = 0; i < k; i++) w[i] += src1[r * k + i];
+        if (type == 2) orc_quantize_row_q4_0(w, d, (int)k); else orc_quantize_row_q4_1(w, d, (int)k);
+    }
+    free(w);
+    return 0;
+}
+
+/* ggml_compute_forward_dup_f32, non-contiguous source -> contiguous F32 destination (Ggml.cs:4199-4398): elements are
+ * visited in (i03, i02, i01, i00) order and written densely -- what ggml_cont(ggml_transpose(x)) executes
+ * (MUL_MAT's backward, Ggml.cs:7453-7462). */
+void orc_dup_f32_strided(const void *src, const int64_t ne[4], const uint64_t nb[4], float *dst)
+{
+    int64_t id = 0;
+    for (int64_t i3 = 0; i3 < ne[3]; i3++)
+        for (int64_t i2 = 0; i2 < ne[2]; i2++)
+            for (int64_t i1 = 0; i1 < ne[1]; i1++)
+                for (int64_t i0 = 0; i0 < ne[0]; i0++)
+                    dst[id++] = *(const float *)((const char *)src + i0 * nb[0] + i1 * nb[1] + i2 * nb[2] + i3 * nb[3]);
+}
+
+/* ggml_compute_forward_repeat_f32 (Ggml.cs:5340-5383): 2-D tiling of src0 into dst, row copies in (i, j, k) order. */
+void orc_repeat_f32(const float *src, int64_t nc0, int64_t nr0, float *dst, int64_t nc, int64_t nr)
+{
+    const int64_t ncr = nc / nc0, nrr = nr / nr0;
+    for (int64_t i = 0; i < nrr; i++)
+        for (int64_t j = 0; j < ncr; j++)
+            for (int64_t k = 0; k < nr0; k++)
+                memcpy(dst + (i * nr0 + k) * nc + j * nc0, src + k * nc0, (size_t)nc0 * sizeof(float));
+}

@@ -146,3 +146,95 @@ def vec_dot(name, n, x, y):
     s = np.zeros(1, dtype=np.float32)
     getattr(lib(), "orc_vec_dot_" + name)(n, _p(s), _p(np.ascontiguousarray(x)), _p(np.ascontiguousarray(y)))
     return float(s[0])
+
+
+# ---- neighbours of mul_mat: element-wise F32 ops, add_q_f32, cont(transpose) ----
+
+def _bin(name, x, y):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    assert x.shape == y.shape
+    z = np.zeros_like(x)
+    f = getattr(lib(), name)
+    f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(x.size, _p(x), _p(y), _p(z))
+    return z
+
+
+def add_f32(x, y):
+    return _bin("orc_add_f32", x, y)
+
+
+def mul_f32(x, y):
+    return _bin("orc_mul_f32", x, y)
+
+
+def scale_f32(x, v):
+    y = np.array(x, dtype=np.float32, copy=True, order="C")
+    f = lib().orc_scale_f32
+    f.argtypes = [C.c_int64, C.c_void_p, C.c_float]
+    f(y.size, _p(y), float(np.float32(v)))
+    return y
+
+
+def silu_f32(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.zeros_like(x)
+    f = lib().orc_silu_f32
+    f.argtypes = [C.c_int64, C.c_void_p, C.c_void_p]
+    f(x.size, _p(x), _p(y))
+    return y
+
+
+def silu_table():
+    t = np.zeros(1 << 16, dtype=np.uint16)
+    f = lib().orc_silu_table
+    f.argtypes = [C.c_void_p]
+    f(_p(t))
+    return t
+
+
+def rms_norm_f32(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    x2 = x.reshape(-1, x.shape[-1])
+    y = np.zeros_like(x2)
+    f = lib().orc_rms_norm_f32
+    f.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    f(x2.shape[0], x2.shape[1], _p(x2), x2.shape[1], _p(y), x2.shape[1])
+    return y.reshape(x.shape)
+
+
+def add_q_f32(t, q, x):
+    """q: uint8 [nrows, row_bytes] of type t, x: float32 [nrows, k] -> uint8 [nrows, row_bytes] (dequantize + x, requantized)."""
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    nrows, k = x.shape
+    assert q.shape == (nrows, row_bytes(t, k))
+    out = np.zeros_like(q)
+    f = lib().orc_add_q_f32
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    rc = f(t, _p(q), _p(x), _p(out), nrows, k)
+    assert rc == 0, rc
+    return out
+
+
+def dup_f32_strided(buf, ne, nb):
+    """Contiguous F32 copy of the strided view (ne, nb in bytes) over `buf` -- ggml_cont of a transposed / permuted tensor."""
+    ne4 = (C.c_int64 * 4)(*(list(ne) + [1] * (4 - len(ne))))
+    nb4 = (C.c_uint64 * 4)(*(list(nb) + [0] * (4 - len(nb))))
+    n = int(np.prod(list(ne)))
+    out = np.zeros(n, dtype=np.float32)
+    f = lib().orc_dup_f32_strided
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(_p(buf), ne4, nb4, _p(out))
+    return out
+
+
+def repeat_f32(x, nr, nc):
+    """ggml_repeat of the 2-D float32 x [nr0, nc0] into [nr, nc]."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros((nr, nc), dtype=np.float32)
+    f = lib().orc_repeat_f32
+    f.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
+    f(_p(x), x.shape[1], x.shape[0], _p(out), nc, nr)
+    return out

@@ -17,6 +17,7 @@ Run:  python tests/golden/make_golden.py      (needs only numpy)
 import json
 import os
 import struct
+import warnings
 
 import numpy as np
 
@@ -204,5 +205,82 @@ def main():
     print("wrote quant_kat.json (%d blocks), mul_mat_small.json" % len(kats))
 
 
+# ---- neighbours of mul_mat: element-wise F32 ops, add_q_f32, cont(transpose) ----
+
+def silu_table():  # Ggml.cs:1461-1471 + 2723-2726: table_silu_f16[i] = (Half)(f / (1.0f + MathF.Exp(-f))), f = (float)Half(i)
+    # MathF.Exp is the C runtime's expf.  It is evaluated here as float32(exp(double)) -- the correctly rounded value, which is
+    # what glibc's expf returns for every fp16-representable argument (numpy's vectorised float32 exp is 1 ulp off for three
+    # of them, which moves three table entries, so it is NOT used).
+    import math
+    f = np.arange(1 << 16, dtype=np.uint16).view(np.float16).astype(np.float32)
+    e = np.empty_like(f)
+    for i, v in enumerate(f):
+        v = float(v)
+        if v != v:
+            e[i] = np.nan
+        elif -v > 700:
+            e[i] = np.inf
+        else:
+            e[i] = f32(math.exp(-v))
+    with np.errstate(over="ignore", invalid="ignore"):
+        s = (f / (f32(1) + e)).astype(np.float32)
+        return s.astype(np.float16)
+
+
+def silu_row(x, table):  # Ggml.cs:2737-2746 (GGML_SILU_FP16 is defined in GGMLSharp.csproj:9)
+    with np.errstate(over="ignore"):
+        idx = np.asarray(x, dtype=np.float32).astype(np.float16).view(np.uint16)
+    return table[idx].astype(np.float32)
+
+
+def rms_norm_row(x):  # Ggml.cs:5895-5917
+    s = 0.0
+    for v in x:
+        s += float(f32(v * v))
+    mean = f32(s / len(x))
+    scale = f32(f32(1) / np.sqrt(f32(mean + f32(1e-6))))
+    return np.array([f32(v * scale) for v in x], dtype=np.float32)
+
+
+def add_q_row(block_fn, deq_fn, bs, qrow, x):  # Ggml.cs:4893-4904
+    k = len(x)
+    w = np.concatenate([deq_fn(qrow[i * bs:(i + 1) * bs]) for i in range(k // 32)]).astype(np.float32)
+    w = (w + np.asarray(x, dtype=np.float32)).astype(np.float32)
+    return quant_row(block_fn, w)
+
+
+def main_ops():
+    rng = np.random.default_rng(20231019)
+    R, K = 3, 64
+    x = rng.standard_normal((R, K)).astype(np.float32)
+    y = (rng.standard_normal((R, K)) * 3).astype(np.float32)
+    x[0, :6] = [0.0, -0.0, 1e-8, -20.0, 20.0, 70000.0]           # silu: zeros, tiny, saturating, beyond fp16 range (-> inf)
+    table = silu_table()
+    out = {"source": "tests/golden/make_golden.py", "R": R, "K": K, "x": hexf(x), "y": hexf(y), "v": hexf(np.array([0.125 * 3.3], dtype=np.float32))}
+    out["add"] = hexf((x + y).astype(np.float32))
+    out["mul"] = hexf((x * y).astype(np.float32))
+    out["scale"] = hexf((x * np.frombuffer(bytes.fromhex(out["v"]), dtype=np.float32)[0]).astype(np.float32))
+    with np.errstate(invalid="ignore"):
+        out["silu"] = hexf(np.stack([silu_row(r, table) for r in x]))
+    out["silu_table_crc"] = int(np.bitwise_xor.reduce(table.view(np.uint16).astype(np.uint64) * (np.arange(1 << 16, dtype=np.uint64) * 2 + 1) % 1000003))
+    out["silu_table_head"] = table[0x3000:0x3010].tobytes().hex()
+    out["rms_norm"] = hexf(np.stack([rms_norm_row(r) for r in y]))
+    w = (rng.standard_normal((R, K)) * 0.05).astype(np.float32)
+    q40 = [quant_row(q4_0_block, r) for r in w]
+    q41 = [quant_row(q4_1_block, r) for r in w]
+    out["w"] = hexf(w)
+    small = (x * f32(0.03)).astype(np.float32)
+    small[0, 5] = 0.01
+    out["addq_x"] = hexf(small)
+    out["addq_q4_0"] = b"".join(add_q_row(q4_0_block, deq4_0_row, 20, q40[i], small[i]) for i in range(R)).hex()
+    out["addq_q4_1"] = b"".join(add_q_row(q4_1_block, deq4_1_row, 24, q41[i], small[i]) for i in range(R)).hex()
+    out["repeat_2x3"] = hexf(np.tile(x[:, :8], (2, 3)))           # ggml_repeat of [R][8] into [2R][24] (Ggml.cs:5371-5382)
+    out["cont_transpose"] = hexf(np.ascontiguousarray(x.T))      # cont(transpose(x)): dst[i1][i0] = x[i0][i1]
+    with open(os.path.join(HERE, "ops_small.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote ops_small.json")
+
+
 if __name__ == "__main__":
     main()
+    main_ops()

@@ -145,3 +145,31 @@ def test_planner_work_buffer_matches_reference_sizes():
             want = orc.lib().orc_mul_mat_work_size(ot, 64 * 3) + 64 * 3
             assert g.work_size == want and g.work.contents.type == N.I8 and g.work.contents.ne[0] == want
             assert g.nodes[0].contents.n_tasks == 4
+
+
+def test_neighbour_builders_follow_the_reference():
+    # ggml_transpose / ggml_scale / ggml_add_inplace return VIEWS (Ggml.cs:7199-7225, 8248-8271, 7868-7890); ggml_cont, ggml_silu,
+    # ggml_rms_norm, ggml_add, ggml_mul duplicate the shape; ggml_repeat takes b's shape; ops carry the reference's enum values
+    with _ctx() as c:
+        a = c.new_tensor(N.F32, 6, 4)
+        b = c.new_tensor(N.F32, 6, 4)
+        s1 = c.new_tensor(N.F32, 1)
+        t = c.op("transpose", a)
+        assert (t.contents.op, list(t.contents.ne)[:2], list(t.contents.nb)[:2], t.contents.data) == (N.OP_TRANSPOSE, [4, 6], [24, 4], a.contents.data)
+        ct = c.op("cont", t)
+        assert (ct.contents.op, list(ct.contents.ne)[:2], list(ct.contents.nb)[:2]) == (N.OP_CONT, [4, 6], [4, 16]) and ct.contents.data != a.contents.data
+        sc = c.op("scale", a, s1)
+        assert sc.contents.op == N.OP_SCALE and sc.contents.data == a.contents.data
+        ad = c.op("add", a, b)
+        assert ad.contents.op == N.OP_ADD and ad.contents.data not in (a.contents.data, b.contents.data)
+        assert c.op("add_inplace", a, b).contents.data == a.contents.data
+        assert c.op("mul", a, b).contents.op == N.OP_MUL and c.op("silu", a).contents.op == N.OP_SILU and c.op("rms_norm", a).contents.op == N.OP_RMS_NORM
+        v = c.new_tensor(N.F32, 6)
+        r = c.op("repeat", v, a)
+        assert r.contents.op == N.OP_REPEAT and list(r.contents.ne)[:2] == [6, 4]
+        with pytest.raises(N.GgbError):
+            c.op("add", a, v)                                   # ggml_are_same_shape
+        with pytest.raises(N.GgbError):
+            c.op("scale", a, b)                                 # ggml_is_scalar
+        g = c.build_forward(c.op("add", c.op("silu", ad), c.op("cont", c.op("transpose", ct))))
+        assert [g.nodes[i].contents.op for i in range(g.n_nodes)] == [N.OP_ADD, N.OP_SILU, N.OP_TRANSPOSE, N.OP_CONT, N.OP_TRANSPOSE, N.OP_CONT, N.OP_ADD]

@@ -86,3 +86,54 @@ def test_quantize_roundtrip_properties():
         rngs = np.abs(xb).max(-1) if t == orc.Q4_0 else (xb.max(-1) - xb.min(-1))
         err = np.abs(y.reshape(64, 8, 32) - xb).max(-1)
         assert (err <= rngs * tol * 1.01 + 1e-12).all()
+
+
+# ---- neighbours of mul_mat: element-wise F32 ops, add_q_f32, cont(transpose) ----
+
+@pytest.fixture(scope="module")
+def ops():
+    with open(os.path.join(G, "ops_small.json")) as f:
+        return json.load(f)
+
+
+def test_elementwise_ops_bit_exact(ops):
+    R, K = ops["R"], ops["K"]
+    x, y = _f32(ops["x"]).reshape(R, K), _f32(ops["y"]).reshape(R, K)
+    v = _f32(ops["v"])[0]
+    assert orc.add_f32(x, y).tobytes().hex() == ops["add"]
+    assert orc.mul_f32(x, y).tobytes().hex() == ops["mul"]
+    assert orc.scale_f32(x, v).tobytes().hex() == ops["scale"]
+    assert orc.silu_f32(x).tobytes().hex() == ops["silu"]
+    assert orc.rms_norm_f32(y).tobytes().hex() == ops["rms_norm"]
+
+
+def test_silu_table_matches_independent_restatement(ops):
+    t = orc.silu_table()
+    crc = int(np.bitwise_xor.reduce(t.astype(np.uint64) * (np.arange(1 << 16, dtype=np.uint64) * 2 + 1) % 1000003))
+    assert crc == ops["silu_table_crc"]
+    assert t[0x3000:0x3010].tobytes().hex() == ops["silu_table_head"]
+    # spot values: silu(0) = 0, silu(1) = 0.731..., large x -> x, very negative -> -0
+    h = lambda f: int(np.float16(f).view(np.uint16))
+    assert t[h(0.0)] == 0 and t[h(1.0)] == h(0.7310586) and t[h(20.0)] == h(20.0) and t[h(-30.0)] == 0x8000
+
+
+def test_add_q_f32_bit_exact(ops):
+    R, K = ops["R"], ops["K"]
+    w, x = _f32(ops["w"]).reshape(R, K), _f32(ops["addq_x"]).reshape(R, K)
+    for t, key in ((orc.Q4_0, "addq_q4_0"), (orc.Q4_1, "addq_q4_1")):
+        q = orc.quantize_rows(t, w)
+        assert orc.add_q_f32(t, q, x).tobytes().hex() == ops[key]
+
+
+def test_cont_transpose(ops):
+    R, K = ops["R"], ops["K"]
+    x = _f32(ops["x"]).reshape(R, K).copy()
+    # ggml_transpose: ne = [R, K] (ne0 = R), nb = [K*4, 4]
+    got = orc.dup_f32_strided(x, (R, K), (K * 4, 4))
+    assert got.tobytes().hex() == ops["cont_transpose"]
+
+
+def test_repeat(ops):
+    R, K = ops["R"], ops["K"]
+    x = _f32(ops["x"]).reshape(R, K)[:, :8].copy()
+    assert orc.repeat_f32(x, 2 * R, 24).tobytes().hex() == ops["repeat_2x3"]
