@@ -174,8 +174,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                     w[4 * i] = v4.x; w[4 * i + 1] = v4.y; w[4 * i + 2] = v4.z; w[4 * i + 3] = v4.w;
                 }
                 // the raw stage is released only after the dequant below has CONSUMED these registers (ggb_gemm.cu)
-                mbar_wait(BAR(A_EMPTY + g), ((gk >> 2) & 1) ^ 1);
-                tc_fence_after();
 #pragma unroll
                 for (int hb = 0; hb < 2; hb++) {                         // two blocks (64 K = 32 columns) per TMEM store
                     uint32_t v[32];
@@ -189,6 +187,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                         const uint32_t *qw = TYPE == GGML_TYPE_Q4_0 ? wb + 1 : wb + 2;
 #pragma unroll
                         for (int i = 0; i < 4; i++) dequant_word<TYPE>(qw[i], d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16 + i * 4]);
+                    }
+                    if (hb == 0) {
+                        // the nibble expansion of the first half ran ahead of this wait: only the TMEM store needs the stage free
+                        mbar_wait(BAR(A_EMPTY + g), ((gk >> 2) & 1) ^ 1);
+                        tc_fence_after();
                     }
                     tmem_st_x32(a_tmem + (uint32_t)(hb * 32), v);
                 }
