@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(256) k_dequantize_rows(const uint8_t *__restri
 // Q8P: quantize exactly as quantize_row_q8_0 / q8_1 do (same d, same 32 quants), stored even/odd-split so a
 // 32-bit word of weight nibbles pairs with one 32-bit word of activations for dp4a, plus the block's integer
 // sum (Q4_0 needs -8*sum, Q4_1 needs m*d*sum; the reference's s0+s1 is d*sum).
-__global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBatch b)
+template <int CAP>
+__global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBatchT<CAP> b)
 {
     if (b.wtype == GGML_TYPE_Q4_0 || b.wtype == GGML_TYPE_Q4_1) {
         const int lane = threadIdx.x & 31, sub = lane & 7;
@@ -698,7 +699,14 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_batch, b));
+    if (b.n_nodes <= GGB_SMALL_BATCH_NODES) {                     // small parameter block: see launch_gemv_batch
+        static thread_local ActBatchT<GGB_SMALL_BATCH_NODES> sb;
+        static_cast<ActHdr &>(sb) = static_cast<const ActHdr &>(b);
+        for (int i = 0; i < b.n_nodes; i++) sb.node[i] = b.node[i];
+        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_batch<GGB_SMALL_BATCH_NODES>, sb));
+    } else {
+        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_batch<GGB_MAX_BATCH_NODES>, b));
+    }
     count_launch();
     return GGB_OK;
 }

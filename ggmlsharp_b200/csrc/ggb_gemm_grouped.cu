@@ -35,11 +35,14 @@ struct alignas(64) GroupNode {
     int n_peers, pad_;
     long long peer_delta[7];       // row split: byte offset from Y to the same element of peer p's dst (CUDA-IPC mapped)
 };
-struct alignas(64) GemmGroup { int n_nodes, total_tiles; int pad_[14]; GroupNode node[GGB_GEMM_GROUP_NODES]; };
+// CAP = 8 keeps the parameter block at 3 KB for small groups (parameters above 4 KB add microseconds to the launch)
+template <int CAP> struct alignas(64) GemmGroupT { int n_nodes, total_tiles; int pad_[14]; GroupNode node[CAP]; };
+using GemmGroup = GemmGroupT<GGB_GEMM_GROUP_NODES>;
+constexpr int SMALL_GROUP = 8;
 static_assert(sizeof(GemmGroup) <= 32000, "kernel parameter space");
 
-template <int TYPE>
-__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_constant__ GemmGroup G)
+template <int TYPE, int CAP>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_constant__ GemmGroupT<CAP> G)
 {
     constexpr int BN = 128, BNL = 64;
     constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
@@ -253,7 +256,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
 // F16 weights: both operands come from shared memory (TMA, swizzle-128B), so the 16 warps that dequantize in the Q4 kernel
 // have nothing to do during the main loop and TMEM has room for TWO accumulator sets (2 x (even-K + odd-K) x 128 columns):
 // the epilogue of tile i runs under the main loop of tile i + 1.
-__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_constant__ GemmGroup G)
+template <int CAP>
+__global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_constant__ GemmGroupT<CAP> G)
 {
     constexpr int BN = 128, BNL = 64;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2, STAGES = 4;
@@ -406,15 +410,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_c
 }
 
 
-template <int TYPE>
-int launch_grouped(const GemmGroup &G, cudaStream_t s)
+template <int TYPE, int CAP>
+int launch_grouped(const GemmGroupT<CAP> &G, cudaStream_t s)
 {
     constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
     constexpr size_t smem = TYPE == GGML_TYPE_F16 ? 1024 + (size_t)4 * (BM * BK * 2) + (size_t)4 * (64 * BK * 2) + 64 * 8 + 16
                                                   : 1024 + (size_t)4 * (64 * BK * 2) + (size_t)8 * (BM * RAW_ROW) + 64 * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    void (*kern)(const GemmGroup) = nullptr;
-    if constexpr (TYPE == GGML_TYPE_F16) kern = k_gemm_f16_grouped; else kern = k_gemm_q_grouped<TYPE>;
+    void (*kern)(const GemmGroupT<CAP>) = nullptr;
+    if constexpr (TYPE == GGML_TYPE_F16) kern = k_gemm_f16_grouped<CAP>; else kern = k_gemm_q_grouped<TYPE, CAP>;
     static bool attr_set = false;
     if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     cudaLaunchConfig_t cfg = {};
@@ -483,8 +487,15 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
         for (int p = 0; p < a.n_peers; p++) nd.peer_delta[p] = (long long)(reinterpret_cast<char *>(a.ypeer[p]) - reinterpret_cast<char *>(a.Y));
     }
     if (G.total_tiles == 0) return GGB_OK;
-    if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16>(G, s);
-    return type == GGML_TYPE_Q4_0 ? launch_grouped<GGML_TYPE_Q4_0>(G, s) : launch_grouped<GGML_TYPE_Q4_1>(G, s);
+    if (count <= SMALL_GROUP) {
+        static thread_local GemmGroupT<SMALL_GROUP> S;
+        S.n_nodes = G.n_nodes; S.total_tiles = G.total_tiles;
+        for (int i = 0; i < count; i++) S.node[i] = G.node[i];
+        if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16, SMALL_GROUP>(S, s);
+        return type == GGML_TYPE_Q4_0 ? launch_grouped<GGML_TYPE_Q4_0, SMALL_GROUP>(S, s) : launch_grouped<GGML_TYPE_Q4_1, SMALL_GROUP>(S, s);
+    }
+    if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16, GGB_GEMM_GROUP_NODES>(G, s);
+    return type == GGML_TYPE_Q4_0 ? launch_grouped<GGML_TYPE_Q4_0, GGB_GEMM_GROUP_NODES>(G, s) : launch_grouped<GGML_TYPE_Q4_1, GGB_GEMM_GROUP_NODES>(G, s);
 }
 
 } // namespace ggb

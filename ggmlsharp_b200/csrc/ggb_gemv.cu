@@ -183,7 +183,7 @@ __device__ __forceinline__ void dot_f32(const uint8_t *w, int off_bytes, int nby
 }
 
 template <int TYPE, int NC>
-__device__ __forceinline__ void dot_chunk(const GemvBatch &b, const uint8_t *w, int off_bytes, int nbytes, const uint8_t *xs,
+__device__ __forceinline__ void dot_chunk(const GemvHdr &b, const uint8_t *w, int off_bytes, int nbytes, const uint8_t *xs,
                                           int lane, float (&acc)[NC])
 {
     if (TYPE == GGML_TYPE_Q4_0) dot_q4_0<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, b.K / GGB_QK, lane, acc);
@@ -195,8 +195,8 @@ __device__ __forceinline__ void dot_chunk(const GemvBatch &b, const uint8_t *w, 
 // Generic path for rows that are not 16-byte multiples / not 16-byte aligned (e.g. K = 4128, byte-offset views): the same
 // math, but every warp stages its own row (or K-chunk of a long row) into shared memory with plain loads.  One group = one
 // weight row; groups are dealt to warps round-robin inside a CTA's contiguous range.
-template <int TYPE, int NC>
-__global__ void __launch_bounds__(NWARPS * 32, 1) k_gemv(const __grid_constant__ GemvBatch b)
+template <int TYPE, int NC, int CAP>
+__global__ void __launch_bounds__(NWARPS * 32, 1) k_gemv(const __grid_constant__ GemvBatchT<CAP> b)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,8 +357,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int TYPE, int NC, bool XREG>
-__global__ void __launch_bounds__((NWF + 1) * 32, 1) k_gemv_fast(const __grid_constant__ GemvBatch b)
+template <int TYPE, int NC, bool XREG, int CAP>
+__global__ void __launch_bounds__((NWF + 1) * 32, 1) k_gemv_fast(const __grid_constant__ GemvBatchT<CAP> b)
 {
     constexpr int UB = UnitTraits<TYPE>::BYTES, BPS = UnitTraits<TYPE>::BPS;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -485,8 +485,8 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_gemv_fast(const __grid_co
     }
 }
 
-template <int TYPE>
-int launch_fast_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s, bool pdl)
+template <int TYPE, int CAP>
+int launch_fast_typed(const GemvBatchT<CAP> &b, size_t smem, int grid, cudaStream_t s, bool pdl)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -501,8 +501,8 @@ int launch_fast_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s,
     const bool xreg = Q && b.ncols == 1 && b.nchunk == 1 && b.row_bytes / UnitTraits<TYPE>::BYTES <= 32;
 #define GGB_FAST_CASE(NCV, XR) { \
         static bool attr_set = false; \
-        if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemv_fast<TYPE, NCV, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; } \
-        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemv_fast<TYPE, NCV, XR>, b)); }
+        if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemv_fast<TYPE, NCV, XR, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; } \
+        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemv_fast<TYPE, NCV, XR, CAP>, b)); }
     if (xreg) { if constexpr (Q) GGB_FAST_CASE(1, true) }
     else switch (b.ncols) {
         case 1: GGB_FAST_CASE(1, false) break;
@@ -516,8 +516,8 @@ int launch_fast_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s,
     return GGB_OK;
 }
 
-template <int TYPE>
-int launch_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s, bool pdl)
+template <int TYPE, int CAP>
+int launch_typed(const GemvBatchT<CAP> &b, size_t smem, int grid, cudaStream_t s, bool pdl)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -530,8 +530,8 @@ int launch_typed(const GemvBatch &b, size_t smem, int grid, cudaStream_t s, bool
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
 #define GGB_GEMV_CASE(NCV) case NCV: { \
         static bool attr_set = false; \
-        if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemv<TYPE, NCV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; } \
-        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemv<TYPE, NCV>, b)); } break;
+        if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemv<TYPE, NCV, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; } \
+        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemv<TYPE, NCV, CAP>, b)); } break;
     switch (b.ncols) {
         GGB_GEMV_CASE(1) GGB_GEMV_CASE(2) GGB_GEMV_CASE(4) GGB_GEMV_CASE(8)
     default: return set_error(GGB_E_INVALID, "gemv: ncols=%d", b.ncols);
@@ -548,11 +548,11 @@ constexpr int STAGE_MAX = 4096;            // bytes of one bulk copy (one row, s
 } // namespace
 
 int gemv_num_ctas() { return device_sm_count(); }
-int gemv_group_rows(const GemvBatch &b) { return b.async ? NWF * b.rs : b.rs; }
-int gemv_act_bps(const GemvBatch &b) { return !b.async ? 1 : b.type == GGML_TYPE_Q4_0 ? 4 : b.type == GGML_TYPE_Q4_1 ? 2 : 1; }
+int gemv_group_rows(const GemvHdr &b) { return b.async ? NWF * b.rs : b.rs; }
+int gemv_act_bps(const GemvHdr &b) { return !b.async ? 1 : b.type == GGML_TYPE_Q4_0 ? 4 : b.type == GGML_TYPE_Q4_1 ? 2 : 1; }
 
 // Fills the shape-dependent fields of b (everything but the node list).  ncols in {1,2,4,8}.
-int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase)
+int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase)
 {
     const int blck = blck_size(type);
     if (K <= 0 || K % blck) return set_error(GGB_E_INVALID, "mul_mat: ne00=%lld is not a multiple of the block size %d (Ggml.cs:6694)", (long long)K, blck);
@@ -613,9 +613,9 @@ int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const 
     return GGB_OK;
 }
 
-int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl)
+template <int CAP>
+static int launch_gemv_cap(const GemvBatchT<CAP> &b, cudaStream_t s, bool pdl)
 {
-    if (b.n_nodes <= 0 || b.total_groups <= 0) return GGB_OK;
     const size_t xbytes = ((size_t)b.ncols * b.xcol_bytes + 127) & ~(size_t)127;
     int grid = gemv_num_ctas();
     // async: groups are tiles and every CTA takes whole tiles; sync: groups are rows, one per warp
@@ -624,19 +624,32 @@ int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl)
     const int want = b.async ? b.total_groups : (b.total_groups + NWARPS - 1) / NWARPS;
     if (grid > want) grid = want;
     if (b.async) switch (b.type) {
-    case GGML_TYPE_Q4_0: return launch_fast_typed<GGML_TYPE_Q4_0>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q4_1: return launch_fast_typed<GGML_TYPE_Q4_1>(b, smem, grid, s, pdl);
-    case GGML_TYPE_F16: return launch_fast_typed<GGML_TYPE_F16>(b, smem, grid, s, pdl);
-    case GGML_TYPE_F32: return launch_fast_typed<GGML_TYPE_F32>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q4_0: return launch_fast_typed<GGML_TYPE_Q4_0, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q4_1: return launch_fast_typed<GGML_TYPE_Q4_1, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_F16: return launch_fast_typed<GGML_TYPE_F16, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_F32: return launch_fast_typed<GGML_TYPE_F32, CAP>(b, smem, grid, s, pdl);
     default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6739-6742)", b.type);
     }
     switch (b.type) {
-    case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1>(b, smem, grid, s, pdl);
-    case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16>(b, smem, grid, s, pdl);
-    case GGML_TYPE_F32: return launch_typed<GGML_TYPE_F32>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_F32: return launch_typed<GGML_TYPE_F32, CAP>(b, smem, grid, s, pdl);
     default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6739-6742)", b.type);
     }
+}
+
+int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl)
+{
+    if (b.n_nodes <= 0 || b.total_groups <= 0) return GGB_OK;
+    if (b.n_nodes <= GGB_SMALL_BATCH_NODES) {
+        // few nodes: a 1.5 KB parameter block instead of 10 KB (large kernel parameters add microseconds to every launch)
+        static thread_local GemvBatchT<GGB_SMALL_BATCH_NODES> sb;
+        static_cast<GemvHdr &>(sb) = static_cast<const GemvHdr &>(b);
+        for (int i = 0; i < b.n_nodes; i++) sb.node[i] = b.node[i];
+        return launch_gemv_cap(sb, s, pdl);
+    }
+    return launch_gemv_cap(b, s, pdl);
 }
 
 } // namespace ggb

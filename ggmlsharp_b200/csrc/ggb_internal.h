@@ -51,7 +51,11 @@ int launch_dup_f32_strided(const void *src, const int64_t ne[4], const uint64_t 
 size_t act_row_bytes(int wtype, int64_t K);
 struct ActNode { const float *x; long long ldx_bytes; uint8_t *out; int N; int blk0; };
 // bps > 1: unit-major Q8P planes for the fast GEMV (block b = bps*u + j stored at plane index j*(kb/bps) + u); else linear
-struct ActBatch { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; ActNode node[GGB_MAX_BATCH_NODES]; };
+struct ActHdr { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; };
+// kernel parameters above 4 KB cost several microseconds per launch, so launches with few nodes pass the small variant
+template <int CAP> struct ActBatchT : ActHdr { ActNode node[CAP]; };
+using ActBatch = ActBatchT<GGB_MAX_BATCH_NODES>;
+constexpr int GGB_SMALL_BATCH_NODES = 32;
 int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl);
 // batched path: activations as dense fp16 [Npad][K] holding d * q (the value the reference's dot multiplies by)
 int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior);
@@ -62,7 +66,7 @@ int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s);
 
 // ---- GEMV (ggb_gemv.cu) ----
 struct GemvNode { const uint8_t *W; const uint8_t *xq; float *y; int M; int ldy; int g0; int ngroups; };
-struct GemvBatch {
+struct GemvHdr {
     int n_nodes, total_groups;
     int type, ncols;
     int K, row_bytes;          // row_bytes = bytes of K elements
@@ -73,12 +77,13 @@ struct GemvBatch {
     int async;                 // 1: cp.async.bulk staging (16-byte aligned rows), 0: plain-load staging
     int n_peers;
     long long peer_delta[7];   // byte offset from a node's y to the same element of peer p's copy
-    GemvNode node[GGB_MAX_BATCH_NODES];
 };
+template <int CAP> struct GemvBatchT : GemvHdr { GemvNode node[CAP]; };
+using GemvBatch = GemvBatchT<GGB_MAX_BATCH_NODES>;
 int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl);
-int gemv_plan(GemvBatch &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase_probe);
-int gemv_act_bps(const GemvBatch &b);
-int gemv_group_rows(const GemvBatch &b);  // weight rows per work group (tile) of the planned kernel   // the ActBatch::bps the planned kernel expects
+int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase_probe);
+int gemv_act_bps(const GemvHdr &b);
+int gemv_group_rows(const GemvHdr &b);  // weight rows per work group (tile) of the planned kernel   // the ActBatch::bps the planned kernel expects
 int gemv_num_ctas();
 
 // ---- GEMM (ggb_gemm.cu): tcgen05 batched path ----

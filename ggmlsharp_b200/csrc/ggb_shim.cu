@@ -192,7 +192,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         if (done[i0]) continue;
         // the activation layout depends on which GEMV kernel will read it, so that is part of the key
         auto act_bps = [&](const ggb_dev_mm &m, int &bps) -> int {
-            GemvBatch probe = {};
+            GemvHdr probe = {};
             int r = gemv_plan(probe, m.type, m.K, m.nb01, 1, m.W);
             bps = r ? 0 : gemv_act_bps(probe);
             return r;
@@ -212,7 +212,8 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         const bool quant = type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1;
         // activation staging (INIT phase)
         for (size_t c0 = 0; c0 < grp.size(); c0 += GGB_MAX_BATCH_NODES) {
-            ActBatch ab = {};
+            static thread_local ActBatch ab;
+            static_cast<ActHdr &>(ab) = ActHdr{};
             ab.K = (int)K; ab.kb = (int)(K / GGB_QK); ab.row_bytes = (int)arow; ab.wtype = type; ab.vec16 = 1; ab.bps = bps0;
             int tot = 0;
             for (size_t c = c0; c < std::min(grp.size(), c0 + (size_t)GGB_MAX_BATCH_NODES); c++) {
@@ -239,7 +240,8 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         for (size_t p0 = 0; p0 < passes.size(); p0++) {
             if (pdone[p0]) continue;
             const ggb_dev_mm &m0 = mm[passes[p0].i];
-            GemvBatch gb = {};
+            static thread_local GemvBatch gb;
+            static_cast<GemvHdr &>(gb) = GemvHdr{};
             int rc = gemv_plan(gb, type, K, m0.nb01, passes[p0].nc, m0.W);
             if (rc) return rc;
             gb.n_peers = m0.n_peers;
