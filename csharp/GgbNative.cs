@@ -25,6 +25,18 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_quantize_rows(int type, float* src, void* dst, long nrows, long k);
     [DllImport(Lib)] public static extern int ggb_dequantize_rows(int type, void* src, float* dst, long nrows, long k);
 
+    // flags of ggb_graph_compute_mul_mats (include/ggb200.h)
+    public const int GGB_GRAPH_KEEP_ON_DEVICE = 1, GGB_GRAPH_NO_WEIGHT_CACHE = 2, GGB_GRAPH_MUL_MAT_ONLY = 4;
+
+    // device-pointer entry points (what the executor itself calls); stream = a cudaStream_t or IntPtr.Zero for the library's own
+    [DllImport(Lib)] public static extern int ggb_dev_binary(int op, float* a, float* b, float* dst, long n, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_scale(float* x, float v, long n, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_silu(float* x, float* dst, long n, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_rms_norm(float* x, long xStride, float* dst, long dstStride, long nrows, long ne00, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_repeat(float* src, long srcStride, long nc0, long nr0, float* dst, long dstStride, long nc, long nr, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_cont(void* src, long* ne, ulong* nb, float* dst, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_add_q(int type, void* src0, float* src1, void* dst, long nrows, long k, IntPtr stream);
+
     public static string LastError() => Marshal.PtrToStringUTF8(ggb_last_error()) ?? "";
 
     // ggml_context* -> ggb_pool*.  ggml_context itself (TypeDefinitions.cs:32-46) is left untouched.
