@@ -23,6 +23,16 @@
  *   D4  Q8 quants are int8 (TypeDefinitions.cs:281,289 declare byte).
  *   D5/D6  the scalar quantize_row_q4_0_reference_impl / scalar dequantize
  *       branches are the targets; the AVX branches are defective.
+ * Sibling formats (Q4_2, Q5_0, Q5_1, Q8_0 as weights) add one more:
+ *   D9  fp16 block scales declared `ushort` (block_q4_2.d, block_q5_1.d/.m,
+ *       TypeDefinitions.cs:249-275) are stored with a NUMERIC cast
+ *       `(ushort)(Half)d` (Ggml.cs:577, 678-679) and read back with numeric
+ *       `(float)(Half)x.d` / `(float)x.d` (Ggml.cs:1003, 1068-1069, 1220-1221,
+ *       1320-1321): a scale of 0.01 is stored as integer 0.  Upstream's
+ *       GGML_FP32_TO_FP16 / GGML_FP16_TO_FP32 move the IEEE binary16 BIT PATTERN,
+ *       which is what block_q5_0 (declared `Half d`, TypeDefinitions.cs:263) does
+ *       in this very file; the oracle stores and loads bit patterns for all three.
+ *       Q8_0 weights read their quants as int8 (D4).
  *
  * PARITY PINNING.  F32 mul_mat and the tensor stride rule are pinned by the
  * reference's own Test3 (generator + expected solution) and Test0 (strides);
@@ -47,13 +57,23 @@ typedef struct { float d; float m; uint8_t qs[QK / 2]; } block_q4_1;   /* 24 B *
 typedef struct { float d; int8_t qs[QK]; } block_q8_0;                 /* 36 B, D4: int8 */
 typedef struct { float d; float s0; float s1; int8_t qs[QK]; } block_q8_1; /* 44 B */
 
+/* TypeDefinitions.cs:249-276 -- the sibling weight formats: fp16 scales, 16- or 32-element blocks, a 5th-bit plane qh. */
+#define QK4_2 16
+#pragma pack(push, 1)
+typedef struct { uint16_t d; uint8_t qs[QK4_2 / 2]; } block_q4_2;                   /* 10 B */
+typedef struct { uint16_t d; uint8_t qh[4]; uint8_t qs[QK / 2]; } block_q5_0;       /* 22 B */
+typedef struct { uint16_t d; uint16_t m; uint8_t qh[4]; uint8_t qs[QK / 2]; } block_q5_1; /* 24 B */
+#pragma pack(pop)
+_Static_assert(sizeof(block_q4_2) == 10, "block_q4_2");
+_Static_assert(sizeof(block_q5_0) == 22, "block_q5_0");
+_Static_assert(sizeof(block_q5_1) == 24, "block_q5_1");
 _Static_assert(sizeof(block_q4_0) == 20, "block_q4_0");
 _Static_assert(sizeof(block_q4_1) == 24, "block_q4_1");
 _Static_assert(sizeof(block_q8_0) == 36, "block_q8_0");
 _Static_assert(sizeof(block_q8_1) == 44, "block_q8_1");
 
 /* TypeDefinitions.cs:153-169 */
-enum { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q8_0 = 8, T_Q8_1 = 9 };
+enum { T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q4_2 = 4, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8, T_Q8_1 = 9 };
 
 /* ---- IEEE binary16 <-> binary32, what .NET's System.Half conversions do ---- */
 
@@ -308,6 +328,283 @@ void orc_vec_dot_q4_1_q8_1(int n, float *s, const void *vx, const void *vy)
     *s = sumf;
 }
 
+/* ---- sibling weight formats: Q4_2, Q5_0, Q5_1, and Q8_0 as a weight type ---- */
+
+/* C# `(int)someFloat` on .NET 8 / x64 is cvttss2si: NaN and out-of-range give 0x80000000. */
+static inline int32_t cs_int_f(float t)
+{
+    if (t != t || t >= 2147483648.0f || t < -2147483648.0f) return INT32_MIN;
+    return (int32_t)t;
+}
+/* C# `(uint)someFloat` on .NET 8 / x64 is cvttss2si r64 + truncation to 32 bits: NaN and |t| >= 2^63 give 0. */
+static inline uint32_t cs_uint_f(float t)
+{
+    if (t != t || t >= 9223372036854775808.0f || t < -9223372036854775808.0f) return 0u;
+    return (uint32_t)(uint64_t)(int64_t)t;
+}
+
+/* Ggml.cs:547-590 quantize_row_q4_2_reference_impl (593-601 just calls it); D9: d stored as fp16 bits. */
+void orc_quantize_row_q4_2(const float *x, void *vy, int k)
+{
+    block_q4_2 *y = (block_q4_2 *)vy;
+    const int nb = k / QK4_2;
+    for (int i = 0; i < nb; i++) {
+        float amax = 0.0f, max = 0.0f;
+        for (int l = 0; l < QK4_2; l++) {
+            const float v = x[i * QK4_2 + l];
+            if (amax < fabsf(v)) { amax = fabsf(v); max = v; }
+        }
+        const float d = max / -8.0f;
+        const float id = d != 0.0f ? 1.0f / d : 0.0f;       /* from the UNROUNDED d (Ggml.cs:575) */
+        y[i].d = orc_f32_to_f16(d);
+        for (int l = 0; l < QK4_2; l += 2) {
+            const float v0 = x[i * QK4_2 + l + 0] * id;
+            const float v1 = x[i * QK4_2 + l + 1] * id;
+            const uint8_t vi0 = cs_byte(cs_min(15.0, nearbyint((double)v0) + 8.0));
+            const uint8_t vi1 = cs_byte(cs_min(15.0, nearbyint((double)v1) + 8.0));
+            y[i].qs[l / 2] = (uint8_t)(vi0 | (vi1 << 4));
+        }
+    }
+}
+
+/* Ggml.cs:609-653 quantize_row_q5_0_reference_impl: d = max / -16, q = min(31, (int)(x*id + 16.5f)) -- truncation of a
+ * float sum, NOT Math.Round; bit 4 of each quant goes to qh at the element's index. */
+void orc_quantize_row_q5_0(const float *x, void *vy, int k)
+{
+    block_q5_0 *y = (block_q5_0 *)vy;
+    const int nb = k / QK;
+    for (int i = 0; i < nb; i++) {
+        float amax = 0.0f, max = 0.0f;
+        for (int l = 0; l < QK; l++) {
+            const float v = x[i * QK + l];
+            if (amax < fabsf(v)) { amax = fabsf(v); max = v; }
+        }
+        const float d = max / -16.0f;
+        const float id = d != 0.0f ? 1.0f / d : 0.0f;
+        y[i].d = orc_f32_to_f16(d);
+        uint32_t qh = 0;
+        for (int l = 0; l < QK; l += 2) {
+            const float v0 = x[i * QK + l + 0] * id;
+            const float v1 = x[i * QK + l + 1] * id;
+            const int32_t t0 = cs_int_f(v0 + 16.5f), t1 = cs_int_f(v1 + 16.5f);
+            const uint32_t vi0 = (uint32_t)(t0 < 31 ? t0 : 31);     /* Math.Min(31, int), then (uint) */
+            const uint32_t vi1 = (uint32_t)(t1 < 31 ? t1 : 31);
+            y[i].qs[l / 2] = (uint8_t)((vi0 & 0x0F) | ((vi1 & 0x0F) << 4));
+            qh |= ((vi0 & 0x10) >> 4) << (l + 0);
+            qh |= ((vi1 & 0x10) >> 4) << (l + 1);
+        }
+        memcpy(y[i].qh, &qh, 4);
+    }
+}
+
+/* Ggml.cs:672-714 quantize_row_q5_1_reference_impl: d = (max-min)/31, q = (uint)((x-min)*id + 0.5f); D9 for d and m. */
+void orc_quantize_row_q5_1(const float *x, void *vy, int k)
+{
+    block_q5_1 *y = (block_q5_1 *)vy;
+    const int nb = k / QK;
+    for (int i = 0; i < nb; i++) {
+        float min = FLT_MAX, max = -FLT_MAX;               /* float.MaxValue / float.MinValue */
+        for (int l = 0; l < QK; l++) {
+            const float v = x[i * QK + l];
+            if (v < min) min = v;
+            if (v > max) max = v;
+        }
+        const float d = (max - min) / 31.0f;
+        const float id = d != 0.0f ? 1.0f / d : 0.0f;
+        y[i].d = orc_f32_to_f16(d);
+        y[i].m = orc_f32_to_f16(min);
+        uint32_t qh = 0;
+        for (int l = 0; l < QK; l += 2) {
+            const float v0 = (x[i * QK + l + 0] - min) * id;
+            const float v1 = (x[i * QK + l + 1] - min) * id;
+            const uint32_t vi0 = cs_uint_f(v0 + 0.5f), vi1 = cs_uint_f(v1 + 0.5f);
+            y[i].qs[l / 2] = (uint8_t)((vi0 & 0x0F) | ((vi1 & 0x0F) << 4));
+            qh |= ((vi0 & 0x10) >> 4) << (l + 0);
+            qh |= ((vi1 & 0x10) >> 4) << (l + 1);
+        }
+        memcpy(y[i].qh, &qh, 4);
+    }
+}
+
+/* Ggml.cs:992-1022 dequantize_row_q4_2 (D9: d read as fp16 bits). */
+void orc_dequantize_row_q4_2(const void *vx, float *y, int k)
+{
+    const block_q4_2 *x = (const block_q4_2 *)vx;
+    const int nb = k / QK4_2;
+    for (int i = 0; i < nb; i++) {
+        const float d = orc_f16_to_f32(x[i].d);
+        for (int l = 0; l < QK4_2; l += 2) {
+            const uint8_t vi = x[i].qs[l / 2];
+            y[i * QK4_2 + l + 0] = (float)((vi & 0x0F) - 8) * d;
+            y[i * QK4_2 + l + 1] = (float)((vi >> 4) - 8) * d;
+        }
+    }
+}
+
+/* Ggml.cs:1025-1061 dequantize_row_q5_0. */
+void orc_dequantize_row_q5_0(const void *vx, float *y, int k)
+{
+    const block_q5_0 *x = (const block_q5_0 *)vx;
+    const int nb = k / QK;
+    for (int i = 0; i < nb; i++) {
+        const float d = orc_f16_to_f32(x[i].d);
+        uint32_t qh; memcpy(&qh, x[i].qh, 4);
+        for (int l = 0; l < QK; l += 2) {
+            const uint8_t vi = x[i].qs[l / 2];
+            const int vh0 = (int)((qh >> (l + 0)) & 1u) << 4, vh1 = (int)((qh >> (l + 1)) & 1u) << 4;
+            const int vi0 = (vi & 0x0F) | vh0, vi1 = (vi >> 4) | vh1;
+            y[i * QK + l + 0] = (float)(vi0 - 16) * d;
+            y[i * QK + l + 1] = (float)(vi1 - 16) * d;
+        }
+    }
+}
+
+/* Ggml.cs:1064-1101 dequantize_row_q5_1 (D9): q*d rounded, then + m rounded. */
+void orc_dequantize_row_q5_1(const void *vx, float *y, int k)
+{
+    const block_q5_1 *x = (const block_q5_1 *)vx;
+    const int nb = k / QK;
+    for (int i = 0; i < nb; i++) {
+        const float d = orc_f16_to_f32(x[i].d), m = orc_f16_to_f32(x[i].m);
+        uint32_t qh; memcpy(&qh, x[i].qh, 4);
+        for (int l = 0; l < QK; l += 2) {
+            const uint8_t vi = x[i].qs[l / 2];
+            const int vh0 = (int)((qh >> (l + 0)) & 1u) << 4, vh1 = (int)((qh >> (l + 1)) & 1u) << 4;
+            const float p0 = (float)((vi & 0x0F) | vh0) * d;
+            const float p1 = (float)((vi >> 4) | vh1) * d;
+            y[i * QK + l + 0] = p0 + m;
+            y[i * QK + l + 1] = p1 + m;
+        }
+    }
+}
+
+/* Ggml.cs:1104-1122 dequantize_row_q8_0, quants signed (D4). */
+void orc_dequantize_row_q8_0(const void *vx, float *y, int k)
+{
+    const block_q8_0 *x = (const block_q8_0 *)vx;
+    const int nb = k / QK;
+    for (int i = 0; i < nb; i++)
+        for (int l = 0; l < QK; l++) y[i * QK + l] = (float)x[i].qs[l] * x[i].d;
+}
+
+/* Ggml.cs:1204-1254: two 16-element Q4_2 blocks against one Q8_0 block; q8 signed (D4), scales as fp16 bits (D9). */
+void orc_vec_dot_q4_2_q8_0(int n, float *s, const void *vx, const void *vy)
+{
+    const block_q4_2 *x = (const block_q4_2 *)vx;
+    const block_q8_0 *y = (const block_q8_0 *)vy;
+    const int nb = n / QK;
+    float sumf = 0.0f;
+    for (int i = 0; i < nb; i++) {
+        const uint8_t *x0 = x[2 * i + 0].qs, *x1 = x[2 * i + 1].qs;
+        const int8_t *y0 = y[i].qs;
+        const float d0 = orc_f16_to_f32(x[2 * i + 0].d), d1 = orc_f16_to_f32(x[2 * i + 1].d);
+        int sumi_0 = 0, sumi_1 = 0;
+        for (int j = 0; j < QK / 4; j++) {
+            const uint8_t v0 = x0[j], v1 = x1[j];
+            const int i0_0 = (v0 & 0x0F) - 8, i1_0 = (v0 >> 4) - 8;
+            const int i0_1 = (v1 & 0x0F) - 8, i1_1 = (v1 >> 4) - 8;
+            const int i2_0 = y0[2 * j + 0], i3_0 = y0[2 * j + 1];
+            const int i2_1 = y0[2 * (j + QK / 4) + 0], i3_1 = y0[2 * (j + QK / 4) + 1];
+            sumi_0 += i0_0 * i2_0 + i1_0 * i3_0;
+            sumi_1 += i0_1 * i2_1 + i1_1 * i3_1;
+        }
+        const float a = d0 * y[i].d, b = d1 * y[i].d;
+        sumf += a * (float)sumi_0;
+        sumf += b * (float)sumi_1;
+    }
+    *s = sumf;
+}
+
+/* Ggml.cs:1258-1301: sumf += (d * sxy) * y.d. */
+void orc_vec_dot_q5_0_q8_0(int n, float *s, const void *vx, const void *vy)
+{
+    const block_q5_0 *x = (const block_q5_0 *)vx;
+    const block_q8_0 *y = (const block_q8_0 *)vy;
+    const int nb = n / QK;
+    float sumf = 0.0f;
+    for (int i = 0; i < nb; i++) {
+        uint32_t qh; memcpy(&qh, x[i].qh, 4);
+        const float d = orc_f16_to_f32(x[i].d);
+        int sxy = 0;
+        for (int j = 0; j < QK / 2; j++) {
+            const uint8_t v0 = x[i].qs[j];
+            const int h0 = (int)((qh >> (2 * j + 0)) & 1u) << 4, h1 = (int)((qh >> (2 * j + 1)) & 1u) << 4;
+            const int a0 = ((v0 & 0x0F) | h0) - 16, a1 = ((v0 >> 4) | h1) - 16;
+            sxy += a0 * y[i].qs[2 * j + 0] + a1 * y[i].qs[2 * j + 1];
+        }
+        const float t = d * (float)sxy;
+        sumf += t * y[i].d;
+    }
+    *s = sumf;
+}
+
+/* Ggml.cs:1304-1348: sumf += (d * sxy) * y.d + m * (y.s0 + y.s1)  (D9 for d and m). */
+void orc_vec_dot_q5_1_q8_1(int n, float *s, const void *vx, const void *vy)
+{
+    const block_q5_1 *x = (const block_q5_1 *)vx;
+    const block_q8_1 *y = (const block_q8_1 *)vy;
+    const int nb = n / QK;
+    float sumf = 0.0f;
+    for (int i = 0; i < nb; i++) {
+        uint32_t qh; memcpy(&qh, x[i].qh, 4);
+        const float d = orc_f16_to_f32(x[i].d), m = orc_f16_to_f32(x[i].m);
+        int sxy = 0;
+        for (int j = 0; j < QK / 2; j++) {
+            const uint8_t v0 = x[i].qs[j];
+            const int h0 = (int)((qh >> (2 * j + 0)) & 1u) << 4, h1 = (int)((qh >> (2 * j + 1)) & 1u) << 4;
+            const int a0 = (v0 & 0x0F) | h0, a1 = (v0 >> 4) | h1;
+            sxy += a0 * y[i].qs[2 * j + 0] + a1 * y[i].qs[2 * j + 1];
+        }
+        const float t = d * (float)sxy;
+        const float u = t * y[i].d;
+        const float ss = y[i].s0 + y[i].s1;
+        const float w = m * ss;
+        const float term = u + w;
+        sumf += term;
+    }
+    *s = sumf;
+}
+
+/* Ggml.cs:1351-1380: both sides int8 (D4). */
+void orc_vec_dot_q8_0_q8_0(int n, float *s, const void *vx, const void *vy)
+{
+    const block_q8_0 *x = (const block_q8_0 *)vx;
+    const block_q8_0 *y = (const block_q8_0 *)vy;
+    const int nb = n / QK;
+    float sumf = 0.0f;
+    for (int i = 0; i < nb; i++) {
+        int sumi = 0;
+        for (int j = 0; j < QK; j++) sumi += (int)x[i].qs[j] * (int)y[i].qs[j];
+        const float dd = x[i].d * y[i].d;
+        sumf += dd * (float)sumi;
+    }
+    *s = sumf;
+}
+
+/* quantize_fns[] looked up BY TYPE (D1): block bytes, block elements, and which Q8 flavour src1 is quantized to. */
+static size_t q_type_size(int t)
+{
+    switch (t) { case T_Q4_0: return 20; case T_Q4_1: return 24; case T_Q4_2: return 10; case T_Q5_0: return 22;
+                 case T_Q5_1: return 24; case T_Q8_0: return 36; case T_Q8_1: return 44; default: return 0; }
+}
+static int q_blck(int t) { return t == T_Q4_2 ? QK4_2 : QK; }
+static int q_dot_type(int t)       /* vec_dot_type, Ggml.cs:226, 235, 244, 254, 263, 272 */
+{
+    switch (t) { case T_Q4_0: case T_Q4_2: case T_Q5_0: case T_Q8_0: return T_Q8_0;
+                 case T_Q4_1: case T_Q5_1: return T_Q8_1; default: return -1; }
+}
+static void q_vec_dot(int t, int n, float *s, const void *x, const void *y)
+{
+    switch (t) {
+    case T_Q4_0: orc_vec_dot_q4_0_q8_0(n, s, x, y); break;
+    case T_Q4_1: orc_vec_dot_q4_1_q8_1(n, s, x, y); break;
+    case T_Q4_2: orc_vec_dot_q4_2_q8_0(n, s, x, y); break;
+    case T_Q5_0: orc_vec_dot_q5_0_q8_0(n, s, x, y); break;
+    case T_Q5_1: orc_vec_dot_q5_1_q8_1(n, s, x, y); break;
+    default:     orc_vec_dot_q8_0_q8_0(n, s, x, y); break;
+    }
+}
+
 /* ---- mul_mat drivers ---- */
 
 /* What ggml_compute_forward_mul_mat sees: shapes and byte strides of three
@@ -327,9 +624,10 @@ size_t orc_mul_mat_work_size(int type, int64_t nelements_src1)
     switch (type) {
     case T_F32: return 0;
     case T_F16: return (size_t)(2 * nelements_src1);
-    case T_Q4_0: return (size_t)(sizeof(block_q8_0) * (size_t)nelements_src1 / QK);
-    case T_Q4_1: return (size_t)(sizeof(block_q8_1) * (size_t)nelements_src1 / QK);
-    default: return 0;
+    default:
+        if (q_dot_type(type) == T_Q8_0) return (size_t)(sizeof(block_q8_0) * (size_t)nelements_src1 / QK);
+        if (q_dot_type(type) == T_Q8_1) return (size_t)(sizeof(block_q8_1) * (size_t)nelements_src1 / QK);
+        return 0;
     }
 }
 
@@ -343,15 +641,16 @@ static void mm_init(const orc_mm *p)
         for (int64_t i11 = 0; i11 < ne11; ++i11) for (int64_t i10 = 0; i10 < ne10; ++i10)
             w[id++] = orc_f32_to_f16(*(const float *)((const char *)p->src1 +
                         i13 * p->nb1[3] + i12 * p->nb1[2] + i11 * p->nb1[1] + i10 * p->nb1[0]));
-    } else if (p->type == T_Q4_0 || p->type == T_Q4_1) {
-        const size_t tsz = p->type == T_Q4_0 ? sizeof(block_q8_0) : sizeof(block_q8_1);
+    } else if (q_dot_type(p->type) >= 0) {
+        const int dot0 = q_dot_type(p->type) == T_Q8_0;
+        const size_t tsz = dot0 ? sizeof(block_q8_0) : sizeof(block_q8_1);
         const size_t row_size = (size_t)ne10 * tsz / QK;
         char *w = (char *)p->wdata;
         for (int64_t i13 = 0; i13 < ne13; ++i13) for (int64_t i12 = 0; i12 < ne12; ++i12)
         for (int64_t i11 = 0; i11 < ne11; ++i11) {
             const float *row = (const float *)((const char *)p->src1 + i13 * p->nb1[3] + i12 * p->nb1[2] + i11 * p->nb1[1]);
-            if (p->type == T_Q4_0) orc_quantize_row_q8_0(row, w, (int)ne10);
-            else                   orc_quantize_row_q8_1(row, w, (int)ne10);
+            if (dot0) orc_quantize_row_q8_0(row, w, (int)ne10);
+            else      orc_quantize_row_q8_1(row, w, (int)ne10);
             w += row_size;
         }
     }
@@ -368,8 +667,8 @@ static void mm_compute(const orc_mm *p, int ith)
     const uint64_t ir0 = dr * (uint64_t)ith;
     const uint64_t ir1 = ir0 + dr < nr ? ir0 + dr : nr;
     size_t row_size = 0;
-    if (p->type == T_Q4_0) row_size = (size_t)ne00 * sizeof(block_q8_0) / QK;
-    if (p->type == T_Q4_1) row_size = (size_t)ne00 * sizeof(block_q8_1) / QK;
+    if (q_dot_type(p->type) == T_Q8_0) row_size = (size_t)ne00 * sizeof(block_q8_0) / QK;
+    if (q_dot_type(p->type) == T_Q8_1) row_size = (size_t)ne00 * sizeof(block_q8_1) / QK;
 
     for (uint64_t ir = ir0; ir < ir1; ++ir) {
         const uint64_t i03 = ir / (uint64_t)(ne02 * ne01);
@@ -391,10 +690,8 @@ static void mm_compute(const orc_mm *p, int ith)
                     orc_vec_dot_f16((int)ne00, &dst_col[ic * ne0], (const uint16_t *)src0_row, col + ic * (uint64_t)ne00);
             } else {
                 const char *col = (const char *)p->wdata + (i02 * (uint64_t)ne11 + i03 * (uint64_t)ne12 * (uint64_t)ne11) * row_size;
-                for (uint64_t ic = 0; ic < (uint64_t)ne11; ++ic) {
-                    if (p->type == T_Q4_0) orc_vec_dot_q4_0_q8_0((int)ne00, &dst_col[ic * ne0], src0_row, col + ic * row_size);
-                    else                   orc_vec_dot_q4_1_q8_1((int)ne00, &dst_col[ic * ne0], src0_row, col + ic * row_size);
-                }
+                for (uint64_t ic = 0; ic < (uint64_t)ne11; ++ic)
+                    q_vec_dot(p->type, (int)ne00, &dst_col[ic * ne0], src0_row, col + ic * row_size);
             }
         }
     }
@@ -409,7 +706,7 @@ static void *mm_thread(void *a) { mm_compute(((mm_arg *)a)->p, ((mm_arg *)a)->it
  * -1 for a type the dispatch asserts on, -2 if wsize is too small. */
 int orc_mul_mat(const orc_mm *p)
 {
-    if (p->type != T_F32 && p->type != T_F16 && p->type != T_Q4_0 && p->type != T_Q4_1) return -1;
+    if (p->type != T_F32 && p->type != T_F16 && q_dot_type(p->type) < 0) return -1;     /* Q4_3 / Q8_1 weights: null table entries */
     int64_t nel1 = p->ne1[0] * p->ne1[1] * p->ne1[2] * p->ne1[3];
     if (orc_mul_mat_work_size(p->type, nel1) > p->wsize) return -2;
     mm_init(p);
@@ -428,9 +725,9 @@ int orc_mul_mat(const orc_mm *p)
 /* Convenience for contiguous 2-D operands: W[M][K] (type), X[N][K] f32 -> Y[N][M] f32. */
 int orc_mul_mat_2d(int type, const void *W, int64_t M, int64_t K, const float *X, int64_t N, float *Y, int nth)
 {
-    size_t tsz = type == T_F32 ? 4 : type == T_F16 ? 2 : type == T_Q4_0 ? 20 : type == T_Q4_1 ? 24 : 0;
-    int64_t blck = (type == T_Q4_0 || type == T_Q4_1) ? QK : 1;
-    if (!tsz || K % blck) return -1;
+    size_t tsz = type == T_F32 ? 4 : type == T_F16 ? 2 : q_dot_type(type) >= 0 ? q_type_size(type) : 0;
+    int64_t blck = (type == T_F32 || type == T_F16) ? 1 : q_blck(type);
+    if (!tsz || K % blck || (blck > 1 && K % QK)) return -1;            /* the dot asserts n % QK8_0 == 0 (Ggml.cs:1209) */
     orc_mm p; memset(&p, 0, sizeof p);
     p.type = type; p.nth = nth;
     p.ne0[0] = K; p.ne0[1] = M; p.ne0[2] = p.ne0[3] = 1;
@@ -450,14 +747,16 @@ int orc_mul_mat_2d(int type, const void *W, int64_t M, int64_t K, const float *X
 /* Row helpers over many rows (what ggml_compute_forward_dup_f32 does per row, Ggml.cs:4339-4363). */
 int orc_quantize_rows(int type, const float *x, void *y, int64_t nrows, int64_t k)
 {
-    if (k % QK) return -1;
-    size_t rs = (size_t)(k / QK) * (type == T_Q4_0 ? 20 : type == T_Q4_1 ? 24 : type == T_Q8_0 ? 36 : type == T_Q8_1 ? 44 : 0);
-    if (!rs) return -1;
+    if (k % QK || !q_type_size(type)) return -1;
+    size_t rs = (size_t)(k / q_blck(type)) * q_type_size(type);
     for (int64_t r = 0; r < nrows; r++) {
         const float *xr = x + r * k; char *yr = (char *)y + (size_t)r * rs;
         switch (type) {
         case T_Q4_0: orc_quantize_row_q4_0(xr, yr, (int)k); break;
         case T_Q4_1: orc_quantize_row_q4_1(xr, yr, (int)k); break;
+        case T_Q4_2: orc_quantize_row_q4_2(xr, yr, (int)k); break;
+        case T_Q5_0: orc_quantize_row_q5_0(xr, yr, (int)k); break;
+        case T_Q5_1: orc_quantize_row_q5_1(xr, yr, (int)k); break;
         case T_Q8_0: orc_quantize_row_q8_0(xr, yr, (int)k); break;
         default:     orc_quantize_row_q8_1(xr, yr, (int)k); break;
         }
@@ -467,11 +766,18 @@ int orc_quantize_rows(int type, const float *x, void *y, int64_t nrows, int64_t 
 
 int orc_dequantize_rows(int type, const void *x, float *y, int64_t nrows, int64_t k)
 {
-    if (k % QK || (type != T_Q4_0 && type != T_Q4_1)) return -1;
-    size_t rs = (size_t)(k / QK) * (type == T_Q4_0 ? 20 : 24);
+    if (k % QK || q_dot_type(type) < 0) return -1;                   /* Q8_1 has no dequantize_row_q (Ggml.cs:278) */
+    size_t rs = (size_t)(k / q_blck(type)) * q_type_size(type);
     for (int64_t r = 0; r < nrows; r++) {
-        if (type == T_Q4_0) orc_dequantize_row_q4_0((const char *)x + (size_t)r * rs, y + r * k, (int)k);
-        else                orc_dequantize_row_q4_1((const char *)x + (size_t)r * rs, y + r * k, (int)k);
+        const char *xr = (const char *)x + (size_t)r * rs; float *yr = y + r * k;
+        switch (type) {
+        case T_Q4_0: orc_dequantize_row_q4_0(xr, yr, (int)k); break;
+        case T_Q4_1: orc_dequantize_row_q4_1(xr, yr, (int)k); break;
+        case T_Q4_2: orc_dequantize_row_q4_2(xr, yr, (int)k); break;
+        case T_Q5_0: orc_dequantize_row_q5_0(xr, yr, (int)k); break;
+        case T_Q5_1: orc_dequantize_row_q5_1(xr, yr, (int)k); break;
+        default:     orc_dequantize_row_q8_0(xr, yr, (int)k); break;
+        }
     }
     return 0;
 }
@@ -538,17 +844,17 @@ void orc_rms_norm_f32(int64_t nrows, int64_t ne00, const float *x, int64_t x_str
  * quantizers (defect D5). */
 int orc_add_q_f32(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k)
 {
-    if (type != 2 && type != 3) return -2;
+    if (q_dot_type(type) < 0) return -2;
     if (k % 32) return -1;
-    const size_t rb = (size_t)(k / 32) * (type == 2 ? 20 : 24);
+    const size_t rb = (size_t)(k / q_blck(type)) * q_type_size(type);
     float *w = (float *)malloc((size_t)k * sizeof(float));
     if (!w) return -4;
     for (int64_t r = 0; r < nrows; r++) {
         const uint8_t *s = (const uint8_t *)src0 + (size_t)r * rb;
         uint8_t *d = (uint8_t *)dst + (size_t)r * rb;
-        if (type == 2) orc_dequantize_row_q4_0(s, w, (int)k); else orc_dequantize_row_q4_1(s, w, (int)k);
+        orc_dequantize_rows(type, s, w, 1, k);
         for (int64_t i = 0; i < k; i++) w[i] += src1[r * k + i];
-        if (type == 2) orc_quantize_row_q4_0(w, d, (int)k); else orc_quantize_row_q4_1(w, d, (int)k);
+        orc_quantize_rows(type, w, d, 1, k);
     }
     free(w);
     return 0;

@@ -13,9 +13,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libggb_oracle.so")
 
-F32, F16, Q4_0, Q4_1, Q8_0, Q8_1 = 0, 1, 2, 3, 8, 9
-TYPE_SIZE = {F32: 4, F16: 2, Q4_0: 20, Q4_1: 24, Q8_0: 36, Q8_1: 44}
-BLCK_SIZE = {F32: 1, F16: 1, Q4_0: 32, Q4_1: 32, Q8_0: 32, Q8_1: 32}
+F32, F16, Q4_0, Q4_1, Q4_2, Q5_0, Q5_1, Q8_0, Q8_1 = 0, 1, 2, 3, 4, 6, 7, 8, 9
+TYPE_SIZE = {F32: 4, F16: 2, Q4_0: 20, Q4_1: 24, Q4_2: 10, Q5_0: 22, Q5_1: 24, Q8_0: 36, Q8_1: 44}
+BLCK_SIZE = {F32: 1, F16: 1, Q4_0: 32, Q4_1: 32, Q4_2: 16, Q5_0: 32, Q5_1: 32, Q8_0: 32, Q8_1: 32}
 
 
 def build(force=False):
@@ -48,7 +48,8 @@ def lib():
         _lib.orc_dequantize_rows.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
         _lib.orc_f32_to_f16_row.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         _lib.orc_f16_to_f32_row.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
-        for n in ("orc_vec_dot_f32", "orc_vec_dot_f16", "orc_vec_dot_q4_0_q8_0", "orc_vec_dot_q4_1_q8_1"):
+        for n in ("orc_vec_dot_f32", "orc_vec_dot_f16", "orc_vec_dot_q4_0_q8_0", "orc_vec_dot_q4_1_q8_1",
+                  "orc_vec_dot_q4_2_q8_0", "orc_vec_dot_q5_0_q8_0", "orc_vec_dot_q5_1_q8_1", "orc_vec_dot_q8_0_q8_0"):
             getattr(_lib, n).argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 

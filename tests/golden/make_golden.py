@@ -281,6 +281,212 @@ def main_ops():
     print("wrote ops_small.json")
 
 
+# ---- sibling weight formats: Q4_2, Q5_0, Q5_1, Q8_0 ----
+# fp16 scales are stored / read as IEEE binary16 bit patterns (defect D9 of oracle/ggb_oracle.c's header: the C# stores
+# `(ushort)(Half)d`, a numeric cast); np.float16 casts are RNE like (Half)float.
+
+def h16(v):
+    return np.float32(v).astype(np.float16)
+
+
+def trunc_int(v):  # C# (int)float for the in-range values these quantizers produce
+    return int(np.trunc(float(v)))
+
+
+def q4_2_block(x):  # Ggml.cs:554-589, 16 elements
+    amax, mx = f32(0), f32(0)
+    for v in x:
+        if amax < abs(v):
+            amax, mx = abs(v), v
+    d = f32(mx / f32(-8))
+    idv = f32(f32(1) / d) if d != 0 else f32(0)
+    qs = bytearray(8)
+    for l in range(0, 16, 2):
+        vi0 = min(15, rne(f32(x[l] * idv)) + 8)
+        vi1 = min(15, rne(f32(x[l + 1] * idv)) + 8)
+        qs[l // 2] = (vi0 | (vi1 << 4)) & 0xFF
+    return h16(d).tobytes() + bytes(qs)
+
+
+def q5_0_block(x):  # Ggml.cs:614-652
+    amax, mx = f32(0), f32(0)
+    for v in x:
+        if amax < abs(v):
+            amax, mx = abs(v), v
+    d = f32(mx / f32(-16))
+    idv = f32(f32(1) / d) if d != 0 else f32(0)
+    qs, qh = bytearray(16), 0
+    for l in range(0, 32, 2):
+        vi0 = min(31, trunc_int(f32(f32(x[l] * idv) + f32(16.5))))
+        vi1 = min(31, trunc_int(f32(f32(x[l + 1] * idv) + f32(16.5))))
+        qs[l // 2] = (vi0 & 15) | ((vi1 & 15) << 4)
+        qh |= ((vi0 >> 4) & 1) << l
+        qh |= ((vi1 >> 4) & 1) << (l + 1)
+    return h16(d).tobytes() + struct.pack("<I", qh) + bytes(qs)
+
+
+def q5_1_block(x):  # Ggml.cs:677-714
+    mn, mx = f32(np.finfo(np.float32).max), f32(-np.finfo(np.float32).max)
+    for v in x:
+        if v < mn:
+            mn = v
+        if v > mx:
+            mx = v
+    d = f32(f32(mx - mn) / f32(31))
+    idv = f32(f32(1) / d) if d != 0 else f32(0)
+    qs, qh = bytearray(16), 0
+    for l in range(0, 32, 2):
+        vi0 = trunc_int(f32(f32(f32(x[l] - mn) * idv) + f32(0.5)))
+        vi1 = trunc_int(f32(f32(f32(x[l + 1] - mn) * idv) + f32(0.5)))
+        qs[l // 2] = (vi0 & 15) | ((vi1 & 15) << 4)
+        qh |= ((vi0 >> 4) & 1) << l
+        qh |= ((vi1 >> 4) & 1) << (l + 1)
+    return h16(d).tobytes() + h16(mn).tobytes() + struct.pack("<I", qh) + bytes(qs)
+
+
+def _h(b, off):
+    return f32(np.frombuffer(b, dtype=np.float16, count=1, offset=off)[0])
+
+
+def deq4_2_row(b):  # Ggml.cs:1001-1021
+    out = []
+    for i in range(0, len(b), 10):
+        d = _h(b, i)
+        for j in range(8):
+            vi = b[i + 2 + j]
+            out += [f32(f32((vi & 15) - 8) * d), f32(f32((vi >> 4) - 8) * d)]
+    return np.array(out, dtype=np.float32)
+
+
+def _q5(b, qoff, qhoff):
+    qh = struct.unpack_from("<I", b, qhoff)[0]
+    q = []
+    for j in range(16):
+        vi = b[qoff + j]
+        q += [(vi & 15) | (((qh >> (2 * j)) & 1) << 4), (vi >> 4) | (((qh >> (2 * j + 1)) & 1) << 4)]
+    return q
+
+
+def deq5_0_row(b):  # Ggml.cs:1034-1060
+    out = []
+    for i in range(0, len(b), 22):
+        d = _h(b, i)
+        out += [f32(f32(q - 16) * d) for q in _q5(b, i + 6, i + 2)]
+    return np.array(out, dtype=np.float32)
+
+
+def deq5_1_row(b):  # Ggml.cs:1073-1100
+    out = []
+    for i in range(0, len(b), 24):
+        d, m = _h(b, i), _h(b, i + 2)
+        out += [f32(f32(f32(q) * d) + m) for q in _q5(b, i + 8, i + 4)]
+    return np.array(out, dtype=np.float32)
+
+
+def deq8_0_row(b):  # Ggml.cs:1111-1121, quants signed (D4)
+    out = []
+    for i in range(0, len(b), 36):
+        d = f32(struct.unpack_from("<f", b, i)[0])
+        out += [f32(f32(q) * d) for q in struct.unpack_from("<32b", b, i + 4)]
+    return np.array(out, dtype=np.float32)
+
+
+def dot_q4_2_q8_0(wb, xb, n):  # Ggml.cs:1216-1251
+    sumf = f32(0)
+    for i in range(n // 32):
+        yd = f32(struct.unpack_from("<f", xb, 36 * i)[0])
+        p = struct.unpack_from("<32b", xb, 36 * i + 4)
+        for half in range(2):
+            o = 10 * (2 * i + half)
+            d = _h(wb, o)
+            sumi = 0
+            for j in range(8):
+                v = wb[o + 2 + j]
+                sumi += ((v & 15) - 8) * p[16 * half + 2 * j] + ((v >> 4) - 8) * p[16 * half + 2 * j + 1]
+            sumf = f32(sumf + f32(f32(d * yd) * f32(sumi)))
+    return sumf
+
+
+def dot_q5_0_q8_0(wb, xb, n):  # Ggml.cs:1270-1298
+    sumf = f32(0)
+    for i in range(n // 32):
+        yd = f32(struct.unpack_from("<f", xb, 36 * i)[0])
+        p = struct.unpack_from("<32b", xb, 36 * i + 4)
+        d = _h(wb, 22 * i)
+        sxy = sum((q - 16) * pv for q, pv in zip(_q5(wb, 22 * i + 6, 22 * i + 2), p))
+        sumf = f32(sumf + f32(f32(d * f32(sxy)) * yd))
+    return sumf
+
+
+def dot_q5_1_q8_1(wb, xb, n):  # Ggml.cs:1316-1345
+    sumf = f32(0)
+    for i in range(n // 32):
+        yd, s0, s1 = (f32(v) for v in struct.unpack_from("<fff", xb, 44 * i))
+        p = struct.unpack_from("<32b", xb, 44 * i + 12)
+        d, m = _h(wb, 24 * i), _h(wb, 24 * i + 2)
+        sxy = sum(q * pv for q, pv in zip(_q5(wb, 24 * i + 8, 24 * i + 4), p))
+        sumf = f32(sumf + f32(f32(f32(d * f32(sxy)) * yd) + f32(m * f32(s0 + s1))))
+    return sumf
+
+
+def dot_q8_0_q8_0(wb, xb, n):  # Ggml.cs:1362-1377
+    sumf = f32(0)
+    for i in range(n // 32):
+        xd = f32(struct.unpack_from("<f", wb, 36 * i)[0])
+        yd = f32(struct.unpack_from("<f", xb, 36 * i)[0])
+        a = struct.unpack_from("<32b", wb, 36 * i + 4)
+        p = struct.unpack_from("<32b", xb, 36 * i + 4)
+        sumf = f32(sumf + f32(f32(xd * yd) * f32(sum(u * v for u, v in zip(a, p)))))
+    return sumf
+
+
+def main_siblings():
+    rng = np.random.default_rng(20231020)
+    blocks = {
+        "A_ramp": np.arange(32, dtype=np.float32) - 16,
+        "B_tenths": (f32(0.1) * np.arange(32, dtype=np.float32)).astype(np.float32),
+        "C_zeros": np.zeros(32, dtype=np.float32),
+        "D_tie_pos_first": np.array([3, -3] + [1] * 30, dtype=np.float32),
+        "E_tie_neg_first": np.array([-3, 3] + [1] * 30, dtype=np.float32),
+        "F_halves": (np.arange(32, dtype=np.float32) - 16) * f32(0.5) + f32(0.25),
+        "G_const": np.full(32, 2.5, dtype=np.float32),
+        "H_one_spike": np.array([0] * 31 + [-7.75], dtype=np.float32),
+        "J_normal": rng.standard_normal(32).astype(np.float32),
+        "K_uniform": rng.uniform(-1, 1, 32).astype(np.float32),
+        "L_weights": (rng.standard_normal(32) * 0.02).astype(np.float32),
+        "N_small": (rng.standard_normal(32) * 1e-4).astype(np.float32),      # d is a subnormal half
+    }
+    q42 = lambda x: q4_2_block(x[:16]) + q4_2_block(x[16:])
+    kats = []
+    for name, x in blocks.items():
+        b42, b50, b51, b80 = q42(x), q5_0_block(x), q5_1_block(x), q8_block(x, False)
+        kats.append({"name": name, "x": hexf(x), "q4_2": b42.hex(), "q5_0": b50.hex(), "q5_1": b51.hex(), "q8_0": b80.hex(),
+                     "deq4_2": hexf(deq4_2_row(b42)), "deq5_0": hexf(deq5_0_row(b50)),
+                     "deq5_1": hexf(deq5_1_row(b51)), "deq8_0": hexf(deq8_0_row(b80))})
+    # hand-derived from Ggml.cs:609-653 for x[l] = l - 16: max = -16 -> d = 1 (0x3c00), x*id + 16.5 truncates to l, so
+    # qs[j] = (2j & 15) | ((2j+1 & 15) << 4) and the fifth bits are set for l >= 16
+    assert kats[0]["q5_0"] == "003c" + "0000ffff" + "1032547698badcfe" * 2
+    # Ggml.cs:672-714: min = -16, d = 1, the same quants, m = -16 (0xcc00)
+    assert kats[0]["q5_1"] == "003c" + "00cc" + "0000ffff" + "1032547698badcfe" * 2
+    # Ggml.cs:547-590 on the two halves: first max = -16 -> d = 2 (0x4000): round(-8, -7.5, .. -0.5) + 8 = 0 0 1 2 2 3 4 4 ...
+    assert kats[0]["q4_2"][:4] == "0040"
+    M, K, N = 6, 96, 3
+    W = (rng.standard_normal((M, K)) * 0.05).astype(np.float32)
+    X = rng.standard_normal((N, K)).astype(np.float32)
+    out = {"source": "tests/golden/make_golden.py", "blocks": kats, "M": M, "K": K, "N": N, "W": hexf(W), "X": hexf(X)}
+    X80 = [quant_row(lambda b: q8_block(b, False), X[n]) for n in range(N)]
+    X81 = [quant_row(lambda b: q8_block(b, True), X[n]) for n in range(N)]
+    for key, qfn, dot, xs in (("q4_2", q42, dot_q4_2_q8_0, X80), ("q5_0", q5_0_block, dot_q5_0_q8_0, X80),
+                              ("q5_1", q5_1_block, dot_q5_1_q8_1, X81), ("q8_0", lambda b: q8_block(b, False), dot_q8_0_q8_0, X80)):
+        Wq = [quant_row(qfn, W[m]) for m in range(M)]
+        out["W_" + key] = b"".join(Wq).hex()
+        out[key] = hexf(np.array([[dot(Wq[m], xs[n], K) for m in range(M)] for n in range(N)]))
+    with open(os.path.join(HERE, "sibling_small.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote sibling_small.json (%d blocks)" % len(kats))
+
+
 if __name__ == "__main__":
     main()
     main_ops()
+    main_siblings()

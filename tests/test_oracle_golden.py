@@ -137,3 +137,58 @@ def test_repeat(ops):
     R, K = ops["R"], ops["K"]
     x = _f32(ops["x"]).reshape(R, K)[:, :8].copy()
     assert orc.repeat_f32(x, 2 * R, 24).tobytes().hex() == ops["repeat_2x3"]
+
+
+# ---- sibling weight formats: Q4_2, Q5_0, Q5_1, Q8_0 ----
+
+SIB = [(orc.Q4_2, "q4_2"), (orc.Q5_0, "q5_0"), (orc.Q5_1, "q5_1"), (orc.Q8_0, "q8_0")]
+
+
+@pytest.fixture(scope="module")
+def sib():
+    with open(os.path.join(G, "sibling_small.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("t,key", SIB)
+def test_sibling_quantize_dequantize_kats_bit_exact(sib, t, key):
+    for b in sib["blocks"]:
+        assert orc.quantize_rows(t, _f32(b["x"])).tobytes().hex() == b[key], (b["name"], key)
+        q = np.frombuffer(bytes.fromhex(b[key]), dtype=np.uint8)
+        assert orc.dequantize_rows(t, q, 32).tobytes().hex() == b["de" + key], (b["name"], key)
+
+
+def test_sibling_hand_derived_kats():
+    # derived by hand from Ggml.cs:609-653 / 672-714 for x[l] = l - 16 (see make_golden.py::main_siblings)
+    x = np.arange(32, dtype=np.float32) - 16
+    assert orc.quantize_rows(orc.Q5_0, x).tobytes().hex() == "003c" + "0000ffff" + "1032547698badcfe" * 2
+    assert orc.quantize_rows(orc.Q5_1, x).tobytes().hex() == "003c" + "00cc" + "0000ffff" + "1032547698badcfe" * 2
+    z = np.zeros(32, dtype=np.float32)
+    assert orc.quantize_rows(orc.Q5_0, z).tobytes().hex() == "0080" + "ffffffff" + "00" * 16     # d = -0.0, every quant 16
+    assert orc.quantize_rows(orc.Q4_2, z).tobytes().hex() == ("0080" + "88" * 8) * 2
+
+
+@pytest.mark.parametrize("t,key", SIB)
+@pytest.mark.parametrize("nth", [1, 3])
+def test_sibling_mul_mat_small_golden_bit_exact(sib, t, key, nth):
+    M, K, N = sib["M"], sib["K"], sib["N"]
+    wb = np.frombuffer(bytes.fromhex(sib["W_" + key]), dtype=np.uint8)
+    X = _f32(sib["X"]).reshape(N, K)
+    np.testing.assert_array_equal(orc.encode_weights(t, _f32(sib["W"]).reshape(M, K)).ravel(), wb)
+    got = orc.mul_mat_2d(t, wb, M, K, X, nth=nth)
+    assert got.tobytes().hex() == sib[key]
+
+
+@pytest.mark.parametrize("t,key", SIB)
+def test_sibling_dot_equals_dequantized_dot(t, key):
+    """Independent of any golden file: the quantized dot equals sum(dequant(w) * dequant(q8(x))) up to float reassociation."""
+    rng = np.random.default_rng(11)
+    M, K, N = 5, 256, 2
+    W = (rng.standard_normal((M, K)) * 0.02).astype(np.float32)
+    X = rng.standard_normal((N, K)).astype(np.float32)
+    wq = orc.quantize_rows(t, W)
+    got = orc.mul_mat_2d(t, wq, M, K, X)
+    wd = orc.dequantize_rows(t, wq, K).astype(np.float64)
+    xd = orc.dequantize_rows(orc.Q8_0, orc.quantize_rows(orc.Q8_0, X), K).astype(np.float64)
+    want = xd @ wd.T
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-6
