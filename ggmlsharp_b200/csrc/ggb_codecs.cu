@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) k_dequantize_rows(const uint8_t *__restri
 template <int CAP>
 __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBatchT<CAP> b)
 {
-    if (b.wtype == GGML_TYPE_Q4_0 || b.wtype == GGML_TYPE_Q4_1) {
+    if (b.wtype != GGML_TYPE_F16 && b.wtype != GGML_TYPE_F32) {     // every quantized weight type: src1 -> Q8 blocks (vec_dot_type)
         const int lane = threadIdx.x & 31, sub = lane & 7;
         const int blk = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
         const bool live = blk < b.total_blk;
@@ -493,8 +493,14 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
         int q[4], s = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) { q[i] = (int)(int8_t)rne_byte(__fmul_rn(e[i], id)); s += q[i]; }
-#pragma unroll
-        for (int off = 1; off < 8; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);                 // lanes 0-3: sum of quants 0..15, lanes 4-7: 16..31
+        {
+            const int other = __shfl_xor_sync(0xffffffffu, s, 4);
+            const int lo = sub < 4 ? s : other, hi = sub < 4 ? other : s;
+            // Q4_2 weights: each 16-element weight block needs its own half sum -> two int16; everything else: the block sum
+            s = b.wtype == GGML_TYPE_Q4_2 ? (int)(((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16)) : lo + hi;
+        }
         uint32_t ev = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[2] & 0xFF) << 8);
         uint32_t od = (uint32_t)(q[1] & 0xFF) | ((uint32_t)(q[3] & 0xFF) << 8);
         ev |= __shfl_down_sync(0xffffffffu, ev, 1) << 16;
@@ -606,7 +612,8 @@ __global__ void __launch_bounds__(256) k_act_f16_dequant(const __grid_constant__
 size_t act_row_bytes(int wtype, int64_t K)
 {
     switch (wtype) {
-    case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_1: return align_up((size_t)(K / GGB_QK) * 40, 16);
+    case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_1: case GGML_TYPE_Q4_2: case GGML_TYPE_Q5_0: case GGML_TYPE_Q5_1: case GGML_TYPE_Q8_0:
+        return align_up((size_t)(K / GGB_QK) * 40, 16);
     case GGML_TYPE_F16: return align_up((size_t)K * 2, 16);
     default: return align_up((size_t)K * 4, 16);
     }
@@ -620,6 +627,7 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
         k_f32_to_f16_rows<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, ldx, (__half *)dst, nrows, k);
         count_launch(); GGB_CUDA(cudaGetLastError()); return GGB_OK;
     }
+    if (type == GGML_TYPE_Q4_2 || type == GGML_TYPE_Q5_0 || type == GGML_TYPE_Q5_1) return launch_quantize_rows_sib(type, src, ldx, dst, nrows, k, s);
     if (k % GGB_QK) return set_error(GGB_E_INVALID, "quantize: k=%lld is not a multiple of %d (Ggml.cs:336)", (long long)k, GGB_QK);
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (ldx & 3))
         return set_error(GGB_E_UNSUPPORTED, "quantize: source rows must be 16-byte aligned");
@@ -655,7 +663,8 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
 int launch_add_q_f32(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k, cudaStream_t s)
 {
     if (nrows <= 0 || k <= 0) return GGB_OK;
-    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1) return set_error(GGB_E_UNSUPPORTED, "add_q_f32: type %d is not on this path (Q4_0, Q4_1)", type);
+    if (is_sibling_q(type)) return launch_add_q_f32_sib(type, src0, src1, dst, nrows, k, s);
+    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1) return set_error(GGB_E_UNSUPPORTED, "add_q_f32: type %d has no codec pair (Ggml.cs:219-282)", type);
     if (k % GGB_QK) return set_error(GGB_E_INVALID, "add_q_f32: ne00=%lld %% 32 != 0 (Ggml.cs:4891)", (long long)k);
     if (reinterpret_cast<uintptr_t>(src1) & 15) return set_error(GGB_E_UNSUPPORTED, "add_q_f32: src1 must be 16-byte aligned");
     const long long nblk = nrows * (k / GGB_QK);
@@ -675,6 +684,7 @@ int launch_add_q_f32(int type, const void *src0, const float *src1, void *dst, i
 int launch_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k, cudaStream_t s)
 {
     if (nrows <= 0 || k <= 0) return GGB_OK;
+    if (is_sibling_q(type)) return launch_dequantize_rows_sib(type, src, dst, nrows, k, s);
     if (k % GGB_QK) return set_error(GGB_E_INVALID, "dequantize: k=%lld is not a multiple of %d (Ggml.cs:839)", (long long)k, GGB_QK);
     const long long nblk = nrows * (k / GGB_QK);
     const unsigned grid = (unsigned)std::min<long long>((nblk * 8 + 1023) / 1024, (long long)device_sm_count() * 8);
@@ -688,7 +698,7 @@ int launch_dequantize_rows(int type, const void *src, float *dst, int64_t nrows,
 int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
 {
     long long threads;
-    if (b.wtype == GGML_TYPE_Q4_0 || b.wtype == GGML_TYPE_Q4_1) threads = (long long)b.total_blk * 8;
+    if (is_q_weight(b.wtype)) threads = (long long)b.total_blk * 8;
     else threads = (long long)b.total_blk * ((b.K + 3) / 4);
     if (threads <= 0) return GGB_OK;
     cudaLaunchConfig_t cfg = {};
@@ -711,7 +721,7 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
     return GGB_OK;
 }
 
-int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s)
+int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s, bool pdl)
 {
     if (b.n_nodes <= 0) return GGB_OK;
     long long maxblk = 0;
@@ -731,18 +741,18 @@ int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s)
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
     GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant, b));
     count_launch();
     return GGB_OK;
 }
 
-int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior)
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior, bool pdl)
 {
     static thread_local ActGemmBatch b;
     b.n_nodes = 1; b.wtype = wtype; b.perm = perm; b.wait_prior = wait_prior ? 1 : 0;
     b.node[0] = ActGemmNode{x, (long long)ldx_bytes, out, (int)N, (int)Npad, (int)K, 0};
-    return launch_act_f16_dequant_batch(b, s);
+    return launch_act_f16_dequant_batch(b, s, pdl);
 }
 
 } // namespace ggb

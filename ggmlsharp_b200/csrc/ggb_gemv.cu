@@ -19,8 +19,13 @@
 // sumf += (d0*d1) * (float)sumi in float.  Only the cross-block summation order differs (lane-strided
 // partial sums + a shuffle tree instead of one sequential chain).
 //
+// The sibling formats Q4_2 / Q5_0 / Q5_1 / Q8_0 (ggml_vec_dot_q4_2_q8_0 ... q8_0_q8_0, Ggml.cs:1204-1380) run through
+// the same two kernels: their per-block arithmetic lives in ggb_sib_math.cuh, only the unit geometry differs (Q4_2: 8 blocks =
+// 80 B, Q5_0: 4 blocks = 88 B read with LDS.64, Q5_1: 2 blocks = 48 B, Q8_0: 4 blocks = 144 B; all lane strides conflict-free).
+//
 // Roofline: HBM.  Algorithmic bytes per node = M*row_bytes (weights) + 4*K*N (x) + 4*M*N (y).
 #include "ggb_internal.h"
+#include "ggb_sib_math.cuh"
 
 #include <algorithm>
 
@@ -182,14 +187,40 @@ __device__ __forceinline__ void dot_f32(const uint8_t *w, int off_bytes, int nby
     }
 }
 
+// sibling formats on the plain-staging path: a lane owns one 32-element group (20 / 22 / 24 / 36 bytes, only 2-byte aligned in the
+// stage), gathers it as 16-bit words and runs the shared per-group dot; activations in the linear (bps = 1) Q8P layout
+template <int TYPE, int NC>
+__device__ __forceinline__ void dot_sib(const uint8_t *w, int off_bytes, int nbytes, const uint8_t *xs, int xcol_bytes, int kb,
+                                        int lane, float (&acc)[NC])
+{
+    constexpr int G = sib::Grp<TYPE>::G, NW = (G + 3) / 4;
+    const int ngrp = nbytes / G, g0 = off_bytes / G;
+    for (int i = lane; i < ngrp; i += 32) {
+        const unsigned short *hp = reinterpret_cast<const unsigned short *>(w + i * G);
+        uint32_t wd[NW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) wd[k] = (uint32_t)hp[2 * k] | (2 * k + 1 < G / 2 ? (uint32_t)hp[2 * k + 1] << 16 : 0u);
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const uint8_t *xc = xs + c * xcol_bytes;
+            sib::XBlk x;
+            x.ev = *reinterpret_cast<const int4 *>(xc + (g0 + i) * 16);
+            x.od = *reinterpret_cast<const int4 *>(xc + kb * 16 + (g0 + i) * 16);
+            x.ds = *reinterpret_cast<const int2 *>(xc + kb * 32 + (g0 + i) * 8);
+            acc[c] = sib::dot_group_words<TYPE>(wd, x, acc[c]);
+        }
+    }
+}
+
 template <int TYPE, int NC>
 __device__ __forceinline__ void dot_chunk(const GemvHdr &b, const uint8_t *w, int off_bytes, int nbytes, const uint8_t *xs,
                                           int lane, float (&acc)[NC])
 {
-    if (TYPE == GGML_TYPE_Q4_0) dot_q4_0<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, b.K / GGB_QK, lane, acc);
-    else if (TYPE == GGML_TYPE_Q4_1) dot_q4_1<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, b.K / GGB_QK, lane, acc);
-    else if (TYPE == GGML_TYPE_F16) dot_f16<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, lane, acc);
-    else dot_f32<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, lane, acc);
+    if constexpr (TYPE == GGML_TYPE_Q4_0) dot_q4_0<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, b.K / GGB_QK, lane, acc);
+    else if constexpr (TYPE == GGML_TYPE_Q4_1) dot_q4_1<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, b.K / GGB_QK, lane, acc);
+    else if constexpr (TYPE == GGML_TYPE_F16) dot_f16<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, lane, acc);
+    else if constexpr (TYPE == GGML_TYPE_F32) dot_f32<NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, lane, acc);
+    else dot_sib<TYPE, NC>(w, off_bytes, nbytes, xs, b.xcol_bytes, b.K / GGB_QK, lane, acc);
 }
 
 // Generic path for rows that are not 16-byte multiples / not 16-byte aligned (e.g. K = 4128, byte-offset views): the same
@@ -264,7 +295,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) k_gemv(const __grid_constant__
 
 constexpr int NWF = 15;      // consumer warps; +1 producer warp = 16 warps = 512 threads -> 128 registers per thread
 
-struct XBlk { int4 ev, od; int2 ds; };
+using sib::XBlk;             // one Q8P activation block: even quants, odd quants, {d, sum}
 
 __device__ __forceinline__ int q4_isum(const uint32_t q0, const uint32_t q1, const uint32_t q2, const uint32_t q3, const XBlk &x, int s)
 {
@@ -317,9 +348,42 @@ __device__ __forceinline__ float q4_1_unit(const uint8_t *w, const XBlk (&x)[4],
     return acc;
 }
 
-template <int TYPE> struct UnitTraits { static constexpr int BYTES = 16, BPS = 0; };
-template <> struct UnitTraits<GGML_TYPE_Q4_0> { static constexpr int BYTES = 80, BPS = 4; };
-template <> struct UnitTraits<GGML_TYPE_Q4_1> { static constexpr int BYTES = 48, BPS = 2; };
+// sibling formats: the unit's words are fetched with the widest aligned loads its size allows (Q5_0's 88 bytes: 11 x LDS.64,
+// lane stride 22 words, conflict-free per half-warp; the others LDS.128 with lane strides of 20 / 12 / 36 words); the arithmetic
+// on those words is ggb_sib_math.cuh's dot_unit_words
+template <int TYPE>
+__device__ __forceinline__ float sib_unit(const uint8_t *w, const XBlk (&x)[4], float acc)
+{
+    constexpr int NWORDS = sib::Unit<TYPE>::BYTES / 4;
+    uint32_t v[NWORDS];
+    if constexpr (sib::Unit<TYPE>::BYTES % 16 == 0) {
+        const uint4 *wp = reinterpret_cast<const uint4 *>(w);
+#pragma unroll
+        for (int i = 0; i < NWORDS / 4; i++) { const uint4 a = wp[i]; v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w; }
+    } else {
+        const uint2 *wp = reinterpret_cast<const uint2 *>(w);
+#pragma unroll
+        for (int i = 0; i < NWORDS / 2; i++) { const uint2 a = wp[i]; v[2 * i] = a.x; v[2 * i + 1] = a.y; }
+    }
+    return sib::dot_unit_words<TYPE>(v, x, acc);
+}
+
+template <int TYPE> struct UnitTraits { static constexpr int BYTES = 16, BPS = 0; static constexpr bool Q = false; };
+template <> struct UnitTraits<GGML_TYPE_Q4_0> { static constexpr int BYTES = 80, BPS = 4; static constexpr bool Q = true; };
+template <> struct UnitTraits<GGML_TYPE_Q4_1> { static constexpr int BYTES = 48, BPS = 2; static constexpr bool Q = true; };
+template <> struct UnitTraits<GGML_TYPE_Q4_2> { static constexpr int BYTES = 80, BPS = 4; static constexpr bool Q = true; };
+template <> struct UnitTraits<GGML_TYPE_Q5_0> { static constexpr int BYTES = 88, BPS = 4; static constexpr bool Q = true; };
+template <> struct UnitTraits<GGML_TYPE_Q5_1> { static constexpr int BYTES = 48, BPS = 2; static constexpr bool Q = true; };
+template <> struct UnitTraits<GGML_TYPE_Q8_0> { static constexpr int BYTES = 144, BPS = 4; static constexpr bool Q = true; };
+
+template <int TYPE>
+__device__ __forceinline__ float unit_dot(const uint8_t *w, const XBlk (&x)[4], float acc)
+{
+    if constexpr (TYPE == GGML_TYPE_Q4_0) return q4_0_unit(w, x, acc);
+    else if constexpr (TYPE == GGML_TYPE_Q4_1) return q4_1_unit(w, x, acc);
+    else if constexpr (UnitTraits<TYPE>::Q) return sib_unit<TYPE>(w, x, acc);
+    else return acc;
+}
 
 // partial dot of `nunits` staged units starting at unit u0 of the row
 template <int TYPE, int NC, bool XREG>
@@ -327,9 +391,9 @@ __device__ __forceinline__ void dot_units(const uint8_t *w, int u0, int nunits, 
                                           const XBlk (&xr)[4], int lane, float (&acc)[NC])
 {
     constexpr int UB = UnitTraits<TYPE>::BYTES, BPS = UnitTraits<TYPE>::BPS;
-    if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_1) {
+    if (UnitTraits<TYPE>::Q) {
         if (XREG) {                                               // NC == 1, S <= 32: this lane owns unit `lane`
-            if (lane < nunits) acc[0] = TYPE == GGML_TYPE_Q4_0 ? q4_0_unit(w + lane * UB, xr, acc[0]) : q4_1_unit(w + lane * UB, xr, acc[0]);
+            if (lane < nunits) acc[0] = unit_dot<TYPE>(w + lane * UB, xr, acc[0]);
         } else {
             for (int u = lane; u < nunits; u += 32) {
 #pragma unroll
@@ -337,7 +401,7 @@ __device__ __forceinline__ void dot_units(const uint8_t *w, int u0, int nunits, 
                     XBlk x[4];
 #pragma unroll
                     for (int j = 0; j < BPS; j++) x[j] = load_xblk(xs + c * xcol_bytes, kb, j * S + u0 + u);
-                    acc[c] = TYPE == GGML_TYPE_Q4_0 ? q4_0_unit(w + u * UB, x, acc[c]) : q4_1_unit(w + u * UB, x, acc[c]);
+                    acc[c] = unit_dot<TYPE>(w + u * UB, x, acc[c]);
                 }
             }
         }
@@ -497,7 +561,7 @@ int launch_fast_typed(const GemvBatchT<CAP> &b, size_t smem, int grid, cudaStrea
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    constexpr bool Q = TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_1;
+    constexpr bool Q = UnitTraits<TYPE>::Q;
     const bool xreg = Q && b.ncols == 1 && b.nchunk == 1 && b.row_bytes / UnitTraits<TYPE>::BYTES <= 32;
 #define GGB_FAST_CASE(NCV, XR) { \
         static bool attr_set = false; \
@@ -549,7 +613,17 @@ constexpr int STAGE_MAX = 4096;            // bytes of one bulk copy (one row, s
 
 int gemv_num_ctas() { return device_sm_count(); }
 int gemv_group_rows(const GemvHdr &b) { return b.async ? NWF * b.rs : b.rs; }
-int gemv_act_bps(const GemvHdr &b) { return !b.async ? 1 : b.type == GGML_TYPE_Q4_0 ? 4 : b.type == GGML_TYPE_Q4_1 ? 2 : 1; }
+static int unit_bytes_async(int type)
+{
+    switch (type) { case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_2: return 80; case GGML_TYPE_Q4_1: case GGML_TYPE_Q5_1: return 48;
+                    case GGML_TYPE_Q5_0: return 88; case GGML_TYPE_Q8_0: return 144; default: return 16; }
+}
+int gemv_act_bps(const GemvHdr &b)
+{
+    if (!b.async) return 1;
+    switch (b.type) { case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_2: case GGML_TYPE_Q5_0: case GGML_TYPE_Q8_0: return 4;
+                      case GGML_TYPE_Q4_1: case GGML_TYPE_Q5_1: return 2; default: return 1; }
+}
 
 // Fills the shape-dependent fields of b (everything but the node list).  ncols in {1,2,4,8}.
 int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase)
@@ -561,11 +635,12 @@ int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const vo
     if (row_bytes > (1ll << 30) || xcol * ncols > X_BUDGET + 32 * 1024)
         return set_error(GGB_E_UNSUPPORTED, "mul_mat: K=%lld too large for the shared-memory resident activation vector", (long long)K);
     b.type = type; b.ncols = ncols; b.K = (int)K; b.row_bytes = (int)row_bytes; b.nb01 = nb01; b.xcol_bytes = (int)xcol;
-    const int unit_async = type == GGML_TYPE_Q4_0 ? 80 : type == GGML_TYPE_Q4_1 ? 48 : 16;
-    const int unit_sync = type == GGML_TYPE_Q4_0 ? 20 : type == GGML_TYPE_Q4_1 ? 24 : 16;
+    const int unit_async = unit_bytes_async(type);
+    const int unit_sync = is_q_weight(type) ? (int)q32_bytes(type) : 16;
     // 16-byte aligned rows made of whole units -> TMA bulk staging + the fast kernel; anything else -> plain-load staging
     b.async = ((reinterpret_cast<uintptr_t>(Wbase) & 15) == 0 && (nb01 & 15) == 0 && (row_bytes & 15) == 0 && row_bytes % unit_async == 0) ? 1 : 0;
-    const int unit = b.async ? unit_async : unit_sync;
+    // K-chunks of a long row are bulk copies too, so a chunk must also be a multiple of 16 bytes (Q5_0's 88-byte unit is not)
+    const int unit = b.async ? (unit_async % 16 ? unit_async * 2 : unit_async) : unit_sync;
     if (b.async) {
         // fast kernel: stage = 16*rpw whole rows, or one K-chunk of 16 rows
         if (row_bytes <= STAGE_MAX) {
@@ -626,16 +701,24 @@ static int launch_gemv_cap(const GemvBatchT<CAP> &b, cudaStream_t s, bool pdl)
     if (b.async) switch (b.type) {
     case GGML_TYPE_Q4_0: return launch_fast_typed<GGML_TYPE_Q4_0, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_Q4_1: return launch_fast_typed<GGML_TYPE_Q4_1, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q4_2: return launch_fast_typed<GGML_TYPE_Q4_2, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q5_0: return launch_fast_typed<GGML_TYPE_Q5_0, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q5_1: return launch_fast_typed<GGML_TYPE_Q5_1, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q8_0: return launch_fast_typed<GGML_TYPE_Q8_0, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_F16: return launch_fast_typed<GGML_TYPE_F16, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_F32: return launch_fast_typed<GGML_TYPE_F32, CAP>(b, smem, grid, s, pdl);
-    default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6739-6742)", b.type);
+    default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6719-6742)", b.type);
     }
     switch (b.type) {
     case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q4_2: return launch_typed<GGML_TYPE_Q4_2, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q5_0: return launch_typed<GGML_TYPE_Q5_0, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q5_1: return launch_typed<GGML_TYPE_Q5_1, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q8_0: return launch_typed<GGML_TYPE_Q8_0, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_F32: return launch_typed<GGML_TYPE_F32, CAP>(b, smem, grid, s, pdl);
-    default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6739-6742)", b.type);
+    default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6719-6742)", b.type);
     }
 }
 

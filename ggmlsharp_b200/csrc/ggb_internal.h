@@ -23,11 +23,22 @@ void count_launch(int n = 1);
 static inline size_t type_size(int t) {
     switch (t) { case GGML_TYPE_F32: return 4; case GGML_TYPE_F16: return 2; case GGML_TYPE_Q4_0: return 20;
                  case GGML_TYPE_Q4_1: return 24; case GGML_TYPE_Q8_0: return 36; case GGML_TYPE_Q8_1: return 44;
+                 case GGML_TYPE_Q4_2: return 10; case GGML_TYPE_Q5_0: return 22; case GGML_TYPE_Q5_1: return 24;
                  case GGML_TYPE_I8: return 1; case GGML_TYPE_I16: return 2; case GGML_TYPE_I32: return 4; default: return 0; }
 }
 static inline int blck_size(int t) {
-    switch (t) { case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_1: case GGML_TYPE_Q8_0: case GGML_TYPE_Q8_1: return GGB_QK; default: return 1; }
+    switch (t) { case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_1: case GGML_TYPE_Q5_0: case GGML_TYPE_Q5_1: case GGML_TYPE_Q8_0: case GGML_TYPE_Q8_1: return GGB_QK;
+                 case GGML_TYPE_Q4_2: return 16; default: return 1; }
 }
+// weight types whose mul_mat goes through a quantized dot (the non-null vec_dot_q rows of quantize_fns[], Ggml.cs:219-282)
+static inline bool is_q_weight(int t) {
+    return t == GGML_TYPE_Q4_0 || t == GGML_TYPE_Q4_1 || t == GGML_TYPE_Q4_2 || t == GGML_TYPE_Q5_0 || t == GGML_TYPE_Q5_1 || t == GGML_TYPE_Q8_0;
+}
+// the sibling formats of SURVEY 8f-2 (everything quantized except the two headline Q4 types)
+static inline bool is_sibling_q(int t) { return is_q_weight(t) && t != GGML_TYPE_Q4_0 && t != GGML_TYPE_Q4_1; }
+static inline bool is_mm_weight(int t) { return t == GGML_TYPE_F32 || t == GGML_TYPE_F16 || is_q_weight(t); }
+// bytes of the weights that pair with ONE 32-element activation block (Q4_2: two 16-element blocks)
+static inline size_t q32_bytes(int t) { return t == GGML_TYPE_Q4_2 ? 20 : type_size(t); }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- codecs (ggb_codecs.cu) ----
@@ -36,6 +47,12 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
 int launch_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k, cudaStream_t s);
 // ggml_compute_forward_add_q_f32 on contiguous rows: dst = quantize(dequantize(src0) + src1); dst may alias src0
 int launch_add_q_f32(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k, cudaStream_t s);
+// ggb_codecs_sib.cu: the same three for Q4_2 / Q5_0 / Q5_1 / Q8_0 (the launchers above forward to these), and the dense fp16
+// expansion [M][K] of a sibling-format weight matrix that the batched (tensor-core) path multiplies
+int launch_quantize_rows_sib(int type, const float *src, int64_t ldx, void *dst, int64_t nrows, int64_t k, cudaStream_t s);
+int launch_dequantize_rows_sib(int type, const void *src, float *dst, int64_t nrows, int64_t k, cudaStream_t s);
+int launch_add_q_f32_sib(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k, cudaStream_t s);
+int launch_expand_f16(int type, const void *W, int64_t nb01, __half *out, int64_t M, int64_t K, cudaStream_t s, bool pdl);
 
 // ---- F32 neighbours of mul_mat (ggb_ops.cu) ----
 int launch_binary_f32(int op, const float *a, const float *b, float *dst, int64_t n, cudaStream_t s);       // GGML_OP_ADD / GGML_OP_MUL
@@ -58,11 +75,12 @@ using ActBatch = ActBatchT<GGB_MAX_BATCH_NODES>;
 constexpr int GGB_SMALL_BATCH_NODES = 32;
 int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl);
 // batched path: activations as dense fp16 [Npad][K] holding d * q (the value the reference's dot multiplies by)
-int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior);
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior, bool pdl = true);
 // the same for every node of a grouped GEMM launch, one kernel (grid.y = node)
 struct ActGemmNode { const float *x; long long ldx_bytes; __half *out; int N, Npad, K, vec16; };
 struct ActGemmBatch { int n_nodes, wtype, perm, wait_prior; ActGemmNode node[GGB_GEMM_GROUP_NODES]; };
-int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s);
+// pdl = false: an ordinary stream-ordered launch (used when an earlier kernel of the batch produced the GEMM's weights)
+int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s, bool pdl = true);
 
 // ---- GEMV (ggb_gemv.cu) ----
 struct GemvNode { const uint8_t *W; const uint8_t *xq; float *y; int M; int ldy; int g0; int ngroups; };

@@ -82,27 +82,36 @@ static bool is_device_ptr(const void *p)
 // device-level batch: plan + launch
 // ------------------------------------------------------------------------------------------------
 
+// Sibling formats (Q4_2 / Q5_0 / Q5_1 / Q8_0) on the batched path: the weights are expanded to dense fp16 [M][K] in the workspace
+// (k_expand_f16) and the F16 tcgen05 GEMM multiplies that, against activations staged as d*q like every quantized type.
+static inline bool use_gemm_expanded(const ggb_dev_mm &m)
+{
+    return is_sibling_q(m.type) && m.N >= 16 && m.M > 0 && m.K % GGB_QK == 0 && ((reinterpret_cast<uintptr_t>(m.W) | (uintptr_t)m.nb01) & 1) == 0;
+}
 static inline bool use_gemm(const ggb_dev_mm &m)
 {
-    return m.N >= 16 && gemm_supported(m.type, m.M, m.K, m.N, m.nb01, m.W);
+    return m.N >= 16 && (use_gemm_expanded(m) || gemm_supported(m.type, m.M, m.K, m.N, m.nb01, m.W));
 }
+static inline size_t expanded_bytes(int64_t M, int64_t K) { return align_up((size_t)M * (size_t)K * 2, 256); }
 static size_t mm_ws_bytes(const ggb_dev_mm &m)
 {
+    if (use_gemm_expanded(m)) return align_up(gemm_workspace_bytes(GGML_TYPE_F16, m.M, m.K, m.N), 256) + expanded_bytes(m.M, m.K);
     if (use_gemm(m)) return align_up(gemm_workspace_bytes(m.type, m.M, m.K, m.N), 256);
     return align_up((size_t)m.N * act_row_bytes(m.type, m.K), 256);
 }
 // upper bound that does not depend on operand addresses (for sizing before buffers exist)
 static size_t mm_ws_bytes_bound(int type, int64_t M, int64_t K, int64_t N)
 {
-    return std::max(align_up(gemm_workspace_bytes(type, M, K, N), 256), align_up((size_t)N * act_row_bytes(type, K), 256));
+    const size_t tc = align_up(gemm_workspace_bytes(type, M, K, N), 256) + (is_sibling_q(type) && N >= 16 ? expanded_bytes(M, K) : 0);
+    return std::max(tc, align_up((size_t)N * act_row_bytes(type, K), 256));
 }
 
 static int check_mm(const ggb_dev_mm &m)
 {
-    if (m.type != GGML_TYPE_F32 && m.type != GGML_TYPE_F16 && m.type != GGML_TYPE_Q4_0 && m.type != GGML_TYPE_Q4_1)
-        return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (F32, F16, Q4_0, Q4_1)", m.type);
+    if (!is_mm_weight(m.type))
+        return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d has no vec_dot (F32, F16, Q4_0, Q4_1, Q4_2, Q5_0, Q5_1, Q8_0; Ggml.cs:219-282)", m.type);
     if (m.M < 0 || m.N < 0 || m.K <= 0) return set_error(GGB_E_INVALID, "mul_mat: bad shape M=%lld N=%lld K=%lld", (long long)m.M, (long long)m.N, (long long)m.K);
-    if (m.K % blck_size(m.type)) return set_error(GGB_E_INVALID, "mul_mat: ne00=%lld %% 32 != 0 (Ggml.cs:6694)", (long long)m.K);
+    if (m.K % blck_size(m.type) || (is_q_weight(m.type) && m.K % GGB_QK)) return set_error(GGB_E_INVALID, "mul_mat: ne00=%lld %% 32 != 0 (Ggml.cs:6694)", (long long)m.K);
     const int64_t rb = m.K / blck_size(m.type) * (int64_t)type_size(m.type);
     if (m.nb01 < rb) return set_error(GGB_E_INVALID, "mul_mat: nb01=%lld < row bytes %lld", (long long)m.nb01, (long long)rb);
     if ((m.ldx_bytes & 3) || (m.ldy_bytes & 3) || m.ldx_bytes < 4 * m.K || (m.N > 1 && m.ldy_bytes < 4 * m.M))
@@ -132,8 +141,17 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     std::vector<int> gemv_idx;
     bool first_gemm = true;
     static const bool grouped = [] { const char *e = getenv("GGB200_GEMM_GROUPED"); return !e || atoi(e) != 0; }();
-    std::vector<int> q_nodes[3];                                  // Q4_0 / Q4_1 / F16 nodes of this batch, for the grouped kernels
-    auto qslot = [](int type) { return type == GGML_TYPE_Q4_0 ? 0 : type == GGML_TYPE_Q4_1 ? 1 : 2; };
+    std::vector<int> q_nodes[4];                                  // Q4_0 / Q4_1 / F16 / expanded-sibling nodes of this batch, for the grouped kernels
+    auto qslot = [](int type) { return type == GGML_TYPE_Q4_0 ? 0 : type == GGML_TYPE_Q4_1 ? 1 : type == GGML_TYPE_F16 ? 2 : 3; };
+    // a sibling-format node: expand the weights behind the activation buffer of its workspace slice and hand the GEMM an F16 node.
+    // The expansion is an ordinary (fully stream-ordered) launch and the activation kernel that follows it is launched WITHOUT
+    // programmatic serialization, so the GEMM -- whose weight TMA does not wait for anything -- cannot start before it is complete.
+    auto expand = [&](int i, const void *&Wout, int64_t &nb01_out) -> int {
+        const ggb_dev_mm &m = mm[i];
+        __half *wh = reinterpret_cast<__half *>(wsb + off[i] + align_up(gemm_workspace_bytes(GGML_TYPE_F16, m.M, m.K, m.N), 256));
+        Wout = wh; nb01_out = 2 * m.K;
+        return launch_expand_f16(m.type, m.W, m.nb01, wh, m.M, m.K, s, false);
+    };
     int n_tc = 0;
     for (int i = 0; i < count; i++) if (mm[i].M > 0 && mm[i].N > 0 && use_gemm(mm[i])) n_tc++;
     for (int i = 0; i < count; i++) {
@@ -141,14 +159,19 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         if (m.M == 0 || m.N == 0) continue;
         if (!use_gemm(m)) { gemv_idx.push_back(i); continue; }
         // a lone node keeps the per-node kernel (smaller launch); two or more go through the persistent grouped kernels
-        if (grouped && n_tc > 1 && !getenv("GGB200_GEMM_TRACE") && gemm_grouped_supported(m.type)) { q_nodes[qslot(m.type)].push_back(i); continue; }
+        const bool sibx = use_gemm_expanded(m);
+        const int gtype = sibx ? GGML_TYPE_F16 : m.type;          // what the tensor-core kernel sees
+        if (grouped && n_tc > 1 && !getenv("GGB200_GEMM_TRACE") && gemm_grouped_supported(gtype)) { q_nodes[qslot(m.type)].push_back(i); continue; }
         const int64_t Npad = (m.N + 15) / 16 * 16;
         __half *xh = reinterpret_cast<__half *>(wsb + off[i]);
-        int rc = launch_act_f16_dequant(m.type, gemm_act_perm(m.type), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s, first_gemm);
+        const void *Wg = m.W; int64_t nb01g = m.nb01;
+        int rc = sibx ? expand(i, Wg, nb01g) : GGB_OK;
+        if (rc) return rc;
+        rc = launch_act_f16_dequant(m.type, gemm_act_perm(gtype), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s, first_gemm, !sibx);
         if (rc) return rc;
         first_gemm = false;
         GemmArgs a = {};
-        a.type = m.type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
+        a.type = gtype; a.M = m.M; a.K = m.K; a.N = m.N; a.W = Wg; a.nb01 = nb01g; a.Xh = xh; a.Npad = Npad;
         a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
         for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
         if (const char *tr = getenv("GGB200_GEMM_TRACE")) a.trace = reinterpret_cast<void *>(strtoull(tr, nullptr, 0));   // debugging: device pointer
@@ -157,14 +180,15 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     }
     // ---- Q4_0 / Q4_1 batched nodes: one activation launch + one persistent grouped GEMM launch per <= 64 nodes.  The GEMM
     //      triggers its dependents at start-up, so the next group's activation staging overlaps it (ggb_gemm_grouped.cu) ----
-    for (int qi = 0; qi < 3; qi++) {
+    for (int qi = 0; qi < 4; qi++) {
         const std::vector<int> &qn = q_nodes[qi];
         for (size_t c0 = 0; c0 < qn.size(); c0 += GGB_GEMM_GROUP_NODES) {
             const int cnt = (int)std::min(qn.size() - c0, (size_t)GGB_GEMM_GROUP_NODES);
             static thread_local ActGemmBatch ab;
             static thread_local GemmArgs ga[GGB_GEMM_GROUP_NODES];
-            const int type = qi == 0 ? GGML_TYPE_Q4_0 : qi == 1 ? GGML_TYPE_Q4_1 : GGML_TYPE_F16;
-            ab.n_nodes = cnt; ab.wtype = type; ab.perm = gemm_act_perm(type); ab.wait_prior = first_gemm ? 1 : 0;
+            const int type = qi == 0 ? GGML_TYPE_Q4_0 : qi == 1 ? GGML_TYPE_Q4_1 : GGML_TYPE_F16;      // slot 3: expanded siblings run the F16 kernel
+            // slot 3 stages activations as d*q (any quantized wtype selects that), in the F16 kernel's natural K order
+            ab.n_nodes = cnt; ab.wtype = qi == 3 ? GGML_TYPE_Q8_0 : type; ab.perm = gemm_act_perm(type); ab.wait_prior = first_gemm ? 1 : 0;
             for (int c = 0; c < cnt; c++) {
                 const int i = qn[c0 + c];
                 const ggb_dev_mm &m = mm[i];
@@ -173,11 +197,12 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
                 ab.node[c] = ActGemmNode{m.X, (long long)m.ldx_bytes, xh, (int)m.N, (int)Npad, (int)m.K, 0};
                 GemmArgs &a = ga[c];
                 a = GemmArgs{};
-                a.type = m.type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
+                a.type = type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
                 a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
                 for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
+                if (qi == 3) { int rce = expand(i, a.W, a.nb01); if (rce) return rce; }
             }
-            int rc = launch_act_f16_dequant_batch(ab, s);
+            int rc = launch_act_f16_dequant_batch(ab, s, qi != 3);
             if (rc) return rc;
             first_gemm = false;
             { KernelTimer kt(s); rc = launch_gemm_grouped(ga, cnt, s); }
@@ -209,7 +234,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         }
         const int type = mm[i0].type; const int64_t K = mm[i0].K;
         const size_t arow = act_row_bytes(type, K);
-        const bool quant = type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1;
+        const bool quant = is_q_weight(type);
         // activation staging (INIT phase)
         for (size_t c0 = 0; c0 < grp.size(); c0 += GGB_MAX_BATCH_NODES) {
             static thread_local ActBatch ab;
@@ -373,8 +398,8 @@ static int validate_mul_mat(const ggml_tensor *dst)
     if (!a || !b) return set_error(GGB_E_INVALID, "MUL_MAT node without src0/src1");
     if (dst->op != GGML_OP_MUL_MAT) return set_error(GGB_E_INVALID, "node op %d is not GGML_OP_MUL_MAT", dst->op);
     if (b->type != GGML_TYPE_F32 || dst->type != GGML_TYPE_F32) return set_error(GGB_E_INVALID, "mul_mat: src1 and dst must be F32 (Ggml.cs:3379-3382)");
-    if (a->type != GGML_TYPE_F32 && a->type != GGML_TYPE_F16 && a->type != GGML_TYPE_Q4_0 && a->type != GGML_TYPE_Q4_1)
-        return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is outside this backend's path (F32, F16, Q4_0, Q4_1)", a->type);
+    if (!is_mm_weight(a->type))
+        return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d has no vec_dot in quantize_fns[] (Ggml.cs:219-282)", a->type);
     if (a->ne[0] != b->ne[0] || a->ne[2] != b->ne[2] || a->ne[3] != b->ne[3]) return set_error(GGB_E_INVALID, "mul_mat: ggml_can_mul_mat fails (Ggml.cs:8345-8353)");
     if (dst->ne[0] != a->ne[1] || dst->ne[1] != b->ne[1] || dst->ne[2] != a->ne[2] || dst->ne[3] != a->ne[3])
         return set_error(GGB_E_INVALID, "mul_mat: dst shape does not match (Ggml.cs:6031-6034)");
@@ -382,7 +407,7 @@ static int validate_mul_mat(const ggml_tensor *dst)
     if (b->nb[0] != 4) return set_error(GGB_E_INVALID, "mul_mat: permuted src1 (nb10 != 4, Ggml.cs:6023/6388/6493)");
     if (dst->nb[0] != 4 || dst->nb[0] > dst->nb[1] || dst->nb[1] > dst->nb[2] || dst->nb[2] > dst->nb[3])
         return set_error(GGB_E_INVALID, "mul_mat: transposed or permuted dst (Ggml.cs:6026-6029)");
-    if (a->ne[0] % blck_size(a->type)) return set_error(GGB_E_INVALID, "mul_mat: ne00 %% 32 != 0 (Ggml.cs:6694)");
+    if (a->ne[0] % blck_size(a->type) || (is_q_weight(a->type) && a->ne[0] % GGB_QK)) return set_error(GGB_E_INVALID, "mul_mat: ne00 %% 32 != 0 (Ggml.cs:6694, 1209)");
     if (!dst_contiguous(dst)) return set_error(GGB_E_UNSUPPORTED, "mul_mat: dst must be contiguous (as ggml_mul_mat always creates it, Ggml.cs:8237-8238)");
     if (!a->data || !b->data || !dst->data) return set_error(GGB_E_INVALID, "mul_mat: tensor without data (no_alloc context?)");
     return GGB_OK;
@@ -393,12 +418,12 @@ static int validate_cpy(const ggml_tensor *node)
     const ggml_tensor *a = node->src0, *b = node->src1;
     if (!a || !b || !a->data || !b->data) return set_error(GGB_E_INVALID, "CPY node without operands/data");
     if (a->type != GGML_TYPE_F32) return set_error(GGB_E_UNSUPPORTED, "cpy: only F32 sources are on this path");
-    if (b->type != GGML_TYPE_Q4_0 && b->type != GGML_TYPE_Q4_1 && b->type != GGML_TYPE_F16)
-        return set_error(GGB_E_UNSUPPORTED, "cpy: destination type %d is not on this path (F16, Q4_0, Q4_1)", b->type);
+    if (!is_q_weight(b->type) && b->type != GGML_TYPE_F16)
+        return set_error(GGB_E_UNSUPPORTED, "cpy: destination type %d is not on this path (F16 and the quantized weight types)", b->type);
     if (nelements(a) != nelements(b)) return set_error(GGB_E_INVALID, "cpy: element counts differ (Ggml.cs:8281)");
     if (!is_contiguous(a)) return set_error(GGB_E_UNSUPPORTED, "cpy: non-contiguous source");
     if (!is_contiguous(b)) return set_error(GGB_E_UNSUPPORTED, "cpy: non-contiguous destination");
-    if (a->ne[0] % blck_size(b->type) || a->ne[0] != b->ne[0]) return set_error(GGB_E_UNSUPPORTED, "cpy: rows must map one to one (ne00 == ne0, %% 32)");
+    if (a->ne[0] % blck_size(b->type) || (is_q_weight(b->type) && a->ne[0] % GGB_QK) || a->ne[0] != b->ne[0]) return set_error(GGB_E_UNSUPPORTED, "cpy: rows must map one to one (ne00 == ne0, %% 32)");
     return GGB_OK;
 }
 
@@ -411,7 +436,7 @@ static int validate_neighbour(const ggml_tensor *t)
     case GGML_OP_ADD:
         if (!b || !b->data) return set_error(GGB_E_INVALID, "add: no src1");
         if (!same_shape(a, b) || !same_shape(a, t)) return set_error(GGB_E_INVALID, "add: shapes differ (Ggml.cs:4628, 4803)");
-        if (a->type == GGML_TYPE_Q4_0 || a->type == GGML_TYPE_Q4_1) {                  // add_q_f32
+        if (is_q_weight(a->type)) {                                                    // add_q_f32
             if (b->type != GGML_TYPE_F32 || t->type != a->type) return set_error(GGB_E_INVALID, "add_q_f32: src1 must be F32 and dst of src0's type (Ggml.cs:4862-4864)");
             if (a->ne[0] % GGB_QK) return set_error(GGB_E_INVALID, "add_q_f32: ne00 %% 32 != 0 (Ggml.cs:4891)");
             if (!is_contiguous(a) || !is_contiguous(b) || !is_contiguous(t)) return set_error(GGB_E_UNSUPPORTED, "add_q_f32: contiguous tensors only");

@@ -325,8 +325,10 @@ void ggml_graph_compute(ggml_context *ctx, ggml_cgraph *g)
             uint64_t cur = 0;
             const int t0 = node->src0->type;
             if (t0 == GGML_TYPE_F16) cur = TSIZE[GGML_TYPE_F16] * (uint64_t)ggml_nelements(node->src1);
-            else if (t0 == GGML_TYPE_Q4_0) cur = TSIZE[GGML_TYPE_Q8_0] * (uint64_t)ggml_nelements(node->src1) / 32;   // vec_dot_type, defect D1 repaired
-            else if (t0 == GGML_TYPE_Q4_1) cur = TSIZE[GGML_TYPE_Q8_1] * (uint64_t)ggml_nelements(node->src1) / 32;
+            // vec_dot_type of quantize_fns[] looked up by type (defect D1 repaired): Ggml.cs:226, 235, 244, 254, 263, 272
+            else if (t0 == GGML_TYPE_Q4_0 || t0 == GGML_TYPE_Q4_2 || t0 == GGML_TYPE_Q5_0 || t0 == GGML_TYPE_Q8_0)
+                cur = TSIZE[GGML_TYPE_Q8_0] * (uint64_t)ggml_nelements(node->src1) / 32;
+            else if (t0 == GGML_TYPE_Q4_1 || t0 == GGML_TYPE_Q5_1) cur = TSIZE[GGML_TYPE_Q8_1] * (uint64_t)ggml_nelements(node->src1) / 32;
             if (cur > work_size) work_size = cur;
         } else if (node->op == GGML_OP_CPY) {
             node->n_tasks = n_threads;                           // Ggml.cs:3266-3286

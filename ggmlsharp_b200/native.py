@@ -6,14 +6,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIBDIR = os.path.join(HERE, "lib")
 
 GGML_MAX_DIMS, GGML_MAX_NODES, GGML_MAX_OPT = 4, 4096, 4
-F32, F16, Q4_0, Q4_1, Q8_0, Q8_1, I8, I16, I32 = 0, 1, 2, 3, 8, 9, 10, 11, 12
+F32, F16, Q4_0, Q4_1, Q4_2, Q5_0, Q5_1, Q8_0, Q8_1, I8, I16, I32 = 0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12
 OP_NONE, OP_MUL_MAT, OP_CPY = 0, 20, 22
 OP_DUP, OP_ADD, OP_MUL, OP_REPEAT, OP_SILU, OP_RMS_NORM, OP_SCALE, OP_CONT, OP_TRANSPOSE = 1, 2, 4, 10, 17, 19, 21, 23, 27
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_ABI, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 GRAPH_KEEP_ON_DEVICE, GRAPH_NO_WEIGHT_CACHE, GRAPH_MUL_MAT_ONLY = 1, 2, 4
 
-TYPE_SIZE = {F32: 4, F16: 2, Q4_0: 20, Q4_1: 24, Q8_0: 36, Q8_1: 44, I8: 1, I16: 2, I32: 4}
-BLCK_SIZE = {F32: 1, F16: 1, Q4_0: 32, Q4_1: 32, Q8_0: 32, Q8_1: 32, I8: 1, I16: 1, I32: 1}
+TYPE_SIZE = {F32: 4, F16: 2, Q4_0: 20, Q4_1: 24, Q4_2: 10, Q5_0: 22, Q5_1: 24, Q8_0: 36, Q8_1: 44, I8: 1, I16: 2, I32: 4}
+BLCK_SIZE = {F32: 1, F16: 1, Q4_0: 32, Q4_1: 32, Q4_2: 16, Q5_0: 32, Q5_1: 32, Q8_0: 32, Q8_1: 32, I8: 1, I16: 1, I32: 1}
 
 
 class GgbError(RuntimeError):

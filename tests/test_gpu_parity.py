@@ -108,7 +108,7 @@ def test_codec_edge_cases():
     x = np.zeros((1, 48), np.float32)
     out = np.zeros(64, np.uint8)
     assert L.ggb_quantize_rows(N.Q4_0, x.ctypes.data, out.ctypes.data, 1, 48) == N.E_INVALID  # k % 32 (Ggml.cs:336)
-    assert L.ggb_quantize_rows(N.Q4_2 if hasattr(N, "Q4_2") else 4, x.ctypes.data, out.ctypes.data, 1, 32) == N.E_UNSUPPORTED
+    assert L.ggb_quantize_rows(5, x.ctypes.data, out.ctypes.data, 1, 32) == N.E_UNSUPPORTED    # Q4_3: removed upstream, `default` table entry (Ggml.cs:247)
 
 
 # ---------------------------------------------------------------- mul_mat through the device-level C ABI
@@ -391,7 +391,7 @@ def test_error_behaviour_matches_reference_asserts():
     with ggml.Context(buf.nbytes, mem_buffer=buf) as c:
         pool = C.c_void_p()
         N.check(L.ggb_pool_adopt(buf.ctypes.data, buf.nbytes, C.byref(pool)))
-        w = c.new_tensor(N.Q8_0, 64, 4)                          # a type outside the path (Ggml.cs:6726 handles it, we do not)
+        w = c.new_tensor(N.Q8_1, 64, 4)                          # vec_dot_q = null in quantize_fns[] (Ggml.cs:274-282): no dot exists
         x = c.new_tensor(N.F32, 64)
         y = c.mul_mat(w, x)
         assert L.ggb_mul_mat_node(pool, y) == N.E_UNSUPPORTED
