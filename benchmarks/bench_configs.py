@@ -37,7 +37,7 @@ def main():
     sp = C.c_void_p(stream.cuda_stream)
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm, tf = float(pk.get("hbm_gbs", 6650.0)), float(pk.get("bf16_tflops", 1590.0))
-    TN = {N.F32: "f32", N.F16: "f16", N.Q4_0: "q4_0", N.Q4_1: "q4_1"}
+    TN = {N.F32: "f32", N.F16: "f16", N.Q4_0: "q4_0", N.Q4_1: "q4_1", N.Q4_2: "q4_2", N.Q5_0: "q5_0", N.Q5_1: "q5_1", N.Q8_0: "q8_0"}
 
     def make_w(t, M, K):
         rb = N.TYPE_SIZE[t] * (K // N.BLCK_SIZE[t])
@@ -144,6 +144,43 @@ def main():
                 del dst, back
             del src
             torch.cuda.empty_cache()
+    if want("siblings"):
+        # the sibling weight formats through the same kernels (GEMV rings > 2x L2, codecs, tensor-core batch)
+        for t in (N.Q4_2, N.Q5_0, N.Q5_1, N.Q8_0):
+            rb = 4096 // N.BLCK_SIZE[t] * N.TYPE_SIZE[t]
+            n_ring = (336 << 20) // (4096 * rb) + 1
+            run_nodes([(t, 4096, 4096)] * n_ring, 1, "sibling %s 4096x4096 GEMV, ring of %d" % (TN[t], n_ring), a.iters)
+            n2 = max(2, n_ring * 4096 // 11008 + 1)
+            run_nodes([(t, 11008, 4096)] * n2, 1, "sibling %s 11008x4096 (w1/w3) GEMV, ring of %d" % (TN[t], n2), a.iters)
+            run_nodes([(t, 4096, 11008)] * n2, 1, "sibling %s 4096x11008 (w2, K=11008) GEMV, ring of %d" % (TN[t], n2), a.iters)
+            run_nodes([(t, 4096, 4096)] * 8, 512, "sibling %s 4096x4096 . 4096x512, batch of 8 nodes (fp16 expansion + F16 GEMM)" % TN[t], max(4, a.iters // 4))
+            run_nodes([(t, 4096, 4096)], 512, "sibling %s 4096x4096 . 4096x512, isolated" % TN[t], a.iters)
+        rows = 11008
+        nsrc = 2
+        src = torch.randn((nsrc, rows, 4096), device=dev) * 0.02
+        back = torch.empty((nsrc, rows, 4096), device=dev)
+        for t in (N.Q4_2, N.Q5_0, N.Q5_1, N.Q8_0):
+            rb = 4096 // N.BLCK_SIZE[t] * N.TYPE_SIZE[t]
+            dst = torch.empty((nsrc, rows, rb), dtype=torch.uint8, device=dev)
+            it = [0]
+
+            def q():
+                N.check(L.ggb_dev_quantize_rows(t, src[it[0] % nsrc].data_ptr(), dst[it[0] % nsrc].data_ptr(), rows, 4096, sp))
+                it[0] += 1
+
+            def dq():
+                N.check(L.ggb_dev_dequantize_rows(t, dst[it[0] % nsrc].data_ptr(), back[it[0] % nsrc].data_ptr(), rows, 4096, sp))
+                it[0] += 1
+            by = rows * 4096 * 4 + rows * rb
+            ms = time_calls(q, a.iters)
+            print(json.dumps({"config": "quantize_row_%s over %dx4096 F32" % (TN[t], rows), "ms": ms, "GB/s": by / ms / 1e6,
+                              "frac_of_measured_hbm": by / ms / 1e6 / hbm}), flush=True)
+            ms = time_calls(dq, a.iters)
+            print(json.dumps({"config": "dequantize_row_%s over %dx4096" % (TN[t], rows), "ms": ms, "GB/s": by / ms / 1e6,
+                              "frac_of_measured_hbm": by / ms / 1e6 / hbm}), flush=True)
+            del dst
+        del src, back
+        torch.cuda.empty_cache()
     if want("cfg2"):
         for t in (N.Q4_1, N.F16):
             n_ring = 10 if t == N.Q4_1 else 4
