@@ -627,7 +627,8 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
         k_f32_to_f16_rows<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, ldx, (__half *)dst, nrows, k);
         count_launch(); GGB_CUDA(cudaGetLastError()); return GGB_OK;
     }
-    if (type == GGML_TYPE_Q4_2 || type == GGML_TYPE_Q5_0 || type == GGML_TYPE_Q5_1) return launch_quantize_rows_sib(type, src, ldx, dst, nrows, k, s);
+    if (is_sibling_q(type)) return launch_quantize_rows_sib(type, src, ldx, dst, nrows, k, s);       // Q4_2, Q5_0, Q5_1, Q8_0
+    if (reinterpret_cast<uintptr_t>(dst) & 3) return set_error(GGB_E_UNSUPPORTED, "quantize: destination must be 4-byte aligned");
     if (k % GGB_QK) return set_error(GGB_E_INVALID, "quantize: k=%lld is not a multiple of %d (Ggml.cs:336)", (long long)k, GGB_QK);
     if ((reinterpret_cast<uintptr_t>(src) & 15) || (ldx & 3))
         return set_error(GGB_E_UNSUPPORTED, "quantize: source rows must be 16-byte aligned");

@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 namespace ggb {
 
@@ -44,44 +45,150 @@ __global__ void __launch_bounds__(128) k_quantize_sib(const float *__restrict__ 
     }
 }
 
-// One thread per 16 output bytes: lane sub = t & 7 of a group expands elements 4*sub .. 4*sub+3, so a warp store is 512 contiguous bytes.
+// Same data movement as k_quantize_q4_tiles (ggb_codecs.cu): every WARP runs its own cp.async pipeline over tiles of 32 groups
+// = 4 KB of contiguous source (eight coalesced 16-byte-per-lane copies into shared rows padded to 144 B, three tiles in flight),
+// lane l quantizes group l from eight conflict-free LDS.128, and the 32 x G output bytes leave through a staging row as one
+// contiguous run of 4-byte lane-consecutive stores.  (The first version -- k_quantize_sib, one thread per group with direct
+// 128-bit loads that touch 32 different lines per instruction and 2-byte scattered stores -- reached 34-54 % of the copy peak.)
+constexpr int ST_WARPS = 4, ST_STAGES = 3, ST_ROW = 144;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(ST_WARPS * 32) k_quantize_sib_tiles(const float *__restrict__ x, long long ldx, uint8_t *__restrict__ y,
+                                                                      long long ngrp, int kb)
+{
+    constexpr int G = Sib<TYPE>::G, OSTAGE = (32 * G + 15) / 16 * 16;
+    extern __shared__ uint4 st_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *wbase = reinterpret_cast<uint8_t *>(st_smem) + (size_t)warp * (ST_STAGES * 32 * ST_ROW + OSTAGE);
+    const uint32_t in0 = (uint32_t)__cvta_generic_to_shared(wbase);
+    uint8_t *ostage = wbase + ST_STAGES * 32 * ST_ROW;
+    const long long ntiles = (ngrp + 31) >> 5;
+    const long long gw = (long long)blockIdx.x * ST_WARPS + warp, nw = (long long)gridDim.x * ST_WARPS;
+    const bool dense = ldx == (long long)kb * GGB_QK;
+    const int sub = lane & 7, q = lane >> 3;
+
+    auto src_of = [&](long long g) -> const float * {
+        if (dense) return x + g * GGB_QK;
+        const long long row = g / kb;
+        return x + row * ldx + (g - row * kb) * GGB_QK;
+    };
+    auto issue = [&](long long tile, int stage) {
+        if (tile < ntiles) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const long long g = tile * 32 + i * 4 + q;
+                if (g < ngrp) cp_async16(in0 + (uint32_t)(stage * 32 * ST_ROW + (i * 4 + q) * ST_ROW + sub * 16), src_of(g) + sub * 4);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");     // always commit so the group count stays uniform
+    };
+
+    issue(gw, 0);
+    issue(gw + nw, 1);
+    int stage = 0;
+    for (long long tile = gw; tile < ntiles; tile += nw) {
+        issue(tile + 2 * nw, stage == 0 ? 2 : stage - 1);       // the stage consumed in the previous iteration
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
+        if (tile * 32 + lane < ngrp) {
+            float e[32];
+            const uint4 *row = reinterpret_cast<const uint4 *>(wbase + stage * 32 * ST_ROW + lane * ST_ROW);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint4 v = row[i];
+                e[4 * i] = __uint_as_float(v.x); e[4 * i + 1] = __uint_as_float(v.y); e[4 * i + 2] = __uint_as_float(v.z); e[4 * i + 3] = __uint_as_float(v.w);
+            }
+            uint32_t o[G / 2];
+            quantize_group<TYPE>(e, o);
+            if (G % 4 == 0) {                                    // 20 / 24 / 36-byte groups are word aligned in the staging row
+                uint32_t *d = reinterpret_cast<uint32_t *>(ostage + lane * G);
+#pragma unroll
+                for (int i = 0; i < G / 4; i++) d[i] = o[2 * i] | (o[2 * i + 1] << 16);
+            } else {
+                unsigned short *d = reinterpret_cast<unsigned short *>(ostage + lane * G);
+#pragma unroll
+                for (int i = 0; i < G / 2; i++) d[i] = (unsigned short)o[i];
+            }
+        }
+        __syncwarp();
+        // nvalid groups x G bytes, contiguous in y (the tile base is a multiple of 32*G, so 4-byte aligned whenever y is)
+        const int nvalid = (int)(ngrp - tile * 32 < 32 ? ngrp - tile * 32 : 32), nbytes = nvalid * G;
+        uint8_t *yo = y + tile * 32 * G;
+#pragma unroll
+        for (int j = 0; j < (8 * G + 31) / 32; j++) {
+            const int wi = j * 32 + lane;
+            if (wi * 4 + 4 <= nbytes) reinterpret_cast<uint32_t *>(yo)[wi] = reinterpret_cast<const uint32_t *>(ostage)[wi];
+        }
+        if ((nbytes & 2) && lane == 0) reinterpret_cast<unsigned short *>(yo)[nbytes / 2 - 1] = reinterpret_cast<const unsigned short *>(ostage)[nbytes / 2 - 1];
+        __syncwarp();                                            // ostage and this input stage are free again
+        stage = stage == ST_STAGES - 1 ? 0 : stage + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// One thread per 16 output bytes: lane sub = t & 7 of a group expands elements 4*sub .. 4*sub+3, so a warp store is 512 contiguous
+// bytes; the small scale / qh / quant loads of four independent slices are all issued before any of them is used.
 template <int TYPE>
 __global__ void __launch_bounds__(256) k_dequantize_sib(const uint8_t *__restrict__ x, float *__restrict__ y, long long ngrp)
 {
-    constexpr int G = Sib<TYPE>::G;
+    constexpr int G = Sib<TYPE>::G, U = 4;
     const long long total = ngrp * 8;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int sub = (int)(t & 7);
-        const unsigned short *g = reinterpret_cast<const unsigned short *>(x + (t >> 3) * G);
-        float4 o;
-        if (TYPE == GGML_TYPE_Q4_2) {
-            const unsigned short *b = g + 5 * (sub >> 2);
-            const float d = h_val(__ldg(b));
-            const uint32_t q = __ldg(b + 1 + (sub & 3));
-            o.x = __fmul_rn((float)((int)(q & 15u) - 8), d); o.y = __fmul_rn((float)((int)((q >> 4) & 15u) - 8), d);
-            o.z = __fmul_rn((float)((int)((q >> 8) & 15u) - 8), d); o.w = __fmul_rn((float)((int)(q >> 12) - 8), d);
-        } else if (TYPE == GGML_TYPE_Q5_0 || TYPE == GGML_TYPE_Q5_1) {
-            constexpr int Q0 = TYPE == GGML_TYPE_Q5_0 ? 3 : 4;
-            const float d = h_val(__ldg(g));
-            const float m = TYPE == GGML_TYPE_Q5_1 ? h_val(__ldg(g + 1)) : 0.0f;
-            const uint32_t qh = ((uint32_t)__ldg(g + Q0 - 2) | ((uint32_t)__ldg(g + Q0 - 1) << 16)) >> (4 * sub);
-            const uint32_t q = __ldg(g + Q0 + sub);
-            const int n0 = (int)((q & 15u) | ((qh & 1u) << 4)), n1 = (int)(((q >> 4) & 15u) | (((qh >> 1) & 1u) << 4));
-            const int n2 = (int)(((q >> 8) & 15u) | (((qh >> 2) & 1u) << 4)), n3 = (int)((q >> 12) | (((qh >> 3) & 1u) << 4));
-            if (TYPE == GGML_TYPE_Q5_0) {
-                o.x = __fmul_rn((float)(n0 - 16), d); o.y = __fmul_rn((float)(n1 - 16), d);
-                o.z = __fmul_rn((float)(n2 - 16), d); o.w = __fmul_rn((float)(n3 - 16), d);
-            } else {                                             // product rounded, then sum rounded
-                o.x = __fadd_rn(__fmul_rn((float)n0, d), m); o.y = __fadd_rn(__fmul_rn((float)n1, d), m);
-                o.z = __fadd_rn(__fmul_rn((float)n2, d), m); o.w = __fadd_rn(__fmul_rn((float)n3, d), m);
+    for (long long base = (long long)blockIdx.x * (256 * U) + threadIdx.x; base < total; base += (long long)gridDim.x * (256 * U)) {
+        uint32_t dm[U], qh[U], q[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long t = base + u * 256;
+            dm[u] = 0; qh[u] = 0; q[u] = 0;
+            if (t >= total) continue;
+            const int sub = (int)(t & 7);
+            const unsigned short *g = reinterpret_cast<const unsigned short *>(x + (t >> 3) * G);
+            if (TYPE == GGML_TYPE_Q4_2) {
+                const unsigned short *b = g + 5 * (sub >> 2);
+                dm[u] = __ldg(b); q[u] = __ldg(b + 1 + (sub & 3));
+            } else if (TYPE == GGML_TYPE_Q5_0) {
+                dm[u] = __ldg(g); qh[u] = (uint32_t)__ldg(g + 1 + (sub >> 2)); q[u] = __ldg(g + 3 + sub);       // the half of qh this slice needs
+            } else if (TYPE == GGML_TYPE_Q5_1) {
+                dm[u] = (uint32_t)__ldg(g) | ((uint32_t)__ldg(g + 1) << 16); qh[u] = (uint32_t)__ldg(g + 2 + (sub >> 2)); q[u] = __ldg(g + 4 + sub);
+            } else {
+                dm[u] = (uint32_t)__ldg(g) | ((uint32_t)__ldg(g + 1) << 16);
+                q[u] = (uint32_t)__ldg(g + 2 + 2 * sub) | ((uint32_t)__ldg(g + 3 + 2 * sub) << 16);
             }
-        } else {
-            const float d = __uint_as_float((uint32_t)__ldg(g) | ((uint32_t)__ldg(g + 1) << 16));
-            const uint32_t q0 = __ldg(g + 2 + 2 * sub), q1 = __ldg(g + 3 + 2 * sub);
-            o.x = __fmul_rn((float)(int)(int8_t)(q0 & 0xFFu), d); o.y = __fmul_rn((float)(int)(int8_t)(q0 >> 8), d);
-            o.z = __fmul_rn((float)(int)(int8_t)(q1 & 0xFFu), d); o.w = __fmul_rn((float)(int)(int8_t)(q1 >> 8), d);
         }
-        reinterpret_cast<float4 *>(y)[t] = o;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long t = base + u * 256;
+            if (t >= total) continue;
+            const int sub = (int)(t & 7);
+            float4 o;
+            if (TYPE == GGML_TYPE_Q4_2) {
+                const float d = h_val(dm[u]);
+                o.x = __fmul_rn((float)((int)(q[u] & 15u) - 8), d); o.y = __fmul_rn((float)((int)((q[u] >> 4) & 15u) - 8), d);
+                o.z = __fmul_rn((float)((int)((q[u] >> 8) & 15u) - 8), d); o.w = __fmul_rn((float)((int)(q[u] >> 12) - 8), d);
+            } else if (TYPE == GGML_TYPE_Q5_0 || TYPE == GGML_TYPE_Q5_1) {
+                const float d = h_val(dm[u] & 0xFFFFu);
+                const uint32_t h = qh[u] >> (4 * (sub & 3));                    // bits of elements 4*sub .. 4*sub+3
+                const int n0 = (int)((q[u] & 15u) | ((h & 1u) << 4)), n1 = (int)(((q[u] >> 4) & 15u) | (((h >> 1) & 1u) << 4));
+                const int n2 = (int)(((q[u] >> 8) & 15u) | (((h >> 2) & 1u) << 4)), n3 = (int)((q[u] >> 12) | (((h >> 3) & 1u) << 4));
+                if (TYPE == GGML_TYPE_Q5_0) {
+                    o.x = __fmul_rn((float)(n0 - 16), d); o.y = __fmul_rn((float)(n1 - 16), d);
+                    o.z = __fmul_rn((float)(n2 - 16), d); o.w = __fmul_rn((float)(n3 - 16), d);
+                } else {                                         // product rounded, then sum rounded
+                    const float m = h_val(dm[u] >> 16);
+                    o.x = __fadd_rn(__fmul_rn((float)n0, d), m); o.y = __fadd_rn(__fmul_rn((float)n1, d), m);
+                    o.z = __fadd_rn(__fmul_rn((float)n2, d), m); o.w = __fadd_rn(__fmul_rn((float)n3, d), m);
+                }
+            } else {
+                const float d = __uint_as_float(dm[u]);
+                o.x = __fmul_rn((float)(int)(int8_t)(q[u] & 0xFFu), d); o.y = __fmul_rn((float)(int)(int8_t)((q[u] >> 8) & 0xFFu), d);
+                o.z = __fmul_rn((float)(int)(int8_t)((q[u] >> 16) & 0xFFu), d); o.w = __fmul_rn((float)(int)(int8_t)(q[u] >> 24), d);
+            }
+            reinterpret_cast<float4 *>(y)[t] = o;
+        }
     }
 }
 
@@ -167,12 +274,12 @@ __global__ void __launch_bounds__(256) k_expand_f16(const uint8_t *__restrict__ 
     asm volatile("griddepcontrol.wait;" ::: "memory");           // completion stays transitive along a PDL chain (see k_act_f16_dequant)
 }
 
-#define GGB_SIB_SWITCH(type, EXPR) \
+#define GGB_SIB_SWITCH(type, ...) \
     switch (type) { \
-    case GGML_TYPE_Q4_2: { constexpr int T = GGML_TYPE_Q4_2; EXPR; } break; \
-    case GGML_TYPE_Q5_0: { constexpr int T = GGML_TYPE_Q5_0; EXPR; } break; \
-    case GGML_TYPE_Q5_1: { constexpr int T = GGML_TYPE_Q5_1; EXPR; } break; \
-    case GGML_TYPE_Q8_0: { constexpr int T = GGML_TYPE_Q8_0; EXPR; } break; \
+    case GGML_TYPE_Q4_2: { constexpr int T = GGML_TYPE_Q4_2; __VA_ARGS__; } break; \
+    case GGML_TYPE_Q5_0: { constexpr int T = GGML_TYPE_Q5_0; __VA_ARGS__; } break; \
+    case GGML_TYPE_Q5_1: { constexpr int T = GGML_TYPE_Q5_1; __VA_ARGS__; } break; \
+    case GGML_TYPE_Q8_0: { constexpr int T = GGML_TYPE_Q8_0; __VA_ARGS__; } break; \
     default: return set_error(GGB_E_UNSUPPORTED, "type %d is not a sibling quantized format", type); }
 
 } // namespace
@@ -185,8 +292,20 @@ int launch_quantize_rows_sib(int type, const float *src, int64_t ldx, void *dst,
     if (reinterpret_cast<uintptr_t>(dst) & 1) return set_error(GGB_E_UNSUPPORTED, "quantize: destination must be 2-byte aligned");
     const int kb = (int)(k / GGB_QK);
     const long long ngrp = nrows * kb;
-    const unsigned grid = (unsigned)std::min<long long>((ngrp + 127) / 128, (long long)device_sm_count() * 16);
-    GGB_SIB_SWITCH(type, (k_quantize_sib<T><<<grid, 128, 0, s>>>(src, ldx, (uint8_t *)dst, ngrp, kb)));
+    static const bool simple = getenv("GGB200_QUANT_SIMPLE") != nullptr;     // testing: the one-thread-per-group kernel
+    if (!simple && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        const long long ntiles = (ngrp + 31) / 32;
+        const unsigned gridt = (unsigned)std::min<long long>((ntiles + ST_WARPS - 1) / ST_WARPS, (long long)device_sm_count() * 3);
+        GGB_SIB_SWITCH(type, {
+            constexpr size_t smem = (size_t)ST_WARPS * (ST_STAGES * 32 * ST_ROW + (32 * Sib<T>::G + 15) / 16 * 16);
+            static bool attr_set = false;
+            if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_quantize_sib_tiles<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            k_quantize_sib_tiles<T><<<gridt, ST_WARPS * 32, smem, s>>>(src, ldx, (uint8_t *)dst, ngrp, kb);
+        });
+    } else {
+        const unsigned grid = (unsigned)std::min<long long>((ngrp + 127) / 128, (long long)device_sm_count() * 16);
+        GGB_SIB_SWITCH(type, (k_quantize_sib<T><<<grid, 128, 0, s>>>(src, ldx, (uint8_t *)dst, ngrp, kb)));
+    }
     count_launch(); GGB_CUDA(cudaGetLastError());
     return GGB_OK;
 }
@@ -197,7 +316,7 @@ int launch_dequantize_rows_sib(int type, const void *src, float *dst, int64_t nr
     if (k % GGB_QK) return set_error(GGB_E_INVALID, "dequantize: k=%lld is not a multiple of %d", (long long)k, GGB_QK);
     if ((reinterpret_cast<uintptr_t>(src) & 1) || (reinterpret_cast<uintptr_t>(dst) & 15)) return set_error(GGB_E_UNSUPPORTED, "dequantize: unaligned operand");
     const long long ngrp = nrows * (k / GGB_QK);
-    const unsigned grid = (unsigned)std::min<long long>((ngrp * 8 + 255) / 256, (long long)device_sm_count() * 16);
+    const unsigned grid = (unsigned)std::min<long long>((ngrp * 8 + 1023) / 1024, (long long)device_sm_count() * 8);
     GGB_SIB_SWITCH(type, (k_dequantize_sib<T><<<grid, 256, 0, s>>>((const uint8_t *)src, dst, ngrp)));
     count_launch(); GGB_CUDA(cudaGetLastError());
     return GGB_OK;

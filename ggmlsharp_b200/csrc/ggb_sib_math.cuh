@@ -30,9 +30,43 @@ template <> struct Grp<GGML_TYPE_Q8_0> { static constexpr int G = 36; };
 
 // ---- .NET 8 / x64 cast semantics (cvttsd2si / cvttss2si): NaN and out-of-range give the "integer indefinite" value ----
 GGB_DI int cs_byte(float r) { return (r != r || fabsf(r) >= 2147483648.0f) ? 0 : (__float2int_rz(r) & 0xFF); }                              // (byte)double
-GGB_DI int rne_q4(float v) { const float r = rintf(v) + 8.0f; return (r != r) ? 0 : (r >= 15.0f ? 15 : cs_byte(r)); }                         // (byte)Math.Min(15, Math.Round(v) + 8)
+// Math.Round(v) (ties to even) for |v| < 2^22 without the quarter-rate FRND / F2I conversions: v + 1.5*2^23 rounds to the nearest
+// integer (RNE add) and leaves it in the low mantissa bits (the trick ggb_codecs.cu's Q4_0 fast path uses); anything larger,
+// infinite or NaN takes the literal path
+GGB_DI bool rne_small(float v, int &r)
+{
+    if (!(fabsf(v) < 4194304.0f)) return false;
+    r = (int)(__float_as_uint(__fadd_rn(v, 12582912.0f)) - 0x4B400000u);
+    return true;
+}
+GGB_DI int rne_q4(float v)                                                                                                                  // (byte)Math.Min(15, Math.Round(v) + 8)
+{
+    int r;
+    if (rne_small(v, r)) { r += 8; return r >= 15 ? 15 : (r & 0xFF); }
+    const float f = rintf(v) + 8.0f;
+    return (f != f) ? 0 : (f >= 15.0f ? 15 : cs_byte(f));
+}
+GGB_DI int rne_byte(float v) { int r; return rne_small(v, r) ? (r & 0xFF) : cs_byte(rintf(v)); }                                              // (byte)Math.Round(v)
 GGB_DI int cs_int_f(float t) { return (t != t || fabsf(t) >= 2147483648.0f) ? INT_MIN : __float2int_rz(t); }                                 // (int)float
 GGB_DI uint32_t cs_uint_f(float t) { return (t != t || fabsf(t) >= 9223372036854775808.0f) ? 0u : (uint32_t)(unsigned long long)__float2ll_rz(t); }   // (uint)float
+
+// `if (amax < |v|) { amax = |v|; max = v; }` over n elements in order (Ggml.cs:343-354, 557-568, 616-627): the signed value of the
+// FIRST element of largest magnitude.  The order only matters when +a and -a are both present, so the common case is a
+// max / min tree (fmaxf / fminf skip NaN exactly like the strict < does) and the sequential scan is the fallback.
+template <int N_>
+GGB_DI float first_signed_absmax(const float *e)
+{
+    float smax = e[0], smin = e[0];
+#pragma unroll
+    for (int l = 1; l < N_; l++) { smax = fmaxf(smax, e[l]); smin = fminf(smin, e[l]); }
+    const float amax = fmaxf(smax, -smin);
+    const bool pos = smax == amax, neg = -smin == amax;
+    if (pos != neg) return pos ? amax : -amax;
+    float am = 0.0f, mx = 0.0f;                                // tie between signs, all zero, or NaN everywhere
+#pragma unroll
+    for (int l = 0; l < N_; l++) { const float av = fabsf(e[l]); if (am < av) { am = av; mx = e[l]; } }
+    return mx;
+}
 
 // ---- codecs: one group of 32 floats <-> Grp<TYPE>::G bytes held as 16-bit words o[] (groups are only 2-byte aligned) ----
 
@@ -42,9 +76,7 @@ GGB_DI void quantize_group(const float (&e)[32], uint32_t (&o)[Grp<TYPE>::G / 2]
     if (TYPE == GGML_TYPE_Q4_2) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            float amax = 0.0f, mx = 0.0f;                      // Ggml.cs:557-568: strict <, the first maximum wins
-#pragma unroll
-            for (int l = 0; l < 16; l++) { const float av = fabsf(e[16 * h + l]); if (amax < av) { amax = av; mx = e[16 * h + l]; } }
+            const float mx = first_signed_absmax<16>(e + 16 * h);     // Ggml.cs:557-568: strict <, the first maximum wins
             const float d = __fdiv_rn(mx, -8.0f);
             const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;    // from the unrounded d (Ggml.cs:575)
             o[5 * h] = h_bits(d);
@@ -60,9 +92,7 @@ GGB_DI void quantize_group(const float (&e)[32], uint32_t (&o)[Grp<TYPE>::G / 2]
             }
         }
     } else if (TYPE == GGML_TYPE_Q5_0) {
-        float amax = 0.0f, mx = 0.0f;                          // Ggml.cs:616-627
-#pragma unroll
-        for (int l = 0; l < 32; l++) { const float av = fabsf(e[l]); if (amax < av) { amax = av; mx = e[l]; } }
+        const float mx = first_signed_absmax<32>(e);           // Ggml.cs:616-627
         const float d = __fdiv_rn(mx, -16.0f);
         const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
         uint32_t qh = 0;
@@ -81,9 +111,16 @@ GGB_DI void quantize_group(const float (&e)[32], uint32_t (&o)[Grp<TYPE>::G / 2]
         }
         o[0] = h_bits(d); o[1] = qh & 0xFFFFu; o[2] = qh >> 16;
     } else if (TYPE == GGML_TYPE_Q5_1) {
-        float mn = 3.402823466e+38f, mx = -3.402823466e+38f;  // Ggml.cs:679-687: equal values keep the earlier element, NaN never wins
+        // Ggml.cs:679-687: `if (v < min) min = v; if (v > max) max = v;` from +-FLT_MAX -- equal values keep the earlier element
+        // (decides the sign of a zero min, which is stored), NaN never wins: a tree unless a zero or a NaN makes the order matter
+        float mn = e[0], mx = e[0];
 #pragma unroll
-        for (int l = 0; l < 32; l++) { if (e[l] < mn) mn = e[l]; if (e[l] > mx) mx = e[l]; }
+        for (int l = 1; l < 32; l++) { mn = fminf(mn, e[l]); mx = fmaxf(mx, e[l]); }
+        if (!(mn < mx) || mn == 0.0f || mx == 0.0f) {
+            mn = 3.402823466e+38f; mx = -3.402823466e+38f;
+#pragma unroll
+            for (int l = 0; l < 32; l++) { if (e[l] < mn) mn = e[l]; if (e[l] > mx) mx = e[l]; }
+        }
         const float d = __fdiv_rn(__fsub_rn(mx, mn), 31.0f);
         const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
         uint32_t qh = 0;
@@ -110,7 +147,7 @@ GGB_DI void quantize_group(const float (&e)[32], uint32_t (&o)[Grp<TYPE>::G / 2]
         o[0] = db & 0xFFFFu; o[1] = db >> 16;
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            const int q0 = cs_byte(rintf(__fmul_rn(e[2 * j], id))), q1 = cs_byte(rintf(__fmul_rn(e[2 * j + 1], id)));
+            const int q0 = rne_byte(__fmul_rn(e[2 * j], id)), q1 = rne_byte(__fmul_rn(e[2 * j + 1], id));
             o[2 + j] = (uint32_t)q0 | ((uint32_t)q1 << 8);
         }
     }

@@ -246,3 +246,24 @@ def test_sibling_add_q_f32(t, inplace):
     finally:
         d.close()
     assert np.array_equal(got, orc.add_q_f32(t, q, x))
+
+
+@pytest.mark.parametrize("t", SIB)
+def test_sibling_quantize_into_a_2_byte_aligned_destination(t):
+    """10- and 22-byte blocks make 2-byte aligned destinations legal (a row slice of a Q5_0 tensor); those take the
+    one-thread-per-group kernel instead of the tiled one, and must give the same bytes.  Also a ragged tile count."""
+    rng = np.random.default_rng(71)
+    R, K = 45, 96                                    # 135 groups: four full tiles + 7
+    x = _nasty(rng, R, K)
+    want = orc.quantize_rows(t, x)
+    d = Dev()
+    try:
+        px = d.put(x)
+        pd = d.empty(want.nbytes + 16)
+        for off in (0, 2):
+            N.check(N.lib().ggb_dev_quantize_rows(t, px, pd + off, R, K, None))
+            N.check(N.lib().ggb_stream_sync(None))
+            got = d.get(pd, (want.nbytes + 16,), np.uint8)[off:off + want.nbytes].reshape(want.shape)
+            assert np.array_equal(got, want), (NAME[t], off)
+    finally:
+        d.close()
