@@ -148,18 +148,19 @@ int  ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst);
 
 #define GGB_GRAPH_KEEP_ON_DEVICE 1   /* do not copy intermediate results back (only graph outputs) */
 #define GGB_GRAPH_NO_WEIGHT_CACHE 2  /* re-upload every src0 (what the CPU path observes if weights change) */
-#define GGB_GRAPH_MUL_MAT_ONLY 4     /* round-1 behaviour: run MUL_MAT and F32->{F16,Q4_0,Q4_1} CPY nodes only */
+#define GGB_GRAPH_MUL_MAT_ONLY 4     /* run MUL_MAT and F32 -> {F16, quantized} CPY nodes only */
 
 /* Called from ggml_graph_compute (Ggml.cs:3539) instead of walking MUL_MAT nodes one by one:
- * runs, in node order and on one stream with one final sync, every MUL_MAT node (and F32->
- * {F16,Q4_0,Q4_1} CPY node, the public route to quantize_row_q, Ggml.cs:4339-4363) whose inputs
+ * runs, in node order and on one stream with one final sync, every MUL_MAT node (and F32 ->
+ * {F16, Q4_0, Q4_1, Q4_2, Q5_0, Q5_1, Q8_0} CPY node, the public route to quantize_row_q,
+ * Ggml.cs:4339-4363) whose inputs
  * are leafs or nodes it runs itself.  done[i] (n_nodes bytes, may be NULL) is set to 1 for each
  * node it executed; the caller's loop runs the rest.  Returns the number executed or < 0. */
 int  ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *graph, int flags, uint8_t *done);
 /* Unless GGB_GRAPH_MUL_MAT_ONLY is set the same call also keeps the neighbours of mul_mat in a Llama layer on the device
  * (SURVEY.md 8f), so consecutive MUL_MATs need no host round trip: F32 ADD / MUL (Ggml.cs:4622-4685, 5007-5034), SILU
  * (5705-5747, fp16 table semantics of GGML_SILU_FP16), RMS_NORM (5858-5921), SCALE (6746-6780, in place on the view of src0),
- * ADD with Q4_0 / Q4_1 src0 (add_q_f32, 4797-4906), 2-D REPEAT (5340-5383) and CONT / DUP of a transposed or permuted F32 tensor (4199-4398; what
+ * ADD with a quantized src0 (add_q_f32, 4797-4906; Q4_0, Q4_1, Q4_2, Q5_0, Q5_1, Q8_0), 2-D REPEAT (5340-5383) and CONT / DUP of a transposed or permuted F32 tensor (4199-4398; what
  * MUL_MAT's backward issues, 7453-7462).  RESHAPE / VIEW / PERMUTE / TRANSPOSE nodes are no-ops in the reference
  * (8668-8687) and are marked done.  An element-wise node is taken only when at least one operand is produced on the device
  * by this call (otherwise uploading it would cost more than the C# loop); contiguous tensors only. */
@@ -169,7 +170,12 @@ int  ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *graph, int flags, u
 /* quantize_row_q / dequantize_row_q over nrows rows of k elements; src and dst may each be a
  * host or a device pointer.  Bit-exact with quantize_row_q4_0_reference_impl (Ggml.cs:334-377),
  * quantize_row_q4_1_reference_impl (487-528), quantize_row_q8_0/q8_1 (733-823, defects D2-D4
- * repaired) and the scalar dequantize_row_q4_0/q4_1 (884-911, 961-987).  F16 = (Half) cast. */
+ * repaired) and the scalar dequantize_row_q4_0/q4_1 (884-911, 961-987).  F16 = (Half) cast.
+ * The sibling formats of the same table: quantize_row_q4_2/q5_0/q5_1_reference_impl
+ * (547-590, 609-653, 672-714) and dequantize_row_q4_2/q5_0/q5_1/q8_0 (992-1122), with fp16 block
+ * scales as IEEE bit patterns (the reference's numeric `(ushort)(Half)d` cast is a defect, see
+ * oracle/ggb_oracle.c D9); k must be a multiple of 32 for every quantized type.  Q8_1 has no
+ * dequantizer and Q4_3 no entry at all in the reference's table: GGB_E_UNSUPPORTED. */
 int  ggb_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k);
 int  ggb_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k);
 
@@ -177,7 +183,9 @@ int  ggb_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, i
 
 /* One mul_mat on device pointers: dst[n][m] = sum_k W[m][k] * X[n][k]  (m < M, n < N).
  * W: M rows of K elements of `type`, row stride nb01 bytes.  X, Y: float32, row strides in
- * bytes.  A rank of a row-split passes its slice of W with Y offset to its column block. */
+ * bytes.  A rank of a row-split passes its slice of W with Y offset to its column block.
+ * type: F32, F16, Q4_0, Q4_1 (the north-star path) and Q4_2, Q5_0, Q5_1, Q8_0 (every other type
+ * whose quantize_fns[] row has a vec_dot_q, Ggml.cs:219-282); Q4_3 / Q8_1 weights: GGB_E_UNSUPPORTED. */
 typedef struct ggb_dev_mm {
     int32_t  type;
     int32_t  n_peers;              /* 0, or number of extra destinations in Y_peer (fused row-split epilogue) */
@@ -199,7 +207,7 @@ int  ggb_dev_dequantize_rows(int type, const void *src, float *dst, int64_t nrow
 
 /* The same neighbours on device pointers (no sync).  op is GGML_OP_ADD or GGML_OP_MUL; n counts floats; rms_norm / repeat row
  * strides are in floats (repeat: dst[r][c] = src[r % nr0][c % nc0]); ggb_dev_cont copies the strided F32 view (ne, nb in bytes: the fields of a transposed / permuted ggml_tensor) into a
- * contiguous dst; ggb_dev_add_q is add_q_f32 over nrows contiguous rows of k elements (type Q4_0 or Q4_1), dst may alias src0. */
+ * contiguous dst; ggb_dev_add_q is add_q_f32 over nrows contiguous rows of k elements (any quantized weight type), dst may alias src0. */
 int  ggb_dev_binary(int op, const float *a, const float *b, float *dst, int64_t n, void *stream);
 int  ggb_dev_scale(float *x, float v, int64_t n, void *stream);
 int  ggb_dev_silu(const float *x, float *dst, int64_t n, void *stream);
