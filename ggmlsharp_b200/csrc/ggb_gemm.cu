@@ -217,7 +217,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
          float *__restrict__ Y, long long ldy, int M, int N, int K, long long *__restrict__ dbg, int dbg_flags,
          const __grid_constant__ GemmPeers peers)
 {
-    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int RAW_ROW = RawRow<TYPE>::BYTES;
     constexpr int RAW_BYTES = BM * RAW_ROW;
     constexpr int BNL = BN / CG;
     constexpr int B_BYTES = BNL * BK * 2;
@@ -363,14 +363,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                     uint32_t v[32];
 #pragma unroll
                     for (int jb = 0; jb < 2; jb++) {
-                        const int j = hb * 2 + jb;
-                        __half2 d2, m2 = __float2half2_rn(0.0f);
-                        const uint32_t *wb = TYPE == GGML_TYPE_Q4_0 ? &w[5 * j] : &w[6 * j];
-                        d2 = __float2half2_rn(__uint_as_float(wb[0]));
-                        if (TYPE == GGML_TYPE_Q4_1) m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(wb[0]), __uint_as_float(wb[1])));   // m + 8d, see dequant_block
-                        const uint32_t *qw = TYPE == GGML_TYPE_Q4_0 ? wb + 1 : wb + 2;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) dequant_word<TYPE>(qw[i], d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16 + i * 4]);
+                        dequant_group<TYPE>(w, hb * 2 + jb, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16]);
                     }
                     tmem_st_x32(a_tmem + (uint32_t)(hb * 32), v);
                 }
@@ -509,10 +502,10 @@ int launch_f16(const GemmArgs &a, cudaStream_t s)
 template <int TYPE, int BN, int CG>
 int launch_q(const GemmArgs &a, cudaStream_t s)
 {
-    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int RAW_ROW = RawRow<TYPE>::BYTES;
     constexpr int BNL = BN / CG;
     CUtensorMap mw, mx;
-    const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * (TYPE == GGML_TYPE_Q4_0 ? 20 : 24);
+    const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * q32_bytes(TYPE);
     int rc = make_map_2d(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, row_bytes, (uint64_t)a.M, (uint64_t)a.nb01, RAW_ROW, BM, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
     rc = make_map_2d(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, BNL, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -547,7 +540,8 @@ int launch_q(const GemmArgs &a, cudaStream_t s)
 
 bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W)
 {
-    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1 && type != GGML_TYPE_F16) return false;     // F32 weights stay on FFMA (1e-5 bar)
+    // F32 weights stay on FFMA (1e-5 bar); Q5_0 (88-byte K steps: not a legal TMA box) and Q8_0 go through an fp16 expansion (ggb_shim.cu)
+    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1 && type != GGML_TYPE_Q4_2 && type != GGML_TYPE_Q5_1 && type != GGML_TYPE_F16) return false;
     if (M <= 0 || N < 16 || K <= 0 || K % GGB_QK) return false;
     if ((reinterpret_cast<uintptr_t>(W) & 15) || (nb01 & 15)) return false;                            // TMA: 16-byte base and strides
     if (type == GGML_TYPE_F16) return K % 8 == 0;
@@ -571,6 +565,8 @@ int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s)
     switch (a.type) {
     case GGML_TYPE_Q4_0: return cg == 1 ? launch_q<GGML_TYPE_Q4_0, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_0, 128, 2>(a, s);
     case GGML_TYPE_Q4_1: return cg == 1 ? launch_q<GGML_TYPE_Q4_1, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_1, 128, 2>(a, s);
+    case GGML_TYPE_Q4_2: return launch_q<GGML_TYPE_Q4_2, 128, 2>(a, s);
+    case GGML_TYPE_Q5_1: return launch_q<GGML_TYPE_Q5_1, 128, 2>(a, s);
     case GGML_TYPE_F16: return cg == 1 ? launch_f16<128, 1>(a, s) : launch_f16<128, 2>(a, s);
     default: return set_error(GGB_E_UNSUPPORTED, "batched path: type %d", a.type);
     }

@@ -45,7 +45,7 @@ template <int TYPE, int CAP>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_constant__ GemmGroupT<CAP> G)
 {
     constexpr int BN = 128, BNL = 64;
-    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int RAW_ROW = RawRow<TYPE>::BYTES;
     constexpr int RAW_BYTES = BM * RAW_ROW, B_BYTES = BNL * BK * 2;
     constexpr int RAW_STAGES = 8, A_STAGES = 4;               // raw ring: a multiple of the 4 dequant groups (see ggb_gemm.cu)
     constexpr int TMEM_COLS = 512, A_COL0 = 2 * BN;           // [0,128) even-K acc, [128,256) odd-K acc, then 4 x 64 columns of A stages
@@ -182,14 +182,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                     uint32_t v[32];
 #pragma unroll
                     for (int jb = 0; jb < 2; jb++) {
-                        const int j = hb * 2 + jb;
-                        __half2 d2, m2 = __float2half2_rn(0.0f);
-                        const uint32_t *wb = TYPE == GGML_TYPE_Q4_0 ? &w[5 * j] : &w[6 * j];
-                        d2 = __float2half2_rn(__uint_as_float(wb[0]));
-                        if (TYPE == GGML_TYPE_Q4_1) m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(wb[0]), __uint_as_float(wb[1])));   // m + 8d
-                        const uint32_t *qw = TYPE == GGML_TYPE_Q4_0 ? wb + 1 : wb + 2;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) dequant_word<TYPE>(qw[i], d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16 + i * 4]);
+                        dequant_group<TYPE>(w, hb * 2 + jb, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16]);
                     }
                     if (hb == 0) {
                         // the nibble expansion of the first half ran ahead of this wait: only the TMEM store needs the stage free
@@ -413,7 +406,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_c
 template <int TYPE, int CAP>
 int launch_grouped(const GemmGroupT<CAP> &G, cudaStream_t s)
 {
-    constexpr int RAW_ROW = TYPE == GGML_TYPE_Q4_0 ? 80 : 96;
+    constexpr int RAW_ROW = RawRow<TYPE>::BYTES;
     constexpr size_t smem = TYPE == GGML_TYPE_F16 ? 1024 + (size_t)4 * (BM * BK * 2) + (size_t)4 * (64 * BK * 2) + 64 * 8 + 16
                                                   : 1024 + (size_t)4 * (64 * BK * 2) + (size_t)8 * (BM * RAW_ROW) + 64 * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
@@ -453,7 +446,7 @@ int launch_grouped(const GemmGroupT<CAP> &G, cudaStream_t s)
 
 } // namespace
 
-bool gemm_grouped_supported(int type) { return type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1 || type == GGML_TYPE_F16; }
+bool gemm_grouped_supported(int type) { return type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1 || type == GGML_TYPE_Q4_2 || type == GGML_TYPE_Q5_1 || type == GGML_TYPE_F16; }
 
 int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
 {
@@ -471,8 +464,8 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
         if (type == GGML_TYPE_F16) {
             rc = make_map_2d(&nd.map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.W, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.nb01, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
         } else {
-            const int raw_row = type == GGML_TYPE_Q4_0 ? 80 : 96;
-            const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * (type == GGML_TYPE_Q4_0 ? 20 : 24);
+            const int raw_row = (type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_2) ? 80 : 96;
+            const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * q32_bytes(type);
             rc = make_map_2d(&nd.map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, row_bytes, (uint64_t)a.M, (uint64_t)a.nb01, (uint32_t)raw_row, BM, CU_TENSOR_MAP_SWIZZLE_NONE);
         }
         if (rc) return rc;
@@ -492,10 +485,20 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
         S.n_nodes = G.n_nodes; S.total_tiles = G.total_tiles;
         for (int i = 0; i < count; i++) S.node[i] = G.node[i];
         if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16, SMALL_GROUP>(S, s);
-        return type == GGML_TYPE_Q4_0 ? launch_grouped<GGML_TYPE_Q4_0, SMALL_GROUP>(S, s) : launch_grouped<GGML_TYPE_Q4_1, SMALL_GROUP>(S, s);
+        switch (type) {
+        case GGML_TYPE_Q4_0: return launch_grouped<GGML_TYPE_Q4_0, SMALL_GROUP>(S, s);
+        case GGML_TYPE_Q4_1: return launch_grouped<GGML_TYPE_Q4_1, SMALL_GROUP>(S, s);
+        case GGML_TYPE_Q4_2: return launch_grouped<GGML_TYPE_Q4_2, SMALL_GROUP>(S, s);
+        default: return launch_grouped<GGML_TYPE_Q5_1, SMALL_GROUP>(S, s);
+        }
     }
     if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16, GGB_GEMM_GROUP_NODES>(G, s);
-    return type == GGML_TYPE_Q4_0 ? launch_grouped<GGML_TYPE_Q4_0, GGB_GEMM_GROUP_NODES>(G, s) : launch_grouped<GGML_TYPE_Q4_1, GGB_GEMM_GROUP_NODES>(G, s);
+    switch (type) {
+    case GGML_TYPE_Q4_0: return launch_grouped<GGML_TYPE_Q4_0, GGB_GEMM_GROUP_NODES>(G, s);
+    case GGML_TYPE_Q4_1: return launch_grouped<GGML_TYPE_Q4_1, GGB_GEMM_GROUP_NODES>(G, s);
+    case GGML_TYPE_Q4_2: return launch_grouped<GGML_TYPE_Q4_2, GGB_GEMM_GROUP_NODES>(G, s);
+    default: return launch_grouped<GGML_TYPE_Q5_1, GGB_GEMM_GROUP_NODES>(G, s);
+    }
 }
 
 } // namespace ggb

@@ -82,11 +82,14 @@ static bool is_device_ptr(const void *p)
 // device-level batch: plan + launch
 // ------------------------------------------------------------------------------------------------
 
-// Sibling formats (Q4_2 / Q5_0 / Q5_1 / Q8_0) on the batched path: the weights are expanded to dense fp16 [M][K] in the workspace
-// (k_expand_f16) and the F16 tcgen05 GEMM multiplies that, against activations staged as d*q like every quantized type.
+// Sibling formats on the batched path.  Q4_2 and Q5_1 have the K-step footprint of Q4_0 / Q4_1 (80 / 96 bytes per 128 weights),
+// so the tcgen05 kernels dequantize them in flight like those.  Q5_0 (88 bytes: not a legal TMA box) and Q8_0 -- and Q4_2 / Q5_1
+// shapes the TMA path cannot take (K not a multiple of 128, unaligned rows) -- are expanded to dense fp16 [M][K] in the workspace
+// (k_expand_f16) and the F16 kernel multiplies that, against activations staged as d*q like every quantized type.
 static inline bool use_gemm_expanded(const ggb_dev_mm &m)
 {
-    return is_sibling_q(m.type) && m.N >= 16 && m.M > 0 && m.K % GGB_QK == 0 && ((reinterpret_cast<uintptr_t>(m.W) | (uintptr_t)m.nb01) & 1) == 0;
+    return is_sibling_q(m.type) && m.N >= 16 && m.M > 0 && m.K % GGB_QK == 0 && ((reinterpret_cast<uintptr_t>(m.W) | (uintptr_t)m.nb01) & 1) == 0 &&
+           !gemm_supported(m.type, m.M, m.K, m.N, m.nb01, m.W);
 }
 static inline bool use_gemm(const ggb_dev_mm &m)
 {
@@ -102,7 +105,7 @@ static size_t mm_ws_bytes(const ggb_dev_mm &m)
 // upper bound that does not depend on operand addresses (for sizing before buffers exist)
 static size_t mm_ws_bytes_bound(int type, int64_t M, int64_t K, int64_t N)
 {
-    const size_t tc = align_up(gemm_workspace_bytes(type, M, K, N), 256) + (is_sibling_q(type) && N >= 16 ? expanded_bytes(M, K) : 0);
+    const size_t tc = align_up(gemm_workspace_bytes(type, M, K, N), 256) + (is_sibling_q(type) && N >= 16 ? expanded_bytes(M, K) : 0);   // alignment unknown yet: assume the expansion
     return std::max(tc, align_up((size_t)N * act_row_bytes(type, K), 256));
 }
 
@@ -141,8 +144,13 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     std::vector<int> gemv_idx;
     bool first_gemm = true;
     static const bool grouped = [] { const char *e = getenv("GGB200_GEMM_GROUPED"); return !e || atoi(e) != 0; }();
-    std::vector<int> q_nodes[4];                                  // Q4_0 / Q4_1 / F16 / expanded-sibling nodes of this batch, for the grouped kernels
-    auto qslot = [](int type) { return type == GGML_TYPE_Q4_0 ? 0 : type == GGML_TYPE_Q4_1 ? 1 : type == GGML_TYPE_F16 ? 2 : 3; };
+    constexpr int NSLOT = 6;                                      // one grouped launch sequence per kernel flavour
+    static const int slot_type[NSLOT] = {GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, GGML_TYPE_F16, GGML_TYPE_F16 /* expanded siblings */, GGML_TYPE_Q4_2, GGML_TYPE_Q5_1};
+    std::vector<int> q_nodes[NSLOT];
+    auto qslot = [&](const ggb_dev_mm &m) {
+        if (use_gemm_expanded(m)) return 3;
+        switch (m.type) { case GGML_TYPE_Q4_0: return 0; case GGML_TYPE_Q4_1: return 1; case GGML_TYPE_Q4_2: return 4; case GGML_TYPE_Q5_1: return 5; default: return 2; }
+    };
     // a sibling-format node: expand the weights behind the activation buffer of its workspace slice and hand the GEMM an F16 node.
     // The expansion is an ordinary (fully stream-ordered) launch and the activation kernel that follows it is launched WITHOUT
     // programmatic serialization, so the GEMM -- whose weight TMA does not wait for anything -- cannot start before it is complete.
@@ -161,7 +169,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         // a lone node keeps the per-node kernel (smaller launch); two or more go through the persistent grouped kernels
         const bool sibx = use_gemm_expanded(m);
         const int gtype = sibx ? GGML_TYPE_F16 : m.type;          // what the tensor-core kernel sees
-        if (grouped && n_tc > 1 && !getenv("GGB200_GEMM_TRACE") && gemm_grouped_supported(gtype)) { q_nodes[qslot(m.type)].push_back(i); continue; }
+        if (grouped && n_tc > 1 && !getenv("GGB200_GEMM_TRACE") && gemm_grouped_supported(gtype)) { q_nodes[qslot(m)].push_back(i); continue; }
         const int64_t Npad = (m.N + 15) / 16 * 16;
         __half *xh = reinterpret_cast<__half *>(wsb + off[i]);
         const void *Wg = m.W; int64_t nb01g = m.nb01;
@@ -180,13 +188,13 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     }
     // ---- Q4_0 / Q4_1 batched nodes: one activation launch + one persistent grouped GEMM launch per <= 64 nodes.  The GEMM
     //      triggers its dependents at start-up, so the next group's activation staging overlaps it (ggb_gemm_grouped.cu) ----
-    for (int qi = 0; qi < 4; qi++) {
+    for (int qi = 0; qi < NSLOT; qi++) {
         const std::vector<int> &qn = q_nodes[qi];
         for (size_t c0 = 0; c0 < qn.size(); c0 += GGB_GEMM_GROUP_NODES) {
             const int cnt = (int)std::min(qn.size() - c0, (size_t)GGB_GEMM_GROUP_NODES);
             static thread_local ActGemmBatch ab;
             static thread_local GemmArgs ga[GGB_GEMM_GROUP_NODES];
-            const int type = qi == 0 ? GGML_TYPE_Q4_0 : qi == 1 ? GGML_TYPE_Q4_1 : GGML_TYPE_F16;      // slot 3: expanded siblings run the F16 kernel
+            const int type = slot_type[qi];                                                             // slot 3: expanded siblings run the F16 kernel
             // slot 3 stages activations as d*q (any quantized wtype selects that), in the F16 kernel's natural K order
             ab.n_nodes = cnt; ab.wtype = qi == 3 ? GGML_TYPE_Q8_0 : type; ab.perm = gemm_act_perm(type); ab.wait_prior = first_gemm ? 1 : 0;
             for (int c = 0; c < cnt; c++) {

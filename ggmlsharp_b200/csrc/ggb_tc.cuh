@@ -131,16 +131,30 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
                      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// 8 weights of one 32-bit nibble word -> 4 half2 in K order (0,4) (1,5) (2,6) (3,7), scaled: (q-8)*d [+ m']
+// bytes one K step (128 weights) of one weight row occupies in its reference layout = the TMA box width of the raw ring:
+// Q4_0 4 x 20, Q4_2 8 x 10; Q4_1 / Q5_1 4 x 24
+template <int TYPE> struct RawRow { static constexpr int BYTES = (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_2) ? 80 : 96; };
+
+// 8 weights of one 32-bit nibble word -> 4 half2 in K order (0,4) (1,5) (2,6) (3,7), scaled: (q-c)*d [+ m'], c = 8 (16 for Q5_1).
+// Q5_1: hb = the 8 fifth bits of these weights (qh >> 8*word); bit e belongs to element e and lands on the 16s place of its half:
+// bit 4 / 20 in the "1024 + n" halves (elements 0,4 / 2,6), bit 8 / 24 in the "64 + n" halves whose ulp is 1/16 (elements 1,5 / 3,7).
+// Each pair is moved by one multiply ((hb & 0x11) * (2^4 + 2^16) etc.: the cross terms fall outside the mask).
 template <int TYPE>
-__device__ __forceinline__ void dequant_word(uint32_t w, __half2 d2, __half2 m2, uint32_t mk_lo, uint32_t mk_hi, uint32_t mg_lo, uint32_t mg_hi, uint32_t *out)
+__device__ __forceinline__ void dequant_word(uint32_t w, uint32_t hb, __half2 d2, __half2 m2, uint32_t mk_lo, uint32_t mk_hi, uint32_t mg_lo, uint32_t mg_hi, uint32_t *out)
 {
-    const __half2 o_lo = __float2half2_rn(1032.0f), o_hi = __float2half2_rn(72.0f);     // 1024+8, 64+8
+    constexpr float C = TYPE == GGML_TYPE_Q5_1 ? 16.0f : 8.0f;
+    const __half2 o_lo = __float2half2_rn(1024.0f + C), o_hi = __float2half2_rn(64.0f + C);
     const uint32_t ws = w >> 8;
     uint32_t v0 = and_or(w, mk_lo, mg_lo), v1 = and_or(w, mk_hi, mg_hi), v2 = and_or(ws, mk_lo, mg_lo), v3 = and_or(ws, mk_hi, mg_hi);
+    if (TYPE == GGML_TYPE_Q5_1) {
+        v0 |= ((hb & 0x11u) * 0x00010010u) & 0x00100010u;
+        v1 |= ((hb & 0x22u) * 0x00080080u) & 0x01000100u;
+        v2 |= ((hb & 0x44u) * 0x00004004u) & 0x00100010u;
+        v3 |= ((hb & 0x88u) * 0x00020020u) & 0x01000100u;
+    }
     __half2 h0 = *reinterpret_cast<__half2 *>(&v0), h1 = *reinterpret_cast<__half2 *>(&v1);
     __half2 h2 = *reinterpret_cast<__half2 *>(&v2), h3 = *reinterpret_cast<__half2 *>(&v3);
-    if (TYPE == GGML_TYPE_Q4_0) {
+    if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_2) {
         h0 = __hmul2(__hsub2(h0, o_lo), d2); h1 = __hmul2(__hsub2(h1, o_hi), d2);
         h2 = __hmul2(__hsub2(h2, o_lo), d2); h3 = __hmul2(__hsub2(h3, o_hi), d2);
     } else {
@@ -149,6 +163,42 @@ __device__ __forceinline__ void dequant_word(uint32_t w, __half2 d2, __half2 m2,
     }
     out[0] = *reinterpret_cast<uint32_t *>(&h0); out[1] = *reinterpret_cast<uint32_t *>(&h1);
     out[2] = *reinterpret_cast<uint32_t *>(&h2); out[3] = *reinterpret_cast<uint32_t *>(&h3);
+}
+
+// Group j (32 weights) of the raw words w[] of one K step of one row -> 16 words of fp16 pairs.
+//   Q4_0  words 5j: [f32 d][qs x 4]                          (q-8)*d
+//   Q4_1  words 6j: [f32 d][f32 m][qs x 4]                   (q-8)*d + (m + 8d)      (recentred so the product stays small)
+//   Q4_2  words 5j: [h d0 | qs0 0-1][qs0 2-5][qs0 6-7 | h d1][qs1 0-3][qs1 4-7]      two 16-weight blocks, fp16 scales used as they are
+//   Q5_1  words 6j: [h d | h m][qh][qs x 4]                  (q5-16)*d + (m + 16d)
+template <int TYPE>
+__device__ __forceinline__ void dequant_group(const uint32_t *w, int j, uint32_t mk_lo, uint32_t mk_hi, uint32_t mg_lo, uint32_t mg_hi, uint32_t *out)
+{
+    if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_1) {
+        const uint32_t *wb = TYPE == GGML_TYPE_Q4_0 ? &w[5 * j] : &w[6 * j];
+        const __half2 d2 = __float2half2_rn(__uint_as_float(wb[0]));
+        __half2 m2 = __float2half2_rn(0.0f);
+        if (TYPE == GGML_TYPE_Q4_1) m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(wb[0]), __uint_as_float(wb[1])));
+        const uint32_t *qw = TYPE == GGML_TYPE_Q4_0 ? wb + 1 : wb + 2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) dequant_word<TYPE>(qw[i], 0u, d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, out + 4 * i);
+    } else if (TYPE == GGML_TYPE_Q4_2) {
+        const uint32_t *wb = &w[5 * j];
+        uint32_t da = (wb[0] & 0xFFFFu) * 0x00010001u, db = (wb[2] >> 16) * 0x00010001u;          // half2(d0, d0), half2(d1, d1)
+        const __half2 d2a = *reinterpret_cast<__half2 *>(&da), d2b = *reinterpret_cast<__half2 *>(&db), z = __float2half2_rn(0.0f);
+        dequant_word<TYPE>(__funnelshift_r(wb[0], wb[1], 16), 0u, d2a, z, mk_lo, mk_hi, mg_lo, mg_hi, out);
+        dequant_word<TYPE>(__funnelshift_r(wb[1], wb[2], 16), 0u, d2a, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 4);
+        dequant_word<TYPE>(wb[3], 0u, d2b, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 8);
+        dequant_word<TYPE>(wb[4], 0u, d2b, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 12);
+    } else {
+        const uint32_t *wb = &w[6 * j];
+        uint32_t dd = (wb[0] & 0xFFFFu) * 0x00010001u;
+        const __half2 d2 = *reinterpret_cast<__half2 *>(&dd);
+        const float df = __half2float(__ushort_as_half((unsigned short)(wb[0] & 0xFFFFu))), mf = __half2float(__ushort_as_half((unsigned short)(wb[0] >> 16)));
+        const __half2 m2 = __float2half2_rn(fmaf(16.0f, df, mf));
+        const uint32_t qh = wb[1];
+#pragma unroll
+        for (int i = 0; i < 4; i++) dequant_word<TYPE>(wb[2 + i], (qh >> (8 * i)) & 0xFFu, d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, out + 4 * i);
+    }
 }
 
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t *v)

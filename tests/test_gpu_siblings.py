@@ -152,9 +152,10 @@ def test_sibling_linearity_and_determinism_full_size(t):
 
 
 @pytest.mark.parametrize("t", SIB)
-@pytest.mark.parametrize("M,K,Nn", [(256, 512, 16), (4096, 4096, 512), (1000, 1024, 100), (384, 11008, 33)])
+@pytest.mark.parametrize("M,K,Nn", [(256, 512, 16), (4096, 4096, 512), (1000, 1024, 100), (384, 11008, 33), (200, 160, 24)])
 def test_sibling_batched_tensor_core_path(t, M, K, Nn):
-    """N >= 16: weights expanded to fp16 on the device, then the F16 tcgen05 GEMM."""
+    """N >= 16 on tcgen05: Q4_2 / Q5_1 dequantized in the kernel like Q4_0 / Q4_1 (K % 128 == 0); Q5_0 / Q8_0 -- and K = 160 for
+    every type -- through the fp16 expansion of the weights and the F16 kernel."""
     rng = np.random.default_rng(3000 + M + Nn)
     W = weights(rng, M, K)
     X = rng.standard_normal((Nn, K)).astype(np.float32)
