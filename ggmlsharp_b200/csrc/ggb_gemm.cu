@@ -540,8 +540,8 @@ int launch_q(const GemmArgs &a, cudaStream_t s)
 
 bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W)
 {
-    // F32 weights stay on FFMA (1e-5 bar); Q5_0 (88-byte K steps: not a legal TMA box) and Q8_0 go through an fp16 expansion (ggb_shim.cu)
-    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1 && type != GGML_TYPE_Q4_2 && type != GGML_TYPE_Q5_1 && type != GGML_TYPE_F16) return false;
+    // F32 weights stay on FFMA (1e-5 bar); Q5_0 (88-byte K steps: not a legal TMA box) goes through an fp16 expansion (ggb_shim.cu)
+    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1 && type != GGML_TYPE_Q4_2 && type != GGML_TYPE_Q5_1 && type != GGML_TYPE_Q8_0 && type != GGML_TYPE_F16) return false;
     if (M <= 0 || N < 16 || K <= 0 || K % GGB_QK) return false;
     if ((reinterpret_cast<uintptr_t>(W) & 15) || (nb01 & 15)) return false;                            // TMA: 16-byte base and strides
     if (type == GGML_TYPE_F16) return K % 8 == 0;
@@ -567,6 +567,7 @@ int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s)
     case GGML_TYPE_Q4_1: return cg == 1 ? launch_q<GGML_TYPE_Q4_1, 128, 1>(a, s) : launch_q<GGML_TYPE_Q4_1, 128, 2>(a, s);
     case GGML_TYPE_Q4_2: return launch_q<GGML_TYPE_Q4_2, 128, 2>(a, s);
     case GGML_TYPE_Q5_1: return launch_q<GGML_TYPE_Q5_1, 128, 2>(a, s);
+    case GGML_TYPE_Q8_0: return launch_q<GGML_TYPE_Q8_0, 128, 2>(a, s);
     case GGML_TYPE_F16: return cg == 1 ? launch_f16<128, 1>(a, s) : launch_f16<128, 2>(a, s);
     default: return set_error(GGB_E_UNSUPPORTED, "batched path: type %d", a.type);
     }

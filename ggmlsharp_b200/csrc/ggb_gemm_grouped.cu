@@ -446,7 +446,7 @@ int launch_grouped(const GemmGroupT<CAP> &G, cudaStream_t s)
 
 } // namespace
 
-bool gemm_grouped_supported(int type) { return type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1 || type == GGML_TYPE_Q4_2 || type == GGML_TYPE_Q5_1 || type == GGML_TYPE_F16; }
+bool gemm_grouped_supported(int type) { return type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1 || type == GGML_TYPE_Q4_2 || type == GGML_TYPE_Q5_1 || type == GGML_TYPE_Q8_0 || type == GGML_TYPE_F16; }
 
 int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
 {
@@ -464,7 +464,7 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
         if (type == GGML_TYPE_F16) {
             rc = make_map_2d(&nd.map_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.W, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.nb01, 64, BM, CU_TENSOR_MAP_SWIZZLE_128B);
         } else {
-            const int raw_row = (type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_2) ? 80 : 96;
+            const int raw_row = (type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_2) ? 80 : type == GGML_TYPE_Q8_0 ? 144 : 96;
             const uint64_t row_bytes = (uint64_t)(a.K / GGB_QK) * q32_bytes(type);
             rc = make_map_2d(&nd.map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, row_bytes, (uint64_t)a.M, (uint64_t)a.nb01, (uint32_t)raw_row, BM, CU_TENSOR_MAP_SWIZZLE_NONE);
         }
@@ -489,6 +489,7 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
         case GGML_TYPE_Q4_0: return launch_grouped<GGML_TYPE_Q4_0, SMALL_GROUP>(S, s);
         case GGML_TYPE_Q4_1: return launch_grouped<GGML_TYPE_Q4_1, SMALL_GROUP>(S, s);
         case GGML_TYPE_Q4_2: return launch_grouped<GGML_TYPE_Q4_2, SMALL_GROUP>(S, s);
+        case GGML_TYPE_Q8_0: return launch_grouped<GGML_TYPE_Q8_0, SMALL_GROUP>(S, s);
         default: return launch_grouped<GGML_TYPE_Q5_1, SMALL_GROUP>(S, s);
         }
     }
@@ -497,6 +498,7 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
     case GGML_TYPE_Q4_0: return launch_grouped<GGML_TYPE_Q4_0, GGB_GEMM_GROUP_NODES>(G, s);
     case GGML_TYPE_Q4_1: return launch_grouped<GGML_TYPE_Q4_1, GGB_GEMM_GROUP_NODES>(G, s);
     case GGML_TYPE_Q4_2: return launch_grouped<GGML_TYPE_Q4_2, GGB_GEMM_GROUP_NODES>(G, s);
+    case GGML_TYPE_Q8_0: return launch_grouped<GGML_TYPE_Q8_0, GGB_GEMM_GROUP_NODES>(G, s);
     default: return launch_grouped<GGML_TYPE_Q5_1, GGB_GEMM_GROUP_NODES>(G, s);
     }
 }

@@ -132,8 +132,8 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
 }
 
 // bytes one K step (128 weights) of one weight row occupies in its reference layout = the TMA box width of the raw ring:
-// Q4_0 4 x 20, Q4_2 8 x 10; Q4_1 / Q5_1 4 x 24
-template <int TYPE> struct RawRow { static constexpr int BYTES = (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_2) ? 80 : 96; };
+// Q4_0 4 x 20, Q4_2 8 x 10; Q4_1 / Q5_1 4 x 24; Q8_0 4 x 36
+template <int TYPE> struct RawRow { static constexpr int BYTES = (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_2) ? 80 : TYPE == GGML_TYPE_Q8_0 ? 144 : 96; };
 
 // 8 weights of one 32-bit nibble word -> 4 half2 in K order (0,4) (1,5) (2,6) (3,7), scaled: (q-c)*d [+ m'], c = 8 (16 for Q5_1).
 // Q5_1: hb = the 8 fifth bits of these weights (qh >> 8*word); bit e belongs to element e and lands on the 16s place of its half:
@@ -189,6 +189,25 @@ __device__ __forceinline__ void dequant_group(const uint32_t *w, int j, uint32_t
         dequant_word<TYPE>(__funnelshift_r(wb[1], wb[2], 16), 0u, d2a, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 4);
         dequant_word<TYPE>(wb[3], 0u, d2b, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 8);
         dequant_word<TYPE>(wb[4], 0u, d2b, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 12);
+    } else if (TYPE == GGML_TYPE_Q8_0) {
+        // words 9j: [f32 d][32 x int8].  Bytes k of two consecutive words are elements k and k+4 of a group of 8: PRMT doubles them
+        // into the two halves and ONE LOP3 (immLut 0x6A = b ? a ^ c : c, b = 0x00FF00FF, c = 0x64806480) masks, flips the sign
+        // bit and ORs the fp16 magic in: half = 1024 + (q + 128), exact; minus 1152, times d.
+        const uint32_t *wb = &w[9 * j];
+        const __half2 d2 = __float2half2_rn(__uint_as_float(wb[0])), o = __float2half2_rn(1152.0f);
+        uint32_t mk = 0x00FF00FFu, mg = 0x64806480u;
+        asm volatile("" : "+r"(mk), "+r"(mg));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t wa = wb[1 + 2 * i], wc = wb[2 + 2 * i];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t t = __byte_perm(wa, wc, (uint32_t)(k | (k << 4) | ((4 + k) << 8) | ((4 + k) << 12))), v;
+                asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(v) : "r"(t), "r"(mk), "r"(mg));
+                const __half2 h = __hmul2(__hsub2(*reinterpret_cast<__half2 *>(&v), o), d2);
+                out[4 * i + k] = *reinterpret_cast<const uint32_t *>(&h);
+            }
+        }
     } else {
         const uint32_t *wb = &w[6 * j];
         uint32_t dd = (wb[0] & 0xFFFFu) * 0x00010001u;
