@@ -153,7 +153,7 @@ def main():
             n2 = max(2, n_ring * 4096 // 11008 + 1)
             run_nodes([(t, 11008, 4096)] * n2, 1, "sibling %s 11008x4096 (w1/w3) GEMV, ring of %d" % (TN[t], n2), a.iters)
             run_nodes([(t, 4096, 11008)] * n2, 1, "sibling %s 4096x11008 (w2, K=11008) GEMV, ring of %d" % (TN[t], n2), a.iters)
-            run_nodes([(t, 4096, 4096)] * 8, 512, "sibling %s 4096x4096 . 4096x512, batch of 8 nodes (%s)" % (TN[t], "in-kernel dequant" if t != N.Q5_0 else "fp16 expansion + F16 GEMM"), max(4, a.iters // 4))
+            run_nodes([(t, 4096, 4096)] * 8, 512, "sibling %s 4096x4096 . 4096x512, batch of 8 nodes (%s)" % (TN[t], "in-kernel dequant"), max(4, a.iters // 4))
             run_nodes([(t, 4096, 4096)], 512, "sibling %s 4096x4096 . 4096x512, isolated" % TN[t], a.iters)
         rows = 11008
         nsrc = 2

@@ -280,7 +280,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
             for (int ks = 0; ks < ksteps; ks++) {
                 mbar_wait(BAR(RAW_EMPTY + s), ph_s);
                 mbar_expect_tx(BAR(RAW_FULL + s), RAW_BYTES);
-                tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &map_w, BAR(RAW_FULL + s), ks * RAW_ROW, m0);
+                tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &map_w, BAR(RAW_FULL + s), RawRow<TYPE>::box_x(ks), m0);
                 if (++s == RAW_STAGES) { s = 0; ph_s ^= 1; }
             }
         }
@@ -345,12 +345,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                 mbar_wait(BAR(RAW_FULL + s), (uint32_t)((ks / RAW_STAGES) & 1));
                 if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 1] = clock64();
                 uint32_t w[RAW_ROW / 4] = {};
-                if (!(dbg_flags & 2))
-#pragma unroll
-                for (int i = 0; i < RAW_ROW / 16; i++) {
-                    const uint4 t = lds128(raw_row + (uint32_t)(s * RAW_BYTES + i * 16));
-                    w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
-                }
+                if (!(dbg_flags & 2)) load_raw_row<TYPE>(raw_row + (uint32_t)(s * RAW_BYTES), ks, w);
                 // NOTE: the raw stage is released only after the dequant below has CONSUMED these registers.  Arriving right after
                 // issuing the LDS (data still in flight) let the next TMA overwrite the stage under the loads: intermittent
                 // rel-L2 ~5e-3 on large Q4_1 shapes (benchmarks/q41_bisect.sh).
@@ -540,8 +535,8 @@ int launch_q(const GemmArgs &a, cudaStream_t s)
 
 bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W)
 {
-    // F32 weights stay on FFMA (1e-5 bar); Q5_0 (88-byte K steps: not a legal TMA box) goes through an fp16 expansion (ggb_shim.cu)
-    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1 && type != GGML_TYPE_Q4_2 && type != GGML_TYPE_Q5_1 && type != GGML_TYPE_Q8_0 && type != GGML_TYPE_F16) return false;
+    // F32 weights stay on FFMA (1e-5 bar)
+    if (type != GGML_TYPE_F16 && !is_q_weight(type)) return false;
     if (M <= 0 || N < 16 || K <= 0 || K % GGB_QK) return false;
     if ((reinterpret_cast<uintptr_t>(W) & 15) || (nb01 & 15)) return false;                            // TMA: 16-byte base and strides
     if (type == GGML_TYPE_F16) return K % 8 == 0;
@@ -568,6 +563,7 @@ int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s)
     case GGML_TYPE_Q4_2: return launch_q<GGML_TYPE_Q4_2, 128, 2>(a, s);
     case GGML_TYPE_Q5_1: return launch_q<GGML_TYPE_Q5_1, 128, 2>(a, s);
     case GGML_TYPE_Q8_0: return launch_q<GGML_TYPE_Q8_0, 128, 2>(a, s);
+    case GGML_TYPE_Q5_0: return launch_q<GGML_TYPE_Q5_0, 128, 2>(a, s);
     case GGML_TYPE_F16: return cg == 1 ? launch_f16<128, 1>(a, s) : launch_f16<128, 2>(a, s);
     default: return set_error(GGB_E_UNSUPPORTED, "batched path: type %d", a.type);
     }

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                     const int s = gk & (RAW_STAGES - 1);
                     mbar_wait(BAR(RAW_EMPTY + s), ((gk >> 3) & 1) ^ 1);
                     mbar_expect_tx(BAR(RAW_FULL + s), RAW_BYTES);
-                    tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &tl.nd->map_w, BAR(RAW_FULL + s), ks * RAW_ROW, tl.m0);
+                    tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &tl.nd->map_w, BAR(RAW_FULL + s), RawRow<TYPE>::box_x(ks), tl.m0);
                 }
             }
         }
@@ -171,11 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                 const int s = gk & (RAW_STAGES - 1);
                 mbar_wait(BAR(RAW_FULL + s), (gk >> 3) & 1);
                 uint32_t w[RAW_ROW / 4];
-#pragma unroll
-                for (int i = 0; i < RAW_ROW / 16; i++) {
-                    const uint4 v4 = lds128(raw_row + (uint32_t)(s * RAW_BYTES + i * 16));
-                    w[4 * i] = v4.x; w[4 * i + 1] = v4.y; w[4 * i + 2] = v4.z; w[4 * i + 3] = v4.w;
-                }
+                load_raw_row<TYPE>(raw_row + (uint32_t)(s * RAW_BYTES), ks, w);
                 // the raw stage is released only after the dequant below has CONSUMED these registers (ggb_gemm.cu)
 #pragma unroll
                 for (int hb = 0; hb < 2; hb++) {                         // two blocks (64 K = 32 columns) per TMEM store
@@ -446,7 +442,7 @@ int launch_grouped(const GemmGroupT<CAP> &G, cudaStream_t s)
 
 } // namespace
 
-bool gemm_grouped_supported(int type) { return type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1 || type == GGML_TYPE_Q4_2 || type == GGML_TYPE_Q5_1 || type == GGML_TYPE_Q8_0 || type == GGML_TYPE_F16; }
+bool gemm_grouped_supported(int type) { return type == GGML_TYPE_Q4_0 || type == GGML_TYPE_Q4_1 || type == GGML_TYPE_F16 || is_q_weight(type); }
 
 int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
 {
@@ -490,6 +486,7 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
         case GGML_TYPE_Q4_1: return launch_grouped<GGML_TYPE_Q4_1, SMALL_GROUP>(S, s);
         case GGML_TYPE_Q4_2: return launch_grouped<GGML_TYPE_Q4_2, SMALL_GROUP>(S, s);
         case GGML_TYPE_Q8_0: return launch_grouped<GGML_TYPE_Q8_0, SMALL_GROUP>(S, s);
+        case GGML_TYPE_Q5_0: return launch_grouped<GGML_TYPE_Q5_0, SMALL_GROUP>(S, s);
         default: return launch_grouped<GGML_TYPE_Q5_1, SMALL_GROUP>(S, s);
         }
     }
@@ -499,6 +496,7 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
     case GGML_TYPE_Q4_1: return launch_grouped<GGML_TYPE_Q4_1, GGB_GEMM_GROUP_NODES>(G, s);
     case GGML_TYPE_Q4_2: return launch_grouped<GGML_TYPE_Q4_2, GGB_GEMM_GROUP_NODES>(G, s);
     case GGML_TYPE_Q8_0: return launch_grouped<GGML_TYPE_Q8_0, GGB_GEMM_GROUP_NODES>(G, s);
+    case GGML_TYPE_Q5_0: return launch_grouped<GGML_TYPE_Q5_0, GGB_GEMM_GROUP_NODES>(G, s);
     default: return launch_grouped<GGML_TYPE_Q5_1, GGB_GEMM_GROUP_NODES>(G, s);
     }
 }

@@ -83,8 +83,8 @@ static bool is_device_ptr(const void *p)
 // ------------------------------------------------------------------------------------------------
 
 // Sibling formats on the batched path.  Q4_2 and Q5_1 have the K-step footprint of Q4_0 / Q4_1 (80 / 96 bytes per 128 weights)
-// and Q8_0's is 144 bytes, so the tcgen05 kernels dequantize them in flight like those.  Q5_0 (88 bytes: not a legal TMA box)
-// -- and shapes of the others that the TMA path cannot take (K not a multiple of 128, unaligned rows) -- are expanded to dense fp16 [M][K] in the workspace
+// and Q8_0's is 144 bytes, so the tcgen05 kernels dequantize them in flight like those; Q5_0's 88 bytes ride in a 96-byte box
+// that advances by 88 (ggb_tc.cuh: RawRow).  Shapes the TMA path cannot take (K not a multiple of 128, unaligned rows) -- are expanded to dense fp16 [M][K] in the workspace
 // (k_expand_f16) and the F16 kernel multiplies that, against activations staged as d*q like every quantized type.
 static inline bool use_gemm_expanded(const ggb_dev_mm &m)
 {
@@ -144,12 +144,12 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     std::vector<int> gemv_idx;
     bool first_gemm = true;
     static const bool grouped = [] { const char *e = getenv("GGB200_GEMM_GROUPED"); return !e || atoi(e) != 0; }();
-    constexpr int NSLOT = 7;                                      // one grouped launch sequence per kernel flavour
-    static const int slot_type[NSLOT] = {GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, GGML_TYPE_F16, GGML_TYPE_F16 /* expanded siblings */, GGML_TYPE_Q4_2, GGML_TYPE_Q5_1, GGML_TYPE_Q8_0};
+    constexpr int NSLOT = 8;                                      // one grouped launch sequence per kernel flavour
+    static const int slot_type[NSLOT] = {GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, GGML_TYPE_F16, GGML_TYPE_F16 /* expanded siblings */, GGML_TYPE_Q4_2, GGML_TYPE_Q5_1, GGML_TYPE_Q8_0, GGML_TYPE_Q5_0};
     std::vector<int> q_nodes[NSLOT];
     auto qslot = [&](const ggb_dev_mm &m) {
         if (use_gemm_expanded(m)) return 3;
-        switch (m.type) { case GGML_TYPE_Q4_0: return 0; case GGML_TYPE_Q4_1: return 1; case GGML_TYPE_Q4_2: return 4; case GGML_TYPE_Q5_1: return 5; case GGML_TYPE_Q8_0: return 6; default: return 2; }
+        switch (m.type) { case GGML_TYPE_Q4_0: return 0; case GGML_TYPE_Q4_1: return 1; case GGML_TYPE_Q4_2: return 4; case GGML_TYPE_Q5_1: return 5; case GGML_TYPE_Q8_0: return 6; case GGML_TYPE_Q5_0: return 7; default: return 2; }
     };
     // a sibling-format node: expand the weights behind the activation buffer of its workspace slice and hand the GEMM an F16 node.
     // The expansion is an ordinary (fully stream-ordered) launch and the activation kernel that follows it is launched WITHOUT

@@ -39,7 +39,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -119,7 +118,6 @@ __device__ __forceinline__ uint32_t and_or(uint32_t w, uint32_t mask, uint32_t m
 
 
 // ---- A operand in tensor memory: nibble -> fp16 expansion and tcgen05.st (used by the Q4_0 / Q4_1 kernels) ----
-__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 
 __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, bool cg2)
 {
@@ -131,9 +129,31 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
                      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 // bytes one K step (128 weights) of one weight row occupies in its reference layout = the TMA box width of the raw ring:
-// Q4_0 4 x 20, Q4_2 8 x 10; Q4_1 / Q5_1 4 x 24; Q8_0 4 x 36
-template <int TYPE> struct RawRow { static constexpr int BYTES = (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_2) ? 80 : TYPE == GGML_TYPE_Q8_0 ? 144 : 96; };
+// Q4_0 4 x 20, Q4_2 8 x 10; Q4_1 / Q5_1 4 x 24; Q8_0 4 x 36; Q5_0 4 x 22
+// Q5_0's 4 x 22 = 88 bytes are neither a legal box width nor a legal box origin for odd K steps (both multiples of 16), so its
+// box is 96 bytes wide and starts at 88 ks rounded down to 16: the step's bytes begin at offset 0 (even ks) or 8 (odd ks) of the
+// shared-memory row -- read with LDS.64 -- and the 8 spare bytes belong to a neighbouring K step (or are TMA's out-of-bounds zeros).
+template <int TYPE> struct RawRow {
+    static constexpr int BYTES = (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_2) ? 80 : TYPE == GGML_TYPE_Q8_0 ? 144 : 96;   // box width = shared-memory row
+    __device__ static __forceinline__ int box_x(int ks) { return TYPE == GGML_TYPE_Q5_0 ? (88 * ks) & ~15 : BYTES * ks; }        // byte coordinate of the box
+    __device__ static __forceinline__ int skew(int ks) { return TYPE == GGML_TYPE_Q5_0 ? (ks & 1) << 3 : 0; }                    // where the step starts inside the row
+};
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+// this thread's raw words of one K step: LDS.128 over the whole row, or (Q5_0) eleven LDS.64 from the skewed start
+template <int TYPE>
+__device__ __forceinline__ void load_raw_row(uint32_t addr, int ks, uint32_t *w)
+{
+    if (TYPE == GGML_TYPE_Q5_0) {
+        const uint32_t a = addr + (uint32_t)RawRow<TYPE>::skew(ks);
+#pragma unroll
+        for (int i = 0; i < 11; i++) { const uint2 t = lds64(a + i * 8); w[2 * i] = t.x; w[2 * i + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < RawRow<TYPE>::BYTES / 16; i++) { const uint4 t = lds128(addr + i * 16); w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w; }
+    }
+}
 
 // 8 weights of one 32-bit nibble word -> 4 half2 in K order (0,4) (1,5) (2,6) (3,7), scaled: (q-c)*d [+ m'], c = 8 (16 for Q5_1).
 // Q5_1: hb = the 8 fifth bits of these weights (qh >> 8*word); bit e belongs to element e and lands on the 16s place of its half:
@@ -142,11 +162,11 @@ template <int TYPE> struct RawRow { static constexpr int BYTES = (TYPE == GGML_T
 template <int TYPE>
 __device__ __forceinline__ void dequant_word(uint32_t w, uint32_t hb, __half2 d2, __half2 m2, uint32_t mk_lo, uint32_t mk_hi, uint32_t mg_lo, uint32_t mg_hi, uint32_t *out)
 {
-    constexpr float C = TYPE == GGML_TYPE_Q5_1 ? 16.0f : 8.0f;
+    constexpr float C = (TYPE == GGML_TYPE_Q5_1 || TYPE == GGML_TYPE_Q5_0) ? 16.0f : 8.0f;
     const __half2 o_lo = __float2half2_rn(1024.0f + C), o_hi = __float2half2_rn(64.0f + C);
     const uint32_t ws = w >> 8;
     uint32_t v0 = and_or(w, mk_lo, mg_lo), v1 = and_or(w, mk_hi, mg_hi), v2 = and_or(ws, mk_lo, mg_lo), v3 = and_or(ws, mk_hi, mg_hi);
-    if (TYPE == GGML_TYPE_Q5_1) {
+    if (TYPE == GGML_TYPE_Q5_1 || TYPE == GGML_TYPE_Q5_0) {
         v0 |= ((hb & 0x11u) * 0x00010010u) & 0x00100010u;
         v1 |= ((hb & 0x22u) * 0x00080080u) & 0x01000100u;
         v2 |= ((hb & 0x44u) * 0x00004004u) & 0x00100010u;
@@ -154,7 +174,7 @@ __device__ __forceinline__ void dequant_word(uint32_t w, uint32_t hb, __half2 d2
     }
     __half2 h0 = *reinterpret_cast<__half2 *>(&v0), h1 = *reinterpret_cast<__half2 *>(&v1);
     __half2 h2 = *reinterpret_cast<__half2 *>(&v2), h3 = *reinterpret_cast<__half2 *>(&v3);
-    if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_2) {
+    if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_2 || TYPE == GGML_TYPE_Q5_0) {
         h0 = __hmul2(__hsub2(h0, o_lo), d2); h1 = __hmul2(__hsub2(h1, o_hi), d2);
         h2 = __hmul2(__hsub2(h2, o_lo), d2); h3 = __hmul2(__hsub2(h3, o_hi), d2);
     } else {
@@ -189,6 +209,24 @@ __device__ __forceinline__ void dequant_group(const uint32_t *w, int j, uint32_t
         dequant_word<TYPE>(__funnelshift_r(wb[1], wb[2], 16), 0u, d2a, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 4);
         dequant_word<TYPE>(wb[3], 0u, d2b, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 8);
         dequant_word<TYPE>(wb[4], 0u, d2b, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 12);
+    } else if (TYPE == GGML_TYPE_Q5_0) {
+        // 22-byte blocks: group j starts at byte 22j = word 5.5j -- even j word aligned [h d | qh lo][qh hi | qs 0-1][qs ..] ...,
+        // odd j in the upper half of a word [.. | h d][qh][qs x 4] (the same two decodes as the GEMV, ggb_sib_math.cuh)
+        const uint32_t *wb = &w[(11 * j) >> 1];
+        uint32_t dd, qh, q[4];
+        if (j & 1) {
+            dd = wb[0] >> 16; qh = wb[1];
+#pragma unroll
+            for (int i = 0; i < 4; i++) q[i] = wb[2 + i];
+        } else {
+            dd = wb[0] & 0xFFFFu; qh = __funnelshift_r(wb[0], wb[1], 16);
+#pragma unroll
+            for (int i = 0; i < 4; i++) q[i] = __funnelshift_r(wb[1 + i], wb[2 + i], 16);
+        }
+        dd *= 0x00010001u;
+        const __half2 d2 = *reinterpret_cast<__half2 *>(&dd), z = __float2half2_rn(0.0f);
+#pragma unroll
+        for (int i = 0; i < 4; i++) dequant_word<TYPE>(q[i], (qh >> (8 * i)) & 0xFFu, d2, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 4 * i);
     } else if (TYPE == GGML_TYPE_Q8_0) {
         // words 9j: [f32 d][32 x int8].  Bytes k of two consecutive words are elements k and k+4 of a group of 8: PRMT doubles them
         // into the two halves and ONE LOP3 (immLut 0x6A = b ? a ^ c : c, b = 0x00FF00FF, c = 0x64806480) masks, flips the sign
