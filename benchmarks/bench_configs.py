@@ -27,6 +27,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--sib-types", default="q4_2,q5_0,q5_1,q8_0", help="sibling formats to run in --only siblings (for targeted ncu captures)")
+    ap.add_argument("--sib-parts", default="gemv,gemm,codecs")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -146,20 +148,25 @@ def main():
             torch.cuda.empty_cache()
     if want("siblings"):
         # the sibling weight formats through the same kernels (GEMV rings > 2x L2, codecs, tensor-core batch)
-        for t in (N.Q4_2, N.Q5_0, N.Q5_1, N.Q8_0):
+        sib = [t for t in (N.Q4_2, N.Q5_0, N.Q5_1, N.Q8_0) if TN[t] in a.sib_types.split(",")]
+        parts = a.sib_parts.split(",")
+        for t in sib:
             rb = 4096 // N.BLCK_SIZE[t] * N.TYPE_SIZE[t]
             n_ring = (336 << 20) // (4096 * rb) + 1
-            run_nodes([(t, 4096, 4096)] * n_ring, 1, "sibling %s 4096x4096 GEMV, ring of %d" % (TN[t], n_ring), a.iters)
             n2 = max(2, n_ring * 4096 // 11008 + 1)
-            run_nodes([(t, 11008, 4096)] * n2, 1, "sibling %s 11008x4096 (w1/w3) GEMV, ring of %d" % (TN[t], n2), a.iters)
-            run_nodes([(t, 4096, 11008)] * n2, 1, "sibling %s 4096x11008 (w2, K=11008) GEMV, ring of %d" % (TN[t], n2), a.iters)
+            if "gemv" in parts:
+                run_nodes([(t, 4096, 4096)] * n_ring, 1, "sibling %s 4096x4096 GEMV, ring of %d" % (TN[t], n_ring), a.iters)
+                run_nodes([(t, 11008, 4096)] * n2, 1, "sibling %s 11008x4096 (w1/w3) GEMV, ring of %d" % (TN[t], n2), a.iters)
+                run_nodes([(t, 4096, 11008)] * n2, 1, "sibling %s 4096x11008 (w2, K=11008) GEMV, ring of %d" % (TN[t], n2), a.iters)
+            if "gemm" not in parts:
+                continue
             run_nodes([(t, 4096, 4096)] * 8, 512, "sibling %s 4096x4096 . 4096x512, batch of 8 nodes (%s)" % (TN[t], "in-kernel dequant"), max(4, a.iters // 4))
             run_nodes([(t, 4096, 4096)], 512, "sibling %s 4096x4096 . 4096x512, isolated" % TN[t], a.iters)
         rows = 11008
         nsrc = 2
         src = torch.randn((nsrc, rows, 4096), device=dev) * 0.02
         back = torch.empty((nsrc, rows, 4096), device=dev)
-        for t in (N.Q4_2, N.Q5_0, N.Q5_1, N.Q8_0):
+        for t in (sib if "codecs" in parts else []):
             rb = 4096 // N.BLCK_SIZE[t] * N.TYPE_SIZE[t]
             dst = torch.empty((nsrc, rows, rb), dtype=torch.uint8, device=dev)
             it = [0]
