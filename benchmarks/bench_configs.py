@@ -62,13 +62,17 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
 
-    def run_nodes(shapes, Nn, label, iters):
-        """shapes: list of (type, M, K); all submitted as one batch per call."""
+    def run_nodes(shapes, Nn, label, iters, share_x=False):
+        """shapes: list of (type, M, K); all submitted as one batch per call.  share_x: every node multiplies the same activations."""
         keep, mm = [], (N.ggb_dev_mm * len(shapes))()
         wbytes = flop = abytes = 0
+        xs = {}
         for i, (t, M, K) in enumerate(shapes):
             w, rb = make_w(t, M, K)
-            x = torch.randn((Nn, K), device=dev)
+            x = xs.get(K) if share_x else None
+            if x is None:
+                x = torch.randn((Nn, K), device=dev)
+                xs[K] = x
             y = torch.zeros((Nn, M), device=dev)
             keep += [w, x, y]
             m = mm[i]
@@ -197,6 +201,9 @@ def main():
         for t in (N.Q4_0, N.F16):
             run_nodes([(t, 4096, 4096)] * 8, 512, "cfg3 %s 4096x4096 . 4096x512, batch of 8 nodes" % TN[t], max(4, a.iters // 4))
             run_nodes([(t, 4096, 4096)], 512, "cfg3 %s 4096x4096 . 4096x512, isolated" % TN[t], a.iters)
+        # how the shape occurs in a layer: wq / wk / wv multiply ONE activation tensor, which is then staged once
+        run_nodes([(N.Q4_0, 4096, 4096)] * 3, 512, "cfg3 q4_0 wq/wk/wv: 3 x 4096x4096 on one shared 4096x512 activation tensor", a.iters, share_x=True)
+        run_nodes([(N.Q4_0, 4096, 4096)] * 3, 512, "cfg3 q4_0 3 x 4096x4096, each with its own 4096x512 activations", a.iters)
     if want("cfg4"):
         layer = [(N.Q4_0, 4096, 4096)] * 4 + [(N.Q4_0, 11008, 4096)] * 2 + [(N.Q4_0, 4096, 11008)]
         run_nodes(layer * 32, 1, "cfg4 Llama-7B-shaped stack, 32 layers x 7 Q4_0 matrices (4.05 GB), N=1 decode step, 1 GPU", max(3, a.iters // 6))

@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(256) k_expand_f16(const uint8_t *__restrict__ 
     constexpr int G = Sib<TYPE>::G;
     const int oct_per_row = K >> 3;
     const long long total = M * oct_per_row;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // no early launch_dependents: whatever follows (the activation kernel, or the GEMM itself when its activations were already
+    // staged for another node) must not start before these weights are complete
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long row = t / oct_per_row;
         const int oc = (int)(t - row * oct_per_row), sub = oc & 3;              // elements 8*sub .. 8*sub+7 of group oc >> 2

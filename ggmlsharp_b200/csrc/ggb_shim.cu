@@ -188,6 +188,10 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     }
     // ---- Q4_0 / Q4_1 batched nodes: one activation launch + one persistent grouped GEMM launch per <= 64 nodes.  The GEMM
     //      triggers its dependents at start-up, so the next group's activation staging overlaps it (ggb_gemm_grouped.cu) ----
+    // Nodes that multiply the SAME activations (wq / wk / wv of a layer, w1 / w3 of its FFN) share one staged copy: the first
+    // node's buffer is staged, the others point their B operand at it.  Keyed by what decides the staged bytes.
+    struct StagedX { const float *X; int64_t ldx, N, K; int cls; __half *xh; };
+    std::vector<StagedX> staged;
     for (int qi = 0; qi < NSLOT; qi++) {
         const std::vector<int> &qn = q_nodes[qi];
         for (size_t c0 = 0; c0 < qn.size(); c0 += GGB_GEMM_GROUP_NODES) {
@@ -196,13 +200,20 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
             static thread_local GemmArgs ga[GGB_GEMM_GROUP_NODES];
             const int type = slot_type[qi];                                                             // slot 3: expanded siblings run the F16 kernel
             // slot 3 stages activations as d*q (any quantized wtype selects that), in the F16 kernel's natural K order
-            ab.n_nodes = cnt; ab.wtype = qi == 3 ? GGML_TYPE_Q8_0 : type; ab.perm = gemm_act_perm(type); ab.wait_prior = first_gemm ? 1 : 0;
+            ab.n_nodes = 0; ab.wtype = qi == 3 ? GGML_TYPE_Q8_0 : type; ab.perm = gemm_act_perm(type); ab.wait_prior = first_gemm ? 1 : 0;
+            const int cls = ab.wtype == GGML_TYPE_F16 ? 2 : ab.perm;      // (Half)x | d*q in natural K order | d*q in the nibble-unpack order
             for (int c = 0; c < cnt; c++) {
                 const int i = qn[c0 + c];
                 const ggb_dev_mm &m = mm[i];
                 const int64_t Npad = (m.N + 15) / 16 * 16;
-                __half *xh = reinterpret_cast<__half *>(wsb + off[i]);
-                ab.node[c] = ActGemmNode{m.X, (long long)m.ldx_bytes, xh, (int)m.N, (int)Npad, (int)m.K, 0};
+                __half *xh = nullptr;
+                for (const StagedX &sx : staged)
+                    if (sx.X == m.X && sx.ldx == m.ldx_bytes && sx.N == m.N && sx.K == m.K && sx.cls == cls) { xh = sx.xh; break; }
+                if (!xh) {
+                    xh = reinterpret_cast<__half *>(wsb + off[i]);
+                    ab.node[ab.n_nodes++] = ActGemmNode{m.X, (long long)m.ldx_bytes, xh, (int)m.N, (int)Npad, (int)m.K, 0};
+                    staged.push_back(StagedX{m.X, m.ldx_bytes, m.N, m.K, cls, xh});
+                }
                 GemmArgs &a = ga[c];
                 a = GemmArgs{};
                 a.type = type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
@@ -210,9 +221,9 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
                 for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
                 if (qi == 3) { int rce = expand(i, a.W, a.nb01); if (rce) return rce; }
             }
-            int rc = launch_act_f16_dequant_batch(ab, s, qi != 3);
+            int rc = launch_act_f16_dequant_batch(ab, s, qi != 3);     // no-op when every node of the group reuses staged activations
             if (rc) return rc;
-            first_gemm = false;
+            if (ab.n_nodes) first_gemm = false;
             { KernelTimer kt(s); rc = launch_gemm_grouped(ga, cnt, s); }
             if (rc) return rc;
         }
@@ -220,6 +231,8 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
 
     // ---- single-token nodes: group by (type, K), fuse each group into one act launch + GEMV launches ----
     std::vector<char> done(count, 0);
+    std::vector<uint8_t *> act_base(count);
+    for (int i = 0; i < count; i++) act_base[i] = wsb + off[i];
     for (size_t a0 = 0; a0 < gemv_idx.size(); a0++) {
         const int i0 = gemv_idx[a0];
         if (done[i0]) continue;
@@ -251,13 +264,20 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
             int tot = 0;
             for (size_t c = c0; c < std::min(grp.size(), c0 + (size_t)GGB_MAX_BATCH_NODES); c++) {
                 const ggb_dev_mm &m = mm[grp[c]];
+                // same activations as an earlier node of this (type, K, layout) group: reuse its staged rows
+                bool shared = false;
+                for (size_t e = 0; e < c && !shared; e++) {
+                    const ggb_dev_mm &o = mm[grp[e]];
+                    if (o.X == m.X && o.ldx_bytes == m.ldx_bytes && o.N == m.N) { act_base[grp[c]] = act_base[grp[e]]; shared = true; }
+                }
+                if (shared) continue;
                 ActNode &an = ab.node[ab.n_nodes++];
                 an.x = m.X; an.ldx_bytes = m.ldx_bytes; an.out = wsb + off[grp[c]]; an.N = (int)m.N; an.blk0 = tot;
                 tot += quant ? (int)(m.N * ab.kb) : (int)m.N;
                 if ((reinterpret_cast<uintptr_t>(m.X) & 15) || (m.ldx_bytes & 15)) ab.vec16 = 0;
             }
             ab.total_blk = tot;
-            if (g_timing == 2) continue;                        // measurement mode: the workspace still holds these activations
+            if (g_timing == 2 || !ab.n_nodes) continue;         // measurement mode: the workspace still holds these activations
             int rc = launch_act_batch(ab, s, true);
             if (rc) return rc;
         }
@@ -301,7 +321,7 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
                 const ggb_dev_mm &m = mm[passes[p1].i];
                 GemvNode &nd = gb.node[gb.n_nodes++];
                 nd.W = static_cast<const uint8_t *>(m.W);
-                nd.xq = wsb + off[passes[p1].i] + (size_t)passes[p1].col0 * arow;
+                nd.xq = act_base[passes[p1].i] + (size_t)passes[p1].col0 * arow;
                 nd.y = m.Y + (size_t)passes[p1].col0 * (m.ldy_bytes / 4);
                 nd.M = (int)m.M; nd.ldy = (int)(m.ldy_bytes / 4);
                 const int64_t rows_per_group = gemv_group_rows(gb);

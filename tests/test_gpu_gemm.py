@@ -177,3 +177,42 @@ def test_grouped_gemm_mixed_batch_and_rerun():
         assert np.array_equal(ya, yb)
         tol = GEMM_TOL[t] if X.shape[0] >= 16 else 5e-6
         assert rel_l2(ya, orc.mul_mat_2d(t, wb, M, K, X, nth=8)) <= tol, (t, M, K, X.shape[0])
+
+
+@pytest.mark.parametrize("Nn", [1, 5, 32])
+def test_nodes_sharing_one_activation_tensor(Nn):
+    """wq / wk / wv (and w1 / w3) of a layer multiply the same src1: the batch stages those activations once and every node reads
+    the shared copy.  Mixed weight types and one node with its own activations, each checked against the oracle."""
+    import ctypes as C
+    from test_gpu_parity import Dev, weights
+    rng = np.random.default_rng(500 + Nn)
+    K = 512
+    Xs = rng.standard_normal((Nn, K)).astype(np.float32)
+    Xo = rng.standard_normal((Nn, K)).astype(np.float32)
+    specs = [(N.Q4_0, 256, True), (N.Q4_0, 384, True), (N.Q4_1, 256, True), (N.F16, 128, True), (N.Q4_0, 256, False),
+             (N.Q5_0, 256, True), (N.Q4_1, 192, True), (N.Q8_0, 128, True), (N.F16, 256, True), (N.F32, 64, True), (N.F32, 96, True)]
+    d = Dev()
+    try:
+        pXs, pXo = d.put(Xs), d.put(Xo)
+        mms = (N.ggb_dev_mm * len(specs))()
+        wbs = []
+        for i, (t, M, shared) in enumerate(specs):
+            wb = orc.encode_weights(t, weights(rng, M, K))
+            wbs.append(wb)
+            mm = mms[i]
+            mm.type, mm.M, mm.K, mm.N = t, M, K, Nn
+            mm.W, mm.nb01 = d.put(wb), wb.shape[1]
+            mm.X, mm.ldx_bytes = (pXs if shared else pXo), 4 * K
+            mm.Y, mm.ldy_bytes = d.empty(4 * M * Nn), 4 * M
+        wsb = N.lib().ggb_dev_workspace_bytes(mms, len(specs))
+        ws = d.empty(wsb)
+        for _ in range(2):                               # twice: the second run must not depend on leftovers of the first
+            N.check(N.lib().ggb_dev_mul_mat_batch(mms, len(specs), ws, wsb, None))
+        N.check(N.lib().ggb_stream_sync(None))
+        for i, (t, M, shared) in enumerate(specs):
+            got = d.get(mms[i].Y, (Nn, M))
+            want = orc.mul_mat_2d(t, wbs[i], M, K, Xs if shared else Xo, nth=4)
+            tol = 1e-3 if (Nn >= 16 and t != N.F32) else 5e-6
+            assert rel_l2(got, want) <= tol, (i, specs[i], rel_l2(got, want))
+    finally:
+        d.close()
