@@ -27,14 +27,15 @@ WORKER = textwrap.dedent('''
     M, K, NODES = 2048, 1024, 3
     Ws = [(rng.standard_normal((M, K)) * 0.02).astype(np.float32) for _ in range(NODES)]
     Xs = [rng.standard_normal((1, K)).astype(np.float32) for _ in range(NODES)]
-    wbs = [orc.quantize_rows(orc.Q4_0, w) for w in Ws]
-    want = np.stack([orc.mul_mat_2d(orc.Q4_0, wb, M, K, x)[0] for wb, x in zip(wbs, Xs)])          # [NODES][M]
+    TYPES = [N.Q4_0, N.Q5_0, N.Q8_0]                          # one headline and two sibling formats, one node each
+    wbs = [orc.quantize_rows(t, w) for t, w in zip(TYPES, Ws)]
+    want = np.stack([orc.mul_mat_2d(t, wb, M, K, x)[0] for t, wb, x in zip(TYPES, wbs, Xs)])      # [NODES][M]
     ok = True
     for variant in ("epilogue", "push", "push_gemm", "epilogue_gemm"):
         NB = 24 if variant.endswith("_gemm") else 1           # 24 activation rows -> the tcgen05 path; dst is [NB][M] per node
         if variant.endswith("_gemm"):
             Xg = [rng.standard_normal((NB, K)).astype(np.float32) for _ in range(NODES)]
-            wantg = np.stack([orc.mul_mat_2d(orc.Q4_0, wb, M, K, x, nth=8) for wb, x in zip(wbs, Xg)])      # [NODES][NB][M]
+            wantg = np.stack([orc.mul_mat_2d(t, wb, M, K, x, nth=8) for t, wb, x in zip(TYPES, wbs, Xg)])  # [NODES][NB][M]
         sym = rowsplit.SymmetricBuffer(NODES * NB * M * 4, rank, world, ago)
         r0, n = rowsplit.shard_rows(M, world, rank)
         keep, mms = [], (N.ggb_dev_mm * NODES)()
@@ -42,7 +43,7 @@ WORKER = textwrap.dedent('''
             p = C.c_void_p(); N.check(L.ggb_dev_alloc(a.nbytes, C.byref(p))); N.check(L.ggb_dev_upload(p, a.ctypes.data, a.nbytes)); keep.append(p); return p.value
         for i in range(NODES):
             m = mms[i]
-            m.type, m.M, m.K, m.N = N.Q4_0, n, K, NB
+            m.type, m.M, m.K, m.N = TYPES[i], n, K, NB
             m.W, m.nb01 = put(np.ascontiguousarray(wbs[i][r0:r0 + n])), wbs[i].shape[1]
             m.X, m.ldx_bytes = put(Xg[i] if variant.endswith("_gemm") else Xs[i]), 4 * K
             off = (i * NB * M + r0) * 4
@@ -64,7 +65,7 @@ WORKER = textwrap.dedent('''
         err = float(np.linalg.norm(got - ref_) / np.linalg.norm(ref_))
         t = torch.from_numpy(got).cuda(); ref = t.clone(); dist.broadcast(ref, 0)
         same = bool(torch.equal(t, ref))
-        ok = ok and err <= (1e-3 if variant.endswith("_gemm") else 2e-6) and same
+        ok = ok and err <= (1e-3 if variant.endswith("_gemm") else 5e-6) and same
         dist.barrier(); sym.close()
     flag = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0: print("ROWSPLIT_GPU_OK" if flag.item() == 1 else "ROWSPLIT_GPU_MISMATCH")
