@@ -442,6 +442,7 @@ def main():
         dt = float(t.item())
     e2e = {"value": world * step_bytes_rank / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3,
            "h2d_bytes_per_step": int(s_e2e.h2d_bytes // n_e2e) * world, "d2h_bytes_per_step": int(s_e2e.d2h_bytes // n_e2e) * world,
+           "device_ms_per_step": float(s_e2e.last_graph_device_ms),       # CUDA-event span of the last call: staging reads over PCIe + kernels + result copy
            "api": "ggml_graph_compute over a %d-node graph per rank (host arena, weights device-cached)%s" % (RING, "; each rank reads back its own dst block" if world > 1 else "")}
     if rank == 0:
         line["e2e"] = e2e

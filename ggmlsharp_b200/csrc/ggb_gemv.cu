@@ -28,6 +28,7 @@
 #include "ggb_sib_math.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ggb {
 
@@ -606,8 +607,8 @@ int launch_typed(const GemvBatchT<CAP> &b, size_t smem, int grid, cudaStream_t s
 }
 
 constexpr int X_BUDGET = 64 * 1024;        // activation columns resident in shared memory
-constexpr int W_BUDGET = 160 * 1024;       // weight stages of all warps
-constexpr int STAGE_MAX = 4096;            // bytes of one bulk copy (one row, several short rows, or a K-chunk of a long row)
+static const int W_BUDGET = [] { const char *e = getenv("GGB200_GEMV_WBUDGET"); return e ? atoi(e) : 200 * 1024; }();       // weight stages of all warps (sweep: benchmarks/gemv_stage_sweep.sh; 160 -> 200 KB: +5 % F32, +10 % F16 K=11008)
+static const int STAGE_MAX = [] { const char *e = getenv("GGB200_GEMV_STAGE_MAX"); return e ? atoi(e) : 4096; }();           // bytes of one bulk copy (one row, several short rows, or a K-chunk of a long row)
 
 } // namespace
 
