@@ -27,6 +27,10 @@
 #include "ggb_internal.h"
 #include "ggb_sib_math.cuh"
 
+#ifndef GGB_GEMV_PART
+#define GGB_GEMV_PART 0
+#endif
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -612,6 +616,37 @@ static const int STAGE_MAX = [] { const char *e = getenv("GGB200_GEMV_STAGE_MAX"
 
 } // namespace
 
+// This file is compiled TWICE (csrc/Makefile): GGB_GEMV_PART 0 instantiates the kernels of the four headline weight types plus
+// the planning / dispatch code, GGB_GEMV_PART 1 those of the sibling formats -- 144 kernel instantiations in one translation unit
+// made it the long pole of the build.
+template <int CAP>
+int launch_gemv_typed_sib(const GemvBatchT<CAP> &b, size_t smem, int grid, cudaStream_t s, bool pdl);
+
+#if GGB_GEMV_PART == 1
+template <int CAP>
+int launch_gemv_typed_sib(const GemvBatchT<CAP> &b, size_t smem, int grid, cudaStream_t s, bool pdl)
+{
+    if (b.async) switch (b.type) {
+    case GGML_TYPE_Q4_2: return launch_fast_typed<GGML_TYPE_Q4_2, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q5_0: return launch_fast_typed<GGML_TYPE_Q5_0, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q5_1: return launch_fast_typed<GGML_TYPE_Q5_1, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q8_0: return launch_fast_typed<GGML_TYPE_Q8_0, CAP>(b, smem, grid, s, pdl);
+    default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6719-6742)", b.type);
+    }
+    switch (b.type) {
+    case GGML_TYPE_Q4_2: return launch_typed<GGML_TYPE_Q4_2, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q5_0: return launch_typed<GGML_TYPE_Q5_0, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q5_1: return launch_typed<GGML_TYPE_Q5_1, CAP>(b, smem, grid, s, pdl);
+    case GGML_TYPE_Q8_0: return launch_typed<GGML_TYPE_Q8_0, CAP>(b, smem, grid, s, pdl);
+    default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6719-6742)", b.type);
+    }
+}
+template int launch_gemv_typed_sib<GGB_SMALL_BATCH_NODES>(const GemvBatchT<GGB_SMALL_BATCH_NODES> &, size_t, int, cudaStream_t, bool);
+template int launch_gemv_typed_sib<GGB_MAX_BATCH_NODES>(const GemvBatchT<GGB_MAX_BATCH_NODES> &, size_t, int, cudaStream_t, bool);
+#else
+extern template int launch_gemv_typed_sib<GGB_SMALL_BATCH_NODES>(const GemvBatchT<GGB_SMALL_BATCH_NODES> &, size_t, int, cudaStream_t, bool);
+extern template int launch_gemv_typed_sib<GGB_MAX_BATCH_NODES>(const GemvBatchT<GGB_MAX_BATCH_NODES> &, size_t, int, cudaStream_t, bool);
+
 int gemv_num_ctas() { return device_sm_count(); }
 int gemv_group_rows(const GemvHdr &b) { return b.async ? NWF * b.rs : b.rs; }
 static int unit_bytes_async(int type)
@@ -699,13 +734,10 @@ static int launch_gemv_cap(const GemvBatchT<CAP> &b, cudaStream_t s, bool pdl)
                                 : xbytes + (size_t)NWARPS * b.stage_bytes;
     const int want = b.async ? b.total_groups : (b.total_groups + NWARPS - 1) / NWARPS;
     if (grid > want) grid = want;
+    if (is_sibling_q(b.type)) return launch_gemv_typed_sib<CAP>(b, smem, grid, s, pdl);
     if (b.async) switch (b.type) {
     case GGML_TYPE_Q4_0: return launch_fast_typed<GGML_TYPE_Q4_0, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_Q4_1: return launch_fast_typed<GGML_TYPE_Q4_1, CAP>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q4_2: return launch_fast_typed<GGML_TYPE_Q4_2, CAP>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q5_0: return launch_fast_typed<GGML_TYPE_Q5_0, CAP>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q5_1: return launch_fast_typed<GGML_TYPE_Q5_1, CAP>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q8_0: return launch_fast_typed<GGML_TYPE_Q8_0, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_F16: return launch_fast_typed<GGML_TYPE_F16, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_F32: return launch_fast_typed<GGML_TYPE_F32, CAP>(b, smem, grid, s, pdl);
     default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6719-6742)", b.type);
@@ -713,10 +745,6 @@ static int launch_gemv_cap(const GemvBatchT<CAP> &b, cudaStream_t s, bool pdl)
     switch (b.type) {
     case GGML_TYPE_Q4_0: return launch_typed<GGML_TYPE_Q4_0, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_Q4_1: return launch_typed<GGML_TYPE_Q4_1, CAP>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q4_2: return launch_typed<GGML_TYPE_Q4_2, CAP>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q5_0: return launch_typed<GGML_TYPE_Q5_0, CAP>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q5_1: return launch_typed<GGML_TYPE_Q5_1, CAP>(b, smem, grid, s, pdl);
-    case GGML_TYPE_Q8_0: return launch_typed<GGML_TYPE_Q8_0, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_F16: return launch_typed<GGML_TYPE_F16, CAP>(b, smem, grid, s, pdl);
     case GGML_TYPE_F32: return launch_typed<GGML_TYPE_F32, CAP>(b, smem, grid, s, pdl);
     default: return set_error(GGB_E_UNSUPPORTED, "mul_mat: src0 type %d is not on this path (Ggml.cs:6719-6742)", b.type);
@@ -735,5 +763,6 @@ int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl)
     }
     return launch_gemv_cap(b, s, pdl);
 }
+#endif
 
 } // namespace ggb
