@@ -653,9 +653,8 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
         else k_quantize_q4_tiles<GGML_TYPE_Q4_1><<<gridt, QT_WARPS * 32, smem, s>>>(src, ldx, y, nblk, kb, exact_only);
         break;
     }
-    case GGML_TYPE_Q8_0: k_quantize_rows<GGML_TYPE_Q8_0><<<grid, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
     case GGML_TYPE_Q8_1: k_quantize_rows<GGML_TYPE_Q8_1><<<grid, 256, 0, s>>>(src, ldx, y, nblk, kb); break;
-    default: return set_error(GGB_E_UNSUPPORTED, "quantize: type %d has no codec on this path", type);
+    default: return set_error(GGB_E_UNSUPPORTED, "quantize: type %d has no quantize_row_q (Ggml.cs:219-290)", type);
     }
     count_launch(); GGB_CUDA(cudaGetLastError());
     return GGB_OK;

@@ -225,10 +225,11 @@ __global__ void __launch_bounds__(128) k_add_q_sib(const uint8_t *__restrict__ q
 // Batched (tensor-core) path of the sibling formats: weights expanded once per call to dense fp16 [M][K] holding the
 // reference's dequantized value rounded to half (the same operand precision the in-kernel Q4_0 / Q4_1 dequant feeds the
 // MMAs), then the F16 tcgen05 GEMM runs on it.  One thread per 8 consecutive elements (one 16-byte store).
+// (Q4_0 / Q4_1 are here too: their shapes that the TMA kernels cannot take -- K not a multiple of 128 -- use the same fallback.)
 template <int TYPE>
 __global__ void __launch_bounds__(256) k_expand_f16(const uint8_t *__restrict__ W, long long nb01, __half *__restrict__ out, long long M, int K)
 {
-    constexpr int G = Sib<TYPE>::G;
+    constexpr int G = TYPE == GGML_TYPE_Q4_0 ? 20 : TYPE == GGML_TYPE_Q4_1 ? 24 : TYPE == GGML_TYPE_Q4_2 ? 20 : TYPE == GGML_TYPE_Q5_0 ? 22 : TYPE == GGML_TYPE_Q5_1 ? 24 : 36;
     const int oct_per_row = K >> 3;
     const long long total = M * oct_per_row;
     // no early launch_dependents: whatever follows (the activation kernel, or the GEMM itself when its activations were already
@@ -238,7 +239,17 @@ __global__ void __launch_bounds__(256) k_expand_f16(const uint8_t *__restrict__ 
         const int oc = (int)(t - row * oct_per_row), sub = oc & 3;              // elements 8*sub .. 8*sub+7 of group oc >> 2
         const unsigned short *g = reinterpret_cast<const unsigned short *>(W + row * nb01 + (long long)(oc >> 2) * G);
         float v[8];
-        if (TYPE == GGML_TYPE_Q4_2) {
+        if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_1) {           // [f32 d][f32 m (Q4_1)][16 nibble bytes], Ggml.cs:884-911 / 961-987
+            constexpr int Q0 = TYPE == GGML_TYPE_Q4_0 ? 2 : 4;
+            const float d = __uint_as_float((uint32_t)__ldg(g) | ((uint32_t)__ldg(g + 1) << 16));
+            const float m = TYPE == GGML_TYPE_Q4_1 ? __uint_as_float((uint32_t)__ldg(g + 2) | ((uint32_t)__ldg(g + 3) << 16)) : 0.0f;
+            const uint32_t q = (uint32_t)__ldg(g + Q0 + 2 * sub) | ((uint32_t)__ldg(g + Q0 + 2 * sub + 1) << 16);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int n = (int)((q >> (4 * i)) & 15u);
+                v[i] = TYPE == GGML_TYPE_Q4_0 ? __fmul_rn((float)(n - 8), d) : __fadd_rn(__fmul_rn((float)n, d), m);
+            }
+        } else if (TYPE == GGML_TYPE_Q4_2) {
             const unsigned short *b = g + 5 * (sub >> 1);
             const float d = h_val(__ldg(b));
             const uint32_t q = (uint32_t)__ldg(b + 1 + 2 * (sub & 1)) | ((uint32_t)__ldg(b + 2 + 2 * (sub & 1)) << 16);
@@ -355,7 +366,9 @@ int launch_expand_f16(int type, const void *W, int64_t nb01, __half *out, int64_
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    GGB_SIB_SWITCH(type, GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<T>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K)));
+    if (type == GGML_TYPE_Q4_0) GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<GGML_TYPE_Q4_0>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K));
+    else if (type == GGML_TYPE_Q4_1) GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<GGML_TYPE_Q4_1>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K));
+    else GGB_SIB_SWITCH(type, GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<T>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K)));
     count_launch();
     return GGB_OK;
 }

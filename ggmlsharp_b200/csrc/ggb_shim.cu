@@ -88,7 +88,7 @@ static bool is_device_ptr(const void *p)
 // (k_expand_f16) and the F16 kernel multiplies that, against activations staged as d*q like every quantized type.
 static inline bool use_gemm_expanded(const ggb_dev_mm &m)
 {
-    return is_sibling_q(m.type) && m.N >= 16 && m.M > 0 && m.K % GGB_QK == 0 && ((reinterpret_cast<uintptr_t>(m.W) | (uintptr_t)m.nb01) & 1) == 0 &&
+    return is_q_weight(m.type) && m.N >= 16 && m.M > 0 && m.K % GGB_QK == 0 && ((reinterpret_cast<uintptr_t>(m.W) | (uintptr_t)m.nb01) & 1) == 0 &&
            !gemm_supported(m.type, m.M, m.K, m.N, m.nb01, m.W);
 }
 static inline bool use_gemm(const ggb_dev_mm &m)
@@ -103,9 +103,11 @@ static size_t mm_ws_bytes(const ggb_dev_mm &m)
     return align_up((size_t)m.N * act_row_bytes(m.type, m.K), 256);
 }
 // upper bound that does not depend on operand addresses (for sizing before buffers exist)
-static size_t mm_ws_bytes_bound(int type, int64_t M, int64_t K, int64_t N)
+// may_expand: the weights might not satisfy the TMA path's alignment once staged (the caller knows nb01 and view offsets)
+static size_t mm_ws_bytes_bound(int type, int64_t M, int64_t K, int64_t N, bool may_expand)
 {
-    const size_t tc = align_up(gemm_workspace_bytes(type, M, K, N), 256) + (is_sibling_q(type) && N >= 16 ? expanded_bytes(M, K) : 0);   // alignment unknown yet: assume the expansion
+    const bool expand = is_q_weight(type) && N >= 16 && (may_expand || K % 128 != 0);
+    const size_t tc = align_up(gemm_workspace_bytes(type, M, K, N), 256) + (expand ? expanded_bytes(M, K) : 0);
     return std::max(tc, align_up((size_t)N * act_row_bytes(type, K), 256));
 }
 
@@ -546,11 +548,15 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             ggml_tensor *t = nodes[i];
             const ggml_tensor *a = t->src0, *b = t->src1;
             if (t->op == GGML_OP_MUL_MAT) {
-                const bool a_dev = find_produced(plan, a->data) != nullptr;
+                Produced *a_pr = find_produced(plan, a->data);
+                const bool a_dev = a_pr != nullptr;
                 const bool a_cached = !a_dev && a->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE);
                 if (!a_dev && !a_cached) need += align_up(tensor_span(a), 256);
                 if (!find_produced(plan, b->data)) need += align_up(tensor_span(b), 256);
-                need += (size_t)(a->ne[2] * a->ne[3]) * mm_ws_bytes_bound(a->type, a->ne[1], a->ne[0], b->ne[1]);
+                // staged weights start 256-byte aligned (mirror / arena) unless they are a view into an earlier node's output
+                const bool may_expand = (a->nb[1] & 15) || (a->nb[2] & 15) || (a->nb[3] & 15) ||
+                                        (a_pr && ((static_cast<const uint8_t *>(a->data) - a_pr->host) & 15));
+                need += (size_t)(a->ne[2] * a->ne[3]) * mm_ws_bytes_bound(a->type, a->ne[1], a->ne[0], b->ne[1], may_expand);
             } else {
                 if (!find_produced(plan, a->data)) need += align_up(tensor_span(a), 256);
                 if (b && t->op != GGML_OP_CPY && t->op != GGML_OP_SCALE && !find_produced(plan, b->data)) need += align_up(tensor_span(b), 256);
@@ -698,6 +704,8 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         if (!mms.empty()) {
             size_t wsb = 0;
             for (const ggb_dev_mm &m : mms) wsb += mm_ws_bytes(m);
+            if (pool->arena.used + align_up(wsb, 256) > pool->arena.cap)
+                return set_error(GGB_E_NOMEM, "executor: mul_mat workspace of %zu B exceeds the planned scratch (%zu of %zu B used)", wsb, pool->arena.used, pool->arena.cap);
             void *ws = pool->arena.take(wsb);
             rc = dev_batch(mms.data(), (int)mms.size(), ws, wsb, s);
             if (rc) return rc;

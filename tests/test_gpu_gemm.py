@@ -216,3 +216,18 @@ def test_nodes_sharing_one_activation_tensor(Nn):
             assert rel_l2(got, want) <= tol, (i, specs[i], rel_l2(got, want))
     finally:
         d.close()
+
+
+@pytest.mark.parametrize("t", [N.Q4_0, N.Q4_1])
+def test_odd_k_batches_reach_the_tensor_cores_through_the_expansion(t):
+    """K = 160 is not a whole number of 128-wide K steps, so the TMA kernels cannot take it; the batch then expands the weights to
+    fp16 once and runs the F16 kernel instead of 24 GEMV column passes.  The fp16 operand rounding (error well above the GEMV
+    path's 2e-6, well below the 1e-3 contract) shows which path ran."""
+    rng = np.random.default_rng(900 + t)
+    M, K, Nn = 200, 160, 24
+    W = weights(rng, M, K)
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    wb = orc.encode_weights(t, W)
+    got = dev_mul_mat(t, wb, M, K, X)
+    err = rel_l2(got, orc.mul_mat_2d(t, wb, M, K, X, nth=4))
+    assert 1e-5 < err <= 1e-3, err
