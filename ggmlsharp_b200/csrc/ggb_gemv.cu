@@ -648,6 +648,7 @@ extern template int launch_gemv_typed_sib<GGB_SMALL_BATCH_NODES>(const GemvBatch
 extern template int launch_gemv_typed_sib<GGB_MAX_BATCH_NODES>(const GemvBatchT<GGB_MAX_BATCH_NODES> &, size_t, int, cudaStream_t, bool);
 
 int gemv_num_ctas() { return device_sm_count(); }
+int64_t gemv_x_budget() { return X_BUDGET + 32 * 1024; }
 int gemv_group_rows(const GemvHdr &b) { return b.async ? NWF * b.rs : b.rs; }
 static int unit_bytes_async(int type)
 {
@@ -668,7 +669,7 @@ int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const vo
     if (K <= 0 || K % blck) return set_error(GGB_E_INVALID, "mul_mat: ne00=%lld is not a multiple of the block size %d (Ggml.cs:6694)", (long long)K, blck);
     const long long row_bytes = (long long)(K / blck) * (long long)type_size(type);
     const long long xcol = (long long)act_row_bytes(type, K);
-    if (row_bytes > (1ll << 30) || xcol * ncols > X_BUDGET + 32 * 1024)
+    if (row_bytes > (1ll << 30) || xcol * ncols > gemv_x_budget())
         return set_error(GGB_E_UNSUPPORTED, "mul_mat: K=%lld too large for the shared-memory resident activation vector", (long long)K);
     b.type = type; b.ncols = ncols; b.K = (int)K; b.row_bytes = (int)row_bytes; b.nb01 = nb01; b.xcol_bytes = (int)xcol;
     const int unit_async = unit_bytes_async(type);

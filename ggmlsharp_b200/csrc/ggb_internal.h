@@ -103,6 +103,7 @@ int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const vo
 int gemv_act_bps(const GemvHdr &b);
 int gemv_group_rows(const GemvHdr &b);  // weight rows per work group (tile) of the planned kernel   // the ActBatch::bps the planned kernel expects
 int gemv_num_ctas();
+int64_t gemv_x_budget();             // bytes of staged activation columns one GEMV pass may keep in shared memory
 
 // ---- GEMM (ggb_gemm.cu): tcgen05 batched path ----
 struct GemmArgs {

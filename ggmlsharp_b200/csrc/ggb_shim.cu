@@ -286,9 +286,16 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         // column passes of 8/4/2/1, grouped by what must be uniform inside one launch
         struct Pass { int i, col0, nc; };
         std::vector<Pass> passes;
+        // ... as many columns per pass as fit beside the weight stages in shared memory (K = 11008: 4 Q8P columns, 2 fp16, 2 fp32)
+        int nc_cap = 8;
+        while (nc_cap > 1 && (int64_t)arow * nc_cap > gemv_x_budget()) nc_cap >>= 1;
         for (int i : grp) {
             int64_t c = 0;
-            while (c < mm[i].N) { int nc = mm[i].N - c >= 8 ? 8 : mm[i].N - c >= 4 ? 4 : mm[i].N - c >= 2 ? 2 : 1; passes.push_back({i, (int)c, nc}); c += nc; }
+            while (c < mm[i].N) {
+                int nc = mm[i].N - c >= 8 ? 8 : mm[i].N - c >= 4 ? 4 : mm[i].N - c >= 2 ? 2 : 1;
+                if (nc > nc_cap) nc = nc_cap;
+                passes.push_back({i, (int)c, nc}); c += nc;
+            }
         }
         std::vector<char> pdone(passes.size(), 0);
         bool first_launch = true;

@@ -183,6 +183,7 @@ SHAPES = [
     (1, 32, 1), (3, 64, 1), (130, 96, 1),          # tiny / ragged: rows shorter than one copy
     (257, 4128, 1),       # 129 blocks per row: Q4_0 rows are not 16-byte multiples -> plain-load staging
     (512, 2048, 2), (300, 1024, 3), (64, 4096, 7), (96, 512, 8), (40, 256, 13), (128, 1024, 15),
+    (64, 11008, 9), (48, 11008, 15),     # long rows x several tokens: eight activation columns no longer fit in shared memory -> narrower passes
 ]
 
 

@@ -106,7 +106,7 @@ SHAPES = [
     (4096, 11008, 1),     # cfg 2: w2 (rows chunked)
     (1, 32, 1), (3, 64, 1), (130, 96, 1), (77, 160, 1),     # rows that are not whole units -> plain-load staging
     (257, 4128, 1),
-    (512, 2048, 2), (300, 1024, 3), (64, 4096, 7), (96, 512, 8), (40, 256, 13), (128, 1024, 15),
+    (512, 2048, 2), (300, 1024, 3), (64, 4096, 7), (96, 512, 8), (40, 256, 13), (128, 1024, 15), (48, 11008, 15),
 ]
 
 
