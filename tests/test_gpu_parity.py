@@ -431,3 +431,19 @@ def test_peer_exchange_degenerates_cleanly_on_one_rank():
         assert flags[0] == 3                     # the last writer was barrier() with host epoch 3; push_barrier used device epochs 1..3
     finally:
         sym.close()
+
+
+def test_longest_rows_that_fit_and_the_first_that_does_not():
+    """One activation row has to sit in shared memory next to the weight stages (README: known limits)."""
+    rng = np.random.default_rng(91)
+    for t, K in ((N.F32, 24576), (N.F16, 49152), (N.Q4_0, 65536), (N.Q5_0, 65536)):
+        M = 5
+        W = weights(rng, M, K)
+        x = rng.standard_normal((1, K)).astype(np.float32)
+        wb = orc.encode_weights(t, W)
+        err = rel_l2(dev_mul_mat(t, wb, M, K, x), orc.mul_mat_2d(t, wb, M, K, x))
+        assert err <= (1e-5 if t == N.F32 else 6e-6), (t, K, err)
+    wb = np.zeros((2, 4 * 24608), dtype=np.uint8)
+    with pytest.raises(N.GgbError) as e:
+        dev_mul_mat(N.F32, wb, 2, 24608, np.zeros((1, 24608), np.float32))
+    assert e.value.code == N.E_UNSUPPORTED
