@@ -18,6 +18,7 @@
 #include "ggb_tc.cuh"
 
 #include <algorithm>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 
@@ -41,14 +42,28 @@ using GemmGroup = GemmGroupT<GGB_GEMM_GROUP_NODES>;
 constexpr int SMALL_GROUP = 8;
 static_assert(sizeof(GemmGroup) <= 32000, "kernel parameter space");
 
-template <int TYPE, int CAP>
+// BN = 128: two issuer warps (even / odd K steps) with a 128-column accumulator each, as in k_gemm_q.
+// BN = 256: every dequantized A stage (and every raw byte) is reused for twice the columns, and one m256n256k16 instruction keeps
+// the tensor pipe busy for ~128 cycles, so ONE issuer thread is enough (a thread that also waits and commits issues an MMA per
+// ~125 cycles, profiles/r01_mma_rate.txt) and the single 256-column accumulator takes the TMEM the two half-width ones had.
+template <int BN, int RAW_ROW> struct GroupedCfg {
+    static constexpr int NISSUE = BN == 256 ? 1 : 2;
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;
+    // raw ring: a multiple of the 4 dequant groups (see ggb_gemm.cu); 8 stages unless shared memory runs out (Q8_0 with 32 KB B stages)
+    static constexpr int RAW_STAGES = (1024 + 4 * B_BYTES + 8 * BM * RAW_ROW + 64 * 8 + 16 <= 227 * 1024) ? 8 : 4;
+    static constexpr size_t SMEM = 1024 + (size_t)4 * B_BYTES + (size_t)RAW_STAGES * (BM * RAW_ROW) + 64 * 8 + 16;
+};
+
+template <int TYPE, int CAP, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_constant__ GemmGroupT<CAP> G)
 {
-    constexpr int BN = 128, BNL = 64;
+    constexpr int BNL = BN / 2;
     constexpr int RAW_ROW = RawRow<TYPE>::BYTES;
+    using Cfg = GroupedCfg<BN, RAW_ROW>;
+    constexpr int NISSUE = Cfg::NISSUE;
     constexpr int RAW_BYTES = BM * RAW_ROW, B_BYTES = BNL * BK * 2;
-    constexpr int RAW_STAGES = 8, A_STAGES = 4;               // raw ring: a multiple of the 4 dequant groups (see ggb_gemm.cu)
-    constexpr int TMEM_COLS = 512, A_COL0 = 2 * BN;           // [0,128) even-K acc, [128,256) odd-K acc, then 4 x 64 columns of A stages
+    constexpr int RAW_STAGES = Cfg::RAW_STAGES, A_STAGES = 4;
+    constexpr int TMEM_COLS = 512, A_COL0 = NISSUE * BN;      // [0,256): one 256-column accumulator or the even-K / odd-K pair; then 4 x 64 columns of A stages
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -60,6 +75,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + NBARS);
     auto BAR = [&](int i) { return bar0 + 8 * i; };
     auto LBAR = [&](int i) { return mapa_u32(BAR(i), 0); };   // the same barrier in the leader CTA
+    constexpr int RAW_SH = RAW_STAGES == 8 ? 3 : 2;           // log2(RAW_STAGES): phase = (gk >> RAW_SH) & 1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -69,7 +85,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
     if (threadIdx.x == 0) {
         for (int i = 0; i < RAW_STAGES; i++) { mbar_init(BAR(RAW_FULL + i), 1); mbar_init(BAR(RAW_EMPTY + i), 4); }
         for (int i = 0; i < A_STAGES; i++) { mbar_init(BAR(A_FULL + i), 4 * 2 + 2); mbar_init(BAR(A_EMPTY + i), 1); }
-        mbar_init(BAR(ACC_FULL), 2);
+        mbar_init(BAR(ACC_FULL), NISSUE);
         mbar_init(BAR(ACC_EMPTY), 2 * NDQ_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -103,7 +119,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                 const Tile tl = locate(t);
                 for (int ks = 0; ks < tl.ksteps; ks++, gk++) {
                     const int s = gk & (RAW_STAGES - 1);
-                    mbar_wait(BAR(RAW_EMPTY + s), ((gk >> 3) & 1) ^ 1);
+                    mbar_wait(BAR(RAW_EMPTY + s), ((gk >> RAW_SH) & 1) ^ 1);
                     mbar_expect_tx(BAR(RAW_FULL + s), RAW_BYTES);
                     tma_load_2d(smem_u32(sRaw + s * RAW_BYTES), &tl.nd->map_w, BAR(RAW_FULL + s), RawRow<TYPE>::box_x(ks), tl.m0);
                 }
@@ -128,8 +144,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
             }
         }
     } else if (warp == 1 || warp == 3) {
-        // ===== MMA issuers (leader CTA): even / odd K steps of every tile, own accumulator each =====
-        if (leader && lane == 0) {
+        // ===== MMA issuers (leader CTA): even / odd K steps of every tile, own accumulator each (BN = 256: warp 1 alone) =====
+        if (leader && lane == 0 && (NISSUE == 2 || warp == 1)) {
             const int me = warp >> 1;
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * 2) >> 4) << 24);
             const uint32_t acc = tmem + (uint32_t)(me * BN);
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
             for (int t = pair; t < G.total_tiles; t += npairs, it++) {
                 const Tile tl = locate(t);
                 if (it) { mbar_wait(BAR(ACC_EMPTY), (it - 1) & 1); tc_fence_after(); }    // both CTAs have drained the previous tile's accumulators
-                for (int ks = me; ks < tl.ksteps; ks += 2) {
+                for (int ks = me; ks < tl.ksteps; ks += NISSUE) {
                     const uint32_t gk = gk0 + (uint32_t)ks;
                     const int g = gk & 3;
                     mbar_wait(BAR(A_FULL + g), (gk >> 2) & 1);           // A rows in TMEM (both CTAs) + both halves of the B tile
@@ -147,7 +163,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                     const uint32_t a_base = tmem + A_COL0 + g * 64;
 #pragma unroll
                     for (int k = 0; k < BK / 16; k++)
-                        tc_mma_f16_ts(acc, a_base + k * 8, bd0 + (uint64_t)(((k >> 2) * (BNL * 128) + (k & 3) * 32) >> 4), idesc, (ks >= 2) || k != 0, true);
+                        tc_mma_f16_ts(acc, a_base + k * 8, bd0 + (uint64_t)(((k >> 2) * (BNL * 128) + (k & 3) * 32) >> 4), idesc, (ks >= NISSUE) || k != 0, true);
                     tc_commit_cg2(BAR(A_EMPTY + g));                      // frees TMEM stage g and B stage g in both CTAs
                 }
                 tc_commit_cg2(BAR(ACC_FULL));
@@ -169,7 +185,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
             for (int ks = (int)((g - gk0) & 3); ks < tl.ksteps; ks += 4) {
                 const uint32_t gk = gk0 + (uint32_t)ks;
                 const int s = gk & (RAW_STAGES - 1);
-                mbar_wait(BAR(RAW_FULL + s), (gk >> 3) & 1);
+                mbar_wait(BAR(RAW_FULL + s), (gk >> RAW_SH) & 1);
                 uint32_t w[RAW_ROW / 4];
                 load_raw_row<TYPE>(raw_row + (uint32_t)(s * RAW_BYTES), ks, w);
                 // the raw stage is released only after the dequant below has CONSUMED these registers (ggb_gemm.cu)
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
             tc_fence_after();
             const GroupNode &nd = *tl.nd;
             const int m = tl.m0 + q * 32 + lane;
-            const bool two = tl.ksteps > 1;
+            const bool two = NISSUE == 2 && tl.ksteps > 1;
 #pragma unroll 1
             for (int cb = g; cb < BN / 32; cb += NDQ_WARPS / 4) {
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
@@ -212,7 +228,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                                    "=r"(ARR[8]), "=r"(ARR[9]), "=r"(ARR[10]), "=r"(ARR[11]), "=r"(ARR[12]), "=r"(ARR[13]), "=r"(ARR[14]), "=r"(ARR[15]) \
                                  : "r"(ADDR) : "memory")
                     GGB_TMEM_LD16(v, taddr + (uint32_t)(hc * 16));
-                    GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
+                    if (NISSUE == 2) GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
 #undef GGB_TMEM_LD16
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (m < nd.M) {
@@ -399,15 +415,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_c
 }
 
 
-template <int TYPE, int CAP>
+template <int TYPE, int CAP, int BN = 128>
 int launch_grouped(const GemmGroupT<CAP> &G, cudaStream_t s)
 {
     constexpr int RAW_ROW = RawRow<TYPE>::BYTES;
     constexpr size_t smem = TYPE == GGML_TYPE_F16 ? 1024 + (size_t)4 * (BM * BK * 2) + (size_t)4 * (64 * BK * 2) + 64 * 8 + 16
-                                                  : 1024 + (size_t)4 * (64 * BK * 2) + (size_t)8 * (BM * RAW_ROW) + 64 * 8 + 16;
+                                                  : GroupedCfg<BN, RAW_ROW>::SMEM;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     void (*kern)(const GemmGroupT<CAP>) = nullptr;
-    if constexpr (TYPE == GGML_TYPE_F16) kern = k_gemm_f16_grouped<CAP>; else kern = k_gemm_q_grouped<TYPE, CAP>;
+    if constexpr (TYPE == GGML_TYPE_F16) kern = k_gemm_f16_grouped<CAP>; else kern = k_gemm_q_grouped<TYPE, CAP, BN>;
     static bool attr_set = false;
     if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     cudaLaunchConfig_t cfg = {};
@@ -451,6 +467,28 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
     static thread_local GemmGroup G;                                   // ~25 KB: kept off the stack
     const int type = args[0].type;
     G.n_nodes = count; G.total_tiles = 0;
+    // Quantized weights: 256-column tiles halve the dequant work and the weight traffic per flop (a K step of a 256-wide tile costs
+    // ~1.78x a 128-wide one, measured on cfg 4: 986 -> 1 074 TFLOP/s), but they also halve the number of tiles, and the static
+    // round-robin deal makes the slowest pair the launch time (cfg 3 batch of 8: 512 tiles = 6.9 rounds of 74 pairs, 256 tiles = 3.5
+    // -> 4 rounds).  So both tilings are dealt out on paper -- K steps plus an epilogue per tile, in units of a 128-wide K step --
+    // and the cheaper one is launched.
+    int bn = 128;
+    if (type != GGML_TYPE_F16) {
+        static const int pairs_est = [] { int p = std::max(1, device_sm_count() / 2); if (const char *e = getenv("GGB200_GEMM_PAIRS")) p = std::max(1, std::min(p, atoi(e))); return p; }();
+        auto dealt = [&](int tile_n, double kstep_cost, double epi_cost) {
+            std::vector<double> load((size_t)pairs_est, 0.0);
+            long long t = 0;
+            for (int i = 0; i < count; i++) {
+                const long long tiles = ((args[i].M + 2 * BM - 1) / (2 * BM)) * ((args[i].N + tile_n - 1) / tile_n);
+                const double per_tile = (double)((args[i].K + BK - 1) / BK) * kstep_cost + epi_cost;
+                for (long long k = 0; k < tiles; k++, t++) load[(size_t)(t % pairs_est)] += per_tile;
+            }
+            return *std::max_element(load.begin(), load.end());
+        };
+        if (dealt(256, 1.78, 13.0) < dealt(128, 1.0, 6.5)) bn = 256;
+        static const int force = [] { const char *e = getenv("GGB200_GEMM_BN"); return e ? atoi(e) : 0; }();
+        if (force == 128 || force == 256) bn = force;
+    }
     for (int i = 0; i < count; i++) {
         const GemmArgs &a = args[i];
         if (a.type != type) return set_error(GGB_E_INVALID, "grouped GEMM: mixed weight types in one group");
@@ -465,10 +503,10 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
             rc = make_map_2d(&nd.map_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, a.W, row_bytes, (uint64_t)a.M, (uint64_t)a.nb01, (uint32_t)raw_row, BM, CU_TENSOR_MAP_SWIZZLE_NONE);
         }
         if (rc) return rc;
-        rc = make_map_2d(&nd.map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+        rc = make_map_2d(&nd.map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.Xh, (uint64_t)a.K, (uint64_t)a.Npad, (uint64_t)a.K * 2, 64, (uint32_t)(bn / 2), CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
         nd.Y = a.Y; nd.ldy = a.ldy; nd.M = (int)a.M; nd.N = (int)a.N; nd.ksteps = (int)((a.K + BK - 1) / BK);
-        nd.nt = (int)((a.N + 127) / 128);
+        nd.nt = (int)((a.N + bn - 1) / bn);
         const int mt = (int)((a.M + 2 * BM - 1) / (2 * BM));
         nd.tile0 = G.total_tiles; nd.tile_end = nd.tile0 + mt * nd.nt;
         G.total_tiles = nd.tile_end;
@@ -476,29 +514,25 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
         for (int p = 0; p < a.n_peers; p++) nd.peer_delta[p] = (long long)(reinterpret_cast<char *>(a.ypeer[p]) - reinterpret_cast<char *>(a.Y));
     }
     if (G.total_tiles == 0) return GGB_OK;
+#define GGB_GROUPED_Q(CAPV, GV) \
+    switch (type) { \
+    case GGML_TYPE_Q4_0: return bn == 256 ? launch_grouped<GGML_TYPE_Q4_0, CAPV, 256>(GV, s) : launch_grouped<GGML_TYPE_Q4_0, CAPV, 128>(GV, s); \
+    case GGML_TYPE_Q4_1: return bn == 256 ? launch_grouped<GGML_TYPE_Q4_1, CAPV, 256>(GV, s) : launch_grouped<GGML_TYPE_Q4_1, CAPV, 128>(GV, s); \
+    case GGML_TYPE_Q4_2: return bn == 256 ? launch_grouped<GGML_TYPE_Q4_2, CAPV, 256>(GV, s) : launch_grouped<GGML_TYPE_Q4_2, CAPV, 128>(GV, s); \
+    case GGML_TYPE_Q8_0: return bn == 256 ? launch_grouped<GGML_TYPE_Q8_0, CAPV, 256>(GV, s) : launch_grouped<GGML_TYPE_Q8_0, CAPV, 128>(GV, s); \
+    case GGML_TYPE_Q5_0: return bn == 256 ? launch_grouped<GGML_TYPE_Q5_0, CAPV, 256>(GV, s) : launch_grouped<GGML_TYPE_Q5_0, CAPV, 128>(GV, s); \
+    default:             return bn == 256 ? launch_grouped<GGML_TYPE_Q5_1, CAPV, 256>(GV, s) : launch_grouped<GGML_TYPE_Q5_1, CAPV, 128>(GV, s); \
+    }
     if (count <= SMALL_GROUP) {
         static thread_local GemmGroupT<SMALL_GROUP> S;
         S.n_nodes = G.n_nodes; S.total_tiles = G.total_tiles;
         for (int i = 0; i < count; i++) S.node[i] = G.node[i];
         if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16, SMALL_GROUP>(S, s);
-        switch (type) {
-        case GGML_TYPE_Q4_0: return launch_grouped<GGML_TYPE_Q4_0, SMALL_GROUP>(S, s);
-        case GGML_TYPE_Q4_1: return launch_grouped<GGML_TYPE_Q4_1, SMALL_GROUP>(S, s);
-        case GGML_TYPE_Q4_2: return launch_grouped<GGML_TYPE_Q4_2, SMALL_GROUP>(S, s);
-        case GGML_TYPE_Q8_0: return launch_grouped<GGML_TYPE_Q8_0, SMALL_GROUP>(S, s);
-        case GGML_TYPE_Q5_0: return launch_grouped<GGML_TYPE_Q5_0, SMALL_GROUP>(S, s);
-        default: return launch_grouped<GGML_TYPE_Q5_1, SMALL_GROUP>(S, s);
-        }
+        GGB_GROUPED_Q(SMALL_GROUP, S)
     }
     if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16, GGB_GEMM_GROUP_NODES>(G, s);
-    switch (type) {
-    case GGML_TYPE_Q4_0: return launch_grouped<GGML_TYPE_Q4_0, GGB_GEMM_GROUP_NODES>(G, s);
-    case GGML_TYPE_Q4_1: return launch_grouped<GGML_TYPE_Q4_1, GGB_GEMM_GROUP_NODES>(G, s);
-    case GGML_TYPE_Q4_2: return launch_grouped<GGML_TYPE_Q4_2, GGB_GEMM_GROUP_NODES>(G, s);
-    case GGML_TYPE_Q8_0: return launch_grouped<GGML_TYPE_Q8_0, GGB_GEMM_GROUP_NODES>(G, s);
-    case GGML_TYPE_Q5_0: return launch_grouped<GGML_TYPE_Q5_0, GGB_GEMM_GROUP_NODES>(G, s);
-    default: return launch_grouped<GGML_TYPE_Q5_1, GGB_GEMM_GROUP_NODES>(G, s);
-    }
+    GGB_GROUPED_Q(GGB_GEMM_GROUP_NODES, G)
+#undef GGB_GROUPED_Q
 }
 
 } // namespace ggb

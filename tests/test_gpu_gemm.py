@@ -159,7 +159,9 @@ def test_grouped_gemm_batch_vs_oracle(t):
         err = rel_l2(y, want)
         assert err <= GEMM_TIGHT[t], (t, M, K, X.shape[0], err)
         alone = dev_mul_mat(tt, wb, M, K, X)
-        assert rel_l2(y, alone) <= 1e-6, (t, M, K, X.shape[0])
+        # same fp16 operands; only the fp32 accumulation order may differ (256-column tiles keep ONE accumulator over all K steps,
+        # the per-node kernel adds an even-K and an odd-K one)
+        assert rel_l2(y, alone) <= 5e-6, (t, M, K, X.shape[0])
 
 
 def test_grouped_gemm_mixed_batch_and_rerun():
