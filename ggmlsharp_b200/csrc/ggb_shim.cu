@@ -139,12 +139,10 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     if (off[count] && (reinterpret_cast<uintptr_t>(ws) & 255)) return set_error(GGB_E_INVALID, "mul_mat: workspace must be 256-byte aligned");
     uint8_t *wsb = static_cast<uint8_t *>(ws);
 
-    // ---- batched (tensor-core) nodes: act(i), gemm(i) interleaved.  Every kernel is launched programmatically dependent on
-    //      its predecessor and the GEMM triggers its dependents as soon as it is set up, so the activation staging of node
-    //      i+1 runs on the SMs WHILE node i's GEMM streams -- nodes of one batch are independent by contract and write
-    //      disjoint workspace regions, so only the first activation kernel has to wait for earlier work in the stream ----
+    // ---- batched (tensor-core) nodes.  Every kernel is launched programmatically dependent on its predecessor; a GEMM starts its
+    //      prologue and its weight streaming while the activation kernel in front of it still runs, and waits for it only before
+    //      the first activation tile.  Activation kernels wait at their start for everything before them (see below) ----
     std::vector<int> gemv_idx;
-    bool first_gemm = true;
     static const bool grouped = [] { const char *e = getenv("GGB200_GEMM_GROUPED"); return !e || atoi(e) != 0; }();
     constexpr int NSLOT = 8;                                      // one grouped launch sequence per kernel flavour
     static const int slot_type[NSLOT] = {GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, GGML_TYPE_F16, GGML_TYPE_F16 /* expanded siblings */, GGML_TYPE_Q4_2, GGML_TYPE_Q5_1, GGML_TYPE_Q8_0, GGML_TYPE_Q5_0};
@@ -177,9 +175,8 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         const void *Wg = m.W; int64_t nb01g = m.nb01;
         int rc = sibx ? expand(i, Wg, nb01g) : GGB_OK;
         if (rc) return rc;
-        rc = launch_act_f16_dequant(m.type, gemm_act_perm(gtype), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s, first_gemm, !sibx);
+        rc = launch_act_f16_dequant(m.type, gemm_act_perm(gtype), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s, true);   // waits for whatever produced X
         if (rc) return rc;
-        first_gemm = false;
         GemmArgs a = {};
         a.type = gtype; a.M = m.M; a.K = m.K; a.N = m.N; a.W = Wg; a.nb01 = nb01g; a.Xh = xh; a.Npad = Npad;
         a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
@@ -194,15 +191,24 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     // node's buffer is staged, the others point their B operand at it.  Keyed by what decides the staged bytes.
     struct StagedX { const float *X; int64_t ldx, N, K; int cls; __half *xh; };
     std::vector<StagedX> staged;
+    // Launch order: the activation kernels of ALL groups first, then the GEMMs.  Every activation kernel waits at its start
+    // (griddepcontrol.wait): the first for whatever produced the activations, each later one for its predecessor -- so when the
+    // last one is complete, all are.  (They used to be interleaved, act(g) GEMM(g) act(g+1) ..., with only the first one waiting:
+    // a later one, launched programmatically dependent on a GEMM that triggers its dependents at start-up, could then read
+    // activations an earlier graph level was still writing.  tests/test_gpu_graph_fuzz.py caught it as a rare wrong result.)
+    struct PendingGroup { std::vector<GemmArgs> ga; };
+    std::vector<PendingGroup> pending;
     for (int qi = 0; qi < NSLOT; qi++) {
         const std::vector<int> &qn = q_nodes[qi];
         for (size_t c0 = 0; c0 < qn.size(); c0 += GGB_GEMM_GROUP_NODES) {
             const int cnt = (int)std::min(qn.size() - c0, (size_t)GGB_GEMM_GROUP_NODES);
             static thread_local ActGemmBatch ab;
-            static thread_local GemmArgs ga[GGB_GEMM_GROUP_NODES];
+            pending.emplace_back();
+            std::vector<GemmArgs> &ga = pending.back().ga;
+            ga.resize((size_t)cnt);
             const int type = slot_type[qi];                                                             // slot 3: expanded siblings run the F16 kernel
             // slot 3 stages activations as d*q (any quantized wtype selects that), in the F16 kernel's natural K order
-            ab.n_nodes = 0; ab.wtype = qi == 3 ? GGML_TYPE_Q8_0 : type; ab.perm = gemm_act_perm(type); ab.wait_prior = first_gemm ? 1 : 0;
+            ab.n_nodes = 0; ab.wtype = qi == 3 ? GGML_TYPE_Q8_0 : type; ab.perm = gemm_act_perm(type); ab.wait_prior = 1;
             const int cls = ab.wtype == GGML_TYPE_F16 ? 2 : ab.perm;      // (Half)x | d*q in natural K order | d*q in the nibble-unpack order
             for (int c = 0; c < cnt; c++) {
                 const int i = qn[c0 + c];
@@ -216,19 +222,21 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
                     ab.node[ab.n_nodes++] = ActGemmNode{m.X, (long long)m.ldx_bytes, xh, (int)m.N, (int)Npad, (int)m.K, 0};
                     staged.push_back(StagedX{m.X, m.ldx_bytes, m.N, m.K, cls, xh});
                 }
-                GemmArgs &a = ga[c];
+                GemmArgs &a = ga[(size_t)c];
                 a = GemmArgs{};
                 a.type = type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
                 a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
                 for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
-                if (qi == 3) { int rce = expand(i, a.W, a.nb01); if (rce) return rce; }
+                if (qi == 3) { int rce = expand(i, a.W, a.nb01); if (rce) return rce; }      // an ordinary launch: a full barrier in the stream
             }
-            int rc = launch_act_f16_dequant_batch(ab, s, qi != 3);     // no-op when every node of the group reuses staged activations
-            if (rc) return rc;
-            if (ab.n_nodes) first_gemm = false;
-            { KernelTimer kt(s); rc = launch_gemm_grouped(ga, cnt, s); }
+            int rc = launch_act_f16_dequant_batch(ab, s);               // no-op when every node of the group reuses staged activations
             if (rc) return rc;
         }
+    }
+    for (PendingGroup &pg : pending) {
+        int rc;
+        { KernelTimer kt(s); rc = launch_gemm_grouped(pg.ga.data(), (int)pg.ga.size(), s); }
+        if (rc) return rc;
     }
 
     // ---- single-token nodes: group by (type, K), fuse each group into one act launch + GEMV launches ----

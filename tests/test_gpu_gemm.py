@@ -3,6 +3,8 @@
 Bar: rel-L2 <= 1e-3 for Q4_0 / Q4_1 / F16 weights.  Expected error: activations enter as fp16(d1*q) and Q4 weights
 as fp16(d0*(q-8)) (two ~2^-12 roundings), products exact, fp32 accumulation -> ~3e-4..5e-4 for Q4, ~1e-6 for F16
 (whose activations the reference itself rounds to Half)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -233,3 +235,37 @@ def test_odd_k_batches_reach_the_tensor_cores_through_the_expansion(t):
     got = dev_mul_mat(t, wb, M, K, X)
     err = rel_l2(got, orc.mul_mat_2d(t, wb, M, K, X, nth=4))
     assert 1e-5 < err <= 1e-3, err
+
+
+def test_two_weight_types_consuming_a_fresh_intermediate():
+    """Regression for a launch-ordering race (found by tests/test_gpu_graph_fuzz.py as a rare wrong result): a graph level whose
+    batched nodes have DIFFERENT weight types launches one activation kernel per type; the later ones used to be launched behind a
+    GEMM that releases its dependents at start-up, without waiting themselves, and could read the previous level's output while it
+    was still being written.  A large producer makes the window wide; every run must reproduce the same bits and match the oracle."""
+    from ggmlsharp_b200 import ggml
+    rng = np.random.default_rng(77)
+    Nn, K0, M0, M1 = 64, 1024, 4096, 256
+    x = rng.standard_normal((Nn, K0)).astype(np.float32)
+    w0 = orc.encode_weights(N.Q4_0, weights(rng, M0, K0))
+    w1 = orc.encode_weights(N.F16, weights(rng, M1, M0))
+    w2 = orc.encode_weights(N.Q4_1, weights(rng, M1, M0))
+    w3 = orc.encode_weights(N.Q8_0, weights(rng, M1, M0))
+    first = None
+    with ggml.Context(256 << 20) as c:
+        tx = c.tensor_from(N.F32, K0, Nn, data=x)
+        n0 = c.mul_mat(c.tensor_from(N.Q4_0, K0, M0, data=w0), tx)
+        outs = [c.mul_mat(c.tensor_from(t, M0, M1, data=w), n0) for t, w in ((N.F16, w1), (N.Q4_1, w2), (N.Q8_0, w3))]
+        g = c.build_forward(outs[0])
+        for o in outs[1:]:
+            N.host().ggml_build_forward_expand(C.byref(g), o)
+        for rep in range(25):
+            c.graph_compute(g)
+            got = [ggml.tensor_f32(o).reshape(Nn, M1).copy() for o in outs]
+            y0 = ggml.tensor_f32(n0).reshape(Nn, M0).copy()
+            if first is None:
+                first = got
+                for t, w, y in zip((N.F16, N.Q4_1, N.Q8_0), (w1, w2, w3), got):
+                    assert rel_l2(y, orc.mul_mat_2d(t, w, M1, M0, y0, nth=8)) <= 1e-3       # like with like: the device's own n0
+            else:
+                for a, b in zip(first, got):
+                    assert np.array_equal(a, b), rep
