@@ -151,9 +151,9 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         if (use_gemm_expanded(m)) return 3;
         switch (m.type) { case GGML_TYPE_Q4_0: return 0; case GGML_TYPE_Q4_1: return 1; case GGML_TYPE_Q4_2: return 4; case GGML_TYPE_Q5_1: return 5; case GGML_TYPE_Q8_0: return 6; case GGML_TYPE_Q5_0: return 7; default: return 2; }
     };
-    // a sibling-format node: expand the weights behind the activation buffer of its workspace slice and hand the GEMM an F16 node.
-    // The expansion is an ordinary (fully stream-ordered) launch and the activation kernel that follows it is launched WITHOUT
-    // programmatic serialization, so the GEMM -- whose weight TMA does not wait for anything -- cannot start before it is complete.
+    // a node whose shape the TMA kernels cannot take: expand the weights behind the activation buffer of its workspace slice and hand
+    // the GEMM an F16 node.  The expansion is an ordinary (fully stream-ordered) launch that never releases its dependents early, so
+    // nothing behind it in the stream -- in particular a GEMM, whose weight TMA does not wait for anything -- starts before it is complete.
     auto expand = [&](int i, const void *&Wout, int64_t &nb01_out) -> int {
         const ggb_dev_mm &m = mm[i];
         __half *wh = reinterpret_cast<__half *>(wsb + off[i] + align_up(gemm_workspace_bytes(GGML_TYPE_F16, m.M, m.K, m.N), 256));
@@ -185,8 +185,8 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         { KernelTimer kt(s); rc = launch_gemm(a, wsb + off[i] + align_up((size_t)Npad * m.K * 2, 256), s); }
         if (rc) return rc;
     }
-    // ---- Q4_0 / Q4_1 batched nodes: one activation launch + one persistent grouped GEMM launch per <= 64 nodes.  The GEMM
-    //      triggers its dependents at start-up, so the next group's activation staging overlaps it (ggb_gemm_grouped.cu) ----
+    // ---- two or more batched nodes: per weight type (kernel flavour) one activation launch + one persistent grouped GEMM launch
+    //      per <= 64 nodes (ggb_gemm_grouped.cu) ----
     // Nodes that multiply the SAME activations (wq / wk / wv of a layer, w1 / w3 of its FFN) share one staged copy: the first
     // node's buffer is staged, the others point their B operand at it.  Keyed by what decides the staged bytes.
     struct StagedX { const float *X; int64_t ldx, N, K; int cls; __half *xh; };
