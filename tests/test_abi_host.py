@@ -135,7 +135,8 @@ def test_planner_work_buffer_matches_reference_sizes():
     from oracle import pyoracle as orc
     if has_gpu():
         pytest.skip("covered by the GPU tests; here we only check the planner before the device call fails")
-    for t, ot in ((N.Q4_0, orc.Q4_0), (N.Q4_1, orc.Q4_1), (N.F16, orc.F16)):
+    for t, ot in ((N.Q4_0, orc.Q4_0), (N.Q4_1, orc.Q4_1), (N.F16, orc.F16),
+                  (N.Q4_2, orc.Q4_2), (N.Q5_0, orc.Q5_0), (N.Q5_1, orc.Q5_1), (N.Q8_0, orc.Q8_0)):      # vec_dot_type by TYPE (defect D1)
         with _ctx() as c:
             w = c.new_tensor(t, 64, 8)
             x = c.new_tensor(N.F32, 64, 3)
@@ -173,3 +174,15 @@ def test_neighbour_builders_follow_the_reference():
             c.op("scale", a, b)                                 # ggml_is_scalar
         g = c.build_forward(c.op("add", c.op("silu", ad), c.op("cont", c.op("transpose", ct))))
         assert [g.nodes[i].contents.op for i in range(g.n_nodes)] == [N.OP_ADD, N.OP_SILU, N.OP_TRANSPOSE, N.OP_CONT, N.OP_TRANSPOSE, N.OP_CONT, N.OP_ADD]
+
+
+def test_sibling_block_layouts_in_the_host_mirror():
+    # TypeDefinitions.cs:249-282 and Ggml.cs:55-87: block sizes / bytes of the sibling formats, and the row stride rule
+    host = N.host()
+    for t, blck, size in ((N.Q4_2, 16, 10), (N.Q5_0, 32, 22), (N.Q5_1, 32, 24), (N.Q8_0, 32, 36), (N.Q8_1, 32, 44)):
+        assert host.ggml_blck_size(t) == blck and host.ggml_type_size(t) == size
+        assert N.TYPE_SIZE[t] == size and N.BLCK_SIZE[t] == blck
+        with _ctx() as c:
+            w = c.new_tensor(t, 128, 6)
+            assert w.contents.nb[0] == size and w.contents.nb[1] == size * (128 // blck)
+            assert host.ggml_nbytes(w) == 6 * size * (128 // blck)
