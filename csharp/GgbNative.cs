@@ -10,8 +10,6 @@ internal static unsafe partial class GgbNative
 {
     const string Lib = "ggb200";   // libggb200.so next to the application
 
-    public const int GGB_GRAPH_KEEP_ON_DEVICE = 1, GGB_GRAPH_NO_WEIGHT_CACHE = 2;
-
     [DllImport(Lib)] public static extern IntPtr ggb_last_error();
     [DllImport(Lib)] public static extern int ggb_abi_check(int sizeofTensor, int offsetofData, int sizeofCgraph, int offsetofNodes, int sizeofQ4_0, int sizeofQ4_1);
     [DllImport(Lib)] public static extern int ggb_init();
@@ -22,6 +20,9 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_tensor_invalidate(IntPtr pool, ggml_tensor* t);
     [DllImport(Lib)] public static extern int ggb_mul_mat_node(IntPtr pool, ggml_tensor* dst);
     [DllImport(Lib)] public static extern int ggb_graph_compute_mul_mats(IntPtr pool, ggml_cgraph* graph, int flags, byte* done);
+    // type = (int)ggml_type.  Weights: F32, F16, Q4_0, Q4_1 and the sibling formats Q4_2, Q5_0, Q5_1, Q8_0; their fp16 block scales are
+    // IEEE bit patterns in memory -- declare block_q4_2.d and block_q5_1.d / .m as Half (as block_q5_0.d already is) instead of
+    // storing (ushort)(Half)d, which writes a rounded integer (Ggml.cs:577, 678-679).
     [DllImport(Lib)] public static extern int ggb_quantize_rows(int type, float* src, void* dst, long nrows, long k);
     [DllImport(Lib)] public static extern int ggb_dequantize_rows(int type, void* src, float* dst, long nrows, long k);
 
