@@ -38,6 +38,43 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_dev_cont(void* src, long* ne, ulong* nb, float* dst, IntPtr stream);
     [DllImport(Lib)] public static extern int ggb_dev_add_q(int type, void* src0, float* src1, void* dst, long nrows, long k, IntPtr stream);
 
+    // the rest of include/ggb200.h (used by benchmarks and by a caller that keeps tensors on the device itself)
+    [StructLayout(LayoutKind.Sequential)]
+    public struct ggb_dev_mm
+    {
+        public int type, n_peers; public long M, K, N;
+        public void* W; public long nb01; public float* X; public long ldx_bytes; public float* Y; public long ldy_bytes;
+        public float* Y_peer0, Y_peer1, Y_peer2, Y_peer3, Y_peer4, Y_peer5, Y_peer6;
+    }
+    [StructLayout(LayoutKind.Sequential)]
+    public struct ggb_stats
+    {
+        public ulong kernel_launches, h2d_bytes, d2h_bytes, weight_uploads, weight_cache_hits, nodes_executed;
+        public double last_graph_device_ms, timed_kernel_ms; public ulong timed_kernel_launches;
+    }
+    [DllImport(Lib)] public static extern int ggb_abi_version();
+    [DllImport(Lib)] public static extern int ggb_device_count(int* count);
+    [DllImport(Lib)] public static extern nuint ggb_dev_workspace_bytes(ggb_dev_mm* mm, int count);
+    [DllImport(Lib)] public static extern int ggb_dev_mul_mat_batch(ggb_dev_mm* mm, int count, void* workspace, nuint workspaceBytes, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_quantize_rows(int type, float* src, void* dst, long nrows, long k, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_dequantize_rows(int type, void* src, float* dst, long nrows, long k, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_alloc(nuint bytes, void** dptr);
+    [DllImport(Lib)] public static extern int ggb_dev_free(void* dptr);
+    [DllImport(Lib)] public static extern int ggb_dev_upload(void* dptr, void* host, nuint bytes);
+    [DllImport(Lib)] public static extern int ggb_dev_download(void* host, void* dptr, nuint bytes);
+    [DllImport(Lib)] public static extern int ggb_stream_sync(IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_set_kernel_timing(int on);
+    [DllImport(Lib)] public static extern int ggb_get_stats(ggb_stats* stats);
+    [DllImport(Lib)] public static extern int ggb_reset_stats();
+    // row split across the GPUs of one box (one process per GPU): CUDA-IPC export / open of the symmetric dst buffer and the
+    // exchange kernels; see ggmlsharp_b200/rowsplit.py for the call sequence
+    [DllImport(Lib)] public static extern int ggb_ipc_export(void* dptr, byte* handle64);
+    [DllImport(Lib)] public static extern int ggb_ipc_open(byte* handle64, void** dptr);
+    [DllImport(Lib)] public static extern int ggb_ipc_close(void* dptr);
+    [DllImport(Lib)] public static extern int ggb_peer_barrier(ulong** peerFlags, int rank, int world, ulong epoch, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_peer_push_barrier(void** peerBases, ulong** peerFlags, uint* counter, int rank, int world,
+                                                                   nuint segOffset, nuint segBytes, nuint segStride, int nSeg, ulong epoch, IntPtr stream);
+
     public static string LastError() => Marshal.PtrToStringUTF8(ggb_last_error()) ?? "";
 
     // ggml_context* -> ggb_pool*.  ggml_context itself (TypeDefinitions.cs:32-46) is left untouched.
