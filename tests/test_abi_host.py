@@ -186,3 +186,16 @@ def test_sibling_block_layouts_in_the_host_mirror():
             w = c.new_tensor(t, 128, 6)
             assert w.contents.nb[0] == size and w.contents.nb[1] == size * (128 // blck)
             assert host.ggml_nbytes(w) == 6 * size * (128 // blck)
+
+
+def test_csharp_stub_declares_every_header_entry_point():
+    # csharp/GgbNative.cs is the binding a GGMLSharp maintainer adds; it cannot be compiled here (no .NET), so at
+    # least its DllImport list is held to include/ggb200.h
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = set(re.findall(r"\b(ggb_[a-z0-9_]+)\s*\(", open(os.path.join(root, "include", "ggb200.h")).read()))
+    cs = open(os.path.join(root, "csharp", "GgbNative.cs")).read()
+    declared = set(re.findall(r"extern\s+[A-Za-z]+\s+(ggb_[a-z0-9_]+)\s*\(", cs))
+    assert hdr <= declared, sorted(hdr - declared)
+    assert declared <= hdr, sorted(declared - hdr)
+    assert len(re.findall(r"const int GGB_GRAPH_KEEP_ON_DEVICE", cs)) == 1          # a duplicate declaration does not compile
