@@ -95,6 +95,15 @@ typedef struct { float d; float m; uint8_t qs[16]; } block_q4_1;           /* 24
 /* TypeDefinitions.cs:277-290 -- activation blocks (quants are int8: SURVEY.md defect D4) */
 typedef struct { float d; int8_t qs[32]; } block_q8_0;                     /* 36 B */
 typedef struct { float d; float s0; float s1; int8_t qs[32]; } block_q8_1; /* 44 B */
+/* TypeDefinitions.cs:249-275 -- the sibling weight blocks.  d / m are IEEE binary16 BIT PATTERNS (the
+ * reference declares them ushort and stores a numeric cast, defect D9 in oracle/ggb_oracle.c; block_q5_0.d is a Half there);
+ * qh bit l is the fifth bit of element l; Q8_0 as a weight type is block_q8_0 above.  2-byte aligned, no padding. */
+typedef struct { uint16_t d; uint8_t qs[8]; } block_q4_2;                               /* 10 B per 16 elements */
+typedef struct { uint16_t d; uint8_t qh[4]; uint8_t qs[16]; } block_q5_0;               /* 22 B */
+typedef struct { uint16_t d; uint16_t m; uint8_t qh[4]; uint8_t qs[16]; } block_q5_1;   /* 24 B */
+typedef char ggb_assert_block_q4_2[sizeof(block_q4_2) == 10 ? 1 : -1];
+typedef char ggb_assert_block_q5_0[sizeof(block_q5_0) == 22 ? 1 : -1];
+typedef char ggb_assert_block_q5_1[sizeof(block_q5_1) == 24 ? 1 : -1];
 
 /* ---- status ------------------------------------------------------------------------ */
 
