@@ -268,3 +268,14 @@ def test_sibling_quantize_into_a_2_byte_aligned_destination(t):
             assert np.array_equal(got, want), (NAME[t], off)
     finally:
         d.close()
+
+
+@pytest.mark.parametrize("t", [N.Q4_0, N.Q4_2, N.Q5_0])
+def test_symmetric_formats_requantize_to_themselves_full_size(t):
+    """Size-independent property at the cfg 1 size, entirely on the device: quantize(dequantize(q)) == q for the symmetric formats
+    (the dequantized block's largest magnitude is exactly -8d / -16d)."""
+    rng = np.random.default_rng(23 + t)
+    W = weights(rng, 4096, 4096)
+    q = ggml.quantize_rows(t, W)
+    again = ggml.quantize_rows(t, ggml.dequantize_rows(t, q, 4096))
+    assert np.array_equal(q, again)

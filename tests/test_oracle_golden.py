@@ -192,3 +192,16 @@ def test_sibling_dot_equals_dequantized_dot(t, key):
     xd = orc.dequantize_rows(orc.Q8_0, orc.quantize_rows(orc.Q8_0, X), K).astype(np.float64)
     want = xd @ wd.T
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-6
+
+
+@pytest.mark.parametrize("t", [orc.Q4_0, orc.Q4_2, orc.Q5_0])
+def test_symmetric_formats_requantize_to_themselves(t):
+    """Size-independent property of the symmetric formats: the dequantized block's largest magnitude is exactly -8d (-16d), so
+    quantizing it again reproduces scale and quants bit for bit.  (Not true for Q4_1 / Q5_1 / Q8_0, whose scale is recomputed
+    from a rounded difference / product.)"""
+    rng = np.random.default_rng(17 + t)
+    x = np.concatenate([(rng.standard_normal((512, 256)) * s).astype(np.float32) for s in (0.02, 1.0, 300.0)])
+    x[0, :32] = 0
+    q = orc.quantize_rows(t, x)
+    again = orc.quantize_rows(t, orc.dequantize_rows(t, q, 256))
+    assert np.array_equal(q, again)
