@@ -415,6 +415,8 @@ def main():
     wq_host = Wq.cpu().numpy()
     x_host = X.cpu().numpy()
     with ggml.Context(arena) as c:
+        # weight residency is opt-in (include/ggb200.h: ggb_pool_set_weight_cache); the reference re-reads src0 on every compute
+        N.check(N.host().ggml_host_set_weight_cache(c.ctx, 1))
         ys, g = [], None
         for i in range(RING):
             a = c.tensor_from(N.Q4_0, K, M_LOCAL, data=wq_host[i])

@@ -18,8 +18,11 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_pool_adopt(void* hostBase, nuint bytes, IntPtr* pool);
     [DllImport(Lib)] public static extern int ggb_pool_free(IntPtr pool);
     [DllImport(Lib)] public static extern int ggb_tensor_invalidate(IntPtr pool, ggml_tensor* t);
+    // weight residency is opt-in: the reference re-reads src0->data on every compute, so the default re-uploads every leaf src0
+    [DllImport(Lib)] public static extern int ggb_pool_set_weight_cache(IntPtr pool, int on);
     [DllImport(Lib)] public static extern int ggb_mul_mat_node(IntPtr pool, ggml_tensor* dst);
     [DllImport(Lib)] public static extern int ggb_graph_compute_mul_mats(IntPtr pool, ggml_cgraph* graph, int flags, byte* done);
+    [DllImport(Lib)] public static extern int ggb_graph_plan(ggml_cgraph* graph, int flags, byte* done);
     // type = (int)ggml_type.  Weights: F32, F16, Q4_0, Q4_1 and the sibling formats Q4_2, Q5_0, Q5_1, Q8_0; their fp16 block scales are
     // IEEE bit patterns in memory -- declare block_q4_2.d and block_q5_1.d / .m as Half (as block_q5_0.d already is) instead of
     // storing (ushort)(Half)d, which writes a rounded integer (Ggml.cs:577, 678-679).
@@ -45,7 +48,10 @@ internal static unsafe partial class GgbNative
         public int type, n_peers; public long M, K, N;
         public void* W; public long nb01; public float* X; public long ldx_bytes; public float* Y; public long ldy_bytes;
         public float* Y_peer0, Y_peer1, Y_peer2, Y_peer3, Y_peer4, Y_peer5, Y_peer6;
+        public int* W_rowexp; public int flags, _pad;       // GGB_MM_W_IN_FLIGHT = 1
     }
+    public const int GGB_MM_W_IN_FLIGHT = 1;
+    [DllImport(Lib)] public static extern int ggb_dev_weight_rowexp(int type, void* W, long nb01, long M, long K, int* rowexp, IntPtr stream);
     [StructLayout(LayoutKind.Sequential)]
     public struct ggb_stats
     {

@@ -542,10 +542,66 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
 }
 
 // Batched (tensor-core) path: activations as fp16 values the reference's dot effectively multiplies by:
-// Q4_x weights -> d * round(x / d) of the Q8 block (same d, same quants as quantize_row_q8_x); F16 -> (Half)x.
-// Rows n >= N of the padded buffer are zero.  One thread per block of 32 elements (128 B in, 64 B out): the kernel is
-// a pure stream (12 B per element), so everything is kept in registers and the K permutation 0,4,1,5,2,6,3,7 that the
-// GEMM's nibble unpack produces costs nothing.
+// quantized weights -> d * round(x / d) of the Q8 block (same d, same quants as quantize_row_q8_x); F16 -> (Half)x.
+// Rows n >= N of the padded buffer are zero.
+//
+// Range (quantized weights only; the reference keeps d in float32, Ggml.cs:1158, 1190-1196): every row is pre-scaled by the exact
+// power of two 2^-ex[n], ex[n] = ilogb(max |x[n][:]|) - 13, before the fp16 rounding, and the GEMM epilogue multiplies it back --
+// so x * 2^+-20, a 1e5 outlier row or values under fp16's 6e-5 normal limit keep their full fp16 mantissa instead of overflowing
+// or going subnormal.  F16 weights are NOT rescaled: there the reference itself rounds src1 to Half (Ggml.cs:6362-6379).
+//
+// One CTA per row at a time (the row maximum needs the whole row), one thread per block of 32 elements (128 B in, 64 B out): the
+// thread's block stays in registers between the reduction and the store, so the kernel is still a pure stream (12 B per element);
+// the K permutation 0,4,1,5,2,6,3,7 that the GEMM's nibble unpack produces costs nothing.
+__device__ __forceinline__ void act_load_block(const char *p, int vec16, float *e)
+{
+    if (vec16) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float4 v = __ldg(reinterpret_cast<const float4 *>(p) + i); e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) e[i] = reinterpret_cast<const float *>(p)[i];
+    }
+}
+__device__ __forceinline__ float act_block_amax(const float *e)
+{
+    float amax = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(e[i]));
+    return amax;
+}
+// one block of 32 activations -> 64 bytes of the fp16 row; rs = 2^-ex of the row (1 for F16 weights)
+__device__ __forceinline__ void act_emit_block(float *e, int wtype, int perm, float rs, __half *dst_h)
+{
+    if (wtype != GGML_TYPE_F16) {
+        const float amax = act_block_amax(e);
+        const float d = __fdiv_rn(amax, 127.0f);
+        const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+        if (id < 3.0e38f) {                                    // every sane block: |x*id| <= 127.0000x, plain ties-to-even
+#pragma unroll
+            for (int i = 0; i < 32; i++) e[i] = __fmul_rn(__fmul_rn(d, (float)__float2int_rn(__fmul_rn(e[i], id))), rs);
+        } else {                                               // 1/d overflowed (subnormal scale): .NET cast semantics
+#pragma unroll
+            for (int i = 0; i < 32; i++) e[i] = __fmul_rn(__fmul_rn(d, (float)(int)(int8_t)rne_byte(__fmul_rn(e[i], id))), rs);
+        }
+    }
+    uint32_t o[16];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        // group of 8 elements -> 4 half2; natural order (0,1)(2,3)(4,5)(6,7) or permuted (0,4)(1,5)(2,6)(3,7)
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const float a = perm ? e[8 * g + t] : e[8 * g + 2 * t];
+            const float b = perm ? e[8 * g + 4 + t] : e[8 * g + 2 * t + 1];
+            const __half2 h = __floats2half2_rn(a, b);
+            o[4 * g + t] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(dst_h);
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+}
+
 __global__ void __launch_bounds__(256) k_act_f16_dequant(const __grid_constant__ ActGemmBatch b)
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the GEMM's prologue and weight streaming may start now
@@ -553,53 +609,47 @@ __global__ void __launch_bounds__(256) k_act_f16_dequant(const __grid_constant__
     const ActGemmNode &nd = b.node[blockIdx.y];
     const int wtype = b.wtype, perm = b.perm, N = nd.N, Npad = nd.Npad, K = nd.K, vec16 = nd.vec16;
     const float *__restrict__ x = nd.x; const long long ldx_bytes = nd.ldx_bytes; __half *__restrict__ out = nd.out;
+    int *__restrict__ ex = nd.ex;
     const int kb = K / GGB_QK;
-    const long long nblk = (long long)Npad * kb;
-    for (long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += (long long)gridDim.x * blockDim.x) {
-        const int row = (int)(blk / kb), col = (int)(blk - (long long)row * kb);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (int)(blockDim.x >> 5);
+    const bool scaled = wtype != GGML_TYPE_F16;
+    __shared__ float s_max[8];
+    for (int row = blockIdx.x; row < Npad; row += gridDim.x) {
+        const char *xrow = reinterpret_cast<const char *>(x) + (long long)row * ldx_bytes;
+        __half *orow = out + (long long)row * K;
         float e[32];
-        if (row < N) {
-            const char *p = reinterpret_cast<const char *>(x) + (long long)row * ldx_bytes + (long long)col * 128;
-            if (vec16) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) { const float4 v = __ldg(reinterpret_cast<const float4 *>(p) + i); e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w; }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 32; i++) e[i] = reinterpret_cast<const float *>(p)[i];
-            }
-        } else {
+        const bool mine = tid < kb;
+        if (mine && row < N) act_load_block(xrow + (long long)tid * 128, vec16, e);
+        else {
 #pragma unroll
             for (int i = 0; i < 32; i++) e[i] = 0.0f;
         }
-        if (wtype != GGML_TYPE_F16) {
-            float amax = 0.0f;
+        float rs = 1.0f;
+        if (scaled) {
+            // ---- the row's largest magnitude -> its power-of-two exponent ----
+            float am = act_block_amax(e);
+            if (row < N)
+                for (int col = tid + (int)blockDim.x; col < kb; col += (int)blockDim.x) {       // rows longer than 32 * blockDim elements
+                    float t[32];
+                    act_load_block(xrow + (long long)col * 128, vec16, t);
+                    am = fmaxf(am, act_block_amax(t));
+                }
 #pragma unroll
-            for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(e[i]));
-            const float d = __fdiv_rn(amax, 127.0f);
-            const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
-            if (id < 3.0e38f) {                                    // every sane block: |x*id| <= 127.0000x, plain ties-to-even
-#pragma unroll
-                for (int i = 0; i < 32; i++) e[i] = __fmul_rn(d, (float)__float2int_rn(__fmul_rn(e[i], id)));
-            } else {                                               // 1/d overflowed (subnormal scale): .NET cast semantics
-#pragma unroll
-                for (int i = 0; i < 32; i++) e[i] = __fmul_rn(d, (float)(int)(int8_t)rne_byte(__fmul_rn(e[i], id)));
-            }
+            for (int off = 16; off; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+            __syncthreads();                                        // s_max of the previous row has been read by everyone
+            if (lane == 0) s_max[warp] = am;
+            __syncthreads();
+            am = s_max[0];
+            for (int w = 1; w < nwarps; w++) am = fmaxf(am, s_max[w]);
+            const int er = range_exp(am);
+            rs = exp2i(-er);
+            if (tid == 0 && ex) ex[row] = er;
         }
-        uint32_t o[16];
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            // group of 8 elements -> 4 half2; natural order (0,1)(2,3)(4,5)(6,7) or permuted (0,4)(1,5)(2,6)(3,7)
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const float a = perm ? e[8 * g + t] : e[8 * g + 2 * t];
-                const float b = perm ? e[8 * g + 4 + t] : e[8 * g + 2 * t + 1];
-                const __half2 h = __floats2half2_rn(a, b);
-                o[4 * g + t] = *reinterpret_cast<const uint32_t *>(&h);
-            }
+        if (mine) act_emit_block(e, wtype, perm, rs, orow + (long long)tid * GGB_QK);
+        for (int col = tid + (int)blockDim.x; col < kb; col += (int)blockDim.x) {
+            if (row < N) act_load_block(xrow + (long long)col * 128, vec16, e);                  // else e is still all zero
+            act_emit_block(e, wtype, perm, rs, orow + (long long)col * GGB_QK);
         }
-        uint4 *dst = reinterpret_cast<uint4 *>(out + (long long)row * K + (long long)col * GGB_QK);
-#pragma unroll
-        for (int i = 0; i < 4; i++) dst[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
     }
     // Completion must be transitive along the stream: kernels of one batch are launched programmatically dependent on their
     // predecessor only, so this kernel does not COMPLETE before everything ahead of it in the stream has (a consumer that
@@ -724,19 +774,20 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
 int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s, bool pdl)
 {
     if (b.n_nodes <= 0) return GGB_OK;
-    long long maxblk = 0;
+    int max_rows = 0, max_kb = 0;
     for (int i = 0; i < b.n_nodes; i++) {
         ActGemmNode &nd = b.node[i];
         nd.vec16 = ((reinterpret_cast<uintptr_t>(nd.x) & 15) == 0 && (nd.ldx_bytes & 15) == 0) ? 1 : 0;
-        maxblk = std::max(maxblk, (long long)nd.Npad * (nd.K / GGB_QK));
+        max_rows = std::max(max_rows, nd.Npad); max_kb = std::max(max_kb, nd.K / GGB_QK);
     }
-    if (maxblk <= 0) return GGB_OK;
-    long long grid = (maxblk + 255) / 256;
-    const long long cap = std::max<long long>(1, (long long)device_sm_count() * 8 / b.n_nodes);
-    if (grid > cap) grid = cap;
+    if (max_rows <= 0 || max_kb <= 0) return GGB_OK;
+    const int threads = max_kb <= 32 ? 32 : max_kb <= 64 ? 64 : max_kb <= 128 ? 128 : 256;     // one block of 32 activations per thread
+    // one CTA per row; capped so that a group of many nodes still launches a bounded grid (CTAs loop over rows)
+    const long long cap = std::max<long long>(1, (long long)device_sm_count() * (2048 / threads) / b.n_nodes);
+    const long long grid = std::min<long long>(max_rows, cap);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, (unsigned)b.n_nodes);
-    cfg.blockDim = dim3(256);
+    cfg.blockDim = dim3((unsigned)threads);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -747,11 +798,11 @@ int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s, bool pdl)
     return GGB_OK;
 }
 
-int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior, bool pdl)
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int *ex, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior, bool pdl)
 {
     static thread_local ActGemmBatch b;
     b.n_nodes = 1; b.wtype = wtype; b.perm = perm; b.wait_prior = wait_prior ? 1 : 0;
-    b.node[0] = ActGemmNode{x, (long long)ldx_bytes, out, (int)N, (int)Npad, (int)K, 0};
+    b.node[0] = ActGemmNode{x, (long long)ldx_bytes, out, ex, (int)N, (int)Npad, (int)K, 0};
     return launch_act_f16_dequant_batch(b, s, pdl);
 }
 

@@ -226,8 +226,64 @@ __global__ void __launch_bounds__(128) k_add_q_sib(const uint8_t *__restrict__ q
 // reference's dequantized value rounded to half (the same operand precision the in-kernel Q4_0 / Q4_1 dequant feeds the
 // MMAs), then the F16 tcgen05 GEMM runs on it.  One thread per 8 consecutive elements (one 16-byte store).
 // (Q4_0 / Q4_1 are here too: their shapes that the TMA kernels cannot take -- K not a multiple of 128 -- use the same fallback.)
+// Per-row range exponent of a quantized weight matrix (see ggb_internal.h: launch_weight_rowexp).  One warp per row; a lane visits
+// every 32nd group and bounds the largest |value| the group can dequantize to from its header alone:
+//   Q4_0 8|d|   Q4_1 max(|m|, |m + 15 d|)   Q4_2 8 max(|d0|, |d1|)   Q5_0 16|d|   Q5_1 max(|m|, |m + 31 d|)   Q8_0 128|d|
+// 2-byte loads throughout: rows of the expansion fallback are only 2-byte aligned.
 template <int TYPE>
-__global__ void __launch_bounds__(256) k_expand_f16(const uint8_t *__restrict__ W, long long nb01, __half *__restrict__ out, long long M, int K)
+__device__ __forceinline__ float rowexp_bound(const uint8_t *__restrict__ row, int kb, int lane)
+{
+    constexpr int G = TYPE == GGML_TYPE_Q4_0 ? 20 : TYPE == GGML_TYPE_Q4_1 ? 24 : TYPE == GGML_TYPE_Q4_2 ? 20 : TYPE == GGML_TYPE_Q5_0 ? 22 : TYPE == GGML_TYPE_Q5_1 ? 24 : 36;
+    float s = 0.0f;
+    for (int b = lane; b < kb; b += 32) {
+        const unsigned short *g = reinterpret_cast<const unsigned short *>(row + (long long)b * G);
+        float v;
+        if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q8_0) {
+            const float d = __uint_as_float((uint32_t)__ldg(g) | ((uint32_t)__ldg(g + 1) << 16));
+            v = fabsf(d) * (TYPE == GGML_TYPE_Q4_0 ? 8.0f : 128.0f);
+        } else if (TYPE == GGML_TYPE_Q4_1) {
+            const float d = __uint_as_float((uint32_t)__ldg(g) | ((uint32_t)__ldg(g + 1) << 16));
+            const float m = __uint_as_float((uint32_t)__ldg(g + 2) | ((uint32_t)__ldg(g + 3) << 16));
+            v = fmaxf(fabsf(m), fabsf(fmaf(15.0f, d, m)));
+        } else if (TYPE == GGML_TYPE_Q4_2) {
+            v = 8.0f * fmaxf(fabsf(h_val(__ldg(g))), fabsf(h_val(__ldg(g + 5))));
+        } else if (TYPE == GGML_TYPE_Q5_0) {
+            v = 16.0f * fabsf(h_val(__ldg(g)));
+        } else {
+            const float d = h_val(__ldg(g)), m = h_val(__ldg(g + 1));
+            v = fmaxf(fabsf(m), fabsf(fmaf(31.0f, d, m)));
+        }
+        if (v <= 3.4028234e38f) s = fmaxf(s, v);                    // NaN / infinite headers do not decide the scale of the finite ones
+    }
+    return s;
+}
+// every node of a batch in one launch: warp -> (node, row)
+__global__ void __launch_bounds__(256) k_weight_rowexp(const __grid_constant__ RowExpBatch b)
+{
+    const int lane = threadIdx.x & 31;
+    const long long grow = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (grow >= b.total_rows) return;
+    int n = 0;
+    { int hi = b.n_nodes - 1; while (n < hi) { const int mid = (n + hi + 1) >> 1; if (grow >= b.node[mid].row0) n = mid; else hi = mid - 1; } }   // last node with row0 <= grow
+    const RowExpNode &nd = b.node[n];
+    const long long r = grow - nd.row0;
+    const uint8_t *row = nd.W + r * nd.nb01;
+    float s;
+    switch (nd.type) {
+    case GGML_TYPE_Q4_0: s = rowexp_bound<GGML_TYPE_Q4_0>(row, nd.kb, lane); break;
+    case GGML_TYPE_Q4_1: s = rowexp_bound<GGML_TYPE_Q4_1>(row, nd.kb, lane); break;
+    case GGML_TYPE_Q4_2: s = rowexp_bound<GGML_TYPE_Q4_2>(row, nd.kb, lane); break;
+    case GGML_TYPE_Q5_0: s = rowexp_bound<GGML_TYPE_Q5_0>(row, nd.kb, lane); break;
+    case GGML_TYPE_Q5_1: s = rowexp_bound<GGML_TYPE_Q5_1>(row, nd.kb, lane); break;
+    default:             s = rowexp_bound<GGML_TYPE_Q8_0>(row, nd.kb, lane); break;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) s = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, off));
+    if (lane == 0) nd.ew[r] = range_exp(s);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(256) k_expand_f16(const uint8_t *__restrict__ W, long long nb01, __half *__restrict__ out, long long M, int K, const int *__restrict__ ew)
 {
     constexpr int G = TYPE == GGML_TYPE_Q4_0 ? 20 : TYPE == GGML_TYPE_Q4_1 ? 24 : TYPE == GGML_TYPE_Q4_2 ? 20 : TYPE == GGML_TYPE_Q5_0 ? 22 : TYPE == GGML_TYPE_Q5_1 ? 24 : 36;
     const int oct_per_row = K >> 3;
@@ -238,6 +294,7 @@ __global__ void __launch_bounds__(256) k_expand_f16(const uint8_t *__restrict__ 
         const long long row = t / oct_per_row;
         const int oc = (int)(t - row * oct_per_row), sub = oc & 3;              // elements 8*sub .. 8*sub+7 of group oc >> 2
         const unsigned short *g = reinterpret_cast<const unsigned short *>(W + row * nb01 + (long long)(oc >> 2) * G);
+        const float rs = ew ? exp2i(-ew[row]) : 1.0f;                          // exact power-of-two pre-scale of this weight row
         float v[8];
         if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_1) {           // [f32 d][f32 m (Q4_1)][16 nibble bytes], Ggml.cs:884-911 / 961-987
             constexpr int Q0 = TYPE == GGML_TYPE_Q4_0 ? 2 : 4;
@@ -275,6 +332,8 @@ __global__ void __launch_bounds__(256) k_expand_f16(const uint8_t *__restrict__ 
                 v[2 * i + 1] = __fmul_rn((float)(int)(int8_t)(q >> 8), d);
             }
         }
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] *= rs;
         uint4 o;
         __half2 h;
         h = __floats2half2_rn(v[0], v[1]); o.x = *reinterpret_cast<const uint32_t *>(&h);
@@ -353,7 +412,33 @@ int launch_add_q_f32_sib(int type, const void *src0, const float *src1, void *ds
     return GGB_OK;
 }
 
-int launch_expand_f16(int type, const void *W, int64_t nb01, __half *out, int64_t M, int64_t K, cudaStream_t s, bool pdl)
+int launch_weight_rowexp_batch(RowExpBatch &b, cudaStream_t s)
+{
+    long long rows = 0;
+    for (int i = 0; i < b.n_nodes; i++) {
+        RowExpNode &nd = b.node[i];
+        if (!is_q_weight(nd.type)) return set_error(GGB_E_UNSUPPORTED, "row exponents: type %d is not a quantized weight type", nd.type);
+        if ((reinterpret_cast<uintptr_t>(nd.W) | (uintptr_t)nd.nb01) & 1) return set_error(GGB_E_UNSUPPORTED, "mul_mat: weight rows must be 2-byte aligned");
+        nd.row0 = rows; rows += nd.M;
+    }
+    b.total_rows = rows;
+    if (rows <= 0) return GGB_OK;
+    k_weight_rowexp<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(b);
+    count_launch(); GGB_CUDA(cudaGetLastError());
+    return GGB_OK;
+}
+
+int launch_weight_rowexp(int type, const void *W, int64_t nb01, int64_t M, int64_t K, int *ew, cudaStream_t s)
+{
+    if (M <= 0) return GGB_OK;
+    if (K <= 0 || K % GGB_QK) return set_error(GGB_E_INVALID, "mul_mat: ne00=%lld %% 32 != 0 (Ggml.cs:6694)", (long long)K);
+    static thread_local RowExpBatch b;
+    b.n_nodes = 1;
+    b.node[0] = RowExpNode{static_cast<const uint8_t *>(W), (long long)nb01, ew, 0, (int)M, (int)(K / GGB_QK), type, 0};
+    return launch_weight_rowexp_batch(b, s);
+}
+
+int launch_expand_f16(int type, const void *W, int64_t nb01, __half *out, int64_t M, int64_t K, const int *ew, cudaStream_t s, bool pdl)
 {
     if (M <= 0 || K <= 0) return GGB_OK;
     if (K % GGB_QK) return set_error(GGB_E_INVALID, "mul_mat: ne00=%lld %% 32 != 0 (Ggml.cs:6694)", (long long)K);
@@ -366,9 +451,9 @@ int launch_expand_f16(int type, const void *W, int64_t nb01, __half *out, int64_
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    if (type == GGML_TYPE_Q4_0) GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<GGML_TYPE_Q4_0>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K));
-    else if (type == GGML_TYPE_Q4_1) GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<GGML_TYPE_Q4_1>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K));
-    else GGB_SIB_SWITCH(type, GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<T>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K)));
+    if (type == GGML_TYPE_Q4_0) GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<GGML_TYPE_Q4_0>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K, ew));
+    else if (type == GGML_TYPE_Q4_1) GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<GGML_TYPE_Q4_1>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K, ew));
+    else GGB_SIB_SWITCH(type, GGB_CUDA(cudaLaunchKernelEx(&cfg, k_expand_f16<T>, (const uint8_t *)W, (long long)nb01, out, (long long)M, (int)K, ew)));
     count_launch();
     return GGB_OK;
 }

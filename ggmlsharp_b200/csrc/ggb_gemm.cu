@@ -43,8 +43,11 @@ struct GemmPeers { int n; float *y[7]; };
 template <int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_f16(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-           float *__restrict__ Y, long long ldy, int M, int N, int K, const __grid_constant__ GemmPeers peers)
+           float *__restrict__ Y, long long ldy, int M, int N, int K, const __grid_constant__ GemmPeers peers,
+           const int *__restrict__ ew, const int *__restrict__ ex, int wait_w)
 {
+    // ew / ex: power-of-two row exponents of an EXPANDED quantized weight matrix and of its d*q activations (ggb_internal.h:
+    // launch_weight_rowexp); both null for true F16 weights, whose operands the reference itself rounds to Half.
     constexpr int BNL = BN / CG;
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2;
     constexpr int STAGES = CG == 2 ? 4 : 3, NISSUE = 2;
@@ -148,6 +151,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
         tc_fence_after();
         const int m = m0 + q * 32 + lane;
         const int nbase = blockIdx.y * BN;
+        int ewr = 0;
+        if (ew) { asm volatile("griddepcontrol.wait;" ::: "memory"); if (m < M) ewr = __ldcg(ew + m); }
 #pragma unroll 1
         for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
@@ -167,8 +172,9 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
 #pragma unroll
                     for (int c = 0; c < 16; c++) {
                         const int n = nbase + cb * 32 + hc * 16 + c;
-                        const float r = ksteps > 1 ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);
+                        float r = ksteps > 1 ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);
                         if (n < N) {
+                            if (ew) r = scale2(r, ewr + __ldcg(ex + n));
                             Y[(long long)n * ldy + m] = r;
                             for (int pp = 0; pp < peers.n; pp++) peers.y[pp][(long long)n * ldy + m] = r;
                         }
@@ -215,7 +221,7 @@ template <int TYPE, int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
          float *__restrict__ Y, long long ldy, int M, int N, int K, long long *__restrict__ dbg, int dbg_flags,
-         const __grid_constant__ GemmPeers peers)
+         const __grid_constant__ GemmPeers peers, const int *__restrict__ ew, const int *__restrict__ ex, int wait_w)
 {
     constexpr int RAW_ROW = RawRow<TYPE>::BYTES;
     constexpr int RAW_BYTES = BM * RAW_ROW;
@@ -276,6 +282,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
     if (warp == 0) {
         // ===== TMA producer 1: raw quant blocks (own barrier ring, never blocked by the activation ring) =====
         if (lane == 0) {
+            if (wait_w) asm volatile("griddepcontrol.wait;" ::: "memory");   // the weights were written by an earlier kernel of this batch (CPY / quantize)
             int s = 0; uint32_t ph_s = 1;
             for (int ks = 0; ks < ksteps; ks++) {
                 mbar_wait(BAR(RAW_EMPTY + s), ph_s);
@@ -339,6 +346,8 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
             uint32_t mk_lo = 0x000F000Fu, mk_hi = 0x00F000F0u, mg_lo = 0x64006400u, mg_hi = 0x54005400u;
             asm volatile("" : "+r"(mk_lo), "+r"(mk_hi), "+r"(mg_lo), "+r"(mg_hi));
             uint32_t ph_a = 1;
+            if (wait_w) asm volatile("griddepcontrol.wait;" ::: "memory");   // ew comes from a kernel launched earlier in this batch
+            const float rs = exp2i(-((m0 + r) < M ? __ldcg(ew + m0 + r) : 0));   // this thread's weight row, pre-scaled by 2^-ew
             for (int ks = g; ks < ksteps; ks += 4) {
                 const int s = ks % RAW_STAGES;
                 if (tdbg && ks < 32 && (threadIdx.x == 128)) tdbg[(threadIdx.x == 128 ? 48 : 96) + (ks >> 2) * 6 + 0] = clock64();
@@ -358,7 +367,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                     uint32_t v[32];
 #pragma unroll
                     for (int jb = 0; jb < 2; jb++) {
-                        dequant_group<TYPE>(w, hb * 2 + jb, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16]);
+                        dequant_group<TYPE>(w, hb * 2 + jb, rs, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16]);
                     }
                     tmem_st_x32(a_tmem + (uint32_t)(hb * 32), v);
                 }
@@ -380,6 +389,8 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
             tc_fence_after();
             const int m = m0 + q * 32 + lane;
             const int nbase = blockIdx.y * BN;
+            asm volatile("griddepcontrol.wait;" ::: "memory");         // ex was written by the activation kernel (long complete: the B tiles came from it)
+            const int ewr = m < M ? __ldcg(ew + m) : 0;
 #pragma unroll 1
             for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
@@ -399,8 +410,9 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
 #pragma unroll
                         for (int c = 0; c < 16; c++) {
                             const int n = nbase + cb * 32 + hc * 16 + c;
-                            const float r = ksteps > 1 ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);   // even-K + odd-K partial sums
+                            float r = ksteps > 1 ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);   // even-K + odd-K partial sums
                             if (n < N) {
+                                r = scale2(r, ewr + __ldcg(ex + n));       // undo the operands' power-of-two pre-scaling (exact)
                                 Y[(long long)n * ldy + m] = r;
                                 for (int pp = 0; pp < peers.n; pp++) peers.y[pp][(long long)n * ldy + m] = r;
                             }
@@ -489,7 +501,7 @@ int launch_f16(const GemmArgs &a, cudaStream_t s)
     GemmPeers peers = {};
     peers.n = a.n_peers;
     for (int p = 0; p < a.n_peers; p++) peers.y[p] = a.ypeer[p];
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_f16<BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, peers));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_f16<BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, peers, a.ew, a.ex, a.wait_w));
     count_launch();
     return GGB_OK;
 }
@@ -497,6 +509,7 @@ int launch_f16(const GemmArgs &a, cudaStream_t s)
 template <int TYPE, int BN, int CG>
 int launch_q(const GemmArgs &a, cudaStream_t s)
 {
+    if (!a.ew || !a.ex) return set_error(GGB_E_INVALID, "batched path: quantized weights need their row exponents (ew / ex)");
     constexpr int RAW_ROW = RawRow<TYPE>::BYTES;
     constexpr int BNL = BN / CG;
     CUtensorMap mw, mx;
@@ -526,7 +539,7 @@ int launch_q(const GemmArgs &a, cudaStream_t s)
     GemmPeers peers = {};
     peers.n = a.n_peers;
     for (int p = 0; p < a.n_peers; p++) peers.y[p] = a.ypeer[p];
-    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_q<TYPE, BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, static_cast<long long *>(a.trace), dbg_flags, peers));
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_q<TYPE, BN, CG>, mw, mx, a.Y, (long long)a.ldy, (int)a.M, (int)a.N, (int)a.K, static_cast<long long *>(a.trace), dbg_flags, peers, a.ew, a.ex, a.wait_w));
     count_launch();
     return GGB_OK;
 }
@@ -545,9 +558,9 @@ bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, con
 
 size_t gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N)
 {
-    (void)type; (void)M;
-    const int64_t Npad = (N + 15) / 16 * 16;
-    return align_up((size_t)Npad * K * 2, 256);
+    // fp16 activations; quantized weights add the two exponent arrays (ggb_internal.h: gemm_ws_ex_offset / gemm_ws_ew_offset)
+    if (type == GGML_TYPE_F16) return gemm_ws_ex_offset(K, N);
+    return align_up(gemm_ws_ew_offset(K, N) + (size_t)(M > 0 ? M : 0) * 4, 256);
 }
 
 int gemm_act_perm(int type) { return type == GGML_TYPE_F16 ? 0 : 1; }

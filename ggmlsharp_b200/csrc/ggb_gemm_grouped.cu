@@ -35,9 +35,11 @@ struct alignas(64) GroupNode {
     int tile0, tile_end, nt;       // this node's tiles in the launch are [tile0, tile_end); nt = tiles along the activation rows
     int n_peers, pad_;
     long long peer_delta[7];       // row split: byte offset from Y to the same element of peer p's dst (CUDA-IPC mapped)
+    const int *ew, *ex;            // power-of-two row exponents of the weights / staged activations (null, null: true F16 weights)
 };
 // CAP = 8 keeps the parameter block at 3 KB for small groups (parameters above 4 KB add microseconds to the launch)
-template <int CAP> struct alignas(64) GemmGroupT { int n_nodes, total_tiles; int pad_[14]; GroupNode node[CAP]; };
+// wait_w: some node's weights (or ew) were written earlier in this stream by a kernel of the same batch, so the weight side waits too
+template <int CAP> struct alignas(64) GemmGroupT { int n_nodes, total_tiles, wait_w; int pad_[13]; GroupNode node[CAP]; };
 using GemmGroup = GemmGroupT<GGB_GEMM_GROUP_NODES>;
 constexpr int SMALL_GROUP = 8;
 static_assert(sizeof(GemmGroup) <= 32000, "kernel parameter space");
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
     if (warp == 0) {
         // ===== TMA producer 1: this CTA's 128 rows of raw quant blocks =====
         if (lane == 0) {
+            if (G.wait_w) asm volatile("griddepcontrol.wait;" ::: "memory");
             uint32_t gk = 0;
             for (int t = pair; t < G.total_tiles; t += npairs) {
                 const Tile tl = locate(t);
@@ -180,8 +183,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
         uint32_t mk_lo = 0x000F000Fu, mk_hi = 0x00F000F0u, mg_lo = 0x64006400u, mg_hi = 0x54005400u;
         asm volatile("" : "+r"(mk_lo), "+r"(mk_hi), "+r"(mg_lo), "+r"(mg_hi));
         uint32_t gk0 = 0, it = 0;
+        if (G.wait_w) asm volatile("griddepcontrol.wait;" ::: "memory");       // ew comes from a kernel launched earlier in this batch
         for (int t = pair; t < G.total_tiles; t += npairs, it++) {
             const Tile tl = locate(t);
+            const int ewr = (tl.m0 + r) < tl.nd->M ? __ldcg(tl.nd->ew + tl.m0 + r) : 0;   // this thread's weight row of the tile
+            const float rs = exp2i(-ewr);
             for (int ks = (int)((g - gk0) & 3); ks < tl.ksteps; ks += 4) {
                 const uint32_t gk = gk0 + (uint32_t)ks;
                 const int s = gk & (RAW_STAGES - 1);
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                     uint32_t v[32];
 #pragma unroll
                     for (int jb = 0; jb < 2; jb++) {
-                        dequant_group<TYPE>(w, hb * 2 + jb, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16]);
+                        dequant_group<TYPE>(w, hb * 2 + jb, rs, mk_lo, mk_hi, mg_lo, mg_hi, &v[jb * 16]);
                     }
                     if (hb == 0) {
                         // the nibble expansion of the first half ran ahead of this wait: only the TMEM store needs the stage free
@@ -216,6 +222,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
             const GroupNode &nd = *tl.nd;
             const int m = tl.m0 + q * 32 + lane;
             const bool two = NISSUE == 2 && tl.ksteps > 1;
+            if (it == 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // ex was written by the activation kernel (complete: the B tiles came from it)
+            const int *__restrict__ exn = nd.ex;
 #pragma unroll 1
             for (int cb = g; cb < BN / 32; cb += NDQ_WARPS / 4) {
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
@@ -235,8 +243,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
 #pragma unroll
                         for (int c = 0; c < 16; c++) {
                             const int n = tl.n0 + cb * 32 + hc * 16 + c;
-                            const float res = two ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);   // even-K + odd-K partial sums
+                            float res = two ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);   // even-K + odd-K partial sums
                             if (n < nd.N) {
+                                res = scale2(res, ewr + __ldcg(exn + n));  // undo the operands' power-of-two pre-scaling (exact)
                                 float *yp = nd.Y + (long long)n * nd.ldy + m;
                                 *yp = res;
                                 for (int pp = 0; pp < nd.n_peers; pp++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + nd.peer_delta[pp]) = res;
@@ -372,6 +381,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_c
             const GroupNode &nd = *tl.nd;
             const int m = tl.m0 + q * 32 + lane;
             const bool two = tl.ksteps > 1;
+            // expanded quantized weights (ggb_shim.cu: use_gemm_expanded) carry row exponents; true F16 weights do not
+            const int *__restrict__ exn = nd.ex;
+            int ewr = 0;
+            if (exn) { if (it == 0) asm volatile("griddepcontrol.wait;" ::: "memory"); if (m < nd.M) ewr = __ldcg(nd.ew + m); }
 #pragma unroll 1
             for (int cb = g; cb < BN / 32; cb += NDQ_WARPS / 4) {
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * BN + cb * 32);
@@ -391,8 +404,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_c
 #pragma unroll
                         for (int c = 0; c < 16; c++) {
                             const int n = tl.n0 + cb * 32 + hc * 16 + c;
-                            const float res = two ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);
+                            float res = two ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);
                             if (n < nd.N) {
+                                if (exn) res = scale2(res, ewr + __ldcg(exn + n));
                                 float *yp = nd.Y + (long long)n * nd.ldy + m;
                                 *yp = res;
                                 for (int pp = 0; pp < nd.n_peers; pp++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + nd.peer_delta[pp]) = res;
@@ -466,7 +480,7 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
     if (count > GGB_GEMM_GROUP_NODES) return set_error(GGB_E_INVALID, "grouped GEMM: %d nodes > %d", count, GGB_GEMM_GROUP_NODES);
     static thread_local GemmGroup G;                                   // ~25 KB: kept off the stack
     const int type = args[0].type;
-    G.n_nodes = count; G.total_tiles = 0;
+    G.n_nodes = count; G.total_tiles = 0; G.wait_w = 0;
     // Quantized weights: 256-column tiles halve the dequant work and the weight traffic per flop (a K step of a 256-wide tile costs
     // ~1.78x a 128-wide one, measured on cfg 4: 986 -> 1 074 TFLOP/s), but they also halve the number of tiles, and the static
     // round-robin deal makes the slowest pair the launch time (cfg 3 batch of 8: 512 tiles = 6.9 rounds of 74 pairs, 256 tiles = 3.5
@@ -510,6 +524,10 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
         const int mt = (int)((a.M + 2 * BM - 1) / (2 * BM));
         nd.tile0 = G.total_tiles; nd.tile_end = nd.tile0 + mt * nd.nt;
         G.total_tiles = nd.tile_end;
+        nd.ew = a.ew; nd.ex = a.ex;
+        if (type != GGML_TYPE_F16 && (!a.ew || !a.ex)) return set_error(GGB_E_INVALID, "grouped GEMM: quantized weights need their row exponents (ew / ex)");
+        if ((a.ew == nullptr) != (a.ex == nullptr)) return set_error(GGB_E_INVALID, "grouped GEMM: ew and ex come together");
+        if (a.wait_w) G.wait_w = 1;
         nd.n_peers = a.n_peers;
         for (int p = 0; p < a.n_peers; p++) nd.peer_delta[p] = (long long)(reinterpret_cast<char *>(a.ypeer[p]) - reinterpret_cast<char *>(a.Y));
     }
@@ -525,7 +543,7 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s)
     }
     if (count <= SMALL_GROUP) {
         static thread_local GemmGroupT<SMALL_GROUP> S;
-        S.n_nodes = G.n_nodes; S.total_tiles = G.total_tiles;
+        S.n_nodes = G.n_nodes; S.total_tiles = G.total_tiles; S.wait_w = G.wait_w;
         for (int i = 0; i < count; i++) S.node[i] = G.node[i];
         if (type == GGML_TYPE_F16) return launch_grouped<GGML_TYPE_F16, SMALL_GROUP>(S, s);
         GGB_GROUPED_Q(SMALL_GROUP, S)

@@ -52,7 +52,18 @@ int launch_add_q_f32(int type, const void *src0, const float *src1, void *dst, i
 int launch_quantize_rows_sib(int type, const float *src, int64_t ldx, void *dst, int64_t nrows, int64_t k, cudaStream_t s);
 int launch_dequantize_rows_sib(int type, const void *src, float *dst, int64_t nrows, int64_t k, cudaStream_t s);
 int launch_add_q_f32_sib(int type, const void *src0, const float *src1, void *dst, int64_t nrows, int64_t k, cudaStream_t s);
-int launch_expand_f16(int type, const void *W, int64_t nb01, __half *out, int64_t M, int64_t K, cudaStream_t s, bool pdl);
+// ew (may be null): per-row power-of-two exponents from launch_weight_rowexp; row m is expanded as value * 2^-ew[m]
+int launch_expand_f16(int type, const void *W, int64_t nb01, __half *out, int64_t M, int64_t K, const int *ew, cudaStream_t s, bool pdl);
+// Range handling of the tensor-core path.  The reference keeps block scales and dot products in float32 (Ggml.cs:1158, 1190-1196);
+// the MMA operands are fp16, so both operands are pre-scaled by an exact power of two per row and the epilogue undoes it:
+//   ew[m] = ilogb(max over the row's blocks of the largest |dequantized value| a block can hold) - 13   (weights, this kernel)
+//   ex[n] = ilogb(max |x[n][:]|) - 13                                                                   (activations, k_act_f16_dequant)
+// so every operand row peaks in [2^13, 2^14) whatever the magnitude of the data, and dst = acc * 2^(ew[m] + ex[n]).
+int launch_weight_rowexp(int type, const void *W, int64_t nb01, int64_t M, int64_t K, int *ew, cudaStream_t s);
+// the same for every node of a batch in one launch (row0 / total_rows are filled in by the launcher)
+struct RowExpNode { const uint8_t *W; long long nb01; int *ew; long long row0; int M, kb, type, pad_; };
+struct RowExpBatch { int n_nodes, pad_; long long total_rows; RowExpNode node[GGB_GEMM_GROUP_NODES]; };
+int launch_weight_rowexp_batch(RowExpBatch &b, cudaStream_t s);
 
 // ---- F32 neighbours of mul_mat (ggb_ops.cu) ----
 int launch_binary_f32(int op, const float *a, const float *b, float *dst, int64_t n, cudaStream_t s);       // GGML_OP_ADD / GGML_OP_MUL
@@ -75,9 +86,9 @@ using ActBatch = ActBatchT<GGB_MAX_BATCH_NODES>;
 constexpr int GGB_SMALL_BATCH_NODES = 32;
 int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl);
 // batched path: activations as dense fp16 [Npad][K] holding d * q (the value the reference's dot multiplies by)
-int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior, bool pdl = true);
+int launch_act_f16_dequant(int wtype, int perm, const float *x, int64_t ldx_bytes, __half *out, int *ex, int64_t N, int64_t Npad, int64_t K, cudaStream_t s, bool wait_prior, bool pdl = true);
 // the same for every node of a grouped GEMM launch, one kernel (grid.y = node)
-struct ActGemmNode { const float *x; long long ldx_bytes; __half *out; int N, Npad, K, vec16; };
+struct ActGemmNode { const float *x; long long ldx_bytes; __half *out; int *ex; int N, Npad, K, vec16; };   // ex: per-row exponents out (null for F16 weights)
 struct ActGemmBatch { int n_nodes, wtype, perm, wait_prior; ActGemmNode node[GGB_GEMM_GROUP_NODES]; };
 // pdl = false: an ordinary stream-ordered launch (used when an earlier kernel of the batch produced the GEMM's weights)
 int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s, bool pdl = true);
@@ -110,7 +121,12 @@ struct GemmArgs {
     int type; int64_t M, K, N; const void *W; int64_t nb01; const __half *Xh; int64_t Npad;
     float *Y; int64_t ldy; int n_peers; float *ypeer[7];
     void *trace;              // optional clock64 timeline buffer (128 x int64 per CTA), debugging only
+    const int *ew, *ex;       // power-of-two row exponents of the weights [M] / staged activations [>= N rounded up to 256]; both null = unscaled (true F16 weights)
+    int wait_w;               // the weights (or ew) were written earlier in this stream by a kernel of the same batch: the weight side waits too
 };
+// workspace slice of a batched node: [fp16 activations Npad x K][ex: N rounded up to 256 ints][ew: M ints]
+static inline size_t gemm_ws_ex_offset(int64_t K, int64_t N) { const int64_t Npad = (N + 15) / 16 * 16; return align_up((size_t)Npad * (size_t)K * 2, 256); }
+static inline size_t gemm_ws_ew_offset(int64_t K, int64_t N) { return gemm_ws_ex_offset(K, N) + align_up((size_t)N, 256) * 4; }
 bool gemm_supported(int type, int64_t M, int64_t K, int64_t N, int64_t nb01, const void *W);
 size_t gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
 int launch_gemm(const GemmArgs &a, void *ws, cudaStream_t s);
@@ -120,6 +136,19 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s);
 int gemm_act_perm(int type);       // 1: the activation buffer must use the K order 0,4,1,5,2,6,3,7 per group of 8
 
 int device_sm_count();
+
+#ifdef __CUDACC__
+// ---- exact power-of-two range handling of the tensor-core path (see launch_weight_rowexp) ----
+__device__ __forceinline__ float exp2i(int e) { return __int_as_float((e + 127) << 23); }          // 2^e, e in [-126, 127]
+__device__ __forceinline__ int range_exp(float amax)                                                 // peak lands in [2^13, 2^14)
+{
+    if (!(amax > 0.0f) || amax > 3.4028234e38f) return 0;                                            // zero, NaN, infinity: leave the row alone
+    const int e = ilogbf(amax) - 13;
+    return e < -126 ? -126 : e > 126 ? 126 : e;
+}
+// acc * 2^e for e in [-252, 252]: two half-exponent factors, so no intermediate over- or underflows unless the result itself does
+__device__ __forceinline__ float scale2(float acc, int e) { const int h = e >> 1; return acc * exp2i(h) * exp2i(e - h); }
+#endif
 
 } // namespace ggb
 

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <vector>
 
 namespace ggb {
@@ -46,8 +47,10 @@ struct KernelTimer {            // RAII bracket around one mul_mat kernel launch
 };
 int device_sm_count() { return g_sms; }
 
+static std::mutex g_init_mu;      // ggb_dev_* entry points reach ensure_init without g_mu
 static int ensure_init()
 {
+    std::lock_guard<std::mutex> lk_init(g_init_mu);
     if (g_inited) return GGB_OK;
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -96,9 +99,10 @@ static inline bool use_gemm(const ggb_dev_mm &m)
     return m.N >= 16 && (use_gemm_expanded(m) || gemm_supported(m.type, m.M, m.K, m.N, m.nb01, m.W));
 }
 static inline size_t expanded_bytes(int64_t M, int64_t K) { return align_up((size_t)M * (size_t)K * 2, 256); }
+// a batched quantized node's slice: [fp16 activations][ex][ew] (gemm_workspace_bytes), then the expanded weights if the shape needs them
 static size_t mm_ws_bytes(const ggb_dev_mm &m)
 {
-    if (use_gemm_expanded(m)) return align_up(gemm_workspace_bytes(GGML_TYPE_F16, m.M, m.K, m.N), 256) + expanded_bytes(m.M, m.K);
+    if (use_gemm_expanded(m)) return align_up(gemm_workspace_bytes(m.type, m.M, m.K, m.N), 256) + expanded_bytes(m.M, m.K);
     if (use_gemm(m)) return align_up(gemm_workspace_bytes(m.type, m.M, m.K, m.N), 256);
     return align_up((size_t)m.N * act_row_bytes(m.type, m.K), 256);
 }
@@ -107,7 +111,7 @@ static size_t mm_ws_bytes(const ggb_dev_mm &m)
 static size_t mm_ws_bytes_bound(int type, int64_t M, int64_t K, int64_t N, bool may_expand)
 {
     const bool expand = is_q_weight(type) && N >= 16 && (may_expand || K % 128 != 0);
-    const size_t tc = align_up(gemm_workspace_bytes(type, M, K, N), 256) + (expand ? expanded_bytes(M, K) : 0);
+    const size_t tc = align_up(gemm_workspace_bytes(type, M, K, N), 256) + (expand ? expanded_bytes(M, K) : 0);      // incl. the exponent arrays
     return std::max(tc, align_up((size_t)N * act_row_bytes(type, K), 256));
 }
 
@@ -154,11 +158,33 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     // a node whose shape the TMA kernels cannot take: expand the weights behind the activation buffer of its workspace slice and hand
     // the GEMM an F16 node.  The expansion is an ordinary (fully stream-ordered) launch that never releases its dependents early, so
     // nothing behind it in the stream -- in particular a GEMM, whose weight TMA does not wait for anything -- starts before it is complete.
+    // power-of-two row exponents (ggb_internal.h: launch_weight_rowexp): the caller's, computed while the weights became resident,
+    // or computed here -- ordinary launches ahead of everything else of the batch, so they are complete before any kernel below starts
+    std::vector<const int *> ew_of(count, nullptr);
+    std::vector<char> w_wait(count, 0);
+    {
+        static thread_local RowExpBatch rb;
+        rb.n_nodes = 0;
+        auto flush = [&]() -> int { if (!rb.n_nodes) return GGB_OK; int r = launch_weight_rowexp_batch(rb, s); rb.n_nodes = 0; return r; };
+        for (int i = 0; i < count; i++) {
+            const ggb_dev_mm &m = mm[i];
+            if (m.M == 0 || m.N == 0 || !use_gemm(m) || !is_q_weight(m.type)) continue;
+            w_wait[i] = (m.flags & GGB_MM_W_IN_FLIGHT) ? 1 : 0;
+            if (m.W_rowexp) { ew_of[i] = m.W_rowexp; continue; }
+            int *ew = reinterpret_cast<int *>(wsb + off[i] + gemm_ws_ew_offset(m.K, m.N));
+            rb.node[rb.n_nodes++] = RowExpNode{static_cast<const uint8_t *>(m.W), (long long)m.nb01, ew, 0, (int)m.M, (int)(m.K / GGB_QK), m.type, 0};
+            ew_of[i] = ew; w_wait[i] = 1;
+            if (rb.n_nodes == GGB_GEMM_GROUP_NODES) { int rc = flush(); if (rc) return rc; }
+        }
+        int rc = flush();
+        if (rc) return rc;
+    }
+    auto ex_of = [&](int i) { return is_q_weight(mm[i].type) ? reinterpret_cast<int *>(wsb + off[i] + gemm_ws_ex_offset(mm[i].K, mm[i].N)) : nullptr; };
     auto expand = [&](int i, const void *&Wout, int64_t &nb01_out) -> int {
         const ggb_dev_mm &m = mm[i];
-        __half *wh = reinterpret_cast<__half *>(wsb + off[i] + align_up(gemm_workspace_bytes(GGML_TYPE_F16, m.M, m.K, m.N), 256));
+        __half *wh = reinterpret_cast<__half *>(wsb + off[i] + align_up(gemm_workspace_bytes(m.type, m.M, m.K, m.N), 256));
         Wout = wh; nb01_out = 2 * m.K;
-        return launch_expand_f16(m.type, m.W, m.nb01, wh, m.M, m.K, s, false);
+        return launch_expand_f16(m.type, m.W, m.nb01, wh, m.M, m.K, ew_of[i], s, false);
     };
     int n_tc = 0;
     for (int i = 0; i < count; i++) if (mm[i].M > 0 && mm[i].N > 0 && use_gemm(mm[i])) n_tc++;
@@ -175,21 +201,22 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
         const void *Wg = m.W; int64_t nb01g = m.nb01;
         int rc = sibx ? expand(i, Wg, nb01g) : GGB_OK;
         if (rc) return rc;
-        rc = launch_act_f16_dequant(m.type, gemm_act_perm(gtype), m.X, m.ldx_bytes, xh, m.N, Npad, m.K, s, true);   // waits for whatever produced X
+        rc = launch_act_f16_dequant(m.type, gemm_act_perm(gtype), m.X, m.ldx_bytes, xh, ex_of(i), m.N, Npad, m.K, s, true);   // waits for whatever produced X
         if (rc) return rc;
         GemmArgs a = {};
         a.type = gtype; a.M = m.M; a.K = m.K; a.N = m.N; a.W = Wg; a.nb01 = nb01g; a.Xh = xh; a.Npad = Npad;
+        a.ew = ew_of[i]; a.ex = ex_of(i); a.wait_w = w_wait[i];
         a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
         for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
         if (const char *tr = getenv("GGB200_GEMM_TRACE")) a.trace = reinterpret_cast<void *>(strtoull(tr, nullptr, 0));   // debugging: device pointer
-        { KernelTimer kt(s); rc = launch_gemm(a, wsb + off[i] + align_up((size_t)Npad * m.K * 2, 256), s); }
+        { KernelTimer kt(s); rc = launch_gemm(a, nullptr, s); }
         if (rc) return rc;
     }
     // ---- two or more batched nodes: per weight type (kernel flavour) one activation launch + one persistent grouped GEMM launch
     //      per <= 64 nodes (ggb_gemm_grouped.cu) ----
     // Nodes that multiply the SAME activations (wq / wk / wv of a layer, w1 / w3 of its FFN) share one staged copy: the first
     // node's buffer is staged, the others point their B operand at it.  Keyed by what decides the staged bytes.
-    struct StagedX { const float *X; int64_t ldx, N, K; int cls; __half *xh; };
+    struct StagedX { const float *X; int64_t ldx, N, K; int cls; __half *xh; int *ex; };
     std::vector<StagedX> staged;
     // Launch order: the activation kernels of ALL groups first, then the GEMMs.  Every activation kernel waits at its start
     // (griddepcontrol.wait): the first for whatever produced the activations, each later one for its predecessor -- so when the
@@ -214,18 +241,19 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
                 const int i = qn[c0 + c];
                 const ggb_dev_mm &m = mm[i];
                 const int64_t Npad = (m.N + 15) / 16 * 16;
-                __half *xh = nullptr;
+                __half *xh = nullptr; int *exs = nullptr;
                 for (const StagedX &sx : staged)
-                    if (sx.X == m.X && sx.ldx == m.ldx_bytes && sx.N == m.N && sx.K == m.K && sx.cls == cls) { xh = sx.xh; break; }
+                    if (sx.X == m.X && sx.ldx == m.ldx_bytes && sx.N == m.N && sx.K == m.K && sx.cls == cls) { xh = sx.xh; exs = sx.ex; break; }
                 if (!xh) {
-                    xh = reinterpret_cast<__half *>(wsb + off[i]);
-                    ab.node[ab.n_nodes++] = ActGemmNode{m.X, (long long)m.ldx_bytes, xh, (int)m.N, (int)Npad, (int)m.K, 0};
-                    staged.push_back(StagedX{m.X, m.ldx_bytes, m.N, m.K, cls, xh});
+                    xh = reinterpret_cast<__half *>(wsb + off[i]); exs = ex_of(i);
+                    ab.node[ab.n_nodes++] = ActGemmNode{m.X, (long long)m.ldx_bytes, xh, exs, (int)m.N, (int)Npad, (int)m.K, 0};
+                    staged.push_back(StagedX{m.X, m.ldx_bytes, m.N, m.K, cls, xh, exs});
                 }
                 GemmArgs &a = ga[(size_t)c];
                 a = GemmArgs{};
                 a.type = type; a.M = m.M; a.K = m.K; a.N = m.N; a.W = m.W; a.nb01 = m.nb01; a.Xh = xh; a.Npad = Npad;
                 a.Y = m.Y; a.ldy = m.ldy_bytes / 4; a.n_peers = m.n_peers;
+                a.ew = ew_of[i]; a.ex = exs; a.wait_w = w_wait[i];
                 for (int p = 0; p < m.n_peers; p++) a.ypeer[p] = m.Y_peer[p];
                 if (qi == 3) { int rce = expand(i, a.W, a.nb01); if (rce) return rce; }      // an ordinary launch: a full barrier in the stream
             }
@@ -384,7 +412,17 @@ static int flush_copy_batch(CopyBatch &cb, cudaStream_t s)
     return GGB_OK;
 }
 
-struct Mirror { void *dptr; size_t bytes; };
+// Device copy of a leaf src0.  rowexp: the power-of-two row exponents of the tensor-core path (launch_weight_rowexp), computed the
+// first time a view (byte offset, type, M, K, nb01) of the mirror meets a batched node and kept for as long as the mirror lives.
+struct RowExpKey { size_t off; int type; int64_t M, K, nb01; bool operator<(const RowExpKey &o) const { return std::tie(off, type, M, K, nb01) < std::tie(o.off, o.type, o.M, o.K, o.nb01); } };
+struct Mirror { void *dptr; size_t bytes; std::map<RowExpKey, int *> rowexp; };
+static void free_mirror(Mirror &m)
+{
+    for (auto &kv : m.rowexp) cudaFree(kv.second);
+    m.rowexp.clear();
+    cudaFree(m.dptr);
+    m.dptr = nullptr;
+}
 
 struct DevArena {           // grow-only device scratch, reset per compute
     uint8_t *base = nullptr; size_t cap = 0, used = 0;
@@ -407,6 +445,10 @@ struct ggb_pool {
     void *host_base = nullptr;
     size_t bytes = 0;
     bool owned = false, registered = false, register_tried = false;
+    // Weight residency is OPT-IN (ggb_pool_set_weight_cache / GGB200_WEIGHT_CACHE=1): the reference re-reads src0->data on every
+    // ggml_graph_compute, so by default every leaf src0 is uploaded again; a resident pool promises that leaf weights are rewritten
+    // only through the API (CPY / in-place nodes, ggml_set_*), or followed by ggb_tensor_invalidate.
+    bool weight_cache = false;
     std::map<const void *, ggb::Mirror> mirrors;    // keyed by host data pointer of a leaf src0
     ggb::DevArena arena;
 };
@@ -533,10 +575,22 @@ static bool is_neighbour_op(int op)
 
 struct Produced { const uint8_t *host; size_t bytes; uint8_t *dev; int level; };
 
-static Produced *find_produced(std::vector<Produced> &v, const void *p)
+static inline bool ranges_overlap(const uint8_t *a, size_t an, const uint8_t *b, size_t bn) { return a < b + bn && b < a + an; }
+
+// The newest earlier result whose host byte range INTERSECTS [p, p + span).  *partial is set when the operand is not wholly inside
+// it (a view that starts before the result, or runs past its end): such an operand is neither the device copy nor the host bytes,
+// and ggb_graph_compute_mul_mats leaves the node to the caller's loop instead.
+static Produced *find_produced(std::vector<Produced> &v, const void *p, size_t span, bool *partial = nullptr)
 {
     const uint8_t *q = static_cast<const uint8_t *>(p);
-    for (size_t i = v.size(); i-- > 0;) if (q >= v[i].host && q < v[i].host + v[i].bytes) return &v[i];     // newest first
+    if (partial) *partial = false;
+    for (size_t i = v.size(); i-- > 0;) {                                                                   // newest first
+        if (!ranges_overlap(q, span, v[i].host, v[i].bytes)) continue;
+        const bool inside = q >= v[i].host && q + span <= v[i].host + v[i].bytes;
+        if (!inside) { if (partial) *partial = true; return nullptr; }
+        // wholly inside the newest overlapping result: every byte of the operand is that result's (older overlapping results were overwritten there)
+        return &v[i];
+    }
     return nullptr;
 }
 
@@ -555,6 +609,11 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     }
     auto out_tensor = [](ggml_tensor *t) -> ggml_tensor * { return t->op == GGML_OP_CPY ? t->src1 : t; };      // whose data the node writes
 
+    const bool cache_on = pool->weight_cache && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE);
+    // a leaf src0 may stay resident only if nothing rewrites it behind the API's back: never a parameter (ggml_opt updates
+    // params in place between computes, Ggml.cs:1734-1760) and never a tensor with a gradient
+    auto cacheable = [&](const ggml_tensor *x) { return cache_on && x->op == GGML_OP_NONE && !x->is_param && !x->grad; };
+
     // ---- pass 1: an upper bound of the scratch needed, so the arena is allocated once before anything is enqueued ----
     size_t need = 0;
     {
@@ -563,18 +622,17 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             ggml_tensor *t = nodes[i];
             const ggml_tensor *a = t->src0, *b = t->src1;
             if (t->op == GGML_OP_MUL_MAT) {
-                Produced *a_pr = find_produced(plan, a->data);
+                Produced *a_pr = find_produced(plan, a->data, tensor_span(a));
                 const bool a_dev = a_pr != nullptr;
-                const bool a_cached = !a_dev && a->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE);
-                if (!a_dev && !a_cached) need += align_up(tensor_span(a), 256);
-                if (!find_produced(plan, b->data)) need += align_up(tensor_span(b), 256);
+                if (!a_dev && !cacheable(a)) need += align_up(tensor_span(a), 256);
+                if (!find_produced(plan, b->data, tensor_span(b))) need += align_up(tensor_span(b), 256);
                 // staged weights start 256-byte aligned (mirror / arena) unless they are a view into an earlier node's output
                 const bool may_expand = (a->nb[1] & 15) || (a->nb[2] & 15) || (a->nb[3] & 15) ||
                                         (a_pr && ((static_cast<const uint8_t *>(a->data) - a_pr->host) & 15));
                 need += (size_t)(a->ne[2] * a->ne[3]) * mm_ws_bytes_bound(a->type, a->ne[1], a->ne[0], b->ne[1], may_expand);
             } else {
-                if (!find_produced(plan, a->data)) need += align_up(tensor_span(a), 256);
-                if (b && t->op != GGML_OP_CPY && t->op != GGML_OP_SCALE && !find_produced(plan, b->data)) need += align_up(tensor_span(b), 256);
+                if (!find_produced(plan, a->data, tensor_span(a))) need += align_up(tensor_span(a), 256);
+                if (b && t->op != GGML_OP_CPY && t->op != GGML_OP_SCALE && !find_produced(plan, b->data, tensor_span(b))) need += align_up(tensor_span(b), 256);
             }
             ggml_tensor *o = out_tensor(t);
             need += align_up(tensor_span(o), 256);
@@ -589,33 +647,48 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
 
     // ---- pass 2: stage inputs, group nodes into dependency levels, launch ----
     std::vector<Produced> produced;
-    struct Item { ggml_tensor *t; int level; uint8_t *da, *db, *dd; };
+    struct Item { ggml_tensor *t; int level; uint8_t *da, *db, *dd; bool a_in_flight, ew_new; std::vector<const int *> ew; };   // ew: row exponents per (i2, i3) slice of a resident src0
     std::vector<Item> items(n);
     int max_level = 0;
-    auto drop_mirror = [&](const void *hostp) {
-        auto f = pool->mirrors.find(hostp);
-        if (f != pool->mirrors.end()) { cudaFree(f->second.dptr); pool->mirrors.erase(f); }
+    // Mirrors made stale by a node of this call may still be read by EARLIER nodes of it that are not launched yet: they are only
+    // unlinked here and freed when the call is over (the stream is synchronised first, also on an error return).
+    struct Graveyard {
+        std::vector<Mirror> dead; cudaStream_t s;
+        ~Graveyard() { if (dead.empty()) return; cudaStreamSynchronize(s); for (Mirror &m : dead) free_mirror(m); cudaGetLastError(); }
+    } graveyard{{}, s};
+    // a write to [host, host + bytes) makes every cached mirror that shares a byte with it stale (a CPY into an offset view of a
+    // cached leaf, an in-place node on it): dropped by byte range, not by start pointer
+    auto drop_mirrors = [&](const void *hostp, size_t bytes) {
+        const uint8_t *h = static_cast<const uint8_t *>(hostp);
+        for (auto f = pool->mirrors.begin(); f != pool->mirrors.end();) {
+            if (ranges_overlap(h, bytes, static_cast<const uint8_t *>(f->first), f->second.bytes)) { graveyard.dead.push_back(std::move(f->second)); f = pool->mirrors.erase(f); }
+            else ++f;
+        }
     };
     // device address of an operand: produced earlier in this call, a cached weight mirror, read in place from the pinned
     // arena (small tensors, UVA), or uploaded into the scratch arena
-    auto stage = [&](const ggml_tensor *x, int &level, bool weight, uint8_t *&out) -> int {
-        if (Produced *pr = find_produced(produced, x->data)) {
+    auto stage = [&](const ggml_tensor *x, int &level, bool weight, uint8_t *&out, Mirror **mir, bool *in_flight) -> int {
+        const size_t span = tensor_span(x);
+        bool partial = false;
+        if (Produced *pr = find_produced(produced, x->data, span, &partial)) {
             out = pr->dev + (static_cast<const uint8_t *>(x->data) - pr->host);
             level = std::max(level, pr->level + 1);
+            if (in_flight) *in_flight = true;
             return GGB_OK;
         }
-        const size_t span = tensor_span(x);
-        if (weight && x->op == GGML_OP_NONE && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE)) {
+        if (partial) return set_error(GGB_E_UNSUPPORTED, "executor: an operand overlaps an earlier node's result without lying inside it");
+        if (weight && cacheable(x)) {
             auto f = pool->mirrors.find(x->data);
-            if (f != pool->mirrors.end() && f->second.bytes < span) { cudaFree(f->second.dptr); pool->mirrors.erase(f); f = pool->mirrors.end(); }
+            if (f != pool->mirrors.end() && f->second.bytes < span) { graveyard.dead.push_back(std::move(f->second)); pool->mirrors.erase(f); f = pool->mirrors.end(); }
             if (f == pool->mirrors.end()) {
                 void *d = nullptr;
                 GGB_CUDA(cudaMalloc(&d, align_up(span, 256)));
                 GGB_CUDA(cudaMemcpyAsync(d, x->data, span, cudaMemcpyHostToDevice, s));
                 g_stats.h2d_bytes += span; g_stats.weight_uploads++;
-                f = pool->mirrors.emplace(x->data, Mirror{d, span}).first;
+                f = pool->mirrors.emplace(x->data, Mirror{d, span, {}}).first;
             } else g_stats.weight_cache_hits++;
             out = static_cast<uint8_t *>(f->second.dptr);
+            if (mir) *mir = &f->second;
             return GGB_OK;
         }
         if (!weight && pool->owned && span <= ZC_MAX && (reinterpret_cast<uintptr_t>(x->data) & 3) == 0) {
@@ -631,7 +704,8 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         ggml_tensor *t = nodes[i];
         ggml_tensor *a = t->src0, *b = t->src1;
         Item &it = items[i];
-        it.t = t; it.level = 0; it.da = it.db = it.dd = nullptr;
+        it.t = t; it.level = 0; it.da = it.db = it.dd = nullptr; it.a_in_flight = false; it.ew_new = false;
+        Mirror *mir = nullptr;
         ggml_tensor *o = out_tensor(t);
         const size_t ospan = tensor_span(o);
         // does the node write over one of its inputs (ggml_scale, ggml_*_inplace: the result is a view of src0)?
@@ -640,30 +714,53 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         if (in_place && t->op != GGML_OP_SCALE && t->op != GGML_OP_ADD && t->op != GGML_OP_MUL && t->op != GGML_OP_SILU && t->op != GGML_OP_RMS_NORM)
             return set_error(GGB_E_UNSUPPORTED, "op %d writing over its own source is not supported", t->op);
         if (in_place && od != ad) return set_error(GGB_E_UNSUPPORTED, "in-place op %d on a shifted view", t->op);
-        if (in_place && !find_produced(produced, a->data)) {
+        bool a_partial = false;
+        Produced *a_prod = in_place ? find_produced(produced, a->data, tensor_span(a), &a_partial) : nullptr;
+        if (a_partial) return set_error(GGB_E_UNSUPPORTED, "executor: an in-place operand overlaps an earlier node's result without lying inside it");
+        if (in_place && !a_prod) {
             // in place on a leaf: work on an arena copy (never on the pinned host arena directly, never on a cached mirror)
             const size_t span = tensor_span(a);
             it.da = static_cast<uint8_t *>(pool->arena.take(span));
             GGB_CUDA(cudaMemcpyAsync(it.da, a->data, span, cudaMemcpyHostToDevice, s));
             g_stats.h2d_bytes += span;
-            drop_mirror(a->data);
+            drop_mirrors(a->data, span);
         } else {
-            rc = stage(a, it.level, t->op == GGML_OP_MUL_MAT, it.da);
+            rc = stage(a, it.level, t->op == GGML_OP_MUL_MAT, it.da, &mir, &it.a_in_flight);
             if (rc) return rc;
         }
+        if (mir && t->op == GGML_OP_MUL_MAT && b->ne[1] >= 16 && is_q_weight(a->type)) {
+            // resident weights: the row exponents of the tensor-core path (launch_weight_rowexp) are computed once per mirror view
+            for (int64_t i3 = 0; i3 < a->ne[3]; i3++) for (int64_t i2 = 0; i2 < a->ne[2]; i2++) {
+                const RowExpKey key{(size_t)(i2 * a->nb[2] + i3 * a->nb[3]), a->type, a->ne[1], a->ne[0], (int64_t)a->nb[1]};
+                auto f = mir->rowexp.find(key);
+                if (f == mir->rowexp.end()) {
+                    int *ew = nullptr;
+                    GGB_CUDA(cudaMalloc(reinterpret_cast<void **>(&ew), align_up((size_t)std::max<int64_t>(a->ne[1], 1) * 4, 256)));
+                    rc = launch_weight_rowexp(a->type, it.da + key.off, (int64_t)a->nb[1], a->ne[1], a->ne[0], ew, s);
+                    if (rc) { cudaFree(ew); return rc; }
+                    f = mir->rowexp.emplace(key, ew).first;
+                    it.ew_new = true;                            // written on this stream just now: the GEMM's weight side waits
+                }
+                it.ew.push_back(f->second);
+            }
+        }
         if (b && t->op != GGML_OP_CPY && t->op != GGML_OP_SCALE && t->op != GGML_OP_REPEAT) {
-            rc = stage(b, it.level, false, it.db);
+            rc = stage(b, it.level, false, it.db, nullptr, nullptr);
             if (rc) return rc;
         }
         if (in_place) {
             // runs after every earlier node (some of them may still read the old contents), and later readers wait for it
             it.level = std::max(it.level, max_level + 1);
             it.dd = it.da;
-            if (Produced *pr = find_produced(produced, a->data)) pr->level = it.level;
+            if (a_prod) { a_prod->level = it.level; drop_mirrors(od, ospan); }
             else produced.push_back({od, ospan, it.dd, it.level});
         } else {
             it.dd = static_cast<uint8_t *>(pool->arena.take(ospan));
-            if (t->op == GGML_OP_CPY) drop_mirror(o->data);      // a CPY rewrites b->data: a cached mirror of it is stale from here on
+            if (t->op == GGML_OP_CPY) {
+                drop_mirrors(od, ospan);                         // a CPY rewrites b->data: every cached mirror sharing bytes with it is stale from here on
+                // ... and it must not overtake an earlier node of this call that still reads or writes those bytes on the device
+                for (const Produced &pr : produced) if (ranges_overlap(od, ospan, pr.host, pr.bytes)) it.level = std::max(it.level, pr.level + 1);
+            }
             produced.push_back({od, ospan, it.dd, it.level});
         }
         max_level = std::max(max_level, it.level);
@@ -684,6 +781,8 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                     m.Y = reinterpret_cast<float *>(it.dd + i2 * t->nb[2] + i3 * t->nb[3]);
                     // the F16 and quantized drivers index dst as dst_col[ic*ne0] (Ggml.cs:6423, 6697); F32 uses nb1 (6160)
                     m.ldy_bytes = a->type == GGML_TYPE_F32 ? (int64_t)t->nb[1] : (int64_t)t->ne[0] * 4;
+                    if (it.a_in_flight || it.ew_new) m.flags |= GGB_MM_W_IN_FLIGHT;     // src0 is an earlier node's result (CPY -> MUL_MAT), or its exponents are brand new
+                    if (!it.ew.empty()) m.W_rowexp = it.ew[(size_t)(i3 * a->ne[2] + i2)];
                     mms.push_back(m);
                 }
                 break;
@@ -804,6 +903,8 @@ int ggb_device_count(int *count)
     return GGB_OK;
 }
 
+static bool weight_cache_default() { const char *e = getenv("GGB200_WEIGHT_CACHE"); return e && atoi(e) != 0; }
+
 int ggb_pool_alloc(size_t bytes, void **host_base, ggb_pool **out)
 {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -813,7 +914,7 @@ int ggb_pool_alloc(size_t bytes, void **host_base, ggb_pool **out)
     void *p = nullptr;
     GGB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault));   // page-aligned >= GGML_MEM_ALIGN
     ggb_pool *pool = new ggb_pool();
-    pool->host_base = p; pool->bytes = bytes; pool->owned = true;
+    pool->host_base = p; pool->bytes = bytes; pool->owned = true; pool->weight_cache = weight_cache_default();
     *host_base = p; *out = pool;
     return GGB_OK;
 }
@@ -825,7 +926,7 @@ int ggb_pool_adopt(void *host_base, size_t bytes, ggb_pool **out)
     if (reinterpret_cast<uintptr_t>(host_base) % GGML_MEM_ALIGN) return set_error(GGB_E_INVALID, "ggb_pool_adopt: buffer not %d-byte aligned (Ggml.cs:1557)", GGML_MEM_ALIGN);
     // No device work yet: the caller owns the memory; it is pinned lazily at the first compute.
     ggb_pool *pool = new ggb_pool();
-    pool->host_base = host_base; pool->bytes = bytes; pool->owned = false;
+    pool->host_base = host_base; pool->bytes = bytes; pool->owned = false; pool->weight_cache = weight_cache_default();
     *out = pool;
     return GGB_OK;
 }
@@ -835,7 +936,7 @@ int ggb_pool_free(ggb_pool *pool)
     std::lock_guard<std::mutex> lk(g_mu);
     if (!pool) return GGB_OK;
     if (g_inited) cudaStreamSynchronize(g_stream);
-    for (auto &kv : pool->mirrors) cudaFree(kv.second.dptr);
+    for (auto &kv : pool->mirrors) free_mirror(kv.second);
     if (pool->arena.base) cudaFree(pool->arena.base);
     if (pool->registered) cudaHostUnregister(pool->host_base);
     if (pool->owned && pool->host_base) cudaFreeHost(pool->host_base);
@@ -849,9 +950,28 @@ int ggb_tensor_invalidate(ggb_pool *pool, const ggml_tensor *t)
     std::lock_guard<std::mutex> lk(g_mu);
     if (!pool) return set_error(GGB_E_INVALID, "ggb_tensor_invalidate: null pool");
     if (g_inited) cudaStreamSynchronize(g_stream);
-    if (!t) { for (auto &kv : pool->mirrors) cudaFree(kv.second.dptr); pool->mirrors.clear(); return GGB_OK; }
-    auto f = pool->mirrors.find(t->data);
-    if (f != pool->mirrors.end()) { cudaFree(f->second.dptr); pool->mirrors.erase(f); }
+    if (!t) { for (auto &kv : pool->mirrors) free_mirror(kv.second); pool->mirrors.clear(); return GGB_OK; }
+    if (!t->data) return GGB_OK;
+    // every mirror that shares a byte with the tensor (it may be a view of a cached leaf, or a leaf some cached view looks into)
+    const uint8_t *h = static_cast<const uint8_t *>(t->data);
+    const size_t span = tensor_span(t);
+    for (auto f = pool->mirrors.begin(); f != pool->mirrors.end();) {
+        if (ranges_overlap(h, span, static_cast<const uint8_t *>(f->first), f->second.bytes)) { free_mirror(f->second); f = pool->mirrors.erase(f); }
+        else ++f;
+    }
+    return GGB_OK;
+}
+
+int ggb_pool_set_weight_cache(ggb_pool *pool, int on)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pool) return set_error(GGB_E_INVALID, "ggb_pool_set_weight_cache: null pool");
+    pool->weight_cache = on != 0;
+    if (!on) {
+        if (g_inited) cudaStreamSynchronize(g_stream);
+        for (auto &kv : pool->mirrors) free_mirror(kv.second);
+        pool->mirrors.clear();
+    }
     return GGB_OK;
 }
 
@@ -865,28 +985,51 @@ int ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst)
     return run_nodes(pool, nodes, 0, std::vector<char>{1});
 }
 
-int ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *g, int flags, uint8_t *done)
+} // extern "C"
+
+namespace ggb {
+
+// ---- seam B: which nodes of a graph run here ----
+//
+// A node is runnable if it is on the path (MUL_MAT, the F32 -> {F16, quantized} CPY, and unless GGB_GRAPH_MUL_MAT_ONLY the neighbours of
+// mul_mat), its operands are leafs (op NONE) or runnable nodes, and running it AHEAD of the caller's CPU loop cannot change a result.
+// RESHAPE / VIEW / PERMUTE / TRANSPOSE do nothing at compute time (Ggml.cs:8668-8687): "runnable" when their source is, never enqueued.
+//
+// The reference executes strictly in node order (Ggml.cs:3539-3704); this call runs every runnable node before the caller's loop runs
+// the rest.  That reordering is only invisible if no dependency passes through memory the pointer graph does not show, so while
+// scanning in node order the byte ranges every NON-runnable node reads and writes are recorded (an in-place op such as
+// ggml_sqr_inplace writes src0's bytes; a CPY writes src1's), and a later candidate is refused -- and, through operand_ok, everything
+// downstream of it -- when
+//   one of its operands intersects bytes an earlier CPU node writes        (it would read them before they are written),
+//   its output intersects bytes an earlier CPU node reads or writes        (in-place / CPY targets: it would clobber them too early),
+//   or an operand intersects an earlier runnable node's result without lying inside it (neither the device copy nor the host bytes).
+struct ByteRange { const uint8_t *p; size_t n; };
+struct Selection { std::vector<ggml_tensor *> run; std::vector<int> run_idx, view_idx; std::vector<char> is_output; };
+
+static int select_nodes(ggml_cgraph *g, int flags, Selection &sel)
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (!pool || !g) return set_error(GGB_E_INVALID, "ggb_graph_compute_mul_mats: null argument");
     if (g->n_nodes < 0 || g->n_nodes > GGML_MAX_NODES) return set_error(GGB_E_INVALID, "graph with %d nodes", g->n_nodes);
-    // A node is runnable here if it is on the path (MUL_MAT, the F32 -> {F16,Q4_0,Q4_1} CPY, and unless GGB_GRAPH_MUL_MAT_ONLY the
-    // neighbours of mul_mat) and its operands are leafs (op NONE) or runnable nodes.  RESHAPE / VIEW / PERMUTE / TRANSPOSE do
-    // nothing at compute time (Ggml.cs:8668-8687): they are "runnable" when their source is, marked done, and never enqueued.
-    std::vector<ggml_tensor *> run;
-    std::vector<int> run_idx, view_idx;
     std::map<const ggml_tensor *, bool> runnable;
     const bool neighbours = !(flags & GGB_GRAPH_MUL_MAT_ONLY);
+    std::vector<ByteRange> cpu_reads, cpu_writes;
+    std::vector<Produced> gpu_results;                            // host byte ranges of the runnable nodes' results, in order
+    auto range_of = [](const ggml_tensor *x) { return ByteRange{static_cast<const uint8_t *>(x->data), x->data ? tensor_span(x) : 0}; };
+    auto hits = [](const std::vector<ByteRange> &v, ByteRange r) {
+        if (!r.p || !r.n) return false;
+        for (const ByteRange &e : v) if (ranges_overlap(r.p, r.n, e.p, e.n)) return true;
+        return false;
+    };
+    auto out_tensor = [](ggml_tensor *t) -> ggml_tensor * { return t->op == GGML_OP_CPY ? t->src1 : t; };
     for (int i = 0; i < g->n_nodes; i++) {
         ggml_tensor *t = g->nodes[i];
-        if (done) done[i] = 0;
         if (!t) return set_error(GGB_E_INVALID, "graph node %d is null", i);
         auto operand_ok = [&](const ggml_tensor *o) { return o && (o->op == GGML_OP_NONE || runnable.count(o)); };
         bool ok = false;
         if (neighbours && is_view_op(t->op)) {
-            if (operand_ok(t->src0)) { runnable[t] = true; view_idx.push_back(i); }
-            continue;
+            if (operand_ok(t->src0)) { runnable[t] = true; sel.view_idx.push_back(i); }
+            continue;                                             // a view node touches no bytes either way
         }
+        if (is_view_op(t->op)) continue;
         if (t->op == GGML_OP_MUL_MAT || t->op == GGML_OP_CPY || (neighbours && is_neighbour_op(t->op))) {
             const bool unary = t->op == GGML_OP_SILU || t->op == GGML_OP_RMS_NORM || t->op == GGML_OP_CONT || t->op == GGML_OP_DUP;
             // REPEAT's src1 only supplies the shape (Ggml.cs:8015-8034); it is never read
@@ -896,31 +1039,89 @@ int ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *g, int flags, uint8_
                 if (rc == GGB_E_INVALID) return rc;        // the reference would assert: report it
                 ok = rc == GGB_OK;                         // unsupported: leave the node to the caller's loop
             }
+            if (ok) {
+                // ---- memory hazards against the nodes that stay on the CPU, and partial views of device results ----
+                const ByteRange ra = range_of(t->src0), rb = (need_b && t->op != GGML_OP_CPY) ? range_of(t->src1) : ByteRange{nullptr, 0};
+                const ByteRange ro = range_of(out_tensor(t));
+                if (hits(cpu_writes, ra) || hits(cpu_writes, rb) || hits(cpu_writes, ro) || hits(cpu_reads, ro)) ok = false;
+                bool partial = false;
+                if (ok && ra.p) { find_produced(gpu_results, ra.p, ra.n, &partial); if (partial) ok = false; }
+                if (ok && rb.p) { find_produced(gpu_results, rb.p, rb.n, &partial); if (partial) ok = false; }
+                if (ok && ro.p && ra.p && !(ro.p == ra.p)) {
+                    // an output that shares bytes with an earlier device result must BE that result's range (in place) or a CPY target
+                    if (t->op != GGML_OP_CPY) { find_produced(gpu_results, ro.p, ro.n, &partial); if (partial) ok = false; }
+                }
+            }
         }
-        if (ok) { runnable[t] = true; run.push_back(t); run_idx.push_back(i); }
+        if (ok) {
+            runnable[t] = true; sel.run.push_back(t); sel.run_idx.push_back(i);
+            const ByteRange ro = range_of(out_tensor(t));
+            gpu_results.push_back({ro.p, ro.n, nullptr, 0});
+        } else {
+            // stays with the caller: remember what it touches.  Its result bytes (a CPY's are src1's), and for safety every operand it names.
+            if (t->src0 && t->src0->data) cpu_reads.push_back(range_of(t->src0));
+            if (t->src1 && t->src1->data) cpu_reads.push_back(range_of(t->src1));
+            for (int k = 0; k < GGML_MAX_OPT; k++) { const ggml_tensor *o = reinterpret_cast<const ggml_tensor *>(t->opt[k]); if (o && o->data) cpu_reads.push_back(range_of(o)); }
+            ggml_tensor *o = out_tensor(t);
+            if (o && o->data) cpu_writes.push_back(range_of(o));
+        }
     }
     // graph outputs = executed nodes nobody else in the executed set consumes (views are looked through)
     auto base_of = [](const ggml_tensor *o) { while (o && is_view_op(o->op) && o->src0) o = o->src0; return o; };
-    std::vector<char> is_output(run.size(), 1);
+    std::vector<ggml_tensor *> &run = sel.run;
+    sel.is_output.assign(run.size(), 1);
     for (size_t i = 0; i < run.size(); i++)
         for (size_t j = i + 1; j < run.size(); j++)
-            if (base_of(run[j]->src0) == run[i] || base_of(run[j]->src1) == run[i]) is_output[i] = 0;
+            if (base_of(run[j]->src0) == run[i] || base_of(run[j]->src1) == run[i]) sel.is_output[i] = 0;
     // a consumer outside the executed set (a CPU op of the caller) needs the data on the host
     for (int i = 0; i < g->n_nodes; i++) {
         ggml_tensor *t = g->nodes[i];
         if (runnable.count(t)) continue;
-        for (size_t j = 0; j < run.size(); j++) if (base_of(t->src0) == run[j] || base_of(t->src1) == run[j]) is_output[j] = 1;
+        for (size_t j = 0; j < run.size(); j++) {
+            if (base_of(t->src0) == run[j] || base_of(t->src1) == run[j]) sel.is_output[j] = 1;
+            // ... also when it reaches the bytes without naming the node (a fresh view tensor over the same data)
+            const ByteRange rj = range_of(out_tensor(run[j]));
+            if ((t->src0 && t->src0->data && ranges_overlap(rj.p, rj.n, static_cast<const uint8_t *>(t->src0->data), tensor_span(t->src0))) ||
+                (t->src1 && t->src1->data && ranges_overlap(rj.p, rj.n, static_cast<const uint8_t *>(t->src1->data), tensor_span(t->src1)))) sel.is_output[j] = 1;
+        }
     }
     // an in-place node (SCALE, *_inplace) shares its host bytes with its source: the LAST writer of a range carries the result
     for (size_t i = 0; i < run.size(); i++)
         for (size_t j = i + 1; j < run.size(); j++)
-            if (run[j]->op != GGML_OP_CPY && run[j]->data == run[i]->data && run[i]->op != GGML_OP_CPY) is_output[i] = 0;
-    int rc = run_nodes(pool, run, flags, is_output);
+            if (run[j]->op != GGML_OP_CPY && run[j]->data == run[i]->data && run[i]->op != GGML_OP_CPY) sel.is_output[i] = 0;
+    return GGB_OK;
+}
+
+} // namespace ggb
+
+extern "C" {
+
+int ggb_graph_plan(ggml_cgraph *g, int flags, uint8_t *done)
+{
+    if (!g || !done) return set_error(GGB_E_INVALID, "ggb_graph_plan: null argument");
+    Selection sel;
+    int rc = select_nodes(g, flags, sel);
     if (rc) return rc;
-    if (done) { for (int i : run_idx) done[i] = 1; for (int i : view_idx) done[i] = 1; }
+    for (int i = 0; i < g->n_nodes; i++) done[i] = 0;
+    for (int i : sel.run_idx) done[i] = 1;
+    for (int i : sel.view_idx) done[i] = 1;
+    return (int)sel.run.size();
+}
+
+int ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *g, int flags, uint8_t *done)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pool || !g) return set_error(GGB_E_INVALID, "ggb_graph_compute_mul_mats: null argument");
+    Selection sel;
+    int rc = select_nodes(g, flags, sel);
+    if (rc) return rc;
+    if (done) for (int i = 0; i < g->n_nodes; i++) done[i] = 0;
+    rc = run_nodes(pool, sel.run, flags, sel.is_output);
+    if (rc) return rc;
+    if (done) { for (int i : sel.run_idx) done[i] = 1; for (int i : sel.view_idx) done[i] = 1; }
     g->perf_runs++;
     g->perf_time_us += (int64_t)(g_stats.last_graph_device_ms * 1000.0);
-    return (int)run.size();
+    return (int)sel.run.size();
 }
 
 // ---- codecs on host or device pointers ----
@@ -977,6 +1178,14 @@ int ggb_dev_mul_mat_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_b
     if (rc) return rc;
     if (count < 0 || (count && !mm)) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch: bad arguments");
     return dev_batch(mm, count, ws, ws_bytes, stream ? static_cast<cudaStream_t>(stream) : g_stream);
+}
+
+int ggb_dev_weight_rowexp(int type, const void *W, int64_t nb01, int64_t M, int64_t K, int32_t *rowexp, void *stream)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!W || !rowexp) return set_error(GGB_E_INVALID, "ggb_dev_weight_rowexp: null pointer");
+    return launch_weight_rowexp(type, W, nb01, M, K, rowexp, stream ? static_cast<cudaStream_t>(stream) : g_stream);
 }
 
 int ggb_dev_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k, void *stream)

@@ -190,21 +190,24 @@ __device__ __forceinline__ void dequant_word(uint32_t w, uint32_t hb, __half2 d2
 //   Q4_1  words 6j: [f32 d][f32 m][qs x 4]                   (q-8)*d + (m + 8d)      (recentred so the product stays small)
 //   Q4_2  words 5j: [h d0 | qs0 0-1][qs0 2-5][qs0 6-7 | h d1][qs1 0-3][qs1 4-7]      two 16-weight blocks, fp16 scales used as they are
 //   Q5_1  words 6j: [h d | h m][qh][qs x 4]                  (q5-16)*d + (m + 16d)
+// rs = 2^-ew of this weight row (ggb_internal.h: launch_weight_rowexp): the block scale -- float32 in Q4_0 / Q4_1 / Q8_0, fp16 in the
+// others -- is multiplied by it in float BEFORE it is rounded to the fp16 MMA operand, so a row of tiny or huge scales keeps its
+// mantissa (the reference multiplies d0 * d1 * sumi in float32, Ggml.cs:1158) and (q - c) * d never overflows fp16.
 template <int TYPE>
-__device__ __forceinline__ void dequant_group(const uint32_t *w, int j, uint32_t mk_lo, uint32_t mk_hi, uint32_t mg_lo, uint32_t mg_hi, uint32_t *out)
+__device__ __forceinline__ void dequant_group(const uint32_t *w, int j, float rs, uint32_t mk_lo, uint32_t mk_hi, uint32_t mg_lo, uint32_t mg_hi, uint32_t *out)
 {
     if (TYPE == GGML_TYPE_Q4_0 || TYPE == GGML_TYPE_Q4_1) {
         const uint32_t *wb = TYPE == GGML_TYPE_Q4_0 ? &w[5 * j] : &w[6 * j];
-        const __half2 d2 = __float2half2_rn(__uint_as_float(wb[0]));
+        const __half2 d2 = __float2half2_rn(__uint_as_float(wb[0]) * rs);
         __half2 m2 = __float2half2_rn(0.0f);
-        if (TYPE == GGML_TYPE_Q4_1) m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(wb[0]), __uint_as_float(wb[1])));
+        if (TYPE == GGML_TYPE_Q4_1) m2 = __float2half2_rn(fmaf(8.0f, __uint_as_float(wb[0]), __uint_as_float(wb[1])) * rs);
         const uint32_t *qw = TYPE == GGML_TYPE_Q4_0 ? wb + 1 : wb + 2;
 #pragma unroll
         for (int i = 0; i < 4; i++) dequant_word<TYPE>(qw[i], 0u, d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, out + 4 * i);
     } else if (TYPE == GGML_TYPE_Q4_2) {
         const uint32_t *wb = &w[5 * j];
-        uint32_t da = (wb[0] & 0xFFFFu) * 0x00010001u, db = (wb[2] >> 16) * 0x00010001u;          // half2(d0, d0), half2(d1, d1)
-        const __half2 d2a = *reinterpret_cast<__half2 *>(&da), d2b = *reinterpret_cast<__half2 *>(&db), z = __float2half2_rn(0.0f);
+        const __half2 d2a = __float2half2_rn(__half2float(__ushort_as_half((unsigned short)(wb[0] & 0xFFFFu))) * rs);
+        const __half2 d2b = __float2half2_rn(__half2float(__ushort_as_half((unsigned short)(wb[2] >> 16))) * rs), z = __float2half2_rn(0.0f);
         dequant_word<TYPE>(__funnelshift_r(wb[0], wb[1], 16), 0u, d2a, z, mk_lo, mk_hi, mg_lo, mg_hi, out);
         dequant_word<TYPE>(__funnelshift_r(wb[1], wb[2], 16), 0u, d2a, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 4);
         dequant_word<TYPE>(wb[3], 0u, d2b, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 8);
@@ -223,8 +226,7 @@ __device__ __forceinline__ void dequant_group(const uint32_t *w, int j, uint32_t
 #pragma unroll
             for (int i = 0; i < 4; i++) q[i] = __funnelshift_r(wb[1 + i], wb[2 + i], 16);
         }
-        dd *= 0x00010001u;
-        const __half2 d2 = *reinterpret_cast<__half2 *>(&dd), z = __float2half2_rn(0.0f);
+        const __half2 d2 = __float2half2_rn(__half2float(__ushort_as_half((unsigned short)dd)) * rs), z = __float2half2_rn(0.0f);
 #pragma unroll
         for (int i = 0; i < 4; i++) dequant_word<TYPE>(q[i], (qh >> (8 * i)) & 0xFFu, d2, z, mk_lo, mk_hi, mg_lo, mg_hi, out + 4 * i);
     } else if (TYPE == GGML_TYPE_Q8_0) {
@@ -232,7 +234,7 @@ __device__ __forceinline__ void dequant_group(const uint32_t *w, int j, uint32_t
         // into the two halves and ONE LOP3 (immLut 0x6A = b ? a ^ c : c, b = 0x00FF00FF, c = 0x64806480) masks, flips the sign
         // bit and ORs the fp16 magic in: half = 1024 + (q + 128), exact; minus 1152, times d.
         const uint32_t *wb = &w[9 * j];
-        const __half2 d2 = __float2half2_rn(__uint_as_float(wb[0])), o = __float2half2_rn(1152.0f);
+        const __half2 d2 = __float2half2_rn(__uint_as_float(wb[0]) * rs), o = __float2half2_rn(1152.0f);
         uint32_t mk = 0x00FF00FFu, mg = 0x64806480u;
         asm volatile("" : "+r"(mk), "+r"(mg));
 #pragma unroll
@@ -248,10 +250,9 @@ __device__ __forceinline__ void dequant_group(const uint32_t *w, int j, uint32_t
         }
     } else {
         const uint32_t *wb = &w[6 * j];
-        uint32_t dd = (wb[0] & 0xFFFFu) * 0x00010001u;
-        const __half2 d2 = *reinterpret_cast<__half2 *>(&dd);
         const float df = __half2float(__ushort_as_half((unsigned short)(wb[0] & 0xFFFFu))), mf = __half2float(__ushort_as_half((unsigned short)(wb[0] >> 16)));
-        const __half2 m2 = __float2half2_rn(fmaf(16.0f, df, mf));
+        const __half2 d2 = __float2half2_rn(df * rs);
+        const __half2 m2 = __float2half2_rn(fmaf(16.0f, df, mf) * rs);
         const uint32_t qh = wb[1];
 #pragma unroll
         for (int i = 0; i < 4; i++) dequant_word<TYPE>(wb[2 + i], (qh >> (8 * i)) & 0xFFu, d2, m2, mk_lo, mk_hi, mg_lo, mg_hi, out + 4 * i);

@@ -57,6 +57,7 @@ namespace {
 constexpr int GGML_MAX_CONTEXTS = 64;
 constexpr int GGML_DEFAULT_N_THREADS = 4;      // Ggml.cs:22
 constexpr int CACHE_LINE_SIZE = 64;
+constexpr int GGML_OP_SQR_ = 6;                // TypeDefinitions.cs:180 -- an op the backend does not take
 
 struct Slot { bool used; ggml_context ctx; ggb_pool *pool; };
 Slot g_state[GGML_MAX_CONTEXTS];
@@ -72,6 +73,14 @@ ggb_pool *pool_of(const ggml_context *ctx)
     for (auto &s : g_state) if (s.used && &s.ctx == ctx) return s.pool;
     return nullptr;
 }
+// the pool whose arena holds these bytes (ggml_set_* take a tensor, not a context)
+ggb_pool *pool_holding(const void *p)
+{
+    const uint8_t *q = static_cast<const uint8_t *>(p);
+    for (auto &s : g_state)
+        if (s.used && q >= static_cast<const uint8_t *>(s.ctx.mem_buffer) && q < static_cast<const uint8_t *>(s.ctx.mem_buffer) + s.ctx.mem_size) return s.pool;
+    return nullptr;
+}
 
 } // namespace
 
@@ -79,6 +88,13 @@ extern "C" {
 
 int ggml_host_last_status(void) { return g_last_status; }
 void *ggml_host_pool_of(const ggml_context *ctx) { return pool_of(ctx); }       // tests drive seam B directly with flags
+// Opt in to weight residency for a context: leaf src0 tensors stay on the device between ggml_graph_compute calls.
+// Off by default, because the reference re-reads src0->data on every compute (Ggml.cs:6139-6164) and user code writes tensor->data directly.
+int ggml_host_set_weight_cache(ggml_context *ctx, int on)
+{
+    ggb_pool *pool = pool_of(ctx);
+    return pool ? ggb_pool_set_weight_cache(pool, on) : GGB_E_INVALID;
+}
 
 ggml_context *ggml_init(ggml_init_params params)
 {
@@ -182,6 +198,8 @@ ggml_tensor *ggml_set_f32(ggml_tensor *t, float value)
     if (t->type != GGML_TYPE_F32) { g_last_status = GGB_E_UNSUPPORTED; return t; }
     const int64_t nr = ggml_nrows(t);
     for (int64_t r = 0; r < nr; r++) { float *p = reinterpret_cast<float *>(static_cast<char *>(t->data) + r * t->nb[1]); for (int64_t i = 0; i < t->ne[0]; i++) p[i] = value; }
+    // a setter of the API rewrites tensor->data: a resident device copy of these bytes (weight cache, opt-in) is stale now
+    if (ggb_pool *pool = pool_holding(t->data)) ggb_tensor_invalidate(pool, t);
     return t;
 }
 float ggml_get_f32_1d(const ggml_tensor *t, int i) { return t->type == GGML_TYPE_F32 ? static_cast<const float *>(t->data)[i] : 0.0f; }
@@ -252,6 +270,9 @@ ggml_tensor *ggml_mul(ggml_context *ctx, ggml_tensor *a, ggml_tensor *b)
     if (!ggml_are_same_shape(a, b)) { g_last_status = GGB_E_INVALID; return nullptr; }
     return unary_or_binary(ctx, GGML_OP_MUL, a, b, false);
 }
+// Ggml.cs:6911-6922, 7978-8000 -- NOT on the B200 path: a node the caller's own CPU loop runs (see ggml_graph_compute below)
+ggml_tensor *ggml_sqr(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_SQR_, a, nullptr, false); }
+ggml_tensor *ggml_sqr_inplace(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_SQR_, a, nullptr, true); }
 ggml_tensor *ggml_silu(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_SILU, a, nullptr, false); }                 // Ggml.cs:8154-8174
 ggml_tensor *ggml_silu_inplace(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_SILU, a, nullptr, true); }
 ggml_tensor *ggml_rms_norm(ggml_context *ctx, ggml_tensor *a) { return unary_or_binary(ctx, GGML_OP_RMS_NORM, a, nullptr, false); }         // Ggml.cs:8199-8220
@@ -349,8 +370,22 @@ void ggml_graph_compute(ggml_context *ctx, ggml_cgraph *g)
     for (int i = 0; i < g->n_nodes; i++)
         if (!done[i]) {
             // RESHAPE/VIEW/PERMUTE/TRANSPOSE are no-ops in the reference (Ggml.cs:8668-8687); anything else is off-path here
-            const int op = g->nodes[i]->op;
+            ggml_tensor *node = g->nodes[i];
+            const int op = node->op;
             if (op >= 24 && op <= 27) continue;
+            // What the unchanged C# loop does with the nodes the backend left alone (Ggml.cs:3539-3704), in node order.  Two ops are
+            // implemented here so that tests can interleave host-side nodes with device nodes: SQR (Ggml.cs:5109-5130) and the
+            // same-type contiguous CPY (a memcpy, Ggml.cs:4208-4213).  This is the HOST's work, not a fallback of the device path.
+            if (op == GGML_OP_SQR_ && node->type == GGML_TYPE_F32 && node->src0 && node->src0->type == GGML_TYPE_F32) {
+                const float *x = static_cast<const float *>(node->src0->data); float *y = static_cast<float *>(node->data);
+                const int64_t ne = ggml_nelements(node);
+                for (int64_t k = 0; k < ne; k++) y[k] = x[k] * x[k];
+                continue;
+            }
+            if (op == GGML_OP_CPY && node->src0 && node->src1 && node->src0->type == node->src1->type && ggml_nbytes(node->src0) == ggml_nbytes(node->src1)) {
+                memmove(node->src1->data, node->src0->data, ggml_nbytes(node->src0));
+                continue;
+            }
             g_last_status = GGB_E_UNSUPPORTED;
             fprintf(stderr, "ggml_graph_compute: node %d (op %d) is outside the B200 mul_mat path; the C# CPU loop would run it\n", i, op);
         }

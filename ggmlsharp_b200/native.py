@@ -11,6 +11,8 @@ OP_NONE, OP_MUL_MAT, OP_CPY = 0, 20, 22
 OP_DUP, OP_ADD, OP_MUL, OP_REPEAT, OP_SILU, OP_RMS_NORM, OP_SCALE, OP_CONT, OP_TRANSPOSE = 1, 2, 4, 10, 17, 19, 21, 23, 27
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_ABI, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 GRAPH_KEEP_ON_DEVICE, GRAPH_NO_WEIGHT_CACHE, GRAPH_MUL_MAT_ONLY = 1, 2, 4
+MM_W_IN_FLIGHT = 1
+OP_SQR = 6
 
 TYPE_SIZE = {F32: 4, F16: 2, Q4_0: 20, Q4_1: 24, Q4_2: 10, Q5_0: 22, Q5_1: 24, Q8_0: 36, Q8_1: 44, I8: 1, I16: 2, I32: 4}
 BLCK_SIZE = {F32: 1, F16: 1, Q4_0: 32, Q4_1: 32, Q4_2: 16, Q5_0: 32, Q5_1: 32, Q8_0: 32, Q8_1: 32, I8: 1, I16: 1, I32: 1}
@@ -65,7 +67,8 @@ class ggml_context(C.Structure):
 class ggb_dev_mm(C.Structure):
     _fields_ = [("type", C.c_int32), ("n_peers", C.c_int32), ("M", C.c_int64), ("K", C.c_int64), ("N", C.c_int64),
                 ("W", C.c_void_p), ("nb01", C.c_int64), ("X", C.c_void_p), ("ldx_bytes", C.c_int64),
-                ("Y", C.c_void_p), ("ldy_bytes", C.c_int64), ("Y_peer", C.c_void_p * 7)]
+                ("Y", C.c_void_p), ("ldy_bytes", C.c_int64), ("Y_peer", C.c_void_p * 7),
+                ("W_rowexp", C.c_void_p), ("flags", C.c_int32), ("_pad", C.c_int32)]
 
 
 class ggb_stats(C.Structure):
@@ -92,6 +95,9 @@ GGB_SYMBOLS = {
     "ggb_pool_adopt": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "ggb_pool_free": (C.c_int, [C.c_void_p]),
     "ggb_tensor_invalidate": (C.c_int, [C.c_void_p, TP]),
+    "ggb_pool_set_weight_cache": (C.c_int, [C.c_void_p, C.c_int]),
+    "ggb_graph_plan": (C.c_int, [C.POINTER(ggml_cgraph), C.c_int, C.POINTER(C.c_uint8)]),
+    "ggb_dev_weight_rowexp": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ggb_mul_mat_node": (C.c_int, [C.c_void_p, TP]),
     "ggb_graph_compute_mul_mats": (C.c_int, [C.c_void_p, C.POINTER(ggml_cgraph), C.c_int, C.POINTER(C.c_uint8)]),
     "ggb_quantize_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
@@ -125,6 +131,9 @@ GGB_SYMBOLS = {
 HOST_SYMBOLS = {
     "ggml_host_last_status": (C.c_int, []),
     "ggml_host_pool_of": (C.c_void_p, [C.POINTER(ggml_context)]),
+    "ggml_host_set_weight_cache": (C.c_int, [C.POINTER(ggml_context), C.c_int]),
+    "ggml_sqr": (TP, [C.POINTER(ggml_context), TP]),
+    "ggml_sqr_inplace": (TP, [C.POINTER(ggml_context), TP]),
     "ggml_init": (C.POINTER(ggml_context), [ggml_init_params]),
     "ggml_free": (None, [C.POINTER(ggml_context)]),
     "ggml_nelements": (C.c_int64, [TP]),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GGB_ABI_VERSION 1
+#define GGB_ABI_VERSION 2
 
 /* ---- mirrors of TypeDefinitions.cs ------------------------------------------------ */
 
@@ -144,8 +144,15 @@ int  ggb_pool_adopt(void *host_base, size_t bytes, ggb_pool **pool);
 /* Replaces NativeMemory.AlignedFree (Ggml.cs:1587); frees device mirrors, and the host memory
  * only if ggb_pool_alloc made it (mirrors mem_buffer_owned, Ggml.cs:1546). */
 int  ggb_pool_free(ggb_pool *pool);
-/* Weight (leaf src0) bytes are uploaded on first use and cached by (data, nbytes).  Call this
- * after rewriting a cached weight tensor in place; pass NULL to drop every mirror. */
+/* Weight residency is OPT-IN.  The reference re-reads src0->data on every ggml_graph_compute (Ggml.cs:6139-6164, 6676-6699) and user
+ * code writes tensor->data through raw pointers, so by default every leaf src0 is uploaded again on every compute.  With the cache
+ * on (this call, or env GGB200_WEIGHT_CACHE=1 for pools created afterwards) a leaf src0 is uploaded on first use and its device
+ * mirror kept; the caller then promises that such tensors change only through the API (CPY / in-place graph nodes and ggml_set_*
+ * invalidate by byte range) or are followed by ggb_tensor_invalidate.  Never cached even then: parameters (is_param) and tensors
+ * with a gradient, which ggml_opt rewrites in place between computes (Ggml.cs:1734-1760).  on = 0 also drops every mirror. */
+int  ggb_pool_set_weight_cache(ggb_pool *pool, int on);
+/* Call after rewriting tensor->data of a cached weight behind the API's back: drops every mirror that shares a byte with the
+ * tensor (a view of a cached leaf, or a leaf some cached view looks into); NULL drops every mirror of the pool. */
 int  ggb_tensor_invalidate(ggb_pool *pool, const ggml_tensor *t);
 
 /* ---- seam C / seam B: execute MUL_MAT nodes ------------------------------------------ */
@@ -166,6 +173,13 @@ int  ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst);
  * are leafs or nodes it runs itself.  done[i] (n_nodes bytes, may be NULL) is set to 1 for each
  * node it executed; the caller's loop runs the rest.  Returns the number executed or < 0. */
 int  ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *graph, int flags, uint8_t *done);
+/* The selection alone, without a device: done[i] = 1 for every node the call above would execute (or look through, for view ops).
+ * The reference runs nodes strictly in order (Ggml.cs:3539-3704); seam B runs the selected nodes BEFORE the caller's loop runs the
+ * rest, so a candidate is refused -- with everything downstream of it -- when that reordering could be observed through memory:
+ * an operand that shares bytes with the output of an earlier node left to the CPU (ggml_*_inplace writes src0's bytes, CPY src1's),
+ * an in-place / CPY destination that an earlier CPU node still reads or writes, or an operand that overlaps an earlier selected
+ * node's result without lying inside it.  Returns the number of nodes it would execute or < 0. */
+int  ggb_graph_plan(ggml_cgraph *graph, int flags, uint8_t *done);
 /* Unless GGB_GRAPH_MUL_MAT_ONLY is set the same call also keeps the neighbours of mul_mat in a Llama layer on the device
  * (SURVEY.md 8f), so consecutive MUL_MATs need no host round trip: F32 ADD / MUL (Ggml.cs:4622-4685, 5007-5034), SILU
  * (5705-5747, fp16 table semantics of GGML_SILU_FP16), RMS_NORM (5858-5921), SCALE (6746-6780, in place on the view of src0),
@@ -203,7 +217,19 @@ typedef struct ggb_dev_mm {
     const float *X;  int64_t ldx_bytes;
     float       *Y;  int64_t ldy_bytes;
     float       *Y_peer[7];        /* peer-mapped copies of Y on other GPUs, written by the same kernel */
+    const int32_t *W_rowexp;       /* optional, N >= 16 with quantized W: M ints from ggb_dev_weight_rowexp (computed once while W is
+                                      resident); NULL = computed inside every call (one extra pass over the block headers) */
+    int32_t      flags;            /* GGB_MM_* */
+    int32_t      _pad;
 } ggb_dev_mm;
+#define GGB_MM_W_IN_FLIGHT 1       /* W (or W_rowexp) is written by work enqueued earlier on the same stream: the weight loads, which otherwise
+                                      start before the activation staging has finished, wait for it as well */
+
+/* Range handling of the tensor-core path (N >= 16, quantized W).  The reference multiplies float32 block scales (Ggml.cs:1158,
+ * 1190-1196); the MMA operands are fp16, so each weight row m is pre-scaled by the exact power of two 2^-rowexp[m] and each staged
+ * activation row by its own, and the epilogue multiplies both back.  rowexp[m] = ilogb(largest |value| row m can dequantize to) - 13.
+ * This computes it for M rows of K elements of `type` (row stride nb01 bytes) on `stream`; pass the result as ggb_dev_mm.W_rowexp. */
+int  ggb_dev_weight_rowexp(int type, const void *W, int64_t nb01, int64_t M, int64_t K, int32_t *rowexp, void *stream);
 
 /* Scratch the batch needs (quantized / converted activations, the reference's `wdata`). */
 size_t ggb_dev_workspace_bytes(const ggb_dev_mm *mm, int count);

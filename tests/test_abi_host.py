@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_handshake():
     L = N.lib()
-    assert L.ggb_abi_version() == 1
+    assert L.ggb_abi_version() == 2
     assert L.ggb_abi_check(176, 160, 98360, 32, 20, 24) == 0
     assert L.ggb_abi_check(176, 168, 98360, 32, 20, 24) == N.E_ABI
     assert b"ABI mismatch" in L.ggb_last_error()

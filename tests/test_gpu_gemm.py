@@ -34,7 +34,8 @@ def test_gemm_vs_oracle(t, M, K, Nn):
     wb = orc.encode_weights(t, W)
     N.lib().ggb_reset_stats()
     got = dev_mul_mat(t, wb, M, K, X)
-    assert N.stats().kernel_launches == 2            # activation kernel + one tcgen05 GEMM launch (not GEMV passes)
+    # (row exponents of quantized weights, when the caller does not pass W_rowexp) + activation kernel + ONE tcgen05 GEMM launch, not GEMV passes
+    assert N.stats().kernel_launches == (2 if t == N.F16 else 3)
     want = orc.mul_mat_2d(t, wb, M, K, X, nth=16)
     err = rel_l2(got, want)
     print('GEMM_ERR type=%d M=%d K=%d N=%d rel_l2=%.3e' % (t, M, K, Nn, err))
@@ -95,7 +96,7 @@ def test_graph_compute_routes_prompt_batches_to_the_tensor_core_path():
         g = c.build_forward(y2)
         N.lib().ggb_reset_stats()
         c.graph_compute(g)
-        assert N.stats().kernel_launches == 5          # 2 x (activation + GEMM) + 1 result-copy kernel... or memcpy for large results
+        assert N.stats().kernel_launches == 6          # Q4_0: row exponents + activation + GEMM; F16: activation + GEMM; + 1 result-copy kernel (y1 goes by memcpy)
         g1, g2 = ggml.tensor_f32(y1).reshape(Nn, M1).copy(), ggml.tensor_f32(y2).reshape(Nn, M2).copy()
     assert rel_l2(g1, orc.mul_mat_2d(orc.Q4_0, w1b, M1, K, X, nth=8)) <= 1e-3
     assert rel_l2(g2, orc.mul_mat_2d(orc.F16, w2b, M2, M1, g1, nth=8)) <= 1e-4
@@ -114,7 +115,7 @@ def test_kernel_timing_brackets_only_the_mul_mat_kernels():
         s = N.stats()
     finally:
         N.check(L.ggb_set_kernel_timing(0))
-    assert s.kernel_launches == 4 and s.timed_kernel_launches == 2 and 0.0 < s.timed_kernel_ms < 5.0
+    assert s.kernel_launches == 5 and s.timed_kernel_launches == 2 and 0.0 < s.timed_kernel_ms < 5.0
 
 
 def dev_mul_mat_batch(nodes):
@@ -155,7 +156,7 @@ def test_grouped_gemm_batch_vs_oracle(t):
         nodes.append((t, wb, M, K, rng.standard_normal((Nn, K)).astype(np.float32)))
     N.lib().ggb_reset_stats()
     got = dev_mul_mat_batch(nodes)
-    assert N.stats().kernel_launches == 2
+    assert N.stats().kernel_launches == (2 if t == N.F16 else 3)      # (one row-exponent launch for all nodes) + one activation launch + one GEMM launch
     for (tt, wb, M, K, X), y in zip(nodes, got):
         want = orc.mul_mat_2d(tt, wb, M, K, X, nth=16)
         err = rel_l2(y, want)
@@ -272,3 +273,149 @@ def test_two_weight_types_consuming_a_fresh_intermediate():
             else:
                 for k, (a, b) in enumerate(zip(base, got)):
                     assert rel_l2(b, a) <= 1e-5, (rep, k, float(scale), rel_l2(b, a))
+
+
+# ---- fp16 operand range of the tensor-core path ----------------------------------------------------------
+#
+# The reference keeps block scales in float32 and multiplies d0 * d1 * sumi in float32 (Ggml.cs:1158, 1190-1196), so its result is
+# exact under any power-of-two rescaling of x or W.  The MMA operands are fp16; without range handling a block scale under 6e-8
+# becomes 0, values under 6.1e-5 go subnormal and anything above 65504 becomes inf.  Every operand row is therefore pre-scaled by an
+# exact power of two (per activation row: exponent of the row's largest |x|; per weight row: exponent of the largest value a block
+# can dequantize to) and the epilogue multiplies both back.  These tests hold the 1e-3 contract far outside O(1) data.
+
+def scale_weights(t, wb, M, K, e):
+    """Multiply a quantized weight matrix by 2^e exactly, by rewriting the float32 / fp16 block scales (and offsets) in place."""
+    wb = np.ascontiguousarray(wb).reshape(M, -1).copy()
+    f = np.float32(2.0 ** e)
+    if t in (N.Q4_0, N.Q8_0):
+        bs = 20 if t == N.Q4_0 else 36
+        blk = wb.reshape(M, -1, bs)
+        d = blk[:, :, 0:4].copy().view(np.float32)
+        blk[:, :, 0:4] = (d * f).astype(np.float32).view(np.uint8)
+    elif t == N.Q4_1:
+        blk = wb.reshape(M, -1, 24)
+        dm = blk[:, :, 0:8].copy().view(np.float32)
+        blk[:, :, 0:8] = (dm * f).astype(np.float32).view(np.uint8)
+    elif t == N.Q5_1:
+        blk = wb.reshape(M, -1, 24)
+        dm = blk[:, :, 0:4].copy().view(np.float16).astype(np.float32) * f
+        assert np.all(np.isfinite(dm.astype(np.float16)))
+        blk[:, :, 0:4] = dm.astype(np.float16).view(np.uint8)
+    else:
+        raise AssertionError(t)
+    return wb.reshape(M, -1)
+
+
+RANGE_TYPES = [N.Q4_0, N.Q4_1, N.Q5_1, N.Q8_0]
+
+
+@pytest.mark.parametrize("t", RANGE_TYPES)
+@pytest.mark.parametrize("ex,ew", [(20, 0), (-20, 0), (0, 12), (0, -12), (20, -12), (-20, 12), (30, 30), (-30, -30)])
+def test_gemm_operand_range_power_of_two_rescaling(t, ex, ew):
+    rng = np.random.default_rng(7000 + t)
+    M, K, Nn = 256, 1024, 48
+    if t == N.Q5_1:
+        ew = max(-4, min(4, ew))                       # its block scales are fp16 in the reference format itself; stay inside fp16
+    W = weights(rng, M, K)
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    wb0 = orc.encode_weights(t, W)
+    wb = scale_weights(t, wb0, M, K, ew)
+    Xs = (X * np.float32(2.0 ** ex)).astype(np.float32)
+    got = dev_mul_mat(t, wb, M, K, Xs)
+    want = orc.mul_mat_2d(t, wb, M, K, Xs, nth=8)
+    assert np.all(np.isfinite(got)), "fp16 operand overflow"
+    err = rel_l2(got, want)
+    print('RANGE type=%d ex=%d ew=%d rel_l2=%.3e' % (t, ex, ew, err))
+    assert err <= 1e-3, (t, ex, ew, err)
+    # ... and it is the SAME answer as on the unscaled data, times 2^(ex + ew): the pre-scaling is exact
+    base = dev_mul_mat(t, wb0, M, K, X)
+    assert rel_l2(got / np.float64(2.0 ** (ex + ew)), base) <= 2e-6, (t, ex, ew)
+
+
+@pytest.mark.parametrize("t", [N.Q4_0, N.Q4_1])
+def test_gemm_outlier_rows_and_scales_near_fp16_limits(t):
+    """One 1e5 activation row and one 3e-7 row among N(0, 1) rows; weight rows whose block scales sit near fp16's largest (6e4) and
+    smallest (6e-8) values among N(0, 0.02) rows.  Per-ROW exponents keep every row at full precision."""
+    rng = np.random.default_rng(7100 + t)
+    M, K, Nn = 384, 512, 32
+    W = weights(rng, M, K)
+    W[7] *= 4.0e6          # block scales ~ 3e4: d itself still fits fp16, (q - 8) * d does not
+    W[100] *= 3.0e9        # scales ~ 2e7: far above fp16
+    W[200] *= 2.0e-5       # scales ~ 1.5e-7: fp16 subnormal
+    W[300] *= 1.0e-9       # scales ~ 8e-12: zero in fp16
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    X[3] *= 1.0e5
+    X[9] *= 3.0e-7
+    X[20] *= 1.0e-12
+    wb = orc.encode_weights(t, W)
+    got = dev_mul_mat(t, wb, M, K, X)
+    want = orc.mul_mat_2d(t, wb, M, K, X, nth=8)
+    assert np.all(np.isfinite(got))
+    # row by row and column by column: an overall rel-L2 would be dominated by the 1e5 row x the 3e9 weight row
+    for n in range(Nn):
+        assert rel_l2(got[n], want[n]) <= 1e-3, ("activation row", n, rel_l2(got[n], want[n]))
+    for m in (7, 100, 200, 300, 0, 383):
+        assert rel_l2(got[:, m], want[:, m]) <= 1e-3, ("weight row", m, rel_l2(got[:, m], want[:, m]))
+
+
+def test_gemm_with_precomputed_row_exponents_matches_the_in_call_ones():
+    """ggb_dev_weight_rowexp once while the weights are resident, then ggb_dev_mm.W_rowexp: same bits as computing them in the call,
+    one launch fewer."""
+    from test_gpu_parity import Dev
+    rng = np.random.default_rng(7200)
+    M, K, Nn = 512, 1024, 64
+    W = weights(rng, M, K)
+    W[5] *= 1.0e6
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    wb = orc.encode_weights(N.Q4_0, W)
+    ref = dev_mul_mat(N.Q4_0, wb, M, K, X)
+    d = Dev()
+    try:
+        mm = N.ggb_dev_mm()
+        mm.type, mm.M, mm.K, mm.N = N.Q4_0, M, K, Nn
+        mm.W, mm.nb01 = d.put(wb), 20 * (K // 32)
+        mm.X, mm.ldx_bytes = d.put(X), 4 * K
+        mm.Y, mm.ldy_bytes = d.empty(4 * M * Nn), 4 * M
+        rowexp = d.empty(4 * M)
+        N.check(N.lib().ggb_dev_weight_rowexp(N.Q4_0, mm.W, mm.nb01, M, K, rowexp, None))
+        e = d.get(rowexp, (M,), dtype=np.int32)
+        # ilogb(8 * max|d|) - 13, from the bytes
+        dmax = np.abs(np.ascontiguousarray(wb).reshape(M, -1, 20)[:, :, 0:4].copy().view(np.float32)).max(axis=(1, 2))
+        assert np.array_equal(e, np.floor(np.log2(8.0 * dmax.astype(np.float64))).astype(np.int32) - 13)
+        mm.W_rowexp = rowexp
+        wsb = N.lib().ggb_dev_workspace_bytes(C.byref(mm), 1)
+        ws = d.empty(wsb)
+        N.lib().ggb_reset_stats()
+        N.check(N.lib().ggb_dev_mul_mat_batch(C.byref(mm), 1, ws, wsb, None))
+        N.check(N.lib().ggb_stream_sync(None))
+        assert N.stats().kernel_launches == 2
+        assert np.array_equal(d.get(mm.Y, (Nn, M)), ref)
+    finally:
+        d.close()
+
+
+def test_expansion_fallback_honours_the_range_too():
+    # K = 160 takes the fp16-expansion path (k_expand_f16 + the F16 kernel): same pre-scaling there
+    rng = np.random.default_rng(7300)
+    M, K, Nn = 200, 160, 24
+    W = weights(rng, M, K) * np.float32(2.0 ** 24)
+    X = (rng.standard_normal((Nn, K)) * 2.0 ** -22).astype(np.float32)
+    wb = orc.encode_weights(N.Q4_0, W)
+    got = dev_mul_mat(N.Q4_0, wb, M, K, X)
+    assert np.all(np.isfinite(got))
+    assert rel_l2(got, orc.mul_mat_2d(N.Q4_0, wb, M, K, X, nth=4)) <= 1e-3
+
+
+def test_f16_weights_keep_the_reference_half_conversion():
+    # F16 weights: the reference itself rounds src1 to Half (Ggml.cs:6362-6379), overflow to inf included -- no rescaling there
+    rng = np.random.default_rng(7400)
+    M, K, Nn = 128, 256, 16
+    W = weights(rng, M, K)
+    X = rng.standard_normal((Nn, K)).astype(np.float32)
+    X[2, 5] = 1.0e6                                       # (Half)1e6 = +inf in the reference
+    wb = orc.encode_weights(N.F16, W)
+    got = dev_mul_mat(N.F16, wb, M, K, X)
+    want = orc.mul_mat_2d(N.F16, wb, M, K, X, nth=4)
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    ok = np.isfinite(want)
+    assert rel_l2(got[ok], want[ok]) <= 1e-4
