@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration sub-records (configs[0], [2], [3], [4]) of the N=1 line")
     ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a captured CUDA graph")
     ap.add_argument("--epilogue-stores", action="store_true", help="fused gather through per-row peer stores in the GEMV epilogue instead of the push kernel")
@@ -446,6 +447,21 @@ def main():
            "h2d_bytes_per_step": int(s_e2e.h2d_bytes // n_e2e) * world, "d2h_bytes_per_step": int(s_e2e.d2h_bytes // n_e2e) * world,
            "device_ms_per_step": float(s_e2e.last_graph_device_ms),       # CUDA-event span of the last call: staging reads over PCIe + kernels + result copy
            "api": "ggml_graph_compute over a %d-node graph per rank (host arena, weights device-cached)%s" % (RING, "; each rank reads back its own dst block" if world > 1 else "")}
+    # ---- every other BASELINE.json configuration on this GPU, as sub-records of the same line (device-resident, CUDA events on the
+    #      launching stream; benchmarks/bench_configs.py: Runner).  configs[1] -- the ring above -- stays the line's `value`. ----
+    if world == 1 and not args.no_configs:
+        from benchmarks.bench_configs import Runner
+        pk = {}
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                pk = json.load(f)
+        del Wq, X, ws
+        torch.cuda.empty_cache()
+        runner = Runner(torch, N, L, dev, stream, float(pk.get("hbm_gbs", 6650.0)), float(pk.get("bf16_tflops", 1590.0)))
+        line["configs"] = list(runner.baseline_records(iters=20))
+        line["configs_note"] = ("one record per BASELINE.json configuration: ms per call of ggb_dev_mul_mat_batch over the listed nodes, achieved = "
+                                "algorithmic bytes (W + x + y) or 2MNK flop / ms, frac of MEASURED_PEAKS.json (hbm_gbs / bf16_tflops burst), "
+                                "frac_of_nominal of 8 TB/s / 2.25 PFLOP/s")
     if rank == 0:
         line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
