@@ -691,11 +691,10 @@ int launch_quantize_rows(int type, const float *src, int64_t ldx, void *dst, int
     case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_1: {
         const int bs = type == GGML_TYPE_Q4_0 ? 20 : 24;
         const size_t smem = (size_t)QT_WARPS * (QT_STAGES * 32 * QT_ROW + 32 * bs);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_once;
+        if (attr_once.need()) {
             GGB_CUDA(cudaFuncSetAttribute(k_quantize_q4_tiles<GGML_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QT_WARPS * (QT_STAGES * 32 * QT_ROW + 32 * 20))));
             GGB_CUDA(cudaFuncSetAttribute(k_quantize_q4_tiles<GGML_TYPE_Q4_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(QT_WARPS * (QT_STAGES * 32 * QT_ROW + 32 * 24))));
-            attr_set = true;
         }
         const long long ntiles = (nblk + 31) / 32;
         const unsigned gridt = (unsigned)std::min<long long>((ntiles + QT_WARPS - 1) / QT_WARPS, (long long)device_sm_count() * 3);

@@ -369,8 +369,8 @@ int launch_quantize_rows_sib(int type, const float *src, int64_t ldx, void *dst,
         const unsigned gridt = (unsigned)std::min<long long>((ntiles + ST_WARPS - 1) / ST_WARPS, (long long)device_sm_count() * 3);
         GGB_SIB_SWITCH(type, {
             constexpr size_t smem = (size_t)ST_WARPS * (ST_STAGES * 32 * ST_ROW + (32 * Sib<T>::G + 15) / 16 * 16);
-            static bool attr_set = false;
-            if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_quantize_sib_tiles<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+            static PerDeviceOnce attr_once;
+            if (attr_once.need()) { GGB_CUDA(cudaFuncSetAttribute(k_quantize_sib_tiles<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
             k_quantize_sib_tiles<T><<<gridt, ST_WARPS * 32, smem, s>>>(src, ldx, (uint8_t *)dst, ngrp, kb);
         });
     } else {

@@ -147,12 +147,16 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
     } else if (warp >= 4) {
         // ===== epilogue on all 16 warps: warp -> (TMEM lane quadrant warp%4, 32-column group) =====
         const int q = warp & 3;
-        mbar_wait(BAR(ACC_FULL), 0);
-        tc_fence_after();
         const int m = m0 + q * 32 + lane;
         const int nbase = blockIdx.y * BN;
-        int ewr = 0;
-        if (ew) { asm volatile("griddepcontrol.wait;" ::: "memory"); if (m < M) ewr = __ldcg(ew + m); }
+        float fw = 1.0f, fxl = 1.0f;
+        if (ew) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (m < M) fw = exp2i(__ldcg(ew + m));
+            fxl = exp2i(__ldcg(ex + nbase + ((warp - 4) >> 2) * 32 + lane));   // BN = 128: one 32-column group per warp; lane l holds column l's factor
+        }
+        mbar_wait(BAR(ACC_FULL), 0);
+        tc_fence_after();
 #pragma unroll 1
         for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
@@ -168,13 +172,13 @@ k_gemm_f16(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CU
                 GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
 #undef GGB_TMEM_LD16
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (m < M) {
+                {
 #pragma unroll
                     for (int c = 0; c < 16; c++) {
                         const int n = nbase + cb * 32 + hc * 16 + c;
                         float r = ksteps > 1 ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);
-                        if (n < N) {
-                            if (ew) r = scale2(r, ewr + __ldcg(ex + n));
+                        if (ew) r = scale_pair(r, fw, __shfl_sync(0xffffffffu, fxl, hc * 16 + c));      // warp-uniform branch; every lane takes part in the shuffle
+                        if (m < M && n < N) {
                             Y[(long long)n * ldy + m] = r;
                             for (int pp = 0; pp < peers.n; pp++) peers.y[pp][(long long)n * ldy + m] = r;
                         }
@@ -384,13 +388,15 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
         {
             // epilogue on all 16 warps: warp -> (TMEM lane quadrant warp%4, 32-column group)
             const int q = warp & 3;
+            const int m = m0 + q * 32 + lane;
+            const int nbase = blockIdx.y * BN;
+            // before the wait for the accumulators, so the loads hide behind the last MMAs: lane l's factor 2^ex of column l of this warp's group
+            asm volatile("griddepcontrol.wait;" ::: "memory");         // ex was written by the activation kernel (long complete: the B tiles came from it)
+            const float fw = exp2i(m < M ? __ldcg(ew + m) : 0);
+            const float fxl = exp2i(__ldcg(ex + nbase + ((warp - 4) >> 2) * 32 + lane));   // BN = 128: one 32-column group per warp
             mbar_wait(BAR(ACC_FULL), 0);
             if (tdbg && threadIdx.x == 128) tdbg[2] = clock64();
             tc_fence_after();
-            const int m = m0 + q * 32 + lane;
-            const int nbase = blockIdx.y * BN;
-            asm volatile("griddepcontrol.wait;" ::: "memory");         // ex was written by the activation kernel (long complete: the B tiles came from it)
-            const int ewr = m < M ? __ldcg(ew + m) : 0;
 #pragma unroll 1
             for (int cb = (warp - 4) >> 2; cb < BN / 32; cb += NDQ_WARPS / 4) {
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
@@ -406,13 +412,13 @@ k_gemm_q(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUte
                     GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
 #undef GGB_TMEM_LD16
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (m < M) {
+                    {
 #pragma unroll
                         for (int c = 0; c < 16; c++) {
                             const int n = nbase + cb * 32 + hc * 16 + c;
                             float r = ksteps > 1 ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);   // even-K + odd-K partial sums
-                            if (n < N) {
-                                r = scale2(r, ewr + __ldcg(ex + n));       // undo the operands' power-of-two pre-scaling (exact)
+                            r = scale_pair(r, fw, __shfl_sync(0xffffffffu, fxl, hc * 16 + c));   // undo the operands' power-of-two pre-scaling (exact); every lane shuffles
+                            if (m < M && n < N) {
                                 Y[(long long)n * ldy + m] = r;
                                 for (int pp = 0; pp < peers.n; pp++) peers.y[pp][(long long)n * ldy + m] = r;
                             }
@@ -483,8 +489,8 @@ int launch_f16(const GemmArgs &a, cudaStream_t s)
     constexpr int STAGES = CG == 2 ? 4 : 3;
     constexpr size_t smem = 1024 + STAGES * (size_t)(BM * BK * 2) + STAGES * (size_t)(BNL * BK * 2) + 64 * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool attr_set = false;
-    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemm_f16<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { GGB_CUDA(cudaFuncSetAttribute(k_gemm_f16<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
     const unsigned mt = (unsigned)((a.M + BM - 1) / BM);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((mt + CG - 1) / CG * CG, (unsigned)((a.N + BN - 1) / BN));    // whole CTA pairs; a padding CTA sees only out-of-bounds (zero) rows
@@ -520,8 +526,8 @@ int launch_q(const GemmArgs &a, cudaStream_t s)
     if (rc) return rc;
     constexpr size_t smem = 1024 + (size_t)QStages<TYPE, CG>::B * (BNL * BK * 2) + (size_t)QStages<TYPE, CG>::RAW * (BM * RAW_ROW) + 64 * 8 + 16;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    static bool attr_set = false;
-    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemm_q<TYPE, BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { GGB_CUDA(cudaFuncSetAttribute(k_gemm_q<TYPE, BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
     const unsigned mt = (unsigned)((a.M + BM - 1) / BM);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((mt + CG - 1) / CG * CG, (unsigned)((a.N + BN - 1) / BN));

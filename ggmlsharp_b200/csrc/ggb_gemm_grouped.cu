@@ -183,10 +183,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
         uint32_t mk_lo = 0x000F000Fu, mk_hi = 0x00F000F0u, mg_lo = 0x64006400u, mg_hi = 0x54005400u;
         asm volatile("" : "+r"(mk_lo), "+r"(mk_hi), "+r"(mg_lo), "+r"(mg_hi));
         uint32_t gk0 = 0, it = 0;
+        int ew_next = 0;
         if (G.wait_w) asm volatile("griddepcontrol.wait;" ::: "memory");       // ew comes from a kernel launched earlier in this batch
         for (int t = pair; t < G.total_tiles; t += npairs, it++) {
             const Tile tl = locate(t);
-            const int ewr = (tl.m0 + r) < tl.nd->M ? __ldcg(tl.nd->ew + tl.m0 + r) : 0;   // this thread's weight row of the tile
+            // this thread's weight row of the tile: its exponent was fetched while the previous tile's accumulators were drained
+            const int ewr = it ? ew_next : ((tl.m0 + r) < tl.nd->M ? __ldcg(tl.nd->ew + tl.m0 + r) : 0);
             const float rs = exp2i(-ewr);
             for (int ks = (int)((g - gk0) & 3); ks < tl.ksteps; ks += 4) {
                 const uint32_t gk = gk0 + (uint32_t)ks;
@@ -217,16 +219,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
             gk0 += (uint32_t)tl.ksteps;
 
             // ---- epilogue of this tile: warp -> (lane quadrant q, 32-column groups g, g+4, ...) ----
+            const GroupNode &nd = *tl.nd;
+            // Issued BEFORE the wait for the accumulators, so their latency hides behind the last MMAs: lane l's factor 2^ex of column
+            // cb*32 + l of each of this warp's column groups (broadcast per column by SHFL below), and the NEXT tile's weight-row exponent.
+            if (it == 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // ex was written by the activation kernel (complete: the B tiles came from it)
+            float fxl[BN / 128];
+#pragma unroll
+            for (int j = 0; j < BN / 128; j++) fxl[j] = exp2i(__ldcg(nd.ex + tl.n0 + (g + 4 * j) * 32 + lane));
+            if (t + npairs < G.total_tiles) {
+                const Tile nx = locate(t + npairs);
+                ew_next = (nx.m0 + r) < nx.nd->M ? __ldcg(nx.nd->ew + nx.m0 + r) : 0;
+            }
+            const float fw = exp2i(ewr);
             mbar_wait(BAR(ACC_FULL), it & 1);
             tc_fence_after();
-            const GroupNode &nd = *tl.nd;
             const int m = tl.m0 + q * 32 + lane;
             const bool two = NISSUE == 2 && tl.ksteps > 1;
-            if (it == 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // ex was written by the activation kernel (complete: the B tiles came from it)
-            const int *__restrict__ exn = nd.ex;
 #pragma unroll 1
             for (int cb = g; cb < BN / 32; cb += NDQ_WARPS / 4) {
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
+                const float fx_cb = (BN == 256 && cb != g) ? fxl[BN / 128 - 1] : fxl[0];     // a select, not a dynamically indexed register array
 #pragma unroll 1
                 for (int hc = 0; hc < 2; hc++) {                      // 16 columns at a time keeps both accumulators in 32 registers
                     uint32_t v[16], u[16];
@@ -239,13 +251,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_q_grouped(const __grid_con
                     if (NISSUE == 2) GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
 #undef GGB_TMEM_LD16
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (m < nd.M) {
+                    {
 #pragma unroll
                         for (int c = 0; c < 16; c++) {
                             const int n = tl.n0 + cb * 32 + hc * 16 + c;
                             float res = two ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);   // even-K + odd-K partial sums
-                            if (n < nd.N) {
-                                res = scale2(res, ewr + __ldcg(exn + n));  // undo the operands' power-of-two pre-scaling (exact)
+                            res = scale_pair(res, fw, __shfl_sync(0xffffffffu, fx_cb, hc * 16 + c));   // undo the operands' power-of-two pre-scaling (exact); every lane shuffles
+                            if (m < nd.M && n < nd.N) {
                                 float *yp = nd.Y + (long long)n * nd.ldy + m;
                                 *yp = res;
                                 for (int pp = 0; pp < nd.n_peers; pp++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + nd.peer_delta[pp]) = res;
@@ -383,8 +395,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_c
             const bool two = tl.ksteps > 1;
             // expanded quantized weights (ggb_shim.cu: use_gemm_expanded) carry row exponents; true F16 weights do not
             const int *__restrict__ exn = nd.ex;
-            int ewr = 0;
-            if (exn) { if (it == 0) asm volatile("griddepcontrol.wait;" ::: "memory"); if (m < nd.M) ewr = __ldcg(nd.ew + m); }
+            float fw = 1.0f, fxl = 1.0f;
+            if (exn) {
+                if (it == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+                if (m < nd.M) fw = exp2i(__ldcg(nd.ew + m));
+                fxl = exp2i(__ldcg(exn + tl.n0 + g * 32 + lane));      // BN = 128: one column group per warp
+            }
 #pragma unroll 1
             for (int cb = g; cb < BN / 32; cb += NDQ_WARPS / 4) {
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * BN + cb * 32);
@@ -400,13 +416,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gemm_f16_grouped(const __grid_c
                     GGB_TMEM_LD16(u, taddr + (uint32_t)(BN + hc * 16));
 #undef GGB_TMEM_LD16
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (m < nd.M) {
+                    {
 #pragma unroll
                         for (int c = 0; c < 16; c++) {
                             const int n = tl.n0 + cb * 32 + hc * 16 + c;
                             float res = two ? __uint_as_float(v[c]) + __uint_as_float(u[c]) : __uint_as_float(v[c]);
-                            if (n < nd.N) {
-                                if (exn) res = scale2(res, ewr + __ldcg(exn + n));
+                            if (exn) res = scale_pair(res, fw, __shfl_sync(0xffffffffu, fxl, hc * 16 + c));      // warp-uniform branch; every lane shuffles
+                            if (m < nd.M && n < nd.N) {
                                 float *yp = nd.Y + (long long)n * nd.ldy + m;
                                 *yp = res;
                                 for (int pp = 0; pp < nd.n_peers; pp++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + nd.peer_delta[pp]) = res;
@@ -438,8 +454,8 @@ int launch_grouped(const GemmGroupT<CAP> &G, cudaStream_t s)
     static_assert(smem <= 227 * 1024, "shared memory budget");
     void (*kern)(const GemmGroupT<CAP>) = nullptr;
     if constexpr (TYPE == GGML_TYPE_F16) kern = k_gemm_f16_grouped<CAP>; else kern = k_gemm_q_grouped<TYPE, CAP, BN>;
-    static bool attr_set = false;
-    if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    static PerDeviceOnce attr_once;
+    if (attr_once.need()) { GGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
@@ -449,7 +465,10 @@ int launch_grouped(const GemmGroupT<CAP> &G, cudaStream_t s)
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     // The tile lists are static, so every pair of the grid must be resident at once: ask how many 2-CTA clusters the device
     // can actually co-schedule (a GPC with an odd number of usable SMs leaves one unpaired) instead of assuming SMs / 2.
-    static int max_pairs = 0;
+    static int max_pairs_dev[16] = {};                          // per device: the GPUs of one box need not have the same usable pairs
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    int &max_pairs = max_pairs_dev[cur_dev & 15];
     if (!max_pairs) {
         cfg.gridDim = dim3((unsigned)(device_sm_count() / 2 * 2));
         cfg.attrs = at; cfg.numAttrs = 1;

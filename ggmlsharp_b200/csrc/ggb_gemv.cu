@@ -569,8 +569,8 @@ int launch_fast_typed(const GemvBatchT<CAP> &b, size_t smem, int grid, cudaStrea
     constexpr bool Q = UnitTraits<TYPE>::Q;
     const bool xreg = Q && b.ncols == 1 && b.nchunk == 1 && b.row_bytes / UnitTraits<TYPE>::BYTES <= 32;
 #define GGB_FAST_CASE(NCV, XR) { \
-        static bool attr_set = false; \
-        if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemv_fast<TYPE, NCV, XR, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; } \
+        static PerDeviceOnce attr_once; \
+        if (attr_once.need()) { GGB_CUDA(cudaFuncSetAttribute(k_gemv_fast<TYPE, NCV, XR, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); } \
         GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemv_fast<TYPE, NCV, XR, CAP>, b)); }
     if (xreg) { if constexpr (Q) GGB_FAST_CASE(1, true) }
     else switch (b.ncols) {
@@ -598,8 +598,8 @@ int launch_typed(const GemvBatchT<CAP> &b, size_t smem, int grid, cudaStream_t s
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
 #define GGB_GEMV_CASE(NCV) case NCV: { \
-        static bool attr_set = false; \
-        if (!attr_set) { GGB_CUDA(cudaFuncSetAttribute(k_gemv<TYPE, NCV, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; } \
+        static PerDeviceOnce attr_once; \
+        if (attr_once.need()) { GGB_CUDA(cudaFuncSetAttribute(k_gemv<TYPE, NCV, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); } \
         GGB_CUDA(cudaLaunchKernelEx(&cfg, k_gemv<TYPE, NCV, CAP>, b)); } break;
     switch (b.ncols) {
         GGB_GEMV_CASE(1) GGB_GEMV_CASE(2) GGB_GEMV_CASE(4) GGB_GEMV_CASE(8)

@@ -136,6 +136,12 @@ int launch_gemm_grouped(const GemmArgs *args, int count, cudaStream_t s);
 int gemm_act_perm(int type);       // 1: the activation buffer must use the K order 0,4,1,5,2,6,3,7 per group of 8
 
 int device_sm_count();
+// cudaFuncSetAttribute (and anything else that is per device) must run once on EVERY device the row split drives:
+// one flag per call site and device ordinal
+struct PerDeviceOnce {
+    bool done[16] = {};
+    bool need() { int d = 0; cudaGetDevice(&d); d &= 15; if (done[d]) return false; done[d] = true; return true; }
+};
 
 #ifdef __CUDACC__
 // ---- exact power-of-two range handling of the tensor-core path (see launch_weight_rowexp) ----
@@ -148,6 +154,9 @@ __device__ __forceinline__ int range_exp(float amax)                            
 }
 // acc * 2^e for e in [-252, 252]: two half-exponent factors, so no intermediate over- or underflows unless the result itself does
 __device__ __forceinline__ float scale2(float acc, int e) { const int h = e >> 1; return acc * exp2i(h) * exp2i(e - h); }
+// acc * fa * fb for two power-of-two factors of possibly opposite sign of exponent: the smaller one first, so that a huge weight
+// exponent against a tiny activation exponent (or the reverse) cannot overflow on the way to an in-range result
+__device__ __forceinline__ float scale_pair(float acc, float fa, float fb) { return (acc * fminf(fa, fb)) * fmaxf(fa, fb); }
 #endif
 
 } // namespace ggb
