@@ -20,6 +20,8 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_tensor_invalidate(IntPtr pool, ggml_tensor* t);
     // weight residency is opt-in: the reference re-reads src0->data on every compute, so the default re-uploads every leaf src0
     [DllImport(Lib)] public static extern int ggb_pool_set_weight_cache(IntPtr pool, int on);
+    // row split of ggml_graph_compute across the GPUs of the box (off by default): max_devices < 0 = all, min_weight_bytes 0 = default 4 MiB
+    [DllImport(Lib)] public static extern int ggb_pool_set_row_split(IntPtr pool, int maxDevices, nuint minWeightBytes);
     [DllImport(Lib)] public static extern int ggb_mul_mat_node(IntPtr pool, ggml_tensor* dst);
     [DllImport(Lib)] public static extern int ggb_graph_compute_mul_mats(IntPtr pool, ggml_cgraph* graph, int flags, byte* done);
     [DllImport(Lib)] public static extern int ggb_graph_plan(ggml_cgraph* graph, int flags, byte* done);
@@ -30,7 +32,7 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_dequantize_rows(int type, void* src, float* dst, long nrows, long k);
 
     // flags of ggb_graph_compute_mul_mats (include/ggb200.h)
-    public const int GGB_GRAPH_KEEP_ON_DEVICE = 1, GGB_GRAPH_NO_WEIGHT_CACHE = 2, GGB_GRAPH_MUL_MAT_ONLY = 4;
+    public const int GGB_GRAPH_KEEP_ON_DEVICE = 1, GGB_GRAPH_NO_WEIGHT_CACHE = 2, GGB_GRAPH_MUL_MAT_ONLY = 4, GGB_GRAPH_SHARD = 8;
 
     // device-pointer entry points (what the executor itself calls); stream = a cudaStream_t or IntPtr.Zero for the library's own
     [DllImport(Lib)] public static extern int ggb_dev_binary(int op, float* a, float* b, float* dst, long n, IntPtr stream);

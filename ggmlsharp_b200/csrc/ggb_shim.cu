@@ -6,12 +6,17 @@
 #include "ggb_internal.h"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -34,7 +39,7 @@ int set_error(int code, const char *fmt, ...)
     va_end(ap);
     return code;
 }
-void count_launch(int n) { g_stats.kernel_launches += (uint64_t)n; }
+void count_launch(int n) { __atomic_fetch_add(&g_stats.kernel_launches, (uint64_t)n, __ATOMIC_RELAXED); }   // the row split launches from one host thread per GPU
 struct KernelTimer {            // RAII bracket around one mul_mat kernel launch
     cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
     explicit KernelTimer(cudaStream_t st) : s(st) {
@@ -51,7 +56,7 @@ static std::mutex g_init_mu;      // ggb_dev_* entry points reach ensure_init wi
 static int ensure_init()
 {
     std::lock_guard<std::mutex> lk_init(g_init_mu);
-    if (g_inited) return GGB_OK;
+    if (g_inited) { cudaSetDevice(g_device); return GGB_OK; }      // the calling host thread may be new: make the library's device current
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -73,6 +78,127 @@ static int ensure_init()
     g_inited = true;
     return GGB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// The GPUs of one box behind ONE process (north_star: "large weight matrices are row-split across the GPUs of one 8xB200 box").
+// The reference splits the rows of src0 over the OS threads of ggml_graph_compute (Ggml.cs:3231-3252, 6665-6672); here every
+// "thread" of that split is a host thread that drives one GPU.  Device 0 of the set is the library's own device (ensure_init).
+// ------------------------------------------------------------------------------------------------
+struct DevCtx { int dev = -1; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr; std::vector<cudaEvent_t> level_ev; };
+static std::vector<DevCtx> g_devs;            // [0] mirrors g_device / g_stream / g_ev0 / g_ev1
+static int g_multi = 0;                       // devices opened with mutual peer access (0 = not probed yet)
+
+struct Worker {
+    std::thread th; std::mutex m; std::condition_variable cv;
+    std::function<void()> job; bool has_job = false, done = false, quit = false;
+    void loop() {
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return has_job || quit; });
+            if (quit) return;
+            std::function<void()> j = std::move(job);
+            has_job = false;
+            lk.unlock();
+            j();
+            lk.lock();
+            done = true;
+            cv.notify_all();
+        }
+    }
+};
+static std::vector<std::unique_ptr<Worker>> g_workers;      // g_workers[g - 1] drives device g; the calling thread drives device 0
+
+// Opens up to `want` sm_100 devices (GGB200_DEVICES = comma list, default: the primary device, then the others in index order) and
+// enables peer access between every pair.  Returns how many are usable together (>= 1).  Under torchrun (LOCAL_RANK set: one process
+// per GPU) the other GPUs belong to other ranks, so nothing beyond the primary is opened unless GGB200_DEVICES says so.
+static int ensure_multi(int want)
+{
+    if (g_multi) return std::min(g_multi, std::max(want, 1));
+    std::vector<int> ids{g_device};
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 1; }
+    if (const char *e = getenv("GGB200_DEVICES")) {
+        ids.clear();
+        for (const char *p = e; *p;) { char *end; long v = strtol(p, &end, 10); if (end == p) break; if (v >= 0 && v < n) ids.push_back((int)v); p = *end ? end + 1 : end; }
+        if (ids.empty() || ids[0] != g_device) ids.insert(ids.begin(), g_device);
+    } else if (!getenv("LOCAL_RANK")) {
+        for (int d = 0; d < n; d++) if (d != g_device) ids.push_back(d);
+    }
+    if ((int)ids.size() > 8) ids.resize(8);
+    g_devs.clear();
+    DevCtx d0; d0.dev = g_device; d0.stream = g_stream; d0.ev0 = g_ev0; d0.ev1 = g_ev1;
+    g_devs.push_back(d0);
+    for (size_t i = 1; i < ids.size(); i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, ids[i]) != cudaSuccess || p.major != 10) { cudaGetLastError(); continue; }
+        bool ok = true;
+        for (const DevCtx &o : g_devs) {                      // mutual peer access with every device already in the set
+            int a = 0, b = 0;
+            if (cudaDeviceCanAccessPeer(&a, ids[i], o.dev) != cudaSuccess || cudaDeviceCanAccessPeer(&b, o.dev, ids[i]) != cudaSuccess || !a || !b) { cudaGetLastError(); ok = false; break; }
+        }
+        if (!ok) continue;
+        DevCtx dc; dc.dev = ids[i];
+        if (cudaSetDevice(dc.dev) != cudaSuccess) { cudaGetLastError(); continue; }
+        for (const DevCtx &o : g_devs) { cudaError_t e1 = cudaDeviceEnablePeerAccess(o.dev, 0); if (e1 != cudaSuccess && e1 != cudaErrorPeerAccessAlreadyEnabled) ok = false; cudaGetLastError(); }
+        if (ok && (cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&dc.ev0) != cudaSuccess || cudaEventCreate(&dc.ev1) != cudaSuccess)) { cudaGetLastError(); ok = false; }
+        if (ok) for (const DevCtx &o : g_devs) {
+            cudaSetDevice(o.dev);
+            cudaError_t e1 = cudaDeviceEnablePeerAccess(dc.dev, 0);
+            if (e1 != cudaSuccess && e1 != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+            cudaGetLastError();
+        }
+        if (ok) g_devs.push_back(dc);
+    }
+    cudaSetDevice(g_device);
+    g_multi = (int)g_devs.size();
+    while ((int)g_workers.size() < g_multi - 1) {
+        g_workers.emplace_back(new Worker());
+        Worker *w = g_workers.back().get();
+        w->th = std::thread([w] { w->loop(); });
+    }
+    if (getenv("GGB200_VERBOSE")) fprintf(stderr, "[ggb200] row split: %d device(s) with mutual peer access\n", g_multi);
+    return std::min(g_multi, std::max(want, 1));
+}
+
+static void sync_all_devices()
+{
+    if (!g_inited) return;
+    if (g_devs.empty()) { cudaStreamSynchronize(g_stream); return; }
+    for (const DevCtx &d : g_devs) { cudaSetDevice(d.dev); cudaStreamSynchronize(d.stream); }
+    cudaSetDevice(g_device);
+}
+// fn(g) on G host threads, g = 0 on the caller's; returns when all are done
+static void run_parallel(int G, const std::function<void(int)> &fn)
+{
+    for (int g = 1; g < G; g++) {
+        Worker *w = g_workers[(size_t)g - 1].get();
+        std::lock_guard<std::mutex> lk(w->m);
+        w->job = [&fn, g] { fn(g); };
+        w->has_job = true; w->done = false;
+        w->cv.notify_all();
+    }
+    fn(0);
+    for (int g = 1; g < G; g++) {
+        Worker *w = g_workers[(size_t)g - 1].get();
+        std::unique_lock<std::mutex> lk(w->m);
+        w->cv.wait(lk, [&] { return w->done; });
+    }
+}
+
+// spinning rendezvous of the G host threads of one sharded call; fail() releases everybody
+struct HostBarrier {
+    int n = 1; std::atomic<int> count{0}, gen{0}, failed{0};
+    bool arrive_and_wait()
+    {
+        const int g = gen.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) { count.store(0, std::memory_order_relaxed); gen.fetch_add(1, std::memory_order_release); }
+        else while (gen.load(std::memory_order_acquire) == g && !failed.load(std::memory_order_acquire)) std::this_thread::yield();
+        return !failed.load(std::memory_order_acquire);
+    }
+    void fail() { failed.store(1, std::memory_order_release); }
+};
+struct ShardShared { int G = 1; HostBarrier bar; uint8_t *sym_base[8] = {}; int rc[8] = {}; char err[8][256] = {}; };
+struct ShardCtx { int g, G; ShardShared *sh; };
 
 static bool is_device_ptr(const void *p)
 {
@@ -415,7 +541,11 @@ static int flush_copy_batch(CopyBatch &cb, cudaStream_t s)
 // Device copy of a leaf src0.  rowexp: the power-of-two row exponents of the tensor-core path (launch_weight_rowexp), computed the
 // first time a view (byte offset, type, M, K, nb01) of the mirror meets a batched node and kept for as long as the mirror lives.
 struct RowExpKey { size_t off; int type; int64_t M, K, nb01; bool operator<(const RowExpKey &o) const { return std::tie(off, type, M, K, nb01) < std::tie(o.off, o.type, o.M, o.K, o.nb01); } };
-struct Mirror { void *dptr; size_t bytes; std::map<RowExpKey, int *> rowexp; };
+struct Mirror {
+    void *dptr = nullptr; size_t bytes = 0;      // bytes: the HOST byte range [data, data + bytes) the mirror stands for
+    int64_t row0 = 0, rows = 0;                  // which rows of the weight matrix this device holds (row split: a slice per GPU)
+    std::map<RowExpKey, int *> rowexp;
+};
 static void free_mirror(Mirror &m)
 {
     for (auto &kv : m.rowexp) cudaFree(kv.second);
@@ -439,6 +569,9 @@ struct DevArena {           // grow-only device scratch, reset per compute
     void *take(size_t bytes) { void *p = base + used; used += align_up(bytes, 256); return p; }
 };
 
+// per-device state of a pool.  mirrors: keyed by the host data pointer of a leaf src0
+struct PoolDev { DevArena arena, sym; std::map<const void *, Mirror> mirrors; };
+
 } // namespace ggb
 
 struct ggb_pool {
@@ -449,8 +582,11 @@ struct ggb_pool {
     // ggml_graph_compute, so by default every leaf src0 is uploaded again; a resident pool promises that leaf weights are rewritten
     // only through the API (CPY / in-place nodes, ggml_set_*), or followed by ggb_tensor_invalidate.
     bool weight_cache = false;
-    std::map<const void *, ggb::Mirror> mirrors;    // keyed by host data pointer of a leaf src0
-    ggb::DevArena arena;
+    // Row split across the GPUs of the box (ggb_pool_set_row_split / GGB200_ROW_SPLIT): 0 = off, n = up to n devices.  A MUL_MAT node is
+    // split only if its src0 has at least shard_min_bytes (north_star: "only for matrices large enough to benefit").
+    int shard_devices = 0;
+    size_t shard_min_bytes = 4u << 20;
+    std::vector<ggb::PoolDev> pd{1};                // per device: scratch arena, symmetric arena of node outputs, weight mirrors
 };
 
 namespace ggb {
@@ -594,28 +730,57 @@ static Produced *find_produced(std::vector<Produced> &v, const void *p, size_t s
     return nullptr;
 }
 
-// Runs `nodes` (already validated to be runnable, in graph order; view ops are not in the list).
-static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output)
+// Rows [row0, row0 + rows) of an M-row weight matrix that shard g of G owns: the reference's thread split dr = ceil(nr / nth),
+// thread ith takes [dr * ith, min(dr * ith + dr, nr)) (Ggml.cs:6665-6672), with nth = G and "thread" = GPU.
+static inline void shard_rows(int64_t M, int g, int G, int64_t &row0, int64_t &rows)
 {
-    int rc = ensure_init();
-    if (rc) return rc;
-    cudaStream_t s = g_stream;
+    const int64_t dr = (M + G - 1) / G;
+    row0 = std::min<int64_t>(dr * g, M);
+    rows = std::min<int64_t>(row0 + dr, M) - row0;
+}
+
+// Runs `nodes` (already validated to be runnable, in graph order; view ops are not in the list).
+//
+// sc == nullptr: everything on the library's device.  Otherwise this is host thread sc->g of sc->G, each driving one GPU of the box
+// (run_nodes_sharded below): every device executes the same node list on its own copy of every intermediate tensor -- element-wise
+// neighbours and CPYs are replicated, they cost nothing next to a mul_mat -- and a MUL_MAT node is row-split: device g multiplies
+// its rows of src0 and its kernel stores the results straight into EVERY device's copy of dst over NVLink (ggb_dev_mm.Y_peer; all
+// devices allocate node outputs from a "symmetric" arena in the same order, so a peer's address is its arena base plus the local
+// offset).  That is the all-gather of north_star, fused into the producing kernel.  After a level with MUL_MATs the devices wait for
+// each other's level events (cudaStreamWaitEvent across devices: no spinning kernels).  Nodes too small to split (ggb_pool.
+// shard_min_bytes) are multiplied by device 0 alone, which still broadcasts the result.  Device 0 returns the results to the host.
+static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output, ShardCtx *sc)
+{
+    const int g = sc ? sc->g : 0, G = sc ? sc->G : 1;
+    int rc = GGB_OK;
+    if (!sc) { rc = ensure_init(); if (rc) return rc; }
+    else GGB_CUDA(cudaSetDevice(g_devs[(size_t)g].dev));
+    cudaStream_t s = sc ? g_devs[(size_t)g].stream : g_stream;
+    cudaEvent_t ev0 = sc ? g_devs[(size_t)g].ev0 : g_ev0, ev1 = sc ? g_devs[(size_t)g].ev1 : g_ev1;
+    const bool lead = g == 0;                                // device 0 keeps the statistics and talks to the host arena
     const size_t n = nodes.size();
     if (!n) return GGB_OK;
-    if (!pool->owned && !pool->register_tried) {
-        // pinning the caller's memory is an optimisation only; pageable memory still works
-        pool->register_tried = true;
-        if (cudaHostRegister(pool->host_base, pool->bytes, cudaHostRegisterDefault) == cudaSuccess) pool->registered = true; else cudaGetLastError();
-    }
+    PoolDev &pd = pool->pd[(size_t)g];
+    DevArena &arena = pd.arena, &sym = pd.sym;
+    std::map<const void *, Mirror> &mirrors = pd.mirrors;
     auto out_tensor = [](ggml_tensor *t) -> ggml_tensor * { return t->op == GGML_OP_CPY ? t->src1 : t; };      // whose data the node writes
 
     const bool cache_on = pool->weight_cache && !(flags & GGB_GRAPH_NO_WEIGHT_CACHE);
     // a leaf src0 may stay resident only if nothing rewrites it behind the API's back: never a parameter (ggml_opt updates
     // params in place between computes, Ggml.cs:1734-1760) and never a tensor with a gradient
     auto cacheable = [&](const ggml_tensor *x) { return cache_on && x->op == GGML_OP_NONE && !x->is_param && !x->grad; };
+    // which rows of a MUL_MAT node's src0 this device multiplies
+    auto my_rows = [&](const ggml_tensor *a, int64_t &row0, int64_t &rows) {
+        row0 = 0; rows = a->ne[1];
+        if (G == 1) return;
+        const bool split = a->ne[2] * a->ne[3] == 1 && (size_t)a->ne[1] * a->nb[1] >= pool->shard_min_bytes && a->ne[1] >= 64 * (int64_t)G;
+        if (split) shard_rows(a->ne[1], g, G, row0, rows);
+        else if (g != 0) rows = 0;                            // too small to split: device 0 multiplies all of it (and still broadcasts)
+    };
 
-    // ---- pass 1: an upper bound of the scratch needed, so the arena is allocated once before anything is enqueued ----
-    size_t need = 0;
+    // ---- pass 1: an upper bound of the scratch needed, so both arenas are allocated once before anything is enqueued.
+    //      `sym` holds node outputs only, taken in node order: the same offsets on every device of a row split ----
+    size_t need = 0, need_sym = 0;
     {
         std::vector<Produced> plan;
         for (size_t i = 0; i < n; i++) {
@@ -631,23 +796,32 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                                         (a_pr && ((static_cast<const uint8_t *>(a->data) - a_pr->host) & 15));
                 need += (size_t)(a->ne[2] * a->ne[3]) * mm_ws_bytes_bound(a->type, a->ne[1], a->ne[0], b->ne[1], may_expand);
             } else {
-                if (!find_produced(plan, a->data, tensor_span(a))) need += align_up(tensor_span(a), 256);
+                if (!find_produced(plan, a->data, tensor_span(a))) need_sym += align_up(tensor_span(a), 256);      // (an in-place node on a leaf works on a sym copy)
                 if (b && t->op != GGML_OP_CPY && t->op != GGML_OP_SCALE && !find_produced(plan, b->data, tensor_span(b))) need += align_up(tensor_span(b), 256);
+                if (!find_produced(plan, a->data, tensor_span(a))) need += align_up(tensor_span(a), 256);
             }
             ggml_tensor *o = out_tensor(t);
-            need += align_up(tensor_span(o), 256);
+            need_sym += align_up(tensor_span(o), 256);
             plan.push_back({static_cast<const uint8_t *>(o->data), tensor_span(o), nullptr, 0});
         }
     }
-    rc = pool->arena.reserve(need + 4096);
+    rc = arena.reserve(need + 4096);
+    if (!rc) rc = sym.reserve(need_sym + 4096);
+    arena.used = 0; sym.used = 0;
+    if (sc) {
+        // every device publishes where its symmetric arena lives; nobody enqueues a peer store before all arenas exist
+        sc->sh->sym_base[g] = sym.base;
+        if (rc) sc->sh->bar.fail();
+        if (!sc->sh->bar.arrive_and_wait()) return rc ? rc : set_error(GGB_E_CUDA, "row split: another device failed to set up");
+    }
     if (rc) return rc;
-    pool->arena.used = 0;
 
-    GGB_CUDA(cudaEventRecord(g_ev0, s));
+    GGB_CUDA(cudaEventRecord(ev0, s));
 
     // ---- pass 2: stage inputs, group nodes into dependency levels, launch ----
     std::vector<Produced> produced;
-    struct Item { ggml_tensor *t; int level; uint8_t *da, *db, *dd; bool a_in_flight, ew_new; std::vector<const int *> ew; };   // ew: row exponents per (i2, i3) slice of a resident src0
+    // ew: row exponents per (i2, i3) slice of a resident src0; row0 / rows: the rows of src0 this device multiplies (da points at row0)
+    struct Item { ggml_tensor *t; int level; uint8_t *da, *db, *dd; bool a_in_flight, ew_new; int64_t row0, rows; std::vector<const int *> ew; };
     std::vector<Item> items(n);
     int max_level = 0;
     // Mirrors made stale by a node of this call may still be read by EARLIER nodes of it that are not launched yet: they are only
@@ -660,44 +834,51 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     // cached leaf, an in-place node on it): dropped by byte range, not by start pointer
     auto drop_mirrors = [&](const void *hostp, size_t bytes) {
         const uint8_t *h = static_cast<const uint8_t *>(hostp);
-        for (auto f = pool->mirrors.begin(); f != pool->mirrors.end();) {
-            if (ranges_overlap(h, bytes, static_cast<const uint8_t *>(f->first), f->second.bytes)) { graveyard.dead.push_back(std::move(f->second)); f = pool->mirrors.erase(f); }
+        for (auto f = mirrors.begin(); f != mirrors.end();) {
+            if (ranges_overlap(h, bytes, static_cast<const uint8_t *>(f->first), f->second.bytes)) { graveyard.dead.push_back(std::move(f->second)); f = mirrors.erase(f); }
             else ++f;
         }
     };
     // device address of an operand: produced earlier in this call, a cached weight mirror, read in place from the pinned
-    // arena (small tensors, UVA), or uploaded into the scratch arena
-    auto stage = [&](const ggml_tensor *x, int &level, bool weight, uint8_t *&out, Mirror **mir, bool *in_flight) -> int {
+    // arena (small tensors, UVA), or uploaded into the scratch arena.  A weight is staged from row `row0` on, `rows` rows only.
+    auto stage = [&](const ggml_tensor *x, int &level, bool weight, int64_t row0, int64_t rows, uint8_t *&out, Mirror **mir, bool *in_flight) -> int {
         const size_t span = tensor_span(x);
         bool partial = false;
         if (Produced *pr = find_produced(produced, x->data, span, &partial)) {
-            out = pr->dev + (static_cast<const uint8_t *>(x->data) - pr->host);
+            out = pr->dev + (static_cast<const uint8_t *>(x->data) - pr->host) + (weight ? (size_t)row0 * x->nb[1] : 0);
             level = std::max(level, pr->level + 1);
             if (in_flight) *in_flight = true;
             return GGB_OK;
         }
         if (partial) return set_error(GGB_E_UNSUPPORTED, "executor: an operand overlaps an earlier node's result without lying inside it");
+        // the bytes this device needs: the whole tensor, or (row split) its rows of a 2-D weight
+        const bool part = weight && rows != x->ne[1];
+        const uint8_t *src = static_cast<const uint8_t *>(x->data) + (part ? (size_t)row0 * x->nb[1] : 0);
+        const size_t bytes = part ? (rows > 0 ? (size_t)(rows - 1) * x->nb[1] + (size_t)(x->ne[0] / blck_size(x->type)) * type_size(x->type) : 0) : span;
         if (weight && cacheable(x)) {
-            auto f = pool->mirrors.find(x->data);
-            if (f != pool->mirrors.end() && f->second.bytes < span) { graveyard.dead.push_back(std::move(f->second)); pool->mirrors.erase(f); f = pool->mirrors.end(); }
-            if (f == pool->mirrors.end()) {
+            auto f = mirrors.find(x->data);
+            if (f != mirrors.end() && (f->second.bytes < span || f->second.row0 != row0 || f->second.rows != rows)) {
+                graveyard.dead.push_back(std::move(f->second)); mirrors.erase(f); f = mirrors.end();      // another shape or another split: stale
+            }
+            if (f == mirrors.end()) {
                 void *d = nullptr;
-                GGB_CUDA(cudaMalloc(&d, align_up(span, 256)));
-                GGB_CUDA(cudaMemcpyAsync(d, x->data, span, cudaMemcpyHostToDevice, s));
-                g_stats.h2d_bytes += span; g_stats.weight_uploads++;
-                f = pool->mirrors.emplace(x->data, Mirror{d, span, {}}).first;
-            } else g_stats.weight_cache_hits++;
+                GGB_CUDA(cudaMalloc(&d, align_up(std::max<size_t>(bytes, 1), 256)));
+                if (bytes) GGB_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s));
+                if (lead) { g_stats.h2d_bytes += bytes; g_stats.weight_uploads++; }
+                Mirror m; m.dptr = d; m.bytes = span; m.row0 = row0; m.rows = rows;      // `bytes` = the HOST range the mirror stands for (invalidation)
+                f = mirrors.emplace(x->data, std::move(m)).first;
+            } else if (lead) g_stats.weight_cache_hits++;
             out = static_cast<uint8_t *>(f->second.dptr);
             if (mir) *mir = &f->second;
             return GGB_OK;
         }
         if (!weight && pool->owned && span <= ZC_MAX && (reinterpret_cast<uintptr_t>(x->data) & 3) == 0) {
-            out = static_cast<uint8_t *>(x->data);               // UVA: kernels read the pinned arena directly
+            out = static_cast<uint8_t *>(x->data);               // UVA: kernels read the pinned arena directly (portable pinned memory: from any device)
         } else {
-            out = static_cast<uint8_t *>(pool->arena.take(span));
-            GGB_CUDA(cudaMemcpyAsync(out, x->data, span, cudaMemcpyHostToDevice, s));
+            out = static_cast<uint8_t *>(arena.take(std::max<size_t>(bytes, 1)));
+            if (bytes) GGB_CUDA(cudaMemcpyAsync(out, src, bytes, cudaMemcpyHostToDevice, s));
         }
-        g_stats.h2d_bytes += span;
+        if (lead) g_stats.h2d_bytes += bytes;
         return GGB_OK;
     };
     for (size_t i = 0; i < n; i++) {
@@ -705,6 +886,9 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         ggml_tensor *a = t->src0, *b = t->src1;
         Item &it = items[i];
         it.t = t; it.level = 0; it.da = it.db = it.dd = nullptr; it.a_in_flight = false; it.ew_new = false;
+        it.row0 = 0; it.rows = a->ne[1];
+        const bool is_mm = t->op == GGML_OP_MUL_MAT;
+        if (is_mm) my_rows(a, it.row0, it.rows);
         Mirror *mir = nullptr;
         ggml_tensor *o = out_tensor(t);
         const size_t ospan = tensor_span(o);
@@ -718,25 +902,28 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         Produced *a_prod = in_place ? find_produced(produced, a->data, tensor_span(a), &a_partial) : nullptr;
         if (a_partial) return set_error(GGB_E_UNSUPPORTED, "executor: an in-place operand overlaps an earlier node's result without lying inside it");
         if (in_place && !a_prod) {
-            // in place on a leaf: work on an arena copy (never on the pinned host arena directly, never on a cached mirror)
+            // in place on a leaf: work on a device copy (never on the pinned host arena directly, never on a cached mirror)
             const size_t span = tensor_span(a);
-            it.da = static_cast<uint8_t *>(pool->arena.take(span));
+            it.da = static_cast<uint8_t *>(sym.take(span));
             GGB_CUDA(cudaMemcpyAsync(it.da, a->data, span, cudaMemcpyHostToDevice, s));
-            g_stats.h2d_bytes += span;
+            if (lead) g_stats.h2d_bytes += span;
             drop_mirrors(a->data, span);
-        } else {
-            rc = stage(a, it.level, t->op == GGML_OP_MUL_MAT, it.da, &mir, &it.a_in_flight);
+        } else if (!is_mm || it.rows > 0) {
+            rc = stage(a, it.level, is_mm, it.row0, it.rows, it.da, &mir, &it.a_in_flight);
             if (rc) return rc;
+        } else {
+            // a MUL_MAT none of whose rows are this device's: nothing to stage, but the node still sits one level above its producers
+            if (Produced *pr = find_produced(produced, a->data, tensor_span(a))) it.level = std::max(it.level, pr->level + 1);
         }
-        if (mir && t->op == GGML_OP_MUL_MAT && b->ne[1] >= 16 && is_q_weight(a->type)) {
+        if (mir && is_mm && b->ne[1] >= 16 && is_q_weight(a->type)) {
             // resident weights: the row exponents of the tensor-core path (launch_weight_rowexp) are computed once per mirror view
             for (int64_t i3 = 0; i3 < a->ne[3]; i3++) for (int64_t i2 = 0; i2 < a->ne[2]; i2++) {
-                const RowExpKey key{(size_t)(i2 * a->nb[2] + i3 * a->nb[3]), a->type, a->ne[1], a->ne[0], (int64_t)a->nb[1]};
+                const RowExpKey key{(size_t)(i2 * a->nb[2] + i3 * a->nb[3]), a->type, it.rows, a->ne[0], (int64_t)a->nb[1]};
                 auto f = mir->rowexp.find(key);
                 if (f == mir->rowexp.end()) {
                     int *ew = nullptr;
-                    GGB_CUDA(cudaMalloc(reinterpret_cast<void **>(&ew), align_up((size_t)std::max<int64_t>(a->ne[1], 1) * 4, 256)));
-                    rc = launch_weight_rowexp(a->type, it.da + key.off, (int64_t)a->nb[1], a->ne[1], a->ne[0], ew, s);
+                    GGB_CUDA(cudaMalloc(reinterpret_cast<void **>(&ew), align_up((size_t)std::max<int64_t>(it.rows, 1) * 4, 256)));
+                    rc = launch_weight_rowexp(a->type, it.da + key.off, (int64_t)a->nb[1], it.rows, a->ne[0], ew, s);
                     if (rc) { cudaFree(ew); return rc; }
                     f = mir->rowexp.emplace(key, ew).first;
                     it.ew_new = true;                            // written on this stream just now: the GEMM's weight side waits
@@ -745,8 +932,10 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             }
         }
         if (b && t->op != GGML_OP_CPY && t->op != GGML_OP_SCALE && t->op != GGML_OP_REPEAT) {
-            rc = stage(b, it.level, false, it.db, nullptr, nullptr);
-            if (rc) return rc;
+            if (!is_mm || it.rows > 0) {
+                rc = stage(b, it.level, false, 0, 0, it.db, nullptr, nullptr);
+                if (rc) return rc;
+            } else if (Produced *pr = find_produced(produced, b->data, tensor_span(b))) it.level = std::max(it.level, pr->level + 1);
         }
         if (in_place) {
             // runs after every earlier node (some of them may still read the old contents), and later readers wait for it
@@ -755,7 +944,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             if (a_prod) { a_prod->level = it.level; drop_mirrors(od, ospan); }
             else produced.push_back({od, ospan, it.dd, it.level});
         } else {
-            it.dd = static_cast<uint8_t *>(pool->arena.take(ospan));
+            it.dd = static_cast<uint8_t *>(sym.take(ospan));
             if (t->op == GGML_OP_CPY) {
                 drop_mirrors(od, ospan);                         // a CPY rewrites b->data: every cached mirror sharing bytes with it is stale from here on
                 // ... and it must not overtake an earlier node of this call that still reads or writes those bytes on the device
@@ -768,21 +957,29 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
 
     for (int lv = 0; lv <= max_level; lv++) {
         std::vector<ggb_dev_mm> mms;
+        bool level_has_mm = false;
         for (Item &it : items) {
             if (it.level != lv) continue;
             ggml_tensor *t = it.t; const ggml_tensor *a = t->src0, *b = t->src1;
             switch (t->op) {
             case GGML_OP_MUL_MAT:
+                level_has_mm = true;
+                if (it.rows <= 0) break;                         // another device's rows; they arrive through its peer stores
                 for (int64_t i3 = 0; i3 < a->ne[3]; i3++) for (int64_t i2 = 0; i2 < a->ne[2]; i2++) {
                     ggb_dev_mm m = {};
-                    m.type = a->type; m.M = a->ne[1]; m.K = a->ne[0]; m.N = b->ne[1];
+                    m.type = a->type; m.M = it.rows; m.K = a->ne[0]; m.N = b->ne[1];
                     m.W = it.da + i2 * a->nb[2] + i3 * a->nb[3]; m.nb01 = (int64_t)a->nb[1];
                     m.X = reinterpret_cast<const float *>(it.db + i2 * b->nb[2] + i3 * b->nb[3]); m.ldx_bytes = (int64_t)b->nb[1];
-                    m.Y = reinterpret_cast<float *>(it.dd + i2 * t->nb[2] + i3 * t->nb[3]);
+                    m.Y = reinterpret_cast<float *>(it.dd + i2 * t->nb[2] + i3 * t->nb[3]) + it.row0;      // this device's column block of dst
                     // the F16 and quantized drivers index dst as dst_col[ic*ne0] (Ggml.cs:6423, 6697); F32 uses nb1 (6160)
                     m.ldy_bytes = a->type == GGML_TYPE_F32 ? (int64_t)t->nb[1] : (int64_t)t->ne[0] * 4;
                     if (it.a_in_flight || it.ew_new) m.flags |= GGB_MM_W_IN_FLIGHT;     // src0 is an earlier node's result (CPY -> MUL_MAT), or its exponents are brand new
                     if (!it.ew.empty()) m.W_rowexp = it.ew[(size_t)(i3 * a->ne[2] + i2)];
+                    if (G > 1) {
+                        // the fused all-gather: the kernel writes each result into every other device's copy of dst as well
+                        const size_t off = reinterpret_cast<uint8_t *>(m.Y) - sym.base;
+                        for (int h = 0; h < G; h++) if (h != g) m.Y_peer[m.n_peers++] = reinterpret_cast<float *>(sc->sh->sym_base[h] + off);
+                    }
                     mms.push_back(m);
                 }
                 break;
@@ -818,44 +1015,105 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         if (!mms.empty()) {
             size_t wsb = 0;
             for (const ggb_dev_mm &m : mms) wsb += mm_ws_bytes(m);
-            if (pool->arena.used + align_up(wsb, 256) > pool->arena.cap)
-                return set_error(GGB_E_NOMEM, "executor: mul_mat workspace of %zu B exceeds the planned scratch (%zu of %zu B used)", wsb, pool->arena.used, pool->arena.cap);
-            void *ws = pool->arena.take(wsb);
+            if (arena.used + align_up(wsb, 256) > arena.cap)
+                return set_error(GGB_E_NOMEM, "executor: mul_mat workspace of %zu B exceeds the planned scratch (%zu of %zu B used)", wsb, arena.used, arena.cap);
+            void *ws = arena.take(wsb);
             rc = dev_batch(mms.data(), (int)mms.size(), ws, wsb, s);
             if (rc) return rc;
         }
+        if (sc && level_has_mm) {
+            // The exchange step of the row split.  The peer stores of this level are in the streams; every device now waits (on the
+            // device, not on the host) until all the others have finished the level: event record, host rendezvous so that every
+            // event IS recorded, then one cross-device cudaStreamWaitEvent per peer.
+            DevCtx &dc = g_devs[(size_t)g];
+            while ((int)dc.level_ev.size() <= lv) {
+                cudaEvent_t e = nullptr;
+                GGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                dc.level_ev.push_back(e);
+            }
+            GGB_CUDA(cudaEventRecord(dc.level_ev[(size_t)lv], s));
+            if (!sc->sh->bar.arrive_and_wait()) return set_error(GGB_E_CUDA, "row split: another device failed");
+            for (int h = 0; h < G; h++) if (h != g) GGB_CUDA(cudaStreamWaitEvent(s, g_devs[(size_t)h].level_ev[(size_t)lv], 0));
+            // (an event of this level is recorded again only by the NEXT call, which starts after every host thread has left this one)
+        }
     }
 
-    // ---- results back into the host arena ----
-    CopyBatch cb = {};
-    for (size_t i = 0; i < n; i++) {
-        const Item &it = items[i];
-        ggml_tensor *t = it.t;
-        if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i] && t->op != GGML_OP_CPY) continue;   // a CPY target is user-visible
-        ggml_tensor *o = out_tensor(t);
-        void *hdst = o->data;
-        const size_t span = tensor_span(o);
-        if (pool->owned && span <= ZC_MAX && (span & 3) == 0 && (reinterpret_cast<uintptr_t>(hdst) & 15) == 0) {
-            CopySeg &sg = cb.seg[cb.n++];
-            sg.src = it.dd; sg.dst = static_cast<uint8_t *>(hdst); sg.bytes = (unsigned)span; sg.vec0 = cb.total_vec;
-            cb.total_vec += (unsigned)((span + 15) / 16);
-            if (cb.n == 96) { rc = flush_copy_batch(cb, s); if (rc) return rc; }
-        } else {
-            GGB_CUDA(cudaMemcpyAsync(hdst, it.dd, span, cudaMemcpyDeviceToHost, s));
+    // ---- results back into the host arena (device 0 holds every result) ----
+    if (lead) {
+        CopyBatch cb = {};
+        for (size_t i = 0; i < n; i++) {
+            const Item &it = items[i];
+            ggml_tensor *t = it.t;
+            if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i] && t->op != GGML_OP_CPY) continue;   // a CPY target is user-visible
+            ggml_tensor *o = out_tensor(t);
+            void *hdst = o->data;
+            const size_t span = tensor_span(o);
+            if (pool->owned && span <= ZC_MAX && (span & 3) == 0 && (reinterpret_cast<uintptr_t>(hdst) & 15) == 0) {
+                CopySeg &sg = cb.seg[cb.n++];
+                sg.src = it.dd; sg.dst = static_cast<uint8_t *>(hdst); sg.bytes = (unsigned)span; sg.vec0 = cb.total_vec;
+                cb.total_vec += (unsigned)((span + 15) / 16);
+                if (cb.n == 96) { rc = flush_copy_batch(cb, s); if (rc) return rc; }
+            } else {
+                GGB_CUDA(cudaMemcpyAsync(hdst, it.dd, span, cudaMemcpyDeviceToHost, s));
+            }
+            g_stats.d2h_bytes += span;
         }
-        g_stats.d2h_bytes += span;
+        rc = flush_copy_batch(cb, s);
+        if (rc) return rc;
     }
-    rc = flush_copy_batch(cb, s);
-    if (rc) return rc;
-    GGB_CUDA(cudaEventRecord(g_ev1, s));
+    GGB_CUDA(cudaEventRecord(ev1, s));
     GGB_CUDA(cudaStreamSynchronize(s));
-    float ms = 0.f;
-    GGB_CUDA(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
-    g_stats.last_graph_device_ms = ms;
-    g_stats.nodes_executed += n;
-    const int64_t us_each = (int64_t)(ms * 1000.0 / (double)n);
-    for (size_t i = 0; i < n; i++) { nodes[i]->perf_runs++; nodes[i]->perf_time_us += us_each; }   // Ggml.cs:3700-3702
+    if (lead) {
+        float ms = 0.f;
+        GGB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        g_stats.last_graph_device_ms = ms;
+        g_stats.nodes_executed += n;
+        const int64_t us_each = (int64_t)(ms * 1000.0 / (double)n);
+        for (size_t i = 0; i < n; i++) { nodes[i]->perf_runs++; nodes[i]->perf_time_us += us_each; }   // Ggml.cs:3700-3702
+    }
     return GGB_OK;
+}
+
+// The row split of one ggml_graph_compute over G GPUs: one host thread per device runs the node list (run_nodes above).
+static int run_nodes_sharded(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output, int G)
+{
+    if (G <= 1) return run_nodes(pool, nodes, flags, is_output, nullptr);
+    while ((int)pool->pd.size() < G) pool->pd.emplace_back();
+    ShardShared sh;
+    sh.G = G; sh.bar.n = G;
+    run_parallel(G, [&](int g) {
+        ShardCtx sc{g, G, &sh};
+        const int rc = run_nodes(pool, nodes, flags, is_output, &sc);
+        sh.rc[g] = rc;
+        if (rc) { snprintf(sh.err[g], sizeof sh.err[g], "%s", g_err); sh.bar.fail(); cudaStreamSynchronize(g_devs[(size_t)g].stream); cudaGetLastError(); }
+    });
+    cudaSetDevice(g_device);
+    for (int g = 0; g < G; g++) if (sh.rc[g]) return set_error(sh.rc[g], "device %d of the row split: %s", g_devs[(size_t)g].dev, sh.err[g]);
+    return GGB_OK;
+}
+
+// How many GPUs one ggml_graph_compute is split over -- "used only for matrices large enough to benefit" (north_star), in numbers:
+//   * nothing to split (no src0 of at least shard_min_bytes), or the split is off: 1;
+//   * single-token nodes only (N < 16, bandwidth-bound): all the devices the pool may use -- each reads 1/G of the weights and the
+//     exchange is 4 bytes per output row;
+//   * prompt-sized nodes (N >= 16, tensor cores): at most 2.  Every device must receive every other device's fp32 results, so with
+//     G devices t_exchange / t_compute ~ 2 (G - 1) P / (K B_link): 0.7 at G = 2, K = 4096 -- hidden behind the math -- but
+//     4.9 at G = 8, where the gather costs five times the mul_mat (measured in round 1: 11.7 ms against 6.1 ms on ONE GPU).
+static int row_split_width(ggb_pool *pool, const std::vector<ggml_tensor *> &run, int flags)
+{
+    int want = pool->shard_devices;
+    if (flags & GGB_GRAPH_SHARD) want = want > 0 ? want : 8;
+    if (want <= 1) return 1;
+    bool any_big = false, any_batched = false;
+    for (const ggml_tensor *t : run) {
+        if (t->op != GGML_OP_MUL_MAT) continue;
+        const ggml_tensor *a = t->src0;
+        if (t->src1->ne[1] >= 16) any_batched = true;
+        if (a->ne[2] * a->ne[3] == 1 && (size_t)a->ne[1] * a->nb[1] >= pool->shard_min_bytes) any_big = true;
+    }
+    if (!any_big) return 1;
+    if (any_batched) want = std::min(want, 2);
+    return ensure_multi(want);
 }
 
 } // namespace ggb
@@ -888,7 +1146,17 @@ int ggb_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_inited) return GGB_OK;
-    cudaStreamSynchronize(g_stream);
+    sync_all_devices();
+    for (auto &w : g_workers) { { std::lock_guard<std::mutex> lw(w->m); w->quit = true; } w->cv.notify_all(); if (w->th.joinable()) w->th.join(); }
+    g_workers.clear();
+    for (size_t i = 1; i < g_devs.size(); i++) {
+        cudaSetDevice(g_devs[i].dev);
+        for (cudaEvent_t e : g_devs[i].level_ev) cudaEventDestroy(e);
+        cudaEventDestroy(g_devs[i].ev0); cudaEventDestroy(g_devs[i].ev1); cudaStreamDestroy(g_devs[i].stream);
+    }
+    if (!g_devs.empty()) for (cudaEvent_t e : g_devs[0].level_ev) cudaEventDestroy(e);
+    g_devs.clear(); g_multi = 0;
+    cudaSetDevice(g_device);
     cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1);
     cudaStreamDestroy(g_stream);
     g_stream = nullptr; g_inited = false;
@@ -904,6 +1172,24 @@ int ggb_device_count(int *count)
 }
 
 static bool weight_cache_default() { const char *e = getenv("GGB200_WEIGHT_CACHE"); return e && atoi(e) != 0; }
+static int row_split_default()
+{
+    const char *e = getenv("GGB200_ROW_SPLIT");
+    if (!e || !*e) return 0;
+    return (!strcmp(e, "all") || !strcmp(e, "ALL")) ? 8 : std::max(0, atoi(e));
+}
+static size_t row_split_min_default() { const char *e = getenv("GGB200_ROW_SPLIT_MIN_BYTES"); return e ? (size_t)strtoull(e, nullptr, 0) : (size_t)(4u << 20); }
+static void drop_all_mirrors(ggb_pool *pool)
+{
+    for (PoolDev &pd : pool->pd) { for (auto &kv : pd.mirrors) free_mirror(kv.second); pd.mirrors.clear(); }
+}
+// pinning the caller's memory is an optimisation only (pageable memory still works); portable, so every device of a row split sees it pinned
+static void register_adopted(ggb_pool *pool)
+{
+    if (pool->owned || pool->register_tried) return;
+    pool->register_tried = true;
+    if (cudaHostRegister(pool->host_base, pool->bytes, cudaHostRegisterPortable) == cudaSuccess) pool->registered = true; else cudaGetLastError();
+}
 
 int ggb_pool_alloc(size_t bytes, void **host_base, ggb_pool **out)
 {
@@ -912,9 +1198,10 @@ int ggb_pool_alloc(size_t bytes, void **host_base, ggb_pool **out)
     int rc = ensure_init();
     if (rc) return rc;
     void *p = nullptr;
-    GGB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault));   // page-aligned >= GGML_MEM_ALIGN
+    GGB_CUDA(cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable));   // page-aligned >= GGML_MEM_ALIGN; pinned for every device of a row split
     ggb_pool *pool = new ggb_pool();
     pool->host_base = p; pool->bytes = bytes; pool->owned = true; pool->weight_cache = weight_cache_default();
+    pool->shard_devices = row_split_default(); pool->shard_min_bytes = row_split_min_default();
     *host_base = p; *out = pool;
     return GGB_OK;
 }
@@ -927,6 +1214,7 @@ int ggb_pool_adopt(void *host_base, size_t bytes, ggb_pool **out)
     // No device work yet: the caller owns the memory; it is pinned lazily at the first compute.
     ggb_pool *pool = new ggb_pool();
     pool->host_base = host_base; pool->bytes = bytes; pool->owned = false; pool->weight_cache = weight_cache_default();
+    pool->shard_devices = row_split_default(); pool->shard_min_bytes = row_split_min_default();
     *out = pool;
     return GGB_OK;
 }
@@ -935,9 +1223,9 @@ int ggb_pool_free(ggb_pool *pool)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!pool) return GGB_OK;
-    if (g_inited) cudaStreamSynchronize(g_stream);
-    for (auto &kv : pool->mirrors) free_mirror(kv.second);
-    if (pool->arena.base) cudaFree(pool->arena.base);
+    sync_all_devices();
+    drop_all_mirrors(pool);
+    for (PoolDev &pd : pool->pd) { if (pd.arena.base) cudaFree(pd.arena.base); if (pd.sym.base) cudaFree(pd.sym.base); }
     if (pool->registered) cudaHostUnregister(pool->host_base);
     if (pool->owned && pool->host_base) cudaFreeHost(pool->host_base);
     cudaGetLastError();
@@ -949,16 +1237,17 @@ int ggb_tensor_invalidate(ggb_pool *pool, const ggml_tensor *t)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!pool) return set_error(GGB_E_INVALID, "ggb_tensor_invalidate: null pool");
-    if (g_inited) cudaStreamSynchronize(g_stream);
-    if (!t) { for (auto &kv : pool->mirrors) free_mirror(kv.second); pool->mirrors.clear(); return GGB_OK; }
+    sync_all_devices();
+    if (!t) { drop_all_mirrors(pool); return GGB_OK; }
     if (!t->data) return GGB_OK;
     // every mirror that shares a byte with the tensor (it may be a view of a cached leaf, or a leaf some cached view looks into)
     const uint8_t *h = static_cast<const uint8_t *>(t->data);
     const size_t span = tensor_span(t);
-    for (auto f = pool->mirrors.begin(); f != pool->mirrors.end();) {
-        if (ranges_overlap(h, span, static_cast<const uint8_t *>(f->first), f->second.bytes)) { free_mirror(f->second); f = pool->mirrors.erase(f); }
-        else ++f;
-    }
+    for (PoolDev &pd : pool->pd)
+        for (auto f = pd.mirrors.begin(); f != pd.mirrors.end();) {
+            if (ranges_overlap(h, span, static_cast<const uint8_t *>(f->first), f->second.bytes)) { free_mirror(f->second); f = pd.mirrors.erase(f); }
+            else ++f;
+        }
     return GGB_OK;
 }
 
@@ -967,11 +1256,18 @@ int ggb_pool_set_weight_cache(ggb_pool *pool, int on)
     std::lock_guard<std::mutex> lk(g_mu);
     if (!pool) return set_error(GGB_E_INVALID, "ggb_pool_set_weight_cache: null pool");
     pool->weight_cache = on != 0;
-    if (!on) {
-        if (g_inited) cudaStreamSynchronize(g_stream);
-        for (auto &kv : pool->mirrors) free_mirror(kv.second);
-        pool->mirrors.clear();
-    }
+    if (!on) { sync_all_devices(); drop_all_mirrors(pool); }
+    return GGB_OK;
+}
+
+int ggb_pool_set_row_split(ggb_pool *pool, int max_devices, size_t min_weight_bytes)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!pool) return set_error(GGB_E_INVALID, "ggb_pool_set_row_split: null pool");
+    if (max_devices < 0) max_devices = 8;
+    if (max_devices != pool->shard_devices) { sync_all_devices(); drop_all_mirrors(pool); }      // resident slices belong to the old split
+    pool->shard_devices = std::min(max_devices, 8);
+    if (min_weight_bytes) pool->shard_min_bytes = min_weight_bytes;
     return GGB_OK;
 }
 
@@ -982,7 +1278,8 @@ int ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst)
     int rc = validate_mul_mat(dst);
     if (rc) return rc;
     std::vector<ggml_tensor *> nodes{dst};
-    return run_nodes(pool, nodes, 0, std::vector<char>{1});
+    register_adopted(pool);
+    return run_nodes(pool, nodes, 0, std::vector<char>{1}, nullptr);
 }
 
 } // extern "C"
@@ -1116,7 +1413,10 @@ int ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *g, int flags, uint8_
     int rc = select_nodes(g, flags, sel);
     if (rc) return rc;
     if (done) for (int i = 0; i < g->n_nodes; i++) done[i] = 0;
-    rc = run_nodes(pool, sel.run, flags, sel.is_output);
+    rc = ensure_init();
+    if (rc) return rc;
+    register_adopted(pool);
+    rc = run_nodes_sharded(pool, sel.run, flags, sel.is_output, row_split_width(pool, sel.run, flags));
     if (rc) return rc;
     if (done) { for (int i : sel.run_idx) done[i] = 1; for (int i : sel.view_idx) done[i] = 1; }
     g->perf_runs++;

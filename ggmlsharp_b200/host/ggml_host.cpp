@@ -96,6 +96,13 @@ int ggml_host_set_weight_cache(ggml_context *ctx, int on)
     return pool ? ggb_pool_set_weight_cache(pool, on) : GGB_E_INVALID;
 }
 
+// Opt in to the row split across the GPUs of the box for a context (include/ggb200.h: ggb_pool_set_row_split)
+int ggml_host_set_row_split(ggml_context *ctx, int max_devices, size_t min_weight_bytes)
+{
+    ggb_pool *pool = pool_of(ctx);
+    return pool ? ggb_pool_set_row_split(pool, max_devices, min_weight_bytes) : GGB_E_INVALID;
+}
+
 ggml_context *ggml_init(ggml_init_params params)
 {
     std::lock_guard<std::mutex> lk(g_cs);

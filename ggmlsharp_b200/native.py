@@ -10,7 +10,7 @@ F32, F16, Q4_0, Q4_1, Q4_2, Q5_0, Q5_1, Q8_0, Q8_1, I8, I16, I32 = 0, 1, 2, 3, 4
 OP_NONE, OP_MUL_MAT, OP_CPY = 0, 20, 22
 OP_DUP, OP_ADD, OP_MUL, OP_REPEAT, OP_SILU, OP_RMS_NORM, OP_SCALE, OP_CONT, OP_TRANSPOSE = 1, 2, 4, 10, 17, 19, 21, 23, 27
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM, E_ABI, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
-GRAPH_KEEP_ON_DEVICE, GRAPH_NO_WEIGHT_CACHE, GRAPH_MUL_MAT_ONLY = 1, 2, 4
+GRAPH_KEEP_ON_DEVICE, GRAPH_NO_WEIGHT_CACHE, GRAPH_MUL_MAT_ONLY, GRAPH_SHARD = 1, 2, 4, 8
 MM_W_IN_FLIGHT = 1
 OP_SQR = 6
 
@@ -96,6 +96,7 @@ GGB_SYMBOLS = {
     "ggb_pool_free": (C.c_int, [C.c_void_p]),
     "ggb_tensor_invalidate": (C.c_int, [C.c_void_p, TP]),
     "ggb_pool_set_weight_cache": (C.c_int, [C.c_void_p, C.c_int]),
+    "ggb_pool_set_row_split": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t]),
     "ggb_graph_plan": (C.c_int, [C.POINTER(ggml_cgraph), C.c_int, C.POINTER(C.c_uint8)]),
     "ggb_dev_weight_rowexp": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ggb_mul_mat_node": (C.c_int, [C.c_void_p, TP]),
@@ -132,6 +133,7 @@ HOST_SYMBOLS = {
     "ggml_host_last_status": (C.c_int, []),
     "ggml_host_pool_of": (C.c_void_p, [C.POINTER(ggml_context)]),
     "ggml_host_set_weight_cache": (C.c_int, [C.POINTER(ggml_context), C.c_int]),
+    "ggml_host_set_row_split": (C.c_int, [C.POINTER(ggml_context), C.c_int, C.c_size_t]),
     "ggml_sqr": (TP, [C.POINTER(ggml_context), TP]),
     "ggml_sqr_inplace": (TP, [C.POINTER(ggml_context), TP]),
     "ggml_init": (C.POINTER(ggml_context), [ggml_init_params]),

@@ -151,6 +151,17 @@ int  ggb_pool_free(ggb_pool *pool);
  * invalidate by byte range) or are followed by ggb_tensor_invalidate.  Never cached even then: parameters (is_param) and tensors
  * with a gradient, which ggml_opt rewrites in place between computes (Ggml.cs:1734-1760).  on = 0 also drops every mirror. */
 int  ggb_pool_set_weight_cache(ggb_pool *pool, int on);
+/* Row split across the GPUs of one box, inside ONE process and behind the unchanged ggml_graph_compute (north_star; the reference
+ * splits the rows of src0 over the OS threads of ggml_graph_compute, Ggml.cs:3231-3252, 6665-6672 -- here each "thread" drives a GPU).
+ * max_devices: 0 = off (default; env GGB200_ROW_SPLIT=<n>|all for pools created afterwards), < 0 = every sm_100 device with mutual
+ * peer access (GGB200_DEVICES=<list> restricts the set), n = at most n.  A MUL_MAT is split only if its src0 is a 2-D tensor of at
+ * least min_weight_bytes (0 = keep; default 4 MiB, env GGB200_ROW_SPLIT_MIN_BYTES): device g multiplies rows
+ * [ceil(M/G) g, ceil(M/G) (g+1)) and its kernel stores the results into every device's copy of dst over NVLink (the all-gather,
+ * fused into the epilogue); element-wise neighbours are replicated; smaller mul_mats run on device 0, which broadcasts them.  A
+ * compute with prompt-sized nodes (N >= 16) uses at most 2 devices, because there the exchange of fp32 results outgrows the
+ * math (see ggb_shim.cu: row_split_width).  Results are identical to the single-GPU ones bit for bit: a row's dot products do not
+ * depend on which device computes them. */
+int  ggb_pool_set_row_split(ggb_pool *pool, int max_devices, size_t min_weight_bytes);
 /* Call after rewriting tensor->data of a cached weight behind the API's back: drops every mirror that shares a byte with the
  * tensor (a view of a cached leaf, or a leaf some cached view looks into); NULL drops every mirror of the pool. */
 int  ggb_tensor_invalidate(ggb_pool *pool, const ggml_tensor *t);
@@ -165,6 +176,7 @@ int  ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst);
 #define GGB_GRAPH_KEEP_ON_DEVICE 1   /* do not copy intermediate results back (only graph outputs) */
 #define GGB_GRAPH_NO_WEIGHT_CACHE 2  /* re-upload every src0 (what the CPU path observes if weights change) */
 #define GGB_GRAPH_MUL_MAT_ONLY 4     /* run MUL_MAT and F32 -> {F16, quantized} CPY nodes only */
+#define GGB_GRAPH_SHARD 8            /* row-split this compute over the GPUs of the box even if the pool was not configured for it */
 
 /* Called from ggml_graph_compute (Ggml.cs:3539) instead of walking MUL_MAT nodes one by one:
  * runs, in node order and on one stream with one final sync, every MUL_MAT node (and F32 ->
