@@ -84,7 +84,12 @@ static int ensure_init()
 // The reference splits the rows of src0 over the OS threads of ggml_graph_compute (Ggml.cs:3231-3252, 6665-6672); here every
 // "thread" of that split is a host thread that drives one GPU.  Device 0 of the set is the library's own device (ensure_init).
 // ------------------------------------------------------------------------------------------------
-struct DevCtx { int dev = -1; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr; std::vector<cudaEvent_t> level_ev; };
+struct DevCtx {
+    int dev = -1; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // one event per dependency level, created on demand by the device's own host thread and read by the others after a rendezvous:
+    // a fixed table, so that growing it never moves what a peer is reading
+    cudaEvent_t level_ev[GGML_MAX_NODES + 1] = {};
+};
 static std::vector<DevCtx> g_devs;            // [0] mirrors g_device / g_stream / g_ev0 / g_ev1
 static int g_multi = 0;                       // devices opened with mutual peer access (0 = not probed yet)
 
@@ -106,7 +111,10 @@ struct Worker {
         }
     }
 };
-static std::vector<std::unique_ptr<Worker>> g_workers;      // g_workers[g - 1] drives device g; the calling thread drives device 0
+// g_workers[g - 1] drives device g; the calling thread drives device 0.  Deliberately leaked: at process exit the threads sit in
+// cv.wait, and destroying a condition variable with waiters (a static destructor would) blocks forever in pthread_cond_destroy.
+// ggb_shutdown stops and joins them properly.
+static std::vector<Worker *> &g_workers = *new std::vector<Worker *>();
 
 // Opens up to `want` sm_100 devices (GGB200_DEVICES = comma list, default: the primary device, then the others in index order) and
 // enables peer access between every pair.  Returns how many are usable together (>= 1).  Under torchrun (LOCAL_RANK set: one process
@@ -152,8 +160,8 @@ static int ensure_multi(int want)
     cudaSetDevice(g_device);
     g_multi = (int)g_devs.size();
     while ((int)g_workers.size() < g_multi - 1) {
-        g_workers.emplace_back(new Worker());
-        Worker *w = g_workers.back().get();
+        Worker *w = new Worker();
+        g_workers.push_back(w);
         w->th = std::thread([w] { w->loop(); });
     }
     if (getenv("GGB200_VERBOSE")) fprintf(stderr, "[ggb200] row split: %d device(s) with mutual peer access\n", g_multi);
@@ -171,7 +179,7 @@ static void sync_all_devices()
 static void run_parallel(int G, const std::function<void(int)> &fn)
 {
     for (int g = 1; g < G; g++) {
-        Worker *w = g_workers[(size_t)g - 1].get();
+        Worker *w = g_workers[(size_t)g - 1];
         std::lock_guard<std::mutex> lk(w->m);
         w->job = [&fn, g] { fn(g); };
         w->has_job = true; w->done = false;
@@ -179,7 +187,7 @@ static void run_parallel(int G, const std::function<void(int)> &fn)
     }
     fn(0);
     for (int g = 1; g < G; g++) {
-        Worker *w = g_workers[(size_t)g - 1].get();
+        Worker *w = g_workers[(size_t)g - 1];
         std::unique_lock<std::mutex> lk(w->m);
         w->cv.wait(lk, [&] { return w->done; });
     }
@@ -197,6 +205,8 @@ struct HostBarrier {
     }
     void fail() { failed.store(1, std::memory_order_release); }
 };
+static const bool g_trace_shard = getenv("GGB200_TRACE_SHARD") != nullptr;
+#define SHARD_TRACE(...) do { if (g_trace_shard) { fprintf(stderr, "[ggb200 shard] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 struct ShardShared { int G = 1; HostBarrier bar; uint8_t *sym_base[8] = {}; int rc[8] = {}; char err[8][256] = {}; };
 struct ShardCtx { int g, G; ShardShared *sh; };
 
@@ -810,6 +820,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     arena.used = 0; sym.used = 0;
     if (sc) {
         // every device publishes where its symmetric arena lives; nobody enqueues a peer store before all arenas exist
+        SHARD_TRACE("dev %d/%d: arenas reserved (%zu + %zu B) rc=%d", g, G, need, need_sym, rc);
         sc->sh->sym_base[g] = sym.base;
         if (rc) sc->sh->bar.fail();
         if (!sc->sh->bar.arrive_and_wait()) return rc ? rc : set_error(GGB_E_CUDA, "row split: another device failed to set up");
@@ -955,6 +966,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         max_level = std::max(max_level, it.level);
     }
 
+    SHARD_TRACE("dev %d/%d: staged %zu nodes, %d levels", g, G, n, max_level + 1);
     for (int lv = 0; lv <= max_level; lv++) {
         std::vector<ggb_dev_mm> mms;
         bool level_has_mm = false;
@@ -1026,14 +1038,12 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             // device, not on the host) until all the others have finished the level: event record, host rendezvous so that every
             // event IS recorded, then one cross-device cudaStreamWaitEvent per peer.
             DevCtx &dc = g_devs[(size_t)g];
-            while ((int)dc.level_ev.size() <= lv) {
-                cudaEvent_t e = nullptr;
-                GGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                dc.level_ev.push_back(e);
-            }
-            GGB_CUDA(cudaEventRecord(dc.level_ev[(size_t)lv], s));
+            if (lv > GGML_MAX_NODES) return set_error(GGB_E_INVALID, "row split: %d dependency levels", lv);
+            if (!dc.level_ev[lv]) GGB_CUDA(cudaEventCreateWithFlags(&dc.level_ev[lv], cudaEventDisableTiming));
+            GGB_CUDA(cudaEventRecord(dc.level_ev[lv], s));
+            SHARD_TRACE("dev %d/%d: level %d enqueued (%zu mul_mats here)", g, G, lv, mms.size());
             if (!sc->sh->bar.arrive_and_wait()) return set_error(GGB_E_CUDA, "row split: another device failed");
-            for (int h = 0; h < G; h++) if (h != g) GGB_CUDA(cudaStreamWaitEvent(s, g_devs[(size_t)h].level_ev[(size_t)lv], 0));
+            for (int h = 0; h < G; h++) if (h != g) GGB_CUDA(cudaStreamWaitEvent(s, g_devs[(size_t)h].level_ev[lv], 0));
             // (an event of this level is recorded again only by the NEXT call, which starts after every host thread has left this one)
         }
     }
@@ -1062,7 +1072,9 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         if (rc) return rc;
     }
     GGB_CUDA(cudaEventRecord(ev1, s));
+    SHARD_TRACE("dev %d/%d: everything enqueued, waiting for the stream", g, G);
     GGB_CUDA(cudaStreamSynchronize(s));
+    SHARD_TRACE("dev %d/%d: done", g, G);
     if (lead) {
         float ms = 0.f;
         GGB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1147,14 +1159,14 @@ int ggb_shutdown(void)
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_inited) return GGB_OK;
     sync_all_devices();
-    for (auto &w : g_workers) { { std::lock_guard<std::mutex> lw(w->m); w->quit = true; } w->cv.notify_all(); if (w->th.joinable()) w->th.join(); }
+    for (Worker *w : g_workers) { { std::lock_guard<std::mutex> lw(w->m); w->quit = true; } w->cv.notify_all(); if (w->th.joinable()) w->th.join(); delete w; }
     g_workers.clear();
     for (size_t i = 1; i < g_devs.size(); i++) {
         cudaSetDevice(g_devs[i].dev);
-        for (cudaEvent_t e : g_devs[i].level_ev) cudaEventDestroy(e);
+        for (cudaEvent_t e : g_devs[i].level_ev) if (e) cudaEventDestroy(e);
         cudaEventDestroy(g_devs[i].ev0); cudaEventDestroy(g_devs[i].ev1); cudaStreamDestroy(g_devs[i].stream);
     }
-    if (!g_devs.empty()) for (cudaEvent_t e : g_devs[0].level_ev) cudaEventDestroy(e);
+    if (!g_devs.empty()) for (cudaEvent_t e : g_devs[0].level_ev) if (e) cudaEventDestroy(e);
     g_devs.clear(); g_multi = 0;
     cudaSetDevice(g_device);
     cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1);
