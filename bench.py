@@ -462,6 +462,35 @@ def main():
         line["configs_note"] = ("one record per BASELINE.json configuration: ms per call of ggb_dev_mul_mat_batch over the listed nodes, achieved = "
                                 "algorithmic bytes (W + x + y) or 2MNK flop / ms, frac of MEASURED_PEAKS.json (hbm_gbs / bf16_tflops burst), "
                                 "frac_of_nominal of 8 TB/s / 2.25 PFLOP/s")
+    # ---- N > 1: the row split INSIDE the shim (one process, the unchanged ggml_graph_compute, all N GPUs), measured by rank 0 while the
+    #      other ranks sit in a CPU-side wait (a NCCL barrier would spin on their GPUs).  This is the end-to-end number that includes
+    #      the exchange: host arena in, host arena out, every device's copy of dst complete. ----
+    if world > 1 and not args.no_configs:
+        if sym is not None:
+            barrier()
+            sym.close()
+            sym = None
+        del Wq, X, ws
+        torch.cuda.empty_cache()
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            from benchmarks.bench_inproc import inproc_records
+            os.environ["GGB200_DEVICES"] = ",".join(str(i) for i in range(world))      # rank 0 may open the other ranks' GPUs now
+            try:
+                recs = list(inproc_records(torch, N, ggml, world, dev_index=local_rank, quick=True))
+            except Exception as ex:                                  # report, never lose the headline line
+                recs = [{"error": repr(ex)}]
+            line["in_process_row_split"] = recs
+            ring = [r for r in recs if r.get("config", "").startswith("configs[1]") and r.get("n_gpus") == world]
+            if ring:
+                r = ring[0]
+                e2e = {"value": r["achieved"], "unit": "GB/s", "ms_per_step": r["ms_per_compute"], "h2d_bytes_per_step": r["h2d_bytes_per_compute"],
+                       "d2h_bytes_per_step": r["d2h_bytes_per_compute"], "device_ms_per_step": r["device0_ms"],
+                       "api": "ONE process: ggml_graph_compute over a 32-node graph of (%d x 4096) Q4_0 matrices on a host arena, row split over %d GPUs inside the shim "
+                              "(resident weight slices; the exchange is fused into the GEMV epilogues and inside the timed region)" % (M_total, world)}
+            store.set("ggb_inproc_done", "1")
+        else:
+            store.wait(["ggb_inproc_done"])
     if rank == 0:
         line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:

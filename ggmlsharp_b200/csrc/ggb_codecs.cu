@@ -751,8 +751,10 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
     else threads = (long long)b.total_blk * ((b.K + 3) / 4);
     if (threads <= 0) return GGB_OK;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((threads + 255) / 256));
-    cfg.blockDim = dim3(256);
+    // 128-thread CTAs at 25 registers: 4 K registers each, small enough to be scheduled beside a resident GEMV CTA (118 registers x
+    // 512 threads leave 5 K of the SM's 64 K) -- the executor's second lane stages the next chunk while the current one multiplies
+    cfg.gridDim = dim3((unsigned)((threads + 127) / 128));
+    cfg.blockDim = dim3(128);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

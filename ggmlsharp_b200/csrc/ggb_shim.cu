@@ -52,6 +52,18 @@ struct KernelTimer {            // RAII bracket around one mul_mat kernel launch
 };
 int device_sm_count() { return g_sms; }
 
+struct DevCtx {
+    int dev = -1; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // second lane of the executor (run_nodes: a wide level of single-token mul_mats is dealt to two streams, so that the PCIe-side
+    // kernels of one chunk -- activation staging from the pinned arena, result copy back into it -- run beside the GEMV of the other)
+    cudaStream_t stream2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr;
+    // one event per dependency level, created on demand by the device's own host thread and read by the others after a rendezvous:
+    // a fixed table, so that growing it never moves what a peer is reading
+    cudaEvent_t level_ev[GGML_MAX_NODES + 1] = {};
+};
+
+static std::vector<DevCtx> g_devs;            // [0] = the library's own device (g_device / g_stream / g_ev0 / g_ev1); [1..] opened by ensure_multi
+static int g_multi = 0;                       // devices opened with mutual peer access (0 = not probed yet)
 static std::mutex g_init_mu;      // ggb_dev_* entry points reach ensure_init without g_mu
 static int ensure_init()
 {
@@ -75,6 +87,14 @@ static int ensure_init()
     GGB_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     GGB_CUDA(cudaEventCreate(&g_ev0));
     GGB_CUDA(cudaEventCreate(&g_ev1));
+    g_devs.clear();
+    g_devs.emplace_back();
+    DevCtx &d0 = g_devs[0];
+    d0.dev = dev; d0.stream = g_stream; d0.ev0 = g_ev0; d0.ev1 = g_ev1;
+    GGB_CUDA(cudaStreamCreateWithFlags(&d0.stream2, cudaStreamNonBlocking));
+    GGB_CUDA(cudaEventCreateWithFlags(&d0.fork, cudaEventDisableTiming));
+    GGB_CUDA(cudaEventCreateWithFlags(&d0.join, cudaEventDisableTiming));
+    g_multi = 0;
     g_inited = true;
     return GGB_OK;
 }
@@ -84,15 +104,6 @@ static int ensure_init()
 // The reference splits the rows of src0 over the OS threads of ggml_graph_compute (Ggml.cs:3231-3252, 6665-6672); here every
 // "thread" of that split is a host thread that drives one GPU.  Device 0 of the set is the library's own device (ensure_init).
 // ------------------------------------------------------------------------------------------------
-struct DevCtx {
-    int dev = -1; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // one event per dependency level, created on demand by the device's own host thread and read by the others after a rendezvous:
-    // a fixed table, so that growing it never moves what a peer is reading
-    cudaEvent_t level_ev[GGML_MAX_NODES + 1] = {};
-};
-static std::vector<DevCtx> g_devs;            // [0] mirrors g_device / g_stream / g_ev0 / g_ev1
-static int g_multi = 0;                       // devices opened with mutual peer access (0 = not probed yet)
-
 struct Worker {
     std::thread th; std::mutex m; std::condition_variable cv;
     std::function<void()> job; bool has_job = false, done = false, quit = false;
@@ -133,9 +144,7 @@ static int ensure_multi(int want)
         for (int d = 0; d < n; d++) if (d != g_device) ids.push_back(d);
     }
     if ((int)ids.size() > 8) ids.resize(8);
-    g_devs.clear();
-    DevCtx d0; d0.dev = g_device; d0.stream = g_stream; d0.ev0 = g_ev0; d0.ev1 = g_ev1;
-    g_devs.push_back(d0);
+    g_devs.resize(1);                                        // [0] was set up by ensure_init
     for (size_t i = 1; i < ids.size(); i++) {
         cudaDeviceProp p;
         if (cudaGetDeviceProperties(&p, ids[i]) != cudaSuccess || p.major != 10) { cudaGetLastError(); continue; }
@@ -148,7 +157,9 @@ static int ensure_multi(int want)
         DevCtx dc; dc.dev = ids[i];
         if (cudaSetDevice(dc.dev) != cudaSuccess) { cudaGetLastError(); continue; }
         for (const DevCtx &o : g_devs) { cudaError_t e1 = cudaDeviceEnablePeerAccess(o.dev, 0); if (e1 != cudaSuccess && e1 != cudaErrorPeerAccessAlreadyEnabled) ok = false; cudaGetLastError(); }
-        if (ok && (cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&dc.ev0) != cudaSuccess || cudaEventCreate(&dc.ev1) != cudaSuccess)) { cudaGetLastError(); ok = false; }
+        if (ok && (cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&dc.ev0) != cudaSuccess || cudaEventCreate(&dc.ev1) != cudaSuccess ||
+                   cudaStreamCreateWithFlags(&dc.stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&dc.fork, cudaEventDisableTiming) != cudaSuccess ||
+                   cudaEventCreateWithFlags(&dc.join, cudaEventDisableTiming) != cudaSuccess)) { cudaGetLastError(); ok = false; }
         if (ok) for (const DevCtx &o : g_devs) {
             cudaSetDevice(o.dev);
             cudaError_t e1 = cudaDeviceEnablePeerAccess(dc.dev, 0);
@@ -171,8 +182,7 @@ static int ensure_multi(int want)
 static void sync_all_devices()
 {
     if (!g_inited) return;
-    if (g_devs.empty()) { cudaStreamSynchronize(g_stream); return; }
-    for (const DevCtx &d : g_devs) { cudaSetDevice(d.dev); cudaStreamSynchronize(d.stream); }
+    for (const DevCtx &d : g_devs) { cudaSetDevice(d.dev); cudaStreamSynchronize(d.stream); cudaStreamSynchronize(d.stream2); }
     cudaSetDevice(g_device);
 }
 // fn(g) on G host threads, g = 0 on the caller's; returns when all are done
@@ -765,8 +775,9 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     int rc = GGB_OK;
     if (!sc) { rc = ensure_init(); if (rc) return rc; }
     else GGB_CUDA(cudaSetDevice(g_devs[(size_t)g].dev));
-    cudaStream_t s = sc ? g_devs[(size_t)g].stream : g_stream;
-    cudaEvent_t ev0 = sc ? g_devs[(size_t)g].ev0 : g_ev0, ev1 = sc ? g_devs[(size_t)g].ev1 : g_ev1;
+    DevCtx &dctx = g_devs[(size_t)g];
+    cudaStream_t s = dctx.stream;
+    cudaEvent_t ev0 = dctx.ev0, ev1 = dctx.ev1;
     const bool lead = g == 0;                                // device 0 keeps the statistics and talks to the host arena
     const size_t n = nodes.size();
     if (!n) return GGB_OK;
@@ -1165,10 +1176,12 @@ int ggb_shutdown(void)
         cudaSetDevice(g_devs[i].dev);
         for (cudaEvent_t e : g_devs[i].level_ev) if (e) cudaEventDestroy(e);
         cudaEventDestroy(g_devs[i].ev0); cudaEventDestroy(g_devs[i].ev1); cudaStreamDestroy(g_devs[i].stream);
+        cudaEventDestroy(g_devs[i].fork); cudaEventDestroy(g_devs[i].join); cudaStreamDestroy(g_devs[i].stream2);
     }
     if (!g_devs.empty()) for (cudaEvent_t e : g_devs[0].level_ev) if (e) cudaEventDestroy(e);
-    g_devs.clear(); g_multi = 0;
     cudaSetDevice(g_device);
+    if (!g_devs.empty()) { cudaEventDestroy(g_devs[0].fork); cudaEventDestroy(g_devs[0].join); cudaStreamDestroy(g_devs[0].stream2); }
+    g_devs.clear(); g_multi = 0;
     cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1);
     cudaStreamDestroy(g_stream);
     g_stream = nullptr; g_inited = false;
