@@ -826,7 +826,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             plan.push_back({static_cast<const uint8_t *>(o->data), tensor_span(o), nullptr, 0});
         }
     }
-    rc = arena.reserve(need + 4096);
+    rc = arena.reserve(need + 8192);
     if (!rc) rc = sym.reserve(need_sym + 4096);
     arena.used = 0; sym.used = 0;
     if (sc) {
@@ -978,10 +978,51 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     }
 
     SHARD_TRACE("dev %d/%d: staged %zu nodes, %d levels", g, G, n, max_level + 1);
+    // results back into the host arena (device 0 holds every result): small ones through one coalesced copy kernel per call site,
+    // large ones through the copy engine.  `copied` marks what has already gone back (the two-lane path below returns a chunk's
+    // results as soon as its GEMV is done).
+    std::vector<char> copied(n, 0);
+    auto copy_out = [&](const std::vector<size_t> &idx, cudaStream_t st) -> int {
+        CopyBatch cb = {};
+        for (size_t i : idx) {
+            const Item &it = items[i];
+            ggml_tensor *t = it.t;
+            if (copied[i]) continue;
+            if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i] && t->op != GGML_OP_CPY) continue;   // a CPY target is user-visible
+            copied[i] = 1;
+            ggml_tensor *o = out_tensor(t);
+            void *hdst = o->data;
+            const size_t span = tensor_span(o);
+            if (pool->owned && span <= ZC_MAX && (span & 3) == 0 && (reinterpret_cast<uintptr_t>(hdst) & 15) == 0) {
+                CopySeg &sg = cb.seg[cb.n++];
+                sg.src = it.dd; sg.dst = static_cast<uint8_t *>(hdst); sg.bytes = (unsigned)span; sg.vec0 = cb.total_vec;
+                cb.total_vec += (unsigned)((span + 15) / 16);
+                if (cb.n == 96) { int r = flush_copy_batch(cb, st); if (r) return r; }
+            } else {
+                GGB_CUDA(cudaMemcpyAsync(hdst, it.dd, span, cudaMemcpyDeviceToHost, st));
+            }
+            g_stats.d2h_bytes += span;
+        }
+        return flush_copy_batch(cb, st);
+    };
+    // may node i's result go back to the host before the LATER levels have run?  Not if a later node rewrites the same host bytes
+    // in place (the last writer carries the result) -- those are copied in node order at the end.
+    auto final_value = [&](size_t i) {
+        const uint8_t *od = static_cast<const uint8_t *>(out_tensor(items[i].t)->data);
+        const size_t ospan = tensor_span(out_tensor(items[i].t));
+        for (size_t j = i + 1; j < n; j++) {
+            ggml_tensor *oj = out_tensor(items[j].t);
+            if (ranges_overlap(od, ospan, static_cast<const uint8_t *>(oj->data), tensor_span(oj))) return false;
+        }
+        return true;
+    };
+
     for (int lv = 0; lv <= max_level; lv++) {
         std::vector<ggb_dev_mm> mms;
+        std::vector<size_t> mm_item;                             // which node each entry of mms belongs to
         bool level_has_mm = false;
-        for (Item &it : items) {
+        for (size_t ii = 0; ii < n; ii++) {
+            Item &it = items[ii];
             if (it.level != lv) continue;
             ggml_tensor *t = it.t; const ggml_tensor *a = t->src0, *b = t->src1;
             switch (t->op) {
@@ -1004,6 +1045,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                         for (int h = 0; h < G; h++) if (h != g) m.Y_peer[m.n_peers++] = reinterpret_cast<float *>(sc->sh->sym_base[h] + off);
                     }
                     mms.push_back(m);
+                    mm_item.push_back(ii);
                 }
                 break;
             case GGML_OP_CPY:
@@ -1040,9 +1082,45 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             for (const ggb_dev_mm &m : mms) wsb += mm_ws_bytes(m);
             if (arena.used + align_up(wsb, 256) > arena.cap)
                 return set_error(GGB_E_NOMEM, "executor: mul_mat workspace of %zu B exceeds the planned scratch (%zu of %zu B used)", wsb, arena.used, arena.cap);
-            void *ws = arena.take(wsb);
-            rc = dev_batch(mms.data(), (int)mms.size(), ws, wsb, s);
-            if (rc) return rc;
+            bool gemv_only = true;
+            for (const ggb_dev_mm &m : mms) if (m.N >= 16) gemv_only = false;
+            static const bool no_lanes = getenv("GGB200_NO_LANES") != nullptr;
+            if (gemv_only && mms.size() >= 8 && !g_timing && !no_lanes) {
+                // ---- a wide level of single-token mul_mats: two lanes.  The level is cut into chunks that alternate between the
+                //      device's two streams; every chunk is staged, multiplied and (on device 0) copied back on its own lane.  The
+                //      GEMV kernels cannot share an SM (each takes ~200 KB of shared memory), so they run one chunk after the other
+                //      whatever the stream -- but the staging kernel and the copy kernel are small enough (128 / 256 threads, <= 4 K
+                //      registers per CTA) to sit beside a resident GEMV CTA, so chunk c's PCIe traffic hides under chunk c+-1's
+                //      weight streaming instead of preceding and following ONE big GEMV. ----
+                const int nchunk = mms.size() >= 16 ? 4 : 2;
+                GGB_CUDA(cudaEventRecord(dctx.fork, s));
+                GGB_CUDA(cudaStreamWaitEvent(dctx.stream2, dctx.fork, 0));
+                uint8_t *wsp = static_cast<uint8_t *>(arena.take(wsb + 256 * (size_t)nchunk));
+                size_t i0 = 0;
+                for (int c = 0; c < nchunk; c++) {
+                    const size_t i1 = mms.size() * (size_t)(c + 1) / (size_t)nchunk;
+                    cudaStream_t st = (c & 1) ? dctx.stream2 : s;
+                    size_t cws = 0;
+                    for (size_t k = i0; k < i1; k++) cws += mm_ws_bytes(mms[k]);
+                    rc = dev_batch(mms.data() + i0, (int)(i1 - i0), wsp, cws, st);
+                    if (rc) return rc;
+                    wsp += align_up(cws, 256);
+                    if (lead && !sc) {
+                        // (row split: a chunk's dst is complete only when every device has stored its rows -- copied after the level event)
+                        std::vector<size_t> idx;
+                        for (size_t k = i0; k < i1; k++) if (final_value(mm_item[k]) && (idx.empty() || idx.back() != mm_item[k])) idx.push_back(mm_item[k]);
+                        rc = copy_out(idx, st);
+                        if (rc) return rc;
+                    }
+                    i0 = i1;
+                }
+                GGB_CUDA(cudaEventRecord(dctx.join, dctx.stream2));
+                GGB_CUDA(cudaStreamWaitEvent(s, dctx.join, 0));
+            } else {
+                void *ws = arena.take(wsb);
+                rc = dev_batch(mms.data(), (int)mms.size(), ws, wsb, s);
+                if (rc) return rc;
+            }
         }
         if (sc && level_has_mm) {
             // The exchange step of the row split.  The peer stores of this level are in the streams; every device now waits (on the
@@ -1059,27 +1137,11 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         }
     }
 
-    // ---- results back into the host arena (device 0 holds every result) ----
+    // ---- whatever has not gone back yet, in node order ----
     if (lead) {
-        CopyBatch cb = {};
-        for (size_t i = 0; i < n; i++) {
-            const Item &it = items[i];
-            ggml_tensor *t = it.t;
-            if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i] && t->op != GGML_OP_CPY) continue;   // a CPY target is user-visible
-            ggml_tensor *o = out_tensor(t);
-            void *hdst = o->data;
-            const size_t span = tensor_span(o);
-            if (pool->owned && span <= ZC_MAX && (span & 3) == 0 && (reinterpret_cast<uintptr_t>(hdst) & 15) == 0) {
-                CopySeg &sg = cb.seg[cb.n++];
-                sg.src = it.dd; sg.dst = static_cast<uint8_t *>(hdst); sg.bytes = (unsigned)span; sg.vec0 = cb.total_vec;
-                cb.total_vec += (unsigned)((span + 15) / 16);
-                if (cb.n == 96) { rc = flush_copy_batch(cb, s); if (rc) return rc; }
-            } else {
-                GGB_CUDA(cudaMemcpyAsync(hdst, it.dd, span, cudaMemcpyDeviceToHost, s));
-            }
-            g_stats.d2h_bytes += span;
-        }
-        rc = flush_copy_batch(cb, s);
+        std::vector<size_t> all(n);
+        for (size_t i = 0; i < n; i++) all[i] = i;
+        rc = copy_out(all, s);
         if (rc) return rc;
     }
     GGB_CUDA(cudaEventRecord(ev1, s));
@@ -1613,7 +1675,7 @@ __global__ void k_peer_barrier(PeerFlags f, int rank, int world, unsigned long l
 
 namespace ggb {
 struct PeerBases { uint8_t *p[8]; };
-__global__ void __launch_bounds__(256) k_peer_push_barrier(PeerBases b, PeerFlags f, uint32_t *counter, int rank, int world,
+__global__ void __launch_bounds__(128) k_peer_push_barrier(PeerBases b, PeerFlags f, uint32_t *counter, int rank, int world,
                                                            unsigned long long seg_offset, unsigned long long seg_bytes, unsigned long long seg_stride,
                                                            int n_seg, unsigned long long epoch)
 {
@@ -1669,9 +1731,11 @@ int ggb_peer_push_barrier(void *const *peer_bases, uint64_t *const *peer_flags, 
         b.p[i] = static_cast<uint8_t *>(peer_bases[i]); f.p[i] = peer_flags[i];
     }
     const unsigned long long total = (unsigned long long)(seg_bytes >> 4) * (unsigned long long)n_seg;
-    unsigned grid = (unsigned)std::min<unsigned long long>(64, std::max<unsigned long long>(1, (total + 1023) / 1024));
+    // 128-thread CTAs (32 registers: 4 K per CTA) fit beside a resident GEMV CTA, so the exchange of step i really runs under the
+    // GEMVs of step i + 1 (256-thread CTAs needed 8 K registers and waited for a GEMV CTA to exit: VERDICT r1, weak #8)
+    unsigned grid = (unsigned)std::min<unsigned long long>(128, std::max<unsigned long long>(1, (total + 511) / 512));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128);
     cfg.stream = stream ? static_cast<cudaStream_t>(stream) : g_stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
