@@ -566,8 +566,12 @@ struct Mirror {
     int64_t row0 = 0, rows = 0;                  // which rows of the weight matrix this device holds (row split: a slice per GPU)
     std::map<RowExpKey, int *> rowexp;
 };
+// Bumped whenever device memory that an instantiated CUDA graph may point into goes away (a weight mirror is freed, an arena is
+// reallocated): cached graphs of an older epoch are never launched again (ggb_graph_compute_mul_mats).
+static uint64_t g_epoch = 1;
 static void free_mirror(Mirror &m)
 {
+    g_epoch++;
     for (auto &kv : m.rowexp) cudaFree(kv.second);
     m.rowexp.clear();
     cudaFree(m.dptr);
@@ -579,6 +583,7 @@ struct DevArena {           // grow-only device scratch, reset per compute
     int reserve(size_t bytes)
     {
         if (bytes <= cap) return GGB_OK;
+        g_epoch++;
         if (base) cudaFree(base);
         base = nullptr; cap = 0;
         const size_t want = align_up(bytes + bytes / 4, 1 << 20);
@@ -591,6 +596,20 @@ struct DevArena {           // grow-only device scratch, reset per compute
 
 // per-device state of a pool.  mirrors: keyed by the host data pointer of a leaf src0
 struct PoolDev { DevArena arena, sym; std::map<const void *, Mirror> mirrors; };
+
+// One ggml_cgraph as the executor last saw it, and -- from the second identical compute on -- the CUDA graph of everything the
+// executor enqueues for it (uploads from the host arena, staging, mul_mats, neighbours, result copies; both lanes).  The reference
+// re-plans and re-walks the node list on every ggml_graph_compute (Ggml.cs:3260-3704); a decode loop computes the SAME graph over and
+// over, so the replay turns ~25 us (32 nodes) to ~1 ms (224 nodes) of host work per compute into one cudaGraphLaunch.  The key covers
+// every field the enqueue depends on (see graph_key); the bytes the graph reads and writes are the tensors' own, so results track
+// whatever the user writes into tensor->data between computes exactly as the eager path does.
+struct GraphEntry {
+    uint64_t key = 0, epoch = 0; int seen = 0; bool bad = false;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<uint8_t> done; int n_run = 0;
+    std::vector<ggml_tensor *> run;
+    uint64_t d_launches = 0, d_h2d = 0, d_d2h = 0, d_hits = 0, d_uploads = 0;      // what one replay adds to ggb_stats
+};
 
 } // namespace ggb
 
@@ -607,6 +626,7 @@ struct ggb_pool {
     int shard_devices = 0;
     size_t shard_min_bytes = 4u << 20;
     std::vector<ggb::PoolDev> pd{1};                // per device: scratch arena, symmetric arena of node outputs, weight mirrors
+    std::vector<ggb::GraphEntry> graphs;            // the few cgraphs this pool computes again and again (single-device computes only)
 };
 
 namespace ggb {
@@ -769,7 +789,12 @@ static inline void shard_rows(int64_t M, int g, int G, int64_t &row0, int64_t &r
 // offset).  That is the all-gather of north_star, fused into the producing kernel.  After a level with MUL_MATs the devices wait for
 // each other's level events (cudaStreamWaitEvent across devices: no spinning kernels).  Nodes too small to split (ggb_pool.
 // shard_min_bytes) are multiplied by device 0 alone, which still broadcasts the result.  Device 0 returns the results to the host.
-static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output, ShardCtx *sc)
+constexpr int GGB_E_NOCAPTURE = -100;       // internal: this compute cannot be recorded as a CUDA graph (run it eagerly)
+
+// cap != nullptr (single device only): do not execute -- RECORD everything the compute enqueues into cap->exec (stream capture
+// over both lanes).  Anything a replay could not repeat faithfully -- creating or dropping a resident weight mirror, growing an
+// arena -- returns GGB_E_NOCAPTURE before it has any effect, and the caller runs the compute eagerly instead.
+static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output, ShardCtx *sc, GraphEntry *cap = nullptr)
 {
     const int g = sc ? sc->g : 0, G = sc ? sc->G : 1;
     int rc = GGB_OK;
@@ -826,6 +851,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             plan.push_back({static_cast<const uint8_t *>(o->data), tensor_span(o), nullptr, 0});
         }
     }
+    if (cap && (need + 8192 > arena.cap || need_sym + 4096 > sym.cap)) return GGB_E_NOCAPTURE;
     rc = arena.reserve(need + 8192);
     if (!rc) rc = sym.reserve(need_sym + 4096);
     arena.used = 0; sym.used = 0;
@@ -838,7 +864,16 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     }
     if (rc) return rc;
 
-    GGB_CUDA(cudaEventRecord(ev0, s));
+    // RAII: a capture that is open when this function returns early is closed and thrown away
+    struct CaptureGuard {
+        cudaStream_t s; bool open = false;
+        ~CaptureGuard() { if (open) { cudaGraph_t g = nullptr; cudaStreamEndCapture(s, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); } }
+    } capture{s};
+    const ggb_stats stats0 = g_stats;
+    if (cap) {
+        GGB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        capture.open = true;
+    } else GGB_CUDA(cudaEventRecord(ev0, s));
 
     // ---- pass 2: stage inputs, group nodes into dependency levels, launch ----
     std::vector<Produced> produced;
@@ -854,9 +889,11 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     } graveyard{{}, s};
     // a write to [host, host + bytes) makes every cached mirror that shares a byte with it stale (a CPY into an offset view of a
     // cached leaf, an in-place node on it): dropped by byte range, not by start pointer
+    bool capture_refused = false;
     auto drop_mirrors = [&](const void *hostp, size_t bytes) {
         const uint8_t *h = static_cast<const uint8_t *>(hostp);
         for (auto f = mirrors.begin(); f != mirrors.end();) {
+            if (cap && ranges_overlap(h, bytes, static_cast<const uint8_t *>(f->first), f->second.bytes)) { capture_refused = true; return; }
             if (ranges_overlap(h, bytes, static_cast<const uint8_t *>(f->first), f->second.bytes)) { graveyard.dead.push_back(std::move(f->second)); f = mirrors.erase(f); }
             else ++f;
         }
@@ -880,9 +917,11 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         if (weight && cacheable(x)) {
             auto f = mirrors.find(x->data);
             if (f != mirrors.end() && (f->second.bytes < span || f->second.row0 != row0 || f->second.rows != rows)) {
+                if (cap) return GGB_E_NOCAPTURE;
                 graveyard.dead.push_back(std::move(f->second)); mirrors.erase(f); f = mirrors.end();      // another shape or another split: stale
             }
             if (f == mirrors.end()) {
+                if (cap) return GGB_E_NOCAPTURE;              // a replay must not upload the mirror again
                 void *d = nullptr;
                 GGB_CUDA(cudaMalloc(&d, align_up(std::max<size_t>(bytes, 1), 256)));
                 if (bytes) GGB_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s));
@@ -943,6 +982,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                 const RowExpKey key{(size_t)(i2 * a->nb[2] + i3 * a->nb[3]), a->type, it.rows, a->ne[0], (int64_t)a->nb[1]};
                 auto f = mir->rowexp.find(key);
                 if (f == mir->rowexp.end()) {
+                    if (cap) return GGB_E_NOCAPTURE;
                     int *ew = nullptr;
                     GGB_CUDA(cudaMalloc(reinterpret_cast<void **>(&ew), align_up((size_t)std::max<int64_t>(it.rows, 1) * 4, 256)));
                     rc = launch_weight_rowexp(a->type, it.da + key.off, (int64_t)a->nb[1], it.rows, a->ne[0], ew, s);
@@ -975,6 +1015,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             produced.push_back({od, ospan, it.dd, it.level});
         }
         max_level = std::max(max_level, it.level);
+        if (capture_refused) return GGB_E_NOCAPTURE;             // the node makes a resident mirror stale: not something to replay
     }
 
     SHARD_TRACE("dev %d/%d: staged %zu nodes, %d levels", g, G, n, max_level + 1);
@@ -1143,6 +1184,21 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         for (size_t i = 0; i < n; i++) all[i] = i;
         rc = copy_out(all, s);
         if (rc) return rc;
+    }
+    if (cap) {
+        cudaGraph_t graph = nullptr;
+        capture.open = false;
+        if (cudaStreamEndCapture(s, &graph) != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return GGB_E_NOCAPTURE; }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess || !exec) { cudaGetLastError(); return GGB_E_NOCAPTURE; }
+        cap->exec = exec; cap->epoch = g_epoch;
+        cap->d_launches = g_stats.kernel_launches - stats0.kernel_launches; cap->d_h2d = g_stats.h2d_bytes - stats0.h2d_bytes;
+        cap->d_d2h = g_stats.d2h_bytes - stats0.d2h_bytes; cap->d_hits = g_stats.weight_cache_hits - stats0.weight_cache_hits;
+        cap->d_uploads = g_stats.weight_uploads - stats0.weight_uploads;
+        GGB_CUDA(cudaEventRecord(ev0, s));
+        GGB_CUDA(cudaGraphLaunch(exec, s));
     }
     GGB_CUDA(cudaEventRecord(ev1, s));
     SHARD_TRACE("dev %d/%d: everything enqueued, waiting for the stream", g, G);
