@@ -58,7 +58,7 @@ internal static unsafe partial class GgbNative
     public struct ggb_stats
     {
         public ulong kernel_launches, h2d_bytes, d2h_bytes, weight_uploads, weight_cache_hits, nodes_executed;
-        public double last_graph_device_ms, timed_kernel_ms; public ulong timed_kernel_launches;
+        public double last_graph_device_ms, timed_kernel_ms; public ulong timed_kernel_launches, graph_replays;
     }
     [DllImport(Lib)] public static extern int ggb_abi_version();
     [DllImport(Lib)] public static extern int ggb_device_count(int* count);

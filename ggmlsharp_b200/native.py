@@ -74,7 +74,8 @@ class ggb_dev_mm(C.Structure):
 class ggb_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("weight_uploads", C.c_uint64), ("weight_cache_hits", C.c_uint64), ("nodes_executed", C.c_uint64),
-                ("last_graph_device_ms", C.c_double), ("timed_kernel_ms", C.c_double), ("timed_kernel_launches", C.c_uint64)]
+                ("last_graph_device_ms", C.c_double), ("timed_kernel_ms", C.c_double), ("timed_kernel_launches", C.c_uint64),
+                ("graph_replays", C.c_uint64)]
 
 
 assert C.sizeof(ggml_tensor) == 176 and ggml_tensor.data.offset == 160

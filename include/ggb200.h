@@ -185,6 +185,12 @@ int  ggb_mul_mat_node(ggb_pool *pool, ggml_tensor *dst);
  * are leafs or nodes it runs itself.  done[i] (n_nodes bytes, may be NULL) is set to 1 for each
  * node it executed; the caller's loop runs the rest.  Returns the number executed or < 0. */
 int  ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *graph, int flags, uint8_t *done);
+/* Repeated computes: the second time the SAME cgraph arrives (same node headers, shapes, data pointers, flags; single-device computes
+ * over pinned memory) the call records everything it enqueues -- uploads from the host arena, staging, kernels, result copies -- as a
+ * CUDA graph, and replays it from then on: one launch instead of re-planning the node list (Ggml.cs:3260-3704 does that per compute).
+ * The replay reads and writes the tensors' own bytes, so it follows whatever the user wrote into tensor->data in between exactly
+ * as the first compute did.  kernel_launches and the byte counters of ggb_stats keep counting per compute; graph_replays counts
+ * the replays.  Env GGB200_NO_GRAPH_CACHE=1 turns it off. */
 /* The selection alone, without a device: done[i] = 1 for every node the call above would execute (or look through, for view ops).
  * The reference runs nodes strictly in order (Ggml.cs:3539-3704); seam B runs the selected nodes BEFORE the caller's loop runs the
  * rest, so a candidate is refused -- with everything downstream of it -- when that reordering could be observed through memory:
@@ -300,6 +306,7 @@ typedef struct ggb_stats {
     double   last_graph_device_ms; /* CUDA-event time of the last ggb_graph_compute_mul_mats / ggb_mul_mat_node */
     double   timed_kernel_ms;      /* with ggb_set_kernel_timing(1): summed CUDA-event time of the GEMV / GEMM launches only */
     uint64_t timed_kernel_launches;
+    uint64_t graph_replays;        /* computes served by replaying the CUDA graph recorded for the same cgraph (ggb_graph_compute_mul_mats) */
 } ggb_stats;
 /* Measurement aid for the roofline.  1: bracket every mul_mat kernel launch (not the activation staging) with CUDA events on
  * the launching stream -- the brackets defeat the programmatic-dependent-launch overlap, so leave it off when timing steps.
