@@ -459,6 +459,15 @@ def main():
         torch.cuda.empty_cache()
         runner = Runner(torch, N, L, dev, stream, float(pk.get("hbm_gbs", 6650.0)), float(pk.get("bf16_tflops", 1590.0)))
         line["configs"] = list(runner.baseline_records(iters=20))
+        # ... and a DEPENDENT decode step (32 layers x 4 mul_mat levels) through ggml_graph_compute: what the launch-latency work is for
+        try:
+            from benchmarks.bench_inproc import chain_record
+            line["dependent_chain"] = chain_record(torch, N, ggml, layers=32, iters=10, dev_index=local_rank)
+            floor_ms = line["dependent_chain"]["weights_GB"] * 1e9 / (float(pk.get("hbm_gbs", 6650.0)) * 1e9) * 1e3
+            line["dependent_chain"]["floor_ms_at_measured_hbm_peak"] = floor_ms
+            line["dependent_chain"]["overhead_us_per_mul_mat_level"] = (line["dependent_chain"]["ms_per_compute"] - floor_ms) * 1e3 / line["dependent_chain"]["mul_mat_levels"]
+        except Exception as ex:
+            line["dependent_chain"] = {"error": repr(ex)}
         line["configs_note"] = ("one record per BASELINE.json configuration: ms per call of ggb_dev_mul_mat_batch over the listed nodes, achieved = "
                                 "algorithmic bytes (W + x + y) or 2MNK flop / ms, frac of MEASURED_PEAKS.json (hbm_gbs / bf16_tflops burst), "
                                 "frac_of_nominal of 8 TB/s / 2.25 PFLOP/s")

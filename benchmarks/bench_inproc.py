@@ -83,6 +83,67 @@ def run_graph(torch, N, ggml, shapes, wq, Nn, G, iters, warm=3, seed=7):
     return rec, check
 
 
+def chain_record(torch, N, ggml, layers=32, iters=10, dev_index=0):
+    """a DEPENDENT graph, as a decode step really is -- `layers` Llama-7B-shaped layers, one token, every mul_mat fed
+    by the previous level through the element-wise neighbours the reference implements (rms_norm, add, silu, mul; it ports no
+    attention ops, so q + k + v stands in for the mixing):
+        xn = rms_norm(x); a = wo . (wq.xn + wk.xn + wv.xn); x1 = x + a; xn2 = rms_norm(x1); x = x1 + w2 . (silu(w1.xn2) * (w3.xn2))
+    15 nodes and 10 dependency levels per layer, 4 of them mul_mat levels (3, 1, 2, 1 nodes wide).  Through ggml_graph_compute on a
+    host arena, weights resident.  The floor is the time to stream the weights once at the measured HBM peak."""
+    import numpy as np
+    L = N.lib()
+    dev = torch.device("cuda", dev_index)
+    sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    shapes = LAYER * layers
+    wq = _quantized_host(torch, N, L, dev, sp, shapes, 13)
+    wbytes = sum(w.nbytes for w in wq)
+    rng = np.random.default_rng(3)
+    arena = wbytes + len(shapes) * 1024 + layers * 16 * (4 * 11008 + 1024) + (16 << 20)
+    out = {}
+    with ggml.Context(arena) as c:
+        N.check(N.host().ggml_host_set_weight_cache(c.ctx, 1))
+        W = [c.tensor_from(Q4_0, K, M, data=w) for w, (M, K) in zip(wq, shapes)]
+        del wq
+        x = c.tensor_from(N.F32, 4096, 1, data=rng.standard_normal((1, 4096)).astype(np.float32))
+        cur = x
+        for l in range(layers):
+            w_q, w_k, w_v, w_o, w_1, w_3, w_2 = W[7 * l:7 * l + 7]
+            xn = c.op("rms_norm", cur)
+            qkv = c.op("add", c.op("add", c.mul_mat(w_q, xn), c.mul_mat(w_k, xn)), c.mul_mat(w_v, xn))
+            x1 = c.op("add", cur, c.mul_mat(w_o, qkv))
+            xn2 = c.op("rms_norm", x1)
+            h = c.op("mul", c.op("silu", c.mul_mat(w_1, xn2)), c.mul_mat(w_3, xn2))
+            cur = c.op("add", x1, c.mul_mat(w_2, h))
+        g = c.build_forward(cur)
+        for mode in ("eager", "graph"):
+            os.environ.pop("GGB200_NO_GRAPH_CACHE", None)
+            # (the library reads GGB200_NO_GRAPH_CACHE once; the eager figure comes from the first two computes of the pool, which are
+            #  never replays, the replay figure from the later ones)
+            if mode == "eager":
+                t0 = time.perf_counter()
+                c.graph_compute(g)
+                first = time.perf_counter() - t0          # includes the one-time upload of the weights
+                t0 = time.perf_counter()
+                c.graph_compute(g)                        # second sighting: enqueued eagerly into a stream capture, then launched
+                out["ms_second_compute_recording"] = (time.perf_counter() - t0) * 1e3
+                out["ms_first_compute_with_upload"] = first * 1e3
+            else:
+                L.ggb_reset_stats()
+                t0 = time.perf_counter()
+                for _ in range(iters):
+                    c.graph_compute(g)
+                dt = (time.perf_counter() - t0) / iters
+                st = N.stats()
+                out.update({"ms_per_compute": dt * 1e3, "device_ms": float(st.last_graph_device_ms), "graph_replays": int(st.graph_replays),
+                            "kernel_launches_per_compute": int(st.kernel_launches // iters)})
+        res = ggml.tensor_f32(cur).reshape(-1).copy()
+    n_levels_mm = 4 * layers
+    out.update({"config": "dependent chain through ggml_graph_compute: %d Llama-7B-shaped layers, one token, 15 nodes / 10 levels per layer (4 mul_mat levels: 3, 1, 2, 1 nodes wide), Q4_0 weights resident (%.2f GB)" % (layers, wbytes / 1e9),
+                "nodes": int(g.n_nodes), "mul_mat_levels": n_levels_mm, "weights_GB": wbytes / 1e9, "achieved": wbytes / (out["ms_per_compute"] * 1e-3) / 1e9, "unit": "GB/s",
+                "finite": bool(np.all(np.isfinite(res)))})
+    return out
+
+
 def inproc_records(torch, N, ggml, G, dev_index=0, quick=False):
     """Yields records for G GPUs driven by THIS process.  Caller makes sure devices 0..G-1 are visible and otherwise idle."""
     import numpy as np
@@ -119,12 +180,13 @@ def inproc_records(torch, N, ggml, G, dev_index=0, quick=False):
     ref = None
     for g in sorted({1, G}):
         rec, chk = run_graph(torch, N, ggml, shapes_p, wq[:len(shapes_p)], 512, g, 3)
+        rec["note"] = "tensor-core path: the tile width is chosen per launch from the tile count, so a half-height shard may sum its K steps in another order than the full matrix (same fp16 operands; fp32 rounding differs)"
         rec["config"] = ("configs[4] prompt step through ggml_graph_compute: %d layers x 7 Q4_0 matrices, 512 tokens, row split requested over %d GPU(s) "
                          "(prompt-sized computes use at most 2: the fp32 exchange outgrows the math beyond that)" % (layers, g))
         if ref is None:
             ref = chk
         else:
-            rec["bit_identical_to_1_gpu"] = bool(all(np.array_equal(a, b) for a, b in zip(ref, chk)))
+            rec["rel_l2_vs_1_gpu"] = float(max(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b.astype(np.float64)), 1e-30) for a, b in zip(chk, ref)))
         yield rec
 
 
@@ -134,10 +196,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=0)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--chain", type=int, default=0, help="only the dependent-chain record, with this many layers")
     a = ap.parse_args()
     G = a.gpus or torch.cuda.device_count()
     torch.cuda.set_device(0)
     N.check(N.lib().ggb_init())
+    if a.chain:
+        print(json.dumps(chain_record(torch, N, ggml, layers=a.chain)), flush=True)
+        return
     for rec in inproc_records(torch, N, ggml, G, quick=a.quick):
         print(json.dumps(rec), flush=True)
 
