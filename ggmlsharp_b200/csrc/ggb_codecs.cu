@@ -468,6 +468,11 @@ __global__ void __launch_bounds__(256) k_dequantize_rows(const uint8_t *__restri
 template <int CAP>
 __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBatchT<CAP> b)
 {
+    // Released at once: the GEMV behind this kernel may be scheduled as soon as every CTA of this grid is running.  Its producer warps
+    // stream weights (which do not depend on this kernel) while the activations are being staged; its consumer warps wait for this
+    // grid to COMPLETE (griddepcontrol.wait) before they touch the workspace.  No deadlock: a dependent grid is only launched once
+    // every CTA here has started, and started CTAs finish whatever the GEMV then occupies.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (b.wtype != GGML_TYPE_F16 && b.wtype != GGML_TYPE_F32) {     // every quantized weight type: src1 -> Q8 blocks (vec_dot_type)
         const int lane = threadIdx.x & 31, sub = lane & 7;
         const int blk = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
@@ -538,7 +543,6 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
             }
         }
     }
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // Batched (tensor-core) path: activations as fp16 values the reference's dot effectively multiplies by:
