@@ -60,6 +60,7 @@ struct DevCtx {
     // one event per dependency level, created on demand by the device's own host thread and read by the others after a rendezvous:
     // a fixed table, so that growing it never moves what a peer is reading
     cudaEvent_t level_ev[GGML_MAX_NODES + 1] = {};
+    std::vector<cudaEvent_t> level_time;      // timing events, one after each dependency level of an eager compute (per-node perf_time_us)
 };
 
 static std::vector<DevCtx> g_devs;            // [0] = the library's own device (g_device / g_stream / g_ev0 / g_ev1); [1..] opened by ensure_multi
@@ -246,11 +247,28 @@ static inline bool use_gemm(const ggb_dev_mm &m)
 }
 static inline size_t expanded_bytes(int64_t M, int64_t K) { return align_up((size_t)M * (size_t)K * 2, 256); }
 // a batched quantized node's slice: [fp16 activations][ex][ew] (gemm_workspace_bytes), then the expanded weights if the shape needs them
-static size_t mm_ws_bytes(const ggb_dev_mm &m)
+// Rows of any length (the reference loops over any ne00, Ggml.cs:6139-6164, 6676-6699).  The GEMV keeps one activation
+// row in shared memory next to its weight stages, which bounds K (gemv_x_budget); a longer row is multiplied in K SEGMENTS of
+// GGB_KSEG elements -- each an ordinary node over a column slice of W (same row stride) and of x (the Q8 blocks of a slice are the
+// blocks of the whole row) writing its partial sums into the workspace -- and k_sum_segments adds the partials in segment order.
+constexpr int64_t GGB_KSEG = 16384;           // 10 / 12 / 11 / 18 / 32 / 64 KB of a Q4_0 / Q4_1 / Q5_0 / Q8_0 / F16 / F32 row: whole units, 16-byte aligned
+static inline bool needs_k_segments(const ggb_dev_mm &m)
+{
+    return m.M > 0 && m.N > 0 && !use_gemm(m) && (int64_t)act_row_bytes(m.type, m.K) > gemv_x_budget();
+}
+static inline int64_t k_segments(int64_t K) { return (K + GGB_KSEG - 1) / GGB_KSEG; }
+static size_t mm_ws_bytes_plain(const ggb_dev_mm &m)
 {
     if (use_gemm_expanded(m)) return align_up(gemm_workspace_bytes(m.type, m.M, m.K, m.N), 256) + expanded_bytes(m.M, m.K);
     if (use_gemm(m)) return align_up(gemm_workspace_bytes(m.type, m.M, m.K, m.N), 256);
     return align_up((size_t)m.N * act_row_bytes(m.type, m.K), 256);
+}
+static size_t mm_ws_bytes(const ggb_dev_mm &m)
+{
+    if (!needs_k_segments(m)) return mm_ws_bytes_plain(m);
+    size_t t = align_up((size_t)k_segments(m.K) * (size_t)m.N * (size_t)m.M * 4, 256);      // the partial sums [segment][N][M]
+    for (int64_t k0 = 0; k0 < m.K; k0 += GGB_KSEG) { ggb_dev_mm seg = m; seg.K = std::min(GGB_KSEG, m.K - k0); t += mm_ws_bytes_plain(seg); }
+    return t;
 }
 // upper bound that does not depend on operand addresses (for sizing before buffers exist)
 // may_expand: the weights might not satisfy the TMA path's alignment once staged (the caller knows nb01 and view offsets)
@@ -258,7 +276,10 @@ static size_t mm_ws_bytes_bound(int type, int64_t M, int64_t K, int64_t N, bool 
 {
     const bool expand = is_q_weight(type) && N >= 16 && (may_expand || K % 128 != 0);
     const size_t tc = align_up(gemm_workspace_bytes(type, M, K, N), 256) + (expand ? expanded_bytes(M, K) : 0);      // incl. the exponent arrays
-    return std::max(tc, align_up((size_t)N * act_row_bytes(type, K), 256));
+    size_t gemv = align_up((size_t)N * act_row_bytes(type, K), 256);
+    if ((int64_t)act_row_bytes(type, K) > gemv_x_budget())      // K segments: partial sums + one staged slice per segment
+        gemv = align_up((size_t)k_segments(K) * (size_t)N * (size_t)M * 4, 256) + (size_t)k_segments(K) * align_up((size_t)N * act_row_bytes(type, std::min(GGB_KSEG, K)), 256);
+    return std::max(tc, gemv);
 }
 
 static int check_mm(const ggb_dev_mm &m)
@@ -276,14 +297,14 @@ static int check_mm(const ggb_dev_mm &m)
     return GGB_OK;
 }
 
-static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, cudaStream_t s)
+static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, cudaStream_t s)
 {
     if (count <= 0) return GGB_OK;
     std::vector<size_t> off(count + 1, 0);
     for (int i = 0; i < count; i++) {
         int rc = check_mm(mm[i]);
         if (rc) return rc;
-        off[i + 1] = off[i] + mm_ws_bytes(mm[i]);
+        off[i + 1] = off[i] + mm_ws_bytes_plain(mm[i]);
     }
     if (off[count] > ws_bytes) return set_error(GGB_E_INVALID, "mul_mat: workspace %zu B < required %zu B", ws_bytes, off[count]);
     if (off[count] && (reinterpret_cast<uintptr_t>(ws) & 255)) return set_error(GGB_E_INVALID, "mul_mat: workspace must be 256-byte aligned");
@@ -527,6 +548,90 @@ static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes,
     return GGB_OK;
 }
 
+// dst[n][m] = sum over segments of part[seg][n][m], in segment order (and into the peers' copies of a row split)
+struct SegPeers { int n; long long delta[7]; };
+__global__ void __launch_bounds__(256) k_sum_segments(const float *__restrict__ part, int nseg, long long M, long long N, float *__restrict__ y, long long ldy,
+                                                      const __grid_constant__ SegPeers peers)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // the segment GEMVs in front of this kernel
+    const long long total = M * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float v = part[i];
+        for (int sgi = 1; sgi < nseg; sgi++) v += part[(long long)sgi * total + i];
+        const long long n = i / M, m = i - n * M;
+        float *yp = y + n * ldy + m;
+        *yp = v;
+        for (int p = 0; p < peers.n; p++) *reinterpret_cast<float *>(reinterpret_cast<char *>(yp) + peers.delta[p]) = v;
+    }
+}
+
+// One batch of independent mul_mats.  Nodes whose rows are too long for the GEMV's shared-memory resident activation row are split
+// into K segments here (see needs_k_segments); everything else goes straight to dev_batch_inner.
+static int dev_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, cudaStream_t s)
+{
+    bool any = false;
+    for (int i = 0; i < count; i++) if (needs_k_segments(mm[i])) any = true;
+    if (!any) return dev_batch_inner(mm, count, ws, ws_bytes, s);
+    std::vector<ggb_dev_mm> sub;
+    struct Long { int node; size_t part_off; int nseg; };
+    std::vector<Long> longs;
+    size_t inner_bytes = 0;
+    for (int i = 0; i < count; i++) {
+        int rc = check_mm(mm[i]);
+        if (rc) return rc;
+        if (!needs_k_segments(mm[i])) { sub.push_back(mm[i]); inner_bytes += mm_ws_bytes_plain(mm[i]); continue; }
+        const ggb_dev_mm &m = mm[i];
+        if (m.K % GGB_QK && is_q_weight(m.type)) return set_error(GGB_E_INVALID, "mul_mat: ne00=%lld %% 32 != 0 (Ggml.cs:6694)", (long long)m.K);
+        longs.push_back({i, 0, (int)k_segments(m.K)});
+        const size_t esz = type_size(m.type);
+        const int blck = blck_size(m.type);
+        for (int64_t k0 = 0; k0 < m.K; k0 += GGB_KSEG) {
+            ggb_dev_mm sg = m;
+            sg.K = std::min(GGB_KSEG, m.K - k0);
+            sg.W = static_cast<const uint8_t *>(m.W) + (size_t)(k0 / blck) * esz;      // same rows, columns k0 .. k0 + K
+            sg.X = m.X + k0;
+            sg.n_peers = 0;                                   // partial sums stay local; the reduction broadcasts
+            sg.W_rowexp = nullptr;
+            sg.Y = nullptr;                                   // filled in below, once the layout is known
+            sg.ldy_bytes = m.M * 4;
+            sub.push_back(sg);
+            inner_bytes += mm_ws_bytes_plain(sg);
+        }
+    }
+    size_t total = align_up(inner_bytes, 256);
+    for (Long &l : longs) { l.part_off = total; total += align_up((size_t)l.nseg * (size_t)mm[l.node].N * (size_t)mm[l.node].M * 4, 256); }
+    if (total > ws_bytes) return set_error(GGB_E_INVALID, "mul_mat: workspace %zu B < required %zu B", ws_bytes, total);
+    uint8_t *wsb = static_cast<uint8_t *>(ws);
+    {   // point every segment at its slab of partial sums
+        size_t j = 0, li = 0;
+        for (int i = 0; i < count; i++) {
+            if (!needs_k_segments(mm[i])) { j++; continue; }
+            const Long &l = longs[li++];
+            for (int sgi = 0; sgi < l.nseg; sgi++, j++)
+                sub[j].Y = reinterpret_cast<float *>(wsb + l.part_off) + (size_t)sgi * (size_t)mm[i].N * (size_t)mm[i].M;
+        }
+    }
+    int rc = dev_batch_inner(sub.data(), (int)sub.size(), ws, inner_bytes, s);
+    if (rc) return rc;
+    for (const Long &l : longs) {
+        const ggb_dev_mm &m = mm[l.node];
+        SegPeers peers = {};
+        peers.n = m.n_peers;
+        for (int p = 0; p < m.n_peers; p++) peers.delta[p] = (long long)(reinterpret_cast<char *>(m.Y_peer[p]) - reinterpret_cast<char *>(m.Y));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)std::min<long long>((m.M * m.N + 255) / 256, (long long)device_sm_count() * 8));
+        cfg.blockDim = dim3(256); cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_sum_segments, reinterpret_cast<const float *>(wsb + l.part_off), l.nseg, (long long)m.M, (long long)m.N, m.Y,
+                                    (long long)(m.ldy_bytes / 4), peers));
+        count_launch();
+    }
+    return GGB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // pool + executor
 // ------------------------------------------------------------------------------------------------
@@ -609,6 +714,7 @@ struct GraphEntry {
     std::vector<uint8_t> done; int n_run = 0;
     std::vector<ggml_tensor *> run;
     uint64_t d_launches = 0, d_h2d = 0, d_d2h = 0, d_hits = 0, d_uploads = 0;      // what one replay adds to ggb_stats
+    std::vector<float> share;                 // each node's share of the compute's device time, as measured level by level when it last ran eagerly
 };
 
 } // namespace ggb
@@ -794,7 +900,8 @@ constexpr int GGB_E_NOCAPTURE = -100;       // internal: this compute cannot be 
 // cap != nullptr (single device only): do not execute -- RECORD everything the compute enqueues into cap->exec (stream capture
 // over both lanes).  Anything a replay could not repeat faithfully -- creating or dropping a resident weight mirror, growing an
 // arena -- returns GGB_E_NOCAPTURE before it has any effect, and the caller runs the compute eagerly instead.
-static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output, ShardCtx *sc, GraphEntry *cap = nullptr)
+static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, int flags, const std::vector<char> &is_output, ShardCtx *sc, GraphEntry *cap = nullptr,
+                     std::vector<float> *share_out = nullptr)
 {
     const int g = sc ? sc->g : 0, G = sc ? sc->G : 1;
     int rc = GGB_OK;
@@ -1163,6 +1270,12 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                 if (rc) return rc;
             }
         }
+        if (!cap && lead) {
+            // per-node timing (Ggml.cs:3695-3703 fills perf_time_us per node): one timing event per level, the level's time is
+            // shared among its nodes by the bytes they move
+            while ((int)dctx.level_time.size() <= lv) { cudaEvent_t e = nullptr; GGB_CUDA(cudaEventCreate(&e)); dctx.level_time.push_back(e); }
+            GGB_CUDA(cudaEventRecord(dctx.level_time[(size_t)lv], s));
+        }
         if (sc && level_has_mm) {
             // The exchange step of the row split.  The peer stores of this level are in the streams; every device now waits (on the
             // device, not on the host) until all the others have finished the level: event record, host rendezvous so that every
@@ -1209,8 +1322,27 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         GGB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
         g_stats.last_graph_device_ms = ms;
         g_stats.nodes_executed += n;
-        const int64_t us_each = (int64_t)(ms * 1000.0 / (double)n);
-        for (size_t i = 0; i < n; i++) { nodes[i]->perf_runs++; nodes[i]->perf_time_us += us_each; }   // Ggml.cs:3700-3702
+        // each node's share of the device time: measured per dependency level (eager computes), split inside a level by bytes moved;
+        // a recorded graph has no events inside, so its nodes keep the shares of the last eager compute of the same cgraph
+        std::vector<float> share(n, 1.0f / (float)n);
+        if (!cap) {
+            std::vector<double> w(n, 0.0), lw((size_t)max_level + 1, 0.0), lms((size_t)max_level + 1, 0.0);
+            for (size_t i = 0; i < n; i++) {
+                const ggml_tensor *t = nodes[i];
+                w[i] = (double)tensor_span(out_tensor(nodes[i])) + (t->src0 ? (double)tensor_span(t->src0) : 0.0) + ((t->src1 && t->src1->data) ? (double)tensor_span(t->src1) : 0.0);
+                lw[(size_t)items[i].level] += w[i];
+            }
+            double tot = 0.0;
+            for (int lv = 0; lv <= max_level; lv++) {
+                float lm = 0.f;
+                if (cudaEventElapsedTime(&lm, lv ? dctx.level_time[(size_t)lv - 1] : ev0, dctx.level_time[(size_t)lv]) != cudaSuccess) { cudaGetLastError(); lm = 0.f; }
+                lms[(size_t)lv] = lm; tot += lm;
+            }
+            if (tot > 0.0)
+                for (size_t i = 0; i < n; i++) { const size_t lv = (size_t)items[i].level; share[i] = (float)(lms[lv] / tot * (lw[lv] > 0.0 ? w[i] / lw[lv] : 0.0)); }
+        } else if (cap->share.size() == n) share = cap->share;
+        if (share_out) *share_out = share;
+        for (size_t i = 0; i < n; i++) { nodes[i]->perf_runs++; nodes[i]->perf_time_us += (int64_t)((double)ms * 1000.0 * share[i] + 0.5); }   // Ggml.cs:3700-3702
     }
     return GGB_OK;
 }
@@ -1299,6 +1431,7 @@ int ggb_shutdown(void)
     if (!g_devs.empty()) for (cudaEvent_t e : g_devs[0].level_ev) if (e) cudaEventDestroy(e);
     cudaSetDevice(g_device);
     if (!g_devs.empty()) { cudaEventDestroy(g_devs[0].fork); cudaEventDestroy(g_devs[0].join); cudaStreamDestroy(g_devs[0].stream2); }
+    for (DevCtx &d : g_devs) { for (cudaEvent_t e : d.level_time) cudaEventDestroy(e); d.level_time.clear(); }
     g_devs.clear(); g_multi = 0;
     cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1);
     cudaStreamDestroy(g_stream);
@@ -1604,8 +1737,10 @@ int ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *g, int flags, uint8_
             __atomic_fetch_add(&g_stats.kernel_launches, ge->d_launches, __ATOMIC_RELAXED);
             g_stats.h2d_bytes += ge->d_h2d; g_stats.d2h_bytes += ge->d_d2h; g_stats.weight_cache_hits += ge->d_hits; g_stats.weight_uploads += ge->d_uploads;
             g_stats.graph_replays++;
-            const int64_t us_each = ge->run.empty() ? 0 : (int64_t)(ms * 1000.0 / (double)ge->run.size());
-            for (ggml_tensor *t : ge->run) { t->perf_runs++; t->perf_time_us += us_each; }
+            for (size_t i = 0; i < ge->run.size(); i++) {
+                const float sh = ge->share.size() == ge->run.size() ? ge->share[i] : 1.0f / (float)ge->run.size();
+                ge->run[i]->perf_runs++; ge->run[i]->perf_time_us += (int64_t)((double)ms * 1000.0 * sh + 0.5);
+            }
             if (done) memcpy(done, ge->done.data(), (size_t)g->n_nodes);
             g->perf_runs++;
             g->perf_time_us += (int64_t)(ms * 1000.0);
@@ -1643,7 +1778,11 @@ int ggb_graph_compute_mul_mats(ggb_pool *pool, ggml_cgraph *g, int flags, uint8_
         }
     }
     if (!ran) {
-        rc = run_nodes_sharded(pool, sel.run, flags, sel.is_output, G);
+        if (G == 1) {
+            std::vector<float> share;
+            rc = run_nodes(pool, sel.run, flags, sel.is_output, nullptr, nullptr, &share);
+            if (ge) ge->share = std::move(share);
+        } else rc = run_nodes_sharded(pool, sel.run, flags, sel.is_output, G);
         if (rc) return rc;
     }
     if (done) { for (int i : sel.run_idx) done[i] = 1; for (int i : sel.view_idx) done[i] = 1; }

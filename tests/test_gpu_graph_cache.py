@@ -108,3 +108,22 @@ def test_uncached_weights_are_reread_by_every_replay():
             want = orc.mul_mat_2d(orc.F32, W.view(np.uint8).reshape(M, -1), M, K, x)
             assert rel_l2(ggml.tensor_f32(y).reshape(1, M), want) <= 2e-6, rep
         assert N.stats().graph_replays == 3
+
+
+def test_perf_time_is_attributed_per_node():
+    """Ggml.cs:3695-3703 fills perf_runs / perf_time_us per node.  The executor times each dependency level with CUDA events and splits
+    a level's time by the bytes its nodes move, so a 64 MB mul_mat must be charged far more than the 64 KB one that follows it."""
+    rng = np.random.default_rng(400)
+    K, Mbig, Msmall = 4096, 4096, 16
+    with ggml.Context(96 << 20) as c:
+        wb = c.tensor_from(N.F32, K, Mbig, data=weights(rng, Mbig, K))
+        ws = c.tensor_from(N.F32, Mbig, Msmall, data=weights(rng, Msmall, Mbig))
+        x = c.tensor_from(N.F32, K, data=rng.standard_normal((1, K)).astype(np.float32))
+        y1 = c.mul_mat(wb, x)
+        y2 = c.mul_mat(ws, y1)
+        g = c.build_forward(y2)
+        for _ in range(4):                                                # eager, recorded, replayed twice
+            c.graph_compute(g)
+        assert y1.contents.perf_runs == 4 and y2.contents.perf_runs == 4
+        assert y1.contents.perf_time_us > 3 * max(y2.contents.perf_time_us, 1), (y1.contents.perf_time_us, y2.contents.perf_time_us)
+        assert g.perf_runs == 4 and g.perf_time_us >= y1.contents.perf_time_us

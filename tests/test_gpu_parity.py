@@ -549,17 +549,28 @@ def test_peer_exchange_degenerates_cleanly_on_one_rank():
         sym.close()
 
 
-def test_longest_rows_that_fit_and_the_first_that_does_not():
-    """One activation row has to sit in shared memory next to the weight stages (README: known limits)."""
+def test_rows_of_any_length():
+    """The reference loops over any ne00 (Ggml.cs:6139-6164, 6676-6699).  One activation row has to sit in shared memory next to the GEMV's
+    weight stages; rows beyond that (24 576 F32 / 49 152 F16 / ~78 000 quantized elements) are multiplied in K segments whose partial sums
+    are added in segment order (ggb_shim.cu: needs_k_segments)."""
     rng = np.random.default_rng(91)
-    for t, K in ((N.F32, 24576), (N.F16, 49152), (N.Q4_0, 65536), (N.Q5_0, 65536)):
+    for t, K, Nn in ((N.F32, 24576, 1), (N.F16, 49152, 1), (N.Q4_0, 65536, 1),                      # the longest rows one pass takes
+                     (N.F32, 24608, 1), (N.F32, 70000 - 70000 % 32, 3), (N.F16, 131072, 1), (N.Q4_0, 131072 + 4096, 2),
+                     (N.Q4_1, 98304, 1), (N.Q5_0, 81920 + 32, 1), (N.Q8_0, 163840, 1)):
         M = 5
         W = weights(rng, M, K)
-        x = rng.standard_normal((1, K)).astype(np.float32)
+        x = rng.standard_normal((Nn, K)).astype(np.float32)
         wb = orc.encode_weights(t, W)
         err = rel_l2(dev_mul_mat(t, wb, M, K, x), orc.mul_mat_2d(t, wb, M, K, x))
-        assert err <= (1e-5 if t == N.F32 else 6e-6), (t, K, err)
-    wb = np.zeros((2, 4 * 24608), dtype=np.uint8)
-    with pytest.raises(N.GgbError) as e:
-        dev_mul_mat(N.F32, wb, 2, 24608, np.zeros((1, 24608), np.float32))
-    assert e.value.code == N.E_UNSUPPORTED
+        assert err <= (1e-5 if t == N.F32 else 6e-6), (t, K, Nn, err)
+    # ... and through the public route, next to an ordinary node
+    K = 100000 - 100000 % 32
+    W, x = weights(rng, 7, K), rng.standard_normal((1, K)).astype(np.float32)
+    wb = orc.encode_weights(N.Q4_0, W)
+    with ggml.Context(64 << 20) as c:
+        a = c.tensor_from(N.Q4_0, K, 7, data=wb)
+        b = c.tensor_from(N.F32, K, data=x)
+        y = c.mul_mat(a, b)
+        c.graph_compute(c.build_forward(y))
+        got = ggml.tensor_f32(y).reshape(1, 7).copy()
+    assert rel_l2(got, orc.mul_mat_2d(N.Q4_0, wb, 7, K, x)) <= 6e-6
