@@ -114,25 +114,35 @@ def test_codec_edge_cases():
 # ---------------------------------------------------------------- mul_mat through the device-level C ABI
 
 class Dev:
-    """Tiny RAII helper over ggb_dev_alloc/upload/download."""
+    """Tiny RAII helper over ggb_dev_alloc/upload/download.
+
+    compute-sanitizer is closed on this GPU pool, so every buffer a test hands to the library is fenced instead: GUARD bytes of a known
+    pattern in front of and behind it, verified when the helper is closed.  A kernel that writes outside dst, outside its workspace
+    slice or past the end of an operand it should only read turns into a test failure (reads out of bounds stay undetected)."""
+    GUARD = 4096
+    PATTERN = 0xA5
 
     def __init__(self):
-        self.ptrs = []
+        self.ptrs = []          # (base pointer, payload bytes)
+
+    def _alloc(self, nbytes):
+        p = C.c_void_p()
+        N.check(N.lib().ggb_dev_alloc(max(nbytes, 1) + 2 * self.GUARD, C.byref(p)))
+        fence = np.full(self.GUARD, self.PATTERN, dtype=np.uint8)
+        N.check(N.lib().ggb_dev_upload(p.value, fence.ctypes.data, self.GUARD))
+        N.check(N.lib().ggb_dev_upload(p.value + self.GUARD + max(nbytes, 1), fence.ctypes.data, self.GUARD))
+        self.ptrs.append((p, max(nbytes, 1)))
+        return p.value + self.GUARD
 
     def put(self, arr):
         arr = np.ascontiguousarray(arr)
-        p = C.c_void_p()
-        N.check(N.lib().ggb_dev_alloc(max(arr.nbytes, 1), C.byref(p)))
-        self.ptrs.append(p)
+        q = self._alloc(arr.nbytes)
         if arr.nbytes:
-            N.check(N.lib().ggb_dev_upload(p, arr.ctypes.data, arr.nbytes))
-        return p.value
+            N.check(N.lib().ggb_dev_upload(q, arr.ctypes.data, arr.nbytes))
+        return q
 
     def empty(self, nbytes):
-        p = C.c_void_p()
-        N.check(N.lib().ggb_dev_alloc(max(nbytes, 1), C.byref(p)))
-        self.ptrs.append(p)
-        return p.value
+        return self._alloc(nbytes)
 
     def get(self, ptr, shape, dtype=np.float32):
         out = np.zeros(shape, dtype=dtype)
@@ -140,10 +150,23 @@ class Dev:
             N.check(N.lib().ggb_dev_download(out.ctypes.data, ptr, out.nbytes))
         return out
 
+    def check_fences(self):
+        N.check(N.lib().ggb_stream_sync(None))
+        got = np.zeros(self.GUARD, dtype=np.uint8)
+        for p, nbytes in self.ptrs:
+            for off, where in ((0, "in front of"), (self.GUARD + nbytes, "behind")):
+                N.check(N.lib().ggb_dev_download(got.ctypes.data, p.value + off, self.GUARD))
+                bad = np.flatnonzero(got != self.PATTERN)
+                assert bad.size == 0, "out-of-bounds write %s a %d-byte buffer: %d bytes, first at offset %d" % (where, nbytes, bad.size, int(bad[0]) - (self.GUARD if off == 0 else 0))
+
     def close(self):
-        for p in self.ptrs:
-            N.lib().ggb_dev_free(p)
-        self.ptrs = []
+        try:
+            if self.ptrs:
+                self.check_fences()
+        finally:
+            for p, _ in self.ptrs:
+                N.lib().ggb_dev_free(p)
+            self.ptrs = []
 
 
 def dev_mul_mat(t, wbytes, M, K, X, nb01=None):
