@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration sub-records (configs[0], [2], [3], [4]) of the N=1 line")
     ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python instead of replaying a captured CUDA graph")
+    ap.add_argument("--no-pipeline", action="store_true", help="one ggb_dev_mul_mat_batch call per step (staging and GEMV back to back) instead of staging step i+1 under the GEMVs of step i")
     ap.add_argument("--epilogue-stores", action="store_true", help="fused gather through per-row peer stores in the GEMV epilogue instead of the push kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -211,12 +212,17 @@ def main():
     X = torch.randn((RING, K), generator=xgen, device=dev, dtype=torch.float32)
     gather = args.gather if world > 1 else "none"
     sym = None
-    NBUF = 2 if gather == "fused" and not args.epilogue_stores else 1
+    # Pipelined steps (default): the steps of this benchmark are independent passes over the ring, so the activation staging of step
+    # i+1 (ggb_dev_mul_mat_batch_phase 1, on its own stream, into the other of two workspaces) runs under the GEMVs of step i
+    # (phase 2), and -- N > 1 -- the exchange of step i on a third stream under step i+1.  Every step still stages AND multiplies
+    # inside the timed region.  --no-pipeline: one ggb_dev_mul_mat_batch call per step, as a lone decode step is issued.
+    pipelined = not args.no_pipeline and gather in ("none", "fused") and not args.epilogue_stores
+    NBUF = 2 if (pipelined or (gather == "fused" and not args.epilogue_stores)) else 1
     mm_bufs = [(N.ggb_dev_mm * RING)() for _ in range(NBUF)]
     if gather == "fused":
         # every rank holds the FULL dst of every node, [node][rows_total] (x2: double buffered).  The exchange is one kernel
         # over CUDA-IPC mapped peer memory: coalesced push of this rank's blocks into every peer's copy + a flag barrier.
-        # It runs on a second stream, so the exchange of step i overlaps the GEMVs of step i+1 (the nodes of consecutive
+        # It runs on its own stream, so the exchange of step i overlaps the GEMVs of step i+1 (the nodes of consecutive
         # steps are independent); the timed region ends only when every step's exchange has completed.
         from ggmlsharp_b200 import rowsplit
 
@@ -249,51 +255,97 @@ def main():
     wsb = L.ggb_dev_workspace_bytes(mms, RING)
     ws = torch.empty(NBUF * wsb + 256, dtype=torch.uint8, device=dev)
     wsp = (ws.data_ptr() + 255) // 256 * 256
-    comm = torch.cuda.Stream(device=dev) if NBUF == 2 else None
+    comm = torch.cuda.Stream(device=dev) if (NBUF == 2 and gather == "fused") else None
     cptr = C.c_void_p(comm.cuda_stream) if comm is not None else None
-    ev_compute = [torch.cuda.Event() for _ in range(NBUF)]
-    ev_comm = [torch.cuda.Event() for _ in range(NBUF)]
-    step_no = [0]
+    stg = torch.cuda.Stream(device=dev) if pipelined else None
+    gptr = C.c_void_p(stg.cuda_stream) if stg is not None else None
+
+    class Ev:                                                # one set of events per buffer: staged, multiplied, exchanged
+        def __init__(self):
+            self.stage = [torch.cuda.Event() for _ in range(2)]
+            self.mul = [torch.cuda.Event() for _ in range(2)]
+            self.comm = [torch.cuda.Event() for _ in range(2)]
+            self.fork = torch.cuda.Event()
+            self.staged, self.multiplied, self.pushed = [False, False], [False, False], [False, False]
+    ev_live = Ev()
+    total_steps = [0]
     torch.cuda.synchronize()
 
-    def step_body(b, evc=None, evm=None, wait=True):
-        # one step on buffer b: GEMVs on the compute stream, exchange on the comm stream (overlaps the next step's GEMVs)
-        evc = evc or ev_compute
-        evm = evm or ev_comm
-        if wait:
-            stream.wait_event(evm[b])                       # the exchange that last read / filled buffer b is done
-        N.check(L.ggb_dev_mul_mat_batch(mm_bufs[b], RING, wsp + b * wsb, wsb, sptr))
-        evc[b].record(stream)
-        comm.wait_event(evc[b])
-        sym.push_barrier(cptr, (b * RING * M_total + rank * M_LOCAL) * 4, M_LOCAL * 4, M_total * 4, RING)
-        evm[b].record(comm)
-
-    def step():
-        if gather == "fused" and NBUF == 2:
-            b = step_no[0] & 1
-            step_no[0] += 1
-            step_body(b)
+    def pipe(n, E):
+        """n pipelined steps starting on buffer total_steps & 1 (see `pipelined` above)."""
+        def stage(b):
+            if E.multiplied[b]:
+                stg.wait_event(E.mul[b])                    # the GEMVs that last read workspace b are done
+            N.check(L.ggb_dev_mul_mat_batch_phase(mm_bufs[b], RING, wsp + b * wsb, wsb, gptr, 1))
+            E.stage[b].record(stg)
+            E.staged[b] = True
+        if n <= 0:
             return
-        N.check(L.ggb_dev_mul_mat_batch(mms, RING, wsp, wsb, sptr))
-        if gather == "fused":
-            sym.barrier(sptr)
-        elif gather == "nccl":
-            dist.all_gather_into_tensor(Y.view(-1), Yloc.reshape(-1))
+        b0 = total_steps[0] & 1
+        E.fork.record(stream)
+        stg.wait_event(E.fork)                              # (inside a capture this is what pulls the staging stream into the graph)
+        stage(b0)
+        for j in range(n):
+            b = (b0 + j) & 1
+            if j + 1 < n:
+                stage(b ^ 1)                                # the next step's staging, under this step's GEMVs
+            stream.wait_event(E.stage[b])
+            if comm is not None and E.pushed[b]:
+                stream.wait_event(E.comm[b])                # the exchange that last read / filled dst buffer b is done
+            N.check(L.ggb_dev_mul_mat_batch_phase(mm_bufs[b], RING, wsp + b * wsb, wsb, sptr, 2))
+            E.mul[b].record(stream)
+            E.multiplied[b] = True
+            if comm is not None:
+                comm.wait_event(E.mul[b])
+                sym.push_barrier(cptr, (b * RING * M_total + rank * M_LOCAL) * 4, M_LOCAL * 4, M_total * 4, RING)
+                E.comm[b].record(comm)
+                E.pushed[b] = True
+        total_steps[0] += n
 
-    # Host launch cost (2 kernels + exchange + 4 event ops per step from Python) is comparable to the 57 us of GPU work, so
-    # GSTEPS steps are captured once into a CUDA graph (both streams) and replayed; the flag-barrier epoch lives in device memory.
+    def step_body(b, E, wait=True):
+        # unpipelined fused step on buffer b: GEMVs on the compute stream, exchange on the comm stream (overlaps the next step's GEMVs)
+        if wait and E.pushed[b]:
+            stream.wait_event(E.comm[b])                    # the exchange that last read / filled buffer b is done
+        N.check(L.ggb_dev_mul_mat_batch(mm_bufs[b], RING, wsp + b * wsb, wsb, sptr))
+        E.mul[b].record(stream)
+        comm.wait_event(E.mul[b])
+        sym.push_barrier(cptr, (b * RING * M_total + rank * M_LOCAL) * 4, M_LOCAL * 4, M_total * 4, RING)
+        E.comm[b].record(comm)
+        E.pushed[b] = True
+
+    def steps_eager(n, E):
+        if pipelined:
+            pipe(n, E)
+            return
+        for _ in range(n):
+            if gather == "fused" and NBUF == 2:
+                step_body(total_steps[0] & 1, E)
+            else:
+                N.check(L.ggb_dev_mul_mat_batch(mms, RING, wsp, wsb, sptr))
+                if gather == "fused":
+                    sym.barrier(sptr)
+                elif gather == "nccl":
+                    dist.all_gather_into_tensor(Y.view(-1), Yloc.reshape(-1))
+            total_steps[0] += 1
+
+    # Host launch cost (2 kernels + exchange + ~8 event ops per step from Python) is comparable to the ~55 us of GPU work, so
+    # GSTEPS steps are captured once into a CUDA graph (all streams) and replayed; the flag-barrier epoch lives in device memory.
     GSTEPS = 8
     graph = None
+    use_graph = (pipelined or (gather == "fused" and NBUF == 2)) and not args.no_graph
 
     def build_graph():
         g = torch.cuda.CUDAGraph()
-        gc, gm = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]      # events that live inside the capture
+        E = Ev()                                             # events that live inside the capture
+        saved = total_steps[0]
         with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
-            for j in range(GSTEPS):
-                # replays serialise on the stream, so the first use of each buffer in a replay has nothing to wait for
-                step_body(j & 1, gc, gm, wait=j >= 2)
-            for e in gm:
-                stream.wait_event(e)                        # join the comm stream back before the capture ends
+            # replays serialise on the stream, so the first use of each buffer in a replay has nothing to wait for
+            steps_eager(GSTEPS, E)
+            if comm is not None:
+                for b in range(2):
+                    if E.pushed[b]:
+                        stream.wait_event(E.comm[b])        # join the exchange stream back before the capture ends
+        total_steps[0] = saved
         return g
 
     def run_steps(n):
@@ -301,24 +353,25 @@ def main():
         if graph is not None:
             for _ in range(n // GSTEPS):
                 graph.replay()
+            total_steps[0] += (n // GSTEPS) * GSTEPS
             n = n % GSTEPS
-        for _ in range(n):
-            step()
+        if n:
+            steps_eager(n, ev_live)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
+    steps_eager(args.warmup, ev_live)
     barrier()
-    if gather == "fused" and NBUF == 2 and not args.no_graph:
-        if step_no[0] & 1:
-            step()                                          # graphs start on buffer 0
+    if use_graph:
+        if total_steps[0] & 1:
+            steps_eager(1, ev_live)                         # graphs start on buffer 0
         torch.cuda.synchronize()
         graph = build_graph()
         graph.replay()
+        total_steps[0] += GSTEPS
         barrier()
     L.ggb_reset_stats()
     sampler = ClockSampler(local_rank)
@@ -330,14 +383,15 @@ def main():
     e0.record(stream)
     run_steps(args.steps)
     if comm is not None:
-        for e in ev_comm:
-            stream.wait_event(e)                            # every step's exchange is inside the timed region
+        for b in range(2):
+            if ev_live.pushed[b]:
+                stream.wait_event(ev_live.comm[b])          # every step's exchange is inside the timed region (graph replays join by themselves)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     launches = int(N.stats().kernel_launches)
     if graph is not None:
-        launches += (args.steps // GSTEPS) * GSTEPS * 3      # replayed steps: act + GEMV + exchange kernels each
+        launches += (args.steps // GSTEPS) * GSTEPS * (3 if comm is not None else 2)      # replayed steps: act + GEMV (+ exchange) kernels each
     # extra untimed steps under the sampler so short runs still see clocks under load; the SAME count on every rank
     # (each step ends in a collective / flag barrier)
     n_extra = int(min(20000, max(10, 0.6 / max(ms / args.steps * 1e-3, 1e-6))))
@@ -360,7 +414,8 @@ def main():
     if gather == "fused":
         mine = np.zeros((RING, M_total), dtype=np.float32)
         N.check(L.ggb_stream_sync(sptr))
-        lastb = (step_no[0] - 1) & 1 if NBUF == 2 else 0
+        torch.cuda.synchronize()
+        lastb = (total_steps[0] - 1) & 1 if NBUF == 2 else 0
         N.check(L.ggb_dev_download(mine.ctypes.data, sym.payload() + lastb * RING * M_total * 4, mine.nbytes))
         loc = torch.from_numpy(mine[:, rank * M_LOCAL:(rank + 1) * M_LOCAL].copy()).to(dev)
         allb = torch.zeros((world, RING, M_LOCAL), dtype=torch.float32, device=dev)
@@ -402,6 +457,7 @@ def main():
             "dtype": "int8 dot (Q4_0 x Q8_0), f32 scales", "data": "synthetic",
             "config": {"workload": "configs[1]: Q4_0 4096x4096 GEMV, single token", "ring": RING,
                        "step": "%d independent MUL_MAT nodes (distinct weights, %.1f MB > 2x L2, no flush needed), 1 act + 1 GEMV launch" % (RING, RING * M_LOCAL * rb / 1e6),
+                       "pipelining": ("steps are independent: the activation staging of step i+1 runs on a second stream under the GEMVs of step i (two workspaces)%s; every step stages and multiplies inside the timed region; %d steps per CUDA-graph replay" % ("; the exchange of step i under step i+1" if world > 1 else "", GSTEPS)) if pipelined else "none (--no-pipeline)",
                        "rows_per_rank": M_LOCAL, "rows_total": M_total, "k": K,
                        "parallelism": "row-split x%d + all-gather (%s)" % (world, args.gather) if world > 1 else "1 GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

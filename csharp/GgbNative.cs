@@ -64,6 +64,7 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_device_count(int* count);
     [DllImport(Lib)] public static extern nuint ggb_dev_workspace_bytes(ggb_dev_mm* mm, int count);
     [DllImport(Lib)] public static extern int ggb_dev_mul_mat_batch(ggb_dev_mm* mm, int count, void* workspace, nuint workspaceBytes, IntPtr stream);
+    [DllImport(Lib)] public static extern int ggb_dev_mul_mat_batch_phase(ggb_dev_mm* mm, int count, void* workspace, nuint workspaceBytes, IntPtr stream, int phase);
     [DllImport(Lib)] public static extern int ggb_dev_quantize_rows(int type, float* src, void* dst, long nrows, long k, IntPtr stream);
     [DllImport(Lib)] public static extern int ggb_dev_dequantize_rows(int type, void* src, float* dst, long nrows, long k, IntPtr stream);
     [DllImport(Lib)] public static extern int ggb_dev_alloc(nuint bytes, void** dptr);

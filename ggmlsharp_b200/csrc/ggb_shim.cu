@@ -297,6 +297,10 @@ static int check_mm(const ggb_dev_mm &m)
     return GGB_OK;
 }
 
+// ggb_dev_mul_mat_batch_phase: 0 = stage the activations and multiply (the default), 1 = stage only, 2 = multiply what an earlier
+// phase-1 call with the same arguments left in the workspace.  Single-token nodes only.
+static thread_local int tl_phase = 0;
+
 static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, cudaStream_t s)
 {
     if (count <= 0) return GGB_OK;
@@ -355,6 +359,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
     };
     int n_tc = 0;
     for (int i = 0; i < count; i++) if (mm[i].M > 0 && mm[i].N > 0 && use_gemm(mm[i])) n_tc++;
+    if (tl_phase && n_tc) return set_error(GGB_E_UNSUPPORTED, "ggb_dev_mul_mat_batch_phase: split phases are for single-token (N < 16) nodes only");
     for (int i = 0; i < count; i++) {
         const ggb_dev_mm &m = mm[i];
         if (m.M == 0 || m.N == 0) continue;
@@ -482,7 +487,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
                 if ((reinterpret_cast<uintptr_t>(m.X) & 15) || (m.ldx_bytes & 15)) ab.vec16 = 0;
             }
             ab.total_blk = tot;
-            if (g_timing == 2 || !ab.n_nodes) continue;         // measurement mode: the workspace still holds these activations
+            if (g_timing == 2 || tl_phase == 2 || !ab.n_nodes) continue;         // the workspace already holds these activations
             int rc = launch_act_batch(ab, s, true);
             if (rc) return rc;
         }
@@ -500,6 +505,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
                 passes.push_back({i, (int)c, nc}); c += nc;
             }
         }
+        if (tl_phase == 1) continue;                            // staging only
         std::vector<char> pdone(passes.size(), 0);
         bool first_launch = true;
         for (size_t p0 = 0; p0 < passes.size(); p0++) {
@@ -1845,6 +1851,18 @@ int ggb_dev_mul_mat_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_b
     if (rc) return rc;
     if (count < 0 || (count && !mm)) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch: bad arguments");
     return dev_batch(mm, count, ws, ws_bytes, stream ? static_cast<cudaStream_t>(stream) : g_stream);
+}
+
+int ggb_dev_mul_mat_batch_phase(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, void *stream, int phase)
+{
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (count < 0 || (count && !mm) || phase < 0 || phase > 2) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch_phase: bad arguments");
+    for (int i = 0; i < count; i++) if (phase && needs_k_segments(mm[i])) return set_error(GGB_E_UNSUPPORTED, "ggb_dev_mul_mat_batch_phase: rows this long are multiplied in K segments (one phase only)");
+    tl_phase = phase;
+    rc = dev_batch(mm, count, ws, ws_bytes, stream ? static_cast<cudaStream_t>(stream) : g_stream);
+    tl_phase = 0;
+    return rc;
 }
 
 int ggb_dev_weight_rowexp(int type, const void *W, int64_t nb01, int64_t M, int64_t K, int32_t *rowexp, void *stream)

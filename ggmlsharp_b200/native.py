@@ -106,6 +106,7 @@ GGB_SYMBOLS = {
     "ggb_dequantize_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     "ggb_dev_workspace_bytes": (C.c_size_t, [C.POINTER(ggb_dev_mm), C.c_int]),
     "ggb_dev_mul_mat_batch": (C.c_int, [C.POINTER(ggb_dev_mm), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ggb_dev_mul_mat_batch_phase": (C.c_int, [C.POINTER(ggb_dev_mm), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]),
     "ggb_dev_quantize_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "ggb_dev_dequantize_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "ggb_dev_binary": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
