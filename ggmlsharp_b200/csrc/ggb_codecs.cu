@@ -764,6 +764,15 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    {
+        // ... and the same shared-memory carve-out as that GEMV: an SM is not shared by kernels whose carve-outs differ
+        static PerDeviceOnce once;
+        if (once.need()) {
+            cudaFuncSetAttribute(k_act_batch<GGB_SMALL_BATCH_NODES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_act_batch<GGB_MAX_BATCH_NODES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaGetLastError();
+        }
+    }
     if (b.n_nodes <= GGB_SMALL_BATCH_NODES) {                     // small parameter block: see launch_gemv_batch
         static thread_local ActBatchT<GGB_SMALL_BATCH_NODES> sb;
         static_cast<ActHdr &>(sb) = static_cast<const ActHdr &>(b);

@@ -662,6 +662,9 @@ __global__ void __launch_bounds__(256) k_copy_batch(const __grid_constant__ Copy
 static int flush_copy_batch(CopyBatch &cb, cudaStream_t s)
 {
     if (!cb.n) return GGB_OK;
+    // same shared-memory carve-out as the GEMV it is meant to run beside: an SM is not shared by kernels of different carve-outs
+    static PerDeviceOnce once;
+    if (once.need()) { cudaFuncSetAttribute(k_copy_batch, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); cudaGetLastError(); }
     k_copy_batch<<<std::min(64u, (cb.total_vec + 255) / 256), 256, 0, s>>>(cb);
     count_launch();
     GGB_CUDA(cudaGetLastError());
@@ -2027,6 +2030,11 @@ int ggb_peer_push_barrier(void *const *peer_bases, uint64_t *const *peer_flags, 
     for (int i = 0; i < world; i++) {
         if (!peer_bases[i] || !peer_flags[i]) return set_error(GGB_E_INVALID, "ggb_peer_push_barrier: null pointer for rank %d", i);
         b.p[i] = static_cast<uint8_t *>(peer_bases[i]); f.p[i] = peer_flags[i];
+    }
+    {
+        // same shared-memory carve-out as the GEMV this kernel is meant to run beside (an SM is not shared by kernels whose carve-outs differ)
+        static PerDeviceOnce once;
+        if (once.need()) { cudaFuncSetAttribute(k_peer_push_barrier, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); cudaGetLastError(); }
     }
     const unsigned long long total = (unsigned long long)(seg_bytes >> 4) * (unsigned long long)n_seg;
     // 128-thread CTAs (32 registers: 4 K per CTA) fit beside a resident GEMV CTA, so the exchange of step i really runs under the
