@@ -334,13 +334,13 @@ def main():
     graph = None
     use_graph = (pipelined or (gather == "fused" and NBUF == 2)) and not args.no_graph
 
-    def build_graph():
+    def build_graph(nsteps):
         g = torch.cuda.CUDAGraph()
         E = Ev()                                             # events that live inside the capture
         saved = total_steps[0]
         with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
             # replays serialise on the stream, so the first use of each buffer in a replay has nothing to wait for
-            steps_eager(GSTEPS, E)
+            steps_eager(nsteps, E)
             if comm is not None:
                 for b in range(2):
                     if E.pushed[b]:
@@ -348,15 +348,38 @@ def main():
         total_steps[0] = saved
         return g
 
+    rem_graphs = {}
+
     def run_steps(n):
-        """exactly n steps"""
+        """exactly n steps: replays of the GSTEPS-step graph, then ONE replay of a graph of the remaining n % GSTEPS steps (captured on
+        first use, outside any timed region: prepare_steps), so that a short --steps run is not a mix of replayed and Python-issued steps"""
         if graph is not None:
+            for aux in (stg, comm):
+                if aux is not None:
+                    stream.wait_stream(aux)                 # Python-issued steps may still have staging / exchange work in flight on the side streams
             for _ in range(n // GSTEPS):
                 graph.replay()
             total_steps[0] += (n // GSTEPS) * GSTEPS
             n = n % GSTEPS
+            if n and n in rem_graphs and not (total_steps[0] & 1):
+                rem_graphs[n].replay()
+                total_steps[0] += n
+                n = 0
         if n:
             steps_eager(n, ev_live)
+
+    def prepare_steps(n):
+        r = n % GSTEPS
+        if graph is not None and r and r not in rem_graphs:
+            if total_steps[0] & 1:
+                steps_eager(1, ev_live)
+            torch.cuda.synchronize()
+            rem_graphs[r] = build_graph(r)
+            rem_graphs[r].replay()
+            total_steps[0] += r
+            if total_steps[0] & 1:
+                steps_eager(1, ev_live)                     # leave the buffer parity even: every graph starts on buffer 0
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -369,9 +392,10 @@ def main():
         if total_steps[0] & 1:
             steps_eager(1, ev_live)                         # graphs start on buffer 0
         torch.cuda.synchronize()
-        graph = build_graph()
+        graph = build_graph(GSTEPS)
         graph.replay()
         total_steps[0] += GSTEPS
+        prepare_steps(args.steps)
         barrier()
     L.ggb_reset_stats()
     sampler = ClockSampler(local_rank)
