@@ -415,7 +415,8 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = int(N.stats().kernel_launches)
     if graph is not None:
-        launches += (args.steps // GSTEPS) * GSTEPS * (3 if comm is not None else 2)      # replayed steps: act + GEMV (+ exchange) kernels each
+        replayed = (args.steps // GSTEPS) * GSTEPS + (args.steps % GSTEPS if args.steps % GSTEPS in rem_graphs else 0)
+        launches += replayed * (3 if comm is not None else 2)      # replayed steps: act + GEMV (+ exchange) kernels each
     # extra untimed steps under the sampler so short runs still see clocks under load; the SAME count on every rank
     # (each step ends in a collective / flag barrier)
     n_extra = int(min(20000, max(10, 0.6 / max(ms / args.steps * 1e-3, 1e-6))))
