@@ -213,9 +213,14 @@ def main():
     gather = args.gather if world > 1 else "none"
     sym = None
     # Pipelined steps (default): the steps of this benchmark are independent passes over the ring, so the activation staging of step
-    # i+1 (ggb_dev_mul_mat_batch_phase 1, on its own stream, into the other of two workspaces) runs under the GEMVs of step i
-    # (phase 2), and -- N > 1 -- the exchange of step i on a third stream under step i+1.  Every step still stages AND multiplies
-    # inside the timed region.  --no-pipeline: one ggb_dev_mul_mat_batch call per step, as a lone decode step is issued.
+    # i+2 (ggb_dev_mul_mat_batch_phase 3: no wait for its predecessor, into the third of three workspaces) is issued IN the GEMV
+    # stream between the GEMVs of steps i and i+1 (phase 2) and runs beside them (its 128-thread CTAs fit next to a resident GEMV
+    # CTA), and -- N > 1 -- the exchange of step i on a second stream under step i+1.  Consecutive GEMVs then stay back-to-back
+    # programmatic launches, as in the kernel-only roofline pass.  Why the orders hold: a GEMV's consumers wait for the staging
+    # kernel in front of it to complete, and that kernel completes only after the GEMV in front of IT has (trailing
+    # griddepcontrol.wait) -- so GEMV j+1 starts after GEMV j, which had waited for staging j+1; and staging j+3, which overwrites
+    # workspace j mod 3, is launched only once GEMV j+1 has passed that wait, i.e. after GEMV j is complete.  Every step still stages
+    # AND multiplies inside the timed region.  --no-pipeline: one ggb_dev_mul_mat_batch call per step, as a lone decode step is issued.
     pipelined = not args.no_pipeline and gather in ("none", "fused") and not args.epilogue_stores
     NBUF = 2 if (pipelined or (gather == "fused" and not args.epilogue_stores)) else 1
     mm_bufs = [(N.ggb_dev_mm * RING)() for _ in range(NBUF)]
@@ -253,12 +258,11 @@ def main():
                 m.Y, m.ldy_bytes = Yloc[i].data_ptr(), 4 * M_LOCAL
     mms = mm_bufs[0]
     wsb = L.ggb_dev_workspace_bytes(mms, RING)
-    ws = torch.empty(NBUF * wsb + 256, dtype=torch.uint8, device=dev)
+    NWS = 3 if pipelined else NBUF
+    ws = torch.empty(NWS * wsb + 256, dtype=torch.uint8, device=dev)
     wsp = (ws.data_ptr() + 255) // 256 * 256
     comm = torch.cuda.Stream(device=dev) if (NBUF == 2 and gather == "fused") else None
     cptr = C.c_void_p(comm.cuda_stream) if comm is not None else None
-    stg = torch.cuda.Stream(device=dev) if pipelined else None
-    gptr = C.c_void_p(stg.cuda_stream) if stg is not None else None
 
     class Ev:                                                # one set of events per buffer: staged, multiplied, exchanged
         def __init__(self):
@@ -272,29 +276,25 @@ def main():
     torch.cuda.synchronize()
 
     def pipe(n, E):
-        """n pipelined steps starting on buffer total_steps & 1 (see `pipelined` above)."""
-        def stage(b):
-            if E.multiplied[b]:
-                stg.wait_event(E.mul[b])                    # the GEMVs that last read workspace b are done
-            N.check(L.ggb_dev_mul_mat_batch_phase(mm_bufs[b], RING, wsp + b * wsb, wsb, gptr, 1))
-            E.stage[b].record(stg)
-            E.staged[b] = True
+        """n pipelined steps (see `pipelined` above); workspaces 0, 1, 2, 0, ... from the start of every call, dst buffers by step parity."""
         if n <= 0:
             return
-        b0 = total_steps[0] & 1
-        E.fork.record(stream)
-        stg.wait_event(E.fork)                              # (inside a capture this is what pulls the staging stream into the graph)
-        stage(b0)
+
+        def stage(w, phase):
+            N.check(L.ggb_dev_mul_mat_batch_phase(mm_bufs[0], RING, wsp + w * wsb, wsb, sptr, phase))
+        # the first two stagings of a sequence wait for whatever is still in flight on the stream (an earlier sequence's GEMVs)
+        stage(0, 1)
+        if n > 1:
+            stage(1, 1)
         for j in range(n):
-            b = (b0 + j) & 1
-            if j + 1 < n:
-                stage(b ^ 1)                                # the next step's staging, under this step's GEMVs
-            stream.wait_event(E.stage[b])
+            b = (total_steps[0] + j) & 1 if NBUF == 2 else 0
             if comm is not None and E.pushed[b]:
                 stream.wait_event(E.comm[b])                # the exchange that last read / filled dst buffer b is done
-            N.check(L.ggb_dev_mul_mat_batch_phase(mm_bufs[b], RING, wsp + b * wsb, wsb, sptr, 2))
-            E.mul[b].record(stream)
-            E.multiplied[b] = True
+            N.check(L.ggb_dev_mul_mat_batch_phase(mm_bufs[b], RING, wsp + (j % 3) * wsb, wsb, sptr, 2))
+            if comm is not None:
+                E.mul[b].record(stream)
+            if j + 2 < n:
+                stage((j + 2) % 3, 3)                       # two steps ahead, beside the GEMVs of steps j and j+1
             if comm is not None:
                 comm.wait_event(E.mul[b])
                 sym.push_barrier(cptr, (b * RING * M_total + rank * M_LOCAL) * 4, M_LOCAL * 4, M_total * 4, RING)
@@ -354,9 +354,8 @@ def main():
         """exactly n steps: replays of the GSTEPS-step graph, then ONE replay of a graph of the remaining n % GSTEPS steps (captured on
         first use, outside any timed region: prepare_steps), so that a short --steps run is not a mix of replayed and Python-issued steps"""
         if graph is not None:
-            for aux in (stg, comm):
-                if aux is not None:
-                    stream.wait_stream(aux)                 # Python-issued steps may still have staging / exchange work in flight on the side streams
+            if comm is not None:
+                stream.wait_stream(comm)                    # Python-issued steps may still have exchange work in flight on the side stream
             for _ in range(n // GSTEPS):
                 graph.replay()
             total_steps[0] += (n // GSTEPS) * GSTEPS
@@ -435,6 +434,15 @@ def main():
     step_bytes_rank = RING * alg_bytes_per_node(M_LOCAL, K)
     value = world * step_bytes_rank / (ms_per_step * 1e-3) / 1e9
 
+    # ---- the pipelined steps must leave the bytes one plain call leaves (N = 1; N > 1 is checked against an all-gather below) ----
+    if pipelined and world == 1:
+        torch.cuda.synchronize()
+        got = Y.clone()
+        Y.zero_()
+        N.check(L.ggb_dev_mul_mat_batch(mms, RING, wsp, wsb, sptr))
+        torch.cuda.synchronize()
+        assert torch.equal(got, Y), "pipelined steps differ from a plain ggb_dev_mul_mat_batch call"
+
     # ---- the fused exchange must leave the same bytes everywhere as a plain all-gather of the per-rank blocks ----
     if gather == "fused":
         mine = np.zeros((RING, M_total), dtype=np.float32)
@@ -492,7 +500,7 @@ def main():
             "dtype": "int8 dot (Q4_0 x Q8_0), f32 scales", "data": "synthetic",
             "config": {"workload": "configs[1]: Q4_0 4096x4096 GEMV, single token", "ring": RING,
                        "step": "%d independent MUL_MAT nodes (distinct weights, %.1f MB > 2x L2, no flush needed), 1 act + 1 GEMV launch" % (RING, RING * M_LOCAL * rb / 1e6),
-                       "pipelining": ("steps are independent: the activation staging of step i+1 runs on a second stream under the GEMVs of step i (two workspaces)%s; every step stages and multiplies inside the timed region; %d steps per CUDA-graph replay" % ("; the exchange of step i under step i+1" if world > 1 else "", GSTEPS)) if pipelined else "none (--no-pipeline)",
+                       "pipelining": ("steps are independent: the activation staging of step i+2 is issued between the GEMVs of steps i and i+1 and runs beside them (three workspaces; consecutive GEMVs stay back-to-back programmatic launches)%s; every step stages and multiplies inside the timed region; %d steps per CUDA-graph replay" % ("; the exchange of step i under step i+1" if world > 1 else "", GSTEPS)) if pipelined else "none (--no-pipeline)",
                        "rows_per_rank": M_LOCAL, "rows_total": M_total, "k": K,
                        "parallelism": "row-split x%d + all-gather (%s)" % (world, args.gather) if world > 1 else "1 GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
         const int local = live ? blk - nd.blk0 : 0;
         const int row = local / b.kb, col = local - row * b.kb;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        asm volatile("griddepcontrol.wait;" ::: "memory");      // activations may be the previous kernel's output
+        if (!b.no_wait) asm volatile("griddepcontrol.wait;" ::: "memory");      // activations may be the previous kernel's output
         if (live) {
             const char *p = reinterpret_cast<const char *>(nd.x) + (long long)row * nd.ldx_bytes + (long long)col * 128 + sub * 16;
             if (b.vec16) v = *reinterpret_cast<const float4 *>(p);
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
         const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
         const int q4 = (b.K + 3) / 4;                           // float4 groups per row
         const long long total = (long long)b.total_blk * q4;    // total_blk = total rows here
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (!b.no_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
         if (t < total) {
             const int grow = (int)(t / q4), c4 = (int)(t - (long long)grow * q4);
             int n = 0;
@@ -543,6 +543,7 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
             }
         }
     }
+    if (b.no_wait) asm volatile("griddepcontrol.wait;" ::: "memory");      // never complete before everything ahead in the stream has
 }
 
 // Batched (tensor-core) path: activations as fp16 values the reference's dot effectively multiplies by:

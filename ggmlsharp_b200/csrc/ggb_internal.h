@@ -79,7 +79,10 @@ int launch_dup_f32_strided(const void *src, const int64_t ne[4], const uint64_t 
 size_t act_row_bytes(int wtype, int64_t K);
 struct ActNode { const float *x; long long ldx_bytes; uint8_t *out; int N; int blk0; };
 // bps > 1: unit-major Q8P planes for the fast GEMV (block b = bps*u + j stored at plane index j*(kb/bps) + u); else linear
-struct ActHdr { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; };
+// no_wait: the caller guarantees that neither the activations nor the rows being written are touched by work still in flight on the
+// stream, so the kernel does not wait for its predecessor before it starts (it still does before it COMPLETES, which keeps completion
+// transitive along a chain of programmatically dependent launches)
+struct ActHdr { int n_nodes; int K; int kb; int row_bytes; int wtype; int total_blk; int vec16; int bps; int no_wait; int pad_; };
 // kernel parameters above 4 KB cost several microseconds per launch, so launches with few nodes pass the small variant
 template <int CAP> struct ActBatchT : ActHdr { ActNode node[CAP]; };
 using ActBatch = ActBatchT<GGB_MAX_BATCH_NODES>;

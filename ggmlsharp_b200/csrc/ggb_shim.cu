@@ -298,7 +298,8 @@ static int check_mm(const ggb_dev_mm &m)
 }
 
 // ggb_dev_mul_mat_batch_phase: 0 = stage the activations and multiply (the default), 1 = stage only, 2 = multiply what an earlier
-// phase-1 call with the same arguments left in the workspace.  Single-token nodes only.
+// staging call with the same arguments left in the workspace, 3 = stage only and do not wait for the preceding kernel of the stream
+// (the caller vouches for the activations and the workspace).  Single-token nodes only.
 static thread_local int tl_phase = 0;
 
 static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, cudaStream_t s)
@@ -470,7 +471,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
         for (size_t c0 = 0; c0 < grp.size(); c0 += GGB_MAX_BATCH_NODES) {
             static thread_local ActBatch ab;
             static_cast<ActHdr &>(ab) = ActHdr{};
-            ab.K = (int)K; ab.kb = (int)(K / GGB_QK); ab.row_bytes = (int)arow; ab.wtype = type; ab.vec16 = 1; ab.bps = bps0;
+            ab.K = (int)K; ab.kb = (int)(K / GGB_QK); ab.row_bytes = (int)arow; ab.wtype = type; ab.vec16 = 1; ab.bps = bps0; ab.no_wait = tl_phase == 3 ? 1 : 0;
             int tot = 0;
             for (size_t c = c0; c < std::min(grp.size(), c0 + (size_t)GGB_MAX_BATCH_NODES); c++) {
                 const ggb_dev_mm &m = mm[grp[c]];
@@ -505,7 +506,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
                 passes.push_back({i, (int)c, nc}); c += nc;
             }
         }
-        if (tl_phase == 1) continue;                            // staging only
+        if (tl_phase == 1 || tl_phase == 3) continue;           // staging only
         std::vector<char> pdone(passes.size(), 0);
         bool first_launch = true;
         for (size_t p0 = 0; p0 < passes.size(); p0++) {
@@ -1860,7 +1861,7 @@ int ggb_dev_mul_mat_batch_phase(const ggb_dev_mm *mm, int count, void *ws, size_
 {
     int rc = ensure_init();
     if (rc) return rc;
-    if (count < 0 || (count && !mm) || phase < 0 || phase > 2) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch_phase: bad arguments");
+    if (count < 0 || (count && !mm) || phase < 0 || phase > 3) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch_phase: bad arguments");
     for (int i = 0; i < count; i++) if (phase && needs_k_segments(mm[i])) return set_error(GGB_E_UNSUPPORTED, "ggb_dev_mul_mat_batch_phase: rows this long are multiplied in K segments (one phase only)");
     tl_phase = phase;
     rc = dev_batch(mm, count, ws, ws_bytes, stream ? static_cast<cudaStream_t>(stream) : g_stream);

@@ -257,7 +257,10 @@ int  ggb_dev_mul_mat_batch(const ggb_dev_mm *mm, int count, void *workspace, siz
 /* The same call in two halves, for callers that pipeline a stream of single-token batches themselves (bench.py does): phase 1 only
  * stages the activations of the batch into `workspace` (the reference's INIT phase: src1 -> Q8 / Half rows, Ggml.cs:6362-6379, 6641-6655),
  * phase 2 only multiplies, reading what a phase-1 call with the same nodes and workspace left there; phase 0 = ggb_dev_mul_mat_batch.
- * With two workspaces the staging of batch i+1 (on one stream) runs under the GEMV of batch i (on another).  N < 16 nodes only. */
+ * With two workspaces the staging of batch i+1 (on one stream) runs under the GEMV of batch i (on another).  Phase 3 stages like
+ * phase 1 but does not wait for the preceding kernel of its stream before it starts: for a caller who knows that neither the activations
+ * nor this workspace are touched by work in flight (a third workspace) -- the staging kernel can then be issued IN the GEMV stream,
+ * between two GEMVs, without breaking their back-to-back launch.  N < 16 nodes only. */
 int  ggb_dev_mul_mat_batch_phase(const ggb_dev_mm *mm, int count, void *workspace, size_t workspace_bytes, void *stream, int phase);
 /* Device-pointer codecs on a stream (no sync). */
 int  ggb_dev_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k, void *stream);
