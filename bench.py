@@ -261,7 +261,10 @@ def main():
     NWS = 3 if pipelined else NBUF
     ws = torch.empty(NWS * wsb + 256, dtype=torch.uint8, device=dev)
     wsp = (ws.data_ptr() + 255) // 256 * 256
-    comm = torch.cuda.Stream(device=dev) if (NBUF == 2 and gather == "fused") else None
+    # HIGH priority: the next GEMV's CTAs are already pending (programmatic launch) when the push is issued, and the block scheduler
+    # serves pending CTAs of equal priority in order -- the 64 small push CTAs would wait a whole GEMV behind CTAs that cannot be
+    # placed yet (benchmarks/coresidency_probe.py: 50 us at equal priority, 19 us = launch + run at high priority)
+    comm = torch.cuda.Stream(device=dev, priority=-1) if (NBUF == 2 and gather == "fused") else None
     cptr = C.c_void_p(comm.cuda_stream) if comm is not None else None
 
     class Ev:                                                # one set of events per buffer: staged, multiplied, exchanged

@@ -647,7 +647,14 @@ template int launch_gemv_typed_sib<GGB_MAX_BATCH_NODES>(const GemvBatchT<GGB_MAX
 extern template int launch_gemv_typed_sib<GGB_SMALL_BATCH_NODES>(const GemvBatchT<GGB_SMALL_BATCH_NODES> &, size_t, int, cudaStream_t, bool);
 extern template int launch_gemv_typed_sib<GGB_MAX_BATCH_NODES>(const GemvBatchT<GGB_MAX_BATCH_NODES> &, size_t, int, cudaStream_t, bool);
 
-int gemv_num_ctas() { return device_sm_count(); }
+// One persistent CTA per SM -- minus GGB200_GEMV_SPARE_SMS (default 0).  Measured (benchmarks/coresidency_probe.py): a small kernel on
+// another stream is NOT placed beside a resident GEMV CTA even when registers, threads and shared memory would allow it; it gets an SM
+// only when a GEMV CTA exits.  Leaving a few SMs to the side kernels (staging, result copy, peer push) is what lets them overlap.
+int gemv_num_ctas()
+{
+    static const int spare = [] { const char *e = getenv("GGB200_GEMV_SPARE_SMS"); return e ? atoi(e) : 0; }();
+    return std::max(1, device_sm_count() - std::max(0, spare));
+}
 int64_t gemv_x_budget() { return X_BUDGET + 32 * 1024; }
 int gemv_group_rows(const GemvHdr &b) { return b.async ? NWF * b.rs : b.rs; }
 static int unit_bytes_async(int type)

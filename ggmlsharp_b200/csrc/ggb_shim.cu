@@ -92,7 +92,13 @@ static int ensure_init()
     g_devs.emplace_back();
     DevCtx &d0 = g_devs[0];
     d0.dev = dev; d0.stream = g_stream; d0.ev0 = g_ev0; d0.ev1 = g_ev1;
-    GGB_CUDA(cudaStreamCreateWithFlags(&d0.stream2, cudaStreamNonBlocking));
+    // Lane 2 gets the HIGHEST priority: when its small PCIe-side kernels are issued, the CTAs of the next GEMV are often already pending
+    // (programmatic launch), and the block scheduler serves pending CTAs of equal priority in order -- a 128-thread staging CTA would
+    // wait a whole GEMV behind CTAs that cannot be placed yet (benchmarks/coresidency_probe.py: 50 us at equal priority, 19 us = launch
+    // + run at high priority)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    GGB_CUDA(cudaStreamCreateWithPriority(&d0.stream2, cudaStreamNonBlocking, prio_hi));
     GGB_CUDA(cudaEventCreateWithFlags(&d0.fork, cudaEventDisableTiming));
     GGB_CUDA(cudaEventCreateWithFlags(&d0.join, cudaEventDisableTiming));
     g_multi = 0;
@@ -159,7 +165,7 @@ static int ensure_multi(int want)
         if (cudaSetDevice(dc.dev) != cudaSuccess) { cudaGetLastError(); continue; }
         for (const DevCtx &o : g_devs) { cudaError_t e1 = cudaDeviceEnablePeerAccess(o.dev, 0); if (e1 != cudaSuccess && e1 != cudaErrorPeerAccessAlreadyEnabled) ok = false; cudaGetLastError(); }
         if (ok && (cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&dc.ev0) != cudaSuccess || cudaEventCreate(&dc.ev1) != cudaSuccess ||
-                   cudaStreamCreateWithFlags(&dc.stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&dc.fork, cudaEventDisableTiming) != cudaSuccess ||
+                   cudaStreamCreateWithPriority(&dc.stream2, cudaStreamNonBlocking, -100 /* clamped to the highest */) != cudaSuccess || cudaEventCreateWithFlags(&dc.fork, cudaEventDisableTiming) != cudaSuccess ||
                    cudaEventCreateWithFlags(&dc.join, cudaEventDisableTiming) != cudaSuccess)) { cudaGetLastError(); ok = false; }
         if (ok) for (const DevCtx &o : g_devs) {
             cudaSetDevice(o.dev);
