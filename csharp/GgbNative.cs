@@ -22,6 +22,7 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_pool_set_weight_cache(IntPtr pool, int on);
     // row split of ggml_graph_compute across the GPUs of the box (off by default): max_devices < 0 = all, min_weight_bytes 0 = default 4 MiB
     [DllImport(Lib)] public static extern int ggb_pool_set_row_split(IntPtr pool, int maxDevices, nuint minWeightBytes);
+    [DllImport(Lib)] public static extern int ggb_row_split_rows(long M, int g, int G, long* row0, long* rows);
     [DllImport(Lib)] public static extern int ggb_mul_mat_node(IntPtr pool, ggml_tensor* dst);
     [DllImport(Lib)] public static extern int ggb_graph_compute_mul_mats(IntPtr pool, ggml_cgraph* graph, int flags, byte* done);
     [DllImport(Lib)] public static extern int ggb_graph_plan(ggml_cgraph* graph, int flags, byte* done);

@@ -20,7 +20,8 @@ namespace ggb {
 
 namespace {
 
-__global__ void __launch_bounds__(256) k_binary_f32(int op, const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ z, long long n)
+// (no __restrict__: the in-place ADD / MUL of ggml_add_inplace and friends passes z == a, and silu / scale run in place too)
+__global__ void __launch_bounds__(256) k_binary_f32(int op, const float *a, const float *b, float *z, long long n)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const long long n4 = n >> 2;
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(256) k_binary_f32(int op, const float *__restr
     }
 }
 
-__global__ void __launch_bounds__(256) k_binary_f32_scalar(int op, const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ z, long long n)
+__global__ void __launch_bounds__(256) k_binary_f32_scalar(int op, const float *a, const float *b, float *z, long long n)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) k_scale_f32(float *__restrict__ y, float 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = __fmul_rn(y[i], v);
 }
 
-__global__ void __launch_bounds__(256) k_silu_f32(const float *__restrict__ x, float *__restrict__ y, long long n, const unsigned short *__restrict__ table)
+__global__ void __launch_bounds__(256) k_silu_f32(const float *x, float *y, long long n, const unsigned short *__restrict__ table)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) k_silu_f32(const float *__restrict__ x, f
 }
 
 // one CTA per row
-__global__ void __launch_bounds__(256) k_rms_norm_f32(const float *__restrict__ x, long long x_stride, float *__restrict__ y, long long y_stride, int ne00)
+__global__ void __launch_bounds__(256) k_rms_norm_f32(const float *x, long long x_stride, float *y, long long y_stride, int ne00)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const float *xr = x + (long long)blockIdx.x * x_stride;

@@ -1554,6 +1554,13 @@ int ggb_pool_set_weight_cache(ggb_pool *pool, int on)
     return GGB_OK;
 }
 
+int ggb_row_split_rows(int64_t M, int g, int G, int64_t *row0, int64_t *rows)
+{
+    if (M < 0 || G < 1 || g < 0 || g >= G || !row0 || !rows) return set_error(GGB_E_INVALID, "ggb_row_split_rows: bad arguments");
+    shard_rows(M, g, G, *row0, *rows);
+    return GGB_OK;
+}
+
 int ggb_pool_set_row_split(ggb_pool *pool, int max_devices, size_t min_weight_bytes)
 {
     std::lock_guard<std::mutex> lk(g_mu);

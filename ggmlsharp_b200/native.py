@@ -98,6 +98,7 @@ GGB_SYMBOLS = {
     "ggb_tensor_invalidate": (C.c_int, [C.c_void_p, TP]),
     "ggb_pool_set_weight_cache": (C.c_int, [C.c_void_p, C.c_int]),
     "ggb_pool_set_row_split": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t]),
+    "ggb_row_split_rows": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ggb_graph_plan": (C.c_int, [C.POINTER(ggml_cgraph), C.c_int, C.POINTER(C.c_uint8)]),
     "ggb_dev_weight_rowexp": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ggb_mul_mat_node": (C.c_int, [C.c_void_p, TP]),

@@ -162,6 +162,9 @@ int  ggb_pool_set_weight_cache(ggb_pool *pool, int on);
  * math (see ggb_shim.cu: row_split_width).  Results are identical to the single-GPU ones bit for bit: a row's dot products do not
  * depend on which device computes them. */
 int  ggb_pool_set_row_split(ggb_pool *pool, int max_devices, size_t min_weight_bytes);
+/* The partition rule itself (no device needed): rows [*row0, *row0 + *rows) of an M-row src0 that device g of G multiplies --
+ * dr = ceil(M / G), [dr g, min(dr g + dr, M)), the reference's thread split (Ggml.cs:6665-6672) with nth = G. */
+int  ggb_row_split_rows(int64_t M, int g, int G, int64_t *row0, int64_t *rows);
 /* Call after rewriting tensor->data of a cached weight behind the API's back: drops every mirror that shares a byte with the
  * tensor (a view of a cached leaf, or a leaf some cached view looks into); NULL drops every mirror of the pool. */
 int  ggb_tensor_invalidate(ggb_pool *pool, const ggml_tensor *t);

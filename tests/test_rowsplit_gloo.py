@@ -26,6 +26,23 @@ def test_shard_rows_is_the_reference_thread_split():
     assert rowsplit.shard_bytes(11008, 2560, 8, 7) == (7 * 1376 * 2560, 1376 * 2560)      # 11008/8 = 1376 rows, ragged vs 128
 
 
+def test_the_shim_splits_rows_by_the_same_rule():
+    # ggb_row_split_rows is what run_nodes_sharded (the row split inside the shim, one host thread per GPU) uses per device
+    import ctypes as C
+    from ggmlsharp_b200 import native as N
+    for nr, world in ((4096, 8), (11008, 8), (11008, 3), (1408, 2), (10, 4), (3, 8), (1, 2), (0, 2), (64 * 8, 8)):
+        covered = []
+        for g in range(world):
+            r0, n = C.c_int64(), C.c_int64()
+            assert N.lib().ggb_row_split_rows(nr, g, world, C.byref(r0), C.byref(n)) == 0
+            want0, wantn = rowsplit.shard_rows(nr, world, g)
+            assert n.value == wantn and (wantn == 0 or r0.value == want0)
+            covered += list(range(r0.value, r0.value + n.value))
+        assert covered == list(range(nr))
+    r0, n = C.c_int64(), C.c_int64()
+    assert N.lib().ggb_row_split_rows(16, 2, 2, C.byref(r0), C.byref(n)) == N.E_INVALID
+
+
 WORKER = textwrap.dedent('''
     import os, sys
     sys.path.insert(0, %r)
