@@ -9,6 +9,8 @@
 // + 0.625 / 0.75 B written per element).
 #include "ggb_internal.h"
 
+#include <vector>
+
 #include <algorithm>
 #include <cstdlib>
 
@@ -662,6 +664,91 @@ __global__ void __launch_bounds__(256) k_act_f16_dequant(const __grid_constant__
     if (!b.wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// The same staging, software-pipelined (16-byte aligned rows; the row must fit twice in shared memory): a CTA loops over rows and
+// copies row r + gridDim.x into the other of two shared-memory row buffers with cp.async while it converts row r.  In the kernel
+// above a CTA's row is strictly phased -- load, reduce, convert, store -- and nothing of the NEXT row is in flight meanwhile: ncu r02
+// measured 30 % of the DRAM rate (staging was 22 % of the 28-node prompt step) -- and its loads, one thread per 128-byte block, touch
+// 32 lines per warp instruction.  Here the copies are coalesced 16-byte chunks, and the chunks of a block are rotated by the block
+// index so that neither the asynchronous copies nor the LDS.128 of the owning thread hit one bank group.
+__global__ void __launch_bounds__(256) k_act_f16_dequant_pipe(const __grid_constant__ ActGemmBatch b)
+{
+    extern __shared__ __align__(16) float act_smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (b.wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const ActGemmNode &nd = b.node[blockIdx.y];
+    const int wtype = b.wtype, perm = b.perm, N = nd.N, Npad = nd.Npad, K = nd.K;
+    const float *__restrict__ x = nd.x; const long long ldx_bytes = nd.ldx_bytes; __half *__restrict__ out = nd.out;
+    int *__restrict__ ex = nd.ex;
+    const int kb = K / GGB_QK;
+    const int tid = threadIdx.x, nth = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    const bool scaled = wtype != GGML_TYPE_F16;
+    __shared__ float s_max[8];
+    float *const buf[2] = {act_smem, act_smem + K};               // K of THIS node: both halves lie inside the launch's allocation (sized by the longest row)
+    // COALESCED copies: consecutive threads take consecutive 16-byte chunks of the row (a warp instruction covers 512 contiguous bytes;
+    // one thread per 128-byte block would touch 32 lines per instruction and is bound by L1 wavefronts, not DRAM), so a block's bytes
+    // arrive through eight different threads and the row is complete only after a CTA barrier
+    auto issue = [&](int row, float *dstrow) {
+        if (row < N) {
+            const char *src = reinterpret_cast<const char *>(x) + (long long)row * ldx_bytes;
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dstrow);
+            for (int c = tid; c < kb * 8; c += nth) {
+                const int col = c >> 3, i = c & 7;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)(col * 128 + (((i + col) & 7) << 4))), "l"(src + (long long)c * 16) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto load_block = [&](const float *srow, int col, float *e) {
+        const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(srow + col * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a0 + (uint32_t)(((i + col) & 7) << 4)));
+            e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w;
+        }
+    };
+    int row = blockIdx.x, cur = 0;
+    issue(row, buf[0]);
+    for (; row < Npad; row += gridDim.x, cur ^= 1) {
+        __syncthreads();                                           // everybody has finished reading the other buffer (the previous row)
+        issue(row + (int)gridDim.x, buf[cur ^ 1]);                 // the next row of this CTA, under the conversion of this one
+        asm volatile("cp.async.wait_group 1;" ::: "memory");      // this thread's copies of `row` have landed ...
+        __syncthreads();                                           // ... and everybody else's
+        const float *srow = buf[cur];
+        __half *orow = out + (long long)row * K;
+        float e[32];
+        const bool mine = tid < kb;
+        if (mine && row < N) load_block(srow, tid, e);
+        else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) e[i] = 0.0f;
+        }
+        float rs = 1.0f;
+        if (scaled) {
+            float am = act_block_amax(e);
+            if (row < N)
+                for (int col = tid + nth; col < kb; col += nth) { float t[32]; load_block(srow, col, t); am = fmaxf(am, act_block_amax(t)); }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+            __syncthreads();                                        // s_max of the previous row has been read by everyone
+            if (lane == 0) s_max[warp] = am;
+            __syncthreads();
+            am = s_max[0];
+            for (int w = 1; w < nwarps; w++) am = fmaxf(am, s_max[w]);
+            const int er = range_exp(am);
+            rs = exp2i(-er);
+            if (tid == 0 && ex) ex[row] = er;
+        }
+        if (mine) act_emit_block(e, wtype, perm, rs, orow + (long long)tid * GGB_QK);
+        for (int col = tid + nth; col < kb; col += nth) {
+            if (row < N) load_block(srow, col, e);                  // else e is still all zero
+            act_emit_block(e, wtype, perm, rs, orow + (long long)col * GGB_QK);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!b.wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory");      // completion stays transitive along the PDL chain
+}
+
 } // namespace
 
 size_t act_row_bytes(int wtype, int64_t K)
@@ -789,6 +876,28 @@ int launch_act_batch(const ActBatch &b, cudaStream_t s, bool pdl)
 int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s, bool pdl)
 {
     if (b.n_nodes <= 0) return GGB_OK;
+    // nodes of two or three different row lengths (a Llama layer: 4096 and 11008): one launch per K, because the pipelined kernel
+    // sizes its shared-memory row buffers -- and with them its occupancy -- by K.  More than that: one launch sized by the longest row.
+    int n_distinct = 0;
+    for (int i = 0; i < b.n_nodes; i++) {
+        bool seen = false;
+        for (int j = 0; j < i && !seen; j++) seen = b.node[j].K == b.node[i].K;
+        if (!seen) n_distinct++;
+    }
+    for (int i = 1; i < b.n_nodes && n_distinct <= 3; i++)
+        if (b.node[i].K != b.node[0].K) {
+            static thread_local ActGemmBatch part;
+            std::vector<char> done((size_t)b.n_nodes, 0);
+            for (int i0 = 0; i0 < b.n_nodes; i0++) {
+                if (done[(size_t)i0]) continue;
+                part.n_nodes = 0; part.wtype = b.wtype; part.perm = b.perm; part.wait_prior = b.wait_prior;
+                for (int j = i0; j < b.n_nodes; j++)
+                    if (!done[(size_t)j] && b.node[j].K == b.node[i0].K) { part.node[part.n_nodes++] = b.node[j]; done[(size_t)j] = 1; }
+                int rc = launch_act_f16_dequant_batch(part, s, pdl);
+                if (rc) return rc;
+            }
+            return GGB_OK;
+        }
     int max_rows = 0, max_kb = 0;
     for (int i = 0; i < b.n_nodes; i++) {
         ActGemmNode &nd = b.node[i];
@@ -797,17 +906,35 @@ int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s, bool pdl)
     }
     if (max_rows <= 0 || max_kb <= 0) return GGB_OK;
     const int threads = max_kb <= 32 ? 32 : max_kb <= 64 ? 64 : max_kb <= 128 ? 128 : 256;     // one block of 32 activations per thread
-    // one CTA per row; capped so that a group of many nodes still launches a bounded grid (CTAs loop over rows)
-    const long long cap = std::max<long long>(1, (long long)device_sm_count() * (2048 / threads) / b.n_nodes);
-    const long long grid = std::min<long long>(max_rows, cap);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid, (unsigned)b.n_nodes);
     cfg.blockDim = dim3((unsigned)threads);
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    // the software-pipelined kernel: every node's rows 16-byte aligned, all nodes of the launch share K (one shared-memory size),
+    // two rows fit in shared memory
+    bool pipe = true;
+    for (int i = 0; i < b.n_nodes; i++) if (!b.node[i].vec16) pipe = false;
+    const size_t smem = (size_t)2 * (size_t)max_kb * GGB_QK * 4;      // (a node with shorter rows uses the front of each half)
+    static const bool no_pipe = getenv("GGB200_ACT_NO_PIPE") != nullptr;
+    if (pipe && !no_pipe && smem <= 200 * 1024) {
+        static PerDeviceOnce once;
+        if (once.need()) GGB_CUDA(cudaFuncSetAttribute(k_act_f16_dequant_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        // as many CTAs as are resident at once (shared memory or registers decide), dealt to the nodes; each loops over its rows
+        const long long per_sm = std::max<long long>(1, std::min<long long>((long long)(220 * 1024) / (long long)(smem + 1024), 65536 / (80 * threads)));
+        const long long cap = std::max<long long>(1, (long long)device_sm_count() * per_sm / b.n_nodes);
+        cfg.gridDim = dim3((unsigned)std::min<long long>(max_rows, cap), (unsigned)b.n_nodes);
+        cfg.dynamicSmemBytes = smem;
+        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant_pipe, b));
+        count_launch();
+        return GGB_OK;
+    }
+    // one CTA per row; capped so that a group of many nodes still launches a bounded grid (CTAs loop over rows)
+    const long long cap = std::max<long long>(1, (long long)device_sm_count() * (2048 / threads) / b.n_nodes);
+    const long long grid = std::min<long long>(max_rows, cap);
+    cfg.gridDim = dim3((unsigned)grid, (unsigned)b.n_nodes);
     GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant, b));
     count_launch();
     return GGB_OK;
