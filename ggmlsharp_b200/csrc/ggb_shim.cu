@@ -366,7 +366,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
     };
     int n_tc = 0;
     for (int i = 0; i < count; i++) if (mm[i].M > 0 && mm[i].N > 0 && use_gemm(mm[i])) n_tc++;
-    if (tl_phase && n_tc) return set_error(GGB_E_UNSUPPORTED, "ggb_dev_mul_mat_batch_phase: split phases are for single-token (N < 16) nodes only");
+
     for (int i = 0; i < count; i++) {
         const ggb_dev_mm &m = mm[i];
         if (m.M == 0 || m.N == 0) continue;
@@ -1876,6 +1876,10 @@ int ggb_dev_mul_mat_batch_phase(const ggb_dev_mm *mm, int count, void *ws, size_
     if (rc) return rc;
     if (count < 0 || (count && !mm) || phase < 0 || phase > 3) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch_phase: bad arguments");
     for (int i = 0; i < count; i++) if (phase && needs_k_segments(mm[i])) return set_error(GGB_E_UNSUPPORTED, "ggb_dev_mul_mat_batch_phase: rows this long are multiplied in K segments (one phase only)");
+    if (phase)
+        for (int i = 0; i < count; i++)
+            if (mm[i].M > 0 && mm[i].N > 0 && use_gemm(mm[i]))
+                return set_error(GGB_E_UNSUPPORTED, "ggb_dev_mul_mat_batch_phase: split phases are for single-token (N < 16) nodes only");
     tl_phase = phase;
     rc = dev_batch(mm, count, ws, ws_bytes, stream ? static_cast<cudaStream_t>(stream) : g_stream);
     tl_phase = 0;

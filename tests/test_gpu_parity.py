@@ -597,3 +597,44 @@ def test_rows_of_any_length():
         c.graph_compute(c.build_forward(y))
         got = ggml.tensor_f32(y).reshape(1, 7).copy()
     assert rel_l2(got, orc.mul_mat_2d(N.Q4_0, wb, 7, K, x)) <= 6e-6
+
+
+def test_split_phases_equal_one_call():
+    """ggb_dev_mul_mat_batch_phase: staging (phase 1, or 3 = without waiting for the preceding kernel) and multiplying (phase 2) as two
+    calls leave the bytes of the one-call form; prompt-sized nodes are refused (their staging and GEMM are one pipeline)."""
+    rng = np.random.default_rng(92)
+    specs = [(N.Q4_0, 300, 512), (N.Q4_1, 129, 512), (N.F16, 64, 256), (N.F32, 33, 128), (N.Q5_0, 48, 512), (N.Q4_0, 40, 4128)]
+    d = Dev()
+    try:
+        mms = (N.ggb_dev_mm * len(specs))()
+        for i, (t, M, K) in enumerate(specs):
+            wb = orc.encode_weights(t, weights(rng, M, K))
+            x = rng.standard_normal((2, K)).astype(np.float32)
+            m = mms[i]
+            m.type, m.M, m.K, m.N = t, M, K, 2
+            m.W, m.nb01 = d.put(wb), wb.shape[1]
+            m.X, m.ldx_bytes = d.put(x), 4 * K
+            m.Y, m.ldy_bytes = d.empty(4 * M * 2), 4 * M
+        wsb = N.lib().ggb_dev_workspace_bytes(mms, len(specs))
+        ws = d.empty(wsb)
+        N.check(N.lib().ggb_dev_mul_mat_batch(mms, len(specs), ws, wsb, None))
+        N.check(N.lib().ggb_stream_sync(None))
+        want = [d.get(mms[i].Y, (2, specs[i][1])) for i in range(len(specs))]
+        zero = np.zeros(wsb, np.uint8)
+        for stage_phase in (1, 3):
+            N.check(N.lib().ggb_dev_upload(ws, zero.ctypes.data, wsb))
+            for i, (t, M, K) in enumerate(specs):
+                z = np.zeros((2, M), np.float32)
+                N.check(N.lib().ggb_dev_upload(mms[i].Y, z.ctypes.data, z.nbytes))
+            N.check(N.lib().ggb_dev_mul_mat_batch_phase(mms, len(specs), ws, wsb, None, stage_phase))
+            N.check(N.lib().ggb_stream_sync(None))
+            assert not d.get(mms[0].Y, (2, specs[0][1])).any()              # staging alone multiplies nothing
+            N.check(N.lib().ggb_dev_mul_mat_batch_phase(mms, len(specs), ws, wsb, None, 2))
+            N.check(N.lib().ggb_stream_sync(None))
+            for i in range(len(specs)):
+                assert np.array_equal(d.get(mms[i].Y, (2, specs[i][1])), want[i]), (stage_phase, i)
+        mms[0].N = 16                                                       # a prompt-sized node
+        assert N.lib().ggb_dev_mul_mat_batch_phase(mms, 1, ws, wsb, None, 1) == N.E_UNSUPPORTED
+        assert N.lib().ggb_dev_mul_mat_batch_phase(mms, 1, ws, wsb, None, 7) == N.E_INVALID
+    finally:
+        d.close()
