@@ -1862,8 +1862,16 @@ size_t ggb_dev_workspace_bytes(const ggb_dev_mm *mm, int count)
     return t;
 }
 
+// The device-level entry points run on the caller's stream without the library lock; with stream == NULL they land on the library's
+// own stream, which the executor may be recording into a CUDA graph on another host thread -- those calls take the lock.
+struct OwnStreamLock {
+    std::unique_lock<std::mutex> lk;
+    explicit OwnStreamLock(const void *stream) { if (!stream) lk = std::unique_lock<std::mutex>(g_mu); }
+};
+
 int ggb_dev_mul_mat_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, void *stream)
 {
+    OwnStreamLock guard(stream);
     int rc = ensure_init();
     if (rc) return rc;
     if (count < 0 || (count && !mm)) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch: bad arguments");
@@ -1872,6 +1880,7 @@ int ggb_dev_mul_mat_batch(const ggb_dev_mm *mm, int count, void *ws, size_t ws_b
 
 int ggb_dev_mul_mat_batch_phase(const ggb_dev_mm *mm, int count, void *ws, size_t ws_bytes, void *stream, int phase)
 {
+    OwnStreamLock guard(stream);
     int rc = ensure_init();
     if (rc) return rc;
     if (count < 0 || (count && !mm) || phase < 0 || phase > 3) return set_error(GGB_E_INVALID, "ggb_dev_mul_mat_batch_phase: bad arguments");
@@ -1888,6 +1897,7 @@ int ggb_dev_mul_mat_batch_phase(const ggb_dev_mm *mm, int count, void *ws, size_
 
 int ggb_dev_weight_rowexp(int type, const void *W, int64_t nb01, int64_t M, int64_t K, int32_t *rowexp, void *stream)
 {
+    OwnStreamLock guard(stream);
     int rc = ensure_init();
     if (rc) return rc;
     if (!W || !rowexp) return set_error(GGB_E_INVALID, "ggb_dev_weight_rowexp: null pointer");
@@ -1896,18 +1906,20 @@ int ggb_dev_weight_rowexp(int type, const void *W, int64_t nb01, int64_t M, int6
 
 int ggb_dev_quantize_rows(int type, const float *src, void *dst, int64_t nrows, int64_t k, void *stream)
 {
+    OwnStreamLock guard(stream);
     int rc = ensure_init();
     if (rc) return rc;
     return launch_quantize_rows(type, src, k, dst, nrows, k, stream ? static_cast<cudaStream_t>(stream) : g_stream);
 }
 int ggb_dev_dequantize_rows(int type, const void *src, float *dst, int64_t nrows, int64_t k, void *stream)
 {
+    OwnStreamLock guard(stream);
     int rc = ensure_init();
     if (rc) return rc;
     return launch_dequantize_rows(type, src, dst, nrows, k, stream ? static_cast<cudaStream_t>(stream) : g_stream);
 }
 
-#define GGB_DEV_WRAP(call) do { int rc_ = ensure_init(); if (rc_) return rc_; cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_stream; return call; } while (0)
+#define GGB_DEV_WRAP(call) do { OwnStreamLock guard(stream); int rc_ = ensure_init(); if (rc_) return rc_; cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : g_stream; return call; } while (0)
 int ggb_dev_binary(int op, const float *a, const float *b, float *dst, int64_t n, void *stream) { GGB_DEV_WRAP(launch_binary_f32(op, a, b, dst, n, st)); }
 int ggb_dev_scale(float *x, float v, int64_t n, void *stream) { GGB_DEV_WRAP(launch_scale_f32(x, v, n, st)); }
 int ggb_dev_silu(const float *x, float *dst, int64_t n, void *stream) { GGB_DEV_WRAP(launch_silu_f32(x, dst, n, st)); }
@@ -1931,6 +1943,7 @@ int ggb_dev_alloc(size_t bytes, void **dptr)
 int ggb_dev_free(void *dptr) { if (dptr) { GGB_CUDA(cudaFree(dptr)); } return GGB_OK; }
 int ggb_dev_upload(void *dptr, const void *host, size_t bytes)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     int rc = ensure_init();
     if (rc) return rc;
     GGB_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, g_stream));
@@ -1940,6 +1953,7 @@ int ggb_dev_upload(void *dptr, const void *host, size_t bytes)
 }
 int ggb_dev_download(void *host, const void *dptr, size_t bytes)
 {
+    std::lock_guard<std::mutex> lk(g_mu);
     int rc = ensure_init();
     if (rc) return rc;
     GGB_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, g_stream));
@@ -1949,6 +1963,7 @@ int ggb_dev_download(void *host, const void *dptr, size_t bytes)
 }
 int ggb_stream_sync(void *stream)
 {
+    OwnStreamLock guard(stream);
     int rc = ensure_init();
     if (rc) return rc;
     GGB_CUDA(cudaStreamSynchronize(stream ? static_cast<cudaStream_t>(stream) : g_stream));

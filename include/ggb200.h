@@ -13,6 +13,11 @@
  * INTEGRATION.md shows the C# stubs.  Every struct below is laid out exactly as the C#
  * struct it mirrors (TypeDefinitions.cs), so the C# side passes its own pointers.
  *
+ * Threading: the library keeps one stream pair per device, so pool-level calls (pool_*, tensor_invalidate, mul_mat_node,
+ * graph_compute_mul_mats, quantize/dequantize_rows) serialise on one lock, whatever the pool; different contexts may be driven from
+ * different host threads.  ggb_dev_* calls run on the stream they are given without that lock; with stream == NULL they use the
+ * library's own stream and take it.
+ *
  * Conventions: every function returns 0 (GGB_OK) or a negative ggb_status and never
  * throws or aborts; ggb_last_error() returns a thread-local message.  There is no CPU
  * fallback: without a CUDA device every compute entry point fails with GGB_E_NODEVICE.
