@@ -113,7 +113,7 @@ class Runner:
         N = self.N
         it = max(4, iters // 4) if quick else iters
         yield self.run_nodes([(N.F32, 4096, 4096)] * 5, 1, "configs[0] on the device: F32 4096x4096 GEMV, ring of 5 distinct matrices (336 MB > 2x L2)", it)
-        yield self.run_nodes([(N.Q4_0, 4096, 4096)], 1, "configs[1] isolated: ONE Q4_0 4096x4096 GEMV per call (L2-warm, launch-latency bound: act + GEMV launch)", it * 4)
+        yield self.run_nodes([(N.Q4_0, 4096, 4096)], 1, "configs[1] isolated: ONE Q4_0 4096x4096 GEMV per call (L2-warm, launch-latency bound: one launch, the GEMV quantizes its own activation row)", it * 4)
         for t in (N.Q4_1, N.F16):
             n_ring = 10 if t == N.Q4_1 else 4
             yield self.run_nodes([(t, 11008, 4096)] * n_ring, 1, "configs[2]: %s 11008x4096 (w1/w3) GEMV, ring of %d (> 2x L2)" % (TN[t], n_ring), it)

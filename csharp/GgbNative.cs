@@ -74,6 +74,7 @@ internal static unsafe partial class GgbNative
     [DllImport(Lib)] public static extern int ggb_dev_download(void* host, void* dptr, nuint bytes);
     [DllImport(Lib)] public static extern int ggb_stream_sync(IntPtr stream);
     [DllImport(Lib)] public static extern int ggb_set_kernel_timing(int on);
+    [DllImport(Lib)] public static extern int ggb_set_decode_program(int on);
     [DllImport(Lib)] public static extern int ggb_get_stats(ggb_stats* stats);
     [DllImport(Lib)] public static extern int ggb_reset_stats();
     // row split across the GPUs of one box (one process per GPU): CUDA-IPC export / open of the symmetric dst buffer and the

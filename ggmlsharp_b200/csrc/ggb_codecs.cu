@@ -8,6 +8,7 @@
 // contiguous bytes per load instruction and the kernel is purely HBM-bound (roofline: 4 B read
 // + 0.625 / 0.75 B written per element).
 #include "ggb_internal.h"
+#include "ggb_act_q8.cuh"
 
 #include <vector>
 
@@ -491,36 +492,9 @@ __global__ void __launch_bounds__(256) k_act_batch(const __grid_constant__ ActBa
             if (b.vec16) v = *reinterpret_cast<const float4 *>(p);
             else { const float *f = reinterpret_cast<const float *>(p); v = make_float4(f[0], f[1], f[2], f[3]); }
         }
-        const float e[4] = {v.x, v.y, v.z, v.w};
-        float amax = fmaxf(fmaxf(fabsf(e[0]), fabsf(e[1])), fmaxf(fabsf(e[2]), fabsf(e[3])));
-#pragma unroll
-        for (int off = 1; off < 8; off <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
-        const float d = __fdiv_rn(amax, 127.0f);
-        const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
-        int q[4], s = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) { q[i] = (int)(int8_t)rne_byte(__fmul_rn(e[i], id)); s += q[i]; }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);                 // lanes 0-3: sum of quants 0..15, lanes 4-7: 16..31
-        {
-            const int other = __shfl_xor_sync(0xffffffffu, s, 4);
-            const int lo = sub < 4 ? s : other, hi = sub < 4 ? other : s;
-            // Q4_2 weights: each 16-element weight block needs its own half sum -> two int16; everything else: the block sum
-            s = b.wtype == GGML_TYPE_Q4_2 ? (int)(((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16)) : lo + hi;
-        }
-        uint32_t ev = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[2] & 0xFF) << 8);
-        uint32_t od = (uint32_t)(q[1] & 0xFF) | ((uint32_t)(q[3] & 0xFF) << 8);
-        ev |= __shfl_down_sync(0xffffffffu, ev, 1) << 16;
-        od |= __shfl_down_sync(0xffffffffu, od, 1) << 16;
-        if (live) {
-            uint8_t *o = nd.out + (long long)row * b.row_bytes;
-            const int idx = b.bps > 1 ? (col % b.bps) * (b.kb / b.bps) + col / b.bps : col;
-            if ((sub & 1) == 0) {
-                reinterpret_cast<uint32_t *>(o + (long long)idx * 16)[sub >> 1] = ev;
-                reinterpret_cast<uint32_t *>(o + (long long)b.kb * 16 + (long long)idx * 16)[sub >> 1] = od;
-            }
-            if (sub == 1) *reinterpret_cast<int2 *>(o + (long long)b.kb * 32 + (long long)idx * 8) = make_int2(__float_as_int(d), s);
-        }
+        uint32_t ev, od; float d; int s;
+        q8_block_sub8(v, sub, b.wtype == GGML_TYPE_Q4_2, ev, od, d, s);
+        if (live) q8_block_store(nd.out + (long long)row * b.row_bytes, b.kb, b.bps, col, sub, ev, od, d, s);
     } else {
         // F16 weights: src1 -> Half (Ggml.cs:6362-6379); F32 weights: dense copy.  One thread per 4 elements.
         const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -749,6 +723,123 @@ __global__ void __launch_bounds__(256) k_act_f16_dequant_pipe(const __grid_const
     if (!b.wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory");      // completion stays transitive along the PDL chain
 }
 
+// The same pipeline with TWO threads per 32-element block (16 elements each; the block maximum is one shuffle between neighbours):
+// half the registers per thread, so twice the warps are resident to cover the latencies of the conversion phase
+// (ncu r02 of the one-thread-per-block version: 79 registers, 24 warps per SM, issue slots 41 % busy at 36 % of the DRAM rate).
+__global__ void __launch_bounds__(512) k_act_f16_dequant_pipe2(const __grid_constant__ ActGemmBatch b)
+{
+    extern __shared__ __align__(16) float act_smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (b.wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const ActGemmNode &nd = b.node[blockIdx.y];
+    const int wtype = b.wtype, perm = b.perm, N = nd.N, Npad = nd.Npad, K = nd.K;
+    const float *__restrict__ x = nd.x; const long long ldx_bytes = nd.ldx_bytes; __half *__restrict__ out = nd.out;
+    int *__restrict__ ex = nd.ex;
+    const int kb = K / GGB_QK, nhalf = kb * 2;
+    const int tid = threadIdx.x, nth = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
+    const bool scaled = wtype != GGML_TYPE_F16;
+    __shared__ float s_max[16];
+    float *const buf[2] = {act_smem, act_smem + K};
+    auto issue = [&](int row, float *dstrow) {
+        if (row < N) {
+            const char *src = reinterpret_cast<const char *>(x) + (long long)row * ldx_bytes;
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dstrow);
+            for (int c = tid; c < kb * 8; c += nth) {
+                const int col = c >> 3, i = c & 7;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + (uint32_t)(col * 128 + (((i + col) & 7) << 4))), "l"(src + (long long)c * 16) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // half h of block col: elements 16 h .. 16 h + 15 = chunks 4 h .. 4 h + 3
+    auto load_half = [&](const float *srow, int hidx, float *e) {
+        const int col = hidx >> 1, h = hidx & 1;
+        const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(srow + col * 32);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a0 + (uint32_t)(((4 * h + i + col) & 7) << 4)));
+            e[4 * i] = v.x; e[4 * i + 1] = v.y; e[4 * i + 2] = v.z; e[4 * i + 3] = v.w;
+        }
+    };
+    auto half_amax = [](const float *e) { float a = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) a = fmaxf(a, fabsf(e[i]));
+        return a; };
+    // convert and store one half block; bmax = the whole block's largest magnitude
+    auto emit_half = [&](float *e, float bmax, float rs, __half *dst_h) {
+        if (scaled) {
+            const float d = __fdiv_rn(bmax, 127.0f);
+            const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+            if (id < 3.0e38f) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) e[i] = __fmul_rn(__fmul_rn(d, (float)__float2int_rn(__fmul_rn(e[i], id))), rs);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) e[i] = __fmul_rn(__fmul_rn(d, (float)(int)(int8_t)rne_byte(__fmul_rn(e[i], id))), rs);
+            }
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int g = 0; g < 2; g++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float a = perm ? e[8 * g + t] : e[8 * g + 2 * t];
+                const float bb = perm ? e[8 * g + 4 + t] : e[8 * g + 2 * t + 1];
+                const __half2 hh = __floats2half2_rn(a, bb);
+                o[4 * g + t] = *reinterpret_cast<const uint32_t *>(&hh);
+            }
+        uint4 *dst = reinterpret_cast<uint4 *>(dst_h);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    };
+    int row = blockIdx.x, cur = 0;
+    issue(row, buf[0]);
+    for (; row < Npad; row += gridDim.x, cur ^= 1) {
+        __syncthreads();
+        issue(row + (int)gridDim.x, buf[cur ^ 1]);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const float *srow = buf[cur];
+        __half *orow = out + (long long)row * K;
+        float e[16];
+        const bool mine = tid < nhalf;
+        if (mine && row < N) load_half(srow, tid, e);
+        else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) e[i] = 0.0f;
+        }
+        float hm = half_amax(e);
+        float bmax = fmaxf(hm, __shfl_xor_sync(0xffffffffu, hm, 1));      // the neighbour owns the other half of the same block
+        float rs = 1.0f;
+        if (scaled) {
+            float am = bmax;
+            if (row < N)
+                for (int hi = tid + nth; hi < nhalf; hi += nth) { float t[16]; load_half(srow, hi, t); am = fmaxf(am, half_amax(t)); }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+            if (lane == 0) s_max[warp] = am;
+            __syncthreads();
+            am = s_max[0];
+            for (int w = 1; w < nwarps; w++) am = fmaxf(am, s_max[w]);
+            const int er = range_exp(am);
+            rs = exp2i(-er);
+            if (tid == 0 && ex) ex[row] = er;
+        }
+        if (mine) emit_half(e, bmax, rs, orow + (long long)tid * 16);
+        for (int base = nth; base < nhalf; base += nth) {             // rows longer than 16 * blockDim elements; the trip count is uniform (shuffle below)
+            const int hi = base + tid;
+            const bool in = hi < nhalf;
+            if (in && row < N) load_half(srow, hi, e);
+            hm = half_amax(e);
+            bmax = fmaxf(hm, __shfl_xor_sync(0xffffffffu, hm, 1));
+            if (in) emit_half(e, bmax, rs, orow + (long long)hi * 16);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!b.wait_prior) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 } // namespace
 
 size_t act_row_bytes(int wtype, int64_t K)
@@ -919,6 +1010,20 @@ int launch_act_f16_dequant_batch(ActGemmBatch &b, cudaStream_t s, bool pdl)
     for (int i = 0; i < b.n_nodes; i++) if (!b.node[i].vec16) pipe = false;
     const size_t smem = (size_t)2 * (size_t)max_kb * GGB_QK * 4;      // (a node with shorter rows uses the front of each half)
     static const bool no_pipe = getenv("GGB200_ACT_NO_PIPE") != nullptr;
+    static const bool two_per_block = getenv("GGB200_ACT_PIPE1") == nullptr;
+    if (pipe && !no_pipe && two_per_block && smem <= 200 * 1024) {
+        static PerDeviceOnce once2;
+        if (once2.need()) GGB_CUDA(cudaFuncSetAttribute(k_act_f16_dequant_pipe2, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const int threads2 = max_kb <= 16 ? 32 : max_kb <= 32 ? 64 : max_kb <= 64 ? 128 : max_kb <= 128 ? 256 : 512;      // two threads per block of 32 activations
+        const long long per_sm = std::max<long long>(1, std::min<long long>((long long)(220 * 1024) / (long long)(smem + 1024), 65536 / (40 * threads2)));
+        const long long cap = std::max<long long>(1, (long long)device_sm_count() * per_sm / b.n_nodes);
+        cfg.blockDim = dim3((unsigned)threads2);
+        cfg.gridDim = dim3((unsigned)std::min<long long>(max_rows, cap), (unsigned)b.n_nodes);
+        cfg.dynamicSmemBytes = smem;
+        GGB_CUDA(cudaLaunchKernelEx(&cfg, k_act_f16_dequant_pipe2, b));
+        count_launch();
+        return GGB_OK;
+    }
     if (pipe && !no_pipe && smem <= 200 * 1024) {
         static PerDeviceOnce once;
         if (once.need()) GGB_CUDA(cudaFuncSetAttribute(k_act_f16_dequant_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

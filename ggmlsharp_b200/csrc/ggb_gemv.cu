@@ -26,6 +26,7 @@
 // Roofline: HBM.  Algorithmic bytes per node = M*row_bytes (weights) + 4*K*N (x) + 4*M*N (y).
 #include "ggb_internal.h"
 #include "ggb_sib_math.cuh"
+#include "ggb_act_q8.cuh"
 
 #ifndef GGB_GEMV_PART
 #define GGB_GEMV_PART 0
@@ -451,7 +452,10 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_gemv_fast(const __grid_co
     __syncthreads();
 
     if (warp == NWF) {
-        // ===== producer warp: weights do not depend on the preceding kernel, so no PDL wait here =====
+        // ===== producer warp: weights normally do not depend on the preceding kernels, so no PDL wait here.  When they do (src0 is an
+        // earlier node's result: the writer may still be running, because the kernel between it and this one released its dependents
+        // before it waited itself), the copies are held back like the activation reads =====
+        if (b.wait_w) asm volatile("griddepcontrol.wait;" ::: "memory");
         const long long nb01 = b.nb01;
         int n = 0, st = 0; uint32_t ph = 0;
         for (int t = t_begin; t < t_end; t++) {
@@ -489,6 +493,21 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_gemv_fast(const __grid_co
             nt0 = b.node[n].g0; nt_end = nt0 + b.node[n].ngroups; nM = b.node[n].M; nldy = b.node[n].ldy; ny = b.node[n].y;
             if (XREG) {
                 const uint8_t *xq = b.node[n].xq;
+                if (b.fuse_x) {
+                    // xq is the F32 row: the consumer warps quantize it into shared memory exactly as k_act_batch would have staged
+                    // it (one definition, ggb_act_q8.cuh) -- 16 KB from L2 per CTA instead of a launch in front of every small level
+                    asm volatile("bar.sync 1, %0;" ::"n"(NWF * 32) : "memory");      // every lane has taken its registers from the previous row
+                    for (int base = 0; base < kb; base += NWF * 4) {                 // 8 lanes per block; uniform trip count (shuffles)
+                        const int col = base + (int)(threadIdx.x >> 3), sub = lane & 7;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col < kb) v = __ldcg(reinterpret_cast<const float4 *>(xq + (long long)col * 128 + sub * 16));
+                        uint32_t ev, od; float d; int sm;
+                        q8_block_sub8(v, sub, TYPE == GGML_TYPE_Q4_2, ev, od, d, sm);
+                        if (col < kb) q8_block_store(xs, kb, BPS, col, sub, ev, od, d, sm);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(NWF * 32) : "memory");
+                    xq = xs;
+                }
 #pragma unroll
                 for (int j = 0; j < 4; j++)
                     if (j < BPS) {
@@ -668,6 +687,13 @@ int gemv_act_bps(const GemvHdr &b)
     switch (b.type) { case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_2: case GGML_TYPE_Q5_0: case GGML_TYPE_Q8_0: return 4;
                       case GGML_TYPE_Q4_1: case GGML_TYPE_Q5_1: return 2; default: return 1; }
 }
+// the conditions of launch_fast_typed's `xreg` case: a quantized type, whole rows per stage, at most one unit per lane
+bool gemv_can_fuse_x(const GemvHdr &b)
+{
+    if (!b.async || !is_q_weight(b.type) || b.ncols != 1 || b.nchunk != 1) return false;
+    const int ub = unit_bytes_async(b.type);
+    return ub > 0 && b.row_bytes % ub == 0 && b.row_bytes / ub <= 32;
+}
 
 // Fills the shape-dependent fields of b (everything but the node list).  ncols in {1,2,4,8}.
 int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase)
@@ -729,6 +755,319 @@ int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const vo
     int depth = 1;
     if ((long long)NWARPS * b.stage_bytes > wbudget) return set_error(GGB_E_UNSUPPORTED, "mul_mat: shape needs more shared memory than one SM has");
     b.depth = depth;
+    return GGB_OK;
+}
+
+
+// ================================================================ the decode program (ggb_internal.h: DpProgram)
+namespace {
+
+constexpr int DP_NT = NWF * 32;                                   // consumer threads
+
+// consumers of all CTAs: everything written before is visible to everyone after (the cooperative-groups grid.sync pattern: CTA barrier,
+// one thread counts + spins, CTA barrier).  The counter only grows: barrier k completes at k * gridDim.x arrivals.
+__device__ __forceinline__ void dp_grid_barrier(unsigned *bar, unsigned target)
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(DP_NT) : "memory");
+    if (threadIdx.x == 0) {
+        // release: this CTA's writes (ordered before by the CTA barrier) are visible before the count; acquire: what the other CTAs
+        // released is visible to everyone behind the second CTA barrier.  No separate fences: each would cost another L2 round trip.
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        unsigned v;
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(DP_NT) : "memory");
+}
+
+__device__ __forceinline__ void dp_stamp(const DpProgram &P, int si, int k)
+{
+    if (P.trace && threadIdx.x == 0 && (blockIdx.x & 31) == 0 && (blockIdx.x >> 5) < 4 && si < 64) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.trace[(((blockIdx.x >> 5) * 64) + si) * 8 + k] = t;
+    }
+}
+
+// a mul_mat result, and -- when the next node of the graph is the SILU of it -- that node's result as well: the one lookup per row
+// disappears among the tiles, where the same SILU as a row op of the next step would have every CTA gather the whole row's entries
+__device__ __forceinline__ void dp_store_y(const DpProgram &P, const DpNode &nd, int row, float v)
+{
+    if (nd.y2 != nd.y) nd.y[row] = v;
+    if (nd.y2) nd.y2[row] = __half2float(__ushort_as_half(__ldg(P.silu_table + __half_as_ushort(__float2half_rn(v)))));
+}
+
+// one step's tiles of this CTA against the staged row in xs; the arithmetic of a row is k_gemv_fast's (dot_units, then warp_sum)
+template <int TYPE>
+__device__ __forceinline__ void dp_consume(const DpProgram &P, const DpStep &sp, const uint8_t *xs, const uint8_t *stages, uint32_t full0, uint32_t empty0,
+                                           int warp, int lane, int &st, uint32_t &ph)
+{
+    constexpr int UB = UnitTraits<TYPE>::BYTES;
+    const int rpw = sp.rs, TR = NWF * rpw, nchunk = sp.nchunk, row_bytes = sp.row_bytes, chunk_bytes = sp.chunk_bytes;
+    const int kb = sp.K / GGB_QK, S = row_bytes / UB, chunk_units = chunk_bytes / UB;
+    const int t_begin = (int)((long long)sp.total_tiles * blockIdx.x / gridDim.x);
+    const int t_end = (int)((long long)sp.total_tiles * (blockIdx.x + 1) / gridDim.x);
+    const XBlk xr[4] = {};
+    int n = sp.node0;
+    for (int t = t_begin; t < t_end; t++) {
+        while (t >= P.node[n].tile0 + P.node[n].ntiles) n++;
+        const DpNode &nd = P.node[n];
+        const int row_base = (t - nd.tile0) * TR + warp * rpw;
+        const int nrows = min(rpw, nd.M - row_base);
+        float acc[1];
+        for (int c = 0; c < nchunk; c++) {
+            mbar_wait(full0 + 8 * st, ph);
+            const uint8_t *stage = stages + (size_t)st * P.slot_bytes;
+            if (nchunk == 1) {
+                for (int r = 0; r < nrows; r++) {
+                    acc[0] = 0.0f;
+                    dot_units<TYPE, 1, false>(stage + (warp * rpw + r) * row_bytes, 0, S, S, kb, xs, 0, xr, lane, acc);
+                    const float v = warp_sum(acc[0]);
+                    if (lane == 0) dp_store_y(P, nd, row_base + r, v);
+                }
+            } else if (nrows > 0) {
+                if (c == 0) acc[0] = 0.0f;
+                const int cbytes = min(chunk_bytes, row_bytes - c * chunk_bytes);
+                dot_units<TYPE, 1, false>(stage + warp * cbytes, c * chunk_units, cbytes / UB, S, kb, xs, 0, xr, lane, acc);
+                if (c == nchunk - 1) {
+                    const float v = warp_sum(acc[0]);
+                    if (lane == 0) dp_store_y(P, nd, row_base, v);
+                }
+            }
+            asm volatile("" ::"f"(acc[0]) : "memory");           // the stage is released only after its bytes have been consumed (see k_gemv_fast)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * st);
+            if (++st == P.depth) { st = 0; ph ^= 1; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__((NWF + 1) * 32, 1) k_decode_program(const __grid_constant__ DpProgram P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    float *v = reinterpret_cast<float *>(smem);                  // the running row
+    uint8_t *xq = smem + P.v_bytes;                              // ... as the step's GEMVs read it: Q8 blocks / halves (F32 weights read v itself)
+    uint8_t *stages = xq + P.xs_bytes;
+    const uint32_t stage0 = smem_u32(stages);
+    const uint32_t full0 = smem_u32(stages + (size_t)P.depth * P.slot_bytes), empty0 = full0 + 8 * MAX_DEPTH;
+    __shared__ double part[8];
+
+    if (tid == 0) {
+        for (int s = 0; s < P.depth; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, NWF); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NWF) {
+        // ===== producer warp: the weight tiles of every step, in step order, as far ahead as the ring allows -- across the grid barriers,
+        // the consumers' prologues and their waits for other CTAs.  (The builder takes only weights nothing in this launch writes.) =====
+        int st = 0; uint32_t ph = 0;
+        for (int si = 0; si < P.n_steps; si++) {
+            const DpStep &sp = P.step[si];
+            if (!sp.nnodes) continue;
+            const int TR = NWF * sp.rs, nchunk = sp.nchunk, row_bytes = sp.row_bytes, chunk_bytes = sp.chunk_bytes;
+            const int t_begin = (int)((long long)sp.total_tiles * blockIdx.x / gridDim.x);
+            const int t_end = (int)((long long)sp.total_tiles * (blockIdx.x + 1) / gridDim.x);
+            int n = sp.node0;
+            for (int t = t_begin; t < t_end; t++) {
+                while (t >= P.node[n].tile0 + P.node[n].ntiles) n++;
+                const DpNode &nd = P.node[n];
+                const int row0 = (t - nd.tile0) * TR;
+                const int rows = min(TR, nd.M - row0);
+                const uint8_t *src = nd.W + (long long)row0 * nd.nb01;
+                for (int c = 0; c < nchunk; c++) {
+                    const int cb = nchunk == 1 ? row_bytes : min(chunk_bytes, row_bytes - c * chunk_bytes);
+                    mbar_wait(empty0 + 8 * st, ph ^ 1);
+                    if (lane == 0) mbar_expect_tx(full0 + 8 * st, (uint32_t)(rows * cb));
+                    __syncwarp();
+                    const uint32_t dst = stage0 + st * P.slot_bytes;
+                    for (int r = lane; r < rows; r += 32)
+                        bulk_g2s(dst + r * cb, src + (long long)r * nd.nb01 + (long long)c * chunk_bytes, (uint32_t)cb, full0 + 8 * st);
+                    if (++st == P.depth) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    int st = 0; uint32_t ph = 0; unsigned nbar = 0;
+    for (int si = 0; si < P.n_steps; si++) {
+        const DpStep &sp = P.step[si];
+        dp_stamp(P, si, 0);
+        // ---- the step's row ops.  float4 i of the running row belongs to thread i mod DP_NT in every op, so element-wise ops need
+        //      no barrier between them; operands other CTAs wrote (before the last grid barrier) are read past L1 (__ldcg) ----
+        for (int oi = sp.op0; oi < sp.op0 + sp.nops; oi++) {
+            const DpOp &op = P.op[oi];
+            const int n = op.n, n4 = n >> 2;                                              // (the builder takes rows of whole, aligned float4s only)
+            const int per = (n4 + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int lo = (int)blockIdx.x * per, hi = min(n4, lo + per);                 // this CTA's slice of the result tensor, in float4s
+            float4 *v4 = reinterpret_cast<float4 *>(v);
+            const float4 *a4 = reinterpret_cast<const float4 *>(op.a), *b4 = reinterpret_cast<const float4 *>(op.b);
+            float4 *d4 = reinterpret_cast<float4 *>(op.dst);
+            constexpr int UNR = 4;                                                        // loads in flight per thread and operand: a latency, not a loop of them
+            float scale = op.scalar;
+            if (op.op == DP_RMS_NORM) {
+                if (a4) {
+                    for (int base = tid; base < n4; base += DP_NT * UNR) {
+                        float4 x[UNR];
+#pragma unroll
+                        for (int u = 0; u < UNR; u++) if (base + u * DP_NT < n4) x[u] = __ldcg(a4 + base + u * DP_NT);
+#pragma unroll
+                        for (int u = 0; u < UNR; u++) if (base + u * DP_NT < n4) v4[base + u * DP_NT] = x[u];
+                    }
+                }
+                // k_rms_norm_f32's reduction, order included (256 threads stride the row, float products summed in double, shuffle tree,
+                // eight partials added in order), so that the two routes agree to the bit (Ggml.cs:5858-5921)
+                asm volatile("bar.sync 1, %0;" ::"n"(DP_NT) : "memory");               // the running row is complete
+                if (tid < 256) {
+                    double sum = 0.0;
+                    for (int i = tid; i < n; i += 256) { const float x = v[i]; sum += (double)__fmul_rn(x, x); }
+#pragma unroll
+                    for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                    if (lane == 0) part[warp] = sum;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(DP_NT) : "memory");
+                double t = 0.0;
+                for (int w = 0; w < 8; w++) t += part[w];
+                const float mean = (float)(t / (double)n);
+                scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, 1e-6f)));
+                a4 = nullptr;                                                             // the row is in v now
+            }
+            for (int base = tid; base < n4; base += DP_NT * UNR) {
+                float4 x[UNR], y[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const int i = base + u * DP_NT;
+                    if (i < n4) {
+                        x[u] = a4 ? __ldcg(a4 + i) : v4[i];
+                        if (op.op == DP_ADD || op.op == DP_MUL) y[u] = __ldcg(b4 + i);
+                    }
+                }
+                if (op.op == DP_SILU) {
+                    // (float)table_silu_f16[(Half)x] (Ggml.cs:2736-2746): all lookups of the batch in flight together
+                    unsigned short h[UNR][4];
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        if (base + u * DP_NT < n4) {
+                            h[u][0] = __ldg(P.silu_table + __half_as_ushort(__float2half_rn(x[u].x)));
+                            h[u][1] = __ldg(P.silu_table + __half_as_ushort(__float2half_rn(x[u].y)));
+                            h[u][2] = __ldg(P.silu_table + __half_as_ushort(__float2half_rn(x[u].z)));
+                            h[u][3] = __ldg(P.silu_table + __half_as_ushort(__float2half_rn(x[u].w)));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; u++)
+                        if (base + u * DP_NT < n4)
+                            x[u] = make_float4(__half2float(__ushort_as_half(h[u][0])), __half2float(__ushort_as_half(h[u][1])),
+                                               __half2float(__ushort_as_half(h[u][2])), __half2float(__ushort_as_half(h[u][3])));
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const int i = base + u * DP_NT;
+                    if (i < n4) {
+                        float4 r = x[u];
+                        if (op.op == DP_ADD) { r.x = __fadd_rn(r.x, y[u].x); r.y = __fadd_rn(r.y, y[u].y); r.z = __fadd_rn(r.z, y[u].z); r.w = __fadd_rn(r.w, y[u].w); }
+                        else if (op.op == DP_MUL) { r.x = __fmul_rn(r.x, y[u].x); r.y = __fmul_rn(r.y, y[u].y); r.z = __fmul_rn(r.z, y[u].z); r.w = __fmul_rn(r.w, y[u].w); }
+                        else if (op.op == DP_SCALE || op.op == DP_RMS_NORM) { r.x = __fmul_rn(r.x, scale); r.y = __fmul_rn(r.y, scale); r.z = __fmul_rn(r.z, scale); r.w = __fmul_rn(r.w, scale); }
+                        v4[i] = r;
+                        if (d4 && i >= lo && i < hi) d4[i] = r;
+                    }
+                }
+            }
+        }
+        dp_stamp(P, si, 1);
+        if (sp.nnodes) {
+            // ---- the row as this step's weight type multiplies it (k_act_batch's conversions; Q8 blocks through ggb_act_q8.cuh) ----
+            asm volatile("bar.sync 1, %0;" ::"n"(DP_NT) : "memory");
+            const int kb = sp.K / GGB_QK;
+            const uint8_t *xs = xq;
+            if (sp.type == GGML_TYPE_F32) xs = reinterpret_cast<const uint8_t *>(v);
+            else if (sp.type == GGML_TYPE_F16) {
+                for (int i = tid; i < sp.K; i += DP_NT) reinterpret_cast<__half *>(xq)[i] = __float2half_rn(v[i]);
+            } else {
+                const int bps = sp.type == GGML_TYPE_Q4_1 ? 2 : 4;
+                for (int base = 0; base < kb; base += DP_NT / 2) {                        // two lanes per block; uniform trip count (shuffles)
+                    const int col = base + (tid >> 1), h = tid & 1;
+                    float e[16];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float4 x4 = col < kb ? *reinterpret_cast<const float4 *>(v + col * GGB_QK + h * 16 + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        e[4 * i] = x4.x; e[4 * i + 1] = x4.y; e[4 * i + 2] = x4.z; e[4 * i + 3] = x4.w;
+                    }
+                    uint32_t ev[2], od[2]; float d; int sm;
+                    q8_block_half16(e, ev, od, d, sm);
+                    if (col < kb) q8_block_half16_store(xq, kb, bps, col, h, ev, od, d, sm);
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(DP_NT) : "memory");
+            dp_stamp(P, si, 2);
+            switch (sp.type) {
+            case GGML_TYPE_Q4_0: dp_consume<GGML_TYPE_Q4_0>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
+            case GGML_TYPE_Q4_1: dp_consume<GGML_TYPE_Q4_1>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
+            case GGML_TYPE_F16: dp_consume<GGML_TYPE_F16>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
+            default: dp_consume<GGML_TYPE_F32>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
+            }
+        }
+        dp_stamp(P, si, 3);
+        if (si + 1 < P.n_steps) dp_grid_barrier(P.bar, ++nbar * gridDim.x);
+        dp_stamp(P, si, 4);
+    }
+}
+
+} // namespace
+
+int64_t decode_program_row_max() { return 12288; }
+int decode_program_tile_rows(const DpStep &st) { return NWF * st.rs; }
+
+bool decode_program_plan_step(DpStep &st, int type, int64_t K, int64_t nb01, const void *W)
+{
+    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1 && type != GGML_TYPE_F16 && type != GGML_TYPE_F32) return false;
+    if (K <= 0 || K > decode_program_row_max() || K % 4) return false;
+    GemvHdr h = {};
+    if (gemv_plan(h, type, K, nb01, 1, W) || !h.async) return false;          // (a refusal leaves its text in the error buffer; the caller falls back and nobody reads it)
+    st.type = type; st.K = (int)K; st.row_bytes = h.row_bytes; st.rs = h.rs; st.nchunk = h.nchunk; st.chunk_bytes = h.chunk_bytes; st.stage_bytes = h.stage_bytes;
+    return true;
+}
+
+bool decode_program_finish(DpProgram &p)
+{
+    int64_t vmax = 0, xmax = 0, slot = 0;
+    for (int i = 0; i < p.n_steps; i++) {
+        const DpStep &st = p.step[i];
+        for (int o = st.op0; o < st.op0 + st.nops; o++) vmax = std::max<int64_t>(vmax, p.op[o].n);
+        if (!st.nnodes) continue;
+        vmax = std::max<int64_t>(vmax, st.K);
+        if (st.type != GGML_TYPE_F32) xmax = std::max<int64_t>(xmax, (int64_t)act_row_bytes(st.type, st.K));
+        slot = std::max<int64_t>(slot, st.stage_bytes);
+    }
+    if (vmax > decode_program_row_max()) return false;
+    p.v_bytes = (int)align_up((size_t)vmax * 4, 128);
+    p.xs_bytes = (int)align_up((size_t)xmax, 128);
+    p.slot_bytes = (int)align_up((size_t)std::max<int64_t>(slot, 128), 128);
+    const int64_t room = 227 * 1024 - 1024 - p.v_bytes - p.xs_bytes - 2 * MAX_DEPTH * 8;
+    p.depth = (int)std::min<int64_t>(MAX_DEPTH, room / p.slot_bytes);
+    return p.depth >= 2;
+}
+
+int launch_decode_program(const DpProgram &p, cudaStream_t s)
+{
+    static PerDeviceOnce once;
+    if (once.need()) GGB_CUDA(cudaFuncSetAttribute(k_decode_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512));
+    const size_t smem = (size_t)p.v_bytes + p.xs_bytes + (size_t)p.depth * p.slot_bytes + 2 * MAX_DEPTH * 8;
+    GGB_CUDA(cudaMemsetAsync(p.bar, 0, sizeof(unsigned), s));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)device_sm_count());             // one CTA per SM, all resident at once: the grid barrier needs it
+    cfg.blockDim = dim3((NWF + 1) * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GGB_CUDA(cudaLaunchKernelEx(&cfg, k_decode_program, p));
+    count_launch();
     return GGB_OK;
 }
 

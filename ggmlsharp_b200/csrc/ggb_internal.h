@@ -109,15 +109,48 @@ struct GemvHdr {
     int async;                 // 1: cp.async.bulk staging (16-byte aligned rows), 0: plain-load staging
     int n_peers;
     long long peer_delta[7];   // byte offset from a node's y to the same element of peer p's copy
+    int fuse_x;                // 1: node.xq is the F32 activation row itself; every CTA quantizes it in its prologue (gemv_can_fuse_x)
+    int wait_w;                // 1: some node's weights are written by work enqueued earlier on this stream (GGB_MM_W_IN_FLIGHT): the weight copies wait too
 };
 template <int CAP> struct GemvBatchT : GemvHdr { GemvNode node[CAP]; };
 using GemvBatch = GemvBatchT<GGB_MAX_BATCH_NODES>;
 int launch_gemv_batch(const GemvBatch &b, cudaStream_t s, bool pdl);
 int gemv_plan(GemvHdr &b, int type, int64_t K, int64_t nb01, int ncols, const void *Wbase_probe);
 int gemv_act_bps(const GemvHdr &b);
+bool gemv_can_fuse_x(const GemvHdr &b);   // the planned kernel can quantize a single F32 activation row itself (no staging launch)
 int gemv_group_rows(const GemvHdr &b);  // weight rows per work group (tile) of the planned kernel   // the ActBatch::bps the planned kernel expects
 int gemv_num_ctas();
 int64_t gemv_x_budget();             // bytes of staged activation columns one GEMV pass may keep in shared memory
+
+// ---- decode program (ggb_gemv.cu: k_decode_program) ----
+// A dependent chain of single-token nodes (one decode step of a Llama layer stack: 10 dependency levels per layer) as ONE persistent
+// launch: one CTA per SM walks a list of STEPS.  A step is a short run of element-wise / row ops on a "running row" every CTA keeps
+// in shared memory (evaluated redundantly by all CTAs; each stores its slice of every result tensor), then the single-token MUL_MATs
+// that multiply that row (the GEMV tiles of the step dealt to the CTAs as in k_gemv_fast), then a grid-wide barrier.  The weight
+// copies do not depend on the activations, so the producer warp of a CTA keeps streaming the NEXT steps' weights into the
+// shared-memory ring while its consumer warps sit in the barrier: HBM stays busy across the dependency levels, which as separate
+// launches cost 2-12 us each against 1.6-8 us of weight streaming (profiles/r02_chain_launches.csv).
+enum { DP_LOAD = 0, DP_ADD, DP_MUL, DP_SILU, DP_RMS_NORM, DP_SCALE };
+struct DpNode { const uint8_t *W; float *y; float *y2; long long nb01; int M, tile0, ntiles, pad_; };     // y2: SILU of the result (may be y itself: in place), or null
+struct DpOp { const float *a, *b; float *dst; float scalar; int op, n, pad_; };      // a == null: the running row; b: second operand (global) or null
+struct DpStep { int op0, nops, node0, nnodes, total_tiles, type, K, row_bytes, rs, nchunk, chunk_bytes, stage_bytes; };
+constexpr int DP_MAX_STEPS = 144, DP_MAX_NODES = 240, DP_MAX_OPS = 280;      // 29.7 KB of kernel parameters (the limit is 32 764 B)
+struct DpProgram {
+    unsigned *bar;                       // grid barrier counter, zero at launch
+    const unsigned short *silu_table;    // table_silu_f16 (ggb_ops.cu)
+    int n_steps, depth, slot_bytes, v_bytes, xs_bytes, pad_;
+    long long *trace;                    // debugging (GGB200_PROGRAM_TRACE): globaltimer stamps [4 CTAs][64 steps][8 points], else null
+    DpStep step[DP_MAX_STEPS];
+    DpNode node[DP_MAX_NODES];
+    DpOp op[DP_MAX_OPS];
+};
+int64_t decode_program_row_max();                                   // longest running row (elements)
+// fills step.{type, K, row_bytes, rs, nchunk, chunk_bytes, stage_bytes} for single-token nodes of this shape; false: not a shape the program takes
+bool decode_program_plan_step(DpStep &st, int type, int64_t K, int64_t nb01, const void *W);
+int decode_program_tile_rows(const DpStep &st);                     // weight rows per tile of a planned step
+bool decode_program_finish(DpProgram &p);                           // sizes the shared-memory regions; false: does not fit
+int launch_decode_program(const DpProgram &p, cudaStream_t s);
+int silu_table_device(const unsigned short **table);               // builds / returns the device copy of table_silu_f16
 
 // ---- GEMM (ggb_gemm.cu): tcgen05 batched path ----
 struct GemmArgs {

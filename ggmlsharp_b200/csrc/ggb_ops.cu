@@ -20,10 +20,22 @@ namespace ggb {
 
 namespace {
 
+// Every kernel here is a programmatic dependent of whatever precedes it in the stream, and lets its own successor be scheduled while
+// it runs: first wait until the predecessor is COMPLETE (so is, transitively, everything before that), then release.  The successor's
+// CTAs become resident and sit in their own griddepcontrol.wait until this grid is complete and flushed -- its launch latency, about
+// as long as one of these kernels on a single-token row, is hidden.  Released only AFTER the wait: a successor that reads something
+// without waiting (the weight copies of a GEMV / GEMM, unless GGB_MM_W_IN_FLIGHT tells them to) can then only run beside THIS
+// kernel, never beside an older one.
+__device__ __forceinline__ void pdl_wait_then_release()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // (no __restrict__: the in-place ADD / MUL of ggml_add_inplace and friends passes z == a, and silu / scale run in place too)
 __global__ void __launch_bounds__(256) k_binary_f32(int op, const float *a, const float *b, float *z, long long n)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait_then_release();
     const long long n4 = n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 x = reinterpret_cast<const float4 *>(a)[i], y = reinterpret_cast<const float4 *>(b)[i];
@@ -40,20 +52,20 @@ __global__ void __launch_bounds__(256) k_binary_f32(int op, const float *a, cons
 
 __global__ void __launch_bounds__(256) k_binary_f32_scalar(int op, const float *a, const float *b, float *z, long long n)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait_then_release();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         z[i] = op == GGML_OP_ADD ? __fadd_rn(a[i], b[i]) : __fmul_rn(a[i], b[i]);
 }
 
 __global__ void __launch_bounds__(256) k_scale_f32(float *__restrict__ y, float v, long long n)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait_then_release();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = __fmul_rn(y[i], v);
 }
 
 __global__ void __launch_bounds__(256) k_silu_f32(const float *x, float *y, long long n, const unsigned short *__restrict__ table)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait_then_release();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const unsigned short h = __half_as_ushort(__float2half_rn(x[i]));          // (Half)x, round to nearest even
         y[i] = __half2float(__ushort_as_half(__ldg(table + h)));                     // (float)table_silu_f16[t]
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(256) k_silu_f32(const float *x, float *y, long
 // one CTA per row
 __global__ void __launch_bounds__(256) k_rms_norm_f32(const float *x, long long x_stride, float *y, long long y_stride, int ne00)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait_then_release();
     const float *xr = x + (long long)blockIdx.x * x_stride;
     float *yr = y + (long long)blockIdx.x * y_stride;
     double sum = 0.0;
@@ -90,7 +102,7 @@ __global__ void __launch_bounds__(256) k_rms_norm_f32(const float *x, long long 
 struct DupArgs { long long ne[4]; long long nb[4]; };
 __global__ void __launch_bounds__(256) k_dup_f32_transposed(const uint8_t *__restrict__ src, float *__restrict__ dst, const __grid_constant__ DupArgs a)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait_then_release();
     __shared__ float tile[32][33];
     const long long plane = blockIdx.z;
     const long long i3 = plane / a.ne[2], i2 = plane - i3 * a.ne[2];
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(256) k_dup_f32_transposed(const uint8_t *__res
 }
 __global__ void __launch_bounds__(256) k_dup_f32_generic(const uint8_t *__restrict__ src, float *__restrict__ dst, const __grid_constant__ DupArgs a, long long n)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait_then_release();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         long long r = i;
         const long long i0 = r % a.ne[0]; r /= a.ne[0];
@@ -126,7 +138,7 @@ __global__ void __launch_bounds__(256) k_dup_f32_generic(const uint8_t *__restri
 __global__ void __launch_bounds__(256) k_repeat_f32(const float *__restrict__ src, long long src_stride, int nc0, int nr0,
                                                     float *__restrict__ dst, long long dst_stride, int nc, long long n)
 {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait_then_release();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / nc; const int c = (int)(i - r * nc);
         dst[r * dst_stride + c] = src[(r % nr0) * src_stride + (c % nc0)];
@@ -191,6 +203,14 @@ int launch_scale_f32(float *y, float v, int64_t n, cudaStream_t s)
 {
     if (n <= 0) return GGB_OK;
     return launch_pdl(k_scale_f32, dim3(stream_grid(n, 256)), dim3(256), s, y, v, (long long)n);
+}
+
+int silu_table_device(const unsigned short **table)
+{
+    std::call_once(g_silu_once, build_silu_table);
+    if (!g_silu_table) return g_silu_rc ? g_silu_rc : set_error(GGB_E_CUDA, "silu table unavailable");
+    *table = g_silu_table;
+    return GGB_OK;
 }
 
 int launch_silu_f32(const float *x, float *y, int64_t n, cudaStream_t s)

@@ -29,6 +29,7 @@ static int g_device = 0, g_sms = 148;
 static cudaStream_t g_stream = nullptr;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static ggb_stats g_stats = {};
+static bool g_decode_program = getenv("GGB200_NO_DECODE_PROGRAM") == nullptr;      // ggb_set_decode_program
 static int g_timing = 0;            // 0 off, 1 bracket every mul_mat kernel, 2 also skip the activation staging (reuse the previous call's)
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timed;   // pending event pairs, resolved in ggb_get_stats
 
@@ -61,6 +62,8 @@ struct DevCtx {
     // a fixed table, so that growing it never moves what a peer is reading
     cudaEvent_t level_ev[GGML_MAX_NODES + 1] = {};
     std::vector<cudaEvent_t> level_time;      // timing events, one after each dependency level of an eager compute (per-node perf_time_us)
+    unsigned *dp_bar = nullptr;               // grid-barrier counter of the decode program (run_nodes)
+    bool dp_silu_ready = false;
 };
 
 static std::vector<DevCtx> g_devs;            // [0] = the library's own device (g_device / g_stream / g_ev0 / g_ev1); [1..] opened by ensure_multi
@@ -473,6 +476,16 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
         const int type = mm[i0].type; const int64_t K = mm[i0].K;
         const size_t arow = act_row_bytes(type, K);
         const bool quant = is_q_weight(type);
+        // Small decode levels (a dependent chain runs one to three single-token nodes per level): the GEMV quantizes the activation
+        // row in its own prologue and the staging launch in front of it -- half of such a level's launches -- goes away.  Larger
+        // batches keep the staged copy: there one staging launch serves many nodes and every CTA would repeat the row's conversion.
+        static const int fuse_max = [] { const char *e = getenv("GGB200_GEMV_FUSE_MAX"); return e ? atoi(e) : 8; }();
+        bool fuse_x = quant && tl_phase == 0 && g_timing != 2 && (int)grp.size() <= fuse_max;
+        for (size_t c = 0; c < grp.size() && fuse_x; c++) {
+            const ggb_dev_mm &m = mm[grp[c]];
+            GemvHdr probe = {};
+            if (m.N != 1 || (reinterpret_cast<uintptr_t>(m.X) & 15) || gemv_plan(probe, type, K, m.nb01, 1, m.W) || !gemv_can_fuse_x(probe)) fuse_x = false;
+        }
         // activation staging (INIT phase)
         for (size_t c0 = 0; c0 < grp.size(); c0 += GGB_MAX_BATCH_NODES) {
             static thread_local ActBatch ab;
@@ -494,7 +507,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
                 if ((reinterpret_cast<uintptr_t>(m.X) & 15) || (m.ldx_bytes & 15)) ab.vec16 = 0;
             }
             ab.total_blk = tot;
-            if (g_timing == 2 || tl_phase == 2 || !ab.n_nodes) continue;         // the workspace already holds these activations
+            if (g_timing == 2 || tl_phase == 2 || !ab.n_nodes || fuse_x) continue;         // the workspace already holds these activations / the GEMV stages them itself
             int rc = launch_act_batch(ab, s, true);
             if (rc) return rc;
         }
@@ -523,6 +536,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
             int rc = gemv_plan(gb, type, K, m0.nb01, passes[p0].nc, m0.W);
             if (rc) return rc;
             gb.n_peers = m0.n_peers;
+            gb.fuse_x = fuse_x ? 1 : 0;
             for (int p = 0; p < m0.n_peers; p++) gb.peer_delta[p] = (long long)(reinterpret_cast<char *>(m0.Y_peer[p]) - reinterpret_cast<char *>(m0.Y));
             auto compatible = [&](const Pass &ps) {
                 const ggb_dev_mm &m = mm[ps.i];
@@ -544,9 +558,10 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
                 if (pdone[p1] || !compatible(passes[p1])) continue;
                 pdone[p1] = 1;
                 const ggb_dev_mm &m = mm[passes[p1].i];
+                if (m.flags & GGB_MM_W_IN_FLIGHT) gb.wait_w = 1;
                 GemvNode &nd = gb.node[gb.n_nodes++];
                 nd.W = static_cast<const uint8_t *>(m.W);
-                nd.xq = act_base[passes[p1].i] + (size_t)passes[p1].col0 * arow;
+                nd.xq = fuse_x ? reinterpret_cast<const uint8_t *>(m.X) : act_base[passes[p1].i] + (size_t)passes[p1].col0 * arow;
                 nd.y = m.Y + (size_t)passes[p1].col0 * (m.ldy_bytes / 4);
                 nd.M = (int)m.M; nd.ldy = (int)(m.ldy_bytes / 4);
                 const int64_t rows_per_group = gemv_group_rows(gb);
@@ -1181,7 +1196,270 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         return true;
     };
 
-    for (int lv = 0; lv <= max_level; lv++) {
+
+    // ---- a dependent chain of single-token nodes runs as ONE persistent launch: the decode program (ggb_internal.h: DpProgram,
+    //      ggb_gemv.cu: k_decode_program).  Built from the node list in node order -- the order the reference executes
+    //      (Ggml.cs:3539-3704).  All or nothing: a node the program does not take, a dependency level whose mul_mats multiply
+    //      different rows (those are one wide batch on the level path), or a graph with a single mul_mat level leaves everything to
+    //      the per-level launches below. ----
+    bool ran_program = false;
+    if (!sc && lead && !g_timing && g_decode_program && n >= 2) {
+        std::vector<DpProgram> progs;
+        bool need_silu = false;
+        static const bool trace = getenv("GGB200_TRACE_PROGRAM") != nullptr;      // says on stderr why a graph was left to the per-level launches
+        size_t at = 0;
+        auto bail = [&](const char *why) { if (trace) fprintf(stderr, "ggb200: decode program not used: %s (node %zu of %zu, op %d)\n", why, at, n, at < n ? (int)items[at].t->op : -1); return false; };
+        auto build = [&]() -> bool {
+            const int64_t vmax = decode_program_row_max();
+            // every node must be one the program takes; mul_mats of one level must share their activations
+            std::vector<const uint8_t *> level_x((size_t)max_level + 1, nullptr);
+            int mm_levels = 0;
+            for (size_t i = 0; i < n; i++) {
+                const Item &it = items[i];
+                const ggml_tensor *t = it.t, *a = t->src0, *b = t->src1;
+                at = i;
+                switch (t->op) {
+                case GGML_OP_MUL_MAT: {
+                    if (b->ne[1] != 1 || a->ne[2] * a->ne[3] != 1 || b->ne[2] * b->ne[3] != 1 || it.a_in_flight || it.rows != a->ne[1] || it.rows <= 0) return bail("a mul_mat that is batched, prompt-sized, or whose src0 is an earlier node's result");
+                    if (b->type != GGML_TYPE_F32) return bail("src1 is not F32");
+                    DpStep probe = {};
+                    if (!decode_program_plan_step(probe, a->type, a->ne[0], (int64_t)a->nb[1], it.da)) return bail("src0 type / row length / alignment");
+                    if (!level_x[(size_t)it.level]) { level_x[(size_t)it.level] = it.db; mm_levels++; }
+                    else if (level_x[(size_t)it.level] != it.db) return bail("mul_mats of one dependency level multiply different rows");
+                    break;
+                }
+                case GGML_OP_ADD: case GGML_OP_MUL:
+                    if (a->type != GGML_TYPE_F32 || b->type != GGML_TYPE_F32 || nelements(a) != nelements(t) || nelements(b) != nelements(t)) return bail("a binary op that broadcasts or is not F32");
+                    // fallthrough
+                case GGML_OP_SILU: case GGML_OP_RMS_NORM: case GGML_OP_SCALE:
+                    if (a->type != GGML_TYPE_F32 || t->ne[1] * t->ne[2] * t->ne[3] != 1 || t->ne[0] > vmax || nelements(a) != nelements(t)) return bail("a row op on more than one row (or a very long one)");
+                    if (t->ne[0] & 3) return bail("a row that is not whole float4s");
+                    break;
+                default:
+                    return bail("an op the program does not take");
+                }
+            }
+            at = n;
+            if (mm_levels < 2) return bail("fewer than two dependent mul_mat levels");
+            // small leaves are normally read in place from the pinned host arena (stage() above); here every CTA would read all of
+            // them over PCIe, so they get a device copy first
+            {
+                std::vector<std::pair<const uint8_t *, uint8_t *>> moved;
+                auto on_device = [&](const ggml_tensor *x, uint8_t *&p) -> bool {
+                    if (!x || p != static_cast<const uint8_t *>(x->data)) return true;
+                    for (const auto &m : moved) if (m.first == p) { p = m.second; return true; }
+                    const size_t bytes = tensor_span(x);
+                    if (arena.used + align_up(std::max<size_t>(bytes, 1), 256) > arena.cap) return false;
+                    uint8_t *d = static_cast<uint8_t *>(arena.take(std::max<size_t>(bytes, 1)));
+                    if (cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) { cudaGetLastError(); return false; }
+                    moved.push_back({p, d});
+                    p = d;
+                    return true;
+                };
+                for (size_t i = 0; i < n; i++) {
+                    Item &it = items[i];
+                    const ggml_tensor *t = it.t;
+                    if (t->op != GGML_OP_MUL_MAT && !on_device(t->src0, it.da)) return bail("no scratch left for a leaf operand");
+                    if (t->op != GGML_OP_SCALE && !on_device(t->src1, it.db)) return bail("no scratch left for a leaf operand");
+                }
+            }
+            for (size_t i = 0; i < n; i++) {
+                const Item &it = items[i];
+                at = i;
+                const bool mm = it.t->op == GGML_OP_MUL_MAT, binary = it.t->op == GGML_OP_ADD || it.t->op == GGML_OP_MUL;
+                if ((reinterpret_cast<uintptr_t>(it.dd) | (mm ? 0 : reinterpret_cast<uintptr_t>(it.da)) | (mm || binary ? reinterpret_cast<uintptr_t>(it.db) : 0)) & 15)
+                    return bail("a row that is not 16-byte aligned on the device");
+            }
+            struct Range { const uint8_t *p; size_t n; };
+            std::vector<Range> step_reads, step_writes;
+            std::vector<int> wstep(n, -1);                         // the (global) step a node's result is written in
+            int gstep = 0;
+            DpProgram cur = {};
+            const uint8_t *run_ptr = nullptr; int64_t run_n = 0;   // the tensor the running row holds
+            int n_nodes = 0, n_ops = 0;
+            auto open_step = [&]() { DpStep &st = cur.step[cur.n_steps]; st = DpStep{}; st.op0 = n_ops; st.node0 = n_nodes; };
+            auto finish_program = [&]() -> bool {
+                if (cur.n_steps == 0) return true;
+                if (!decode_program_finish(cur)) return false;
+                progs.push_back(cur);
+                cur = DpProgram{}; n_nodes = 0; n_ops = 0; run_ptr = nullptr; run_n = 0;
+                open_step();
+                return true;
+            };
+            auto close_step = [&]() -> bool {                      // ends the open step with a grid barrier (an empty step is not closed)
+                DpStep &st = cur.step[cur.n_steps];
+                if (st.nops == 0 && st.nnodes == 0) return true;
+                cur.n_steps++; gstep++;
+                step_reads.clear(); step_writes.clear();
+                if (cur.n_steps == DP_MAX_STEPS) return finish_program();
+                open_step();
+                return true;
+            };
+            auto room = [&](int ops, int nodes) -> bool {          // the open step keeps its ops and nodes in one program
+                if (n_ops + ops <= DP_MAX_OPS && n_nodes + nodes <= DP_MAX_NODES) return true;
+                if (!close_step() || !finish_program()) return false;
+                return ops <= DP_MAX_OPS && nodes <= DP_MAX_NODES;
+            };
+            // is the operand at device address p complete and visible to every CTA in the open step?  (Results of the open step are
+            // spread over the CTAs' slices until its barrier.)
+            auto available = [&](size_t j, const uint8_t *p) {
+                for (size_t k = j; k-- > 0;) {
+                    const size_t span = tensor_span(out_tensor(items[k].t));
+                    if (p >= items[k].dd && p < items[k].dd + span) return wstep[k] < gstep;
+                }
+                return true;                                       // a leaf: uploaded or read in place
+            };
+            auto overlaps = [&](const std::vector<Range> &v, const uint8_t *p, size_t bytes, bool allow_same) {
+                for (const Range &r : v) if (ranges_overlap(p, bytes, r.p, r.n) && !(allow_same && r.p == p && r.n == bytes)) return true;
+                return false;
+            };
+            auto push_op = [&](int op, const uint8_t *a_ptr, const uint8_t *b_ptr, uint8_t *dst, int64_t len, float scalar) {
+                DpOp &o = cur.op[n_ops++];
+                o = DpOp{};
+                o.op = op; o.a = reinterpret_cast<const float *>(a_ptr); o.b = reinterpret_cast<const float *>(b_ptr);
+                o.dst = reinterpret_cast<float *>(dst); o.n = (int)len; o.scalar = scalar;
+                cur.step[cur.n_steps].nops++;
+                if (a_ptr) step_reads.push_back({a_ptr, (size_t)len * 4});
+                if (b_ptr) step_reads.push_back({b_ptr, (size_t)len * 4});
+                if (dst) step_writes.push_back({dst, (size_t)len * 4});
+            };
+            open_step();
+            // level by level (a valid execution order: a node's operands sit on lower levels), so that the mul_mats of one level
+            // -- wq / wk / wv -- meet in one step even when the graph lists an ADD between them
+            std::vector<size_t> order(n);
+            for (size_t i = 0; i < n; i++) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return items[x].level < items[y].level; });
+            for (size_t oi = 0; oi < n; oi++) {
+                const size_t i = order[oi];
+                const Item &it = items[i];
+                const ggml_tensor *t = it.t, *a = t->src0, *b = t->src1;
+                at = i;
+                if (t->op == GGML_OP_MUL_MAT) {
+                    const int64_t K = a->ne[0];
+                    DpStep plan = {};
+                    decode_program_plan_step(plan, a->type, K, (int64_t)a->nb[1], it.da);
+                    DpStep *st = &cur.step[cur.n_steps];
+                    const bool joins = st->nnodes > 0 && st->type == plan.type && st->K == plan.K && run_ptr == it.db && run_n == K;
+                    if (st->nnodes > 0 && !joins) { if (!close_step()) return bail("program does not fit shared memory"); }
+                    if (!joins) {
+                        if (!(run_ptr == it.db && run_n == K) && !available(i, it.db)) { if (!close_step()) return bail("program does not fit shared memory"); }
+                        if (!room(1, 1)) return bail("program does not fit shared memory");                                   // (may start a new program, which drops the running row)
+                        if (!(run_ptr == it.db && run_n == K)) {
+                            push_op(DP_LOAD, it.db, nullptr, nullptr, K, 0.0f);
+                            run_ptr = it.db; run_n = K;
+                        }
+                        st = &cur.step[cur.n_steps];
+                        const int op0 = st->op0, nops = st->nops, node0 = st->node0;
+                        *st = plan; st->op0 = op0; st->nops = nops; st->node0 = node0;
+                    } else if (n_nodes + 1 > DP_MAX_NODES) return bail("a level of too many mul_mats");      // (a step of more than DP_MAX_NODES mul_mats: not a decode chain)
+                    const size_t ybytes = (size_t)a->ne[1] * 4;
+                    if (overlaps(step_reads, it.dd, ybytes, false) || overlaps(step_writes, it.dd, ybytes, false)) return bail("a mul_mat result aliases something its step touches");
+                    DpNode &nd = cur.node[n_nodes++];
+                    nd = DpNode{};
+                    nd.W = it.da; nd.y = reinterpret_cast<float *>(it.dd); nd.nb01 = (long long)a->nb[1]; nd.M = (int)a->ne[1];
+                    const int tr = decode_program_tile_rows(*st);
+                    nd.tile0 = st->total_tiles; nd.ntiles = (int)((a->ne[1] + tr - 1) / tr);
+                    st->total_tiles += nd.ntiles; st->nnodes++;
+                    step_writes.push_back({it.dd, ybytes});
+                    wstep[i] = gstep;
+                    continue;
+                }
+                const int64_t len = nelements(t);
+                if (t->op == GGML_OP_SILU && cur.step[cur.n_steps].nnodes > 0) {
+                    // the SILU of a mul_mat result of the open step: stored by the lane that stores the result (DpNode::y2)
+                    DpStep &st = cur.step[cur.n_steps];
+                    DpNode *hit = nullptr;
+                    for (int k = st.node0; k < st.node0 + st.nnodes; k++) if (reinterpret_cast<const uint8_t *>(cur.node[k].y) == it.da && cur.node[k].M == len && !cur.node[k].y2) hit = &cur.node[k];
+                    const size_t bytes = (size_t)len * 4;
+                    if (hit && (it.dd == it.da || (!overlaps(step_reads, it.dd, bytes, false) && !overlaps(step_writes, it.dd, bytes, false)))) {
+                        hit->y2 = reinterpret_cast<float *>(it.dd);
+                        if (it.dd != it.da) step_writes.push_back({it.dd, bytes});
+                        need_silu = true;
+                        wstep[i] = gstep;
+                        continue;
+                    }
+                }
+                // a row op.  The open step's mul_mats (if any) come after its ops: a new op starts the next step.
+                if (cur.step[cur.n_steps].nnodes > 0) { if (!close_step()) return bail("program does not fit shared memory"); }
+                const bool binary = t->op == GGML_OP_ADD || t->op == GGML_OP_MUL;
+                const uint8_t *pa = it.da, *pb = binary ? it.db : nullptr;
+                bool a_run = run_ptr == pa && run_n == len, b_run = binary && !a_run && run_ptr == pb && run_n == len;
+                if ((!a_run && !available(i, pa)) || (binary && !b_run && !available(i, pb))) { if (!close_step()) return bail("program does not fit shared memory"); }
+                const size_t bytes = (size_t)len * 4;
+                if (it.dd == it.da && !a_run) {
+                    // in place on a tensor the row does not hold: every CTA reads all of it, then each overwrites its slice -- load it in
+                    // one step, overwrite it in the next
+                    if (!room(1, 0)) return bail("program does not fit shared memory");
+                    push_op(DP_LOAD, pa, nullptr, nullptr, len, 0.0f);
+                    run_ptr = pa; run_n = len; a_run = true; b_run = false;
+                }
+                if (binary && pb && ranges_overlap(it.dd, bytes, pb, bytes)) return bail("a binary op writing over its second operand");
+                // a slice store must not hit bytes other CTAs still read (or write differently) in this step
+                if (overlaps(step_reads, it.dd, bytes, false) || overlaps(step_writes, it.dd, bytes, true)) { if (!close_step()) return bail("program does not fit shared memory"); }
+                if (!room(1, 0)) return bail("program does not fit shared memory");
+                if (!(run_ptr == pa && run_n == len)) a_run = false;       // (a program split drops the running row)
+                if (!(binary && run_ptr == pb && run_n == len)) b_run = false;
+                if (it.dd == it.da && !a_run) return bail("an in-place op across a program split");
+                int op = DP_LOAD; float scalar = 0.0f;
+                switch (t->op) {
+                case GGML_OP_ADD: op = DP_ADD; break;
+                case GGML_OP_MUL: op = DP_MUL; break;
+                case GGML_OP_SILU: op = DP_SILU; break;
+                case GGML_OP_RMS_NORM: op = DP_RMS_NORM; break;
+                default: op = DP_SCALE; scalar = *static_cast<const float *>(b->data); break;       // float v = *(float*)src1->data (Ggml.cs:6763)
+                }
+                if (binary) push_op(op, a_run || b_run ? nullptr : pa, a_run ? pb : b_run ? pa : pb, it.dd, len, 0.0f);   // x + y == y + x, x * y == y * x to the bit
+                else push_op(op, a_run ? nullptr : pa, nullptr, it.dd, len, scalar);
+                run_ptr = it.dd; run_n = len;
+                wstep[i] = gstep;
+            }
+            {
+                DpStep &st = cur.step[cur.n_steps];
+                if (st.nops || st.nnodes) cur.n_steps++;
+            }
+            if (cur.n_steps) { if (!decode_program_finish(cur)) return bail("program does not fit shared memory"); progs.push_back(cur); }
+            return !progs.empty();
+        };
+        if (build()) {
+            DevCtx &dc = dctx;
+            if (!dc.dp_bar) {
+                if (cap) return GGB_E_NOCAPTURE;
+                GGB_CUDA(cudaMalloc(reinterpret_cast<void **>(&dc.dp_bar), 256));
+            }
+            const unsigned short *silu = nullptr;
+            for (const DpProgram &pg : progs) for (int sti = 0; sti < pg.n_steps; sti++) for (int o = pg.step[sti].op0; o < pg.step[sti].op0 + pg.step[sti].nops; o++) if (pg.op[o].op == DP_SILU) need_silu = true;
+            if (need_silu) {
+                if (cap && !dc.dp_silu_ready) return GGB_E_NOCAPTURE;
+                rc = silu_table_device(&silu);
+                if (rc) return rc;
+                dc.dp_silu_ready = true;
+            }
+            static const bool dp_trace = getenv("GGB200_PROGRAM_TRACE") != nullptr;
+            long long *tbuf = nullptr;
+            if (dp_trace && !cap) { GGB_CUDA(cudaMalloc(reinterpret_cast<void **>(&tbuf), 4 * 64 * 8 * 8)); GGB_CUDA(cudaMemsetAsync(tbuf, 0, 4 * 64 * 8 * 8, s)); }
+            for (DpProgram &pg : progs) {
+                pg.bar = dc.dp_bar; pg.silu_table = silu; pg.trace = &pg == &progs[0] ? tbuf : nullptr;
+                rc = launch_decode_program(pg, s);
+                if (rc) return rc;
+            }
+            if (tbuf) {
+                // debugging aid: where the first 64 steps of CTAs 0 / 32 / 64 / 96 spent their time (ns): row ops | staging | tiles | barrier
+                std::vector<long long> h(4 * 64 * 8);
+                GGB_CUDA(cudaStreamSynchronize(s));
+                GGB_CUDA(cudaMemcpy(h.data(), tbuf, h.size() * 8, cudaMemcpyDeviceToHost));
+                cudaFree(tbuf);
+                for (int c = 0; c < 4; c++)
+                    for (int si = 0; si < std::min(64, progs[0].n_steps); si++) {
+                        const long long *t = &h[(size_t)((c * 64 + si) * 8)];
+                        fprintf(stderr, "dp trace cta %3d step %2d (%d ops, %d nodes, %d tiles): ops %5lld  stage %5lld  tiles %6lld  barrier %5lld  | since start %lld\n", c * 32, si,
+                                progs[0].step[si].nops, progs[0].step[si].nnodes, progs[0].step[si].total_tiles, t[1] - t[0], t[2] ? t[2] - t[1] : 0, t[2] ? t[3] - t[2] : 0, t[4] - t[3], t[4] - h[(size_t)(c * 64 * 8)]);
+                    }
+            }
+            ran_program = true;
+        }
+    }
+
+    for (int lv = 0; lv <= max_level && !ran_program; lv++) {
         std::vector<ggb_dev_mm> mms;
         std::vector<size_t> mm_item;                             // which node each entry of mms belongs to
         bool level_has_mm = false;
@@ -1341,7 +1619,17 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
         // each node's share of the device time: measured per dependency level (eager computes), split inside a level by bytes moved;
         // a recorded graph has no events inside, so its nodes keep the shares of the last eager compute of the same cgraph
         std::vector<float> share(n, 1.0f / (float)n);
-        if (!cap) {
+        if (ran_program) {
+            // one launch, no events inside: the nodes share its time by the bytes they move
+            double tot = 0.0;
+            std::vector<double> w(n, 0.0);
+            for (size_t i = 0; i < n; i++) {
+                const ggml_tensor *t = nodes[i];
+                w[i] = (double)tensor_span(out_tensor(nodes[i])) + (t->src0 ? (double)tensor_span(t->src0) : 0.0) + ((t->src1 && t->src1->data) ? (double)tensor_span(t->src1) : 0.0);
+                tot += w[i];
+            }
+            if (tot > 0.0) for (size_t i = 0; i < n; i++) share[i] = (float)(w[i] / tot);
+        } else if (!cap) {
             std::vector<double> w(n, 0.0), lw((size_t)max_level + 1, 0.0), lms((size_t)max_level + 1, 0.0);
             for (size_t i = 0; i < n; i++) {
                 const ggml_tensor *t = nodes[i];
@@ -2100,6 +2388,13 @@ int ggb_peer_barrier(uint64_t *const *peer_flags, int rank, int world, uint64_t 
 }
 
 int ggb_set_kernel_timing(int on) { g_timing = on < 0 ? 0 : on > 2 ? 2 : on; return GGB_OK; }
+int ggb_set_decode_program(int on)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    const bool want = on != 0;
+    if (want != g_decode_program) { g_decode_program = want; g_epoch++; }      // recorded graphs were enqueued the other way
+    return GGB_OK;
+}
 int ggb_get_stats(ggb_stats *out)
 {
     if (!out) return set_error(GGB_E_INVALID, "null");

@@ -130,6 +130,7 @@ GGB_SYMBOLS = {
     "ggb_get_stats": (C.c_int, [C.POINTER(ggb_stats)]),
     "ggb_reset_stats": (C.c_int, []),
     "ggb_set_kernel_timing": (C.c_int, [C.c_int]),
+    "ggb_set_decode_program": (C.c_int, [C.c_int]),
 }
 
 HOST_SYMBOLS = {

@@ -553,7 +553,47 @@ def test_stats_count_launches():
     W = weights(rng, 64, 128)
     dev_mul_mat(N.Q4_0, orc.encode_weights(N.Q4_0, W), 64, 128, rng.standard_normal((1, 128)).astype(np.float32))
     s = N.stats()
-    assert s.kernel_launches == 2            # activation quantize + fused GEMV
+    assert s.kernel_launches == 1            # a small single-token level: the GEMV quantizes the activation row in its prologue
+
+
+def test_gemv_that_quantizes_its_own_row_equals_the_staged_path():
+    """Levels of up to 8 single-token nodes skip the staging launch: k_gemv_fast builds the Q8 blocks of src1 itself (ggb_act_q8.cuh,
+    quantize_row_q8_0 Ggml.cs:1158-1196).  The split-phase calls always stage with k_act_batch, so phase 1 + phase 2 over the same
+    nodes must leave the same bytes -- on inputs that exercise every branch that decides a bit -- and one call is one launch."""
+    rng = np.random.default_rng(93)
+    # (type, M, K, launches of the one-call form): rows that are not whole 16-byte-aligned units take the plain-load GEMV, which is staged
+    specs = [(N.Q4_0, 4096, 4096, 1), (N.Q4_1, 300, 2048, 1), (N.Q4_2, 129, 1024, 1), (N.Q5_0, 48, 4096, 1), (N.Q5_1, 7, 64, 1), (N.Q8_0, 100, 512, 1),
+             (N.Q5_1, 7, 32, 2), (N.Q4_0, 33, 96, 2)]
+    d = Dev()
+    try:
+        for t, M, K, launches in specs:
+            wb = orc.encode_weights(t, weights(rng, M, K))
+            xs = _nasty(rng, 11, K)
+            xs[3, :] = 0.0
+            mm = N.ggb_dev_mm()
+            mm.type, mm.M, mm.K, mm.N = t, M, K, 1
+            mm.W, mm.nb01 = d.put(wb), wb.shape[1]
+            X = d.put(xs)
+            mm.ldx_bytes = 4 * K
+            mm.Y, mm.ldy_bytes = d.empty(4 * M), 4 * M
+            wsb = N.lib().ggb_dev_workspace_bytes(C.byref(mm), 1)
+            ws = d.empty(wsb)
+            for r in range(xs.shape[0]):
+                mm.X = X + 4 * K * r
+                N.lib().ggb_reset_stats()
+                N.check(N.lib().ggb_dev_mul_mat_batch(C.byref(mm), 1, ws, wsb, None))
+                N.check(N.lib().ggb_stream_sync(None))
+                assert N.stats().kernel_launches == launches, (t, M, K)
+                fused = d.get(mm.Y, (1, M))
+                N.check(N.lib().ggb_dev_mul_mat_batch_phase(C.byref(mm), 1, ws, wsb, None, 1))
+                N.check(N.lib().ggb_dev_mul_mat_batch_phase(C.byref(mm), 1, ws, wsb, None, 2))
+                N.check(N.lib().ggb_stream_sync(None))
+                staged = d.get(mm.Y, (1, M))
+                assert np.array_equal(fused.view(np.uint32), staged.view(np.uint32)), (t, M, K, r)
+                want = orc.mul_mat_2d(t, wb, M, K, xs[r:r + 1])
+                assert rel_l2(fused, want) <= 6e-6 or not np.isfinite(want).all(), (t, M, K, r, rel_l2(fused, want))
+    finally:
+        d.close()
 
 
 def test_peer_exchange_degenerates_cleanly_on_one_rank():
