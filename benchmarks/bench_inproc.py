@@ -137,10 +137,26 @@ def chain_record(torch, N, ggml, layers=32, iters=10, dev_index=0):
                 out.update({"ms_per_compute": dt * 1e3, "device_ms": float(st.last_graph_device_ms), "graph_replays": int(st.graph_replays),
                             "kernel_launches_per_compute": int(st.kernel_launches // iters)})
         res = ggml.tensor_f32(cur).reshape(-1).copy()
+        # the same chain as one or two launches per dependency level (ggb_set_decode_program(0)): what the persistent launch replaces
+        N.check(L.ggb_set_decode_program(0))
+        try:
+            for _ in range(3):                                # eager, recorded, first replay
+                c.graph_compute(g)
+            L.ggb_reset_stats()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                c.graph_compute(g)
+            dt = (time.perf_counter() - t0) / iters
+            st = N.stats()
+            out["per_level_route"] = {"ms_per_compute": dt * 1e3, "device_ms": float(st.last_graph_device_ms), "kernel_launches_per_compute": int(st.kernel_launches // iters),
+                                      "bit_identical": bool(np.array_equal(ggml.tensor_f32(cur).reshape(-1).view(np.uint32), res.view(np.uint32)))}
+        finally:
+            N.check(L.ggb_set_decode_program(1))
     n_levels_mm = 4 * layers
     out.update({"config": "dependent chain through ggml_graph_compute: %d Llama-7B-shaped layers, one token, 15 nodes / 10 levels per layer (4 mul_mat levels: 3, 1, 2, 1 nodes wide), Q4_0 weights resident (%.2f GB)" % (layers, wbytes / 1e9),
                 "nodes": int(g.n_nodes), "mul_mat_levels": n_levels_mm, "weights_GB": wbytes / 1e9, "achieved": wbytes / (out["ms_per_compute"] * 1e-3) / 1e9, "unit": "GB/s",
-                "finite": bool(np.all(np.isfinite(res)))})
+                "finite": bool(np.all(np.isfinite(res))),
+                "route": "decode program: the chain is one persistent cooperative launch (k_decode_program) + the result copies" if out["kernel_launches_per_compute"] < n_levels_mm else "per-level launches"})
     return out
 
 

@@ -1051,6 +1051,24 @@ bool decode_program_finish(DpProgram &p)
     return p.depth >= 2;
 }
 
+// the grid barrier needs every CTA resident at once: a device (or an MPS partition) that cannot launch one 512-thread CTA with the
+// full shared memory per SM cooperatively does not get the program
+bool decode_program_available()
+{
+    static int state[16] = {};                                    // per device: 0 unknown, 1 yes, -1 no
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { cudaGetLastError(); return false; }
+    if (state[dev] == 0) {
+        int coop = 0, per_sm = 0;
+        bool ok = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop != 0;
+        ok = ok && cudaFuncSetAttribute(k_decode_program, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512) == cudaSuccess;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_program, (NWF + 1) * 32, 227 * 1024 - 512) == cudaSuccess && per_sm >= 1;
+        cudaGetLastError();
+        state[dev] = ok ? 1 : -1;
+    }
+    return state[dev] > 0;
+}
+
 int launch_decode_program(const DpProgram &p, cudaStream_t s)
 {
     static PerDeviceOnce once;

@@ -149,6 +149,7 @@ int64_t decode_program_row_max();                                   // longest r
 bool decode_program_plan_step(DpStep &st, int type, int64_t K, int64_t nb01, const void *W);
 int decode_program_tile_rows(const DpStep &st);                     // weight rows per tile of a planned step
 bool decode_program_finish(DpProgram &p);                           // sizes the shared-memory regions; false: does not fit
+bool decode_program_available();                                    // cooperative launch of one full CTA per SM is possible on the current device
 int launch_decode_program(const DpProgram &p, cudaStream_t s);
 int silu_table_device(const unsigned short **table);               // builds / returns the device copy of table_silu_f16
 

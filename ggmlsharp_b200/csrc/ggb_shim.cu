@@ -1420,7 +1420,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             if (cur.n_steps) { if (!decode_program_finish(cur)) return bail("program does not fit shared memory"); progs.push_back(cur); }
             return !progs.empty();
         };
-        if (build()) {
+        if (decode_program_available() && build()) {
             DevCtx &dc = dctx;
             if (!dc.dp_bar) {
                 if (cap) return GGB_E_NOCAPTURE;
@@ -1440,8 +1440,16 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             for (DpProgram &pg : progs) {
                 pg.bar = dc.dp_bar; pg.silu_table = silu; pg.trace = &pg == &progs[0] ? tbuf : nullptr;
                 rc = launch_decode_program(pg, s);
+                if (rc && &pg == &progs[0] && !cap) {
+                    // the first launch was refused (co-residency not available right now): nothing is enqueued yet, take the per-level route
+                    cudaGetLastError();
+                    if (trace) fprintf(stderr, "ggb200: decode program not used: %s\n", g_err);
+                    break;
+                }
                 if (rc) return rc;
+                ran_program = true;
             }
+            if (tbuf && !ran_program) { cudaFree(tbuf); tbuf = nullptr; }
             if (tbuf) {
                 // debugging aid: where the first 64 steps of CTAs 0 / 32 / 64 / 96 spent their time (ns): row ops | staging | tiles | barrier
                 std::vector<long long> h(4 * 64 * 8);
@@ -1455,7 +1463,6 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                                 progs[0].step[si].nops, progs[0].step[si].nnodes, progs[0].step[si].total_tiles, t[1] - t[0], t[2] ? t[2] - t[1] : 0, t[2] ? t[3] - t[2] : 0, t[4] - t[3], t[4] - h[(size_t)(c * 64 * 8)]);
                     }
             }
-            ran_program = true;
         }
     }
 
