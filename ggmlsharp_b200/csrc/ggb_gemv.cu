@@ -896,6 +896,14 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_decode_program(const __gr
     for (int si = 0; si < P.n_steps; si++) {
         const DpStep &sp = P.step[si];
         dp_stamp(P, si, 0);
+        // ---- results of earlier steps go to the host arena: one warp per tensor, this CTA's slice of it (coalesced 16-byte stores that
+        //      nobody waits for) ----
+        for (int ci = sp.copy0 + warp; ci < sp.copy0 + sp.ncopies; ci += NWF) {
+            const DpCopy &cp = P.copy[ci];
+            const int per = (cp.n4 + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int lo = (int)blockIdx.x * per, hi = min(cp.n4, lo + per);
+            for (int i = lo + lane; i < hi; i += 32) cp.dst[i] = __ldcg(cp.src + i);
+        }
         // ---- the step's row ops.  float4 i of the running row belongs to thread i mod DP_NT in every op, so element-wise ops need
         //      no barrier between them; operands other CTAs wrote (before the last grid barrier) are read past L1 (__ldcg) ----
         for (int oi = sp.op0; oi < sp.op0 + sp.nops; oi++) {

@@ -133,8 +133,11 @@ int64_t gemv_x_budget();             // bytes of staged activation columns one G
 enum { DP_LOAD = 0, DP_ADD, DP_MUL, DP_SILU, DP_RMS_NORM, DP_SCALE };
 struct DpNode { const uint8_t *W; float *y; float *y2; long long nb01; int M, tile0, ntiles, pad_; };     // y2: SILU of the result (may be y itself: in place), or null
 struct DpOp { const float *a, *b; float *dst; float scalar; int op, n, pad_; };      // a == null: the running row; b: second operand (global) or null
-struct DpStep { int op0, nops, node0, nnodes, total_tiles, type, K, row_bytes, rs, nchunk, chunk_bytes, stage_bytes; };
-constexpr int DP_MAX_STEPS = 144, DP_MAX_NODES = 240, DP_MAX_OPS = 280;      // 29.7 KB of kernel parameters (the limit is 32 764 B)
+struct DpStep { int op0, nops, node0, nnodes, total_tiles, type, K, row_bytes, rs, nchunk, chunk_bytes, stage_bytes, copy0, ncopies, pad_[2]; };
+// a result of an EARLIER step on its way to the host arena (the reference's tensors live in host memory): every CTA stores its slice at
+// the start of the step, so the PCIe writes of a level run under the following levels instead of after the whole chain
+struct DpCopy { const float4 *src; float4 *dst; int n4, pad_; };
+constexpr int DP_MAX_STEPS = 96, DP_MAX_NODES = 168, DP_MAX_OPS = 192, DP_MAX_COPIES = 360;      // 30.6 KB of kernel parameters (the limit is 32 764 B): 24 Llama layers
 struct DpProgram {
     unsigned *bar;                       // grid barrier counter, zero at launch
     const unsigned short *silu_table;    // table_silu_f16 (ggb_ops.cu)
@@ -143,7 +146,9 @@ struct DpProgram {
     DpStep step[DP_MAX_STEPS];
     DpNode node[DP_MAX_NODES];
     DpOp op[DP_MAX_OPS];
+    DpCopy copy[DP_MAX_COPIES];
 };
+static_assert(sizeof(DpProgram) <= 32764, "kernel parameter space");
 int64_t decode_program_row_max();                                   // longest running row (elements)
 // fills step.{type, K, row_bytes, rs, nchunk, chunk_bytes, stage_bytes} for single-token nodes of this shape; false: not a shape the program takes
 bool decode_program_plan_step(DpStep &st, int type, int64_t K, int64_t nb01, const void *W);

@@ -1205,6 +1205,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
     bool ran_program = false;
     if (!sc && lead && !g_timing && g_decode_program && n >= 2) {
         std::vector<DpProgram> progs;
+        std::vector<size_t> prog_copied;                           // nodes whose results the program itself stores into the host arena
         bool need_silu = false;
         static const bool trace = getenv("GGB200_TRACE_PROGRAM") != nullptr;      // says on stderr why a graph was left to the per-level launches
         size_t at = 0;
@@ -1277,18 +1278,37 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
             DpProgram cur = {};
             const uint8_t *run_ptr = nullptr; int64_t run_n = 0;   // the tensor the running row holds
             int n_nodes = 0, n_ops = 0;
-            auto open_step = [&]() { DpStep &st = cur.step[cur.n_steps]; st = DpStep{}; st.op0 = n_ops; st.node0 = n_nodes; };
+            // results of closed steps that go back to the host arena from inside the program (the conditions of copy_out's coalesced
+            // kernel, in whole float4s); what does not fit a parameter block is left to copy_out
+            struct Pending { DpCopy c; size_t item; };
+            std::vector<Pending> pending;
+            int n_copies = 0;
+            auto to_host = [&](size_t i) {
+                const Item &it = items[i];
+                ggml_tensor *o = out_tensor(it.t);
+                const size_t span = tensor_span(o);
+                if ((flags & GGB_GRAPH_KEEP_ON_DEVICE) && !is_output[i]) return;
+                if (!pool->owned || span > ZC_MAX || (span & 15) || ((reinterpret_cast<uintptr_t>(o->data) | reinterpret_cast<uintptr_t>(it.dd)) & 15) || !final_value(i)) return;
+                pending.push_back({DpCopy{reinterpret_cast<const float4 *>(it.dd), static_cast<float4 *>(o->data), (int)(span / 16), 0}, i});
+            };
+            auto open_step = [&]() {
+                DpStep &st = cur.step[cur.n_steps];
+                st = DpStep{}; st.op0 = n_ops; st.node0 = n_nodes; st.copy0 = n_copies;
+                for (const Pending &pc : pending) if (n_copies < DP_MAX_COPIES) { cur.copy[n_copies++] = pc.c; prog_copied.push_back(pc.item); }
+                pending.clear();
+                st.ncopies = n_copies - st.copy0;
+            };
             auto finish_program = [&]() -> bool {
                 if (cur.n_steps == 0) return true;
                 if (!decode_program_finish(cur)) return false;
                 progs.push_back(cur);
-                cur = DpProgram{}; n_nodes = 0; n_ops = 0; run_ptr = nullptr; run_n = 0;
+                cur = DpProgram{}; n_nodes = 0; n_ops = 0; n_copies = 0; run_ptr = nullptr; run_n = 0;
                 open_step();
                 return true;
             };
             auto close_step = [&]() -> bool {                      // ends the open step with a grid barrier (an empty step is not closed)
                 DpStep &st = cur.step[cur.n_steps];
-                if (st.nops == 0 && st.nnodes == 0) return true;
+                if (st.nops == 0 && st.nnodes == 0 && st.ncopies == 0) return true;
                 cur.n_steps++; gstep++;
                 step_reads.clear(); step_writes.clear();
                 if (cur.n_steps == DP_MAX_STEPS) return finish_program();
@@ -1349,8 +1369,8 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                             run_ptr = it.db; run_n = K;
                         }
                         st = &cur.step[cur.n_steps];
-                        const int op0 = st->op0, nops = st->nops, node0 = st->node0;
-                        *st = plan; st->op0 = op0; st->nops = nops; st->node0 = node0;
+                        const int op0 = st->op0, nops = st->nops, node0 = st->node0, copy0 = st->copy0, ncopies = st->ncopies;
+                        *st = plan; st->op0 = op0; st->nops = nops; st->node0 = node0; st->copy0 = copy0; st->ncopies = ncopies;
                     } else if (n_nodes + 1 > DP_MAX_NODES) return bail("a level of too many mul_mats");      // (a step of more than DP_MAX_NODES mul_mats: not a decode chain)
                     const size_t ybytes = (size_t)a->ne[1] * 4;
                     if (overlaps(step_reads, it.dd, ybytes, false) || overlaps(step_writes, it.dd, ybytes, false)) return bail("a mul_mat result aliases something its step touches");
@@ -1362,6 +1382,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                     st->total_tiles += nd.ntiles; st->nnodes++;
                     step_writes.push_back({it.dd, ybytes});
                     wstep[i] = gstep;
+                    to_host(i);
                     continue;
                 }
                 const int64_t len = nelements(t);
@@ -1376,6 +1397,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                         if (it.dd != it.da) step_writes.push_back({it.dd, bytes});
                         need_silu = true;
                         wstep[i] = gstep;
+                        to_host(i);
                         continue;
                     }
                 }
@@ -1412,10 +1434,17 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                 else push_op(op, a_run ? nullptr : pa, nullptr, it.dd, len, scalar);
                 run_ptr = it.dd; run_n = len;
                 wstep[i] = gstep;
+                to_host(i);
             }
             {
                 DpStep &st = cur.step[cur.n_steps];
-                if (st.nops || st.nnodes) cur.n_steps++;
+                if (st.nops || st.nnodes || st.ncopies) cur.n_steps++;
+                if (!pending.empty()) {
+                    // the last step's results: one more step (behind its barrier) that only ships them
+                    if (cur.n_steps == DP_MAX_STEPS) { if (!finish_program()) return bail("program does not fit shared memory"); }
+                    else open_step();
+                    if (cur.step[cur.n_steps].ncopies) cur.n_steps++;
+                }
             }
             if (cur.n_steps) { if (!decode_program_finish(cur)) return bail("program does not fit shared memory"); progs.push_back(cur); }
             return !progs.empty();
@@ -1449,6 +1478,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                 if (rc) return rc;
                 ran_program = true;
             }
+            if (ran_program) for (size_t i : prog_copied) { copied[i] = 1; g_stats.d2h_bytes += tensor_span(out_tensor(items[i].t)); }
             if (tbuf && !ran_program) { cudaFree(tbuf); tbuf = nullptr; }
             if (tbuf) {
                 // debugging aid: where the first 64 steps of CTAs 0 / 32 / 64 / 96 spent their time (ns): row ops | staging | tiles | barrier

@@ -160,7 +160,7 @@ def test_a_long_chain_is_split_into_several_launches():
                 nodes["c%d" % l] = cur
         return c.build_forward(cur), nodes, None
     (prog, lp, _), (lvl, ll, _) = _both_routes(build, cache=False, computes=3)
-    assert 3 <= lp <= 8 and ll >= 480, (lp, ll)                    # two program launches + the result copies (96 tensors each)
+    assert 2 <= lp <= 8 and ll >= 480, (lp, ll)                    # two program launches (+ a result copy for what they did not ship themselves)
     for k in prog:
         assert np.array_equal(prog[k].view(np.uint32), lvl[k].view(np.uint32)), k
     assert np.isfinite(prog["c159"]).all()
