@@ -54,6 +54,7 @@ internal static unsafe partial class GgbNative
         public int* W_rowexp; public int flags, _pad;       // GGB_MM_W_IN_FLIGHT = 1
     }
     public const int GGB_MM_W_IN_FLIGHT = 1;
+    public const int GGB_MM_X_HOST = 2;
     [DllImport(Lib)] public static extern int ggb_dev_weight_rowexp(int type, void* W, long nb01, long M, long K, int* rowexp, IntPtr stream);
     [StructLayout(LayoutKind.Sequential)]
     public struct ggb_stats

@@ -484,7 +484,7 @@ static int dev_batch_inner(const ggb_dev_mm *mm, int count, void *ws, size_t ws_
         for (size_t c = 0; c < grp.size() && fuse_x; c++) {
             const ggb_dev_mm &m = mm[grp[c]];
             GemvHdr probe = {};
-            if (m.N != 1 || (reinterpret_cast<uintptr_t>(m.X) & 15) || gemv_plan(probe, type, K, m.nb01, 1, m.W) || !gemv_can_fuse_x(probe)) fuse_x = false;
+            if (m.N != 1 || (m.flags & GGB_MM_X_HOST) || (reinterpret_cast<uintptr_t>(m.X) & 15) || gemv_plan(probe, type, K, m.nb01, 1, m.W) || !gemv_can_fuse_x(probe)) fuse_x = false;
         }
         // activation staging (INIT phase)
         for (size_t c0 = 0; c0 < grp.size(); c0 += GGB_MAX_BATCH_NODES) {
@@ -1517,6 +1517,7 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                     // the F16 and quantized drivers index dst as dst_col[ic*ne0] (Ggml.cs:6423, 6697); F32 uses nb1 (6160)
                     m.ldy_bytes = a->type == GGML_TYPE_F32 ? (int64_t)t->nb[1] : (int64_t)t->ne[0] * 4;
                     if (it.a_in_flight || it.ew_new) m.flags |= GGB_MM_W_IN_FLIGHT;     // src0 is an earlier node's result (CPY -> MUL_MAT), or its exponents are brand new
+                    if (it.db == static_cast<const uint8_t *>(b->data)) m.flags |= GGB_MM_X_HOST;      // a small leaf read in place from the pinned arena
                     if (!it.ew.empty()) m.W_rowexp = it.ew[(size_t)(i3 * a->ne[2] + i2)];
                     if (G > 1) {
                         // the fused all-gather: the kernel writes each result into every other device's copy of dst as well

@@ -250,6 +250,9 @@ typedef struct ggb_dev_mm {
 } ggb_dev_mm;
 #define GGB_MM_W_IN_FLIGHT 1       /* W (or W_rowexp) is written by work enqueued earlier on the same stream: the weight loads, which otherwise
                                       start before the activation staging has finished, wait for it as well */
+#define GGB_MM_X_HOST      2       /* X is pinned host memory the kernels read in place (UVA): it is staged by ONE pass over it; without the flag a
+                                      small batch of single-token nodes lets every CTA of the GEMV read the row itself, which is right for device memory
+                                      (16 KB from L2) and 148 trips over PCIe for host memory */
 
 /* Range handling of the tensor-core path (N >= 16, quantized W).  The reference multiplies float32 block scales (Ggml.cs:1158,
  * 1190-1196); the MMA operands are fp16, so each weight row m is pre-scaled by the exact power of two 2^-rowexp[m] and each staged
