@@ -1774,6 +1774,7 @@ int ggb_shutdown(void)
     cudaSetDevice(g_device);
     if (!g_devs.empty()) { cudaEventDestroy(g_devs[0].fork); cudaEventDestroy(g_devs[0].join); cudaStreamDestroy(g_devs[0].stream2); }
     for (DevCtx &d : g_devs) { for (cudaEvent_t e : d.level_time) cudaEventDestroy(e); d.level_time.clear(); }
+    if (!g_devs.empty() && g_devs[0].dp_bar) { cudaFree(g_devs[0].dp_bar); g_devs[0].dp_bar = nullptr; g_devs[0].dp_silu_ready = false; }
     g_devs.clear(); g_multi = 0;
     cudaEventDestroy(g_ev0); cudaEventDestroy(g_ev1);
     cudaStreamDestroy(g_stream);
