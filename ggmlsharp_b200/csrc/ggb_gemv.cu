@@ -515,9 +515,22 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_gemv_fast(const __grid_co
                     }
             } else {
                 asm volatile("bar.sync 1, %0;" ::"n"(NWF * 32) : "memory");      // all consumers are done with the previous x
-                const uint4 *src = reinterpret_cast<const uint4 *>(b.node[n].xq);
-                uint4 *dst = reinterpret_cast<uint4 *>(xs);
-                for (int i = threadIdx.x; i < (NC * xcol_bytes) >> 4; i += NWF * 32) dst[i] = src[i];
+                if (UnitTraits<TYPE>::Q && NC == 1 && b.fuse_x) {
+                    // long rows (more than 32 units, K-chunked stages): the same self-staging as above, the blocks stay in shared memory
+                    const uint8_t *xf = b.node[n].xq;
+                    for (int base = 0; base < kb; base += NWF * 4) {
+                        const int col = base + (int)(threadIdx.x >> 3), sub = lane & 7;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (col < kb) v = __ldcg(reinterpret_cast<const float4 *>(xf + (long long)col * 128 + sub * 16));
+                        uint32_t ev, od; float d; int sm;
+                        q8_block_sub8(v, sub, TYPE == GGML_TYPE_Q4_2, ev, od, d, sm);
+                        if (col < kb) q8_block_store(xs, kb, BPS, col, sub, ev, od, d, sm);
+                    }
+                } else {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(b.node[n].xq);
+                    uint4 *dst = reinterpret_cast<uint4 *>(xs);
+                    for (int i = threadIdx.x; i < (NC * xcol_bytes) >> 4; i += NWF * 32) dst[i] = src[i];
+                }
                 asm volatile("bar.sync 1, %0;" ::"n"(NWF * 32) : "memory");
             }
         }
@@ -687,12 +700,12 @@ int gemv_act_bps(const GemvHdr &b)
     switch (b.type) { case GGML_TYPE_Q4_0: case GGML_TYPE_Q4_2: case GGML_TYPE_Q5_0: case GGML_TYPE_Q8_0: return 4;
                       case GGML_TYPE_Q4_1: case GGML_TYPE_Q5_1: return 2; default: return 1; }
 }
-// the conditions of launch_fast_typed's `xreg` case: a quantized type, whole rows per stage, at most one unit per lane
+// the fast kernel, a quantized type, one activation column: its consumer warps can build the Q8 blocks of the row themselves
 bool gemv_can_fuse_x(const GemvHdr &b)
 {
-    if (!b.async || !is_q_weight(b.type) || b.ncols != 1 || b.nchunk != 1) return false;
+    if (!b.async || !is_q_weight(b.type) || b.ncols != 1) return false;
     const int ub = unit_bytes_async(b.type);
-    return ub > 0 && b.row_bytes % ub == 0 && b.row_bytes / ub <= 32;
+    return ub > 0 && b.row_bytes % ub == 0;
 }
 
 // Fills the shape-dependent fields of b (everything but the node list).  ncols in {1,2,4,8}.

@@ -563,6 +563,7 @@ def test_gemv_that_quantizes_its_own_row_equals_the_staged_path():
     rng = np.random.default_rng(93)
     # (type, M, K, launches of the one-call form): rows that are not whole 16-byte-aligned units take the plain-load GEMV, which is staged
     specs = [(N.Q4_0, 4096, 4096, 1), (N.Q4_1, 300, 2048, 1), (N.Q4_2, 129, 1024, 1), (N.Q5_0, 48, 4096, 1), (N.Q5_1, 7, 64, 1), (N.Q8_0, 100, 512, 1),
+             (N.Q4_0, 64, 11008, 1), (N.Q4_1, 40, 11008, 1), (N.Q8_0, 33, 8192, 1),      # rows of more than 32 units, staged in K-chunks
              (N.Q5_1, 7, 32, 2), (N.Q4_0, 33, 96, 2)]
     d = Dev()
     try:
