@@ -57,19 +57,39 @@ __global__ void __launch_bounds__(256) k_binary_f32_scalar(int op, const float *
         z[i] = op == GGML_OP_ADD ? __fadd_rn(a[i], b[i]) : __fmul_rn(a[i], b[i]);
 }
 
+// VEC: 16-byte aligned operands, four elements per thread and step (the scalar form moved 3.4 -- SILU -- and 4.3 TB/s -- SCALE -- on a
+// 64 MB tensor against ADD / MUL's 6.7: profiles/r02_ops_throughput.txt); the tail of up to three elements goes element by element
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_scale_f32(float *__restrict__ y, float v, long long n)
 {
     pdl_wait_then_release();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = __fmul_rn(y[i], v);
+    const long long n4 = VEC ? n >> 2 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 r = reinterpret_cast<float4 *>(y)[i];
+        r.x = __fmul_rn(r.x, v); r.y = __fmul_rn(r.y, v); r.z = __fmul_rn(r.z, v); r.w = __fmul_rn(r.w, v);
+        reinterpret_cast<float4 *>(y)[i] = r;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = __fmul_rn(y[i], v);
 }
 
+__device__ __forceinline__ float silu_lookup(float x, const unsigned short *__restrict__ table)
+{
+    const unsigned short h = __half_as_ushort(__float2half_rn(x));                   // (Half)x, round to nearest even
+    return __half2float(__ushort_as_half(__ldg(table + h)));                         // (float)table_silu_f16[t]
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_silu_f32(const float *x, float *y, long long n, const unsigned short *__restrict__ table)
 {
     pdl_wait_then_release();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned short h = __half_as_ushort(__float2half_rn(x[i]));          // (Half)x, round to nearest even
-        y[i] = __half2float(__ushort_as_half(__ldg(table + h)));                     // (float)table_silu_f16[t]
+    const long long n4 = VEC ? n >> 2 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4 *>(x)[i];
+        float4 r;
+        r.x = silu_lookup(a.x, table); r.y = silu_lookup(a.y, table); r.z = silu_lookup(a.z, table); r.w = silu_lookup(a.w, table);
+        reinterpret_cast<float4 *>(y)[i] = r;
     }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = silu_lookup(x[i], table);
 }
 
 // one CTA per row
@@ -79,7 +99,19 @@ __global__ void __launch_bounds__(256) k_rms_norm_f32(const float *x, long long 
     const float *xr = x + (long long)blockIdx.x * x_stride;
     float *yr = y + (long long)blockIdx.x * y_stride;
     double sum = 0.0;
-    for (int i = threadIdx.x; i < ne00; i += blockDim.x) { const float v = xr[i]; sum += (double)__fmul_rn(v, v); }   // float product, double accumulate
+    // rows of up to 4096 elements stay in registers between the two passes (the second read of the row was the other half of this
+    // kernel's traffic and latency); the order of the additions is the one it always was: thread t adds elements t, t + 256, ...
+    constexpr int KEEP = 16;
+    float keep[KEEP];
+    const bool kept = ne00 <= KEEP * (int)blockDim.x;
+    if (kept) {
+#pragma unroll
+        for (int k = 0; k < KEEP; k++) { const int i = threadIdx.x + k * (int)blockDim.x; keep[k] = i < ne00 ? xr[i] : 0.0f; }
+#pragma unroll
+        for (int k = 0; k < KEEP; k++) if ((int)threadIdx.x + k * (int)blockDim.x < ne00) sum += (double)__fmul_rn(keep[k], keep[k]);
+    } else {
+        for (int i = threadIdx.x; i < ne00; i += blockDim.x) { const float v = xr[i]; sum += (double)__fmul_rn(v, v); }   // float product, double accumulate
+    }
 #pragma unroll
     for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     __shared__ double part[8];
@@ -94,7 +126,12 @@ __global__ void __launch_bounds__(256) k_rms_norm_f32(const float *x, long long 
     }
     __syncthreads();
     const float scale = s_scale;
-    for (int i = threadIdx.x; i < ne00; i += blockDim.x) yr[i] = __fmul_rn(xr[i], scale);
+    if (kept) {
+#pragma unroll
+        for (int k = 0; k < KEEP; k++) { const int i = threadIdx.x + k * (int)blockDim.x; if (i < ne00) yr[i] = __fmul_rn(keep[k], scale); }
+    } else {
+        for (int i = threadIdx.x; i < ne00; i += blockDim.x) yr[i] = __fmul_rn(xr[i], scale);
+    }
 }
 
 // dst (contiguous, [ne3][ne2][ne1][ne0]) <- strided src.  TRANSPOSED: the source's fast dimension is i1 (nb[1] == 4), the
@@ -202,7 +239,8 @@ int launch_binary_f32(int op, const float *a, const float *b, float *dst, int64_
 int launch_scale_f32(float *y, float v, int64_t n, cudaStream_t s)
 {
     if (n <= 0) return GGB_OK;
-    return launch_pdl(k_scale_f32, dim3(stream_grid(n, 256)), dim3(256), s, y, v, (long long)n);
+    if ((reinterpret_cast<uintptr_t>(y) & 15) == 0) return launch_pdl(k_scale_f32<true>, dim3(stream_grid(n / 4 + 1, 256)), dim3(256), s, y, v, (long long)n);
+    return launch_pdl(k_scale_f32<false>, dim3(stream_grid(n, 256)), dim3(256), s, y, v, (long long)n);
 }
 
 int silu_table_device(const unsigned short **table)
@@ -218,7 +256,9 @@ int launch_silu_f32(const float *x, float *y, int64_t n, cudaStream_t s)
     if (n <= 0) return GGB_OK;
     std::call_once(g_silu_once, build_silu_table);
     if (!g_silu_table) return g_silu_rc ? g_silu_rc : set_error(GGB_E_CUDA, "silu table unavailable");
-    return launch_pdl(k_silu_f32, dim3(stream_grid(n, 256)), dim3(256), s, x, y, (long long)n, (const unsigned short *)g_silu_table);
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+        return launch_pdl(k_silu_f32<true>, dim3(stream_grid(n / 4 + 1, 256)), dim3(256), s, x, y, (long long)n, (const unsigned short *)g_silu_table);
+    return launch_pdl(k_silu_f32<false>, dim3(stream_grid(n, 256)), dim3(256), s, x, y, (long long)n, (const unsigned short *)g_silu_table);
 }
 
 int launch_rms_norm_f32(const float *x, int64_t x_stride, float *y, int64_t y_stride, int64_t nrows, int64_t ne00, cudaStream_t s)
