@@ -12,7 +12,7 @@ sys.path.insert(0, ".")
 
 ROWS, COLS = 4096, 4096
 # bytes each kernel moves per element: (kernel-name fragment, node, algorithmic bytes per element)
-MOVES = [("k_binary_f32", "add / mul", 12), ("k_silu_f32", "silu (fp16 table)", 8), ("k_rms_norm_f32", "rms_norm (row read twice: L2 holds a 16 KB row)", 8),
+MOVES = [("k_binary_f32", "add / mul", 12), ("k_silu_f32", "silu (fp16 table)", 8), ("k_rms_norm_f32", "rms_norm (row held in registers between the passes)", 8),
          ("k_scale_f32", "scale (in place)", 8)]
 
 
