@@ -1572,7 +1572,8 @@ static int run_nodes(ggb_pool *pool, const std::vector<ggml_tensor *> &nodes, in
                 //      whatever the stream -- but the staging kernel and the copy kernel are small enough (128 / 256 threads, <= 4 K
                 //      registers per CTA) to sit beside a resident GEMV CTA, so chunk c's PCIe traffic hides under chunk c+-1's
                 //      weight streaming instead of preceding and following ONE big GEMV. ----
-                const int nchunk = mms.size() >= 16 ? 4 : 2;
+                static const int chunks_env = [] { const char *e = getenv("GGB200_LANE_CHUNKS"); return e ? atoi(e) : 0; }();
+                const int nchunk = chunks_env >= 2 ? std::min<int>(chunks_env, (int)mms.size()) : mms.size() >= 16 ? 4 : 2;
                 GGB_CUDA(cudaEventRecord(dctx.fork, s));
                 GGB_CUDA(cudaStreamWaitEvent(dctx.stream2, dctx.fork, 0));
                 uint8_t *wsp = static_cast<uint8_t *>(arena.take(wsb + 256 * (size_t)nchunk));
