@@ -50,8 +50,8 @@ __device__ __forceinline__ void q8_block_sub8(const float4 v, int sub, bool q4_2
 // The same block by TWO neighbouring lanes (h = lane & 1 holds elements 16 h .. 16 h + 15 in e[]): an eighth of the divisions and a third
 // of the shuffles per block -- the decode program stages a row per dependency level and every microsecond of it is on the critical
 // path.  Same d, same quants, same sum (a maximum and an integer sum do not depend on how they are split).  Returns this half's four
-// 32-bit words: ev[0..1] / od[0..1] = words 2 h, 2 h + 1 of the two planes.
-__device__ __forceinline__ void q8_block_half16(const float (&e)[16], uint32_t (&ev)[2], uint32_t (&od)[2], float &d, int &s)
+// 32-bit words: ev[0..1] / od[0..1] = words 2 h, 2 h + 1 of the two planes.  The half index h is the lane's parity.
+__device__ __forceinline__ void q8_block_half16(const float (&e)[16], bool q4_2, uint32_t (&ev)[2], uint32_t (&od)[2], float &d, int &s)
 {
     float amax = 0.0f;
 #pragma unroll
@@ -63,7 +63,13 @@ __device__ __forceinline__ void q8_block_half16(const float (&e)[16], uint32_t (
     s = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) { q[i] = q8_round(__fmul_rn(e[i], id)); s += q[i]; }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    {
+        // lane h = 0 summed quants 0..15, lane h = 1 quants 16..31.  Q4_2 weights: two int16 half sums; everything else: the block sum
+        const int other = __shfl_xor_sync(0xffffffffu, s, 1);
+        const bool first = (threadIdx.x & 1) == 0;
+        const int lo = first ? s : other, hi = first ? other : s;
+        s = q4_2 ? (int)(((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16)) : lo + hi;
+    }
 #pragma unroll
     for (int m = 0; m < 2; m++) {
         ev[m] = (uint32_t)(q[8 * m] & 0xFF) | ((uint32_t)(q[8 * m + 2] & 0xFF) << 8) | ((uint32_t)(q[8 * m + 4] & 0xFF) << 16) | ((uint32_t)(q[8 * m + 6] & 0xFF) << 24);

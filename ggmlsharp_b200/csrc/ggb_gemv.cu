@@ -1008,7 +1008,8 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_decode_program(const __gr
             else if (sp.type == GGML_TYPE_F16) {
                 for (int i = tid; i < sp.K; i += DP_NT) reinterpret_cast<__half *>(xq)[i] = __float2half_rn(v[i]);
             } else {
-                const int bps = sp.type == GGML_TYPE_Q4_1 ? 2 : 4;
+                const int bps = (sp.type == GGML_TYPE_Q4_1 || sp.type == GGML_TYPE_Q5_1) ? 2 : 4;
+                const bool q4_2 = sp.type == GGML_TYPE_Q4_2;                          // (its two 16-element blocks need their own half sums)
                 for (int base = 0; base < kb; base += DP_NT / 2) {                        // two lanes per block; uniform trip count (shuffles)
                     const int col = base + (tid >> 1), h = tid & 1;
                     float e[16];
@@ -1018,7 +1019,7 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_decode_program(const __gr
                         e[4 * i] = x4.x; e[4 * i + 1] = x4.y; e[4 * i + 2] = x4.z; e[4 * i + 3] = x4.w;
                     }
                     uint32_t ev[2], od[2]; float d; int sm;
-                    q8_block_half16(e, ev, od, d, sm);
+                    q8_block_half16(e, q4_2, ev, od, d, sm);
                     if (col < kb) q8_block_half16_store(xq, kb, bps, col, h, ev, od, d, sm);
                 }
             }
@@ -1027,6 +1028,10 @@ __global__ void __launch_bounds__((NWF + 1) * 32, 1) k_decode_program(const __gr
             switch (sp.type) {
             case GGML_TYPE_Q4_0: dp_consume<GGML_TYPE_Q4_0>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
             case GGML_TYPE_Q4_1: dp_consume<GGML_TYPE_Q4_1>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
+            case GGML_TYPE_Q4_2: dp_consume<GGML_TYPE_Q4_2>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
+            case GGML_TYPE_Q5_0: dp_consume<GGML_TYPE_Q5_0>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
+            case GGML_TYPE_Q5_1: dp_consume<GGML_TYPE_Q5_1>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
+            case GGML_TYPE_Q8_0: dp_consume<GGML_TYPE_Q8_0>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
             case GGML_TYPE_F16: dp_consume<GGML_TYPE_F16>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
             default: dp_consume<GGML_TYPE_F32>(P, sp, xs, stages, full0, empty0, warp, lane, st, ph); break;
             }
@@ -1044,7 +1049,7 @@ int decode_program_tile_rows(const DpStep &st) { return NWF * st.rs; }
 
 bool decode_program_plan_step(DpStep &st, int type, int64_t K, int64_t nb01, const void *W)
 {
-    if (type != GGML_TYPE_Q4_0 && type != GGML_TYPE_Q4_1 && type != GGML_TYPE_F16 && type != GGML_TYPE_F32) return false;
+    if (!is_q_weight(type) && type != GGML_TYPE_F16 && type != GGML_TYPE_F32) return false;
     if (K <= 0 || K > decode_program_row_max() || K % 4) return false;
     GemvHdr h = {};
     if (gemv_plan(h, type, K, nb01, 1, W) || !h.async) return false;          // (a refusal leaves its text in the error buffer; the caller falls back and nobody reads it)

@@ -332,8 +332,8 @@ typedef struct ggb_stats {
  * 2: additionally skip the activation staging of single-token nodes and reuse what the previous identical call left in the
  * workspace, so that a stream of calls is a stream of the GEMV kernel alone (time it with your own events). 0: off. */
 int  ggb_set_kernel_timing(int on);
-/* The decode program: a ggml_graph_compute whose device-runnable nodes are a dependent chain of single-token mul_mats (Q4_0 / Q4_1 /
- * F16 / F32 weights) and their ADD / MUL / SILU / RMS_NORM / SCALE neighbours on single rows -- one decode step of a layer stack -- is
+/* The decode program: a ggml_graph_compute whose device-runnable nodes are a dependent chain of single-token mul_mats (F32 / F16 /
+ * quantized weights) and their ADD / MUL / SILU / RMS_NORM / SCALE neighbours on single rows -- one decode step of a layer stack -- is
  * enqueued as ONE persistent kernel that walks the dependency levels behind grid-wide barriers while its weight copies run ahead of
  * them (ggb_gemv.cu: k_decode_program).  Same results to the bit as the per-level launches it replaces; everything else (wide
  * levels, prompt-sized nodes, other ops, the row split) takes the per-level route as before.  1 (default): on, 0: per-level launches
