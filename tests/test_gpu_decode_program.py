@@ -19,7 +19,7 @@ def weights(rng, M, K):
     return (rng.standard_normal((M, K)) * (1.0 / np.sqrt(K))).astype(np.float32)
 
 
-def _layers(c, rng, K, F, types, layers, inplace=False):
+def _layers(c, rng, K, F, types, layers, inplace=False, norm_weights=False):
     """The chain of benchmarks/bench_inproc.py's dependent_chain record: per layer rms_norm -> {wq, wk, wv} -> two adds -> wo -> add ->
     rms_norm -> {w1, w3} -> silu, mul -> w2 -> add.  Returns the graph, every node's tensor and the encoded weights."""
     x = c.tensor_from(N.F32, K, 1, data=rng.standard_normal((1, K)).astype(np.float32))
@@ -34,6 +34,9 @@ def _layers(c, rng, K, F, types, layers, inplace=False):
             enc.append((t, wb, M, Kk))
             wt.append(c.tensor_from(t, Kk, M, data=wb))
         xn = c.op("rms_norm", cur)
+        if norm_weights:                                         # cur = ggml_mul(ggml_repeat(norm, cur), cur), as a Llama layer has it (one token: ggml_repeat returns norm itself)
+            nw = c.tensor_from(N.F32, K, 1, data=rng.uniform(0.5, 1.5, (1, K)).astype(np.float32))
+            xn = c.op("mul", c.op("repeat", nw, xn), xn)
         q, k, v = c.mul_mat(wt[0], xn), c.mul_mat(wt[1], xn), c.mul_mat(wt[2], xn)
         qkv = c.op("add", c.op("add", q, k), v)
         o = c.mul_mat(wt[3], qkv)
@@ -98,7 +101,7 @@ def test_program_equals_the_per_level_path_bit_for_bit(types, K, F):
 
 def test_in_place_ops_and_a_scale_factor():
     def build(c, rng):
-        g, nodes, enc = _layers(c, rng, 256, 768, (N.Q4_0, N.Q4_1), 2, inplace=True)
+        g, nodes, enc = _layers(c, rng, 256, 768, (N.Q4_0, N.Q4_1), 2, inplace=True, norm_weights=True)
         return g, nodes, enc
     (prog, lp, _), (lvl, ll, _) = _both_routes(build, computes=2)
     assert lp <= 3 < ll
